@@ -1,0 +1,163 @@
+/* mgcfd_b200.h -- C ABI of libmgcfd_b200.so: the B200-native (sm_100a, fp64) replacement for the
+ * per-cycle solver loop of MG-CFD (warwick-hpsc/MG-CFD-app-plain).
+ *
+ * The reference has no plugin/FFI layer: its hot path is a set of free C++ functions on raw host arrays,
+ * called only from main()'s V-cycle loop (src/euler3d_cpu_double.cpp:371-694).  This header is the boundary
+ * a maintainer binds instead: one entry point per reference function, same argument meaning, but on
+ * DEVICE-RESIDENT level state owned by an opaque context (passing host arrays per call would make every
+ * kernel PCIe-bound).  Each declaration cites the reference interface it replaces.  INTEGRATION.md shows
+ * the main() a maintainer would write against it.
+ *
+ * Conventions
+ *  - plain C, no torch / C++ types in any signature; every function returns an int status (0 = ok).
+ *  - host arrays use the REFERENCE layout and node order: node arrays AoS double[nel*5] (rho, mx, my, mz,
+ *    rhoE; src/Base/const.h:19-26), edges AoS `edge_neighbour` {long a,b; double x,y,z} (40 B,
+ *    src/Base/definitions.h:83) stored [internal | boundary(-1) | wall(-2)] (src/Base/io.cpp:149-181),
+ *    coords AoS double3, MG map long[nel_fine].  The library copies what it is given; callers keep ownership.
+ *  - the library renumbers nodes/edges internally (partition + RCM, colouring); everything it returns
+ *    is un-permuted back to the reference order.
+ *  - not re-entrant per context; one host thread drives one context (as the reference's main() does).
+ *  - there is NO CPU fallback: without a usable CUDA device mgcfd_create fails with MGCFD_ERR_NO_DEVICE.
+ */
+#ifndef MGCFD_B200_H
+#define MGCFD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGCFD_NVAR 5
+#define MGCFD_RK 3
+
+/* status codes */
+#define MGCFD_OK 0
+#define MGCFD_ERR_CUDA 1              /* a CUDA runtime call failed; see mgcfd_last_error() */
+#define MGCFD_ERR_ARG 2               /* bad argument / call order */
+#define MGCFD_ERR_INVALID_VARIABLES 3 /* NaN/Inf/negative density or energy (validation.cpp:107-138) */
+#define MGCFD_ERR_NO_DEVICE 4
+#define MGCFD_ERR_IO 5
+#define MGCFD_ERR_COMM 6
+
+/* mesh variants: values of the reference's MESH_* (src/Base/const.h:38-41) */
+#define MGCFD_MESH_FVCORR 0
+#define MGCFD_MESH_M6_WING 2
+#define MGCFD_MESH_LA_CASCADE 3
+#define MGCFD_MESH_ROTOR_37 4
+
+/* device fields addressable by mgcfd_get_field / mgcfd_set_field */
+#define MGCFD_FIELD_VARIABLES 0
+#define MGCFD_FIELD_OLD_VARIABLES 1
+#define MGCFD_FIELD_RESIDUALS 2
+#define MGCFD_FIELD_FLUXES 3
+#define MGCFD_FIELD_STEP_FACTORS 4 /* 1 double per node */
+#define MGCFD_FIELD_VOLUMES 5      /* 1 double per node, read-only */
+
+/* how the flux scatter is made race-free */
+#define MGCFD_FLUX_TILED_COLOURED 0 /* default: node tiles staged in shared memory, conflict-free edge colouring, no atomics, deterministic */
+#define MGCFD_FLUX_SORTED_SEGMENT 1 /* deterministic CSR-by-node gather (every edge evaluated from both ends), no scatter at all */
+#define MGCFD_FLUX_ATOMIC 2         /* one thread per edge, fp64 atomics (baseline; the ordering-sweep kernel) */
+
+/* node renumbering applied at upload */
+#define MGCFD_ORDER_AS_GIVEN 0
+#define MGCFD_ORDER_RCM 1
+#define MGCFD_ORDER_PARTITION_RCM 2 /* default: recursive bisection into tiles, RCM inside each tile */
+
+typedef struct mgcfd_ctx mgcfd_ctx;
+
+typedef struct mgcfd_options {
+    int device;     /* CUDA device ordinal (default 0) */
+    int flux_mode;  /* MGCFD_FLUX_* */
+    int ordering;   /* MGCFD_ORDER_* */
+    int tile_nodes; /* owned nodes per tile = threads per CTA of the tiled kernel; 0 = default (256) */
+    int use_graph;  /* run_cycles replays one captured CUDA graph per V-cycle (default 1) */
+    int timing;     /* record CUDA-event times per kernel per level (forces use_graph=0) */
+    int reserved[10];
+} mgcfd_options;
+
+void mgcfd_default_options(mgcfd_options* opt);
+const char* mgcfd_last_error(void);
+const char* mgcfd_version(void);
+
+/* ---- lifetime --------------------------------------------------------------------------------- */
+/* replaces the per-level array set-up in main() (euler3d_cpu_double.cpp:138-243) */
+int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_ctx** out);
+int mgcfd_destroy(mgcfd_ctx* ctx);
+
+/* globals ff_variable[5] and ff_flux_contribution_{momentum_x,momentum_y,momentum_z,density_energy}
+ * (src/Base/globals.h:10-14) made explicit; ffc = 4 x double3 in that order. */
+int mgcfd_set_farfield(mgcfd_ctx* ctx, const double ff_variable[5], const double ff_flux_contribution[12]);
+/* host evaluation of initialize_far_field_conditions (src/Kernels/cfd_loops.h:85-119) */
+void mgcfd_far_field_conditions(double ff_variable[5], double ff_flux_contribution[12]);
+
+/* Takes one level exactly as read_grid + read_mg_connectivity leave it (io.cpp:14-199,
+ * io_enhanced.cpp:629-650), AFTER adjust_ewt/dampen_ewt (validation.cpp:28-75) if the mesh variant asks
+ * for them (mgcfd_adjust_dampen_ewt does that on the host).  coords may be NULL iff levels == 1;
+ * mg_map NULL on the coarsest level. */
+int mgcfd_upload_level(mgcfd_ctx* ctx, int level, long nel, const double* volumes, const double* coords_xyz,
+                       long num_internal, long num_boundary, long num_wall, const void* edges_aos40,
+                       const long* mg_map, long mgc);
+/* builds MG operators (needs all levels), allocates node state, zeroes it (euler3d_cpu_double.cpp:234-243) */
+int mgcfd_finalize(mgcfd_ctx* ctx);
+/* adjust_ewt + dampen_ewt in place on a host edge array, by mesh variant (euler3d_cpu_double.cpp:337-352) */
+int mgcfd_adjust_dampen_ewt(int mesh_variant, const double* coords_xyz, long num_edges, void* edges_aos40);
+
+/* ---- one entry point per reference function (granular path) -------------------------------------- */
+int mgcfd_initialize_variables(mgcfd_ctx* ctx, int level);      /* cfd_loops.h:44-55 */
+int mgcfd_copy_old_variables(mgcfd_ctx* ctx, int level);        /* copy<double>(old, variables), common.h:100-112 */
+int mgcfd_compute_step_factor(mgcfd_ctx* ctx, int level, int legacy); /* cfd_loops.cpp:76-157 / :13-73 (legacy) */
+int mgcfd_compute_flux_edge(mgcfd_ctx* ctx, int level);          /* flux_loops.cpp:78-153 */
+int mgcfd_compute_boundary_flux_edge(mgcfd_ctx* ctx, int level); /* flux_loops.cpp:10-42 */
+int mgcfd_compute_wall_flux_edge(mgcfd_ctx* ctx, int level);     /* flux_loops.cpp:44-76 */
+int mgcfd_time_step(mgcfd_ctx* ctx, int level, int rk_stage);    /* cfd_loops.cpp:215-280 */
+int mgcfd_zero_fluxes(mgcfd_ctx* ctx, int level);                /* cfd_loops.cpp:282-305 */
+int mgcfd_indirect_rw(mgcfd_ctx* ctx, int level);                /* indirect_rw_loop.cpp:11-78 (bandwidth probe) */
+int mgcfd_residual(mgcfd_ctx* ctx, int level);                   /* validation.cpp:77-89 */
+/* calc_rms (validation.cpp:91-105) plus the per-variable RMS the north star asks for */
+int mgcfd_calc_rms(mgcfd_ctx* ctx, int level, double* rms_all, double rms_var[5]);
+/* check_for_invalid_variables (validation.cpp:107-138): returns MGCFD_ERR_INVALID_VARIABLES and the first
+ * offending cell (reference node order) + reason (1 NaN/Inf, 2 negative density, 3 negative energy). */
+int mgcfd_check_for_invalid_variables(mgcfd_ctx* ctx, int level, long* first_bad_cell, int* reason);
+/* mg_restrict(variables[l-1] -> variables[l]) (mg_loops.cpp:30-202), l = coarse level */
+int mgcfd_mg_restrict(mgcfd_ctx* ctx, int coarse_level);
+/* prolong_residuals_interpolate_proper(level l+1 -> l) (mg_loops.cpp:678-864), l = fine level */
+int mgcfd_prolong(mgcfd_ctx* ctx, int fine_level);
+
+/* ---- fused fast path ------------------------------------------------------------------------------ */
+/* Runs `ncycles` iterations of main()'s loop (euler3d_cpu_double.cpp:371-694) entirely on the device.
+ * rms_all[c]   = the value main() prints as "(RMS = ...)" for cycle c  (may be NULL)
+ * rms_var[c*5+v] = per-variable residual RMS of level 0               (may be NULL)
+ * Returns MGCFD_ERR_INVALID_VARIABLES if a NaN/negative state appeared (checked once per call). */
+int mgcfd_run_cycles(mgcfd_ctx* ctx, int ncycles, double* rms_all, double* rms_var);
+
+/* ---- host <-> device state, reference layout ------------------------------------------------------ */
+int mgcfd_get_field(mgcfd_ctx* ctx, int level, int field, double* host_out);
+int mgcfd_set_field(mgcfd_ctx* ctx, int level, int field, const double* host_in);
+int mgcfd_synchronize(mgcfd_ctx* ctx);
+
+/* ---- introspection (tests, Times.csv, roofline) --------------------------------------------------- */
+/* info[0..]: nel, nI, nB, nW, padded nodes, tiles, tile_nodes, max colours, slots stored, halo entries, cut edges */
+int mgcfd_level_info(mgcfd_ctx* ctx, int level, long info[16]);
+/* new_of_old[nel]: the node renumbering (a bijection onto [0,padded) minus padding) */
+int mgcfd_get_permutation(mgcfd_ctx* ctx, int level, long* new_of_old);
+/* verifies on the host that no two edges of one colour round of one tile write the same node; returns #conflicts */
+long mgcfd_check_colouring(mgcfd_ctx* ctx, int level);
+/* accumulated CUDA-event milliseconds, reference kernel ids (src/Base/const.h:30-37):
+ * out[kernel*levels + level], kernels = compute_step, flux, update(0), indirect_rw, time_step, restrict, prolong */
+int mgcfd_get_times(mgcfd_ctx* ctx, double* out_ms, long* out_iters);
+int mgcfd_reset_times(mgcfd_ctx* ctx);
+/* launches issued by this context since creation (all kernels are ours) */
+long mgcfd_launch_count(mgcfd_ctx* ctx);
+/* time (ms, CUDA events on the context's stream) of `reps` back-to-back launches of one kernel on `level`:
+ * which = 0 fused flux+update stage, 1 flux only (internal), 2 indirect_rw, 3 atomic flux, 4 sorted-segment flux */
+int mgcfd_time_kernel(mgcfd_ctx* ctx, int level, int which, int reps, double* ms_total);
+
+/* Host-only run of the integer preprocessing (no device needed): renumbering, tiling and colouring of one level.
+ * info[] as mgcfd_level_info; new_of_old may be NULL; *conflicts = result of the colouring validity check. */
+int mgcfd_plan_level(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall,
+                     const void* edges_aos40, int ordering, int tile_nodes, long info[16], long* new_of_old, long* conflicts);
+void mgcfd_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGCFD_B200_H */

@@ -1,0 +1,41 @@
+/* mgcfd_mesh.h -- host-side mesh utilities of libmgcfd_b200.so: the reference's mesh interchange formats
+ * (text mesh + .coords + MG map + input.dat, src/Base/io.cpp:14-199, src/Base/io_enhanced.cpp:407-650; the .bin
+ * cache, io_enhanced.cpp:203-405) and the synthetic generators for the BASELINE.json configs.  A mgcfd_mesh holds
+ * every level exactly as read_grid / read_mg_connectivity would leave it in memory. */
+#ifndef MGCFD_MESH_H
+#define MGCFD_MESH_H
+#include "mgcfd_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgcfd_mesh mgcfd_mesh;
+
+#define MGCFD_GEN_HEX_BOX 0   /* vertex-centred hex dual, 6 neighbours (~3 edges/node: Onera-M6-like density) */
+#define MGCFD_GEN_TET_BOX 1   /* Kuhn tetrahedra, 14 neighbours (7 edges/node) */
+#define MGCFD_GEN_TET_CELLS 2 /* cell-centred tetrahedra, 4 faces per cell (fvcorr.domn.097K-like), single level */
+
+/* dims = levels x 3 node counts (cube counts for TET_CELLS); ordering 0 = lexicographic, 1 = seeded random permutation */
+int mgcfd_mesh_generate(int kind, int levels, const long* dims, const double lengths[3], int mesh_variant, int ordering,
+                        unsigned long seed, double tilt, mgcfd_mesh** out);
+/* read_input_dat + read_grid (+ .coords) + read_mg_connectivity; prefers <layer>.bin when present */
+int mgcfd_mesh_load(const char* input_dat, const char* input_directory, mgcfd_mesh** out);
+/* writes input.dat, one text mesh (+ .coords) per level and the MG maps; binary != 0 additionally writes <layer>.bin */
+int mgcfd_mesh_write(const mgcfd_mesh* m, const char* directory, const char* input_dat_name, int binary);
+int mgcfd_mesh_levels(const mgcfd_mesh* m);
+int mgcfd_mesh_variant(const mgcfd_mesh* m);
+/* out = nel, num_internal, num_boundary, num_wall, mgc */
+int mgcfd_mesh_dims(const mgcfd_mesh* m, int level, long out[5]);
+/* what: 0 volumes (double[nel]), 1 edges (edge_neighbour[nI+nB+nW]), 2 coords (double[3*nel]), 3 mg map (long[mgc]) */
+const void* mgcfd_mesh_ptr(const mgcfd_mesh* m, int level, int what);
+/* adjust_ewt + dampen_ewt on every level, once (euler3d_cpu_double.cpp:337-352) */
+int mgcfd_mesh_apply_ewt(mgcfd_mesh* m);
+/* mgcfd_upload_level for every level (applying the edge-weight adjustment first if not yet done) + mgcfd_finalize */
+int mgcfd_mesh_upload(mgcfd_mesh* m, mgcfd_ctx* ctx);
+void mgcfd_mesh_free(mgcfd_mesh* m);
+const char* mgcfd_mesh_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

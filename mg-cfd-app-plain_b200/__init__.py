@@ -1,0 +1,372 @@
+"""mgcfd_b200 -- host-side Python mirror of the reference's kernel interface for the MG-CFD solver loop.
+
+Thin ctypes bindings over ``libmgcfd_b200.so`` (C ABI in ``include/mgcfd_b200.h`` / ``include/mgcfd_mesh.h``).
+Method names follow the reference's free functions (``src/Kernels/*.h``) so parity tests read like the
+reference's own call sequence in ``main()`` (``src/euler3d_cpu_double.cpp:371-694``).
+
+There is no CPU fallback here: if the CUDA library is missing or no device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmgcfd_b200.so")
+
+NVAR = 5
+RK = 3
+MESH_FVCORR, MESH_M6_WING, MESH_LA_CASCADE, MESH_ROTOR_37 = 0, 2, 3, 4
+FIELD_VARIABLES, FIELD_OLD_VARIABLES, FIELD_RESIDUALS, FIELD_FLUXES, FIELD_STEP_FACTORS, FIELD_VOLUMES = range(6)
+FLUX_TILED_COLOURED, FLUX_SORTED_SEGMENT, FLUX_ATOMIC = 0, 1, 2
+ORDER_AS_GIVEN, ORDER_RCM, ORDER_PARTITION_RCM = 0, 1, 2
+GEN_HEX_BOX, GEN_TET_BOX, GEN_TET_CELLS = 0, 1, 2
+KERNEL_NAMES = ("compute_step", "flux", "update", "indirect_rw", "time_step", "restrict", "prolong")
+
+# layout of the reference's `edge_neighbour` (src/Base/definitions.h:83)
+EDGE_DTYPE = np.dtype([("a", np.int64), ("b", np.int64), ("x", np.float64), ("y", np.float64), ("z", np.float64)])
+assert EDGE_DTYPE.itemsize == 40
+
+
+class MgcfdError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mgcfd error {code}: {msg}")
+        self.code = code
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int), ("flux_mode", C.c_int), ("ordering", C.c_int), ("tile_nodes", C.c_int),
+                ("use_graph", C.c_int), ("timing", C.c_int), ("reserved", C.c_int * 10)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). mgcfd_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, l, dp = C.c_void_p, C.c_int, C.c_long, C.POINTER(C.c_double)
+    L.mgcfd_last_error.restype = C.c_char_p
+    L.mgcfd_mesh_last_error.restype = C.c_char_p
+    L.mgcfd_version.restype = C.c_char_p
+    L.mgcfd_default_options.argtypes = [C.POINTER(Options)]
+    L.mgcfd_create.argtypes = [i, i, C.POINTER(Options), C.POINTER(vp)]
+    L.mgcfd_destroy.argtypes = [vp]
+    L.mgcfd_set_farfield.argtypes = [vp, dp, dp]
+    L.mgcfd_far_field_conditions.argtypes = [dp, dp]
+    L.mgcfd_far_field_conditions.restype = None
+    L.mgcfd_upload_level.argtypes = [vp, i, l, vp, vp, l, l, l, vp, vp, l]
+    L.mgcfd_finalize.argtypes = [vp]
+    L.mgcfd_adjust_dampen_ewt.argtypes = [i, vp, l, vp]
+    for name in ("initialize_variables", "copy_old_variables", "compute_flux_edge", "compute_boundary_flux_edge",
+                 "compute_wall_flux_edge", "zero_fluxes", "indirect_rw", "residual", "mg_restrict", "prolong"):
+        getattr(L, "mgcfd_" + name).argtypes = [vp, i]
+    L.mgcfd_compute_step_factor.argtypes = [vp, i, i]
+    L.mgcfd_time_step.argtypes = [vp, i, i]
+    L.mgcfd_calc_rms.argtypes = [vp, i, dp, dp]
+    L.mgcfd_check_for_invalid_variables.argtypes = [vp, i, C.POINTER(l), C.POINTER(i)]
+    L.mgcfd_run_cycles.argtypes = [vp, i, vp, vp]
+    L.mgcfd_get_field.argtypes = [vp, i, i, vp]
+    L.mgcfd_set_field.argtypes = [vp, i, i, vp]
+    L.mgcfd_synchronize.argtypes = [vp]
+    L.mgcfd_level_info.argtypes = [vp, i, C.POINTER(l)]
+    L.mgcfd_get_permutation.argtypes = [vp, i, vp]
+    L.mgcfd_check_colouring.argtypes = [vp, i]
+    L.mgcfd_check_colouring.restype = l
+    L.mgcfd_get_times.argtypes = [vp, vp, vp]
+    L.mgcfd_reset_times.argtypes = [vp]
+    L.mgcfd_launch_count.argtypes = [vp]
+    L.mgcfd_launch_count.restype = l
+    L.mgcfd_time_kernel.argtypes = [vp, i, i, i, dp]
+    L.mgcfd_plan_level.argtypes = [l, vp, l, l, l, vp, i, i, C.POINTER(l), vp, C.POINTER(l)]
+    L.mgcfd_mesh_generate.argtypes = [i, i, vp, dp, i, i, C.c_ulong, C.c_double, C.POINTER(vp)]
+    L.mgcfd_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    L.mgcfd_mesh_write.argtypes = [vp, C.c_char_p, C.c_char_p, i]
+    L.mgcfd_mesh_levels.argtypes = [vp]
+    L.mgcfd_mesh_variant.argtypes = [vp]
+    L.mgcfd_mesh_dims.argtypes = [vp, i, C.POINTER(l)]
+    L.mgcfd_mesh_ptr.argtypes = [vp, i, i]
+    L.mgcfd_mesh_ptr.restype = vp
+    L.mgcfd_mesh_apply_ewt.argtypes = [vp]
+    L.mgcfd_mesh_upload.argtypes = [vp, vp]
+    L.mgcfd_mesh_free.argtypes = [vp]
+    L.mgcfd_mesh_free.restype = None
+    _lib = L
+    return L
+
+
+def _check(rc: int, mesh: bool = False):
+    if rc != 0:
+        L = lib()
+        msg = (L.mgcfd_mesh_last_error() if mesh else L.mgcfd_last_error()).decode()
+        raise MgcfdError(rc, msg)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def far_field_conditions():
+    """initialize_far_field_conditions (src/Kernels/cfd_loops.h:85-119) -> (ff_variable[5], ff_flux_contribution[12])."""
+    ffv, ffc = np.zeros(5), np.zeros(12)
+    lib().mgcfd_far_field_conditions(ffv.ctypes.data_as(C.POINTER(C.c_double)), ffc.ctypes.data_as(C.POINTER(C.c_double)))
+    return ffv, ffc
+
+
+class Mesh:
+    """A multigrid mesh as the reference holds it in memory after read_grid / read_mg_connectivity."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @staticmethod
+    def generate(kind: int, dims: Sequence[Sequence[int]], mesh_variant: int = MESH_M6_WING, lengths=(1.0, 1.0, 1.0),
+                 ordering: int = 0, seed: int = 12345, tilt: float = 0.05) -> "Mesh":
+        d = np.ascontiguousarray(np.asarray(dims, dtype=np.int64).reshape(-1, 3))
+        ln = np.asarray(lengths, dtype=np.float64)
+        h = C.c_void_p()
+        _check(lib().mgcfd_mesh_generate(kind, d.shape[0], _ptr(d), ln.ctypes.data_as(C.POINTER(C.c_double)), mesh_variant,
+                                         ordering, seed, tilt, C.byref(h)), mesh=True)
+        return Mesh(h)
+
+    @staticmethod
+    def load(input_dat: str, directory: str = "") -> "Mesh":
+        h = C.c_void_p()
+        _check(lib().mgcfd_mesh_load(input_dat.encode(), directory.encode(), C.byref(h)), mesh=True)
+        return Mesh(h)
+
+    def write(self, directory: str, input_dat: str = "input.dat", binary: bool = False):
+        _check(lib().mgcfd_mesh_write(self._h, directory.encode(), input_dat.encode(), int(binary)), mesh=True)
+
+    @property
+    def levels(self) -> int:
+        return lib().mgcfd_mesh_levels(self._h)
+
+    @property
+    def mesh_variant(self) -> int:
+        return lib().mgcfd_mesh_variant(self._h)
+
+    def dims(self, level: int):
+        out = (C.c_long * 5)()
+        _check(lib().mgcfd_mesh_dims(self._h, level, out), mesh=True)
+        return tuple(out)  # nel, nI, nB, nW, mgc
+
+    def _view(self, level, what, dtype, count):
+        p = lib().mgcfd_mesh_ptr(self._h, level, what)
+        if not p or count == 0:
+            return None
+        buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=dtype, count=count)
+
+    def volumes(self, level):
+        return self._view(level, 0, np.float64, self.dims(level)[0])
+
+    def edges(self, level):
+        nel, nI, nB, nW, _ = self.dims(level)
+        return self._view(level, 1, EDGE_DTYPE, nI + nB + nW)
+
+    def coords(self, level):
+        v = self._view(level, 2, np.float64, 3 * self.dims(level)[0])
+        return None if v is None else v.reshape(-1, 3)
+
+    def mg_map(self, level):
+        return self._view(level, 3, np.int64, self.dims(level)[4])
+
+    def apply_ewt(self):
+        """adjust_ewt + dampen_ewt (src/Kernels/validation.cpp:28-75) as main() applies them per mesh variant."""
+        _check(lib().mgcfd_mesh_apply_ewt(self._h), mesh=True)
+
+    def close(self):
+        if self._h:
+            lib().mgcfd_mesh_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Solver:
+    """Device-resident multigrid state + the reference's kernel functions, one method per function."""
+
+    def __init__(self, levels: int, mesh_variant: int, device: int = 0, flux_mode: int = FLUX_TILED_COLOURED,
+                 ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 256, use_graph: bool = True, timing: bool = False):
+        L = lib()
+        opt = Options()
+        L.mgcfd_default_options(C.byref(opt))
+        opt.device, opt.flux_mode, opt.ordering, opt.tile_nodes = device, flux_mode, ordering, tile_nodes
+        opt.use_graph, opt.timing = int(use_graph), int(timing)
+        self._h = C.c_void_p()
+        self.levels, self.mesh_variant = levels, mesh_variant
+        _check(L.mgcfd_create(levels, mesh_variant, C.byref(opt), C.byref(self._h)))
+        self._nel = {}
+
+    @classmethod
+    def from_mesh(cls, mesh: Mesh, **kw) -> "Solver":
+        s = cls(mesh.levels, mesh.mesh_variant, **kw)
+        _check(lib().mgcfd_mesh_upload(mesh._h, s._h), mesh=True)
+        for l in range(mesh.levels):
+            s._nel[l] = mesh.dims(l)[0]
+        return s
+
+    def upload_level(self, level, volumes, coords, nI, nB, nW, edges, mg_map=None):
+        volumes = np.ascontiguousarray(volumes, dtype=np.float64)
+        coords = None if coords is None else np.ascontiguousarray(coords, dtype=np.float64)
+        edges = np.ascontiguousarray(edges)
+        assert edges.dtype.itemsize == 40
+        mg = None if mg_map is None else np.ascontiguousarray(mg_map, dtype=np.int64)
+        self._nel[level] = volumes.shape[0]
+        _check(lib().mgcfd_upload_level(self._h, level, volumes.shape[0], _ptr(volumes), _ptr(coords), nI, nB, nW, _ptr(edges),
+                                        _ptr(mg), 0 if mg is None else mg.shape[0]))
+
+    def finalize(self):
+        _check(lib().mgcfd_finalize(self._h))
+
+    # ---- one method per reference function ----
+    def initialize_variables(self, level): _check(lib().mgcfd_initialize_variables(self._h, level))
+    def copy_old_variables(self, level): _check(lib().mgcfd_copy_old_variables(self._h, level))
+    def compute_step_factor(self, level, legacy=False): _check(lib().mgcfd_compute_step_factor(self._h, level, int(legacy)))
+    def compute_flux_edge(self, level): _check(lib().mgcfd_compute_flux_edge(self._h, level))
+    def compute_boundary_flux_edge(self, level): _check(lib().mgcfd_compute_boundary_flux_edge(self._h, level))
+    def compute_wall_flux_edge(self, level): _check(lib().mgcfd_compute_wall_flux_edge(self._h, level))
+    def time_step(self, level, j): _check(lib().mgcfd_time_step(self._h, level, j))
+    def zero_fluxes(self, level): _check(lib().mgcfd_zero_fluxes(self._h, level))
+    def indirect_rw(self, level): _check(lib().mgcfd_indirect_rw(self._h, level))
+    def residual(self, level): _check(lib().mgcfd_residual(self._h, level))
+    def mg_restrict(self, coarse_level): _check(lib().mgcfd_mg_restrict(self._h, coarse_level))
+    def prolong(self, fine_level): _check(lib().mgcfd_prolong(self._h, fine_level))
+
+    def calc_rms(self, level):
+        a, v = C.c_double(), np.zeros(5)
+        _check(lib().mgcfd_calc_rms(self._h, level, C.byref(a), v.ctypes.data_as(C.POINTER(C.c_double))))
+        return a.value, v
+
+    def check_for_invalid_variables(self, level):
+        """Returns None when the state is valid, else (cell, reason) like validation.cpp:107-138 would report."""
+        cell, reason = C.c_long(-1), C.c_int(0)
+        rc = lib().mgcfd_check_for_invalid_variables(self._h, level, C.byref(cell), C.byref(reason))
+        if rc == 3:
+            return cell.value, reason.value
+        _check(rc)
+        return None
+
+    def run_cycles(self, ncycles: int):
+        """The fused device loop; returns (rms_all[ncycles], rms_var[ncycles, 5])."""
+        ra, rv = np.zeros(ncycles), np.zeros((ncycles, 5))
+        _check(lib().mgcfd_run_cycles(self._h, ncycles, _ptr(ra), _ptr(rv)))
+        return ra, rv
+
+    def get_field(self, level, field, out: Optional[np.ndarray] = None):
+        n = self._nel[level]
+        ncomp = 1 if field in (FIELD_STEP_FACTORS, FIELD_VOLUMES) else NVAR
+        if out is None:
+            out = np.empty(n * ncomp)
+        _check(lib().mgcfd_get_field(self._h, level, field, _ptr(out)))
+        return out.reshape(n, ncomp) if ncomp > 1 else out
+
+    def set_field(self, level, field, values):
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        _check(lib().mgcfd_set_field(self._h, level, field, _ptr(values)))
+
+    def synchronize(self): _check(lib().mgcfd_synchronize(self._h))
+
+    def level_info(self, level):
+        out = (C.c_long * 16)()
+        _check(lib().mgcfd_level_info(self._h, level, out))
+        keys = ("nel", "nI", "nB", "nW", "npad", "ntiles", "tile_nodes", "max_rounds", "slots", "halo_entries", "cut_edges",
+                "used_slots", "max_halo", "bslots", "smem_bytes")
+        return dict(zip(keys, out))
+
+    def permutation(self, level):
+        p = np.empty(self._nel[level], dtype=np.int64)
+        _check(lib().mgcfd_get_permutation(self._h, level, _ptr(p)))
+        return p
+
+    def check_colouring(self, level) -> int:
+        return lib().mgcfd_check_colouring(self._h, level)
+
+    def times(self):
+        ms = np.zeros((len(KERNEL_NAMES), self.levels))
+        it = np.zeros((len(KERNEL_NAMES), self.levels), dtype=np.int64)
+        _check(lib().mgcfd_get_times(self._h, _ptr(ms), _ptr(it)))
+        return ms, it
+
+    def reset_times(self): _check(lib().mgcfd_reset_times(self._h))
+
+    def launch_count(self) -> int:
+        return lib().mgcfd_launch_count(self._h)
+
+    def time_kernel(self, level, which, reps) -> float:
+        ms = C.c_double()
+        _check(lib().mgcfd_time_kernel(self._h, level, which, reps, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().mgcfd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+INFO_KEYS = ("nel", "nI", "nB", "nW", "npad", "ntiles", "tile_nodes", "max_rounds", "slots", "halo_entries", "cut_edges",
+             "used_slots", "max_halo", "bslots", "smem_bytes")
+
+
+def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 256):
+    """Host-only integer preprocessing of one level: returns (info dict, new_of_old permutation, colouring conflicts)."""
+    nel, nI, nB, nW, _ = mesh.dims(level)
+    info = (C.c_long * 16)()
+    perm = np.empty(nel, dtype=np.int64)
+    conflicts = C.c_long(-1)
+    c = mesh.coords(level)
+    _check(lib().mgcfd_plan_level(nel, _ptr(c), nI, nB, nW, _ptr(mesh.edges(level)), ordering, tile_nodes, info, _ptr(perm),
+                                  C.byref(conflicts)))
+    return dict(zip(INFO_KEYS, info)), perm, conflicts.value
+
+
+def smooth_granular(s: Solver, level: int, legacy: bool):
+    """One smoothing visit through the per-function API, call for call as main() (euler3d_cpu_double.cpp:383-512)."""
+    s.copy_old_variables(level)
+    s.compute_step_factor(level, legacy)
+    for j in range(RK):
+        s.compute_flux_edge(level)
+        s.compute_boundary_flux_edge(level)
+        s.compute_wall_flux_edge(level)
+        s.time_step(level, j)
+    s.residual(level)
+
+
+def run_cycles_granular(s: Solver, cycles: int):
+    """main()'s V-cycle loop (euler3d_cpu_double.cpp:371-694) through the per-function API."""
+    legacy = s.mesh_variant == MESH_FVCORR
+    rms_all, rms_var = [], []
+    nl = s.levels
+    for _ in range(cycles):
+        smooth_granular(s, 0, legacy)
+        a, v = s.calc_rms(0)
+        rms_all.append(a)
+        rms_var.append(v)
+        for l in range(1, nl):
+            s.mg_restrict(l)
+            smooth_granular(s, l, legacy)
+        for l in range(nl - 2, -1, -1):
+            s.prolong(l)
+            if l > 0:
+                smooth_granular(s, l, legacy)
+    return np.array(rms_all), np.array(rms_var)

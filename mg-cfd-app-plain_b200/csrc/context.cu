@@ -1,0 +1,792 @@
+// context.cu -- device-resident level state, kernel launch sequencing (granular + fused/graph paths) and the
+// extern "C" boundary declared in include/mgcfd_b200.h.  No CPU fallback: every compute entry point launches
+// CUDA kernels; without a device mgcfd_create fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/mgcfd_b200.h"
+#include "host_mesh.h"
+#include "kernels.cuh"
+#include "plan.h"
+
+using namespace mgcfd;
+
+namespace {
+
+thread_local std::string g_err;
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"; \
+            return MGCFD_ERR_CUDA;                                                                       \
+        }                                                                                                \
+    } while (0)
+#define CKRC(call) do { int rc_ = (call); if (rc_ != MGCFD_OK) return rc_; } while (0)
+
+template <class T>
+int dev_upload(T** dptr, const std::vector<T>& h, cudaStream_t s) {
+    *dptr = nullptr;
+    const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+    CK(cudaMalloc((void**)dptr, bytes));
+    if (!h.empty()) CK(cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+    return MGCFD_OK;
+}
+
+enum KernelId { K_STEP = 0, K_FLUX = 1, K_UPDATE = 2, K_INDIRECT = 3, K_TIME = 4, K_RESTRICT = 5, K_PROLONG = 6, K_COUNT = 7 };
+
+struct Level {
+    HostLevel host;            // kept until finalize (transfer operators need mg + coords of both levels)
+    LevelPlan plan;
+    bool uploaded = false;
+    long nel = 0, npad = 0, ntiles = 0, nI = 0, nB = 0, nW = 0;
+    int TN = 256, smem_nodes = 0;
+    size_t smem_bytes = 0;
+    double* buf[3] = {nullptr, nullptr, nullptr};
+    int i_var = 0, i_old = 1, i_tmp = 2;
+    double *res = nullptr, *flux = nullptr, *sf = nullptr, *vol = nullptr, *vol_root = nullptr;
+    int *new_of_old = nullptr, *old_of_new = nullptr;
+    long* halo_off = nullptr; int* halo_ids = nullptr;
+    long* slot_off = nullptr; int* tile_rounds = nullptr; uint16_t* slot_other = nullptr; double* slot_w = nullptr; long nslots = 0;
+    long* bslot_off = nullptr; int* tile_brounds = nullptr; uint8_t* bslot_kind = nullptr; double* bslot_w = nullptr; long nbslots = 0;
+    // flat + CSR (lazy)
+    int *ea = nullptr, *eb = nullptr; double* ew = nullptr;
+    int* bnode = nullptr; uint8_t* bkind = nullptr; double* bw = nullptr;
+    long* adj_off = nullptr; int* adj_nbr = nullptr; double* adj_w = nullptr;
+    bool flat_up = false, csr_up = false;
+    // transfers (operators between this level and the next coarser one)
+    long* child_off = nullptr; int* child_ids = nullptr;       // stored on the COARSE level (children in level-1)
+    int* parent = nullptr; double* idist_own = nullptr; long* ent_off = nullptr; int* ent_src = nullptr; double* ent_w = nullptr;
+    double* rms_partial = nullptr; long rms_parts = 0;
+    double* io = nullptr;      // AoS staging for get/set_field
+    double* V(int i) const { return buf[i]; }
+};
+
+}  // namespace
+
+struct mgcfd_ctx {
+    mgcfd_options opt;
+    int levels = 0, variant = 2;
+    bool finalized = false;
+    std::vector<Level> L;
+    cudaStream_t stream = nullptr;
+    double ff[5], ffc[12];
+    bool have_ff = false;
+    unsigned long long* d_minbits = nullptr;
+    unsigned long long* d_badkey = nullptr;
+    double* d_rms = nullptr;       // [cap][6]
+    int* d_rms_counter = nullptr;
+    int rms_cap = 0;
+    long launches = 0;
+    std::map<std::string, cudaGraphExec_t> graphs;
+    // timing
+    std::vector<double> t_ms;      // [K_COUNT][levels]
+    std::vector<long> t_iters;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool capturing = false;
+    unsigned long long stage_seq = 0;
+    double kdiss;
+};
+
+namespace {
+
+inline long blocks_for(long n, int bs) { return (n + bs - 1) / bs; }
+
+struct Timed {
+    mgcfd_ctx* c; int kid, lev; long iters; bool on;
+    Timed(mgcfd_ctx* c_, int kid_, int lev_, long iters_) : c(c_), kid(kid_), lev(lev_), iters(iters_) {
+        on = c->opt.timing && !c->capturing;
+        if (on) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~Timed() {
+        if (!on) return;
+        cudaEventRecord(c->ev1, c->stream);
+        cudaEventSynchronize(c->ev1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->t_ms[kid * c->levels + lev] += ms;
+        c->t_iters[kid * c->levels + lev] += iters;
+    }
+};
+
+int post_launch(mgcfd_ctx* c) {
+    c->launches++;
+    CK(cudaGetLastError());
+    return MGCFD_OK;
+}
+
+template <int TN, bool FUSED>
+int launch_tile_t(mgcfd_ctx* c, Level& v, const TileArgs& a) {
+    static bool attr_set = false;
+    static size_t attr_bytes = 0;
+    if (!attr_set || v.smem_bytes > attr_bytes) {
+        CK(cudaFuncSetAttribute(k_tile_flux<TN, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem_bytes));
+        attr_set = true; attr_bytes = v.smem_bytes;
+    }
+    k_tile_flux<TN, FUSED><<<(unsigned)v.ntiles, TN, v.smem_bytes, c->stream>>>(a);
+    return post_launch(c);
+}
+
+int launch_tile(mgcfd_ctx* c, Level& v, const TileArgs& a, bool fused) {
+    if (v.TN == 256) return fused ? launch_tile_t<256, true>(c, v, a) : launch_tile_t<256, false>(c, v, a);
+    if (v.TN == 128) return fused ? launch_tile_t<128, true>(c, v, a) : launch_tile_t<128, false>(c, v, a);
+    if (v.TN == 512) return fused ? launch_tile_t<512, true>(c, v, a) : launch_tile_t<512, false>(c, v, a);
+    g_err = "tile_nodes must be 128, 256 or 512";
+    return MGCFD_ERR_ARG;
+}
+
+TileArgs base_args(mgcfd_ctx* c, Level& v) {
+    TileArgs a;
+    memset(&a, 0, sizeof(a));
+    a.stride = v.npad;
+    a.halo_off = v.halo_off; a.halo_ids = v.halo_ids;
+    a.slot_off = v.slot_off; a.tile_rounds = v.tile_rounds; a.slot_other = v.slot_other; a.slot_w = v.slot_w; a.nslots = v.nslots;
+    a.bslot_off = v.bslot_off; a.tile_brounds = v.tile_brounds; a.bslot_kind = v.bslot_kind; a.bslot_w = v.bslot_w; a.nbslots = v.nbslots;
+    a.kdiss = c->kdiss;
+    a.old_of_new = v.old_of_new;
+    a.smem_nodes = v.smem_nodes;
+    a.sf = v.sf;
+    return a;
+}
+
+int ensure_flux(mgcfd_ctx* c, Level& v) {
+    if (v.flux) return MGCFD_OK;
+    CK(cudaMalloc((void**)&v.flux, sizeof(double) * 5 * v.npad));
+    CK(cudaMemsetAsync(v.flux, 0, sizeof(double) * 5 * v.npad, c->stream));
+    return MGCFD_OK;
+}
+int ensure_flat(mgcfd_ctx* c, Level& v) {
+    if (v.flat_up) return MGCFD_OK;
+    CKRC(dev_upload(&v.ea, v.plan.ea, c->stream)); CKRC(dev_upload(&v.eb, v.plan.eb, c->stream)); CKRC(dev_upload(&v.ew, v.plan.ew, c->stream));
+    CKRC(dev_upload(&v.bnode, v.plan.bnode, c->stream)); CKRC(dev_upload(&v.bkind, v.plan.bkind, c->stream)); CKRC(dev_upload(&v.bw, v.plan.bw, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    v.flat_up = true;
+    return MGCFD_OK;
+}
+int ensure_csr(mgcfd_ctx* c, Level& v) {
+    if (v.csr_up) return MGCFD_OK;
+    CKRC(dev_upload(&v.adj_off, v.plan.adj_off, c->stream)); CKRC(dev_upload(&v.adj_nbr, v.plan.adj_nbr, c->stream));
+    CKRC(dev_upload(&v.adj_w, v.plan.adj_w, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    v.csr_up = true;
+    return MGCFD_OK;
+}
+
+// flux into v.flux (+=) for the edge classes in mask, honouring the configured flux mode
+int flux_granular(mgcfd_ctx* c, int l, int mask) {
+    Level& v = c->L[l];
+    CKRC(ensure_flux(c, v));
+    const int mode = c->opt.flux_mode;
+    if (mode == MGCFD_FLUX_TILED_COLOURED) {
+        TileArgs a = base_args(c, v);
+        a.vin = v.V(v.i_var); a.vout = v.flux; a.mask = mask;
+        return launch_tile(c, v, a, false);
+    }
+    if (mask & 1) {
+        if (mode == MGCFD_FLUX_ATOMIC) {
+            CKRC(ensure_flat(c, v));
+            if (v.nI) { k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, c->kdiss); CKRC(post_launch(c)); }
+        } else {
+            CKRC(ensure_csr(c, v));
+            k_flux_segment<<<(unsigned)blocks_for(v.npad, 128), 128, 0, c->stream>>>(v.npad, v.adj_off, v.adj_nbr, v.adj_w, 2 * v.nI, v.V(v.i_var), v.npad, v.flux, c->kdiss);
+            CKRC(post_launch(c));
+        }
+    }
+    if ((mask & 6) && (v.nB + v.nW)) {
+        CKRC(ensure_flat(c, v));
+        k_bflux_atomic<<<(unsigned)blocks_for(v.nB + v.nW, 256), 256, 0, c->stream>>>(v.nB + v.nW, v.bnode, v.bkind, v.bw, v.V(v.i_var), v.npad, v.flux, mask);
+        CKRC(post_launch(c));
+    }
+    return MGCFD_OK;
+}
+
+int step_factor(mgcfd_ctx* c, int l, int legacy) {
+    Level& v = c->L[l];
+    Timed tm(c, K_STEP, l, v.nel);
+    const unsigned nb = (unsigned)blocks_for(v.npad, 256);
+    if (legacy) {
+        k_step_factor<true><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.vol_root, v.sf, c->d_minbits);
+        CKRC(post_launch(c));
+    } else {
+        CK(cudaMemsetAsync(c->d_minbits, 0x7F, sizeof(unsigned long long), c->stream));
+        k_step_factor<false><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.vol_root, v.sf, c->d_minbits);
+        CKRC(post_launch(c));
+        k_apply_min_dt<<<nb, 256, 0, c->stream>>>(c->d_minbits, v.vol, v.sf, v.npad);
+        CKRC(post_launch(c));
+    }
+    return MGCFD_OK;
+}
+
+int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
+    k_rms_final<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel, use_counter ? c->d_rms : c->d_rms + 6 * (c->rms_cap - 1),
+                                          use_counter ? c->d_rms_counter : nullptr, c->rms_cap - 1);
+    return post_launch(c);
+}
+
+// one smoothing visit (euler3d_cpu_double.cpp:383-512) on the fused path
+int smooth_fused(mgcfd_ctx* c, int l) {
+    Level& v = c->L[l];
+    CKRC(step_factor(c, l, c->variant == MGCFD_MESH_FVCORR));
+    const int X = v.i_var, A = v.i_tmp, B = v.i_old;   // the previous old_variables are dead once a smooth starts
+    for (int j = 0; j < MGCFD_RK; j++) {
+        Timed tm(c, K_FLUX, l, v.nI);
+        TileArgs a = base_args(c, v);
+        a.vold = v.V(X);
+        a.vin = (j == 0) ? v.V(X) : (j == 1 ? v.V(A) : v.V(B));
+        a.vout = (j == 1) ? v.V(B) : v.V(A);
+        a.rk_div = double(MGCFD_RK + 1 - j);
+        a.mask = 7;
+        a.bad_key = c->d_badkey;
+        a.stage_seq = (c->stage_seq++) & 0xFFFFFFull;
+        if (j == MGCFD_RK - 1) {
+            a.res = v.res;
+            a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
+        }
+        CKRC(launch_tile(c, v, a, true));
+    }
+    v.i_old = X; v.i_var = A; v.i_tmp = B;
+    if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
+    return MGCFD_OK;
+}
+
+int do_restrict(mgcfd_ctx* c, int lc) {
+    Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
+    Timed tm(c, K_RESTRICT, lc, vf.nel);
+    k_restrict<<<(unsigned)blocks_for(vc.npad, 128), 128, 0, c->stream>>>(vf.V(vf.i_var), vf.npad, vc.V(vc.i_var), vc.npad, vc.npad, vc.child_off, vc.child_ids);
+    return post_launch(c);
+}
+int do_prolong(mgcfd_ctx* c, int lf) {
+    Level& vf = c->L[lf]; Level& vc = c->L[lf + 1];
+    Timed tm(c, K_PROLONG, lf, vf.nI);
+    k_prolong<<<(unsigned)blocks_for(vf.npad, 128), 128, 0, c->stream>>>(vf.npad, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
+                                                                       vc.res, vf.res, vf.V(vf.i_var));
+    return post_launch(c);
+}
+
+// one full iteration of main()'s loop body sequence for a V-cycle (euler3d_cpu_double.cpp:371-694)
+int cycle_fused(mgcfd_ctx* c) {
+    const int nl = c->levels;
+    CKRC(smooth_fused(c, 0));
+    if (nl == 1) return MGCFD_OK;
+    for (int l = 1; l < nl; l++) { CKRC(do_restrict(c, l)); CKRC(smooth_fused(c, l)); }
+    for (int l = nl - 2; l >= 1; l--) { CKRC(do_prolong(c, l)); CKRC(smooth_fused(c, l)); }
+    CKRC(do_prolong(c, 0));
+    return MGCFD_OK;
+}
+
+std::string role_key(mgcfd_ctx* c) {
+    std::string k;
+    for (auto& v : c->L) { k += char('0' + v.i_var); k += char('0' + v.i_old); }
+    return k;
+}
+
+int field_ptr(mgcfd_ctx* c, Level& v, int field, double** p, int* ncomp, bool for_write) {
+    *ncomp = 5;
+    switch (field) {
+        case MGCFD_FIELD_VARIABLES: *p = v.V(v.i_var); return MGCFD_OK;
+        case MGCFD_FIELD_OLD_VARIABLES: *p = v.V(v.i_old); return MGCFD_OK;
+        case MGCFD_FIELD_RESIDUALS: *p = v.res; return MGCFD_OK;
+        case MGCFD_FIELD_FLUXES: CKRC(ensure_flux(c, v)); *p = v.flux; return MGCFD_OK;
+        case MGCFD_FIELD_STEP_FACTORS: *p = v.sf; *ncomp = 1; return MGCFD_OK;
+        case MGCFD_FIELD_VOLUMES: if (for_write) break; *p = v.vol; *ncomp = 1; return MGCFD_OK;
+    }
+    g_err = "unknown or read-only field";
+    return MGCFD_ERR_ARG;
+}
+
+int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    if (l < 0 || l >= c->levels) { g_err = "level out of range"; return MGCFD_ERR_ARG; }
+    if (need_final && !c->finalized) { g_err = "mgcfd_finalize has not been called"; return MGCFD_ERR_ARG; }
+    return MGCFD_OK;
+}
+
+void free_level(Level& v) {
+    void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.halo_off, v.halo_ids,
+                    v.slot_off, v.tile_rounds, v.slot_other, v.slot_w, v.bslot_off, v.tile_brounds, v.bslot_kind, v.bslot_w, v.ea, v.eb, v.ew,
+                    v.bnode, v.bkind, v.bw, v.adj_off, v.adj_nbr, v.adj_w, v.child_off, v.child_ids, v.parent, v.idist_own, v.ent_off, v.ent_src,
+                    v.ent_w, v.rms_partial, v.io};
+    for (void* p : ptrs) if (p) cudaFree(p);
+}
+
+}  // namespace
+
+extern "C" {
+
+void mgcfd_default_options(mgcfd_options* opt) {
+    memset(opt, 0, sizeof(*opt));
+    opt->device = 0;
+    opt->flux_mode = MGCFD_FLUX_TILED_COLOURED;
+    opt->ordering = MGCFD_ORDER_PARTITION_RCM;
+    opt->tile_nodes = 256;
+    opt->use_graph = 1;
+    opt->timing = 0;
+}
+const char* mgcfd_last_error(void) { return g_err.c_str(); }
+const char* mgcfd_version(void) { return "mgcfd-b200 0.1 (sm_100a, fp64)"; }
+
+void mgcfd_far_field_conditions(double ffv[5], double ffc[12]) {
+    // initialize_far_field_conditions (src/Kernels/cfd_loops.h:85-119), same expressions in the same order
+    const double gamma = 1.4, ff_mach = 1.2, deg_aoa = 0.0;
+    const double angle_of_attack = double(3.1415926535897931 / 180.0) * double(deg_aoa);
+    ffv[0] = double(1.4);
+    const double ff_pressure = double(1.0);
+    const double ff_speed_of_sound = sqrt(gamma * ff_pressure / ffv[0]);
+    const double ff_speed = double(ff_mach) * ff_speed_of_sound;
+    const double vel[3] = {ff_speed * double(cos(angle_of_attack)), ff_speed * double(sin(angle_of_attack)), 0.0};
+    ffv[1] = ffv[0] * vel[0]; ffv[2] = ffv[0] * vel[1]; ffv[3] = ffv[0] * vel[2];
+    ffv[4] = ffv[0] * (double(0.5) * (ff_speed * ff_speed)) + (ff_pressure / double(gamma - 1.0));
+    const double mom[3] = {ffv[1], ffv[2], ffv[3]};
+    // compute_flux_contribution (cfd_loops.h:57-83)
+    ffc[0] = vel[0] * mom[0] + ff_pressure; ffc[1] = vel[0] * mom[1]; ffc[2] = vel[0] * mom[2];
+    ffc[3] = ffc[1]; ffc[4] = vel[1] * mom[1] + ff_pressure; ffc[5] = vel[1] * mom[2];
+    ffc[6] = ffc[2]; ffc[7] = ffc[5]; ffc[8] = vel[2] * mom[2] + ff_pressure;
+    const double de_p = ffv[4] + ff_pressure;
+    ffc[9] = vel[0] * de_p; ffc[10] = vel[1] * de_p; ffc[11] = vel[2] * de_p;
+}
+
+int mgcfd_adjust_dampen_ewt(int mesh_variant, const double* coords_xyz, long num_edges, void* edges_aos40) {
+    if (!edges_aos40 || (mesh_variant != MGCFD_MESH_FVCORR && !coords_xyz)) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    apply_ewt(mesh_variant, coords_xyz, num_edges, (EdgeNb*)edges_aos40);
+    return MGCFD_OK;
+}
+
+int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_ctx** out) {
+    if (!out || levels < 1 || levels > 8) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    *out = nullptr;
+    mgcfd_options o;
+    if (opt) o = *opt; else mgcfd_default_options(&o);
+    if (o.tile_nodes == 0) o.tile_nodes = 256;
+    if (o.tile_nodes != 128 && o.tile_nodes != 256 && o.tile_nodes != 512) { g_err = "tile_nodes must be 128, 256 or 512"; return MGCFD_ERR_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || o.device >= ndev) {
+        g_err = std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); libmgcfd_b200 has no CPU fallback";
+        return MGCFD_ERR_NO_DEVICE;
+    }
+    CK(cudaSetDevice(o.device));
+    mgcfd_ctx* c = new mgcfd_ctx();
+    c->opt = o; c->levels = levels; c->variant = mesh_variant;
+    c->L.resize(levels);
+    c->kdiss = -0.5 * double(0.2f);
+    c->t_ms.assign(K_COUNT * levels, 0.0);
+    c->t_iters.assign(K_COUNT * levels, 0);
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
+    CK(cudaMalloc((void**)&c->d_minbits, 8)); CK(cudaMalloc((void**)&c->d_badkey, 8));
+    CK(cudaMemset(c->d_badkey, 0xFF, 8));
+    c->rms_cap = 4096 + 1;
+    CK(cudaMalloc((void**)&c->d_rms, sizeof(double) * 6 * c->rms_cap));
+    CK(cudaMalloc((void**)&c->d_rms_counter, sizeof(int)));
+    CK(cudaMemset(c->d_rms_counter, 0, sizeof(int)));
+    mgcfd_far_field_conditions(c->ff, c->ffc);
+    CK(cudaMemcpyToSymbol(c_ff, c->ff, sizeof(c->ff)));
+    CK(cudaMemcpyToSymbol(c_ffc, c->ffc, sizeof(c->ffc)));
+    *out = c;
+    return MGCFD_OK;
+}
+
+int mgcfd_destroy(mgcfd_ctx* c) {
+    if (!c) return MGCFD_OK;
+    cudaSetDevice(c->opt.device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    for (auto& v : c->L) free_level(v);
+    cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_rms); cudaFree(c->d_rms_counter);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return MGCFD_OK;
+}
+
+int mgcfd_set_farfield(mgcfd_ctx* c, const double ffv[5], const double ffc[12]) {
+    if (!c || !ffv || !ffc) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    memcpy(c->ff, ffv, sizeof(c->ff)); memcpy(c->ffc, ffc, sizeof(c->ffc));
+    CK(cudaMemcpyToSymbol(c_ff, c->ff, sizeof(c->ff)));
+    CK(cudaMemcpyToSymbol(c_ffc, c->ffc, sizeof(c->ffc)));
+    return MGCFD_OK;
+}
+
+int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, const double* coords, long nI, long nB, long nW,
+                       const void* edges, const long* mg_map, long mgc) {
+    CKRC(check_level(c, l, false));
+    if (c->finalized) { g_err = "context already finalized"; return MGCFD_ERR_ARG; }
+    if (nel <= 0 || !volumes || !edges || nI < 0 || nB < 0 || nW < 0) { g_err = "bad mesh arguments"; return MGCFD_ERR_ARG; }
+    if (c->levels > 1 && !coords) { g_err = "coords are required when levels > 1"; return MGCFD_ERR_ARG; }
+    if (l < c->levels - 1 && (!mg_map || mgc != nel)) { g_err = "mg_map of size nel is required on every level but the coarsest"; return MGCFD_ERR_ARG; }
+    Level& v = c->L[l];
+    HostLevel& H = v.host;
+    H.nel = nel; H.nI = nI; H.nB = nB; H.nW = nW;
+    H.volumes.assign(volumes, volumes + nel);
+    const EdgeNb* e = (const EdgeNb*)edges;
+    H.edges.assign(e, e + nI + nB + nW);
+    for (long k = 0; k < nI + nB + nW; k++) {
+        const bool internal = k < nI;
+        if (H.edges[k].b < 0 || H.edges[k].b >= nel || (internal && (H.edges[k].a < 0 || H.edges[k].a >= nel))) {
+            g_err = "edge endpoint out of range"; return MGCFD_ERR_ARG;
+        }
+    }
+    if (coords) H.coords.assign(coords, coords + 3 * nel); else H.coords.clear();
+    if (mg_map && l < c->levels - 1) H.mg.assign(mg_map, mg_map + mgc); else H.mg.clear();
+    PlanOptions po; po.ordering = c->opt.ordering; po.tile_nodes = c->opt.tile_nodes;
+    try { build_level_plan(H, po, v.plan); }
+    catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    v.uploaded = true;
+    return MGCFD_OK;
+}
+
+int mgcfd_finalize(mgcfd_ctx* c) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    if (c->finalized) return MGCFD_OK;
+    for (auto& v : c->L) if (!v.uploaded) { g_err = "not every level has been uploaded"; return MGCFD_ERR_ARG; }
+    CK(cudaSetDevice(c->opt.device));
+    cudaStream_t s = c->stream;
+    for (int l = 0; l < c->levels; l++) {
+        Level& v = c->L[l];
+        LevelPlan& P = v.plan;
+        v.nel = P.nel; v.npad = P.npad; v.ntiles = P.ntiles; v.nI = P.nI; v.nB = P.nB; v.nW = P.nW; v.TN = P.TN;
+        v.smem_nodes = ((P.TN + P.max_halo + 3) / 4) * 4;
+        v.smem_bytes = sizeof(double) * (10 * (size_t)v.smem_nodes + 5 * (size_t)P.TN);
+        if (v.smem_bytes > 227 * 1024) { g_err = "tile halo too large for shared memory; use a smaller tile_nodes or a locality-preserving ordering"; return MGCFD_ERR_ARG; }
+        for (int b = 0; b < 3; b++) CK(cudaMalloc((void**)&v.buf[b], sizeof(double) * 5 * v.npad));
+        CK(cudaMalloc((void**)&v.res, sizeof(double) * 5 * v.npad));
+        CK(cudaMalloc((void**)&v.sf, sizeof(double) * v.npad));
+        // volumes in new order; padding: volume 1, root +inf so that padded nodes never win the min-dt reduction
+        std::vector<double> vol(v.npad, 1.0), root(v.npad, INFINITY);
+        const bool legacy = (c->variant == MGCFD_MESH_FVCORR);
+        for (long i = 0; i < v.nel; i++) {
+            const long g = P.new_of_old[i];
+            vol[g] = v.host.volumes[i];
+            root[g] = legacy ? sqrt(v.host.volumes[i]) : cbrt(v.host.volumes[i]);   // host libm, as the reference (cfd_loops.cpp:60,:123)
+        }
+        if (legacy) for (long g = 0; g < v.npad; g++) if (P.old_of_new[g] < 0) root[g] = 1.0;
+        CKRC(dev_upload(&v.vol, vol, s)); CKRC(dev_upload(&v.vol_root, root, s));
+        std::vector<int> n2o(P.old_of_new.begin(), P.old_of_new.end()), o2n(P.new_of_old.begin(), P.new_of_old.end());
+        CKRC(dev_upload(&v.old_of_new, n2o, s)); CKRC(dev_upload(&v.new_of_old, o2n, s));
+        CKRC(dev_upload(&v.halo_off, P.halo_off, s)); CKRC(dev_upload(&v.halo_ids, P.halo_ids, s));
+        CKRC(dev_upload(&v.slot_off, P.slot_off, s)); CKRC(dev_upload(&v.tile_rounds, P.tile_rounds, s));
+        CKRC(dev_upload(&v.slot_other, P.slot_other, s)); CKRC(dev_upload(&v.slot_w, P.slot_w, s));
+        v.nslots = P.slot_off[P.ntiles];
+        CKRC(dev_upload(&v.bslot_off, P.bslot_off, s)); CKRC(dev_upload(&v.tile_brounds, P.tile_brounds, s));
+        CKRC(dev_upload(&v.bslot_kind, P.bslot_kind, s)); CKRC(dev_upload(&v.bslot_w, P.bslot_w, s));
+        v.nbslots = P.bslot_off[P.ntiles];
+        const long parts = std::max<long>(v.ntiles, blocks_for(v.npad, 256));
+        CK(cudaMalloc((void**)&v.rms_partial, sizeof(double) * 5 * parts));
+        CK(cudaStreamSynchronize(s));
+        // node state: every buffer starts at the far-field state (what initialize_variables leaves, cfd_loops.h:44-55);
+        // padding nodes keep it forever (no edges, zero residual), which keeps them finite in every stage
+        for (int b = 0; b < 3; b++) { k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, s>>>(v.buf[b], v.npad, v.npad); CKRC(post_launch(c)); }
+        CK(cudaMemsetAsync(v.res, 0, sizeof(double) * 5 * v.npad, s));
+        CK(cudaMemsetAsync(v.sf, 0, sizeof(double) * v.npad, s));
+    }
+    // multigrid operators
+    for (int l = 0; l + 1 < c->levels; l++) {
+        Level& vf = c->L[l]; Level& vc = c->L[l + 1];
+        for (long i = 0; i < vf.nel; i++)
+            if (vf.host.mg[i] < 0 || vf.host.mg[i] >= vc.nel) { g_err = "mg_map entry out of range"; return MGCFD_ERR_ARG; }
+        TransferPlan T;
+        build_transfer_plan(vf.host, vc.host, vf.plan, vc.plan, T);
+        CKRC(dev_upload(&vc.child_off, T.child_off, s)); CKRC(dev_upload(&vc.child_ids, T.child_ids, s));
+        CKRC(dev_upload(&vf.parent, T.parent, s)); CKRC(dev_upload(&vf.idist_own, T.idist_own, s));
+        CKRC(dev_upload(&vf.ent_off, T.ent_off, s)); CKRC(dev_upload(&vf.ent_src, T.ent_src, s)); CKRC(dev_upload(&vf.ent_w, T.ent_w, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    CK(cudaStreamSynchronize(s));
+    // host copies are no longer needed, except the plan pieces used lazily (flat/CSR) and by introspection
+    for (auto& v : c->L) {
+        v.host = HostLevel();
+        v.plan.slot_w.clear(); v.plan.slot_w.shrink_to_fit();
+        v.plan.bslot_w.clear(); v.plan.bslot_w.shrink_to_fit();
+    }
+    c->finalized = true;
+    return MGCFD_OK;
+}
+
+// ---- granular path -------------------------------------------------------------------------------------
+int mgcfd_initialize_variables(mgcfd_ctx* c, int l) {
+    CKRC(check_level(c, l));
+    Level& v = c->L[l];
+    k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad);
+    return post_launch(c);
+}
+int mgcfd_copy_old_variables(mgcfd_ctx* c, int l) {
+    CKRC(check_level(c, l));
+    Level& v = c->L[l];
+    k_copy<<<(unsigned)blocks_for(5 * v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_old), v.V(v.i_var), 5 * v.npad);
+    return post_launch(c);
+}
+int mgcfd_compute_step_factor(mgcfd_ctx* c, int l, int legacy) {
+    CKRC(check_level(c, l));
+    return step_factor(c, l, legacy);
+}
+int mgcfd_compute_flux_edge(mgcfd_ctx* c, int l) {
+    CKRC(check_level(c, l));
+    Timed tm(c, K_FLUX, l, c->L[l].nI);
+    return flux_granular(c, l, 1);
+}
+int mgcfd_compute_boundary_flux_edge(mgcfd_ctx* c, int l) { CKRC(check_level(c, l)); return flux_granular(c, l, 2); }
+int mgcfd_compute_wall_flux_edge(mgcfd_ctx* c, int l) { CKRC(check_level(c, l)); return flux_granular(c, l, 4); }
+int mgcfd_time_step(mgcfd_ctx* c, int l, int j) {
+    CKRC(check_level(c, l));
+    if (j < 0 || j >= MGCFD_RK) { g_err = "rk_stage out of range"; return MGCFD_ERR_ARG; }
+    Level& v = c->L[l];
+    CKRC(ensure_flux(c, v));
+    Timed tm(c, K_TIME, l, v.nel);
+    k_time_step<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(double(MGCFD_RK + 1 - j), v.npad, v.npad, v.sf, v.flux, v.V(v.i_old), v.V(v.i_var));
+    return post_launch(c);
+}
+int mgcfd_zero_fluxes(mgcfd_ctx* c, int l) {
+    CKRC(check_level(c, l));
+    Level& v = c->L[l];
+    CKRC(ensure_flux(c, v));
+    k_fill<<<(unsigned)blocks_for(5 * v.npad, 256), 256, 0, c->stream>>>(v.flux, 5 * v.npad, 0.0);
+    return post_launch(c);
+}
+int mgcfd_indirect_rw(mgcfd_ctx* c, int l) {
+    CKRC(check_level(c, l));
+    Level& v = c->L[l];
+    CKRC(ensure_flux(c, v)); CKRC(ensure_flat(c, v));
+    Timed tm(c, K_INDIRECT, l, v.nI);
+    if (v.nI) { k_indirect_rw<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux); CKRC(post_launch(c)); }
+    return MGCFD_OK;
+}
+int mgcfd_residual(mgcfd_ctx* c, int l) {
+    CKRC(check_level(c, l));
+    Level& v = c->L[l];
+    k_residual<<<(unsigned)blocks_for(5 * v.npad, 256), 256, 0, c->stream>>>(5 * v.npad, v.V(v.i_old), v.V(v.i_var), v.res);
+    return post_launch(c);
+}
+int mgcfd_calc_rms(mgcfd_ctx* c, int l, double* rms_all, double rms_var[5]) {
+    CKRC(check_level(c, l));
+    Level& v = c->L[l];
+    const long nb = blocks_for(v.npad, 256);
+    k_rms_partial<<<(unsigned)nb, 256, 0, c->stream>>>(v.res, v.npad, v.npad, v.rms_partial);
+    CKRC(post_launch(c));
+    v.rms_parts = nb;
+    CKRC(rms_final(c, v, false));
+    double out[6];
+    CK(cudaMemcpyAsync(out, c->d_rms + 6 * (c->rms_cap - 1), sizeof(out), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (rms_all) *rms_all = out[0];
+    if (rms_var) for (int k = 0; k < 5; k++) rms_var[k] = out[1 + k];
+    return MGCFD_OK;
+}
+int mgcfd_check_for_invalid_variables(mgcfd_ctx* c, int l, long* first_bad_cell, int* reason) {
+    CKRC(check_level(c, l));
+    Level& v = c->L[l];
+    unsigned long long* key = c->d_minbits;   // scratch word; the step-factor kernel re-initialises it before use
+    CK(cudaMemsetAsync(key, 0xFF, 8, c->stream));
+    k_check_invalid<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.old_of_new, key);
+    CKRC(post_launch(c));
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, key, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h == ~0ull) { if (first_bad_cell) *first_bad_cell = -1; if (reason) *reason = 0; return MGCFD_OK; }
+    if (first_bad_cell) *first_bad_cell = (long)(h >> 2);
+    if (reason) *reason = (int)(h & 3);
+    g_err = "invalid variables detected";
+    return MGCFD_ERR_INVALID_VARIABLES;
+}
+int mgcfd_mg_restrict(mgcfd_ctx* c, int lc) {
+    CKRC(check_level(c, lc));
+    if (lc < 1) { g_err = "coarse_level must be >= 1"; return MGCFD_ERR_ARG; }
+    return do_restrict(c, lc);
+}
+int mgcfd_prolong(mgcfd_ctx* c, int lf) {
+    CKRC(check_level(c, lf));
+    if (lf >= c->levels - 1) { g_err = "fine_level must have a coarser level"; return MGCFD_ERR_ARG; }
+    return do_prolong(c, lf);
+}
+
+// ---- fused path ----------------------------------------------------------------------------------------
+int mgcfd_run_cycles(mgcfd_ctx* c, int ncycles, double* rms_all, double* rms_var) {
+    if (!c || !c->finalized) { g_err = "context not finalized"; return MGCFD_ERR_ARG; }
+    if (ncycles < 0) { g_err = "ncycles < 0"; return MGCFD_ERR_ARG; }
+    CK(cudaSetDevice(c->opt.device));
+    const bool graph = c->opt.use_graph && !c->opt.timing;
+    int done = 0;
+    while (done < ncycles) {
+        const int chunk = std::min(ncycles - done, c->rms_cap - 1);
+        CK(cudaMemsetAsync(c->d_rms_counter, 0, sizeof(int), c->stream));
+        for (int i = 0; i < chunk; i++) {
+            if (!graph) { CKRC(cycle_fused(c)); continue; }
+            const std::string key = role_key(c);
+            auto it = c->graphs.find(key);
+            if (it == c->graphs.end()) {
+                cudaGraph_t g = nullptr;
+                c->capturing = true;
+                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                int rc = cycle_fused(c);
+                cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+                c->capturing = false;
+                if (rc != MGCFD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+                CK(ce);
+                cudaGraphExec_t ge = nullptr;
+                CK(cudaGraphInstantiate(&ge, g, 0));
+                CK(cudaGraphDestroy(g));
+                c->graphs[key] = ge;
+                // capture only recorded the cycle (and advanced the buffer roles): roll the roles back and replay it
+                for (size_t l = 0; l < c->L.size(); l++) { c->L[l].i_var = key[2 * l] - '0'; c->L[l].i_old = key[2 * l + 1] - '0'; c->L[l].i_tmp = 3 - c->L[l].i_var - c->L[l].i_old; }
+                it = c->graphs.find(key);
+            }
+            CK(cudaGraphLaunch(it->second, c->stream));
+            // advance the roles exactly as cycle_fused does: one smooth on levels 0 and L-1, two on the others
+            for (int l = 0; l < c->levels; l++) {
+                const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
+                for (int k = 0; k < visits; k++) { Level& v = c->L[l]; const int X = v.i_var, A = v.i_tmp, B = v.i_old; v.i_old = X; v.i_var = A; v.i_tmp = B; }
+            }
+            // the graph replays the launches recorded in it
+            long per_cycle = 0;
+            for (int l = 0; l < c->levels; l++) {
+                const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
+                per_cycle += visits * (MGCFD_RK + (c->variant == MGCFD_MESH_FVCORR ? 1 : 2)) + (l == 0 ? 1 : 0);
+            }
+            per_cycle += 2 * (c->levels - 1);
+            c->launches += per_cycle;
+        }
+        std::vector<double> h(6 * (size_t)chunk);
+        if (chunk) CK(cudaMemcpyAsync(h.data(), c->d_rms, sizeof(double) * 6 * chunk, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < chunk; i++) {
+            if (rms_all) rms_all[done + i] = h[6 * i];
+            if (rms_var) for (int k = 0; k < 5; k++) rms_var[(done + i) * 5 + k] = h[6 * i + 1 + k];
+        }
+        done += chunk;
+    }
+    unsigned long long key = 0;
+    CK(cudaMemcpyAsync(&key, c->d_badkey, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (key != ~0ull) { g_err = "invalid variables detected (cell " + std::to_string((key >> 2) & 0x3FFFFFFFFFull) + ")"; return MGCFD_ERR_INVALID_VARIABLES; }
+    return MGCFD_OK;
+}
+
+// ---- state access ----------------------------------------------------------------------------------------
+int mgcfd_get_field(mgcfd_ctx* c, int l, int field, double* host_out) {
+    CKRC(check_level(c, l));
+    if (!host_out) { g_err = "null buffer"; return MGCFD_ERR_ARG; }
+    Level& v = c->L[l];
+    double* p; int nc;
+    CKRC(field_ptr(c, v, field, &p, &nc, false));
+    if (!v.io) CK(cudaMalloc((void**)&v.io, sizeof(double) * 5 * v.nel));
+    k_export_aos<<<(unsigned)blocks_for(v.nel, 256), 256, 0, c->stream>>>(p, v.npad, nc, v.nel, v.new_of_old, v.io);
+    CKRC(post_launch(c));
+    CK(cudaMemcpyAsync(host_out, v.io, sizeof(double) * nc * v.nel, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MGCFD_OK;
+}
+int mgcfd_set_field(mgcfd_ctx* c, int l, int field, const double* host_in) {
+    CKRC(check_level(c, l));
+    if (!host_in) { g_err = "null buffer"; return MGCFD_ERR_ARG; }
+    Level& v = c->L[l];
+    double* p; int nc;
+    CKRC(field_ptr(c, v, field, &p, &nc, true));
+    if (!v.io) CK(cudaMalloc((void**)&v.io, sizeof(double) * 5 * v.nel));
+    CK(cudaMemcpyAsync(v.io, host_in, sizeof(double) * nc * v.nel, cudaMemcpyHostToDevice, c->stream));
+    k_import_aos<<<(unsigned)blocks_for(v.nel, 256), 256, 0, c->stream>>>(p, v.npad, nc, v.nel, v.new_of_old, v.io);
+    CKRC(post_launch(c));
+    CK(cudaStreamSynchronize(c->stream));
+    return MGCFD_OK;
+}
+int mgcfd_synchronize(mgcfd_ctx* c) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    CK(cudaStreamSynchronize(c->stream));
+    return MGCFD_OK;
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------
+int mgcfd_level_info(mgcfd_ctx* c, int l, long info[16]) {
+    CKRC(check_level(c, l, false));
+    const LevelPlan& P = c->L[l].plan;
+    memset(info, 0, sizeof(long) * 16);
+    info[0] = P.nel; info[1] = P.nI; info[2] = P.nB; info[3] = P.nW; info[4] = P.npad; info[5] = P.ntiles; info[6] = P.TN;
+    info[7] = P.max_rounds; info[8] = P.slot_off.empty() ? 0 : P.slot_off[P.ntiles]; info[9] = (long)P.halo_ids.size();
+    info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off.empty() ? 0 : P.bslot_off[P.ntiles];
+    info[14] = (long)c->L[l].smem_bytes;
+    return MGCFD_OK;
+}
+int mgcfd_get_permutation(mgcfd_ctx* c, int l, long* new_of_old) {
+    CKRC(check_level(c, l, false));
+    const LevelPlan& P = c->L[l].plan;
+    memcpy(new_of_old, P.new_of_old.data(), sizeof(long) * P.nel);
+    return MGCFD_OK;
+}
+long mgcfd_check_colouring(mgcfd_ctx* c, int l) {
+    if (check_level(c, l, false) != MGCFD_OK) return -1;
+    return check_colouring(c->L[l].plan);
+}
+int mgcfd_get_times(mgcfd_ctx* c, double* out_ms, long* out_iters) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    if (out_ms) memcpy(out_ms, c->t_ms.data(), sizeof(double) * c->t_ms.size());
+    if (out_iters) memcpy(out_iters, c->t_iters.data(), sizeof(long) * c->t_iters.size());
+    return MGCFD_OK;
+}
+int mgcfd_reset_times(mgcfd_ctx* c) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    std::fill(c->t_ms.begin(), c->t_ms.end(), 0.0);
+    std::fill(c->t_iters.begin(), c->t_iters.end(), 0L);
+    return MGCFD_OK;
+}
+long mgcfd_launch_count(mgcfd_ctx* c) { return c ? c->launches : -1; }
+
+int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total) {
+    CKRC(check_level(c, l));
+    if (reps < 1 || !ms_total) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    Level& v = c->L[l];
+    CKRC(ensure_flux(c, v));
+    if (which == 2 || which == 3) CKRC(ensure_flat(c, v));
+    if (which == 4) CKRC(ensure_csr(c, v));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int r = 0; r < reps; r++) {
+        if (which == 0 || which == 1) {
+            TileArgs a = base_args(c, v);
+            a.vin = v.V(v.i_var); a.vold = v.V(v.i_var); a.rk_div = 4.0;
+            if (which == 0) { a.vout = v.V(v.i_tmp); a.mask = 7; CKRC(launch_tile(c, v, a, true)); }
+            else { a.vout = v.flux; a.mask = 1; CKRC(launch_tile(c, v, a, false)); }
+        } else if (which == 2) {
+            k_indirect_rw<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux); CKRC(post_launch(c));
+        } else if (which == 3) {
+            k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, c->kdiss); CKRC(post_launch(c));
+        } else if (which == 4) {
+            k_flux_segment<<<(unsigned)blocks_for(v.npad, 128), 128, 0, c->stream>>>(v.npad, v.adj_off, v.adj_nbr, v.adj_w, 2 * v.nI, v.V(v.i_var), v.npad, v.flux, c->kdiss); CKRC(post_launch(c));
+        } else { g_err = "unknown kernel selector"; return MGCFD_ERR_ARG; }
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaEventSynchronize(c->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_total = ms;
+    CK(cudaMemsetAsync(v.flux, 0, sizeof(double) * 5 * v.npad, c->stream));
+    return MGCFD_OK;
+}
+
+int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, const void* edges, int ordering, int tile_nodes,
+                     long info[16], long* new_of_old, long* conflicts) {
+    if (nel <= 0 || !edges || !info) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    HostLevel H;
+    H.nel = nel; H.nI = nI; H.nB = nB; H.nW = nW;
+    H.volumes.assign(nel, 1.0);
+    const EdgeNb* e = (const EdgeNb*)edges;
+    H.edges.assign(e, e + nI + nB + nW);
+    if (coords) H.coords.assign(coords, coords + 3 * nel);
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 256;
+    LevelPlan P;
+    try { build_level_plan(H, po, P); }
+    catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    memset(info, 0, sizeof(long) * 16);
+    info[0] = P.nel; info[1] = P.nI; info[2] = P.nB; info[3] = P.nW; info[4] = P.npad; info[5] = P.ntiles; info[6] = P.TN;
+    info[7] = P.max_rounds; info[8] = P.slot_off[P.ntiles]; info[9] = (long)P.halo_ids.size();
+    info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off[P.ntiles];
+    if (new_of_old) memcpy(new_of_old, P.new_of_old.data(), sizeof(long) * nel);
+    if (conflicts) *conflicts = check_colouring(P);
+    return MGCFD_OK;
+}
+
+void mgcfd_free(void* p) { free(p); }
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// mesh_api.cpp -- extern "C" surface of the host mesh utilities (include/mgcfd_mesh.h)
+#include <cstring>
+#include <string>
+
+#include "../../include/mgcfd_mesh.h"
+#include "host_mesh.h"
+
+using namespace mgcfd;
+
+struct mgcfd_mesh { HostMesh m; };
+
+namespace { thread_local std::string g_mesh_err; }
+extern "C" const char* mgcfd_mesh_last_error(void) { return g_mesh_err.c_str(); }
+
+extern "C" {
+
+int mgcfd_mesh_generate(int kind, int levels, const long* dims, const double lengths[3], int mesh_variant, int ordering,
+                        unsigned long seed, double tilt, mgcfd_mesh** out) {
+    if (!out || !dims || levels < 1 || levels > 8) { g_mesh_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    MeshSpec s;
+    s.kind = kind; s.levels = levels; s.mesh_variant = mesh_variant; s.ordering = ordering; s.seed = seed; s.tilt = tilt;
+    for (int l = 0; l < levels; l++) for (int k = 0; k < 3; k++) s.dims[l][k] = dims[3 * l + k];
+    if (lengths) for (int k = 0; k < 3; k++) s.lengths[k] = lengths[k];
+    mgcfd_mesh* m = new mgcfd_mesh();
+    int rc = generate_mesh(s, m->m, g_mesh_err);
+    if (rc) { delete m; *out = nullptr; return rc; }
+    *out = m;
+    return MGCFD_OK;
+}
+
+int mgcfd_mesh_load(const char* input_dat, const char* dir, mgcfd_mesh** out) {
+    if (!out || !input_dat) { g_mesh_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    mgcfd_mesh* m = new mgcfd_mesh();
+    int rc = load_mesh(input_dat, dir ? dir : "", m->m, g_mesh_err);
+    if (rc) { delete m; *out = nullptr; return rc; }
+    *out = m;
+    return MGCFD_OK;
+}
+
+int mgcfd_mesh_write(const mgcfd_mesh* m, const char* dir, const char* name, int binary) {
+    if (!m || !dir || !name) { g_mesh_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    if (m->m.ewt_applied) { g_mesh_err = "edge weights already adjusted: write the mesh before mgcfd_mesh_apply_ewt"; return MGCFD_ERR_ARG; }
+    const std::string d(dir);
+    const int nl = int(m->m.levels.size());
+    for (int l = 0; l < nl; l++) {
+        const HostLevel& L = m->m.levels[l];
+        int rc = write_level_text(L, m->m.mesh_variant, d + "/" + L.name, true);
+        if (rc) { g_mesh_err = "cannot write " + L.name; return rc; }
+        if (l + 1 < nl) { rc = write_mg_text(L, d + "/" + L.name + ".mg"); if (rc) { g_mesh_err = "cannot write mg map"; return rc; } }
+        if (binary) { rc = write_level_bin(L, d + "/" + L.name + ".bin"); if (rc) { g_mesh_err = "cannot write .bin"; return rc; } }
+    }
+    int rc = write_input_dat(m->m, d, name);
+    if (rc) g_mesh_err = "cannot write input.dat";
+    return rc;
+}
+
+int mgcfd_mesh_levels(const mgcfd_mesh* m) { return m ? int(m->m.levels.size()) : -1; }
+int mgcfd_mesh_variant(const mgcfd_mesh* m) { return m ? m->m.mesh_variant : -1; }
+
+int mgcfd_mesh_dims(const mgcfd_mesh* m, int l, long out[5]) {
+    if (!m || l < 0 || l >= int(m->m.levels.size())) { g_mesh_err = "bad level"; return MGCFD_ERR_ARG; }
+    const HostLevel& L = m->m.levels[l];
+    out[0] = L.nel; out[1] = L.nI; out[2] = L.nB; out[3] = L.nW; out[4] = long(L.mg.size());
+    return MGCFD_OK;
+}
+
+const void* mgcfd_mesh_ptr(const mgcfd_mesh* m, int l, int what) {
+    if (!m || l < 0 || l >= int(m->m.levels.size())) return nullptr;
+    const HostLevel& L = m->m.levels[l];
+    switch (what) {
+        case 0: return L.volumes.data();
+        case 1: return L.edges.data();
+        case 2: return L.coords.empty() ? nullptr : L.coords.data();
+        case 3: return L.mg.empty() ? nullptr : L.mg.data();
+    }
+    return nullptr;
+}
+
+int mgcfd_mesh_apply_ewt(mgcfd_mesh* m) {
+    if (!m) { g_mesh_err = "null mesh"; return MGCFD_ERR_ARG; }
+    if (m->m.ewt_applied) return MGCFD_OK;
+    for (auto& L : m->m.levels) {
+        if (m->m.mesh_variant != MGCFD_MESH_FVCORR && L.coords.empty()) { g_mesh_err = "coords needed for adjust_ewt"; return MGCFD_ERR_ARG; }
+        apply_ewt(m->m.mesh_variant, L.coords.data(), L.nI + L.nB + L.nW, L.edges.data());
+    }
+    m->m.ewt_applied = true;
+    return MGCFD_OK;
+}
+
+int mgcfd_mesh_upload(mgcfd_mesh* m, mgcfd_ctx* ctx) {
+    if (!m || !ctx) { g_mesh_err = "null argument"; return MGCFD_ERR_ARG; }
+    int rc = mgcfd_mesh_apply_ewt(m);
+    if (rc) return rc;
+    const int nl = int(m->m.levels.size());
+    for (int l = 0; l < nl; l++) {
+        const HostLevel& L = m->m.levels[l];
+        rc = mgcfd_upload_level(ctx, l, L.nel, L.volumes.data(), L.coords.empty() ? nullptr : L.coords.data(), L.nI, L.nB, L.nW,
+                                L.edges.data(), L.mg.empty() ? nullptr : L.mg.data(), long(L.mg.size()));
+        if (rc) { g_mesh_err = mgcfd_last_error(); return rc; }
+    }
+    rc = mgcfd_finalize(ctx);
+    if (rc) g_mesh_err = mgcfd_last_error();
+    return rc;
+}
+
+void mgcfd_mesh_free(mgcfd_mesh* m) { delete m; }
+
+}  // extern "C"

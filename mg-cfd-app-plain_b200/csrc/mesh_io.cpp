@@ -1,0 +1,301 @@
+// mesh_io.cpp -- readers/writers for the reference's mesh interchange formats:
+//   text mesh     `nel nedges` + per node `volume degree` + degree x (`nbr wx wy wz`)   src/Base/io.cpp:56-137
+//   <mesh>.coords `x y z` per node (needed iff levels > 1)                               src/Base/io.cpp:49-54,77-81
+//   MG map        `mgc` + mgc fine->coarse indices                                       src/Base/io_enhanced.cpp:629-650
+//   input.dat     size= / num_levels= / mesh_name= / [levels] / [mg_mapping]             src/Base/io_enhanced.cpp:407-579
+//   .bin cache    8 long header, volumes, edges, coords, mg_size, mg                     src/Base/io_enhanced.cpp:384-400
+// Own implementation (single pass over a file buffer with strtol/strtod); the edge construction rules are
+// shared with the generators through build_level_like_read_grid.
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+#include "host_mesh.h"
+
+namespace mgcfd {
+
+namespace {
+
+bool slurp(const std::string& path, std::vector<char>& buf) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long sz = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize(size_t(sz) + 1);
+    size_t got = fread(buf.data(), 1, size_t(sz), f);
+    fclose(f);
+    buf[got] = 0;
+    return got == size_t(sz);
+}
+
+std::string trim(const std::string& s) {
+    size_t a = s.find_first_not_of(" \t\r\n");
+    if (a == std::string::npos) return "";
+    size_t b = s.find_last_not_of(" \t\r\n");
+    return s.substr(a, b - a + 1);
+}
+
+const char* variant_name(int v) {
+    switch (v) { case 0: return "fvcorr"; case 2: return "m6wing"; case 3: return "la_cascade"; case 4: return "rotor37"; }
+    return "m6wing";
+}
+
+// node source over an in-memory text file; parses lazily and sequentially (listing(i) must be called with i ascending)
+struct TextSource : NodeSource {
+    mutable char* p;
+    long n = 0, ne_claimed = 0;
+    mutable char* cp;   // coords cursor or NULL
+    mutable double vol = 0;
+    mutable long cur = -1;
+    mutable Entry ent[32];
+    mutable int deg = 0;
+    mutable double xyz[3] = {0, 0, 0};
+    TextSource(char* mesh, char* coords) : p(mesh), cp(coords) {
+        n = strtol(p, &p, 10);
+        ne_claimed = strtol(p, &p, 10);
+    }
+    void advance(long i) const {
+        while (cur < i) {
+            vol = strtod(p, &p);
+            deg = int(strtol(p, &p, 10));
+            for (int j = 0; j < deg; j++) {
+                Entry e;
+                e.nbr = strtol(p, &p, 10);
+                e.w[0] = strtod(p, &p); e.w[1] = strtod(p, &p); e.w[2] = strtod(p, &p);
+                if (j < 32) ent[j] = e;
+            }
+            if (deg > 32) deg = 32;
+            if (cp) { xyz[0] = strtod(cp, &cp); xyz[1] = strtod(cp, &cp); xyz[2] = strtod(cp, &cp); }
+            cur++;
+        }
+    }
+    long nel() const override { return n; }
+    double volume(long i) const override { advance(i); return vol; }
+    void coords(long i, double* o) const override { advance(i); o[0] = xyz[0]; o[1] = xyz[1]; o[2] = xyz[2]; }
+    int listing(long i, Entry* out) const override { advance(i); memcpy(out, ent, sizeof(Entry) * deg); return deg; }
+};
+
+}  // namespace
+
+int write_level_text(const HostLevel& L, int mesh_variant, const std::string& path, bool with_coords) {
+    const long n = L.nel;
+    const long ne = L.nI + L.nB + L.nW;
+    // CSR of edges incident to each node: lower entries (b == i) keep edge order; upper entries (a == i) follow.
+    std::vector<long> cnt(n + 1, 0);
+    for (long e = 0; e < ne; e++) {
+        cnt[L.edges[e].b + 1]++;
+        if (L.edges[e].a >= 0) cnt[L.edges[e].a + 1]++;
+    }
+    for (long i = 0; i < n; i++) cnt[i + 1] += cnt[i];
+    std::vector<long> pos(cnt.begin(), cnt.end() - 1), slot(cnt[n]);
+    // order per node: internal lower, boundary, wall, then upper -- fill in that class order
+    for (long e = 0; e < ne; e++) slot[pos[L.edges[e].b]++] = e;                              // b-side, edge order: internal, bnd, wall
+    for (long e = 0; e < L.nI; e++) slot[pos[L.edges[e].a]++] = -(e + 1);                      // a-side (upper neighbour)
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) return 5;
+    fprintf(f, "%ld %ld\n", n, ne);
+    const bool fv = (mesh_variant == 0);
+    for (long i = 0; i < n; i++) {
+        fprintf(f, "%.17g %ld\n", L.volumes[i], cnt[i + 1] - cnt[i]);
+        for (long k = cnt[i]; k < cnt[i + 1]; k++) {
+            const long s = slot[k];
+            if (s >= 0) {
+                const EdgeNb& e = L.edges[s];
+                const double sg = (fv || e.a >= 0) ? -1.0 : 1.0;   // undo the loader's flip (io.cpp:111-133)
+                fprintf(f, "%ld %.17g %.17g %.17g\n", e.a, sg * e.x, sg * e.y, sg * e.z);
+            } else {
+                const EdgeNb& e = L.edges[-s - 1];                // listed from a: ignored by the loader (nbr > i)
+                fprintf(f, "%ld %.17g %.17g %.17g\n", e.b, e.x, e.y, e.z);
+            }
+        }
+    }
+    fclose(f);
+    if (with_coords && !L.coords.empty()) {
+        FILE* c = fopen((path + ".coords").c_str(), "w");
+        if (!c) return 5;
+        for (long i = 0; i < n; i++) fprintf(c, "%.17g %.17g %.17g\n", L.coords[3 * i], L.coords[3 * i + 1], L.coords[3 * i + 2]);
+        fclose(c);
+    }
+    return 0;
+}
+
+int write_mg_text(const HostLevel& L, const std::string& path) {
+    FILE* f = fopen(path.c_str(), "w");
+    if (!f) return 5;
+    fprintf(f, "%ld\n", long(L.mg.size()));
+    for (long v : L.mg) fprintf(f, "%ld\n", v);
+    fclose(f);
+    return 0;
+}
+
+int write_input_dat(const HostMesh& m, const std::string& dir, const std::string& fname) {
+    FILE* f = fopen((dir + "/" + fname).c_str(), "w");
+    if (!f) return 5;
+    fprintf(f, "# synthetic mesh written by mgcfd-b200 in the MG-CFD input format\n");
+    fprintf(f, "size = %d\nnum_levels = %d\nmesh_name = %s\n", m.size, int(m.levels.size()), variant_name(m.mesh_variant));
+    fprintf(f, "[levels]\n");
+    for (size_t l = 0; l < m.levels.size(); l++) fprintf(f, "%zu = %s\n", l, m.levels[l].name.c_str());
+    if (m.levels.size() > 1) {
+        fprintf(f, "[mg_mapping]\n");
+        for (size_t l = 0; l + 1 < m.levels.size(); l++) fprintf(f, "%zu = %s.mg\n", l, m.levels[l].name.c_str());
+    }
+    fclose(f);
+    return 0;
+}
+
+int read_level_text(const std::string& path, int mesh_variant, bool need_coords, HostLevel& out, std::string& err) {
+    std::vector<char> buf, cbuf;
+    if (!slurp(path, buf)) { err = "could not open data file: '" + path + "'"; return 5; }
+    const bool have_coords = slurp(path + ".coords", cbuf);
+    if (!have_coords && need_coords) { err = "could not open coords file for: " + path; return 5; }
+    TextSource src(buf.data(), have_coords ? cbuf.data() : nullptr);
+    build_level_like_read_grid(src, mesh_variant, have_coords, out);
+    if (out.nI + out.nB + out.nW != src.ne_claimed)
+        fprintf(stderr, "WARNING: Mesh claims to have %ld edges, actually has %ld\n", src.ne_claimed, out.nI + out.nB + out.nW);
+    return 0;
+}
+
+int read_mg_text(const std::string& path, std::vector<long>& mg, std::string& err) {
+    std::vector<char> buf;
+    if (!slurp(path, buf)) { err = "could not open mg file: '" + path + "'"; return 5; }
+    char* p = buf.data();
+    long n = strtol(p, &p, 10);
+    mg.resize(n);
+    for (long i = 0; i < n; i++) mg[i] = strtol(p, &p, 10);
+    return 0;
+}
+
+int read_input_dat(const std::string& path, int& size, int& levels, int& variant, std::vector<std::string>& layers,
+                   std::vector<std::string>& mgfiles, std::string& err) {
+    std::ifstream file(path.c_str());
+    if (!file.is_open()) { err = "Error: Could not open input file '" + path + "'"; return 5; }
+    bool have_size = false, have_levels = false, have_name = false, have_files = false;
+    std::string line;
+    levels = 0;
+    auto read_block = [&](std::vector<std::string>& dst, int count, const char* what) -> bool {
+        dst.assign(count, "");
+        for (int i = 0; i < count; i++) {
+            if (!std::getline(file, line)) { err = std::string("Error parsing ") + path + ": reached EOF before reading all " + what; return false; }
+            size_t eq = line.find('=');
+            if (eq == std::string::npos) { err = std::string("Error parsing '") + path + "': expected key-value pair in " + what; return false; }
+            int idx = atoi(trim(line.substr(0, eq)).c_str());
+            if (idx >= 0 && idx < count) dst[idx] = trim(line.substr(eq + 1));
+        }
+        return true;
+    };
+    while (std::getline(file, line)) {
+        if (!line.empty() && line[0] == '#') continue;
+        if (!line.empty() && line[0] == '[') {
+            const std::string t = trim(line);
+            if (t == "[levels]") {
+                if (!have_levels) { err = "Error parsing " + path + ": Need to know number of levels before parsing level filenames"; return 5; }
+                if (!read_block(layers, levels, "mesh filenames")) return 5;
+                have_files = true;
+            } else if (t == "[mg_mapping]") {
+                if (!have_levels) { err = "Error parsing " + path + ": Need to know number of levels before parsing level filenames"; return 5; }
+                if (!read_block(mgfiles, levels - 1, "MG filenames")) return 5;
+            }
+            continue;
+        }
+        size_t eq = line.find('=');
+        if (eq == std::string::npos) continue;
+        const std::string key = trim(line.substr(0, eq)), value = trim(line.substr(eq + 1));
+        if (value.empty()) continue;
+        if (key == "size") { size = atoi(value.c_str()); have_size = true; }
+        else if (key == "num_levels") { levels = atoi(value.c_str()); have_levels = true; }
+        else if (key == "mesh_name") {
+            if (value == "la_cascade") variant = 3;
+            else if (value == "rotor37") variant = 4;
+            else if (value == "fvcorr") variant = 0;
+            else if (value == "m6wing") variant = 2;
+            else { err = "Error parsing " + path + ": Unknown mesh_name '" + value + "'"; return 5; }
+            have_name = true;
+        }
+    }
+    if (!have_size) { err = "Error parsing '" + path + "': size not present"; return 5; }
+    if (!have_levels) { err = "Error parsing '" + path + "': number of levels not present"; return 5; }
+    if (!have_name) { err = "Error parsing '" + path + "': mesh name not present"; return 5; }
+    if (!have_files) { err = "Error parsing '" + path + "': mesh filenames not present"; return 5; }
+    if (int(mgfiles.size()) != levels - 1) mgfiles.assign(levels > 0 ? levels - 1 : 0, "");
+    return 0;
+}
+
+int write_level_bin(const HostLevel& L, const std::string& path) {
+    FILE* f = fopen(path.c_str(), "wb");
+    if (!f) return 5;
+    const long ne = L.nI + L.nB + L.nW;
+    const long hdr[8] = {L.nel, ne, L.nI, L.nB, L.nW, 0, L.nI, L.nI + L.nB};
+    fwrite(hdr, sizeof(long), 8, f);
+    fwrite(L.volumes.data(), sizeof(double), L.nel, f);
+    fwrite(L.edges.data(), sizeof(EdgeNb), ne, f);
+    if (L.coords.empty()) { std::vector<double> z(3 * L.nel, 0.0); fwrite(z.data(), sizeof(double), 3 * L.nel, f); }
+    else fwrite(L.coords.data(), sizeof(double), 3 * L.nel, f);
+    const long mgs = long(L.mg.size());
+    fwrite(&mgs, sizeof(long), 1, f);
+    if (mgs) fwrite(L.mg.data(), sizeof(long), mgs, f);
+    fclose(f);
+    return 0;
+}
+
+int read_level_bin(const std::string& path, HostLevel& out, std::string& err) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { err = "'" + path + "' binary file cannot be read"; return 5; }
+    long hdr[8];
+    auto bad = [&]() { fclose(f); err = "Corruption detected in '" + path + "'"; return 5; };
+    if (fread(hdr, sizeof(long), 8, f) != 8) return bad();
+    for (int k = 0; k < 8; k++) if (hdr[k] < 0) return bad();
+    if (hdr[2] + hdr[3] + hdr[4] > hdr[1]) return bad();
+    out.nel = hdr[0]; out.nI = hdr[2]; out.nB = hdr[3]; out.nW = hdr[4];
+    const long ne = hdr[1];
+    out.volumes.resize(out.nel);
+    if (fread(out.volumes.data(), sizeof(double), out.nel, f) != size_t(out.nel)) return bad();
+    std::vector<EdgeNb> all(ne);
+    if (fread(all.data(), sizeof(EdgeNb), ne, f) != size_t(ne)) return bad();
+    // the header allows gaps between the three ranges; we store them contiguously
+    out.edges.clear();
+    out.edges.insert(out.edges.end(), all.begin() + hdr[5], all.begin() + hdr[5] + out.nI);
+    out.edges.insert(out.edges.end(), all.begin() + hdr[6], all.begin() + hdr[6] + out.nB);
+    out.edges.insert(out.edges.end(), all.begin() + hdr[7], all.begin() + hdr[7] + out.nW);
+    out.coords.resize(3 * out.nel);
+    if (fread(out.coords.data(), sizeof(double), 3 * out.nel, f) != size_t(3 * out.nel)) return bad();
+    long mgs = 0;
+    if (fread(&mgs, sizeof(long), 1, f) != 1 || mgs < 0) return bad();
+    out.mg.resize(mgs);   // (the reference casts the POINTER mg_size here, io_enhanced.cpp:341; not reproduced)
+    if (mgs && fread(out.mg.data(), sizeof(long), mgs, f) != size_t(mgs)) return bad();
+    fclose(f);
+    return 0;
+}
+
+int load_mesh(const std::string& input_dat, const std::string& dir, HostMesh& out, std::string& err) {
+    std::string path = input_dat;
+    if (!dir.empty()) path = dir + "/" + input_dat;
+    int size = 0, levels = 0, variant = 2;
+    std::vector<std::string> layers, mgs;
+    int rc = read_input_dat(path, size, levels, variant, layers, mgs, err);
+    if (rc) return rc;
+    out = HostMesh();
+    out.mesh_variant = variant; out.size = size;
+    out.levels.resize(levels);
+    for (int l = 0; l < levels; l++) {
+        std::string lp = dir.empty() ? layers[l] : dir + "/" + layers[l];
+        HostLevel& L = out.levels[l];
+        std::string e2;
+        if (read_level_bin(lp + ".bin", L, e2) != 0) {
+            rc = read_level_text(lp, variant, levels > 1, L, err);
+            if (rc) return rc;
+            if (l != levels - 1) {
+                std::string mp = dir.empty() ? mgs[l] : dir + "/" + mgs[l];
+                rc = read_mg_text(mp, L.mg, err);
+                if (rc) return rc;
+            }
+        }
+        L.name = layers[l];
+    }
+    return 0;
+}
+
+}  // namespace mgcfd

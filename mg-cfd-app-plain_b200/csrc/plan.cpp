@@ -1,0 +1,447 @@
+// plan.cpp -- integer preprocessing (renumbering, tiling, colouring, MG operators). See plan.h.
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <numeric>
+#include <stdexcept>
+
+namespace mgcfd {
+
+namespace {
+
+struct Csr {
+    std::vector<long> off;
+    std::vector<int> nbr;
+};
+
+// undirected adjacency of the internal edges, in OLD ids; per node, entries in ascending edge index
+Csr adjacency_old(const HostLevel& L) {
+    Csr g;
+    g.off.assign(L.nel + 1, 0);
+    for (long e = 0; e < L.nI; e++) { g.off[L.edges[e].a + 1]++; g.off[L.edges[e].b + 1]++; }
+    for (long i = 0; i < L.nel; i++) g.off[i + 1] += g.off[i];
+    g.nbr.resize(g.off[L.nel]);
+    std::vector<long> pos(g.off.begin(), g.off.end() - 1);
+    for (long e = 0; e < L.nI; e++) {
+        const long a = L.edges[e].a, b = L.edges[e].b;
+        g.nbr[pos[a]++] = int(b);
+        g.nbr[pos[b]++] = int(a);
+    }
+    return g;
+}
+
+// Breadth-first (Cuthill-McKee) order of the nodes for which member(i) holds, appended to `order`.
+// Neighbours are visited by (degree, id). `visited` is a stamp array.
+template <class Member>
+void cm_order(const Csr& g, const std::vector<long>& nodes, Member member, std::vector<int>& stamp, int mark,
+              std::vector<long>& order) {
+    auto degree = [&](long i) { return g.off[i + 1] - g.off[i]; };
+    std::vector<long> frontier_nbrs;
+    // seeds by (degree, id): low-degree nodes first, as in classical CM
+    std::vector<long> seeds(nodes);
+    std::sort(seeds.begin(), seeds.end(), [&](long x, long y) {
+        const long dx = degree(x), dy = degree(y);
+        return dx != dy ? dx < dy : x < y;
+    });
+    for (long seed : seeds) {
+        if (stamp[seed] == mark) continue;
+        // pseudo-peripheral start: two BFS sweeps from the seed inside the member set
+        long start = seed;
+        for (int sweep = 0; sweep < 2; sweep++) {
+            std::vector<long> q{start};
+            std::vector<long> touched{start};
+            stamp[start] = -mark;
+            size_t head = 0;
+            while (head < q.size()) {
+                long u = q[head++];
+                for (long k = g.off[u]; k < g.off[u + 1]; k++) {
+                    long v = g.nbr[k];
+                    if (!member(v) || stamp[v] == mark || stamp[v] == -mark) continue;
+                    stamp[v] = -mark;
+                    q.push_back(v);
+                    touched.push_back(v);
+                }
+            }
+            // last level: pick the lowest-degree node of the final BFS layer (approximate: last visited)
+            start = q.back();
+            for (long v : touched) stamp[v] = 0;
+        }
+        size_t head = order.size();
+        order.push_back(start);
+        stamp[start] = mark;
+        while (head < order.size()) {
+            long u = order[head++];
+            frontier_nbrs.clear();
+            for (long k = g.off[u]; k < g.off[u + 1]; k++) {
+                long v = g.nbr[k];
+                if (!member(v) || stamp[v] == mark) continue;
+                stamp[v] = mark;
+                frontier_nbrs.push_back(v);
+            }
+            std::sort(frontier_nbrs.begin(), frontier_nbrs.end(), [&](long x, long y) {
+                const long dx = degree(x), dy = degree(y);
+                return dx != dy ? dx < dy : x < y;
+            });
+            order.insert(order.end(), frontier_nbrs.begin(), frontier_nbrs.end());
+        }
+    }
+}
+
+struct Bisector {
+    const HostLevel& L;
+    const Csr& g;
+    long TN;
+    std::vector<long>& tile_of;
+    std::vector<int> sub;     // subset stamp for the graph variant
+    std::vector<int> stamp;
+    int next_mark = 1;
+    Bisector(const HostLevel& L_, const Csr& g_, long tn, std::vector<long>& t) : L(L_), g(g_), TN(tn), tile_of(t) {}
+
+    static long left_count(long n, long k, long kl, long TN) {
+        long nl = (n * kl + k / 2) / k;
+        nl = std::min(nl, kl * TN);
+        nl = std::max(nl, n - (k - kl) * TN);
+        return nl;
+    }
+    // recursive coordinate bisection: split the widest extent at the proportional rank
+    void rcb(long* idx, long n, long k, long tile0, int depth) {
+        if (k == 1) { for (long i = 0; i < n; i++) tile_of[idx[i]] = tile0; return; }
+        const long kl = k / 2, nl = left_count(n, k, kl, TN);
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (long i = 0; i < n; i++) for (int d = 0; d < 3; d++) {
+            const double c = L.coords[3 * idx[i] + d];
+            lo[d] = std::min(lo[d], c); hi[d] = std::max(hi[d], c);
+        }
+        int ax = 0;
+        for (int d = 1; d < 3; d++) if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+        const double* c = L.coords.data();
+        std::nth_element(idx, idx + nl, idx + n, [c, ax](long x, long y) {
+            const double cx = c[3 * x + ax], cy = c[3 * y + ax];
+            return cx != cy ? cx < cy : x < y;
+        });
+        if (depth < 3 && n > 200000) {
+            auto fut = std::async(std::launch::async, [&] { rcb(idx, nl, kl, tile0, depth + 1); });
+            rcb(idx + nl, n - nl, k - kl, tile0 + kl, depth + 1);
+            fut.get();
+        } else {
+            rcb(idx, nl, kl, tile0, depth + 1);
+            rcb(idx + nl, n - nl, k - kl, tile0 + kl, depth + 1);
+        }
+    }
+    // graph bisection: BFS order of the subset from a pseudo-peripheral node, first nl nodes go left
+    void gbis(long* idx, long n, long k, long tile0) {
+        if (k == 1) { for (long i = 0; i < n; i++) tile_of[idx[i]] = tile0; return; }
+        const long kl = k / 2, nl = left_count(n, k, kl, TN);
+        if (sub.empty()) { sub.assign(L.nel, 0); stamp.assign(L.nel, 0); }
+        const int s = next_mark++;
+        for (long i = 0; i < n; i++) sub[idx[i]] = s;
+        std::vector<long> nodes(idx, idx + n), order;
+        order.reserve(n);
+        const int mark = next_mark++;
+        cm_order(g, nodes, [&](long v) { return sub[v] == s; }, stamp, mark, order);
+        std::copy(order.begin(), order.end(), idx);
+        gbis(idx, nl, kl, tile0);
+        gbis(idx + nl, n - nl, k - kl, tile0 + kl);
+    }
+};
+
+struct Mask256 {
+    uint64_t w[4] = {0, 0, 0, 0};
+    inline void set(int c) { w[c >> 6] |= (1ull << (c & 63)); }
+    static inline int first_free(const Mask256& a, const Mask256& b) {
+        for (int k = 0; k < 4; k++) {
+            uint64_t m = ~(a.w[k] | b.w[k]);
+            if (m) return 64 * k + __builtin_ctzll(m);
+        }
+        throw std::runtime_error("mgcfd: more than 256 colours needed in one tile");
+    }
+};
+
+}  // namespace
+
+void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) {
+    const long n = L.nel;
+    const long TN = opt.tile_nodes;
+    P = LevelPlan();
+    P.nel = n; P.nI = L.nI; P.nB = L.nB; P.nW = L.nW; P.TN = int(TN);
+    P.ntiles = std::max<long>(1, (n + TN - 1) / TN);
+    P.npad = P.ntiles * TN;
+    if (P.npad > 0x7fffffffL) throw std::runtime_error("mgcfd: level too large for 32-bit node ids");
+    const Csr g = adjacency_old(L);
+
+    // ---- 1. node -> tile, and order inside tiles --------------------------------------------------
+    std::vector<long> tile_of(n, 0);
+    std::vector<long> seq(n);    // global visiting sequence used to rank nodes inside a tile
+    if (opt.ordering == 0) {
+        for (long i = 0; i < n; i++) { tile_of[i] = i / TN; seq[i] = i; }
+    } else if (opt.ordering == 1) {
+        std::vector<long> nodes(n), order;
+        std::iota(nodes.begin(), nodes.end(), 0L);
+        std::vector<int> stamp(n, 0);
+        order.reserve(n);
+        cm_order(g, nodes, [](long) { return true; }, stamp, 1, order);
+        std::reverse(order.begin(), order.end());   // reverse Cuthill-McKee
+        for (long r = 0; r < n; r++) { tile_of[order[r]] = r / TN; seq[order[r]] = r; }
+    } else {
+        std::vector<long> idx(n);
+        std::iota(idx.begin(), idx.end(), 0L);
+        Bisector B(L, g, TN, tile_of);
+        if (!L.coords.empty()) B.rcb(idx.data(), n, P.ntiles, 0, 0);
+        else B.gbis(idx.data(), n, P.ntiles, 0);
+        // Cuthill-McKee inside every tile
+        std::vector<long> toff(P.ntiles + 1, 0);
+        for (long i = 0; i < n; i++) toff[tile_of[i] + 1]++;
+        for (long t = 0; t < P.ntiles; t++) toff[t + 1] += toff[t];
+        std::vector<long> members(n), pos(toff.begin(), toff.end() - 1);
+        for (long i = 0; i < n; i++) members[pos[tile_of[i]]++] = i;
+        std::vector<int> stamp(n, 0);
+        std::vector<long> order, nodes;
+        long r = 0;
+        for (long t = 0; t < P.ntiles; t++) {
+            nodes.assign(members.begin() + toff[t], members.begin() + toff[t + 1]);
+            order.clear();
+            cm_order(g, nodes, [&](long v) { return tile_of[v] == t; }, stamp, int(t % 1000000000) + 1, order);
+            for (long v : order) seq[v] = r++;
+            // stamps are tile specific (t+1) and tiles are disjoint, so no reset is needed
+        }
+    }
+    // rank inside tile by seq
+    P.new_of_old.assign(n, -1);
+    P.old_of_new.assign(P.npad, -1);
+    P.tile_nown.assign(P.ntiles, 0);
+    {
+        std::vector<long> byseq(n);
+        std::iota(byseq.begin(), byseq.end(), 0L);
+        std::sort(byseq.begin(), byseq.end(), [&](long x, long y) { return seq[x] < seq[y]; });
+        for (long i : byseq) {
+            const long t = tile_of[i];
+            const long id = t * TN + P.tile_nown[t]++;
+            P.new_of_old[i] = id;
+            P.old_of_new[id] = i;
+        }
+        for (long t = 0; t < P.ntiles; t++)
+            if (P.tile_nown[t] > TN) throw std::runtime_error("mgcfd: internal error, tile overflow");
+    }
+
+    // ---- 2. flat edge list + CSR by node in new ids (entries in ascending original edge index) ------
+    P.ea.resize(L.nI); P.eb.resize(L.nI); P.ew.resize(3 * L.nI);
+    for (long e = 0; e < L.nI; e++) {
+        P.ea[e] = int(P.new_of_old[L.edges[e].a]);
+        P.eb[e] = int(P.new_of_old[L.edges[e].b]);
+        P.ew[e] = L.edges[e].x; P.ew[L.nI + e] = L.edges[e].y; P.ew[2 * L.nI + e] = L.edges[e].z;
+    }
+    const long nbw = L.nB + L.nW;
+    P.bnode.resize(nbw); P.bkind.resize(nbw); P.bw.resize(3 * nbw);
+    for (long k = 0; k < nbw; k++) {
+        const EdgeNb& e = L.edges[L.nI + k];
+        P.bnode[k] = int(P.new_of_old[e.b]);
+        P.bkind[k] = uint8_t(k < L.nB ? 1 : 2);
+        P.bw[k] = e.x; P.bw[nbw + k] = e.y; P.bw[2 * nbw + k] = e.z;
+    }
+    P.adj_off.assign(P.npad + 1, 0);
+    for (long e = 0; e < L.nI; e++) { P.adj_off[P.ea[e] + 1]++; P.adj_off[P.eb[e] + 1]++; }
+    for (long i = 0; i < P.npad; i++) P.adj_off[i + 1] += P.adj_off[i];
+    P.adj_nbr.resize(2 * L.nI);
+    std::vector<int> adj_eid(2 * L.nI);
+    {
+        std::vector<long> pos(P.adj_off.begin(), P.adj_off.end() - 1);
+        for (long e = 0; e < L.nI; e++) {
+            const int a = P.ea[e], b = P.eb[e];
+            long pa = pos[a]++, pb = pos[b]++;
+            P.adj_nbr[pa] = b;                       adj_eid[pa] = int(e);
+            P.adj_nbr[pb] = int(uint32_t(a) | 0x80000000u); adj_eid[pb] = int(e);
+        }
+    }
+    P.adj_w.resize(3 * 2 * L.nI);
+    for (long k = 0; k < 2 * L.nI; k++) {
+        const long e = adj_eid[k];
+        P.adj_w[k] = P.ew[e]; P.adj_w[2 * L.nI + k] = P.ew[L.nI + e]; P.adj_w[4 * L.nI + k] = P.ew[2 * L.nI + e];
+    }
+    // boundary/wall edges per node (CSR, original order)
+    std::vector<long> bn_off(P.npad + 1, 0);
+    for (long k = 0; k < nbw; k++) bn_off[P.bnode[k] + 1]++;
+    for (long i = 0; i < P.npad; i++) bn_off[i + 1] += bn_off[i];
+    std::vector<long> bn_idx(nbw);
+    {
+        std::vector<long> pos(bn_off.begin(), bn_off.end() - 1);
+        for (long k = 0; k < nbw; k++) bn_idx[pos[P.bnode[k]]++] = k;
+    }
+
+    // ---- 3. tiles: halo lists, edge ownership, colour rounds -----------------------------------------
+    P.halo_off.assign(P.ntiles + 1, 0);
+    P.slot_off.assign(P.ntiles + 1, 0);
+    P.bslot_off.assign(P.ntiles + 1, 0);
+    P.tile_rounds.assign(P.ntiles, 0);
+    P.tile_brounds.assign(P.ntiles, 0);
+    struct Slot { int owner; int colour; int other; long e; bool owner_is_a; };
+    std::vector<Slot> slots;
+    std::vector<int> halo;
+    std::vector<Mask256> Lm(TN), Rm(TN);
+    std::vector<int> nassigned(TN);
+    std::vector<int> slot_eid;
+    std::vector<signed char> slot_sgn;
+    for (long t = 0; t < P.ntiles; t++) {
+        const long base = t * TN;
+        const int nown = P.tile_nown[t];
+        halo.clear();
+        for (int lu = 0; lu < nown; lu++)
+            for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++) {
+                const int v = P.adj_nbr[k] & 0x7fffffff;
+                if (v < base || v >= base + TN) halo.push_back(v);
+            }
+        std::sort(halo.begin(), halo.end());
+        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+        if (long(TN) + long(halo.size()) >= 0xFFFF) throw std::runtime_error("mgcfd: tile halo too large for 16-bit local ids");
+        P.halo_off[t + 1] = P.halo_off[t] + long(halo.size());
+        P.halo_ids.insert(P.halo_ids.end(), halo.begin(), halo.end());
+        P.max_halo = std::max(P.max_halo, int(halo.size()));
+
+        for (int i = 0; i < nown; i++) { Lm[i] = Mask256(); Rm[i] = Mask256(); nassigned[i] = 0; }
+        slots.clear();
+        // internal-to-tile edges first (visited from their `a` end, ascending edge index per node)
+        for (int lu = 0; lu < nown; lu++)
+            for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++) {
+                if (P.adj_nbr[k] < 0) continue;                   // this node is the `b` end: handled from `a`
+                const int v = P.adj_nbr[k];
+                if (v < base || v >= base + TN) continue;
+                const int lv = int(v - base);
+                const int c1 = Mask256::first_free(Lm[lu], Rm[lv]);   // lu computes, scatters into lv
+                const int c2 = Mask256::first_free(Lm[lv], Rm[lu]);
+                bool pick_u = c1 < c2 || (c1 == c2 && nassigned[lu] <= nassigned[lv]);
+                if (pick_u) { Lm[lu].set(c1); Rm[lv].set(c1); nassigned[lu]++; slots.push_back({lu, c1, lv, adj_eid[k], true}); }
+                else        { Lm[lv].set(c2); Rm[lu].set(c2); nassigned[lv]++; slots.push_back({lv, c2, lu, adj_eid[k], false}); }
+            }
+        // cut edges: computed by the owned end, the halo end is read-only
+        static const Mask256 none;
+        for (int lu = 0; lu < nown; lu++)
+            for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++) {
+                const int v = P.adj_nbr[k] & 0x7fffffff;
+                if (v >= base && v < base + TN) continue;
+                const int hl = int(std::lower_bound(halo.begin(), halo.end(), v) - halo.begin());
+                const int c = Mask256::first_free(Lm[lu], none);
+                Lm[lu].set(c); nassigned[lu]++;
+                slots.push_back({lu, c, int(TN) + hl, adj_eid[k], P.adj_nbr[k] >= 0});
+                P.cut_edges++;
+            }
+        int rounds = 0;
+        for (const Slot& s : slots) rounds = std::max(rounds, s.colour + 1);
+        P.tile_rounds[t] = rounds;
+        P.max_rounds = std::max(P.max_rounds, rounds);
+        const long s0 = P.slot_off[t];
+        P.slot_off[t + 1] = s0 + long(rounds) * TN;
+        P.slot_other.resize(P.slot_off[t + 1], 0xFFFF);
+        slot_eid.resize(P.slot_off[t + 1], -1);
+        slot_sgn.resize(P.slot_off[t + 1], 0);
+        for (const Slot& s : slots) {
+            const long si = s0 + long(s.colour) * TN + s.owner;
+            P.slot_other[si] = uint16_t(s.other);
+            slot_eid[si] = int(s.e);
+            slot_sgn[si] = s.owner_is_a ? 1 : -1;
+        }
+        P.used_slots += long(slots.size());
+        // boundary rounds
+        int br = 0;
+        for (int lu = 0; lu < nown; lu++) br = std::max<int>(br, int(bn_off[base + lu + 1] - bn_off[base + lu]));
+        P.tile_brounds[t] = br;
+        P.bslot_off[t + 1] = P.bslot_off[t] + long(br) * TN;
+    }
+    // weights: three planes over all slots, oriented thread-node -> other (negated when the thread node is the edge's `b`)
+    const long ns = P.slot_off[P.ntiles];
+    P.slot_w.assign(3 * ns, 0.0);
+    for (long si = 0; si < ns; si++) {
+        const long e = slot_eid[si];
+        if (e < 0) continue;
+        const double sg = double(slot_sgn[si]);
+        P.slot_w[si] = sg * P.ew[e];
+        P.slot_w[ns + si] = sg * P.ew[L.nI + e];
+        P.slot_w[2 * ns + si] = sg * P.ew[2 * L.nI + e];
+    }
+    const long nbs = P.bslot_off[P.ntiles];
+    P.bslot_kind.assign(nbs, 0);
+    P.bslot_w.assign(3 * nbs, 0.0);
+    for (long t = 0; t < P.ntiles; t++) {
+        const long base = t * TN;
+        for (int lu = 0; lu < P.tile_nown[t]; lu++) {
+            int r = 0;
+            for (long k = bn_off[base + lu]; k < bn_off[base + lu + 1]; k++, r++) {
+                const long bi = bn_idx[k];
+                const long si = P.bslot_off[t] + long(r) * TN + lu;
+                P.bslot_kind[si] = P.bkind[bi];
+                P.bslot_w[si] = P.bw[bi]; P.bslot_w[nbs + si] = P.bw[nbw + bi]; P.bslot_w[2 * nbs + si] = P.bw[2 * nbw + bi];
+            }
+        }
+    }
+}
+
+long check_colouring(const LevelPlan& P) {
+    long conflicts = 0;
+    const long TN = P.TN;
+    std::vector<int> seen(TN);
+    std::vector<long> edge_count;
+    long stored = 0;
+    for (long t = 0; t < P.ntiles; t++) {
+        for (int c = 0; c < P.tile_rounds[t]; c++) {
+            std::fill(seen.begin(), seen.end(), 0);
+            for (long lu = 0; lu < TN; lu++) {
+                const uint16_t o = P.slot_other[P.slot_off[t] + long(c) * TN + lu];
+                if (o == 0xFFFF) continue;
+                stored++;
+                if (lu >= P.tile_nown[t]) conflicts++;               // padding threads must own nothing
+                if (o < TN) { if (seen[o]++) conflicts++; if (o >= P.tile_nown[t]) conflicts++; }
+                else if (o - TN >= P.halo_off[t + 1] - P.halo_off[t]) conflicts++;
+            }
+        }
+    }
+    // coverage: every internal edge is stored once if both ends share a tile, twice otherwise
+    if (stored != P.nI + P.cut_edges / 2) conflicts += 1000000;
+    return conflicts;
+}
+
+void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const LevelPlan& Pf, const LevelPlan& Pc, TransferPlan& T) {
+    T = TransferPlan();
+    const long nf = fine.nel;
+    // restrict: stable counting sort of fine nodes (ascending original index) by coarse parent
+    T.child_off.assign(Pc.npad + 1, 0);
+    for (long i = 0; i < nf; i++) T.child_off[Pc.new_of_old[fine.mg[i]] + 1]++;
+    for (long i = 0; i < Pc.npad; i++) T.child_off[i + 1] += T.child_off[i];
+    T.child_ids.resize(nf);
+    {
+        std::vector<long> pos(T.child_off.begin(), T.child_off.end() - 1);
+        for (long i = 0; i < nf; i++) T.child_ids[pos[Pc.new_of_old[fine.mg[i]]]++] = int(Pf.new_of_old[i]);
+    }
+    // prolong
+    T.parent.assign(Pf.npad, -1);
+    T.idist_own.assign(Pf.npad, 0.0);
+    T.ent_off.assign(Pf.npad + 1, 0);
+    for (long i = 0; i < Pf.npad; i++) T.ent_off[i + 1] = T.ent_off[i] + (Pf.adj_off[i + 1] - Pf.adj_off[i]);
+    T.ent_src.resize(T.ent_off[Pf.npad]);
+    T.ent_w.resize(T.ent_off[Pf.npad]);
+    const double* cf = fine.coords.data();
+    const double* cc = coarse.coords.data();
+    auto idist = [](const double* x, const double* y) {
+        const double dx = x[0] - y[0], dy = x[1] - y[1], dz = x[2] - y[2];
+        return 1.0 / std::sqrt(dx * dx + dy * dy + dz * dz);
+    };
+    for (long id = 0; id < Pf.npad; id++) {
+        const long on = Pf.old_of_new[id];
+        if (on < 0) continue;
+        const long p = fine.mg[on];
+        T.parent[id] = int(Pc.new_of_old[p]);
+        const double dx = cf[3 * on] - cc[3 * p], dy = cf[3 * on + 1] - cc[3 * p + 1], dz = cf[3 * on + 2] - cc[3 * p + 2];
+        const bool coincident = (dx == 0.0 && dy == 0.0 && dz == 0.0);     // exact test, mg_loops.cpp:745,781
+        T.idist_own[id] = coincident ? -1.0 : 1.0 / std::sqrt(dx * dx + dy * dy + dz * dz);
+        for (long k = Pf.adj_off[id], o = T.ent_off[id]; k < Pf.adj_off[id + 1]; k++, o++) {
+            const bool node_is_b = Pf.adj_nbr[k] < 0;
+            const long om = Pf.old_of_new[Pf.adj_nbr[k] & 0x7fffffff];
+            const long q = fine.mg[om];
+            T.ent_w[o] = idist(&cc[3 * q], &cf[3 * on]);
+            // mg_loops.cpp:804-810: on the b side the neighbour-parent term multiplies residuals1[b1] (= own parent)
+            T.ent_src[o] = int(Pc.new_of_old[node_is_b ? p : q]);
+        }
+    }
+}
+
+}  // namespace mgcfd

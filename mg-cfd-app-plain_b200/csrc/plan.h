@@ -1,0 +1,69 @@
+// plan.h -- host-side integer preprocessing of one mesh level for the B200 kernels:
+// node renumbering (partition into tiles + RCM inside), per-tile halo lists, conflict-free edge colouring
+// (ELL rounds), CSR views for the deterministic sorted-segment mode, and the multigrid transfer operators.
+// The reference contains no renumbering or colouring code (SURVEY.md 8c "Integer work"): this host
+// implementation is the definition; tests check its invariants (bijection, tile coverage, colour validity)
+// and that un-permuted results equal the oracle's.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "host_mesh.h"
+
+namespace mgcfd {
+
+struct PlanOptions {
+    int ordering = 2;     // MGCFD_ORDER_*
+    int tile_nodes = 256; // owned nodes per tile (= CTA size of the tiled kernel)
+};
+
+struct LevelPlan {
+    long nel = 0, nI = 0, nB = 0, nW = 0;
+    int TN = 256;
+    long ntiles = 0, npad = 0;
+    std::vector<long> new_of_old;         // nel -> padded id
+    std::vector<long> old_of_new;         // npad -> old id or -1 (padding)
+    // ---- tiled, coloured flux structure -------------------------------------------------------
+    std::vector<int> tile_nown;           // owned nodes per tile
+    std::vector<long> halo_off;           // ntiles+1
+    std::vector<int> halo_ids;            // padded global ids, sorted per tile
+    std::vector<long> slot_off;           // ntiles+1, in slots (each tile: rounds*TN)
+    std::vector<int> tile_rounds;         // colour rounds per tile
+    std::vector<uint16_t> slot_other;     // local index of the other endpoint (<TN owned, >=TN halo), 0xFFFF empty
+    std::vector<double> slot_w;           // 3 planes [3][nslots]: edge vector oriented thread-node -> other
+    std::vector<long> bslot_off;          // ntiles+1
+    std::vector<int> tile_brounds;
+    std::vector<uint8_t> bslot_kind;      // 0 none, 1 boundary (-1), 2 wall (-2)
+    std::vector<double> bslot_w;          // [3][nbslots]
+    int max_halo = 0, max_rounds = 0;
+    long cut_edges = 0, used_slots = 0;
+    // ---- flat edge list in new numbering (atomic mode, indirect_rw, ordering sweeps) -------------
+    std::vector<int> ea, eb;              // internal edges, original edge order
+    std::vector<double> ew;               // [3][nI]
+    std::vector<int> bnode;               // boundary+wall edges: node, kind
+    std::vector<uint8_t> bkind;
+    std::vector<double> bw;               // [3][nB+nW]
+    // ---- CSR by node, original edge order (sorted-segment flux mode + prolong) -------------------
+    std::vector<long> adj_off;            // npad+1
+    std::vector<int> adj_nbr;             // neighbour padded id, bit31 set when this node is the edge's `b`
+    std::vector<double> adj_w;            // [3][2*nI] edge vector as stored (a->b)
+};
+
+void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P);
+long check_colouring(const LevelPlan& P);   // number of write conflicts (must be 0)
+
+// multigrid operators between level l (fine) and l+1 (coarse), in padded new ids of both
+struct TransferPlan {
+    // restrict: children of each coarse node in ascending ORIGINAL fine index (the reference's summation order)
+    std::vector<long> child_off;          // npad_c+1
+    std::vector<int> child_ids;           // fine padded ids
+    // prolong: per fine node, entries in ORIGINAL edge order
+    std::vector<int> parent;              // npad_f: own coarse parent (padded id), -1 for padding
+    std::vector<double> idist_own;        // npad_f: 1/dist(parent, node); -1.0 if coincident (exact ==)
+    std::vector<long> ent_off;            // npad_f+1
+    std::vector<int> ent_src;             // coarse padded id whose residual is multiplied (the b-side quirk is baked in)
+    std::vector<double> ent_w;            // 1/dist(parent of neighbour, node)
+};
+void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const LevelPlan& Pf, const LevelPlan& Pc, TransferPlan& T);
+
+}  // namespace mgcfd

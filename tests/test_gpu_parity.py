@@ -1,0 +1,219 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+Tolerance (north star): per variable, max|gpu - oracle| <= 1e-11 * max|oracle| for fp64 fields and RMS histories.
+Kernel-level checks are far tighter in practice (~1e-15); the assertions use 1e-12 there."""
+import numpy as np
+import pytest
+
+from conftest import linf_rel, mesh_levels, perturbed_state
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+KTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def M():
+    import mgcfd_b200 as M
+    return M
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle.loader import Oracle
+    return Oracle()
+
+
+MESHES = {
+    "hex3": dict(kind=0, dims=[[17, 17, 17], [9, 9, 9], [5, 5, 5]], variant=2),
+    "tet3": dict(kind=1, dims=[[13, 12, 11], [7, 7, 6], [4, 4, 4]], variant=2),
+    "hex_nonnested": dict(kind=0, dims=[[20, 18, 16], [13, 12, 11], [8, 7, 7], [5, 5, 4]], variant=2),
+    "fvcorr": dict(kind=2, dims=[[8, 7, 6]], variant=0),
+    "hex_random": dict(kind=0, dims=[[15, 14, 13], [8, 8, 7]], variant=3, ordering=1),
+}
+
+
+def make(M, name):
+    s = MESHES[name]
+    return M.Mesh.generate(s["kind"], s["dims"], mesh_variant=s["variant"], ordering=s.get("ordering", 0))
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("flux_mode", [0, 1, 2])
+def test_flux_kernels_match_oracle(M, oracle, name, flux_mode):
+    mesh = make(M, name)
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    s = M.Solver.from_mesh(mesh, flux_mode=flux_mode)
+    for l in range(mesh.levels):
+        L = lv[l]
+        var = perturbed_state(L["nel"], seed=100 + l)
+        s.set_field(l, M.FIELD_VARIABLES, var)
+        s.zero_fluxes(l)
+        want = np.zeros(5 * L["nel"])
+        s.compute_flux_edge(l)
+        oracle.flux_edge(0, L["nI"], L["edges"], var, want)
+        got = s.get_field(l, M.FIELD_FLUXES)
+        assert np.all(linf_rel(got, want) < KTOL), ("internal", l, linf_rel(got, want))
+        s.compute_boundary_flux_edge(l)
+        oracle.boundary_flux_edge(L["nI"], L["nB"], L["edges"], var, want)
+        s.compute_wall_flux_edge(l)
+        oracle.wall_flux_edge(L["nI"] + L["nB"], L["nW"], L["edges"], var, want)
+        got = s.get_field(l, M.FIELD_FLUXES)
+        assert np.all(linf_rel(got, want) < KTOL), ("all", l, linf_rel(got, want))
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["hex3", "fvcorr"])
+def test_node_kernels_match_oracle(M, oracle, name):
+    mesh = make(M, name)
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    s = M.Solver.from_mesh(mesh)
+    L = lv[0]
+    n = L["nel"]
+    var = perturbed_state(n, seed=7)
+    s.set_field(0, M.FIELD_VARIABLES, var)
+    for legacy in (False, True):
+        s.compute_step_factor(0, legacy)
+        got = s.get_field(0, M.FIELD_STEP_FACTORS)
+        want = oracle.step_factor(var, L["vol"], legacy)
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-14, legacy
+    # time_step
+    rng = np.random.default_rng(3)
+    flux = rng.standard_normal(5 * n)
+    old = perturbed_state(n, seed=8)
+    sf = oracle.step_factor(var, L["vol"], False)
+    for j in range(3):
+        s.set_field(0, M.FIELD_FLUXES, flux)
+        s.set_field(0, M.FIELD_OLD_VARIABLES, old)
+        s.set_field(0, M.FIELD_STEP_FACTORS, sf)
+        s.time_step(0, j)
+        f2, v2 = flux.copy(), np.zeros(5 * n)
+        oracle.time_step(j, sf, f2, old, v2)
+        assert np.all(linf_rel(s.get_field(0, M.FIELD_VARIABLES), v2) < 1e-15)
+        assert np.all(s.get_field(0, M.FIELD_FLUXES) == 0.0)
+    # residual + rms
+    s.set_field(0, M.FIELD_VARIABLES, var)
+    s.set_field(0, M.FIELD_OLD_VARIABLES, old)
+    s.residual(0)
+    res = oracle.residual(old, var)
+    assert np.array_equal(s.get_field(0, M.FIELD_RESIDUALS).reshape(-1), res)
+    ra, rv = s.calc_rms(0)
+    assert abs(ra - oracle.calc_rms(res)) / ra < 1e-13
+    assert np.max(np.abs(rv - oracle.rms_per_var(res)) / rv) < 1e-13
+    # copy + validity
+    s.copy_old_variables(0)
+    assert np.array_equal(s.get_field(0, M.FIELD_OLD_VARIABLES).reshape(-1), var)
+    assert s.check_for_invalid_variables(0) is None
+    bad = var.copy()
+    bad[5 * 11 + 4] = -1.0
+    bad[5 * 40 + 2] = np.nan
+    bad[5 * 90 + 0] = -2.0
+    s.set_field(0, M.FIELD_VARIABLES, bad)
+    assert s.check_for_invalid_variables(0) == oracle.check_invalid(bad) == (11, 3)
+    s.close()
+
+
+@pytest.mark.parametrize("name", ["hex3", "tet3", "hex_nonnested", "hex_random"])
+def test_mg_transfers_match_oracle(M, oracle, name):
+    mesh = make(M, name)
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    s = M.Solver.from_mesh(mesh)
+    rng = np.random.default_rng(5)
+    for l in range(mesh.levels - 1):
+        F, Cc = lv[l], lv[l + 1]
+        vf = perturbed_state(F["nel"], seed=20 + l)
+        vc = perturbed_state(Cc["nel"], seed=30 + l)
+        s.set_field(l, M.FIELD_VARIABLES, vf)
+        s.set_field(l + 1, M.FIELD_VARIABLES, vc)
+        s.mg_restrict(l + 1)
+        want = vc.copy()
+        oracle.mg_restrict(vf, want, F["map"])
+        # restrict sums children in the reference's order: bit-exact
+        assert np.array_equal(s.get_field(l + 1, M.FIELD_VARIABLES).reshape(-1), want)
+        r1 = 1e-3 * rng.standard_normal(5 * Cc["nel"])
+        r2 = 1e-3 * rng.standard_normal(5 * F["nel"])
+        s.set_field(l + 1, M.FIELD_RESIDUALS, r1)
+        s.set_field(l, M.FIELD_RESIDUALS, r2)
+        s.set_field(l, M.FIELD_VARIABLES, vf)
+        s.prolong(l)
+        want = vf.copy()
+        oracle.prolong(F["edges"], F["nI"], r1, r2, want, F["map"], Cc["coords"], F["coords"])
+        assert np.all(linf_rel(s.get_field(l, M.FIELD_VARIABLES), want) < 1e-14)
+    s.close()
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+@pytest.mark.parametrize("graph", [True, False])
+def test_cycles_match_oracle(M, oracle, name, graph):
+    cycles = 12
+    mesh = make(M, name)
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    ora, orv, st = oracle.run_cycles(mesh.mesh_variant, lv, cycles)
+    s = M.Solver.from_mesh(mesh, use_graph=graph)
+    ra, rv = s.run_cycles(cycles)
+    assert np.max(np.abs(ra - ora) / ora) < TOL
+    assert np.max(np.abs(rv - orv) / np.maximum(orv, 1e-300)) < TOL
+    for l in range(mesh.levels):
+        assert np.all(linf_rel(s.get_field(l, M.FIELD_VARIABLES), st[l]["var"]) < TOL), l
+    assert np.all(linf_rel(s.get_field(0, M.FIELD_RESIDUALS), st[0]["res"]) < 1e-9)
+    # split calls continue the same trajectory (buffer roles / graph cache are consistent)
+    s2 = M.Solver.from_mesh(make(M, name), use_graph=graph)
+    a1, _ = s2.run_cycles(5)
+    a2, _ = s2.run_cycles(cycles - 5)
+    assert np.array_equal(np.concatenate([a1, a2]), ra)
+    assert np.array_equal(s2.get_field(0, M.FIELD_VARIABLES), s.get_field(0, M.FIELD_VARIABLES))
+    s.close(); s2.close()
+
+
+@pytest.mark.parametrize("flux_mode", [0, 1, 2])
+def test_granular_api_matches_oracle(M, oracle, flux_mode):
+    from mgcfd_b200 import run_cycles_granular
+    cycles = 4
+    mesh = make(M, "hex_nonnested")
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    ora, orv, st = oracle.run_cycles(mesh.mesh_variant, lv, cycles)
+    s = M.Solver.from_mesh(mesh, flux_mode=flux_mode)
+    ra, rv = run_cycles_granular(s, cycles)
+    assert np.max(np.abs(ra - ora) / ora) < TOL
+    for l in range(mesh.levels):
+        assert np.all(linf_rel(s.get_field(l, M.FIELD_VARIABLES), st[l]["var"]) < TOL)
+    s.close()
+
+
+def test_tiled_mode_is_deterministic_and_orderings_agree(M, oracle):
+    mesh = make(M, "tet3")
+    outs = []
+    for ordering in (0, 1, 2, 2):
+        s = M.Solver.from_mesh(make(M, "tet3"), ordering=ordering)
+        s.run_cycles(6)
+        outs.append(s.get_field(0, M.FIELD_VARIABLES).copy())
+        s.close()
+    assert np.array_equal(outs[2], outs[3])            # bit-reproducible run to run
+    for o in outs[:2]:
+        assert np.all(linf_rel(o, outs[2]) < TOL)      # renumbering only changes summation order
+
+
+@pytest.mark.parametrize("tile_nodes", [128, 256, 512])
+def test_tile_sizes(M, oracle, tile_nodes):
+    mesh = make(M, "hex3")
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    ora, orv, st = oracle.run_cycles(mesh.mesh_variant, lv, 5)
+    s = M.Solver.from_mesh(mesh, tile_nodes=tile_nodes)
+    assert s.check_colouring(0) == 0
+    ra, _ = s.run_cycles(5)
+    assert np.max(np.abs(ra - ora) / ora) < TOL
+    assert np.all(linf_rel(s.get_field(0, M.FIELD_VARIABLES), st[0]["var"]) < TOL)
+    s.close()
+
+
+def test_invalid_state_is_reported(M):
+    mesh = make(M, "hex3")
+    s = M.Solver.from_mesh(mesh)
+    n = mesh.dims(0)[0]
+    var = s.get_field(0, M.FIELD_VARIABLES).copy().reshape(-1)
+    var[5 * 17 + 0] = np.nan
+    s.set_field(0, M.FIELD_VARIABLES, var)
+    with pytest.raises(M.MgcfdError) as e:
+        s.run_cycles(1)
+    assert e.value.code == 3
+    s.close()

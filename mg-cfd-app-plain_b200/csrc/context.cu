@@ -210,7 +210,7 @@ int step_factor(mgcfd_ctx* c, int l, int legacy) {
     Timed tm(c, K_STEP, l, v.nel);
     const unsigned nb = (unsigned)blocks_for(v.npad, 256);
     if (legacy) {
-        k_step_factor<true><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.vol_root, v.sf, c->d_minbits);
+        k_step_factor<true><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.vol, v.sf, c->d_minbits);
         CKRC(post_launch(c));
     } else {
         CK(cudaMemsetAsync(c->d_minbits, 0x7F, sizeof(unsigned long long), c->stream));
@@ -458,13 +458,11 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         CK(cudaMalloc((void**)&v.sf, sizeof(double) * v.npad));
         // volumes in new order; padding: volume 1, root +inf so that padded nodes never win the min-dt reduction
         std::vector<double> vol(v.npad, 1.0), root(v.npad, INFINITY);
-        const bool legacy = (c->variant == MGCFD_MESH_FVCORR);
         for (long i = 0; i < v.nel; i++) {
             const long g = P.new_of_old[i];
             vol[g] = v.host.volumes[i];
-            root[g] = legacy ? sqrt(v.host.volumes[i]) : cbrt(v.host.volumes[i]);   // host libm, as the reference (cfd_loops.cpp:60,:123)
+            root[g] = cbrt(v.host.volumes[i]);   // host libm cbrt, as the reference (cfd_loops.cpp:123); cbrt is not correctly rounded anywhere
         }
-        if (legacy) for (long g = 0; g < v.npad; g++) if (P.old_of_new[g] < 0) root[g] = 1.0;
         CKRC(dev_upload(&v.vol, vol, s)); CKRC(dev_upload(&v.vol_root, root, s));
         std::vector<int> n2o(P.old_of_new.begin(), P.old_of_new.end()), o2n(P.new_of_old.begin(), P.new_of_old.end());
         CKRC(dev_upload(&v.old_of_new, n2o, s)); CKRC(dev_upload(&v.new_of_old, o2n, s));

@@ -234,7 +234,7 @@ __global__ void k_step_factor(const double* __restrict__ v, long stride, long n,
         double vx, vy, vz, p, speed, sos;
         derive(v[i], v[stride + i], v[2 * stride + i], v[3 * stride + i], v[4 * stride + i], vx, vy, vz, p, speed, sos);
         if (LEGACY) {
-            sf[i] = double(0.5) / (vol_root[i] * (speed + sos));      // vol_root = sqrt(volume), cfd_loops.cpp:60
+            sf[i] = double(0.5) / (sqrt(vol_root[i]) * (speed + sos));   // vol_root = volumes here; IEEE sqrt, cfd_loops.cpp:60
         } else {
             const double dt = vol_root[i] / (speed + sos);           // vol_root = cbrt(volume) (host glibc), :123
             val = 0.5 * dt;

@@ -269,11 +269,13 @@ void apply_ewt(int mesh_variant, const double* coords, long ne, EdgeNb* edges) {
     for (long i = 0; i < ne; i++) {
         EdgeNb& e = edges[i];
         if (e.a >= 0 && e.b >= 0) {
-            // same accumulation order as adjust_ewt (validation.cpp:41-48)
-            double dist = 0.0, d;
-            d = coords[3 * e.b + 0] - coords[3 * e.a + 0]; dist += d * d;
-            d = coords[3 * e.b + 1] - coords[3 * e.a + 1]; dist += d * d;
-            d = coords[3 * e.b + 2] - coords[3 * e.a + 2]; dist += d * d;
+            // same accumulation order as adjust_ewt (validation.cpp:41-48).  The reference's own build (gcc, default
+            // -ffp-contract=fast, -march=native on any FMA host; Makefile:95-108) contracts `dist += d*d` into an fma:
+            // spelled out here so that the weights every kernel consumes are bit-identical to the reference's
+            double dist, d;
+            d = coords[3 * e.b + 0] - coords[3 * e.a + 0]; dist = d * d;
+            d = coords[3 * e.b + 1] - coords[3 * e.a + 1]; dist = std::fma(d, d, dist);
+            d = coords[3 * e.b + 2] - coords[3 * e.a + 2]; dist = std::fma(d, d, dist);
             dist = std::sqrt(dist);
             e.x /= dist; e.y /= dist; e.z /= dist;
         }

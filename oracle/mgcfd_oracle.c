@@ -74,8 +74,10 @@ void orc_adjust_dampen(int variant, const double* coords, long ne, orc_edge* e) 
     if (damp == 0.0) return;
     for (long i = 0; i < ne; i++) {
         if (e[i].a >= 0 && e[i].b >= 0) {
+            /* `dist += d*d` three times; the reference's build contracts the 2nd and 3rd into fma (gcc -ffp-contract=fast on
+             * an FMA host, Makefile:95-108) -- written explicitly because this file is compiled with -ffp-contract=off */
             double dist = 0.0;
-            for (int d = 0; d < 3; d++) { const double t = coords[3 * e[i].b + d] - coords[3 * e[i].a + d]; dist += t * t; }
+            for (int d = 0; d < 3; d++) { const double t = coords[3 * e[i].b + d] - coords[3 * e[i].a + d]; dist = d ? fma(t, t, dist) : t * t; }
             dist = sqrt(dist);
             e[i].x /= dist; e[i].y /= dist; e[i].z /= dist;
         }

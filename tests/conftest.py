@@ -48,3 +48,30 @@ def perturbed_state(nel, seed):
     var[:, 3] = 0.03 * np.cos(3 * x)
     var[:, 4] *= 1.0 + 0.04 * np.sin(2 * x + 1.0)
     return np.ascontiguousarray(var.reshape(-1))
+
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN_CASES = ("hex3_m6wing", "tet2_cascade", "hex4_nonnested_rotor", "fvcorr_cells", "hex2_random_m6wing")
+# generator arguments of every golden case (tests/golden/make_golden.py): kind, dims, ordering
+GOLDEN_SPECS = {
+    "hex3_m6wing": (0, [[9, 9, 9], [5, 5, 5], [3, 3, 3]], 0),
+    "tet2_cascade": (1, [[7, 6, 5], [4, 4, 3]], 0),
+    "hex4_nonnested_rotor": (0, [[10, 9, 8], [7, 6, 6], [5, 4, 4], [3, 3, 3]], 0),
+    "fvcorr_cells": (2, [[4, 3, 3]], 0),
+    "hex2_random_m6wing": (0, [[8, 7, 6], [4, 4, 3]], 1),
+}
+
+
+def load_golden(name):
+    """A tests/golden fixture (outputs of the unmodified reference, see make_golden.py) as
+    (dict of arrays, raw levels, levels with the reference's adjusted edge weights)."""
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    raw, adj = [], []
+    for l in range(int(g["levels"])):
+        lv = dict(nel=int(g[f"L{l}_nel"]), nI=int(g[f"L{l}_nI"]), nB=int(g[f"L{l}_nB"]), nW=int(g[f"L{l}_nW"]),
+                  vol=g[f"L{l}_vol"], edges=g[f"L{l}_edges"], coords=g.get(f"L{l}_coords"), map=g.get(f"L{l}_map"))
+        raw.append(lv)
+        a = dict(lv)
+        a["edges"] = g[f"L{l}_ewt_edges"]
+        adj.append(a)
+    return g, raw, adj

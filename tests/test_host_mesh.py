@@ -1,0 +1,154 @@
+"""Host-side code (no GPU): the synthetic generators, the reference's mesh interchange formats, and the integer
+preprocessing (renumbering, tiling, colouring).  Integer work is checked bit-exactly: edge lists and MG
+maps must equal what the reference's read_grid / read_mg_connectivity produce from the same files."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import mgcfd_b200 as M
+from conftest import GOLDEN_CASES, GOLDEN_SPECS, load_golden, mesh_levels
+from oracle.loader import HERE as ORACLE_DIR
+from oracle.loader import Reference, reference_available
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_generator_is_deterministic_and_matches_fixture_mesh(name):
+    g, raw, adj = load_golden(name)
+    kind, dims, ordering = GOLDEN_SPECS[name]
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=int(g["variant"]), ordering=ordering)
+    lv = mesh_levels(mesh)
+    assert len(lv) == len(raw)
+    for a, b in zip(lv, raw):
+        assert (a["nel"], a["nI"], a["nB"], a["nW"]) == (b["nel"], b["nI"], b["nB"], b["nW"])
+        assert a["edges"].tobytes() == b["edges"].tobytes()
+        assert np.array_equal(a["vol"], b["vol"])
+        if b["coords"] is not None:
+            assert np.array_equal(a["coords"], b["coords"])
+        if b["map"] is not None:
+            assert np.array_equal(a["map"], b["map"])
+    # adjust_ewt + dampen_ewt on the host mesh == the reference's (bit for bit)
+    mesh.apply_ewt()
+    for l, a in enumerate(adj):
+        assert mesh.edges(l).tobytes() == a["edges"].tobytes()
+
+
+def test_mesh_structure_invariants():
+    """constraints the reference's loader and kernels rely on."""
+    for kind, dims in ((0, [[9, 8, 7], [5, 4, 4]]), (1, [[6, 6, 5], [3, 3, 3]]), (2, [[3, 3, 2]])):
+        mesh = M.Mesh.generate(kind, dims, mesh_variant=0 if kind == 2 else 2)
+        for l in range(mesh.levels):
+            nel, nI, nB, nW, mgc = mesh.dims(l)
+            e = mesh.edges(l)
+            assert np.all(e["a"][:nI] >= 0) and np.all(e["a"][:nI] < e["b"][:nI]) and np.all(e["b"] < nel)
+            assert np.all(e["a"][nI:nI + nB] == -1) and np.all(e["a"][nI + nB:] == -2)
+            deg = np.bincount(np.concatenate([e["a"][:nI], e["b"][:nI]]), minlength=nel)
+            assert deg.min() >= 1                       # prolong divides by the weight sum of internal edges
+            assert np.all(mesh.volumes(l) > 0)
+            if l + 1 < mesh.levels:
+                assert mgc == nel
+                assert mesh.mg_map(l).min() >= 0 and mesh.mg_map(l).max() < mesh.dims(l + 1)[0]
+        # closed control volumes: the signed face vectors around every node sum to ~0 (raw weights)
+        nel, nI, nB, nW, _ = mesh.dims(0)
+        e = mesh.edges(0)
+        s = np.zeros((nel, 3))
+        w = np.stack([e["x"], e["y"], e["z"]], axis=1)
+        np.add.at(s, e["a"][:nI], w[:nI])
+        np.add.at(s, e["b"][:nI], -w[:nI])
+        if kind != 2:                                    # boundary weights are inward for non-fvcorr meshes
+            np.add.at(s, e["b"][nI:], -w[nI:])
+            tilt = np.abs(s).max()
+            assert tilt < 0.06 * np.abs(w).max()         # only the tilted wall patch is not closed
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_write_then_load_round_trip(tmp_path, binary):
+    mesh = M.Mesh.generate(M.GEN_HEX_BOX, [[8, 7, 6], [4, 4, 3], [2, 2, 2]], mesh_variant=M.MESH_ROTOR_37)
+    mesh.write(str(tmp_path), "input.dat", binary=binary)
+    if binary:                                           # the .bin cache is preferred: remove the text so it has to be used
+        for f in os.listdir(tmp_path):
+            if not f.endswith((".bin", ".dat")):
+                os.remove(tmp_path / f)
+    back = M.Mesh.load("input.dat", str(tmp_path))
+    assert back.levels == mesh.levels and back.mesh_variant == mesh.mesh_variant
+    for a, b in zip(mesh_levels(mesh), mesh_levels(back)):
+        assert (a["nel"], a["nI"], a["nB"], a["nW"]) == (b["nel"], b["nI"], b["nB"], b["nW"])
+        assert a["edges"].tobytes() == b["edges"].tobytes()
+        assert np.array_equal(a["vol"], b["vol"]) and np.array_equal(a["coords"], b["coords"])
+        assert (a["map"] is None and b["map"] is None) or np.array_equal(a["map"], b["map"])
+
+
+def test_load_errors_are_reported(tmp_path):
+    with pytest.raises(M.MgcfdError):
+        M.Mesh.load("does-not-exist.dat", str(tmp_path))
+    (tmp_path / "input.dat").write_text("size = 1\nnum_levels = 1\nmesh_name = m6wing\n[levels]\n0 = missing.mesh\n")
+    with pytest.raises(M.MgcfdError):
+        M.Mesh.load("input.dat", str(tmp_path))
+
+
+@pytest.mark.skipif(not reference_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kind,dims,variant", [(0, [[7, 6, 5], [4, 3, 3]], 2), (1, [[5, 5, 4], [3, 3, 2]], 3), (2, [[3, 3, 2]], 0)])
+def test_files_read_by_the_reference_loader_give_our_arrays(tmp_path, kind, dims, variant):
+    """our writer -> the reference's read_input_dat / read_grid / read_mg_connectivity (io.cpp:14-199,
+    io_enhanced.cpp:407-650) -> identical in-memory arrays (edge order, orientation, sign flips, classes)."""
+    ref = Reference()
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+    mesh.write(str(tmp_path), "input.dat")
+    info = ref.read_input_dat(str(tmp_path / "input.dat"))
+    assert info["levels"] == mesh.levels and info["variant"] == variant
+    for l, a in enumerate(mesh_levels(mesh)):
+        r = ref.read_grid(str(tmp_path / info["layers"][l]), mesh.levels, variant)
+        assert (r["nel"], r["nI"], r["nB"], r["nW"]) == (a["nel"], a["nI"], a["nB"], a["nW"])
+        assert r["edges"].tobytes() == a["edges"].tobytes()
+        assert np.array_equal(r["vol"], a["vol"])
+        if mesh.levels > 1:
+            assert np.array_equal(r["coords"], a["coords"])
+        if l + 1 < mesh.levels:
+            assert np.array_equal(ref.read_mg(str(tmp_path / info["mg"][l])), a["map"])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ORACLE_DIR, "_ref", "euler3d_ref.b")), reason="reference binary not built")
+def test_reference_binary_runs_our_files_and_matches_oracle(tmp_path):
+    """the reference's own main() on files we wrote: its printed RMS history equals the oracle's to print precision."""
+    from oracle.loader import Oracle
+    mesh = M.Mesh.generate(M.GEN_HEX_BOX, [[9, 9, 9], [5, 5, 5], [3, 3, 3]], mesh_variant=M.MESH_M6_WING)
+    mesh.write(str(tmp_path), "input.dat")
+    exe = os.path.join(ORACLE_DIR, "_ref", "euler3d_ref.b")
+    out = subprocess.run([exe, "-i", "input.dat", "-d", str(tmp_path) + "/", "-g", "4", "-o", str(tmp_path) + "/", "--output-variables"],
+                         capture_output=True, text=True, cwd=tmp_path, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rms = [float(line.split("RMS =")[1].split(")")[0]) for line in out.stdout.splitlines() if "RMS =" in line]
+    orc = Oracle()
+    oa, _, st = orc.run_cycles(mesh.mesh_variant, mesh_levels(mesh, apply_ewt_with=orc), 4)
+    assert len(rms) == 4 and np.allclose(rms, oa, rtol=6e-4)        # printed with %.3e
+    dump = [f for f in os.listdir(tmp_path) if f.startswith("variables")]
+    if dump:
+        vals = np.loadtxt(tmp_path / dump[0], skiprows=1).reshape(-1)
+        if vals.size == st[0]["var"].size:
+            assert np.max(np.abs(vals - st[0]["var"])) < 1e-13
+
+
+@pytest.mark.parametrize("kind,dims", [(0, [[21, 20, 19]]), (1, [[14, 13, 12]]), (2, [[6, 5, 5]])])
+@pytest.mark.parametrize("ordering", [M.ORDER_AS_GIVEN, M.ORDER_RCM, M.ORDER_PARTITION_RCM])
+@pytest.mark.parametrize("tile_nodes", [128, 256])
+def test_plan_invariants(kind, dims, ordering, tile_nodes):
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=0 if kind == 2 else 2)
+    info, perm, conflicts = M.plan_level(mesh, 0, ordering=ordering, tile_nodes=tile_nodes)
+    nel, nI = info["nel"], info["nI"]
+    assert conflicts == 0                                             # no two edges of a round write one node
+    assert len(np.unique(perm)) == nel and perm.min() >= 0 and perm.max() < info["npad"]      # injective renumbering
+    assert info["npad"] == info["ntiles"] * tile_nodes and info["npad"] - nel < tile_nodes * max(1, info["ntiles"] // 8 + 1)
+    assert info["used_slots"] == nI + info["cut_edges"]               # inside edges once, cut edges from both sides
+    # determinism: the plan is a pure function of the mesh
+    info2, perm2, _ = M.plan_level(mesh, 0, ordering=ordering, tile_nodes=tile_nodes)
+    assert info2 == info and np.array_equal(perm, perm2)
+
+
+def test_partition_rcm_improves_locality_on_a_shuffled_mesh():
+    shuffled = M.Mesh.generate(M.GEN_HEX_BOX, [[24, 24, 24]], ordering=1, seed=7)
+    as_given, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_AS_GIVEN)
+    rcm, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_RCM)
+    part, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_PARTITION_RCM)
+    assert part["cut_edges"] < rcm["cut_edges"] < as_given["cut_edges"]
+    assert part["halo_entries"] < 0.5 * as_given["halo_entries"]

@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the MG-CFD per-cycle solver loop on B200 (and of the reference CPU solver beside it).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c2|c1|c3|c3s|tiny] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A STEP is one multigrid V-cycle of main()'s loop (src/euler3d_cpu_double.cpp:371-694) over the whole mesh: for a
+4-level mesh 6 smoothing visits (step factor, 3 Runge-Kutta stages of flux + boundary/wall flux + time_step, residual),
+3 restrictions and 3 prolongations.  The unit of work is one internal-edge flux evaluation ("flux edge-update"):
+a cycle performs  sum_l E_I(l) * RK(3) * visits(l)  of them (BASELINE.json metric).
+
+  value  = edge-updates of all ranks / device time of the K timed cycles (CUDA events on the solver's own stream,
+           state resident in HBM, L2 flushed before every timed cycle, max over ranks)
+  e2e    = the same metric through the public API with HOST buffers: every step copies level-0 `variables` from pinned
+           host memory (set_field), runs one cycle (run_cycles -> RMS back), and reads `variables` back (get_field)
+  roofline = the dominant kernel (the fused flux + time_step stage on level 0): algorithmic bytes per launch
+           (32*E_I + 28*(E_B+E_W) + 128*N) / its mean launch duration, measured with CUDA events around every
+           launch in a second pass over the same K cycles; peak = MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline = the UNMODIFIED reference (oracle/_ref/libmgcfd_ref_omp.so: its own sources built -DOMP -DOMP_SCATTERS)
+           on the host cores, mesh duplicated once per thread as its assess-memory protocol does (gen_job.py:360-365)
+
+`--impl reference` times that reference build alone (all host threads) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RK = 3
+WORKLOADS = {
+    # name: (generator kind, per-level node dims, mesh variant, description)
+    "c2": (0, [[67] * 3, [55] * 3, [48] * 3, [43] * 3], 2,
+           "C2: Onera-M6-shaped 4-level multigrid, hex-dual box 300763/166375/110592/79507 nodes, 888822 fine internal edges, mesh_name=m6wing"),
+    "c1": (2, [[26, 25, 25]], 0, "C1: fvcorr.domn.097K-shaped single level, 97500 cell-centred tets, mesh_name=fvcorr"),
+    "c3": (1, [[201] * 3, [101] * 3, [51] * 3, [26] * 3], 2, "C3: 8.1M-node Kuhn-tet box, 4 levels, 56.4M fine internal edges, mesh_name=m6wing"),
+    "c3s": (1, [[129] * 3, [65] * 3, [33] * 3, [17] * 3], 2, "2.1M-node Kuhn-tet box, 4 levels (reduced C3)"),
+    "tiny": (0, [[21, 19, 17], [11, 10, 9], [6, 5, 5]], 2, "tiny 3-level hex box (smoke)"),
+}
+
+
+def visits(level, levels):
+    return 1 if (levels == 1 or level == 0 or level == levels - 1) else 2
+
+
+def units_per_cycle(dims):
+    nl = len(dims)
+    return sum(d[1] * RK * visits(l, nl) for l, d in enumerate(dims))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def reference_cpu_run(workload, steps, warmup, threads):
+    """The unmodified reference on `threads` host threads over `threads` copies of the mesh (its OMP_SCATTERS protocol).
+    Returns (edge-updates/s aggregated over the copies, seconds per step, kind, description)."""
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    import mgcfd_b200 as M
+    from oracle.loader import Oracle, Reference, reference_available
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from conftest import mesh_levels
+    kind, dims, variant, desc = WORKLOADS[workload]
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+    units = units_per_cycle([mesh.dims(l) for l in range(mesh.levels)])
+    if reference_available(omp=True):
+        ref = Reference(omp=True)
+        t = ref.threads()
+        sess = ref.session(variant, mesh_levels(mesh))
+        if t > 1:
+            sess.duplicate(t)
+        sess.prepare()
+        if warmup:
+            sess.run(warmup)
+        _, _, secs = sess.run(steps)
+        sess.close()
+        return t * units * steps / secs, secs / steps, "reference", t, \
+            f"{steps} V-cycle(s) (+{warmup} warm-up) of {workload} duplicated x{t} (one copy per thread, -DOMP -DOMP_SCATTERS, -DPRECISE_FP), oracle/_ref/libmgcfd_ref_omp.so"
+    orc = Oracle()                      # scalar port, 1 thread
+    lv = mesh_levels(mesh, apply_ewt_with=orc)
+    if warmup:
+        orc.run_cycles(variant, lv, warmup)
+    t0 = time.perf_counter()
+    orc.run_cycles(variant, lv, steps)
+    secs = time.perf_counter() - t0
+    return units * steps / secs, secs / steps, "port", 1, f"{steps} V-cycle(s) of {workload}, oracle/libmgcfd_oracle.so (scalar C port), 1 thread"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--flux-mode", type=int, default=None)
+    ap.add_argument("--tile-nodes", type=int, default=None)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    kind, dims, variant, desc = WORKLOADS[args.workload]
+    W = max(args.warmup, 0)
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        thr = host_threads()
+        v, spstep, kindname, cores, sample = reference_cpu_run(args.workload, args.steps, W, thr)
+        print(json.dumps({
+            "impl": "reference", "metric": "flux edge-updates/s", "value": v, "unit": "edge-updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": W, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "step": "one V-cycle", "note": "CPU only; the mesh is duplicated once per host thread"},
+            "cpu_baseline": {"value": v, "unit": "edge-updates/s", "cores": cores, "kind": kindname, "sample": sample},
+            "e2e": {"value": v, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ------------------------------------------------------------------ B200 arm
+    import numpy as np
+    import torch
+    import mgcfd_b200 as M
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; mgcfd_b200 has no CPU fallback (use --impl reference for the CPU solver)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+    ldims = [mesh.dims(l) for l in range(mesh.levels)]
+    units = units_per_cycle(ldims)
+    kw = {}
+    if args.flux_mode is not None:
+        kw["flux_mode"] = args.flux_mode
+    if args.tile_nodes is not None:
+        kw["tile_nodes"] = args.tile_nodes
+    t0 = time.perf_counter()
+    s = M.Solver.from_mesh(mesh, device=local, **kw)
+    setup_s = time.perf_counter() - t0
+    stream = torch.cuda.ExternalStream(s.cuda_stream(), device=local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")      # > 126 MB of L2
+    K = args.steps
+
+    def timed_pass():
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        l0 = s.launch_count()
+        barrier()
+        with torch.cuda.stream(stream):
+            for a, b in ev:
+                flush.zero_()
+                a.record(stream)
+                s.enqueue_cycles(1)
+                b.record(stream)
+        ra, _ = s.collect()
+        barrier()
+        return sum(a.elapsed_time(b) for a, b in ev), s.launch_count() - l0, ra
+
+    s.run_cycles(W)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches, rms = timed_pass()
+    # second pass, same K cycles, every kernel bracketed by its own CUDA events (graphs bypassed): per-kernel durations
+    s.set_timing(True)
+    s.reset_times()
+    s.run_cycles(2)
+    s.reset_times()
+    ms_total_timed, _, _ = timed_pass()
+    t_ms, t_it = s.times()
+    s.set_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # e2e: host buffers through the public API
+    n0 = ldims[0][0]
+    host_in = torch.empty(5 * n0, dtype=torch.float64).pin_memory()
+    host_out = torch.empty(5 * n0, dtype=torch.float64).pin_memory()
+    host_in.numpy()[:] = s.get_field(0, M.FIELD_VARIABLES).reshape(-1)
+    e2e_steps = max(3, min(K, 20))
+    for _ in range(2):
+        s.set_field(0, M.FIELD_VARIABLES, host_in.numpy()); s.run_cycles(1); s.get_field(0, M.FIELD_VARIABLES, out=host_out.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        s.set_field(0, M.FIELD_VARIABLES, host_in.numpy())
+        s.run_cycles(1)
+        s.get_field(0, M.FIELD_VARIABLES, out=host_out.numpy())
+        host_in, host_out = host_out, host_in
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    if dist is not None:
+        t = torch.tensor([ms_total, e2e_s, ms_total_timed], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s, ms_total_timed = t.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    nl = mesh.levels
+    info0 = s.level_info(0)
+    nel, nI, nB, nW = ldims[0][:4]
+    flux_ms0, flux_it0 = float(t_ms[1, 0]), int(t_it[1, 0])
+    flux_launches0 = flux_it0 // max(nI, 1)
+    peak, peak_src = measured_peak()
+    alg_bytes = 32 * nI + 28 * (nB + nW) + 128 * nel
+    avg_launch_ms = flux_ms0 / max(flux_launches0, 1)
+    achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    per_level = {}
+    for l in range(nl):
+        if t_ms[1, l] > 0:
+            per_level[f"L{l}"] = float(t_it[1, l]) / (float(t_ms[1, l]) * 1e-3)
+    kernel_share = {name: float(t_ms[k].sum()) for k, name in enumerate(M.KERNEL_NAMES) if t_ms[k].sum() > 0}
+    out = {
+        "metric": "flux edge-updates/s", "value": world * units * K / (ms_total * 1e-3), "unit": "edge-updates/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "step": "one V-cycle (euler3d_cpu_double.cpp:371-694), all levels",
+                   "edge_updates_per_step": units, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
+                   "l2": "256 MiB buffer written before every timed cycle (L2 flush)", "flux_mode": int(kw.get("flux_mode", 0)),
+                   "tile_nodes": int(info0["tile_nodes"]), "setup_s": round(setup_s, 2)},
+        "mg_cycles_per_sec": world * K / (ms_total * 1e-3),
+        "flux_edge_updates_per_sec_by_level": per_level,
+        "kernel_ms_timed_pass": kernel_share, "ms_per_step_timed_pass": ms_total_timed / K,
+        "final_rms": float(rms[-1]) if len(rms) else None,
+        "roofline": {"bound": "hbm", "kernel": "k_tile_flux<fused> level 0 (flux + boundary + wall flux + time_step)", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_launch_ms * 1e3, "launches_timed": flux_launches0,
+                     "edge_updates_per_sec": nI / (avg_launch_ms * 1e-3) if avg_launch_ms > 0 else 0.0},
+        "e2e": {"value": world * units * e2e_steps / e2e_s, "unit": "edge-updates/s", "h2d_bytes_per_step": 40 * n0, "d2h_bytes_per_step": 40 * n0 + 48,
+                "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                "path": "Solver.set_field(pinned host) -> Solver.run_cycles(1) -> Solver.get_field(pinned host), C ABI mgcfd_set_field/mgcfd_run_cycles/mgcfd_get_field"},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    s.close()
+    del flush
+    if not args.no_cpu_baseline:
+        try:
+            # in a fresh process: the OpenMP runtime must see OMP_NUM_THREADS before it starts, and torch has started it here
+            env = dict(os.environ)
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                env.pop(k, None)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps",
+                                str(args.cpu_baseline_steps), "--warmup", "1"], capture_output=True, text=True, env=env, timeout=900)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+            cb = json.loads(line)
+            out["cpu_baseline"] = dict(cb["cpu_baseline"], ms_per_step=cb["ms_per_step"])
+        except Exception as e:  # the baseline is reported, never required
+            out["cpu_baseline"] = {"value": None, "unit": "edge-updates/s", "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

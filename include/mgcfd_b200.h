@@ -128,11 +128,21 @@ int mgcfd_prolong(mgcfd_ctx* ctx, int fine_level);
  * rms_var[c*5+v] = per-variable residual RMS of level 0               (may be NULL)
  * Returns MGCFD_ERR_INVALID_VARIABLES if a NaN/negative state appeared (checked once per call). */
 int mgcfd_run_cycles(mgcfd_ctx* ctx, int ncycles, double* rms_all, double* rms_var);
+/* The same loop split in two so that a caller can keep the device busy: enqueue (no host synchronisation; at most 4096
+ * cycles may be outstanding) and collect (one synchronisation: RMS histories of the cycles enqueued since the last
+ * collect + the invalid-state verdict). mgcfd_run_cycles == enqueue + collect. */
+int mgcfd_enqueue_cycles(mgcfd_ctx* ctx, int ncycles);
+int mgcfd_collect(mgcfd_ctx* ctx, double* rms_all, double* rms_var);
+/* after MGCFD_ERR_INVALID_VARIABLES from run_cycles/collect: the first offending cell (reference node order) of the first
+ * offending RK stage and the reason, i.e. what check_for_invalid_variables would have printed before exit(1) */
+int mgcfd_invalid_cell(mgcfd_ctx* ctx, long* cell, int* reason);
 
 /* ---- host <-> device state, reference layout ------------------------------------------------------ */
 int mgcfd_get_field(mgcfd_ctx* ctx, int level, int field, double* host_out);
 int mgcfd_set_field(mgcfd_ctx* ctx, int level, int field, const double* host_in);
 int mgcfd_synchronize(mgcfd_ctx* ctx);
+/* the cudaStream_t every kernel of this context is launched on (for callers that bracket calls with their own CUDA events) */
+int mgcfd_get_stream(mgcfd_ctx* ctx, void** cuda_stream);
 
 /* ---- introspection (tests, Times.csv, roofline) --------------------------------------------------- */
 /* info[0..]: nel, nI, nB, nW, padded nodes, tiles, tile_nodes, max colours, slots stored, halo entries, cut edges */
@@ -145,6 +155,8 @@ long mgcfd_check_colouring(mgcfd_ctx* ctx, int level);
  * out[kernel*levels + level], kernels = compute_step, flux, update(0), indirect_rw, time_step, restrict, prolong */
 int mgcfd_get_times(mgcfd_ctx* ctx, double* out_ms, long* out_iters);
 int mgcfd_reset_times(mgcfd_ctx* ctx);
+/* switches per-kernel CUDA-event timing on/off (on: every kernel is launched individually, graphs are bypassed) */
+int mgcfd_set_timing(mgcfd_ctx* ctx, int on);
 /* launches issued by this context since creation (all kernels are ours) */
 long mgcfd_launch_count(mgcfd_ctx* ctx);
 /* time (ms, CUDA events on the context's stream) of `reps` back-to-back launches of one kernel on `level`:

@@ -75,6 +75,11 @@ def lib() -> C.CDLL:
     L.mgcfd_calc_rms.argtypes = [vp, i, dp, dp]
     L.mgcfd_check_for_invalid_variables.argtypes = [vp, i, C.POINTER(l), C.POINTER(i)]
     L.mgcfd_run_cycles.argtypes = [vp, i, vp, vp]
+    L.mgcfd_enqueue_cycles.argtypes = [vp, i]
+    L.mgcfd_collect.argtypes = [vp, vp, vp]
+    L.mgcfd_invalid_cell.argtypes = [vp, C.POINTER(l), C.POINTER(i)]
+    L.mgcfd_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.mgcfd_set_timing.argtypes = [vp, i]
     L.mgcfd_get_field.argtypes = [vp, i, i, vp]
     L.mgcfd_set_field.argtypes = [vp, i, i, vp]
     L.mgcfd_synchronize.argtypes = [vp]
@@ -266,6 +271,32 @@ class Solver:
         ra, rv = np.zeros(ncycles), np.zeros((ncycles, 5))
         _check(lib().mgcfd_run_cycles(self._h, ncycles, _ptr(ra), _ptr(rv)))
         return ra, rv
+
+    def enqueue_cycles(self, ncycles: int):
+        """Queues V-cycles on the solver's stream without synchronising the host (at most 4096 outstanding)."""
+        _check(lib().mgcfd_enqueue_cycles(self._h, ncycles))
+        self._pending = getattr(self, "_pending", 0) + ncycles
+
+    def collect(self):
+        """Synchronises and returns (rms_all, rms_var) of the cycles enqueued since the last collect."""
+        n = getattr(self, "_pending", 0)
+        ra, rv = np.zeros(n), np.zeros((n, 5))
+        self._pending = 0
+        _check(lib().mgcfd_collect(self._h, _ptr(ra), _ptr(rv)))
+        return ra, rv
+
+    def invalid_cell(self):
+        cell, reason = C.c_long(-1), C.c_int(0)
+        _check(lib().mgcfd_invalid_cell(self._h, C.byref(cell), C.byref(reason)))
+        return cell.value, reason.value
+
+    def cuda_stream(self) -> int:
+        """The cudaStream_t (as an integer) all kernels of this solver are launched on."""
+        p = C.c_void_p()
+        _check(lib().mgcfd_get_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def set_timing(self, on: bool): _check(lib().mgcfd_set_timing(self._h, int(on)))
 
     def get_field(self, level, field, out: Optional[np.ndarray] = None):
         n = self._nel[level]

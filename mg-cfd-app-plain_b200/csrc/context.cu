@@ -88,29 +88,62 @@ struct mgcfd_ctx {
     std::vector<double> t_ms;      // [K_COUNT][levels]
     std::vector<long> t_iters;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // per-kernel timing without host synchronisation: start/stop events are drawn from a pool and resolved lazily
+    struct PendingTime { int kid, lev; long iters; cudaEvent_t e0, e1; };
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_next = 0;
+    std::vector<PendingTime> pending;
     bool capturing = false;
     unsigned long long stage_seq = 0;
     double kdiss;
+    int rms_pending = 0;
+    long bad_cell = -1; int bad_reason = 0;
 };
 
 namespace {
 
 inline long blocks_for(long n, int bs) { return (n + bs - 1) / bs; }
 
+// folds every recorded (start, stop) pair into the per-kernel per-level totals; synchronises the stream once
+void resolve_times(mgcfd_ctx* c) {
+    if (c->pending.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (const auto& p : c->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            c->t_ms[p.kid * c->levels + p.lev] += ms;
+            c->t_iters[p.kid * c->levels + p.lev] += p.iters;
+        }
+    }
+    c->pending.clear();
+    c->ev_next = 0;
+}
+
+// hands out the next pooled event; the caller has made sure (reserve_events) that the pool will not be recycled
+// between the start and the stop event of one bracket
+cudaEvent_t pool_event(mgcfd_ctx* c) {
+    if (c->ev_next == c->ev_pool.size()) { cudaEvent_t e = nullptr; cudaEventCreate(&e); c->ev_pool.push_back(e); }
+    return c->ev_pool[c->ev_next++];
+}
+void reserve_events(mgcfd_ctx* c, size_t n) {
+    if (c->ev_next + n > 8192) resolve_times(c);      // recycle: one stream sync every ~4096 timed launches
+}
+
+// CUDA-event bracket around the launches of one reference kernel on one level (the analogue of the reference's
+// start_timer()/stop_timer() pairs, src/Monitoring/timer.cpp:58-104), recorded on the context's own stream
 struct Timed {
-    mgcfd_ctx* c; int kid, lev; long iters; bool on;
+    mgcfd_ctx* c; int kid, lev; long iters; bool on; cudaEvent_t e0 = nullptr, e1 = nullptr;
     Timed(mgcfd_ctx* c_, int kid_, int lev_, long iters_) : c(c_), kid(kid_), lev(lev_), iters(iters_) {
         on = c->opt.timing && !c->capturing;
-        if (on) cudaEventRecord(c->ev0, c->stream);
+        if (!on) return;
+        reserve_events(c, 2);
+        e0 = pool_event(c); e1 = pool_event(c);
+        cudaEventRecord(e0, c->stream);
     }
     ~Timed() {
         if (!on) return;
-        cudaEventRecord(c->ev1, c->stream);
-        cudaEventSynchronize(c->ev1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-        c->t_ms[kid * c->levels + lev] += ms;
-        c->t_iters[kid * c->levels + lev] += iters;
+        cudaEventRecord(e1, c->stream);
+        c->pending.push_back({kid, lev, iters, e0, e1});
     }
 };
 
@@ -399,6 +432,7 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     for (auto& v : c->L) free_level(v);
     cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_rms); cudaFree(c->d_rms_counter);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
     return MGCFD_OK;
@@ -602,64 +636,119 @@ int mgcfd_prolong(mgcfd_ctx* c, int lf) {
 }
 
 // ---- fused path ----------------------------------------------------------------------------------------
+namespace {
+void advance_roles_one_cycle(mgcfd_ctx* c) {
+    // exactly as cycle_fused does: one smooth on levels 0 and L-1, two on the others
+    for (int l = 0; l < c->levels; l++) {
+        const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
+        for (int k = 0; k < visits; k++) { Level& v = c->L[l]; const int X = v.i_var, A = v.i_tmp, B = v.i_old; v.i_old = X; v.i_var = A; v.i_tmp = B; }
+    }
+}
+long launches_per_cycle(mgcfd_ctx* c) {
+    long per_cycle = 0;
+    for (int l = 0; l < c->levels; l++) {
+        const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
+        per_cycle += visits * (MGCFD_RK + (c->variant == MGCFD_MESH_FVCORR ? 1 : 2)) + (l == 0 ? 1 : 0);
+    }
+    return per_cycle + 2 * (c->levels - 1);
+}
+// enqueues one V-cycle on the context's stream (a graph replay when enabled); no host synchronisation
+int enqueue_one_cycle(mgcfd_ctx* c) {
+    const bool graph = c->opt.use_graph && !c->opt.timing;
+    if (!graph) return cycle_fused(c);
+    const std::string key = role_key(c);
+    auto it = c->graphs.find(key);
+    if (it == c->graphs.end()) {
+        cudaGraph_t g = nullptr;
+        const long launches_before = c->launches;
+        const unsigned long long seq_before = c->stage_seq;
+        c->capturing = true;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = cycle_fused(c);
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+        c->capturing = false;
+        c->launches = launches_before;        // capture recorded the launches, it did not run them
+        (void)seq_before;
+        if (rc != MGCFD_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        CK(ce);
+        cudaGraphExec_t ge = nullptr;
+        CK(cudaGraphInstantiate(&ge, g, 0));
+        CK(cudaGraphDestroy(g));
+        c->graphs[key] = ge;
+        // capture advanced the buffer roles: roll them back, the replay below advances them for real
+        for (size_t l = 0; l < c->L.size(); l++) { c->L[l].i_var = key[2 * l] - '0'; c->L[l].i_old = key[2 * l + 1] - '0'; c->L[l].i_tmp = 3 - c->L[l].i_var - c->L[l].i_old; }
+        it = c->graphs.find(key);
+    }
+    CK(cudaGraphLaunch(it->second, c->stream));
+    advance_roles_one_cycle(c);
+    c->launches += launches_per_cycle(c);
+    return MGCFD_OK;
+}
+}  // namespace
+
+int mgcfd_enqueue_cycles(mgcfd_ctx* c, int ncycles) {
+    if (!c || !c->finalized) { g_err = "context not finalized"; return MGCFD_ERR_ARG; }
+    if (ncycles < 0 || c->rms_pending + ncycles > c->rms_cap - 1) { g_err = "too many cycles enqueued without mgcfd_collect (limit 4096)"; return MGCFD_ERR_ARG; }
+    CK(cudaSetDevice(c->opt.device));
+    for (int i = 0; i < ncycles; i++) CKRC(enqueue_one_cycle(c));
+    c->rms_pending += ncycles;
+    return MGCFD_OK;
+}
+
+int mgcfd_collect(mgcfd_ctx* c, double* rms_all, double* rms_var) {
+    if (!c || !c->finalized) { g_err = "context not finalized"; return MGCFD_ERR_ARG; }
+    const int n = c->rms_pending;
+    std::vector<double> h(6 * (size_t)std::max(n, 1));
+    unsigned long long key = 0;
+    if (n) CK(cudaMemcpyAsync(h.data(), c->d_rms, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&key, c->d_badkey, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemsetAsync(c->d_rms_counter, 0, sizeof(int), c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->rms_pending = 0;
+    for (int i = 0; i < n; i++) {
+        if (rms_all) rms_all[i] = h[6 * i];
+        if (rms_var) for (int k = 0; k < 5; k++) rms_var[i * 5 + k] = h[6 * i + 1 + k];
+    }
+    if (key != ~0ull) {
+        c->bad_cell = (long)((key >> 2) & 0x3FFFFFFFFFull); c->bad_reason = (int)(key & 3);
+        g_err = "invalid variables detected (cell " + std::to_string(c->bad_cell) + ")";
+        return MGCFD_ERR_INVALID_VARIABLES;
+    }
+    return MGCFD_OK;
+}
+
 int mgcfd_run_cycles(mgcfd_ctx* c, int ncycles, double* rms_all, double* rms_var) {
     if (!c || !c->finalized) { g_err = "context not finalized"; return MGCFD_ERR_ARG; }
     if (ncycles < 0) { g_err = "ncycles < 0"; return MGCFD_ERR_ARG; }
-    CK(cudaSetDevice(c->opt.device));
-    const bool graph = c->opt.use_graph && !c->opt.timing;
-    int done = 0;
+    if (c->rms_pending) { g_err = "cycles enqueued with mgcfd_enqueue_cycles are still pending: call mgcfd_collect first"; return MGCFD_ERR_ARG; }
+    int done = 0, rc_final = MGCFD_OK;
     while (done < ncycles) {
         const int chunk = std::min(ncycles - done, c->rms_cap - 1);
-        CK(cudaMemsetAsync(c->d_rms_counter, 0, sizeof(int), c->stream));
-        for (int i = 0; i < chunk; i++) {
-            if (!graph) { CKRC(cycle_fused(c)); continue; }
-            const std::string key = role_key(c);
-            auto it = c->graphs.find(key);
-            if (it == c->graphs.end()) {
-                cudaGraph_t g = nullptr;
-                c->capturing = true;
-                CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-                int rc = cycle_fused(c);
-                cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
-                c->capturing = false;
-                if (rc != MGCFD_OK) { if (g) cudaGraphDestroy(g); return rc; }
-                CK(ce);
-                cudaGraphExec_t ge = nullptr;
-                CK(cudaGraphInstantiate(&ge, g, 0));
-                CK(cudaGraphDestroy(g));
-                c->graphs[key] = ge;
-                // capture only recorded the cycle (and advanced the buffer roles): roll the roles back and replay it
-                for (size_t l = 0; l < c->L.size(); l++) { c->L[l].i_var = key[2 * l] - '0'; c->L[l].i_old = key[2 * l + 1] - '0'; c->L[l].i_tmp = 3 - c->L[l].i_var - c->L[l].i_old; }
-                it = c->graphs.find(key);
-            }
-            CK(cudaGraphLaunch(it->second, c->stream));
-            // advance the roles exactly as cycle_fused does: one smooth on levels 0 and L-1, two on the others
-            for (int l = 0; l < c->levels; l++) {
-                const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
-                for (int k = 0; k < visits; k++) { Level& v = c->L[l]; const int X = v.i_var, A = v.i_tmp, B = v.i_old; v.i_old = X; v.i_var = A; v.i_tmp = B; }
-            }
-            // the graph replays the launches recorded in it
-            long per_cycle = 0;
-            for (int l = 0; l < c->levels; l++) {
-                const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
-                per_cycle += visits * (MGCFD_RK + (c->variant == MGCFD_MESH_FVCORR ? 1 : 2)) + (l == 0 ? 1 : 0);
-            }
-            per_cycle += 2 * (c->levels - 1);
-            c->launches += per_cycle;
-        }
-        std::vector<double> h(6 * (size_t)chunk);
-        if (chunk) CK(cudaMemcpyAsync(h.data(), c->d_rms, sizeof(double) * 6 * chunk, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < chunk; i++) {
-            if (rms_all) rms_all[done + i] = h[6 * i];
-            if (rms_var) for (int k = 0; k < 5; k++) rms_var[(done + i) * 5 + k] = h[6 * i + 1 + k];
-        }
+        CKRC(mgcfd_enqueue_cycles(c, chunk));
+        int rc = mgcfd_collect(c, rms_all ? rms_all + done : nullptr, rms_var ? rms_var + 5 * (size_t)done : nullptr);
+        if (rc != MGCFD_OK && rc != MGCFD_ERR_INVALID_VARIABLES) return rc;
+        if (rc != MGCFD_OK) rc_final = rc;
         done += chunk;
     }
-    unsigned long long key = 0;
-    CK(cudaMemcpyAsync(&key, c->d_badkey, 8, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (key != ~0ull) { g_err = "invalid variables detected (cell " + std::to_string((key >> 2) & 0x3FFFFFFFFFull) + ")"; return MGCFD_ERR_INVALID_VARIABLES; }
+    if (ncycles == 0) return mgcfd_collect(c, nullptr, nullptr);
+    return rc_final;
+}
+
+int mgcfd_get_stream(mgcfd_ctx* c, void** stream) {
+    if (!c || !stream) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    *stream = (void*)c->stream;
+    return MGCFD_OK;
+}
+int mgcfd_set_timing(mgcfd_ctx* c, int on) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    resolve_times(c);
+    c->opt.timing = on ? 1 : 0;
+    return MGCFD_OK;
+}
+int mgcfd_invalid_cell(mgcfd_ctx* c, long* cell, int* reason) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    if (cell) *cell = c->bad_cell;
+    if (reason) *reason = c->bad_reason;
     return MGCFD_OK;
 }
 
@@ -719,12 +808,14 @@ long mgcfd_check_colouring(mgcfd_ctx* c, int l) {
 }
 int mgcfd_get_times(mgcfd_ctx* c, double* out_ms, long* out_iters) {
     if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    resolve_times(c);
     if (out_ms) memcpy(out_ms, c->t_ms.data(), sizeof(double) * c->t_ms.size());
     if (out_iters) memcpy(out_iters, c->t_iters.data(), sizeof(long) * c->t_iters.size());
     return MGCFD_OK;
 }
 int mgcfd_reset_times(mgcfd_ctx* c) {
     if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    resolve_times(c);
     std::fill(c->t_ms.begin(), c->t_ms.end(), 0.0);
     std::fill(c->t_iters.begin(), c->t_iters.end(), 0L);
     return MGCFD_OK;

@@ -53,9 +53,9 @@ extern "C" {
 #define MGCFD_FIELD_VOLUMES 5      /* 1 double per node, read-only */
 
 /* how the flux scatter is made race-free */
-#define MGCFD_FLUX_TILED_COLOURED 0 /* default: node tiles staged in shared memory, conflict-free edge colouring, no atomics, deterministic */
-#define MGCFD_FLUX_SORTED_SEGMENT 1 /* deterministic CSR-by-node gather (every edge evaluated from both ends), no scatter at all */
-#define MGCFD_FLUX_ATOMIC 2         /* one thread per edge, fp64 atomics (baseline; the ordering-sweep kernel) */
+#define MGCFD_FLUX_TILED_COLOURED 0 /* node tiles staged in shared memory; an edge inside a tile is evaluated once and scattered to its other end through a shared accumulator, conflict-free by edge colouring; no atomics, deterministic */
+#define MGCFD_FLUX_SORTED_SEGMENT 1 /* node tiles staged in shared memory; every node walks its CSR segment (original edge order), every edge is evaluated from both ends, nothing is scattered; no atomics, no barriers in the edge loop, deterministic */
+#define MGCFD_FLUX_ATOMIC 2         /* one thread per edge in original edge order, fp64 atomics (baseline; the ordering-sweep kernel) */
 
 /* node renumbering applied at upload */
 #define MGCFD_ORDER_AS_GIVEN 0
@@ -160,13 +160,15 @@ int mgcfd_set_timing(mgcfd_ctx* ctx, int on);
 /* launches issued by this context since creation (all kernels are ours) */
 long mgcfd_launch_count(mgcfd_ctx* ctx);
 /* time (ms, CUDA events on the context's stream) of `reps` back-to-back launches of one kernel on `level`:
- * which = 0 fused flux+update stage, 1 flux only (internal), 2 indirect_rw, 3 atomic flux, 4 sorted-segment flux */
+ * which = 0 fused stage kernel (flux + boundary + wall + time_step) of the configured tiled mode, 1 its flux-only form
+ * (internal edges, granular API), 2 indirect_rw, 3 atomic flux */
 int mgcfd_time_kernel(mgcfd_ctx* ctx, int level, int which, int reps, double* ms_total);
 
 /* Host-only run of the integer preprocessing (no device needed): renumbering, tiling and colouring of one level.
  * info[] as mgcfd_level_info; new_of_old may be NULL; *conflicts = result of the colouring validity check. */
 int mgcfd_plan_level(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall,
-                     const void* edges_aos40, int ordering, int tile_nodes, long info[16], long* new_of_old, long* conflicts);
+                     const void* edges_aos40, int ordering, int tile_nodes, int flux_mode, long info[16], long* new_of_old,
+                     long* conflicts);
 void mgcfd_free(void* p);
 
 #ifdef __cplusplus

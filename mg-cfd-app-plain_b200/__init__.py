@@ -92,7 +92,7 @@ def lib() -> C.CDLL:
     L.mgcfd_launch_count.argtypes = [vp]
     L.mgcfd_launch_count.restype = l
     L.mgcfd_time_kernel.argtypes = [vp, i, i, i, dp]
-    L.mgcfd_plan_level.argtypes = [l, vp, l, l, l, vp, i, i, C.POINTER(l), vp, C.POINTER(l)]
+    L.mgcfd_plan_level.argtypes = [l, vp, l, l, l, vp, i, i, i, C.POINTER(l), vp, C.POINTER(l)]
     L.mgcfd_mesh_generate.argtypes = [i, i, vp, dp, i, i, C.c_ulong, C.c_double, C.POINTER(vp)]
     L.mgcfd_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
     L.mgcfd_mesh_write.argtypes = [vp, C.c_char_p, C.c_char_p, i]
@@ -359,14 +359,14 @@ INFO_KEYS = ("nel", "nI", "nB", "nW", "npad", "ntiles", "tile_nodes", "max_round
              "used_slots", "max_halo", "bslots", "smem_bytes")
 
 
-def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 256):
+def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 256, flux_mode: int = FLUX_TILED_COLOURED):
     """Host-only integer preprocessing of one level: returns (info dict, new_of_old permutation, colouring conflicts)."""
     nel, nI, nB, nW, _ = mesh.dims(level)
     info = (C.c_long * 16)()
     perm = np.empty(nel, dtype=np.int64)
     conflicts = C.c_long(-1)
     c = mesh.coords(level)
-    _check(lib().mgcfd_plan_level(nel, _ptr(c), nI, nB, nW, _ptr(mesh.edges(level)), ordering, tile_nodes, info, _ptr(perm),
+    _check(lib().mgcfd_plan_level(nel, _ptr(c), nI, nB, nW, _ptr(mesh.edges(level)), ordering, tile_nodes, flux_mode, info, _ptr(perm),
                                   C.byref(conflicts)))
     return dict(zip(INFO_KEYS, info)), perm, conflicts.value
 

@@ -47,18 +47,17 @@ struct Level {
     long nel = 0, npad = 0, ntiles = 0, nI = 0, nB = 0, nW = 0;
     int TN = 256, smem_nodes = 0;
     size_t smem_bytes = 0;
-    double* buf[3] = {nullptr, nullptr, nullptr};
+    double* buf[3] = {nullptr, nullptr, nullptr};   // node records (8 doubles each), rotating roles
     int i_var = 0, i_old = 1, i_tmp = 2;
     double *res = nullptr, *flux = nullptr, *sf = nullptr, *vol = nullptr, *vol_root = nullptr;
     int *new_of_old = nullptr, *old_of_new = nullptr;
     long* halo_off = nullptr; int* halo_ids = nullptr;
-    long* slot_off = nullptr; int* tile_rounds = nullptr; uint16_t* slot_other = nullptr; double* slot_w = nullptr; long nslots = 0;
-    long* bslot_off = nullptr; int* tile_brounds = nullptr; uint8_t* bslot_kind = nullptr; double* bslot_w = nullptr; long nbslots = 0;
+    long* slot_off = nullptr; unsigned char* slots = nullptr;
+    long* bslot_off = nullptr; unsigned char* bslots = nullptr;
     // flat + CSR (lazy)
     int *ea = nullptr, *eb = nullptr; double* ew = nullptr;
     int* bnode = nullptr; uint8_t* bkind = nullptr; double* bw = nullptr;
-    long* adj_off = nullptr; int* adj_nbr = nullptr; double* adj_w = nullptr;
-    bool flat_up = false, csr_up = false;
+    bool flat_up = false;
     // transfers (operators between this level and the next coarser one)
     long* child_off = nullptr; int* child_ids = nullptr;       // stored on the COARSE level (children in level-1)
     int* parent = nullptr; double* idist_own = nullptr; long* ent_off = nullptr; int* ent_src = nullptr; double* ent_w = nullptr;
@@ -153,36 +152,39 @@ int post_launch(mgcfd_ctx* c) {
     return MGCFD_OK;
 }
 
-template <int TN, bool FUSED>
-int launch_tile_t(mgcfd_ctx* c, Level& v, const TileArgs& a) {
-    static bool attr_set = false;
+template <int TN, bool SCATTER, bool FUSED>
+int launch_stage_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     static size_t attr_bytes = 0;
-    if (!attr_set || v.smem_bytes > attr_bytes) {
-        CK(cudaFuncSetAttribute(k_tile_flux<TN, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem_bytes));
-        attr_set = true; attr_bytes = v.smem_bytes;
+    if (v.smem_bytes > attr_bytes) {
+        CK(cudaFuncSetAttribute(k_stage<TN, SCATTER, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.smem_bytes));
+        attr_bytes = v.smem_bytes;
     }
-    k_tile_flux<TN, FUSED><<<(unsigned)v.ntiles, TN, v.smem_bytes, c->stream>>>(a);
+    k_stage<TN, SCATTER, FUSED><<<(unsigned)v.ntiles, TN, v.smem_bytes, c->stream>>>(a);
     return post_launch(c);
 }
-
-int launch_tile(mgcfd_ctx* c, Level& v, const TileArgs& a, bool fused) {
-    if (v.TN == 256) return fused ? launch_tile_t<256, true>(c, v, a) : launch_tile_t<256, false>(c, v, a);
-    if (v.TN == 128) return fused ? launch_tile_t<128, true>(c, v, a) : launch_tile_t<128, false>(c, v, a);
-    if (v.TN == 512) return fused ? launch_tile_t<512, true>(c, v, a) : launch_tile_t<512, false>(c, v, a);
+template <int TN>
+int launch_stage_tn(mgcfd_ctx* c, Level& v, const StageArgs& a, bool scatter, bool fused) {
+    if (scatter) return fused ? launch_stage_t<TN, true, true>(c, v, a) : launch_stage_t<TN, true, false>(c, v, a);
+    return fused ? launch_stage_t<TN, false, true>(c, v, a) : launch_stage_t<TN, false, false>(c, v, a);
+}
+int launch_stage(mgcfd_ctx* c, Level& v, const StageArgs& a, bool fused) {
+    const bool scatter = v.plan.scatter;
+    if (v.TN == 256) return launch_stage_tn<256>(c, v, a, scatter, fused);
+    if (v.TN == 128) return launch_stage_tn<128>(c, v, a, scatter, fused);
+    if (v.TN == 512) return launch_stage_tn<512>(c, v, a, scatter, fused);
     g_err = "tile_nodes must be 128, 256 or 512";
     return MGCFD_ERR_ARG;
 }
 
-TileArgs base_args(mgcfd_ctx* c, Level& v) {
-    TileArgs a;
+StageArgs base_args(mgcfd_ctx* c, Level& v) {
+    StageArgs a;
     memset(&a, 0, sizeof(a));
     a.stride = v.npad;
     a.halo_off = v.halo_off; a.halo_ids = v.halo_ids;
-    a.slot_off = v.slot_off; a.tile_rounds = v.tile_rounds; a.slot_other = v.slot_other; a.slot_w = v.slot_w; a.nslots = v.nslots;
-    a.bslot_off = v.bslot_off; a.tile_brounds = v.tile_brounds; a.bslot_kind = v.bslot_kind; a.bslot_w = v.bslot_w; a.nbslots = v.nbslots;
-    a.kdiss = c->kdiss;
+    a.slot_off = v.slot_off; a.slots = v.slots;
+    a.bslot_off = v.bslot_off; a.bslots = v.bslots;
+    a.k2 = 2.0 * c->kdiss;
     a.old_of_new = v.old_of_new;
-    a.smem_nodes = v.smem_nodes;
     a.sf = v.sf;
     return a;
 }
@@ -201,37 +203,21 @@ int ensure_flat(mgcfd_ctx* c, Level& v) {
     v.flat_up = true;
     return MGCFD_OK;
 }
-int ensure_csr(mgcfd_ctx* c, Level& v) {
-    if (v.csr_up) return MGCFD_OK;
-    CKRC(dev_upload(&v.adj_off, v.plan.adj_off, c->stream)); CKRC(dev_upload(&v.adj_nbr, v.plan.adj_nbr, c->stream));
-    CKRC(dev_upload(&v.adj_w, v.plan.adj_w, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    v.csr_up = true;
-    return MGCFD_OK;
-}
-
 // flux into v.flux (+=) for the edge classes in mask, honouring the configured flux mode
 int flux_granular(mgcfd_ctx* c, int l, int mask) {
     Level& v = c->L[l];
     CKRC(ensure_flux(c, v));
-    const int mode = c->opt.flux_mode;
-    if (mode == MGCFD_FLUX_TILED_COLOURED) {
-        TileArgs a = base_args(c, v);
-        a.vin = v.V(v.i_var); a.vout = v.flux; a.mask = mask;
-        return launch_tile(c, v, a, false);
+    if (c->opt.flux_mode != MGCFD_FLUX_ATOMIC) {
+        StageArgs a = base_args(c, v);
+        a.vin = v.V(v.i_var); a.flux = v.flux; a.mask = mask;
+        return launch_stage(c, v, a, false);
     }
-    if (mask & 1) {
-        if (mode == MGCFD_FLUX_ATOMIC) {
-            CKRC(ensure_flat(c, v));
-            if (v.nI) { k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, c->kdiss); CKRC(post_launch(c)); }
-        } else {
-            CKRC(ensure_csr(c, v));
-            k_flux_segment<<<(unsigned)blocks_for(v.npad, 128), 128, 0, c->stream>>>(v.npad, v.adj_off, v.adj_nbr, v.adj_w, 2 * v.nI, v.V(v.i_var), v.npad, v.flux, c->kdiss);
-            CKRC(post_launch(c));
-        }
+    CKRC(ensure_flat(c, v));
+    if ((mask & 1) && v.nI) {
+        k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, 2.0 * c->kdiss);
+        CKRC(post_launch(c));
     }
     if ((mask & 6) && (v.nB + v.nW)) {
-        CKRC(ensure_flat(c, v));
         k_bflux_atomic<<<(unsigned)blocks_for(v.nB + v.nW, 256), 256, 0, c->stream>>>(v.nB + v.nW, v.bnode, v.bkind, v.bw, v.V(v.i_var), v.npad, v.flux, mask);
         CKRC(post_launch(c));
     }
@@ -243,11 +229,11 @@ int step_factor(mgcfd_ctx* c, int l, int legacy) {
     Timed tm(c, K_STEP, l, v.nel);
     const unsigned nb = (unsigned)blocks_for(v.npad, 256);
     if (legacy) {
-        k_step_factor<true><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.vol, v.sf, c->d_minbits);
+        k_step_factor<true><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.vol, v.sf, c->d_minbits);
         CKRC(post_launch(c));
     } else {
         CK(cudaMemsetAsync(c->d_minbits, 0x7F, sizeof(unsigned long long), c->stream));
-        k_step_factor<false><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.vol_root, v.sf, c->d_minbits);
+        k_step_factor<false><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.vol_root, v.sf, c->d_minbits);
         CKRC(post_launch(c));
         k_apply_min_dt<<<nb, 256, 0, c->stream>>>(c->d_minbits, v.vol, v.sf, v.npad);
         CKRC(post_launch(c));
@@ -268,7 +254,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     const int X = v.i_var, A = v.i_tmp, B = v.i_old;   // the previous old_variables are dead once a smooth starts
     for (int j = 0; j < MGCFD_RK; j++) {
         Timed tm(c, K_FLUX, l, v.nI);
-        TileArgs a = base_args(c, v);
+        StageArgs a = base_args(c, v);
         a.vold = v.V(X);
         a.vin = (j == 0) ? v.V(X) : (j == 1 ? v.V(A) : v.V(B));
         a.vout = (j == 1) ? v.V(B) : v.V(A);
@@ -280,7 +266,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
             a.res = v.res;
             a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
         }
-        CKRC(launch_tile(c, v, a, true));
+        CKRC(launch_stage(c, v, a, true));
     }
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
@@ -290,7 +276,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
 int do_restrict(mgcfd_ctx* c, int lc) {
     Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
     Timed tm(c, K_RESTRICT, lc, vf.nel);
-    k_restrict<<<(unsigned)blocks_for(vc.npad, 128), 128, 0, c->stream>>>(vf.V(vf.i_var), vf.npad, vc.V(vc.i_var), vc.npad, vc.npad, vc.child_off, vc.child_ids);
+    k_restrict<<<(unsigned)blocks_for(vc.npad, 128), 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.npad, vc.child_off, vc.child_ids);
     return post_launch(c);
 }
 int do_prolong(mgcfd_ctx* c, int lf) {
@@ -341,9 +327,8 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
 
 void free_level(Level& v) {
     void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.halo_off, v.halo_ids,
-                    v.slot_off, v.tile_rounds, v.slot_other, v.slot_w, v.bslot_off, v.tile_brounds, v.bslot_kind, v.bslot_w, v.ea, v.eb, v.ew,
-                    v.bnode, v.bkind, v.bw, v.adj_off, v.adj_nbr, v.adj_w, v.child_off, v.child_ids, v.parent, v.idist_own, v.ent_off, v.ent_src,
-                    v.ent_w, v.rms_partial, v.io};
+                    v.slot_off, v.slots, v.bslot_off, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
+                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.io};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -467,7 +452,7 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     }
     if (coords) H.coords.assign(coords, coords + 3 * nel); else H.coords.clear();
     if (mg_map && l < c->levels - 1) H.mg.assign(mg_map, mg_map + mgc); else H.mg.clear();
-    PlanOptions po; po.ordering = c->opt.ordering; po.tile_nodes = c->opt.tile_nodes;
+    PlanOptions po; po.ordering = c->opt.ordering; po.tile_nodes = c->opt.tile_nodes; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
     try { build_level_plan(H, po, v.plan); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     v.uploaded = true;
@@ -485,9 +470,9 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         LevelPlan& P = v.plan;
         v.nel = P.nel; v.npad = P.npad; v.ntiles = P.ntiles; v.nI = P.nI; v.nB = P.nB; v.nW = P.nW; v.TN = P.TN;
         v.smem_nodes = ((P.TN + P.max_halo + 3) / 4) * 4;
-        v.smem_bytes = sizeof(double) * (10 * (size_t)v.smem_nodes + 5 * (size_t)P.TN);
+        v.smem_bytes = 64 * (size_t)v.smem_nodes + (P.scatter ? 40 * (size_t)P.TN : 0);
         if (v.smem_bytes > 227 * 1024) { g_err = "tile halo too large for shared memory; use a smaller tile_nodes or a locality-preserving ordering"; return MGCFD_ERR_ARG; }
-        for (int b = 0; b < 3; b++) CK(cudaMalloc((void**)&v.buf[b], sizeof(double) * 5 * v.npad));
+        for (int b = 0; b < 3; b++) CK(cudaMalloc((void**)&v.buf[b], sizeof(double) * 8 * v.npad));
         CK(cudaMalloc((void**)&v.res, sizeof(double) * 5 * v.npad));
         CK(cudaMalloc((void**)&v.sf, sizeof(double) * v.npad));
         // volumes in new order; padding: volume 1, root +inf so that padded nodes never win the min-dt reduction
@@ -501,18 +486,14 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         std::vector<int> n2o(P.old_of_new.begin(), P.old_of_new.end()), o2n(P.new_of_old.begin(), P.new_of_old.end());
         CKRC(dev_upload(&v.old_of_new, n2o, s)); CKRC(dev_upload(&v.new_of_old, o2n, s));
         CKRC(dev_upload(&v.halo_off, P.halo_off, s)); CKRC(dev_upload(&v.halo_ids, P.halo_ids, s));
-        CKRC(dev_upload(&v.slot_off, P.slot_off, s)); CKRC(dev_upload(&v.tile_rounds, P.tile_rounds, s));
-        CKRC(dev_upload(&v.slot_other, P.slot_other, s)); CKRC(dev_upload(&v.slot_w, P.slot_w, s));
-        v.nslots = P.slot_off[P.ntiles];
-        CKRC(dev_upload(&v.bslot_off, P.bslot_off, s)); CKRC(dev_upload(&v.tile_brounds, P.tile_brounds, s));
-        CKRC(dev_upload(&v.bslot_kind, P.bslot_kind, s)); CKRC(dev_upload(&v.bslot_w, P.bslot_w, s));
-        v.nbslots = P.bslot_off[P.ntiles];
+        CKRC(dev_upload(&v.slot_off, P.slot_off, s)); CKRC(dev_upload(&v.slots, P.slots, s));
+        CKRC(dev_upload(&v.bslot_off, P.bslot_off, s)); CKRC(dev_upload(&v.bslots, P.bslots, s));
         const long parts = std::max<long>(v.ntiles, blocks_for(v.npad, 256));
         CK(cudaMalloc((void**)&v.rms_partial, sizeof(double) * 5 * parts));
         CK(cudaStreamSynchronize(s));
         // node state: every buffer starts at the far-field state (what initialize_variables leaves, cfd_loops.h:44-55);
         // padding nodes keep it forever (no edges, zero residual), which keeps them finite in every stage
-        for (int b = 0; b < 3; b++) { k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, s>>>(v.buf[b], v.npad, v.npad); CKRC(post_launch(c)); }
+        for (int b = 0; b < 3; b++) { k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, s>>>(v.buf[b], v.npad); CKRC(post_launch(c)); }
         CK(cudaMemsetAsync(v.res, 0, sizeof(double) * 5 * v.npad, s));
         CK(cudaMemsetAsync(v.sf, 0, sizeof(double) * v.npad, s));
     }
@@ -532,8 +513,10 @@ int mgcfd_finalize(mgcfd_ctx* c) {
     // host copies are no longer needed, except the plan pieces used lazily (flat/CSR) and by introspection
     for (auto& v : c->L) {
         v.host = HostLevel();
-        v.plan.slot_w.clear(); v.plan.slot_w.shrink_to_fit();
-        v.plan.bslot_w.clear(); v.plan.bslot_w.shrink_to_fit();
+        if (v.npad > 2000000) {   // big levels: drop the host copy of the edge stream (introspection needs it only on small meshes)
+            v.plan.slots.clear(); v.plan.slots.shrink_to_fit();
+            v.plan.bslots.clear(); v.plan.bslots.shrink_to_fit();
+        }
     }
     c->finalized = true;
     return MGCFD_OK;
@@ -543,13 +526,13 @@ int mgcfd_finalize(mgcfd_ctx* c) {
 int mgcfd_initialize_variables(mgcfd_ctx* c, int l) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
-    k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad);
+    k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad);
     return post_launch(c);
 }
 int mgcfd_copy_old_variables(mgcfd_ctx* c, int l) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
-    k_copy<<<(unsigned)blocks_for(5 * v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_old), v.V(v.i_var), 5 * v.npad);
+    k_copy<<<(unsigned)blocks_for(8 * v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_old), v.V(v.i_var), 8 * v.npad);
     return post_launch(c);
 }
 int mgcfd_compute_step_factor(mgcfd_ctx* c, int l, int legacy) {
@@ -590,7 +573,7 @@ int mgcfd_indirect_rw(mgcfd_ctx* c, int l) {
 int mgcfd_residual(mgcfd_ctx* c, int l) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
-    k_residual<<<(unsigned)blocks_for(5 * v.npad, 256), 256, 0, c->stream>>>(5 * v.npad, v.V(v.i_old), v.V(v.i_var), v.res);
+    k_residual<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.npad, v.npad, v.V(v.i_old), v.V(v.i_var), v.res);
     return post_launch(c);
 }
 int mgcfd_calc_rms(mgcfd_ctx* c, int l, double* rms_all, double rms_var[5]) {
@@ -613,7 +596,7 @@ int mgcfd_check_for_invalid_variables(mgcfd_ctx* c, int l, long* first_bad_cell,
     Level& v = c->L[l];
     unsigned long long* key = c->d_minbits;   // scratch word; the step-factor kernel re-initialises it before use
     CK(cudaMemsetAsync(key, 0xFF, 8, c->stream));
-    k_check_invalid<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.npad, v.old_of_new, key);
+    k_check_invalid<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.old_of_new, key);
     CKRC(post_launch(c));
     unsigned long long h = 0;
     CK(cudaMemcpyAsync(&h, key, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -760,7 +743,9 @@ int mgcfd_get_field(mgcfd_ctx* c, int l, int field, double* host_out) {
     double* p; int nc;
     CKRC(field_ptr(c, v, field, &p, &nc, false));
     if (!v.io) CK(cudaMalloc((void**)&v.io, sizeof(double) * 5 * v.nel));
-    k_export_aos<<<(unsigned)blocks_for(v.nel, 256), 256, 0, c->stream>>>(p, v.npad, nc, v.nel, v.new_of_old, v.io);
+    const unsigned nb = (unsigned)blocks_for(v.nel, 256);
+    if (field == MGCFD_FIELD_VARIABLES || field == MGCFD_FIELD_OLD_VARIABLES) k_export_recs<<<nb, 256, 0, c->stream>>>(p, v.nel, v.new_of_old, v.io);
+    else k_export_soa<<<nb, 256, 0, c->stream>>>(p, v.npad, nc, v.nel, v.new_of_old, v.io);
     CKRC(post_launch(c));
     CK(cudaMemcpyAsync(host_out, v.io, sizeof(double) * nc * v.nel, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -774,7 +759,10 @@ int mgcfd_set_field(mgcfd_ctx* c, int l, int field, const double* host_in) {
     CKRC(field_ptr(c, v, field, &p, &nc, true));
     if (!v.io) CK(cudaMalloc((void**)&v.io, sizeof(double) * 5 * v.nel));
     CK(cudaMemcpyAsync(v.io, host_in, sizeof(double) * nc * v.nel, cudaMemcpyHostToDevice, c->stream));
-    k_import_aos<<<(unsigned)blocks_for(v.nel, 256), 256, 0, c->stream>>>(p, v.npad, nc, v.nel, v.new_of_old, v.io);
+    const unsigned nb = (unsigned)blocks_for(v.nel, 256);
+    // state fields: the record's derived quantities (1/rho, p, |v|+c) are rebuilt from the five variables
+    if (field == MGCFD_FIELD_VARIABLES || field == MGCFD_FIELD_OLD_VARIABLES) k_import_recs<<<nb, 256, 0, c->stream>>>(p, v.nel, v.new_of_old, v.io);
+    else k_import_soa<<<nb, 256, 0, c->stream>>>(p, v.npad, nc, v.nel, v.new_of_old, v.io);
     CKRC(post_launch(c));
     CK(cudaStreamSynchronize(c->stream));
     return MGCFD_OK;
@@ -791,8 +779,8 @@ int mgcfd_level_info(mgcfd_ctx* c, int l, long info[16]) {
     const LevelPlan& P = c->L[l].plan;
     memset(info, 0, sizeof(long) * 16);
     info[0] = P.nel; info[1] = P.nI; info[2] = P.nB; info[3] = P.nW; info[4] = P.npad; info[5] = P.ntiles; info[6] = P.TN;
-    info[7] = P.max_rounds; info[8] = P.slot_off.empty() ? 0 : P.slot_off[P.ntiles]; info[9] = (long)P.halo_ids.size();
-    info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off.empty() ? 0 : P.bslot_off[P.ntiles];
+    info[7] = P.max_rounds; info[8] = P.slot_off.empty() ? 0 : P.slot_off[P.ntiles] * P.TN; info[9] = (long)P.halo_ids.size();
+    info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off.empty() ? 0 : P.bslot_off[P.ntiles] * P.TN;
     info[14] = (long)c->L[l].smem_bytes;
     return MGCFD_OK;
 }
@@ -828,21 +816,19 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
     Level& v = c->L[l];
     CKRC(ensure_flux(c, v));
     if (which == 2 || which == 3) CKRC(ensure_flat(c, v));
-    if (which == 4) CKRC(ensure_csr(c, v));
+    if ((which == 0 || which == 1) && c->opt.flux_mode == MGCFD_FLUX_ATOMIC) { g_err = "the stage kernel needs a tiled flux mode"; return MGCFD_ERR_ARG; }
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int r = 0; r < reps; r++) {
         if (which == 0 || which == 1) {
-            TileArgs a = base_args(c, v);
+            StageArgs a = base_args(c, v);
             a.vin = v.V(v.i_var); a.vold = v.V(v.i_var); a.rk_div = 4.0;
-            if (which == 0) { a.vout = v.V(v.i_tmp); a.mask = 7; CKRC(launch_tile(c, v, a, true)); }
-            else { a.vout = v.flux; a.mask = 1; CKRC(launch_tile(c, v, a, false)); }
+            if (which == 0) { a.vout = v.V(v.i_tmp); a.mask = 7; CKRC(launch_stage(c, v, a, true)); }
+            else { a.flux = v.flux; a.mask = 1; CKRC(launch_stage(c, v, a, false)); }
         } else if (which == 2) {
             k_indirect_rw<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux); CKRC(post_launch(c));
         } else if (which == 3) {
-            k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, c->kdiss); CKRC(post_launch(c));
-        } else if (which == 4) {
-            k_flux_segment<<<(unsigned)blocks_for(v.npad, 128), 128, 0, c->stream>>>(v.npad, v.adj_off, v.adj_nbr, v.adj_w, 2 * v.nI, v.V(v.i_var), v.npad, v.flux, c->kdiss); CKRC(post_launch(c));
+            k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, 2.0 * c->kdiss); CKRC(post_launch(c));
         } else { g_err = "unknown kernel selector"; return MGCFD_ERR_ARG; }
     }
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -855,7 +841,7 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
 }
 
 int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, const void* edges, int ordering, int tile_nodes,
-                     long info[16], long* new_of_old, long* conflicts) {
+                     int flux_mode, long info[16], long* new_of_old, long* conflicts) {
     if (nel <= 0 || !edges || !info) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
     HostLevel H;
     H.nel = nel; H.nI = nI; H.nB = nB; H.nW = nW;
@@ -863,14 +849,14 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     const EdgeNb* e = (const EdgeNb*)edges;
     H.edges.assign(e, e + nI + nB + nW);
     if (coords) H.coords.assign(coords, coords + 3 * nel);
-    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 256;
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 256; po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED);
     LevelPlan P;
     try { build_level_plan(H, po, P); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     memset(info, 0, sizeof(long) * 16);
     info[0] = P.nel; info[1] = P.nI; info[2] = P.nB; info[3] = P.nW; info[4] = P.npad; info[5] = P.ntiles; info[6] = P.TN;
-    info[7] = P.max_rounds; info[8] = P.slot_off[P.ntiles]; info[9] = (long)P.halo_ids.size();
-    info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off[P.ntiles];
+    info[7] = P.max_rounds; info[8] = P.slot_off[P.ntiles] * P.TN; info[9] = (long)P.halo_ids.size();
+    info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off[P.ntiles] * P.TN;
     if (new_of_old) memcpy(new_of_old, P.new_of_old.data(), sizeof(long) * nel);
     if (conflicts) *conflicts = check_colouring(P);
     return MGCFD_OK;

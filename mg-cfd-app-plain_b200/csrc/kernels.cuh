@@ -1,6 +1,15 @@
 // kernels.cuh -- hand-written fp64 CUDA kernels (sm_100a) for the MG-CFD per-cycle solver loop.
-// Node state is SoA: plane v of a level lives at base + v*stride (stride = padded node count).
-// No tensor cores: the path is gather/scatter and FP64/memory bound.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   node state  : one 64-byte RECORD per node, {rho, mx, my, mz, rhoE, 1/rho, p, |v|+c}: the five conserved variables of the
+//                 reference (src/Base/const.h:19-26) plus the three per-node quantities every incident edge needs
+//                 (compute_velocity / compute_pressure / compute_speed_of_sound, src/Kernels/cfd_loops.h:121-148), computed
+//                 ONCE per node by whichever kernel writes the state instead of twice per edge.  A record is exactly two
+//                 32-byte sectors, so the halo gather of a tile moves no padding.
+//   residuals / fluxes (granular API) / step factors / volumes : SoA planes of length npad.
+//   edge slots  : per tile, per round, one block [hx[TN] | hy[TN] | hz[TN] | other[TN](u16)], h = -0.5 * (edge vector
+//                 oriented thread-node -> other); a tile's rounds are contiguous, so the edge stream is read once, coalesced.
+// No tensor cores: the path is gather/scatter, FP64- and LSU-bound (profiles/).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -8,181 +17,222 @@
 namespace mgcfd {
 
 #define MG_GAMMA 1.4
-// smoothing_coefficient = double(0.2f) (src/Base/common.h:24); -ewt*smoothing*0.5 == ewt*MG_KDISS exactly
-// (scaling by 0.5 and negation are exact)
 __device__ __constant__ double c_ff[5];      // ff_variable
 __device__ __constant__ double c_ffc[12];    // ff_flux_contribution_{momentum_x,y,z,density_energy}
 
-struct NodeVals { double rho, mx, my, mz, re, vx, vy, vz, p, s; };
-
-// compute_velocity / speed_sqd / pressure / speed_of_sound (src/Kernels/cfd_loops.h:121-148), true divisions kept
-__device__ __forceinline__ void derive(double rho, double mx, double my, double mz, double re,
-                                       double& vx, double& vy, double& vz, double& p, double& speed, double& sos) {
-    vx = mx / rho; vy = my / rho; vz = mz / rho;
-    const double sq = vx * vx + vy * vy + vz * vz;
-    speed = sqrt(sq);
-    p = (double(MG_GAMMA) - double(1.0)) * (re - double(0.5) * rho * sq);
-    sos = sqrt(double(MG_GAMMA) * p / rho);
-}
-
-// One internal edge seen from end A (the thread's node) towards B, (wx,wy,wz) = stored edge vector oriented A->B.
-// Returns A's five flux increments (flux_kernel.elemfunc.c:130-162); B's are their exact negation (:170-189 is the
-// same expression with every term negated, which IEEE arithmetic rounds symmetrically).
+struct Rec { double rho, mx, my, mz, re, ir, p, s; };   // ir = 1/rho, s = |v| + speed of sound
 struct Flux5 { double r, mx, my, mz, e; };
-__device__ __forceinline__ Flux5 edge_flux(const NodeVals& A, const NodeVals& B, double wx, double wy, double wz, double kdiss) {
-    const double ewt = sqrt(wx * wx + wy * wy + wz * wz);
-    const double factor = (ewt * kdiss) * (A.s + B.s);
-    const double fx = -0.5 * wx, fy = -0.5 * wy, fz = -0.5 * wz;
-    // flux contributions of both ends (cfd_loops.h:57-83); A's could be hoisted by the caller, the compiler does it
-    const double axx = A.vx * A.mx + A.p, axy = A.vx * A.my, axz = A.vx * A.mz;
-    const double ayy = A.vy * A.my + A.p, ayz = A.vy * A.mz, azz = A.vz * A.mz + A.p;
-    const double adp = A.re + A.p;
-    const double bxx = B.vx * B.mx + B.p, bxy = B.vx * B.my, bxz = B.vx * B.mz;
-    const double byy = B.vy * B.my + B.p, byz = B.vy * B.mz, bzz = B.vz * B.mz + B.p;
-    const double bdp = B.re + B.p;
-    Flux5 f;
-    f.r  = factor * (A.rho - B.rho) + fx * (A.mx + B.mx) + fy * (A.my + B.my) + fz * (A.mz + B.mz);
-    f.e  = factor * (A.re - B.re) + fx * (A.vx * adp + B.vx * bdp) + fy * (A.vy * adp + B.vy * bdp) + fz * (A.vz * adp + B.vz * bdp);
-    f.mx = factor * (A.mx - B.mx) + fx * (axx + bxx) + fy * (axy + bxy) + fz * (axz + bxz);
-    f.my = factor * (A.my - B.my) + fx * (axy + bxy) + fy * (ayy + byy) + fz * (ayz + byz);
-    f.mz = factor * (A.mz - B.mz) + fx * (axz + bxz) + fy * (ayz + byz) + fz * (azz + bzz);
-    return f;
-}
 
-// boundary edge (neighbour -1): flux_boundary_kernel.elemfunc.c:33-45
-__device__ __forceinline__ Flux5 boundary_flux(const NodeVals& B, double x, double y, double z) {
-    Flux5 f; f.r = 0.0; f.e = 0.0;
-    f.mx = x * B.p; f.my = y * B.p; f.mz = z * B.p;
-    return f;
-}
-// wall edge (neighbour -2, far field): flux_wall_kernel.elemfunc.c:47-69
-__device__ __forceinline__ Flux5 wall_flux(const NodeVals& B, double x, double y, double z) {
-    const double fx = 0.5 * x, fy = 0.5 * y, fz = 0.5 * z;
-    const double bxx = B.vx * B.mx + B.p, bxy = B.vx * B.my, bxz = B.vx * B.mz;
-    const double byy = B.vy * B.my + B.p, byz = B.vy * B.mz, bzz = B.vz * B.mz + B.p;
-    const double bdp = B.re + B.p;
-    Flux5 f;
-    f.r  = fx * (c_ff[1] + B.mx) + fy * (c_ff[2] + B.my) + fz * (c_ff[3] + B.mz);
-    f.e  = fx * (c_ffc[9] + B.vx * bdp) + fy * (c_ffc[10] + B.vy * bdp) + fz * (c_ffc[11] + B.vz * bdp);
-    f.mx = fx * (c_ffc[0] + bxx) + fy * (c_ffc[1] + bxy) + fz * (c_ffc[2] + bxz);
-    f.my = fx * (c_ffc[3] + bxy) + fy * (c_ffc[4] + byy) + fz * (c_ffc[5] + byz);
-    f.mz = fx * (c_ffc[6] + bxz) + fy * (c_ffc[7] + byz) + fz * (c_ffc[8] + bzz);
-    return f;
-}
-
-__device__ __forceinline__ NodeVals load_node(const double* __restrict__ v, long stride, long i) {
-    NodeVals n;
-    n.rho = v[i]; n.mx = v[stride + i]; n.my = v[2 * stride + i]; n.mz = v[3 * stride + i]; n.re = v[4 * stride + i];
-    double speed, sos;
-    derive(n.rho, n.mx, n.my, n.mz, n.re, n.vx, n.vy, n.vz, n.p, speed, sos);
-    n.s = speed + sos;
+// per-node derived quantities (cfd_loops.h:121-148): velocity = momentum / rho, speed_sqd, pressure, speed of sound.
+// The reference divides three times by rho; here one correctly rounded reciprocal and three products (<= 1 ulp apart).
+__device__ __forceinline__ Rec make_rec(double rho, double mx, double my, double mz, double re) {
+    Rec n;
+    n.rho = rho; n.mx = mx; n.my = my; n.mz = mz; n.re = re;
+    n.ir = 1.0 / rho;
+    const double vx = mx * n.ir, vy = my * n.ir, vz = mz * n.ir;
+    const double sq = vx * vx + vy * vy + vz * vz;
+    n.p = (double(MG_GAMMA) - double(1.0)) * (re - double(0.5) * rho * sq);
+    n.s = sqrt(sq) + sqrt(double(MG_GAMMA) * n.p * n.ir);
     return n;
 }
 
+__device__ __forceinline__ Rec load_rec(const double* __restrict__ recs, long i) {
+    const double2* p = reinterpret_cast<const double2*>(recs + 8 * i);
+    const double2 a = p[0], b = p[1], c = p[2], d = p[3];
+    Rec n; n.rho = a.x; n.mx = a.y; n.my = b.x; n.mz = b.y; n.re = c.x; n.ir = c.y; n.p = d.x; n.s = d.y;
+    return n;
+}
+__device__ __forceinline__ void store_rec(double* __restrict__ recs, long i, const Rec& n) {
+    double2* p = reinterpret_cast<double2*>(recs + 8 * i);
+    p[0] = make_double2(n.rho, n.mx); p[1] = make_double2(n.my, n.mz); p[2] = make_double2(n.re, n.ir); p[3] = make_double2(n.p, n.s);
+}
+// shared-memory copy of a record: 16-byte chunk k of record o lives at chunk k ^ ((o >> 1) & 3) of its 64-byte row, the
+// 64B swizzle pattern, so that the 8 lanes of a quarter-warp reading chunk k of 8 consecutive records hit 8 distinct bank groups
+__device__ __forceinline__ void sm_store_rec(double2* sm, int o, const double2& a, const double2& b, const double2& c, const double2& d) {
+    double2* row = sm + 4 * o;
+    const int x = (o >> 1) & 3;
+    row[0 ^ x] = a; row[1 ^ x] = b; row[2 ^ x] = c; row[3 ^ x] = d;
+}
+__device__ __forceinline__ Rec sm_load_rec(const double2* sm, int o) {
+    const double2* row = sm + 4 * o;
+    const int x = (o >> 1) & 3;
+    const double2 a = row[0 ^ x], b = row[1 ^ x], c = row[2 ^ x], d = row[3 ^ x];
+    Rec n; n.rho = a.x; n.mx = a.y; n.my = b.x; n.mz = b.y; n.re = c.x; n.ir = c.y; n.p = d.x; n.s = d.y;
+    return n;
+}
+
+// One internal edge seen from end A towards B; (hx,hy,hz) = -0.5 * stored edge vector oriented A->B; k2 = 2*kdiss with
+// kdiss = -0.5*smoothing_coefficient (src/Base/common.h:24), so that |e|*kdiss == |h|*k2 exactly.
+// Adds A's five flux increments (flux_kernel.elemfunc.c:130-162) to acc; B's increments are their exact negation (:170-189).
+// Algebra: sum_d h_d * flux_contribution_momentum_x[d] = mx*(h.v) + p*hx etc. (cfd_loops.h:57-83), with h.v = (h.m)/rho.
+__device__ __forceinline__ void edge_flux_acc(const Rec& A, double A_ep, const Rec& B, double hx, double hy, double hz, double k2, Flux5& acc) {
+    const double ewt = sqrt(hx * hx + hy * hy + hz * hz);
+    const double factor = (ewt * k2) * (A.s + B.s);
+    const double gA = hx * A.mx + hy * A.my + hz * A.mz;
+    const double gB = hx * B.mx + hy * B.my + hz * B.mz;
+    const double qA = gA * A.ir, qB = gB * B.ir;
+    const double ps = A.p + B.p;
+    acc.r  += factor * (A.rho - B.rho) + (gA + gB);
+    acc.e  += factor * (A.re - B.re) + (A_ep * qA + (B.re + B.p) * qB);
+    acc.mx += factor * (A.mx - B.mx) + (A.mx * qA + B.mx * qB + ps * hx);
+    acc.my += factor * (A.my - B.my) + (A.my * qA + B.my * qB + ps * hy);
+    acc.mz += factor * (A.mz - B.mz) + (A.mz * qA + B.mz * qB + ps * hz);
+}
+__device__ __forceinline__ Flux5 edge_flux(const Rec& A, const Rec& B, double hx, double hy, double hz, double k2) {
+    Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
+    edge_flux_acc(A, A.re + A.p, B, hx, hy, hz, k2, f);
+    return f;
+}
+// boundary edge (neighbour -1): flux_boundary_kernel.elemfunc.c:33-45; (x,y,z) = stored edge vector
+__device__ __forceinline__ void boundary_flux_acc(const Rec& B, double x, double y, double z, Flux5& acc) {
+    acc.mx += x * B.p; acc.my += y * B.p; acc.mz += z * B.p;
+}
+// wall edge (neighbour -2, far field): flux_wall_kernel.elemfunc.c:47-69
+__device__ __forceinline__ void wall_flux_acc(const Rec& B, double x, double y, double z, Flux5& acc) {
+    const double fx = 0.5 * x, fy = 0.5 * y, fz = 0.5 * z;
+    const double g = fx * B.mx + fy * B.my + fz * B.mz;
+    const double q = g * B.ir;
+    acc.r  += (fx * c_ff[1] + fy * c_ff[2] + fz * c_ff[3]) + g;
+    acc.e  += (fx * c_ffc[9] + fy * c_ffc[10] + fz * c_ffc[11]) + (B.re + B.p) * q;
+    acc.mx += (fx * c_ffc[0] + fy * c_ffc[1] + fz * c_ffc[2]) + (B.mx * q + B.p * fx);
+    acc.my += (fx * c_ffc[3] + fy * c_ffc[4] + fz * c_ffc[5]) + (B.my * q + B.p * fy);
+    acc.mz += (fx * c_ffc[6] + fy * c_ffc[7] + fz * c_ffc[8]) + (B.mz * q + B.p * fz);
+}
+
 // ------------------------------------------------------------------------------------------------------
-// Tiled, coloured flux kernel.  One CTA = one tile of TN owned nodes (thread t <-> node tile*TN+t).
-//   phase 1: owned + halo node state is staged in shared memory together with the derived quantities
-//            (velocity, pressure, |v|+c), computed ONCE per node per tile instead of twice per edge;
-//   phase 2: colour rounds.  In round r thread t evaluates the edge in its slot r, keeps its own end's
-//            increment in registers and scatters the other end's (the exact negation) into a shared
-//            accumulator.  The host colouring guarantees that within one round no two threads of the CTA
-//            target the same node, so plain shared-memory read-modify-writes suffice: no atomics, fixed
-//            summation order, bit-reproducible.  Edges cut by a tile boundary are evaluated by both tiles
-//            (owner-computes), so nothing is ever scattered outside the tile;
-//   phase 3: FUSED: the Runge-Kutta update of time_step (cfd_loops.cpp:215-280) is applied directly,
-//            the flux never touches HBM; on the last stage residual, RMS partials and the validity check
-//            (validation.cpp:77-138) ride along.  !FUSED: fluxes[node] += total (granular API).
+// The stage kernel: one CTA = one tile of TN owned nodes (thread t <-> node tile*TN+t), one launch = one Runge-Kutta
+// stage of one smoothing visit (compute_flux_edge + compute_boundary_flux_edge + compute_wall_flux_edge + time_step,
+// euler3d_cpu_double.cpp:397-506), the flux never touching HBM.
+//   phase 1: the records of the owned nodes and of the tile's halo (nodes of other tiles adjacent to it) are staged in
+//            shared memory (swizzled rows);
+//   phase 2: edge rounds.
+//            SCATTER = false (sorted-segment): every node walks ALL its incident edges (its CSR segment, original edge
+//              order), each edge is evaluated from both of its ends, nothing is ever written to another node: no colouring,
+//              no barriers inside the loop, no atomics, bit-reproducible;
+//            SCATTER = true (coloured): an edge inside the tile is evaluated by one of its ends, which adds the negated
+//              increment to a shared accumulator of the other end; the host colouring guarantees that within one round no
+//              two threads of the CTA target the same node (no atomics, fixed order, bit-reproducible); edges cut by a
+//              tile boundary are evaluated by both tiles (owner computes);
+//   phase 3: FUSED: time_step (cfd_loops.cpp:215-280) applied directly, the new record (state + derived quantities)
+//            written once; on the last stage residual (validation.cpp:77-89), RMS partials (:91-105) and the validity
+//            check (:107-138) ride along.  !FUSED (granular API): fluxes[node] += total.
 // ------------------------------------------------------------------------------------------------------
-struct TileArgs {
-    const double* vin;     // stage input state
-    const double* vold;    // old_variables (FUSED)
-    double* vout;          // stage output state (FUSED) or fluxes (+=) (!FUSED)
-    double* res;           // residuals (last stage) or nullptr
+struct StageArgs {
+    const double* vin;     // records: stage input state
+    const double* vold;    // records: old_variables (FUSED)
+    double* vout;          // records: stage output state (FUSED)
+    double* flux;          // SoA fluxes (+=) (!FUSED)
+    double* res;           // SoA residuals (last stage) or nullptr
     const double* sf;      // step factors
-    long stride;
+    long stride;           // npad
     const long* halo_off; const int* halo_ids;
-    const long* slot_off; const int* tile_rounds; const uint16_t* slot_other; const double* slot_w; long nslots;
-    const long* bslot_off; const int* tile_brounds; const uint8_t* bslot_kind; const double* bslot_w; long nbslots;
+    const long* slot_off;  // per tile: first round block of the tile (prefix sum of rounds); slot_off[ntiles] = total
+    const unsigned char* slots;   // round blocks of TN*26 bytes
+    const long* bslot_off; const unsigned char* bslots;   // boundary/wall round blocks of TN*25 bytes
     double rk_div;         // double(RK+1-j)
-    double kdiss;
+    double k2;             // 2 * kdiss
     double* rms_partial;   // [ntiles][5] or nullptr
     unsigned long long* bad_key;  // invalid-state key or nullptr
     const int* old_of_new;
     unsigned long long stage_seq;
     int mask;              // bit0 internal, bit1 boundary, bit2 wall
-    int smem_nodes;        // plane length of the staged state (TN + max halo, padded)
 };
 
-template <int TN, bool FUSED>
-__global__ void __launch_bounds__(TN, (TN <= 256 ? 2 : 1))
-k_tile_flux(const TileArgs a) {
-    extern __shared__ double sm[];
-    const int NL = a.smem_nodes;
-    double* st = sm;                 // [10][NL]
-    double* acc = sm + 10 * NL;      // [5][TN]
+template <int TN, bool SCATTER, bool FUSED>
+__global__ void __launch_bounds__(TN, (TN <= 128 ? 5 : (TN <= 256 ? 2 : 1)))
+k_stage(const StageArgs a) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double2* st = reinterpret_cast<double2*>(smraw);          // [(TN + nh) records][4 chunks]
     const int t = threadIdx.x;
     const long tile = blockIdx.x;
     const long gid = tile * TN + t;
     const long h0 = a.halo_off[tile];
     const int nh = int(a.halo_off[tile + 1] - h0);
+    double* acc = reinterpret_cast<double*>(st + 4 * (TN + ((nh + 3) & ~3)));   // SCATTER: [5][TN]
 
-    NodeVals me = load_node(a.vin, a.stride, gid);
-    st[0 * NL + t] = me.rho; st[1 * NL + t] = me.mx; st[2 * NL + t] = me.my; st[3 * NL + t] = me.mz; st[4 * NL + t] = me.re;
-    st[5 * NL + t] = me.vx;  st[6 * NL + t] = me.vy; st[7 * NL + t] = me.vz; st[8 * NL + t] = me.p;  st[9 * NL + t] = me.s;
-    for (int h = t; h < nh; h += TN) {
-        const NodeVals o = load_node(a.vin, a.stride, a.halo_ids[h0 + h]);
-        const int l = TN + h;
-        st[0 * NL + l] = o.rho; st[1 * NL + l] = o.mx; st[2 * NL + l] = o.my; st[3 * NL + l] = o.mz; st[4 * NL + l] = o.re;
-        st[5 * NL + l] = o.vx;  st[6 * NL + l] = o.vy; st[7 * NL + l] = o.vz; st[8 * NL + l] = o.p;  st[9 * NL + l] = o.s;
+    // ---- phase 1: stage records ----
+    Rec me;
+    {
+        const double2* p = reinterpret_cast<const double2*>(a.vin + 8 * gid);
+        const double2 c0 = p[0], c1 = p[1], c2 = p[2], c3 = p[3];
+        sm_store_rec(st, t, c0, c1, c2, c3);
+        me.rho = c0.x; me.mx = c0.y; me.my = c1.x; me.mz = c1.y; me.re = c2.x; me.ir = c2.y; me.p = c3.x; me.s = c3.y;
     }
+    for (int h = t; h < nh; h += TN) {
+        const double2* p = reinterpret_cast<const double2*>(a.vin + 8 * (long)a.halo_ids[h0 + h]);
+        const double2 c0 = p[0], c1 = p[1], c2 = p[2], c3 = p[3];
+        sm_store_rec(st, TN + h, c0, c1, c2, c3);
+    }
+    if (SCATTER) {
 #pragma unroll
-    for (int k = 0; k < 5; k++) acc[k * TN + t] = 0.0;
+        for (int k = 0; k < 5; k++) acc[k * TN + t] = 0.0;
+    }
     __syncthreads();
 
-    double fr = 0.0, fmx = 0.0, fmy = 0.0, fmz = 0.0, fe = 0.0;
+    // ---- phase 2: edge rounds ----
+    Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const double me_ep = me.re + me.p;
     if (a.mask & 1) {
-        const int rounds = a.tile_rounds[tile];
-        const long s0 = a.slot_off[tile] + t;
-        for (int r = 0; r < rounds; r++) {
-            const long si = s0 + long(r) * TN;
-            const unsigned o = a.slot_other[si];
-            if (o != 0xFFFFu) {
-                const double wx = a.slot_w[si], wy = a.slot_w[a.nslots + si], wz = a.slot_w[2 * a.nslots + si];
-                NodeVals B;
-                B.rho = st[0 * NL + o]; B.mx = st[1 * NL + o]; B.my = st[2 * NL + o]; B.mz = st[3 * NL + o]; B.re = st[4 * NL + o];
-                B.vx = st[5 * NL + o];  B.vy = st[6 * NL + o]; B.vz = st[7 * NL + o]; B.p = st[8 * NL + o];  B.s = st[9 * NL + o];
-                const Flux5 f = edge_flux(me, B, wx, wy, wz, a.kdiss);
-                fr += f.r; fmx += f.mx; fmy += f.my; fmz += f.mz; fe += f.e;
-                if (o < (unsigned)TN) {   // owned by this tile: conflict-free by colouring
-                    acc[0 * TN + o] -= f.r; acc[1 * TN + o] -= f.mx; acc[2 * TN + o] -= f.my; acc[3 * TN + o] -= f.mz; acc[4 * TN + o] -= f.e;
-                }
+        const long b0 = a.slot_off[tile];
+        const int rounds = int(a.slot_off[tile + 1] - b0);
+        const unsigned char* blk = a.slots + b0 * (long)(TN * 26);
+        if (!SCATTER) {
+#pragma unroll 2
+            for (int r = 0; r < rounds; r++, blk += TN * 26) {
+                const double* w = reinterpret_cast<const double*>(blk);
+                const unsigned o = reinterpret_cast<const unsigned short*>(blk + TN * 24)[t];
+                const double hx = w[t], hy = w[TN + t], hz = w[2 * TN + t];
+                const Rec B = sm_load_rec(st, o);             // empty slots point at the node itself with h = 0: exact zeros
+                edge_flux_acc(me, me_ep, B, hx, hy, hz, a.k2, f);
             }
-            __syncthreads();
+        } else {
+            for (int r = 0; r < rounds; r++, blk += TN * 26) {
+                const double* w = reinterpret_cast<const double*>(blk);
+                const unsigned o = reinterpret_cast<const unsigned short*>(blk + TN * 24)[t];
+                if (o != 0xFFFFu) {
+                    const double hx = w[t], hy = w[TN + t], hz = w[2 * TN + t];
+                    const Rec B = sm_load_rec(st, o);
+                    Flux5 g = {0.0, 0.0, 0.0, 0.0, 0.0};
+                    edge_flux_acc(me, me_ep, B, hx, hy, hz, a.k2, g);
+                    f.r += g.r; f.mx += g.mx; f.my += g.my; f.mz += g.mz; f.e += g.e;
+                    if (o < (unsigned)TN) {   // owned by this tile: conflict-free by colouring
+                        acc[0 * TN + o] -= g.r; acc[1 * TN + o] -= g.mx; acc[2 * TN + o] -= g.my; acc[3 * TN + o] -= g.mz; acc[4 * TN + o] -= g.e;
+                    }
+                }
+                __syncthreads();
+            }
         }
     }
     if (a.mask & 6) {
-        const int br = a.tile_brounds[tile];
-        const long b0 = a.bslot_off[tile] + t;
-        for (int r = 0; r < br; r++) {
-            const long si = b0 + long(r) * TN;
-            const int kind = a.bslot_kind[si];
+        const long b0 = a.bslot_off[tile];
+        const int br = int(a.bslot_off[tile + 1] - b0);
+        const unsigned char* blk = a.bslots + b0 * (long)(TN * 25);
+        for (int r = 0; r < br; r++, blk += TN * 25) {
+            const int kind = blk[TN * 24 + t];
             if (kind == 0 || !((a.mask >> kind) & 1)) continue;
-            const double x = a.bslot_w[si], y = a.bslot_w[a.nbslots + si], z = a.bslot_w[2 * a.nbslots + si];
-            const Flux5 f = (kind == 1) ? boundary_flux(me, x, y, z) : wall_flux(me, x, y, z);
-            fr += f.r; fmx += f.mx; fmy += f.my; fmz += f.mz; fe += f.e;
+            const double* w = reinterpret_cast<const double*>(blk);
+            if (kind == 1) boundary_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
+            else wall_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
         }
     }
-    fr += acc[0 * TN + t]; fmx += acc[1 * TN + t]; fmy += acc[2 * TN + t]; fmz += acc[3 * TN + t]; fe += acc[4 * TN + t];
+    if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
 
+    // ---- phase 3 ----
     const long S = a.stride;
     if (!FUSED) {
-        a.vout[gid] += fr; a.vout[S + gid] += fmx; a.vout[2 * S + gid] += fmy; a.vout[3 * S + gid] += fmz; a.vout[4 * S + gid] += fe;
+        a.flux[gid] += f.r; a.flux[S + gid] += f.mx; a.flux[2 * S + gid] += f.my; a.flux[3 * S + gid] += f.mz; a.flux[4 * S + gid] += f.e;
         return;
     } else {
         const double factor = a.sf[gid] / a.rk_div;     // a true divide, cfd_loops.cpp:243
-        const double o0 = a.vold[gid], o1 = a.vold[S + gid], o2 = a.vold[2 * S + gid], o3 = a.vold[3 * S + gid], o4 = a.vold[4 * S + gid];
-        const double n0 = o0 + factor * fr, n1 = o1 + factor * fmx, n2 = o2 + factor * fmy, n3 = o3 + factor * fmz, n4 = o4 + factor * fe;
-        a.vout[gid] = n0; a.vout[S + gid] = n1; a.vout[2 * S + gid] = n2; a.vout[3 * S + gid] = n3; a.vout[4 * S + gid] = n4;
+        double o0, o1, o2, o3, o4;
+        if (a.vold == a.vin) { o0 = me.rho; o1 = me.mx; o2 = me.my; o3 = me.mz; o4 = me.re; }
+        else {
+            const double2* p = reinterpret_cast<const double2*>(a.vold + 8 * gid);
+            const double2 c0 = p[0], c1 = p[1];
+            o0 = c0.x; o1 = c0.y; o2 = c1.x; o3 = c1.y; o4 = a.vold[8 * gid + 4];
+        }
+        const double n0 = o0 + factor * f.r, n1 = o1 + factor * f.mx, n2 = o2 + factor * f.my, n3 = o3 + factor * f.mz, n4 = o4 + factor * f.e;
+        store_rec(a.vout, gid, make_rec(n0, n1, n2, n3, n4));
         if (a.bad_key) {
             // check_for_invalid_variables (validation.cpp:107-138): first offending cell of the first offending stage
             int reason = 0;
@@ -198,8 +248,8 @@ k_tile_flux(const TileArgs a) {
             const double r0 = n0 - o0, r1 = n1 - o1, r2 = n2 - o2, r3 = n3 - o3, r4 = n4 - o4;   // residual(), validation.cpp:77-89
             a.res[gid] = r0; a.res[S + gid] = r1; a.res[2 * S + gid] = r2; a.res[3 * S + gid] = r3; a.res[4 * S + gid] = r4;
             if (a.rms_partial) {
-                // deterministic block reduction of r^2 per variable: warp shuffles, then warp 0 over the warp sums
-                __syncthreads();   // acc is free again
+                // deterministic block reduction of r^2 per variable: warp shuffles, then 5 threads over the warp sums
+                __shared__ double ws[5][32];
                 double q[5] = {r0 * r0, r1 * r1, r2 * r2, r3 * r3, r4 * r4};
 #pragma unroll
                 for (int k = 0; k < 5; k++) {
@@ -208,12 +258,12 @@ k_tile_flux(const TileArgs a) {
                 }
                 if ((t & 31) == 0) {
 #pragma unroll
-                    for (int k = 0; k < 5; k++) acc[k * 32 + (t >> 5)] = q[k];
+                    for (int k = 0; k < 5; k++) ws[k][t >> 5] = q[k];
                 }
                 __syncthreads();
                 if (t < 5) {
                     double s = 0.0;
-                    for (int w = 0; w < TN / 32; w++) s += acc[t * 32 + w];
+                    for (int w = 0; w < TN / 32; w++) s += ws[t][w];
                     a.rms_partial[tile * 5 + t] = s;
                 }
             }
@@ -224,19 +274,19 @@ k_tile_flux(const TileArgs a) {
 // ------------------------------------------------------------------------------------------------------
 // node kernels
 // ------------------------------------------------------------------------------------------------------
-// compute_step_factor (cfd_loops.cpp:76-157) part 1 / compute_step_factor_legacy (:13-73)
+// compute_step_factor (cfd_loops.cpp:76-157) part 1 / compute_step_factor_legacy (:13-73); speed + speed_of_sound is the
+// record's s
 template <bool LEGACY>
-__global__ void k_step_factor(const double* __restrict__ v, long stride, long n, const double* __restrict__ vol_root,
+__global__ void k_step_factor(const double* __restrict__ recs, long n, const double* __restrict__ vol_root,
                               double* __restrict__ sf, unsigned long long* __restrict__ min_bits) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double val = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
     if (i < n) {
-        double vx, vy, vz, p, speed, sos;
-        derive(v[i], v[stride + i], v[2 * stride + i], v[3 * stride + i], v[4 * stride + i], vx, vy, vz, p, speed, sos);
+        const double s = recs[8 * i + 7];
         if (LEGACY) {
-            sf[i] = double(0.5) / (sqrt(vol_root[i]) * (speed + sos));   // vol_root = volumes here; IEEE sqrt, cfd_loops.cpp:60
+            sf[i] = double(0.5) / (sqrt(vol_root[i]) * s);   // vol_root = volumes here; IEEE sqrt, cfd_loops.cpp:60
         } else {
-            const double dt = vol_root[i] / (speed + sos);           // vol_root = cbrt(volume) (host glibc), :123
+            const double dt = vol_root[i] / s;               // vol_root = cbrt(volume) (host glibc), :123
             val = 0.5 * dt;
         }
     }
@@ -267,30 +317,33 @@ __global__ void k_time_step(double rk_div, long n, long stride, const double* __
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double factor = sf[i] / rk_div;
+    double nv[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) {
-        v[k * stride + i] = vold[k * stride + i] + factor * flux[k * stride + i];
+        nv[k] = vold[8 * i + k] + factor * flux[k * stride + i];
         flux[k * stride + i] = 0.0;
     }
+    store_rec(v, i, make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]));
 }
 __global__ void k_fill(double* __restrict__ p, long n, double val) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i < n) p[i] = val;
 }
-__global__ void k_fill_state(double* __restrict__ p, long stride, long n) {
+__global__ void k_fill_state(double* __restrict__ recs, long n) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-#pragma unroll
-    for (int k = 0; k < 5; k++) p[k * stride + i] = c_ff[k];
+    store_rec(recs, i, make_rec(c_ff[0], c_ff[1], c_ff[2], c_ff[3], c_ff[4]));
 }
 __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, long n) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
 }
 // residual (validation.cpp:77-89)
-__global__ void k_residual(long n, const double* __restrict__ vold, const double* __restrict__ v, double* __restrict__ r) {
+__global__ void k_residual(long n, long stride, const double* __restrict__ vold, const double* __restrict__ v, double* __restrict__ r) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i < n) r[i] = v[i] - vold[i];
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 5; k++) r[k * stride + i] = v[8 * i + k] - vold[8 * i + k];
 }
 // calc_rms (validation.cpp:91-105) stage 1: per-block sums of r^2 per variable (fixed order => deterministic)
 __global__ void k_rms_partial(const double* __restrict__ r, long stride, long n, double* __restrict__ partial) {
@@ -338,13 +391,13 @@ __global__ void k_rms_final(const double* __restrict__ partial, long nparts, dou
     }
 }
 // check_for_invalid_variables (validation.cpp:107-138): lowest offending cell in reference order + reason
-__global__ void k_check_invalid(const double* __restrict__ v, long stride, long n, const int* __restrict__ old_of_new,
+__global__ void k_check_invalid(const double* __restrict__ recs, long n, const int* __restrict__ old_of_new,
                                 unsigned long long* __restrict__ key) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int oi = old_of_new[i];
     if (oi < 0) return;
-    const double a0 = v[i], a1 = v[stride + i], a2 = v[2 * stride + i], a3 = v[3 * stride + i], a4 = v[4 * stride + i];
+    const double a0 = recs[8 * i], a1 = recs[8 * i + 1], a2 = recs[8 * i + 2], a3 = recs[8 * i + 3], a4 = recs[8 * i + 4];
     int reason = 0;
     if (!(isfinite(a0) && isfinite(a1) && isfinite(a2) && isfinite(a3) && isfinite(a4))) reason = 1;
     else if (a0 < 0.0) reason = 2;
@@ -357,7 +410,7 @@ __global__ void k_check_invalid(const double* __restrict__ v, long stride, long 
 // ------------------------------------------------------------------------------------------------------
 // mg_restrict (mg_loops.cpp:30-202) as a gather: children summed in ascending original fine index (the reference's
 // accumulation order, bit for bit), then multiplied by 1.0/count; coarse nodes without children keep their value.
-__global__ void k_restrict(const double* __restrict__ vf, long sfine, double* __restrict__ vc, long scoarse, long ncoarse,
+__global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ vc, long ncoarse,
                            const long* __restrict__ child_off, const int* __restrict__ child_ids) {
     const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (c >= ncoarse) return;
@@ -365,13 +418,13 @@ __global__ void k_restrict(const double* __restrict__ vf, long sfine, double* __
     if (k1 == k0) return;
     double s[5] = {0, 0, 0, 0, 0};
     for (long k = k0; k < k1; k++) {
-        const long f = child_ids[k];
-#pragma unroll
-        for (int j = 0; j < 5; j++) s[j] += vf[j * sfine + f];
+        const double2* p = reinterpret_cast<const double2*>(vf + 8 * (long)child_ids[k]);
+        const double2 c0 = p[0], c1 = p[1];
+        const double e = vf[8 * (long)child_ids[k] + 4];
+        s[0] += c0.x; s[1] += c0.y; s[2] += c1.x; s[3] += c1.y; s[4] += e;
     }
     const double average = 1.0 / (double)(k1 - k0);
-#pragma unroll
-    for (int j = 0; j < 5; j++) vc[j * scoarse + c] = s[j] * average;
+    store_rec(vc, c, make_rec(s[0] * average, s[1] * average, s[2] * average, s[3] * average, s[4] * average));
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
 // edges in original edge order: per edge the own-parent term then the neighbour-parent term (whose source is the own
@@ -410,25 +463,27 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
             wsum += w;
         }
     }
+    double nv[5];
 #pragma unroll
     for (int j = 0; j < 5; j++) {
         const double avg = acc[j] / wsum;
-        var_f[j * sfine + i] += res_f[j * sfine + i] - avg;
+        nv[j] = var_f[8 * i + j] + (res_f[j * sfine + i] - avg);
     }
+    store_rec(var_f, i, make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]));
 }
 
 // ------------------------------------------------------------------------------------------------------
-// alternative flux modes and the bandwidth probe
+// alternative flux path and the bandwidth probe (node-ordering sweeps, BASELINE.json config 5)
 // ------------------------------------------------------------------------------------------------------
-// one thread per internal edge, fp64 atomics (RED.ADD.F64): baseline + node-ordering sweep kernel
+// one thread per internal edge in ORIGINAL edge order, fp64 atomics (RED.ADD.F64): baseline + ordering-sweep kernel
 __global__ void k_flux_atomic(long ne, const int* __restrict__ ea, const int* __restrict__ eb, const double* __restrict__ ew,
-                              const double* __restrict__ v, long stride, double* __restrict__ flux, double kdiss) {
+                              const double* __restrict__ recs, long stride, double* __restrict__ flux, double k2) {
     const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (e >= ne) return;
     const int a = ea[e], b = eb[e];
-    const NodeVals B = load_node(v, stride, b);
-    const NodeVals A = load_node(v, stride, a);
-    const Flux5 f = edge_flux(A, B, ew[e], ew[ne + e], ew[2 * ne + e], kdiss);
+    const Rec B = load_rec(recs, b);
+    const Rec A = load_rec(recs, a);
+    const Flux5 f = edge_flux(A, B, -0.5 * ew[e], -0.5 * ew[ne + e], -0.5 * ew[2 * ne + e], k2);
     atomicAdd(&flux[a], f.r); atomicAdd(&flux[stride + a], f.mx); atomicAdd(&flux[2 * stride + a], f.my);
     atomicAdd(&flux[3 * stride + a], f.mz); atomicAdd(&flux[4 * stride + a], f.e);
     atomicAdd(&flux[b], -f.r); atomicAdd(&flux[stride + b], -f.mx); atomicAdd(&flux[2 * stride + b], -f.my);
@@ -436,66 +491,59 @@ __global__ void k_flux_atomic(long ne, const int* __restrict__ ea, const int* __
 }
 // boundary + wall edges, one thread per edge (a node can carry several, hence atomics)
 __global__ void k_bflux_atomic(long nb, const int* __restrict__ bnode, const uint8_t* __restrict__ bkind, const double* __restrict__ bw,
-                               const double* __restrict__ v, long stride, double* __restrict__ flux, int mask) {
+                               const double* __restrict__ recs, long stride, double* __restrict__ flux, int mask) {
     const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (e >= nb) return;
     const int kind = bkind[e];
     if (!((mask >> kind) & 1)) return;
     const int b = bnode[e];
-    const NodeVals B = load_node(v, stride, b);
-    const Flux5 f = (kind == 1) ? boundary_flux(B, bw[e], bw[nb + e], bw[2 * nb + e]) : wall_flux(B, bw[e], bw[nb + e], bw[2 * nb + e]);
+    const Rec B = load_rec(recs, b);
+    Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
+    if (kind == 1) boundary_flux_acc(B, bw[e], bw[nb + e], bw[2 * nb + e], f);
+    else wall_flux_acc(B, bw[e], bw[nb + e], bw[2 * nb + e], f);
     atomicAdd(&flux[b], f.r); atomicAdd(&flux[stride + b], f.mx); atomicAdd(&flux[2 * stride + b], f.my);
     atomicAdd(&flux[3 * stride + b], f.mz); atomicAdd(&flux[4 * stride + b], f.e);
 }
-// deterministic sorted-segment mode: one thread per node walks its CSR segment (original edge order) and evaluates
-// every incident edge from its own end; nothing is scattered (the reference's FLUX_FISSION + update_edges analogue,
-// cfd_loops.cpp:159-213, without materialising per-edge values)
-__global__ void k_flux_segment(long n, const long* __restrict__ adj_off, const int* __restrict__ adj_nbr, const double* __restrict__ adj_w,
-                               long nadj, const double* __restrict__ v, long stride, double* __restrict__ flux, double kdiss) {
-    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const long k0 = adj_off[i], k1 = adj_off[i + 1];
-    if (k1 == k0) return;
-    const NodeVals A = load_node(v, stride, i);
-    double fr = 0, fmx = 0, fmy = 0, fmz = 0, fe = 0;
-    for (long k = k0; k < k1; k++) {
-        const int raw = adj_nbr[k];
-        const double sg = raw < 0 ? -1.0 : 1.0;
-        const NodeVals B = load_node(v, stride, raw & 0x7fffffff);
-        const Flux5 f = edge_flux(A, B, sg * adj_w[k], sg * adj_w[nadj + k], sg * adj_w[2 * nadj + k], kdiss);
-        fr += f.r; fmx += f.mx; fmy += f.my; fmz += f.mz; fe += f.e;
-    }
-    flux[i] += fr; flux[stride + i] += fmx; flux[2 * stride + i] += fmy; flux[3 * stride + i] += fmz; flux[4 * stride + i] += fe;
-}
 // indirect_rw (indirect_rw_kernel.elemfunc.c): same gather/scatter as the flux kernel, no arithmetic to speak of
 __global__ void k_indirect_rw(long ne, const int* __restrict__ ea, const int* __restrict__ eb, const double* __restrict__ ew,
-                              const double* __restrict__ v, long stride, double* __restrict__ flux) {
+                              const double* __restrict__ recs, long stride, double* __restrict__ flux) {
     const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (e >= ne) return;
     const int a = ea[e], b = eb[e];
     const double ex = ew[e], ey = ew[ne + e], ez = ew[2 * ne + e];
-    const double ra = v[a], mxa = v[stride + a], mya = v[2 * stride + a], mza = v[3 * stride + a], ea_ = v[4 * stride + a];
-    const double rb = v[b], mxb = v[stride + b], myb = v[2 * stride + b], mzb = v[3 * stride + b], eb_ = v[4 * stride + b];
-    atomicAdd(&flux[a], rb + ex); atomicAdd(&flux[4 * stride + a], eb_ + ey); atomicAdd(&flux[stride + a], mxb + ez);
-    atomicAdd(&flux[2 * stride + a], myb); atomicAdd(&flux[3 * stride + a], mzb);
-    atomicAdd(&flux[b], ra); atomicAdd(&flux[4 * stride + b], ea_); atomicAdd(&flux[stride + b], mxa);
-    atomicAdd(&flux[2 * stride + b], mya); atomicAdd(&flux[3 * stride + b], mza);
+    const Rec A = load_rec(recs, a), B = load_rec(recs, b);
+    atomicAdd(&flux[a], B.rho + ex); atomicAdd(&flux[4 * stride + a], B.re + ey); atomicAdd(&flux[stride + a], B.mx + ez);
+    atomicAdd(&flux[2 * stride + a], B.my); atomicAdd(&flux[3 * stride + a], B.mz);
+    atomicAdd(&flux[b], A.rho); atomicAdd(&flux[4 * stride + b], A.re); atomicAdd(&flux[stride + b], A.mx);
+    atomicAdd(&flux[2 * stride + b], A.my); atomicAdd(&flux[3 * stride + b], A.mz);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// layout conversion at the boundary: reference AoS (old order) <-> device SoA (new order, padded)
+// layout conversion at the boundary: reference AoS (old order) <-> device (new order, padded)
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_export_aos(const double* __restrict__ soa, long stride, int ncomp, long nel, const int* __restrict__ new_of_old, double* __restrict__ aos) {
+__global__ void k_export_soa(const double* __restrict__ soa, long stride, int ncomp, long nel, const int* __restrict__ new_of_old, double* __restrict__ aos) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= nel) return;
     const long g = new_of_old[i];
     for (int k = 0; k < ncomp; k++) aos[i * ncomp + k] = soa[k * stride + g];
 }
-__global__ void k_import_aos(double* __restrict__ soa, long stride, int ncomp, long nel, const int* __restrict__ new_of_old, const double* __restrict__ aos) {
+__global__ void k_import_soa(double* __restrict__ soa, long stride, int ncomp, long nel, const int* __restrict__ new_of_old, const double* __restrict__ aos) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= nel) return;
     const long g = new_of_old[i];
     for (int k = 0; k < ncomp; k++) soa[k * stride + g] = aos[i * ncomp + k];
+}
+__global__ void k_export_recs(const double* __restrict__ recs, long nel, const int* __restrict__ new_of_old, double* __restrict__ aos) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= nel) return;
+    const long g = new_of_old[i];
+    for (int k = 0; k < 5; k++) aos[i * 5 + k] = recs[8 * g + k];
+}
+__global__ void k_import_recs(double* __restrict__ recs, long nel, const int* __restrict__ new_of_old, const double* __restrict__ aos) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= nel) return;
+    const long g = new_of_old[i];
+    store_rec(recs, g, make_rec(aos[i * 5], aos[i * 5 + 1], aos[i * 5 + 2], aos[i * 5 + 3], aos[i * 5 + 4]));
 }
 
 }  // namespace mgcfd

@@ -255,11 +255,6 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
             P.adj_nbr[pb] = int(uint32_t(a) | 0x80000000u); adj_eid[pb] = int(e);
         }
     }
-    P.adj_w.resize(3 * 2 * L.nI);
-    for (long k = 0; k < 2 * L.nI; k++) {
-        const long e = adj_eid[k];
-        P.adj_w[k] = P.ew[e]; P.adj_w[2 * L.nI + k] = P.ew[L.nI + e]; P.adj_w[4 * L.nI + k] = P.ew[2 * L.nI + e];
-    }
     // boundary/wall edges per node (CSR, original order)
     std::vector<long> bn_off(P.npad + 1, 0);
     for (long k = 0; k < nbw; k++) bn_off[P.bnode[k] + 1]++;
@@ -270,19 +265,17 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         for (long k = 0; k < nbw; k++) bn_idx[pos[P.bnode[k]]++] = k;
     }
 
-    // ---- 3. tiles: halo lists, edge ownership, colour rounds -----------------------------------------
+    // ---- 3. tiles: halo lists, edge rounds ------------------------------------------------------------
+    P.scatter = opt.scatter;
     P.halo_off.assign(P.ntiles + 1, 0);
     P.slot_off.assign(P.ntiles + 1, 0);
     P.bslot_off.assign(P.ntiles + 1, 0);
-    P.tile_rounds.assign(P.ntiles, 0);
-    P.tile_brounds.assign(P.ntiles, 0);
-    struct Slot { int owner; int colour; int other; long e; bool owner_is_a; };
+    struct Slot { int owner; int round; int other; long e; bool owner_is_a; };
     std::vector<Slot> slots;
     std::vector<int> halo;
     std::vector<Mask256> Lm(TN), Rm(TN);
     std::vector<int> nassigned(TN);
-    std::vector<int> slot_eid;
-    std::vector<signed char> slot_sgn;
+    const size_t BLK = size_t(TN) * 26, BBLK = size_t(TN) * 25;
     for (long t = 0; t < P.ntiles; t++) {
         const long base = t * TN;
         const int nown = P.tile_nown[t];
@@ -298,79 +291,86 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         P.halo_off[t + 1] = P.halo_off[t] + long(halo.size());
         P.halo_ids.insert(P.halo_ids.end(), halo.begin(), halo.end());
         P.max_halo = std::max(P.max_halo, int(halo.size()));
+        auto local_of = [&](int v) -> int {
+            if (v >= base && v < base + TN) return int(v - base);
+            return int(TN) + int(std::lower_bound(halo.begin(), halo.end(), v) - halo.begin());
+        };
 
-        for (int i = 0; i < nown; i++) { Lm[i] = Mask256(); Rm[i] = Mask256(); nassigned[i] = 0; }
         slots.clear();
-        // internal-to-tile edges first (visited from their `a` end, ascending edge index per node)
-        for (int lu = 0; lu < nown; lu++)
-            for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++) {
-                if (P.adj_nbr[k] < 0) continue;                   // this node is the `b` end: handled from `a`
-                const int v = P.adj_nbr[k];
-                if (v < base || v >= base + TN) continue;
-                const int lv = int(v - base);
-                const int c1 = Mask256::first_free(Lm[lu], Rm[lv]);   // lu computes, scatters into lv
-                const int c2 = Mask256::first_free(Lm[lv], Rm[lu]);
-                bool pick_u = c1 < c2 || (c1 == c2 && nassigned[lu] <= nassigned[lv]);
-                if (pick_u) { Lm[lu].set(c1); Rm[lv].set(c1); nassigned[lu]++; slots.push_back({lu, c1, lv, adj_eid[k], true}); }
-                else        { Lm[lv].set(c2); Rm[lu].set(c2); nassigned[lv]++; slots.push_back({lv, c2, lu, adj_eid[k], false}); }
+        if (!opt.scatter) {
+            // sorted-segment rounds: round r of a node = its r-th incident edge in ascending original edge index
+            for (int lu = 0; lu < nown; lu++) {
+                int r = 0;
+                for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++, r++) {
+                    const int v = P.adj_nbr[k] & 0x7fffffff;
+                    const bool cut = (v < base || v >= base + TN);
+                    slots.push_back({lu, r, local_of(v), adj_eid[k], P.adj_nbr[k] >= 0});
+                    if (cut) P.cut_edges++;
+                }
             }
-        // cut edges: computed by the owned end, the halo end is read-only
-        static const Mask256 none;
-        for (int lu = 0; lu < nown; lu++)
-            for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++) {
-                const int v = P.adj_nbr[k] & 0x7fffffff;
-                if (v >= base && v < base + TN) continue;
-                const int hl = int(std::lower_bound(halo.begin(), halo.end(), v) - halo.begin());
-                const int c = Mask256::first_free(Lm[lu], none);
-                Lm[lu].set(c); nassigned[lu]++;
-                slots.push_back({lu, c, int(TN) + hl, adj_eid[k], P.adj_nbr[k] >= 0});
-                P.cut_edges++;
-            }
+        } else {
+            for (int i = 0; i < nown; i++) { Lm[i] = Mask256(); Rm[i] = Mask256(); nassigned[i] = 0; }
+            // internal-to-tile edges first (visited from their `a` end, ascending edge index per node)
+            for (int lu = 0; lu < nown; lu++)
+                for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++) {
+                    if (P.adj_nbr[k] < 0) continue;                   // this node is the `b` end: handled from `a`
+                    const int v = P.adj_nbr[k];
+                    if (v < base || v >= base + TN) continue;
+                    const int lv = int(v - base);
+                    const int c1 = Mask256::first_free(Lm[lu], Rm[lv]);   // lu computes, scatters into lv
+                    const int c2 = Mask256::first_free(Lm[lv], Rm[lu]);
+                    bool pick_u = c1 < c2 || (c1 == c2 && nassigned[lu] <= nassigned[lv]);
+                    if (pick_u) { Lm[lu].set(c1); Rm[lv].set(c1); nassigned[lu]++; slots.push_back({lu, c1, lv, adj_eid[k], true}); }
+                    else        { Lm[lv].set(c2); Rm[lu].set(c2); nassigned[lv]++; slots.push_back({lv, c2, lu, adj_eid[k], false}); }
+                }
+            // cut edges: computed by the owned end, the halo end is read-only
+            static const Mask256 none;
+            for (int lu = 0; lu < nown; lu++)
+                for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++) {
+                    const int v = P.adj_nbr[k] & 0x7fffffff;
+                    if (v >= base && v < base + TN) continue;
+                    const int c = Mask256::first_free(Lm[lu], none);
+                    Lm[lu].set(c); nassigned[lu]++;
+                    slots.push_back({lu, c, local_of(v), adj_eid[k], P.adj_nbr[k] >= 0});
+                    P.cut_edges++;
+                }
+        }
         int rounds = 0;
-        for (const Slot& s : slots) rounds = std::max(rounds, s.colour + 1);
-        P.tile_rounds[t] = rounds;
+        for (const Slot& s : slots) rounds = std::max(rounds, s.round + 1);
         P.max_rounds = std::max(P.max_rounds, rounds);
-        const long s0 = P.slot_off[t];
-        P.slot_off[t + 1] = s0 + long(rounds) * TN;
-        P.slot_other.resize(P.slot_off[t + 1], 0xFFFF);
-        slot_eid.resize(P.slot_off[t + 1], -1);
-        slot_sgn.resize(P.slot_off[t + 1], 0);
+        const long b0 = P.slot_off[t];
+        P.slot_off[t + 1] = b0 + rounds;
+        P.slots.resize(size_t(P.slot_off[t + 1]) * BLK, 0);
+        // empty slots
+        for (int r = 0; r < rounds; r++) {
+            uint16_t* oth = reinterpret_cast<uint16_t*>(P.slots.data() + size_t(b0 + r) * BLK + size_t(TN) * 24);
+            for (int lu = 0; lu < TN; lu++) oth[lu] = opt.scatter ? uint16_t(0xFFFF) : uint16_t(lu);
+        }
         for (const Slot& s : slots) {
-            const long si = s0 + long(s.colour) * TN + s.owner;
-            P.slot_other[si] = uint16_t(s.other);
-            slot_eid[si] = int(s.e);
-            slot_sgn[si] = s.owner_is_a ? 1 : -1;
+            unsigned char* blk = P.slots.data() + size_t(b0 + s.round) * BLK;
+            double* w = reinterpret_cast<double*>(blk);
+            uint16_t* oth = reinterpret_cast<uint16_t*>(blk + size_t(TN) * 24);
+            const double sg = s.owner_is_a ? -0.5 : 0.5;      // h = -0.5 * vector(thread-node -> other); stored vector is a -> b
+            w[s.owner] = sg * P.ew[s.e];
+            w[TN + s.owner] = sg * P.ew[L.nI + s.e];
+            w[2 * TN + s.owner] = sg * P.ew[2 * L.nI + s.e];
+            oth[s.owner] = uint16_t(s.other);
         }
         P.used_slots += long(slots.size());
-        // boundary rounds
+        // boundary / wall rounds: round r of a node = its r-th boundary or wall edge in original order
         int br = 0;
         for (int lu = 0; lu < nown; lu++) br = std::max<int>(br, int(bn_off[base + lu + 1] - bn_off[base + lu]));
-        P.tile_brounds[t] = br;
-        P.bslot_off[t + 1] = P.bslot_off[t] + long(br) * TN;
-    }
-    // weights: three planes over all slots, oriented thread-node -> other (negated when the thread node is the edge's `b`)
-    const long ns = P.slot_off[P.ntiles];
-    P.slot_w.assign(3 * ns, 0.0);
-    for (long si = 0; si < ns; si++) {
-        const long e = slot_eid[si];
-        if (e < 0) continue;
-        const double sg = double(slot_sgn[si]);
-        P.slot_w[si] = sg * P.ew[e];
-        P.slot_w[ns + si] = sg * P.ew[L.nI + e];
-        P.slot_w[2 * ns + si] = sg * P.ew[2 * L.nI + e];
-    }
-    const long nbs = P.bslot_off[P.ntiles];
-    P.bslot_kind.assign(nbs, 0);
-    P.bslot_w.assign(3 * nbs, 0.0);
-    for (long t = 0; t < P.ntiles; t++) {
-        const long base = t * TN;
-        for (int lu = 0; lu < P.tile_nown[t]; lu++) {
+        const long bb0 = P.bslot_off[t];
+        P.bslot_off[t + 1] = bb0 + br;
+        P.bslots.resize(size_t(P.bslot_off[t + 1]) * BBLK, 0);
+        for (int lu = 0; lu < nown; lu++) {
             int r = 0;
             for (long k = bn_off[base + lu]; k < bn_off[base + lu + 1]; k++, r++) {
                 const long bi = bn_idx[k];
-                const long si = P.bslot_off[t] + long(r) * TN + lu;
-                P.bslot_kind[si] = P.bkind[bi];
-                P.bslot_w[si] = P.bw[bi]; P.bslot_w[nbs + si] = P.bw[nbw + bi]; P.bslot_w[2 * nbs + si] = P.bw[2 * nbw + bi];
+                unsigned char* blk = P.bslots.data() + size_t(bb0 + r) * BBLK;
+                double* w = reinterpret_cast<double*>(blk);
+                w[lu] = P.bw[bi]; w[TN + lu] = P.bw[nbw + bi]; w[2 * TN + lu] = P.bw[2 * nbw + bi];
+                blk[size_t(TN) * 24 + lu] = P.bkind[bi];
             }
         }
     }
@@ -379,24 +379,32 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
 long check_colouring(const LevelPlan& P) {
     long conflicts = 0;
     const long TN = P.TN;
+    const size_t BLK = size_t(TN) * 26;
     std::vector<int> seen(TN);
-    std::vector<long> edge_count;
     long stored = 0;
     for (long t = 0; t < P.ntiles; t++) {
-        for (int c = 0; c < P.tile_rounds[t]; c++) {
+        const long nhalo = P.halo_off[t + 1] - P.halo_off[t];
+        for (long b = P.slot_off[t]; b < P.slot_off[t + 1]; b++) {
+            const unsigned char* blk = P.slots.data() + size_t(b) * BLK;
+            const double* w = reinterpret_cast<const double*>(blk);
+            const uint16_t* oth = reinterpret_cast<const uint16_t*>(blk + size_t(TN) * 24);
             std::fill(seen.begin(), seen.end(), 0);
             for (long lu = 0; lu < TN; lu++) {
-                const uint16_t o = P.slot_other[P.slot_off[t] + long(c) * TN + lu];
-                if (o == 0xFFFF) continue;
+                const uint16_t o = oth[lu];
+                const bool empty = P.scatter ? (o == 0xFFFF) : (o == lu && w[lu] == 0.0 && w[TN + lu] == 0.0 && w[2 * TN + lu] == 0.0);
+                if (empty) continue;
                 stored++;
                 if (lu >= P.tile_nown[t]) conflicts++;               // padding threads must own nothing
-                if (o < TN) { if (seen[o]++) conflicts++; if (o >= P.tile_nown[t]) conflicts++; }
-                else if (o - TN >= P.halo_off[t + 1] - P.halo_off[t]) conflicts++;
+                if (o < TN) {
+                    if (o >= P.tile_nown[t]) conflicts++;
+                    if (P.scatter && seen[o]++) conflicts++;         // two writers of one node in one round
+                } else if (o - TN >= nhalo) conflicts++;
             }
         }
     }
-    // coverage: every internal edge is stored once if both ends share a tile, twice otherwise
-    if (stored != P.nI + P.cut_edges / 2) conflicts += 1000000;
+    // coverage: scatter mode stores an edge once if both ends share a tile and twice otherwise; segment mode always twice
+    const long expect = P.scatter ? P.nI + P.cut_edges / 2 : 2 * P.nI;
+    if (stored != expect) conflicts += 1000000;
     return conflicts;
 }
 

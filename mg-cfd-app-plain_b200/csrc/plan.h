@@ -15,6 +15,7 @@ namespace mgcfd {
 struct PlanOptions {
     int ordering = 2;     // MGCFD_ORDER_*
     int tile_nodes = 256; // owned nodes per tile (= CTA size of the tiled kernel)
+    bool scatter = false; // true: coloured-scatter rounds (each in-tile edge once); false: sorted-segment rounds (every edge from both ends)
 };
 
 struct LevelPlan {
@@ -27,14 +28,15 @@ struct LevelPlan {
     std::vector<int> tile_nown;           // owned nodes per tile
     std::vector<long> halo_off;           // ntiles+1
     std::vector<int> halo_ids;            // padded global ids, sorted per tile
-    std::vector<long> slot_off;           // ntiles+1, in slots (each tile: rounds*TN)
-    std::vector<int> tile_rounds;         // colour rounds per tile
-    std::vector<uint16_t> slot_other;     // local index of the other endpoint (<TN owned, >=TN halo), 0xFFFF empty
-    std::vector<double> slot_w;           // 3 planes [3][nslots]: edge vector oriented thread-node -> other
-    std::vector<long> bslot_off;          // ntiles+1
-    std::vector<int> tile_brounds;
-    std::vector<uint8_t> bslot_kind;      // 0 none, 1 boundary (-1), 2 wall (-2)
-    std::vector<double> bslot_w;          // [3][nbslots]
+    bool scatter = false;
+    // edge rounds: per tile `rounds` blocks of TN*26 bytes, block = [hx[TN] | hy[TN] | hz[TN] | other[TN] (uint16)],
+    //   h = -0.5 * (edge vector oriented thread-node -> other); other = local index of the other endpoint (< TN owned,
+    //   >= TN halo).  Empty slot: scatter mode other = 0xFFFF; segment mode other = the thread's own index with h = 0.
+    std::vector<long> slot_off;           // ntiles+1, in blocks (prefix sum of rounds)
+    std::vector<unsigned char> slots;
+    // boundary/wall rounds: blocks of TN*25 bytes, block = [x[TN] | y[TN] | z[TN] | kind[TN] (uint8: 0 none, 1 boundary, 2 wall)]
+    std::vector<long> bslot_off;          // ntiles+1, in blocks
+    std::vector<unsigned char> bslots;
     int max_halo = 0, max_rounds = 0;
     long cut_edges = 0, used_slots = 0;
     // ---- flat edge list in new numbering (atomic mode, indirect_rw, ordering sweeps) -------------
@@ -43,10 +45,9 @@ struct LevelPlan {
     std::vector<int> bnode;               // boundary+wall edges: node, kind
     std::vector<uint8_t> bkind;
     std::vector<double> bw;               // [3][nB+nW]
-    // ---- CSR by node, original edge order (sorted-segment flux mode + prolong) -------------------
+    // ---- CSR by node, original edge order (segment rounds + prolong) -----------------------------
     std::vector<long> adj_off;            // npad+1
     std::vector<int> adj_nbr;             // neighbour padded id, bit31 set when this node is the edge's `b`
-    std::vector<double> adj_w;            // [3][2*nI] edge vector as stored (a->b)
 };
 
 void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P);

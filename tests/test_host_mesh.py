@@ -132,16 +132,20 @@ def test_reference_binary_runs_our_files_and_matches_oracle(tmp_path):
 @pytest.mark.parametrize("kind,dims", [(0, [[21, 20, 19]]), (1, [[14, 13, 12]]), (2, [[6, 5, 5]])])
 @pytest.mark.parametrize("ordering", [M.ORDER_AS_GIVEN, M.ORDER_RCM, M.ORDER_PARTITION_RCM])
 @pytest.mark.parametrize("tile_nodes", [128, 256])
-def test_plan_invariants(kind, dims, ordering, tile_nodes):
+@pytest.mark.parametrize("flux_mode", [M.FLUX_TILED_COLOURED, M.FLUX_SORTED_SEGMENT])
+def test_plan_invariants(kind, dims, ordering, tile_nodes, flux_mode):
     mesh = M.Mesh.generate(kind, dims, mesh_variant=0 if kind == 2 else 2)
-    info, perm, conflicts = M.plan_level(mesh, 0, ordering=ordering, tile_nodes=tile_nodes)
+    info, perm, conflicts = M.plan_level(mesh, 0, ordering=ordering, tile_nodes=tile_nodes, flux_mode=flux_mode)
     nel, nI = info["nel"], info["nI"]
-    assert conflicts == 0                                             # no two edges of a round write one node
+    assert conflicts == 0               # every edge stored the right number of times; no two edges of a round write one node
     assert len(np.unique(perm)) == nel and perm.min() >= 0 and perm.max() < info["npad"]      # injective renumbering
     assert info["npad"] == info["ntiles"] * tile_nodes and info["npad"] - nel < tile_nodes * max(1, info["ntiles"] // 8 + 1)
-    assert info["used_slots"] == nI + info["cut_edges"]               # inside edges once, cut edges from both sides
+    if flux_mode == M.FLUX_TILED_COLOURED:
+        assert info["used_slots"] == nI + info["cut_edges"]           # inside edges once, cut edges from both sides
+    else:
+        assert info["used_slots"] == 2 * nI                           # every edge from both of its ends
     # determinism: the plan is a pure function of the mesh
-    info2, perm2, _ = M.plan_level(mesh, 0, ordering=ordering, tile_nodes=tile_nodes)
+    info2, perm2, _ = M.plan_level(mesh, 0, ordering=ordering, tile_nodes=tile_nodes, flux_mode=flux_mode)
     assert info2 == info and np.array_equal(perm, perm2)
 
 

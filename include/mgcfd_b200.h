@@ -71,7 +71,9 @@ typedef struct mgcfd_options {
     int tile_nodes; /* owned nodes per tile = threads per CTA of the tiled kernel; 0 = default (256) */
     int use_graph;  /* run_cycles replays one captured CUDA graph per V-cycle (default 1) */
     int timing;     /* record CUDA-event times per kernel per level (forces use_graph=0) */
-    int reserved[10];
+    int no_pipeline; /* 1: fused stages use the simple one-CTA-per-tile kernel instead of the persistent kernel whose transfers
+                        (TMA bulk copies of the edge stream, cp.async gathers of node records) run one tile ahead (default 0) */
+    int reserved[9];
 } mgcfd_options;
 
 void mgcfd_default_options(mgcfd_options* opt);
@@ -145,7 +147,8 @@ int mgcfd_synchronize(mgcfd_ctx* ctx);
 int mgcfd_get_stream(mgcfd_ctx* ctx, void** cuda_stream);
 
 /* ---- introspection (tests, Times.csv, roofline) --------------------------------------------------- */
-/* info[0..]: nel, nI, nB, nW, padded nodes, tiles, tile_nodes, max colours, slots stored, halo entries, cut edges */
+/* info[0..15]: nel, nI, nB, nW, padded nodes, tiles, tile_nodes, max rounds, slots allocated, halo entries, cut edges,
+ * slots used, max halo of a tile, boundary slots allocated, shared memory per CTA (bytes), persistent grid (0 = simple kernel) */
 int mgcfd_level_info(mgcfd_ctx* ctx, int level, long info[16]);
 /* new_of_old[nel]: the node renumbering (a bijection onto [0,padded) minus padding) */
 int mgcfd_get_permutation(mgcfd_ctx* ctx, int level, long* new_of_old);

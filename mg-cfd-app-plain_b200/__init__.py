@@ -39,7 +39,7 @@ class MgcfdError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("flux_mode", C.c_int), ("ordering", C.c_int), ("tile_nodes", C.c_int),
-                ("use_graph", C.c_int), ("timing", C.c_int), ("reserved", C.c_int * 10)]
+                ("use_graph", C.c_int), ("timing", C.c_int), ("no_pipeline", C.c_int), ("reserved", C.c_int * 9)]
 
 
 _lib = None
@@ -206,12 +206,14 @@ class Solver:
     """Device-resident multigrid state + the reference's kernel functions, one method per function."""
 
     def __init__(self, levels: int, mesh_variant: int, device: int = 0, flux_mode: int = FLUX_TILED_COLOURED,
-                 ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 256, use_graph: bool = True, timing: bool = False):
+                 ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 256, use_graph: bool = True, timing: bool = False,
+                 pipeline: bool = True):
         L = lib()
         opt = Options()
         L.mgcfd_default_options(C.byref(opt))
         opt.device, opt.flux_mode, opt.ordering, opt.tile_nodes = device, flux_mode, ordering, tile_nodes
         opt.use_graph, opt.timing = int(use_graph), int(timing)
+        opt.no_pipeline = int(not pipeline)
         self._h = C.c_void_p()
         self.levels, self.mesh_variant = levels, mesh_variant
         _check(L.mgcfd_create(levels, mesh_variant, C.byref(opt), C.byref(self._h)))
@@ -316,7 +318,7 @@ class Solver:
         out = (C.c_long * 16)()
         _check(lib().mgcfd_level_info(self._h, level, out))
         keys = ("nel", "nI", "nB", "nW", "npad", "ntiles", "tile_nodes", "max_rounds", "slots", "halo_entries", "cut_edges",
-                "used_slots", "max_halo", "bslots", "smem_bytes")
+                "used_slots", "max_halo", "bslots", "smem_bytes", "pipe_grid")
         return dict(zip(keys, out))
 
     def permutation(self, level):
@@ -356,7 +358,7 @@ class Solver:
 
 
 INFO_KEYS = ("nel", "nI", "nB", "nW", "npad", "ntiles", "tile_nodes", "max_rounds", "slots", "halo_entries", "cut_edges",
-             "used_slots", "max_halo", "bslots", "smem_bytes")
+             "used_slots", "max_halo", "bslots", "smem_bytes", "pipe_grid")
 
 
 def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 256, flux_mode: int = FLUX_TILED_COLOURED):

@@ -46,14 +46,15 @@ struct Level {
     bool uploaded = false;
     long nel = 0, npad = 0, ntiles = 0, nI = 0, nB = 0, nW = 0;
     int TN = 256, smem_nodes = 0;
-    size_t smem_bytes = 0;
+    size_t smem_bytes = 0;        // simple stage kernel
+    size_t pipe_smem = 0;         // pipelined stage kernel
+    int pipe_grid = 0, chunk_rounds = 0;
+    bool pipe = false;
     double* buf[3] = {nullptr, nullptr, nullptr};   // node records (8 doubles each), rotating roles
     int i_var = 0, i_old = 1, i_tmp = 2;
     double *res = nullptr, *flux = nullptr, *sf = nullptr, *vol = nullptr, *vol_root = nullptr;
     int *new_of_old = nullptr, *old_of_new = nullptr;
-    long* halo_off = nullptr; int* halo_ids = nullptr;
-    long* slot_off = nullptr; unsigned char* slots = nullptr;
-    long* bslot_off = nullptr; unsigned char* bslots = nullptr;
+    unsigned char *hdrs = nullptr, *slots = nullptr, *bslots = nullptr;
     // flat + CSR (lazy)
     int *ea = nullptr, *eb = nullptr; double* ew = nullptr;
     int* bnode = nullptr; uint8_t* bkind = nullptr; double* bw = nullptr;
@@ -95,6 +96,7 @@ struct mgcfd_ctx {
     bool capturing = false;
     unsigned long long stage_seq = 0;
     double kdiss;
+    int num_sms = 148;
     int rms_pending = 0;
     long bad_cell = -1; int bad_reason = 0;
 };
@@ -162,27 +164,59 @@ int launch_stage_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     k_stage<TN, SCATTER, FUSED><<<(unsigned)v.ntiles, TN, v.smem_bytes, c->stream>>>(a);
     return post_launch(c);
 }
-template <int TN>
-int launch_stage_tn(mgcfd_ctx* c, Level& v, const StageArgs& a, bool scatter, bool fused) {
-    if (scatter) return fused ? launch_stage_t<TN, true, true>(c, v, a) : launch_stage_t<TN, true, false>(c, v, a);
-    return fused ? launch_stage_t<TN, false, true>(c, v, a) : launch_stage_t<TN, false, false>(c, v, a);
+template <int TN, bool SCATTER>
+int launch_pipe_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
+    k_stage_pipe<TN, SCATTER><<<(unsigned)v.pipe_grid, TN, v.pipe_smem, c->stream>>>(a);
+    return post_launch(c);
+}
+// persistent grid of the pipelined kernel: as many CTAs as fit on the device at once (occupancy API), never more than tiles
+template <int TN, bool SCATTER>
+int setup_pipe_t(mgcfd_ctx* c, Level& v) {
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, k_stage_pipe<TN, SCATTER>));
+    if (v.pipe_smem + fa.sharedSizeBytes > 227 * 1024) { v.pipe = false; return MGCFD_OK; }
+    static size_t attr_bytes = 0;       // per instantiation: the attribute only ever grows
+    if (v.pipe_smem > attr_bytes) {
+        CK(cudaFuncSetAttribute(k_stage_pipe<TN, SCATTER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.pipe_smem));
+        attr_bytes = v.pipe_smem;
+    }
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stage_pipe<TN, SCATTER>, TN, v.pipe_smem));
+    if (per_sm < 1) { v.pipe = false; return MGCFD_OK; }
+    v.pipe_grid = (int)std::min<long>(v.ntiles, (long)per_sm * c->num_sms);
+    v.pipe = true;
+    return MGCFD_OK;
+}
+int setup_pipe(mgcfd_ctx* c, Level& v) {
+    const bool sc = v.plan.scatter;
+    if (v.TN == 128) return sc ? setup_pipe_t<128, true>(c, v) : setup_pipe_t<128, false>(c, v);
+    if (v.TN == 256) return sc ? setup_pipe_t<256, true>(c, v) : setup_pipe_t<256, false>(c, v);
+    return sc ? setup_pipe_t<512, true>(c, v) : setup_pipe_t<512, false>(c, v);
 }
 int launch_stage(mgcfd_ctx* c, Level& v, const StageArgs& a, bool fused) {
-    const bool scatter = v.plan.scatter;
-    if (v.TN == 256) return launch_stage_tn<256>(c, v, a, scatter, fused);
-    if (v.TN == 128) return launch_stage_tn<128>(c, v, a, scatter, fused);
-    if (v.TN == 512) return launch_stage_tn<512>(c, v, a, scatter, fused);
-    g_err = "tile_nodes must be 128, 256 or 512";
-    return MGCFD_ERR_ARG;
+    const bool sc = v.plan.scatter;
+    if (fused && v.pipe) {
+        if (v.TN == 128) return sc ? launch_pipe_t<128, true>(c, v, a) : launch_pipe_t<128, false>(c, v, a);
+        if (v.TN == 256) return sc ? launch_pipe_t<256, true>(c, v, a) : launch_pipe_t<256, false>(c, v, a);
+        return sc ? launch_pipe_t<512, true>(c, v, a) : launch_pipe_t<512, false>(c, v, a);
+    }
+    if (v.TN == 128) return sc ? (fused ? launch_stage_t<128, true, true>(c, v, a) : launch_stage_t<128, true, false>(c, v, a))
+                               : (fused ? launch_stage_t<128, false, true>(c, v, a) : launch_stage_t<128, false, false>(c, v, a));
+    if (v.TN == 256) return sc ? (fused ? launch_stage_t<256, true, true>(c, v, a) : launch_stage_t<256, true, false>(c, v, a))
+                               : (fused ? launch_stage_t<256, false, true>(c, v, a) : launch_stage_t<256, false, false>(c, v, a));
+    return sc ? (fused ? launch_stage_t<512, true, true>(c, v, a) : launch_stage_t<512, true, false>(c, v, a))
+              : (fused ? launch_stage_t<512, false, true>(c, v, a) : launch_stage_t<512, false, false>(c, v, a));
 }
 
 StageArgs base_args(mgcfd_ctx* c, Level& v) {
     StageArgs a;
     memset(&a, 0, sizeof(a));
     a.stride = v.npad;
-    a.halo_off = v.halo_off; a.halo_ids = v.halo_ids;
-    a.slot_off = v.slot_off; a.slots = v.slots;
-    a.bslot_off = v.bslot_off; a.bslots = v.bslots;
+    a.hdrs = v.hdrs; a.hdr_stride = v.plan.hdr_stride;
+    a.slots = v.slots; a.bslots = v.bslots;
+    a.ntiles = (int)v.ntiles;
+    a.rec_rows = v.smem_nodes;
+    a.chunk_rounds = v.chunk_rounds;
     a.k2 = 2.0 * c->kdiss;
     a.old_of_new = v.old_of_new;
     a.sf = v.sf;
@@ -326,8 +360,8 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
 }
 
 void free_level(Level& v) {
-    void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.halo_off, v.halo_ids,
-                    v.slot_off, v.slots, v.bslot_off, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
+    void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
+                    v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
                     v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.io};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
@@ -389,6 +423,7 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     }
     CK(cudaSetDevice(o.device));
     mgcfd_ctx* c = new mgcfd_ctx();
+    cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, o.device);
     c->opt = o; c->levels = levels; c->variant = mesh_variant;
     c->L.resize(levels);
     c->kdiss = -0.5 * double(0.2f);
@@ -469,8 +504,22 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         Level& v = c->L[l];
         LevelPlan& P = v.plan;
         v.nel = P.nel; v.npad = P.npad; v.ntiles = P.ntiles; v.nI = P.nI; v.nB = P.nB; v.nW = P.nW; v.TN = P.TN;
-        v.smem_nodes = ((P.TN + P.max_halo + 3) / 4) * 4;
+        v.smem_nodes = P.TN + P.hpad;
         v.smem_bytes = 64 * (size_t)v.smem_nodes + (P.scatter ? 40 * (size_t)P.TN : 0);
+        // pipelined kernel: ring of RING entries of chunk_rounds round blocks + two record buffers + three header buffers
+        // pipelined kernel: a ring of RING entries of chunk_rounds round blocks + two record buffers + three header buffers.
+        // chunk_rounds as large as possible (fewer CTA-wide hand-overs), at most half the rounds of a tile rounded up (so that
+        // one entry is being filled while the other is consumed), while `want_ctas` CTAs still fit the SM's 228 KB
+        {
+            const int want_ctas = P.TN <= 256 ? 2 : 1;
+            const size_t budget = (228 * 1024) / want_ctas - 1024 - 2048;
+            const size_t fixed = 2 * 64 * (size_t)v.smem_nodes + 3 * (size_t)P.hdr_stride + (P.scatter ? 40 * (size_t)P.TN : 0);
+            int R = std::max(1, P.max_rounds > 8 ? (P.max_rounds + 1) / 2 : P.max_rounds);
+            while (R > 1 && fixed + (size_t)RING * R * P.TN * 26 > budget) R--;
+            const int nchunks = std::max(1, (P.max_rounds + R - 1) / R);
+            v.chunk_rounds = std::max(1, (P.max_rounds + nchunks - 1) / nchunks);
+            v.pipe_smem = fixed + (size_t)RING * v.chunk_rounds * P.TN * 26;
+        }
         if (v.smem_bytes > 227 * 1024) { g_err = "tile halo too large for shared memory; use a smaller tile_nodes or a locality-preserving ordering"; return MGCFD_ERR_ARG; }
         for (int b = 0; b < 3; b++) CK(cudaMalloc((void**)&v.buf[b], sizeof(double) * 8 * v.npad));
         CK(cudaMalloc((void**)&v.res, sizeof(double) * 5 * v.npad));
@@ -485,9 +534,9 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         CKRC(dev_upload(&v.vol, vol, s)); CKRC(dev_upload(&v.vol_root, root, s));
         std::vector<int> n2o(P.old_of_new.begin(), P.old_of_new.end()), o2n(P.new_of_old.begin(), P.new_of_old.end());
         CKRC(dev_upload(&v.old_of_new, n2o, s)); CKRC(dev_upload(&v.new_of_old, o2n, s));
-        CKRC(dev_upload(&v.halo_off, P.halo_off, s)); CKRC(dev_upload(&v.halo_ids, P.halo_ids, s));
-        CKRC(dev_upload(&v.slot_off, P.slot_off, s)); CKRC(dev_upload(&v.slots, P.slots, s));
-        CKRC(dev_upload(&v.bslot_off, P.bslot_off, s)); CKRC(dev_upload(&v.bslots, P.bslots, s));
+        CKRC(dev_upload(&v.hdrs, P.hdrs, s)); CKRC(dev_upload(&v.slots, P.slots, s)); CKRC(dev_upload(&v.bslots, P.bslots, s));
+        v.pipe = false;
+        if (!c->opt.no_pipeline) CKRC(setup_pipe(c, v));
         const long parts = std::max<long>(v.ntiles, blocks_for(v.npad, 256));
         CK(cudaMalloc((void**)&v.rms_partial, sizeof(double) * 5 * parts));
         CK(cudaStreamSynchronize(s));
@@ -781,7 +830,7 @@ int mgcfd_level_info(mgcfd_ctx* c, int l, long info[16]) {
     info[0] = P.nel; info[1] = P.nI; info[2] = P.nB; info[3] = P.nW; info[4] = P.npad; info[5] = P.ntiles; info[6] = P.TN;
     info[7] = P.max_rounds; info[8] = P.slot_off.empty() ? 0 : P.slot_off[P.ntiles] * P.TN; info[9] = (long)P.halo_ids.size();
     info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off.empty() ? 0 : P.bslot_off[P.ntiles] * P.TN;
-    info[14] = (long)c->L[l].smem_bytes;
+    info[14] = (long)(c->L[l].pipe ? c->L[l].pipe_smem : c->L[l].smem_bytes); info[15] = c->L[l].pipe ? c->L[l].pipe_grid : 0;
     return MGCFD_OK;
 }
 int mgcfd_get_permutation(mgcfd_ctx* c, int l, long* new_of_old) {
@@ -849,7 +898,7 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     const EdgeNb* e = (const EdgeNb*)edges;
     H.edges.assign(e, e + nI + nB + nW);
     if (coords) H.coords.assign(coords, coords + 3 * nel);
-    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 256; po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED);
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 256; po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
     LevelPlan P;
     try { build_level_plan(H, po, P); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
@@ -858,7 +907,7 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     info[7] = P.max_rounds; info[8] = P.slot_off[P.ntiles] * P.TN; info[9] = (long)P.halo_ids.size();
     info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off[P.ntiles] * P.TN;
     if (new_of_old) memcpy(new_of_old, P.new_of_old.data(), sizeof(long) * nel);
-    if (conflicts) *conflicts = check_colouring(P);
+    if (conflicts) *conflicts = P.oversize ? -1 : check_colouring(P);
     return MGCFD_OK;
 }
 

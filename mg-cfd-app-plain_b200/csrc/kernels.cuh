@@ -23,6 +23,21 @@ __device__ __constant__ double c_ffc[12];    // ff_flux_contribution_{momentum_x
 struct Rec { double rho, mx, my, mz, re, ir, p, s; };   // ir = 1/rho, s = |v| + speed of sound
 struct Flux5 { double r, mx, my, mz, e; };
 
+// sqrt for the edge weight |h|: MUFU.RSQ64H seed (2^-22) + two coupled Newton steps + one residual correction, branch-free.
+// x is a sum of squares >= 1e-300 here (never 0, inf or denormal), so the special-case paths of sqrt() are dead weight;
+// the result is within 1 ulp of the correctly rounded root.
+__device__ __forceinline__ double sqrt_pos(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+
 // per-node derived quantities (cfd_loops.h:121-148): velocity = momentum / rho, speed_sqd, pressure, speed of sound.
 // The reference divides three times by rho; here one correctly rounded reciprocal and three products (<= 1 ulp apart).
 __device__ __forceinline__ Rec make_rec(double rho, double mx, double my, double mz, double re) {
@@ -32,7 +47,7 @@ __device__ __forceinline__ Rec make_rec(double rho, double mx, double my, double
     const double vx = mx * n.ir, vy = my * n.ir, vz = mz * n.ir;
     const double sq = vx * vx + vy * vy + vz * vz;
     n.p = (double(MG_GAMMA) - double(1.0)) * (re - double(0.5) * rho * sq);
-    n.s = sqrt(sq) + sqrt(double(MG_GAMMA) * n.p * n.ir);
+    n.s = sqrt_pos(sq + 1e-300) + sqrt_pos(double(MG_GAMMA) * n.p * n.ir);   // + 1e-300: still fluid (sq == 0) stays finite; vanishes in the sum
     return n;
 }
 
@@ -61,12 +76,32 @@ __device__ __forceinline__ Rec sm_load_rec(const double2* sm, int o) {
     return n;
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: one thread moves a tile's whole edge stream into shared memory
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // make the initialised barrier visible to the async (TMA) proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile("{\n.reg .pred p;\nMG_WAIT:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra MG_DONE;\nbra MG_WAIT;\nMG_DONE:\n}"
+                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // One internal edge seen from end A towards B; (hx,hy,hz) = -0.5 * stored edge vector oriented A->B; k2 = 2*kdiss with
 // kdiss = -0.5*smoothing_coefficient (src/Base/common.h:24), so that |e|*kdiss == |h|*k2 exactly.
 // Adds A's five flux increments (flux_kernel.elemfunc.c:130-162) to acc; B's increments are their exact negation (:170-189).
 // Algebra: sum_d h_d * flux_contribution_momentum_x[d] = mx*(h.v) + p*hx etc. (cfd_loops.h:57-83), with h.v = (h.m)/rho.
-__device__ __forceinline__ void edge_flux_acc(const Rec& A, double A_ep, const Rec& B, double hx, double hy, double hz, double k2, Flux5& acc) {
-    const double ewt = sqrt(hx * hx + hy * hy + hz * hz);
+__device__ __forceinline__ double edge_weight(double hx, double hy, double hz) {
+    return sqrt_pos(fma(hx, hx, fma(hy, hy, fma(hz, hz, 1e-300))));   // + 1e-300: exact no-op unless h == 0 (empty slot)
+}
+__device__ __forceinline__ void edge_flux_acc_w(const Rec& A, double A_ep, const Rec& B, double hx, double hy, double hz, double ewt, double k2, Flux5& acc) {
     const double factor = (ewt * k2) * (A.s + B.s);
     const double gA = hx * A.mx + hy * A.my + hz * A.mz;
     const double gB = hx * B.mx + hy * B.my + hz * B.mz;
@@ -77,6 +112,9 @@ __device__ __forceinline__ void edge_flux_acc(const Rec& A, double A_ep, const R
     acc.mx += factor * (A.mx - B.mx) + (A.mx * qA + B.mx * qB + ps * hx);
     acc.my += factor * (A.my - B.my) + (A.my * qA + B.my * qB + ps * hy);
     acc.mz += factor * (A.mz - B.mz) + (A.mz * qA + B.mz * qB + ps * hz);
+}
+__device__ __forceinline__ void edge_flux_acc(const Rec& A, double A_ep, const Rec& B, double hx, double hy, double hz, double k2, Flux5& acc) {
+    edge_flux_acc_w(A, A_ep, B, hx, hy, hz, edge_weight(hx, hy, hz), k2, acc);
 }
 __device__ __forceinline__ Flux5 edge_flux(const Rec& A, const Rec& B, double hx, double hy, double hz, double k2) {
     Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -117,6 +155,13 @@ __device__ __forceinline__ void wall_flux_acc(const Rec& B, double x, double y, 
 //            written once; on the last stage residual (validation.cpp:77-89), RMS partials (:91-105) and the validity
 //            check (:107-138) ride along.  !FUSED (granular API): fluxes[node] += total.
 // ------------------------------------------------------------------------------------------------------
+// fixed-stride per-tile header (hdr_stride bytes per tile): what a CTA needs to know about a tile before it can fetch it
+struct TileHdr {
+    int rounds, nh, brounds, pad;
+    long long slot_blk0, bslot_blk0;
+    // followed by int halo_ids[hpad]
+};
+
 struct StageArgs {
     const double* vin;     // records: stage input state
     const double* vold;    // records: old_variables (FUSED)
@@ -125,10 +170,12 @@ struct StageArgs {
     double* res;           // SoA residuals (last stage) or nullptr
     const double* sf;      // step factors
     long stride;           // npad
-    const long* halo_off; const int* halo_ids;
-    const long* slot_off;  // per tile: first round block of the tile (prefix sum of rounds); slot_off[ntiles] = total
-    const unsigned char* slots;   // round blocks of TN*26 bytes
-    const long* bslot_off; const unsigned char* bslots;   // boundary/wall round blocks of TN*25 bytes
+    const unsigned char* hdrs; int hdr_stride;    // TileHdr + halo ids, one per tile
+    const unsigned char* slots;   // edge round blocks of TN*26 bytes
+    const unsigned char* bslots;  // boundary/wall round blocks of TN*25 bytes
+    int ntiles;
+    int rec_rows;          // rows of one shared-memory record buffer (TN + padded max halo)
+    int chunk_rounds;      // pipelined kernel: edge rounds per ring entry
     double rk_div;         // double(RK+1-j)
     double k2;             // 2 * kdiss
     double* rms_partial;   // [ntiles][5] or nullptr
@@ -138,19 +185,144 @@ struct StageArgs {
     int mask;              // bit0 internal, bit1 boundary, bit2 wall
 };
 
+// A slot's `other` field is the byte offset of logical chunk 0 of the other endpoint's row in the shared record buffer,
+// off0 = (o << 6) | (((o >> 1) & 3) << 4); chunk k lives at off0 ^ (k << 4) (the buffer is 64-byte aligned).
+__device__ __forceinline__ Rec sm_load_rec_off(const unsigned char* recs, unsigned off0) {
+    const double2 c0 = *reinterpret_cast<const double2*>(recs + off0);
+    const double2 c1 = *reinterpret_cast<const double2*>(recs + (off0 ^ 16u));
+    const double2 c2 = *reinterpret_cast<const double2*>(recs + (off0 ^ 32u));
+    const double2 c3 = *reinterpret_cast<const double2*>(recs + (off0 ^ 48u));
+    Rec n; n.rho = c0.x; n.mx = c0.y; n.my = c1.x; n.mz = c1.y; n.re = c2.x; n.ir = c2.y; n.p = c3.x; n.s = c3.y;
+    return n;
+}
+
+// edge rounds of one block sequence (`nr` blocks of TN*26 bytes at `blk`, in shared or global memory)
+template <int TN, bool SCATTER>
+__device__ __forceinline__ void edge_rounds(const unsigned char* blk, int nr, const unsigned char* recs, double* acc, int t,
+                                            const Rec& me, double me_ep, double k2, Flux5& f) {
+    if (!SCATTER) {
+        // software pipeline: the slot, the other endpoint's record and the edge weight (the sqrt chain) of round r+1 are fetched /
+        // computed while round r's flux arithmetic runs; empty slots point at the node itself with h = 0 and add exact zeros
+        if (nr <= 0) return;
+        // two register sets used alternately (no rotation copies): set 0 holds even rounds, set 1 odd rounds
+        const double* w = reinterpret_cast<const double*>(blk);
+        double h0x = w[t], h0y = w[TN + t], h0z = w[2 * TN + t];
+        Rec B0 = sm_load_rec_off(recs, reinterpret_cast<const unsigned short*>(blk + TN * 24)[t]);
+        double e0 = edge_weight(h0x, h0y, h0z);
+        int r = 1;
+        for (; r + 1 < nr; r += 2) {
+            blk += TN * 26;
+            const double* w1 = reinterpret_cast<const double*>(blk);
+            const double h1x = w1[t], h1y = w1[TN + t], h1z = w1[2 * TN + t];
+            const Rec B1 = sm_load_rec_off(recs, reinterpret_cast<const unsigned short*>(blk + TN * 24)[t]);
+            const double e1 = edge_weight(h1x, h1y, h1z);
+            edge_flux_acc_w(me, me_ep, B0, h0x, h0y, h0z, e0, k2, f);
+            blk += TN * 26;
+            const double* w2 = reinterpret_cast<const double*>(blk);
+            h0x = w2[t]; h0y = w2[TN + t]; h0z = w2[2 * TN + t];
+            B0 = sm_load_rec_off(recs, reinterpret_cast<const unsigned short*>(blk + TN * 24)[t]);
+            e0 = edge_weight(h0x, h0y, h0z);
+            edge_flux_acc_w(me, me_ep, B1, h1x, h1y, h1z, e1, k2, f);
+        }
+        if (r < nr) {       // one round left to fetch
+            blk += TN * 26;
+            const double* w1 = reinterpret_cast<const double*>(blk);
+            const double h1x = w1[t], h1y = w1[TN + t], h1z = w1[2 * TN + t];
+            const Rec B1 = sm_load_rec_off(recs, reinterpret_cast<const unsigned short*>(blk + TN * 24)[t]);
+            const double e1 = edge_weight(h1x, h1y, h1z);
+            edge_flux_acc_w(me, me_ep, B0, h0x, h0y, h0z, e0, k2, f);
+            edge_flux_acc_w(me, me_ep, B1, h1x, h1y, h1z, e1, k2, f);
+        } else {
+            edge_flux_acc_w(me, me_ep, B0, h0x, h0y, h0z, e0, k2, f);
+        }
+    } else {
+        for (int r = 0; r < nr; r++, blk += TN * 26) {
+            const double* w = reinterpret_cast<const double*>(blk);
+            const unsigned off0 = reinterpret_cast<const unsigned short*>(blk + TN * 24)[t];
+            if (off0 != 0xFFFFu) {
+                const double hx = w[t], hy = w[TN + t], hz = w[2 * TN + t];
+                const Rec B = sm_load_rec_off(recs, off0);
+                Flux5 g = {0.0, 0.0, 0.0, 0.0, 0.0};
+                edge_flux_acc(me, me_ep, B, hx, hy, hz, k2, g);
+                f.r += g.r; f.mx += g.mx; f.my += g.my; f.mz += g.mz; f.e += g.e;
+                const unsigned o = off0 >> 6;
+                if (o < (unsigned)TN) {   // owned by this tile: conflict-free by colouring
+                    acc[0 * TN + o] -= g.r; acc[1 * TN + o] -= g.mx; acc[2 * TN + o] -= g.my; acc[3 * TN + o] -= g.mz; acc[4 * TN + o] -= g.e;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+// boundary / wall rounds (global memory; only tiles touching the domain boundary have any)
+template <int TN>
+__device__ __forceinline__ void boundary_rounds(const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f) {
+    for (int r = 0; r < br; r++, blk += TN * 25) {
+        const int kind = blk[TN * 24 + t];
+        if (kind == 0 || !((mask >> kind) & 1)) continue;
+        const double* w = reinterpret_cast<const double*>(blk);
+        if (kind == 1) boundary_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
+        else wall_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
+    }
+}
+// phase 3 of a fused stage for node gid: time_step + record + validity + residual; returns the five squared residuals in q
+__device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5]) {
+    const long S = a.stride;
+    const double factor = sf / a.rk_div;     // a true divide, cfd_loops.cpp:243
+    const double n0 = o[0] + factor * f.r, n1 = o[1] + factor * f.mx, n2 = o[2] + factor * f.my, n3 = o[3] + factor * f.mz, n4 = o[4] + factor * f.e;
+    store_rec(a.vout, gid, make_rec(n0, n1, n2, n3, n4));
+    if (a.bad_key) {
+        // check_for_invalid_variables (validation.cpp:107-138): first offending cell of the first offending stage
+        int reason = 0;
+        if (!(isfinite(n0) && isfinite(n1) && isfinite(n2) && isfinite(n3) && isfinite(n4))) reason = 1;
+        else if (n0 < 0.0) reason = 2;
+        else if (n4 < 0.0) reason = 3;
+        if (reason) {
+            const int oi = a.old_of_new[gid];
+            if (oi >= 0) atomicMin(a.bad_key, (a.stage_seq << 40) | ((unsigned long long)oi << 2) | (unsigned long long)reason);
+        }
+    }
+    if (a.res) {
+        const double r0 = n0 - o[0], r1 = n1 - o[1], r2 = n2 - o[2], r3 = n3 - o[3], r4 = n4 - o[4];   // residual(), validation.cpp:77-89
+        a.res[gid] = r0; a.res[S + gid] = r1; a.res[2 * S + gid] = r2; a.res[3 * S + gid] = r3; a.res[4 * S + gid] = r4;
+        q[0] = r0 * r0; q[1] = r1 * r1; q[2] = r2 * r2; q[3] = r3 * r3; q[4] = r4 * r4;
+    }
+}
+// deterministic block reduction of r^2 per variable (calc_rms partials): warp shuffles, then 5 threads over the warp sums
+template <int TN>
+__device__ __forceinline__ void rms_block(double q[5], double (*ws)[32], int t, double* out5) {
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) q[k] += __shfl_down_sync(0xffffffffu, q[k], d);
+    }
+    if ((t & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) ws[k][t >> 5] = q[k];
+    }
+    __syncthreads();
+    if (t < 5) {
+        double s = 0.0;
+        for (int w = 0; w < TN / 32; w++) s += ws[t][w];
+        out5[t] = s;
+    }
+}
+
+// ---- simple form: one CTA per tile, loads issued where they are needed (granular API; reference point for the pipeline) ----
 template <int TN, bool SCATTER, bool FUSED>
 __global__ void __launch_bounds__(TN, (TN <= 128 ? 5 : (TN <= 256 ? 2 : 1)))
 k_stage(const StageArgs a) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    double2* st = reinterpret_cast<double2*>(smraw);          // [(TN + nh) records][4 chunks]
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ double ws[5][32];
     const int t = threadIdx.x;
     const long tile = blockIdx.x;
     const long gid = tile * TN + t;
-    const long h0 = a.halo_off[tile];
-    const int nh = int(a.halo_off[tile + 1] - h0);
-    double* acc = reinterpret_cast<double*>(st + 4 * (TN + ((nh + 3) & ~3)));   // SCATTER: [5][TN]
+    const TileHdr* hdr = reinterpret_cast<const TileHdr*>(a.hdrs + tile * (long)a.hdr_stride);
+    const int* ids = reinterpret_cast<const int*>(hdr + 1);
+    const int nh = hdr->nh;
+    double2* st = reinterpret_cast<double2*>(smraw);          // [rec_rows records][4 chunks]
+    double* acc = reinterpret_cast<double*>(smraw + 64 * (size_t)a.rec_rows);   // SCATTER: [5][TN]
 
-    // ---- phase 1: stage records ----
     Rec me;
     {
         const double2* p = reinterpret_cast<const double2*>(a.vin + 8 * gid);
@@ -159,7 +331,7 @@ k_stage(const StageArgs a) {
         me.rho = c0.x; me.mx = c0.y; me.my = c1.x; me.mz = c1.y; me.re = c2.x; me.ir = c2.y; me.p = c3.x; me.s = c3.y;
     }
     for (int h = t; h < nh; h += TN) {
-        const double2* p = reinterpret_cast<const double2*>(a.vin + 8 * (long)a.halo_ids[h0 + h]);
+        const double2* p = reinterpret_cast<const double2*>(a.vin + 8 * (long)ids[h]);
         const double2 c0 = p[0], c1 = p[1], c2 = p[2], c3 = p[3];
         sm_store_rec(st, TN + h, c0, c1, c2, c3);
     }
@@ -169,105 +341,163 @@ k_stage(const StageArgs a) {
     }
     __syncthreads();
 
-    // ---- phase 2: edge rounds ----
     Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
-    const double me_ep = me.re + me.p;
-    if (a.mask & 1) {
-        const long b0 = a.slot_off[tile];
-        const int rounds = int(a.slot_off[tile + 1] - b0);
-        const unsigned char* blk = a.slots + b0 * (long)(TN * 26);
-        if (!SCATTER) {
-#pragma unroll 2
-            for (int r = 0; r < rounds; r++, blk += TN * 26) {
-                const double* w = reinterpret_cast<const double*>(blk);
-                const unsigned o = reinterpret_cast<const unsigned short*>(blk + TN * 24)[t];
-                const double hx = w[t], hy = w[TN + t], hz = w[2 * TN + t];
-                const Rec B = sm_load_rec(st, o);             // empty slots point at the node itself with h = 0: exact zeros
-                edge_flux_acc(me, me_ep, B, hx, hy, hz, a.k2, f);
-            }
-        } else {
-            for (int r = 0; r < rounds; r++, blk += TN * 26) {
-                const double* w = reinterpret_cast<const double*>(blk);
-                const unsigned o = reinterpret_cast<const unsigned short*>(blk + TN * 24)[t];
-                if (o != 0xFFFFu) {
-                    const double hx = w[t], hy = w[TN + t], hz = w[2 * TN + t];
-                    const Rec B = sm_load_rec(st, o);
-                    Flux5 g = {0.0, 0.0, 0.0, 0.0, 0.0};
-                    edge_flux_acc(me, me_ep, B, hx, hy, hz, a.k2, g);
-                    f.r += g.r; f.mx += g.mx; f.my += g.my; f.mz += g.mz; f.e += g.e;
-                    if (o < (unsigned)TN) {   // owned by this tile: conflict-free by colouring
-                        acc[0 * TN + o] -= g.r; acc[1 * TN + o] -= g.mx; acc[2 * TN + o] -= g.my; acc[3 * TN + o] -= g.mz; acc[4 * TN + o] -= g.e;
-                    }
-                }
-                __syncthreads();
-            }
-        }
-    }
-    if (a.mask & 6) {
-        const long b0 = a.bslot_off[tile];
-        const int br = int(a.bslot_off[tile + 1] - b0);
-        const unsigned char* blk = a.bslots + b0 * (long)(TN * 25);
-        for (int r = 0; r < br; r++, blk += TN * 25) {
-            const int kind = blk[TN * 24 + t];
-            if (kind == 0 || !((a.mask >> kind) & 1)) continue;
-            const double* w = reinterpret_cast<const double*>(blk);
-            if (kind == 1) boundary_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
-            else wall_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
-        }
-    }
+    if (a.mask & 1) edge_rounds<TN, SCATTER>(a.slots + hdr->slot_blk0 * (long)(TN * 26), hdr->rounds, smraw, acc, t, me, me.re + me.p, a.k2, f);
+    if (a.mask & 6) boundary_rounds<TN>(a.bslots + hdr->bslot_blk0 * (long)(TN * 25), hdr->brounds, t, a.mask, me, f);
     if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
 
-    // ---- phase 3 ----
-    const long S = a.stride;
     if (!FUSED) {
+        const long S = a.stride;
         a.flux[gid] += f.r; a.flux[S + gid] += f.mx; a.flux[2 * S + gid] += f.my; a.flux[3 * S + gid] += f.mz; a.flux[4 * S + gid] += f.e;
-        return;
     } else {
-        const double factor = a.sf[gid] / a.rk_div;     // a true divide, cfd_loops.cpp:243
-        double o0, o1, o2, o3, o4;
-        if (a.vold == a.vin) { o0 = me.rho; o1 = me.mx; o2 = me.my; o3 = me.mz; o4 = me.re; }
+        double o[5];
+        if (a.vold == a.vin) { o[0] = me.rho; o[1] = me.mx; o[2] = me.my; o[3] = me.mz; o[4] = me.re; }
         else {
             const double2* p = reinterpret_cast<const double2*>(a.vold + 8 * gid);
             const double2 c0 = p[0], c1 = p[1];
-            o0 = c0.x; o1 = c0.y; o2 = c1.x; o3 = c1.y; o4 = a.vold[8 * gid + 4];
+            o[0] = c0.x; o[1] = c0.y; o[2] = c1.x; o[3] = c1.y; o[4] = a.vold[8 * gid + 4];
         }
-        const double n0 = o0 + factor * f.r, n1 = o1 + factor * f.mx, n2 = o2 + factor * f.my, n3 = o3 + factor * f.mz, n4 = o4 + factor * f.e;
-        store_rec(a.vout, gid, make_rec(n0, n1, n2, n3, n4));
-        if (a.bad_key) {
-            // check_for_invalid_variables (validation.cpp:107-138): first offending cell of the first offending stage
-            int reason = 0;
-            if (!(isfinite(n0) && isfinite(n1) && isfinite(n2) && isfinite(n3) && isfinite(n4))) reason = 1;
-            else if (n0 < 0.0) reason = 2;
-            else if (n4 < 0.0) reason = 3;
-            if (reason) {
-                const int oi = a.old_of_new[gid];
-                if (oi >= 0) atomicMin(a.bad_key, (a.stage_seq << 40) | ((unsigned long long)oi << 2) | (unsigned long long)reason);
-            }
+        double q[5] = {0, 0, 0, 0, 0};
+        fused_update(a, gid, a.sf[gid], o, f, q);
+        if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
+    }
+}
+
+// ---- pipelined form: persistent CTAs, every global->shared transfer asynchronous and issued ahead of its use ----
+//   * tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; iteration `it` computes tile T_it
+//   * headers (+ halo ids) of T_{it+2}: cp.async (LDGSTS) at iteration it           (3 header buffers)
+//   * records of T_{it+1} (owned rows + halo rows, swizzled): cp.async at iteration it, completion tracked by an
+//     mbarrier through cp.async.mbarrier.arrive                                        (2 record buffers)
+//   * the edge stream: a ring of RING entries of `chunk_rounds` round blocks, each filled by ONE TMA bulk copy
+//     (cp.async.bulk, SASS UBLKCP) issued by thread 0 as soon as the entry is free, completion by mbarrier complete_tx
+//   so the edge loop reads shared memory only and, in steady state, never waits on HBM or L2.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int RING = 2;     // ring entries (each `chunk_rounds` round blocks)
+
+template <int TN, bool SCATTER>
+__global__ void __launch_bounds__(TN, (TN <= 128 ? 3 : (TN <= 256 ? 2 : 1)))
+k_stage_pipe(const StageArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    __shared__ __align__(8) unsigned long long bar_ring[RING], bar_recs[2];
+    __shared__ double ws[5][32];
+    const int t = threadIdx.x;
+    const int G = gridDim.x;
+    const int my_count = (a.ntiles - (int)blockIdx.x + G - 1) / G;
+    const int R = a.chunk_rounds;
+    const unsigned ring_bytes = unsigned(R) * unsigned(TN * 26);
+    unsigned char* ring = smraw;                                                // RING * ring_bytes (ring_bytes is a multiple of 128)
+    unsigned char* recs = ring + RING * (size_t)ring_bytes;                     // 2 * rec_rows * 64
+    unsigned char* hdrs = recs + 2 * 64 * (size_t)a.rec_rows;                   // 3 * hdr_stride
+    double* acc = reinterpret_cast<double*>(hdrs + 3 * (size_t)a.hdr_stride);   // SCATTER: [5][TN]
+
+    if (t == 0) {
+        for (int i = 0; i < RING; i++) mbar_init(&bar_ring[i], 1);
+        mbar_init(&bar_recs[0], TN); mbar_init(&bar_recs[1], TN);
+    }
+    __syncthreads();
+
+    auto tile_of = [&](int it) -> long { return (long)blockIdx.x + (long)it * G; };
+    auto hdr_of = [&](int it) -> const TileHdr* { return reinterpret_cast<const TileHdr*>(hdrs + (it % 3) * (size_t)a.hdr_stride); };
+    auto copy_hdr = [&](int it) {
+        if (it >= my_count) return;
+        const unsigned char* src = a.hdrs + tile_of(it) * (long)a.hdr_stride;
+        unsigned char* dst = hdrs + (it % 3) * (size_t)a.hdr_stride;
+        for (int c = t * 16; c < a.hdr_stride; c += TN * 16) cp_async16(dst + c, src + c);
+    };
+    auto copy_recs = [&](int it) {      // needs the header of T_it in shared memory
+        if (it >= my_count) return;
+        const TileHdr* hd = hdr_of(it);
+        const int* ids = reinterpret_cast<const int*>(hd + 1);
+        unsigned char* buf = recs + (it & 1) * 64 * (size_t)a.rec_rows;
+        {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vin + 8 * (tile_of(it) * TN + t));
+            unsigned char* row = buf + 64 * t;
+            const int x = ((t >> 1) & 3) << 4;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cp_async16(row + ((16 * k) ^ x), src + 16 * k);
         }
-        if (a.res) {
-            const double r0 = n0 - o0, r1 = n1 - o1, r2 = n2 - o2, r3 = n3 - o3, r4 = n4 - o4;   // residual(), validation.cpp:77-89
-            a.res[gid] = r0; a.res[S + gid] = r1; a.res[2 * S + gid] = r2; a.res[3 * S + gid] = r3; a.res[4 * S + gid] = r4;
-            if (a.rms_partial) {
-                // deterministic block reduction of r^2 per variable: warp shuffles, then 5 threads over the warp sums
-                __shared__ double ws[5][32];
-                double q[5] = {r0 * r0, r1 * r1, r2 * r2, r3 * r3, r4 * r4};
+        const int nh = hd->nh;
+        for (int h = t; h < nh; h += TN) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vin + 8 * (long)ids[h]);
+            const int o = TN + h;
+            unsigned char* row = buf + 64 * o;
+            const int x = ((o >> 1) & 3) << 4;
 #pragma unroll
-                for (int k = 0; k < 5; k++) {
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) q[k] += __shfl_down_sync(0xffffffffu, q[k], d);
-                }
-                if ((t & 31) == 0) {
-#pragma unroll
-                    for (int k = 0; k < 5; k++) ws[k][t >> 5] = q[k];
-                }
-                __syncthreads();
-                if (t < 5) {
-                    double s = 0.0;
-                    for (int w = 0; w < TN / 32; w++) s += ws[t][w];
-                    a.rms_partial[tile * 5 + t] = s;
-                }
-            }
+            for (int k = 0; k < 4; k++) cp_async16(row + ((16 * k) ^ x), src + 16 * k);
         }
+        cp_async_mbar_arrive(&bar_recs[it & 1]);
+    };
+    // edge-stream producer state (thread 0): next chunk to issue = chunk `p_chunk` of tile iteration `p_it`
+    int p_it = 0, p_chunk = 0, issued = 0, consumed = 0;
+    auto produce = [&](int it_visible) {          // headers of T_0..T_it_visible are in shared memory
+        while (issued - consumed < RING && p_it <= it_visible && p_it < my_count) {
+            const TileHdr* hd = hdr_of(p_it);
+            const int rounds = (a.mask & 1) ? hd->rounds : 0;
+            const int nchunks = (rounds + R - 1) / R;
+            if (p_chunk >= nchunks) { p_it++; p_chunk = 0; continue; }
+            const int nr = min(R, rounds - p_chunk * R);
+            const unsigned bytes = unsigned(nr) * unsigned(TN * 26);
+            const int e = issued % RING;
+            mbar_expect_tx(&bar_ring[e], bytes);
+            bulk_g2s(ring + e * (size_t)ring_bytes, a.slots + (hd->slot_blk0 + (long)p_chunk * R) * (long)(TN * 26), bytes, &bar_ring[e]);
+            issued++; p_chunk++;
+        }
+    };
+
+    // prologue: headers of T_0 and T_1, then the records of T_0 and the first edge chunks
+    copy_hdr(0); copy_hdr(1);
+    cp_async_wait_all();
+    __syncthreads();
+    copy_recs(0);
+    if (t == 0) produce(1);
+
+    for (int it = 0; it < my_count; it++) {
+        const long tile = tile_of(it);
+        const long gid = tile * TN + t;
+        const TileHdr* hd = hdr_of(it);
+        copy_hdr(it + 2);
+        mbar_wait(&bar_recs[it & 1], (it >> 1) & 1);       // records of T_it and the header of T_{it+1} have landed
+        copy_recs(it + 1);
+        if (t == 0) produce(it + 1);
+        const double sf = a.sf[gid];                       // early loads for the epilogue
+        double o[5];
+        const unsigned char* buf = recs + (it & 1) * 64 * (size_t)a.rec_rows;
+        const Rec me = sm_load_rec_off(buf, (unsigned(t) << 6) | (((unsigned(t) >> 1) & 3u) << 4));
+        if (a.vold == a.vin) { o[0] = me.rho; o[1] = me.mx; o[2] = me.my; o[3] = me.mz; o[4] = me.re; }
+        else {
+            const double2* p = reinterpret_cast<const double2*>(a.vold + 8 * gid);
+            const double2 c0 = p[0], c1 = p[1];
+            o[0] = c0.x; o[1] = c0.y; o[2] = c1.x; o[3] = c1.y; o[4] = a.vold[8 * gid + 4];
+        }
+        if (SCATTER) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) acc[k * TN + t] = 0.0;
+            __syncthreads();
+        }
+        Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const double me_ep = me.re + me.p;
+        const int rounds = (a.mask & 1) ? hd->rounds : 0;
+        for (int r0 = 0; r0 < rounds; r0 += R) {
+            const int e = consumed % RING;
+            mbar_wait(&bar_ring[e], (consumed / RING) & 1);
+            edge_rounds<TN, SCATTER>(ring + e * (size_t)ring_bytes, min(R, rounds - r0), buf, acc, t, me, me_ep, a.k2, f);
+            __syncthreads();                                // every thread is done with ring entry e
+            consumed++;
+            if (t == 0) produce(it + 1);
+        }
+        if (a.mask & 6) boundary_rounds<TN>(a.bslots + hd->bslot_blk0 * (long)(TN * 25), hd->brounds, t, a.mask, me, f);
+        if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
+        double q[5] = {0, 0, 0, 0, 0};
+        fused_update(a, gid, sf, o, f, q);
+        if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
+        __syncthreads();      // record buffer (it & 1), header buffer (it % 3), acc and ws are free again
     }
 }
 

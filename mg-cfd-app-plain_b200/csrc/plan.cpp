@@ -148,6 +148,10 @@ struct Bisector {
     }
 };
 
+// byte offset of chunk 0 of row o in a tile's shared record buffer (64-byte rows, 64B swizzle)
+inline uint16_t row_code(int o) { return uint16_t((o << 6) | (((o >> 1) & 3) << 4)); }
+inline int row_of_code(uint16_t c) { return c >> 6; }
+
 struct Mask256 {
     uint64_t w[4] = {0, 0, 0, 0};
     inline void set(int c) { w[c >> 6] |= (1ull << (c & 63)); }
@@ -287,7 +291,11 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
             }
         std::sort(halo.begin(), halo.end());
         halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
-        if (long(TN) + long(halo.size()) >= 0xFFFF) throw std::runtime_error("mgcfd: tile halo too large for 16-bit local ids");
+        if (long(TN) + long(halo.size()) >= 1020) {
+            // the 16-bit row code addresses at most 1020 rows of 64 bytes; a tile this scattered could not be staged anyway
+            if (opt.strict) throw std::runtime_error("mgcfd: tile halo too large (TN + halo must stay below 1020 rows): use a smaller tile_nodes or a locality-preserving ordering (MGCFD_ORDER_PARTITION_RCM)");
+            P.oversize = true;
+        }
         P.halo_off[t + 1] = P.halo_off[t] + long(halo.size());
         P.halo_ids.insert(P.halo_ids.end(), halo.begin(), halo.end());
         P.max_halo = std::max(P.max_halo, int(halo.size()));
@@ -298,7 +306,8 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
 
         slots.clear();
         if (!opt.scatter) {
-            // sorted-segment rounds: round r of a node = its r-th incident edge in ascending original edge index
+            // sorted-segment rounds: every node lists all its incident edges (ascending original edge index) ...
+            int tile_rounds = 0;
             for (int lu = 0; lu < nown; lu++) {
                 int r = 0;
                 for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++, r++) {
@@ -306,6 +315,47 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
                     const bool cut = (v < base || v >= base + TN);
                     slots.push_back({lu, r, local_of(v), adj_eid[k], P.adj_nbr[k] >= 0});
                     if (cut) P.cut_edges++;
+                }
+                tile_rounds = std::max(tile_rounds, r);
+            }
+            // ... and the ROUND in which each edge of a node is taken is then chosen so that the 8 lanes of a quarter-warp
+            // (which share one 128-bit shared-memory transaction) read rows with distinct (row mod 8), i.e. distinct bank
+            // groups under the 64B swizzle: a greedy list schedule per group of 8 consecutive nodes.  Only the order of a
+            // node's additions changes (still a fixed, reproducible order).
+            if (opt.conflict_free_rounds) {
+                size_t s0 = 0;
+                while (s0 < slots.size()) {
+                    const int g = slots[s0].owner / 8;
+                    size_t s1 = s0;
+                    while (s1 < slots.size() && slots[s1].owner / 8 == g) s1++;
+                    // remaining edges per lane
+                    std::vector<size_t> lane_edges[8];
+                    for (size_t k = s0; k < s1; k++) lane_edges[slots[k].owner % 8].push_back(k);
+                    for (int r = 0; r < tile_rounds; r++) {
+                        int used_by[8];                       // residue -> row using it in this round (-1 free)
+                        for (int q = 0; q < 8; q++) used_by[q] = -1;
+                        int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                        std::stable_sort(order, order + 8, [&](int x, int y) { return lane_edges[x].size() > lane_edges[y].size(); });
+                        const int rounds_left = tile_rounds - r;
+                        for (int oi = 0; oi < 8; oi++) {
+                            auto& le = lane_edges[order[oi]];
+                            if (le.empty()) continue;
+                            int pick = -1;
+                            for (size_t c = 0; c < le.size(); c++) {
+                                const int row = slots[le[c]].other;
+                                if (used_by[row & 7] == -1 || used_by[row & 7] == row) { pick = int(c); break; }
+                            }
+                            if (pick < 0) {
+                                if (int(le.size()) < rounds_left) continue;     // can wait: leave this round empty
+                                pick = 0;                                        // must go now: accept the conflict
+                            }
+                            const size_t k = le[pick];
+                            slots[k].round = r;
+                            used_by[slots[k].other & 7] = slots[k].other;
+                            le.erase(le.begin() + pick);
+                        }
+                    }
+                    s0 = s1;
                 }
             }
         } else {
@@ -344,7 +394,7 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         // empty slots
         for (int r = 0; r < rounds; r++) {
             uint16_t* oth = reinterpret_cast<uint16_t*>(P.slots.data() + size_t(b0 + r) * BLK + size_t(TN) * 24);
-            for (int lu = 0; lu < TN; lu++) oth[lu] = opt.scatter ? uint16_t(0xFFFF) : uint16_t(lu);
+            for (int lu = 0; lu < TN; lu++) oth[lu] = opt.scatter ? uint16_t(0xFFFF) : row_code(lu);
         }
         for (const Slot& s : slots) {
             unsigned char* blk = P.slots.data() + size_t(b0 + s.round) * BLK;
@@ -354,7 +404,7 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
             w[s.owner] = sg * P.ew[s.e];
             w[TN + s.owner] = sg * P.ew[L.nI + s.e];
             w[2 * TN + s.owner] = sg * P.ew[2 * L.nI + s.e];
-            oth[s.owner] = uint16_t(s.other);
+            oth[s.owner] = row_code(s.other);
         }
         P.used_slots += long(slots.size());
         // boundary / wall rounds: round r of a node = its r-th boundary or wall edge in original order
@@ -374,6 +424,21 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
             }
         }
     }
+    // fixed-stride tile headers (+ halo ids) for the pipelined stage kernel
+    P.hpad = (P.max_halo + 3) & ~3;
+    P.hdr_stride = 32 + 4 * P.hpad;
+    P.hdrs.assign(size_t(P.ntiles) * P.hdr_stride, 0);
+    for (long t = 0; t < P.ntiles; t++) {
+        unsigned char* h = P.hdrs.data() + size_t(t) * P.hdr_stride;
+        int* hi = reinterpret_cast<int*>(h);
+        long long* hl = reinterpret_cast<long long*>(h + 16);
+        hi[0] = int(P.slot_off[t + 1] - P.slot_off[t]);
+        hi[1] = int(P.halo_off[t + 1] - P.halo_off[t]);
+        hi[2] = int(P.bslot_off[t + 1] - P.bslot_off[t]);
+        hl[0] = P.slot_off[t]; hl[1] = P.bslot_off[t];
+        int* ids = reinterpret_cast<int*>(h + 32);
+        for (long k = P.halo_off[t]; k < P.halo_off[t + 1]; k++) ids[k - P.halo_off[t]] = P.halo_ids[k];
+    }
 }
 
 long check_colouring(const LevelPlan& P) {
@@ -390,9 +455,11 @@ long check_colouring(const LevelPlan& P) {
             const uint16_t* oth = reinterpret_cast<const uint16_t*>(blk + size_t(TN) * 24);
             std::fill(seen.begin(), seen.end(), 0);
             for (long lu = 0; lu < TN; lu++) {
-                const uint16_t o = oth[lu];
-                const bool empty = P.scatter ? (o == 0xFFFF) : (o == lu && w[lu] == 0.0 && w[TN + lu] == 0.0 && w[2 * TN + lu] == 0.0);
+                const uint16_t code = oth[lu];
+                const int o = row_of_code(code);
+                const bool empty = P.scatter ? (code == 0xFFFF) : (o == lu && w[lu] == 0.0 && w[TN + lu] == 0.0 && w[2 * TN + lu] == 0.0);
                 if (empty) continue;
+                if (code != row_code(o)) conflicts++;
                 stored++;
                 if (lu >= P.tile_nown[t]) conflicts++;               // padding threads must own nothing
                 if (o < TN) {

@@ -15,6 +15,8 @@ namespace mgcfd {
 struct PlanOptions {
     int ordering = 2;     // MGCFD_ORDER_*
     int tile_nodes = 256; // owned nodes per tile (= CTA size of the tiled kernel)
+    bool strict = true;   // false (introspection only): tiles whose halo cannot be staged are flagged (LevelPlan::oversize) instead of rejected
+    bool conflict_free_rounds = true;  // segment mode: schedule each node's edges over the rounds so that quarter-warps avoid shared-memory bank conflicts
     bool scatter = false; // true: coloured-scatter rounds (each in-tile edge once); false: sorted-segment rounds (every edge from both ends)
 };
 
@@ -28,15 +30,19 @@ struct LevelPlan {
     std::vector<int> tile_nown;           // owned nodes per tile
     std::vector<long> halo_off;           // ntiles+1
     std::vector<int> halo_ids;            // padded global ids, sorted per tile
-    bool scatter = false;
+    bool scatter = false, oversize = false;
     // edge rounds: per tile `rounds` blocks of TN*26 bytes, block = [hx[TN] | hy[TN] | hz[TN] | other[TN] (uint16)],
-    //   h = -0.5 * (edge vector oriented thread-node -> other); other = local index of the other endpoint (< TN owned,
-    //   >= TN halo).  Empty slot: scatter mode other = 0xFFFF; segment mode other = the thread's own index with h = 0.
+    //   h = -0.5 * (edge vector oriented thread-node -> other); other = the row of the other endpoint in the tile's shared
+    //   record buffer (local index o: < TN owned, >= TN halo) encoded as the byte offset of its chunk 0 under the 64B
+    //   swizzle, (o << 6) | (((o >> 1) & 3) << 4).  Empty slot: scatter mode 0xFFFF; segment mode the thread's own row, h = 0.
     std::vector<long> slot_off;           // ntiles+1, in blocks (prefix sum of rounds)
     std::vector<unsigned char> slots;
     // boundary/wall rounds: blocks of TN*25 bytes, block = [x[TN] | y[TN] | z[TN] | kind[TN] (uint8: 0 none, 1 boundary, 2 wall)]
     std::vector<long> bslot_off;          // ntiles+1, in blocks
     std::vector<unsigned char> bslots;
+    // fixed-stride tile headers: {int rounds, nh, brounds, pad; long slot_blk0, bslot_blk0; int halo_ids[hpad]}
+    std::vector<unsigned char> hdrs;
+    int hdr_stride = 0, hpad = 0;
     int max_halo = 0, max_rounds = 0;
     long cut_edges = 0, used_slots = 0;
     // ---- flat edge list in new numbering (atomic mode, indirect_rw, ordering sweeps) -------------

@@ -5,17 +5,17 @@ import numpy as np
 import mgcfd_b200 as M
 
 PEAK = 6548.5e9
-def probe(name, kind, dims, tn, ordering=2, cycles=20, modes=(0, 1), flux_mode=1):
+def probe(name, kind, dims, tn, ordering=2, cycles=20, modes=(0, 1), flux_mode=1, pf=True):
     t = time.time()
     mesh = M.Mesh.generate(kind, dims, mesh_variant=M.MESH_M6_WING)
     tg = time.time() - t
     t = time.time()
-    s = M.Solver.from_mesh(mesh, tile_nodes=tn, ordering=ordering, flux_mode=flux_mode)
+    s = M.Solver.from_mesh(mesh, tile_nodes=tn, ordering=ordering, flux_mode=flux_mode, pipeline=pf)
     tu = time.time() - t
     info = s.level_info(0)
     nel, nI, nB, nW = info["nel"], info["nI"], info["nB"], info["nW"]
     alg = 32 * nI + 28 * (nB + nW) + 128 * nel
-    out = {"mesh": name, "flux_mode": flux_mode, "tile": tn, "ordering": ordering, "nel": nel, "nI": nI, "gen_s": round(tg, 2), "setup_s": round(tu, 2),
+    out = {"mesh": name, "flux_mode": flux_mode, "pipeline": pf, "tile": tn, "ordering": ordering, "nel": nel, "nI": nI, "gen_s": round(tg, 2), "setup_s": round(tu, 2),
            "rounds": info["max_rounds"], "slot_util": round(info["used_slots"] / max(info["slots"], 1), 3), "smem": info["smem_bytes"]}
     names = {0: "fused_stage", 1: "tile_flux_only", 2: "indirect_rw", 3: "flux_atomic"}
     for which in modes:
@@ -35,18 +35,18 @@ def probe(name, kind, dims, tn, ordering=2, cycles=20, modes=(0, 1), flux_mode=1
     s.close()
 
 if __name__ == "__main__":
-    big = len(sys.argv) > 1 and sys.argv[1] == "big"
+    what = sys.argv[1] if len(sys.argv) > 1 else "quick"
     c2 = [[67, 67, 67], [55, 55, 55], [48, 48, 48], [43, 43, 43]]
-    for fm in (1, 0):
-        for tn in (128, 256, 512):
-            probe("c2-hex", M.GEN_HEX_BOX, c2, tn, flux_mode=fm)
-    probe("c2-hex-asgiven", M.GEN_HEX_BOX, c2, 256, ordering=0, modes=(0, 1, 2, 3))
-    probe("c2-hex-rcm", M.GEN_HEX_BOX, c2, 256, ordering=1, modes=(0, 1, 2, 3))
     tet = [[129, 129, 129], [65, 65, 65], [33, 33, 33], [17, 17, 17]]
-    for fm in (1, 0):
-        for tn in (128, 256):
-            probe("tet-2M", M.GEN_TET_BOX, tet, tn, cycles=5, flux_mode=fm)
-    if big:
-        tet8 = [[201, 201, 201], [101, 101, 101], [51, 51, 51], [26, 26, 26]]
+    tet8 = [[201, 201, 201], [101, 101, 101], [51, 51, 51], [26, 26, 26]]
+    if what == "quick":
+        for fm, tn, pf in ((1, 128, True), (1, 128, False), (1, 256, True), (0, 128, True), (0, 256, True)):
+            probe("c2-hex", M.GEN_HEX_BOX, c2, tn, flux_mode=fm, pf=pf)
+        for fm, tn, pf in ((1, 128, True), (1, 128, False), (1, 256, True), (0, 128, True)):
+            probe("tet-2M", M.GEN_TET_BOX, tet, tn, cycles=5, flux_mode=fm, pf=pf)
+    elif what == "orderings":
+        for o in (0, 1, 2):
+            probe("c2-hex-order%d" % o, M.GEN_HEX_BOX, c2, 128, ordering=o, modes=(0, 1, 2, 3))
+    elif what == "big":
         for fm in (1, 0):
-            probe("c3-tet-8M", M.GEN_TET_BOX, tet8, 256, cycles=3, flux_mode=fm)
+            probe("c3-tet-8M", M.GEN_TET_BOX, tet8, 128, cycles=3, flux_mode=fm)

@@ -285,13 +285,13 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "step": "one V-cycle (euler3d_cpu_double.cpp:371-694), all levels",
                    "edge_updates_per_step": units, "parallelism": "single GPU" if world == 1 else f"{world} independent replicas",
-                   "l2": "256 MiB buffer written before every timed cycle (L2 flush)", "flux_mode": int(kw.get("flux_mode", 0)),
+                   "l2": "256 MiB buffer written before every timed cycle (L2 flush)", "flux_mode": {0: "tiled coloured scatter", 1: "tiled sorted segment", 2: "atomic"}[int(kw.get("flux_mode", 1))], "pipelined": bool(info0["pipe_grid"]),
                    "tile_nodes": int(info0["tile_nodes"]), "setup_s": round(setup_s, 2)},
         "mg_cycles_per_sec": world * K / (ms_total * 1e-3),
         "flux_edge_updates_per_sec_by_level": per_level,
         "kernel_ms_timed_pass": kernel_share, "ms_per_step_timed_pass": ms_total_timed / K,
         "final_rms": float(rms[-1]) if len(rms) else None,
-        "roofline": {"bound": "hbm", "kernel": "k_tile_flux<fused> level 0 (flux + boundary + wall flux + time_step)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "k_stage_pipe level 0 (compute_flux_edge + boundary + wall flux + time_step fused, one launch per RK stage)", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_launch_ms * 1e3, "launches_timed": flux_launches0,
                      "edge_updates_per_sec": nI / (avg_launch_ms * 1e-3) if avg_launch_ms > 0 else 0.0},

@@ -373,9 +373,9 @@ extern "C" {
 void mgcfd_default_options(mgcfd_options* opt) {
     memset(opt, 0, sizeof(*opt));
     opt->device = 0;
-    opt->flux_mode = MGCFD_FLUX_TILED_COLOURED;
+    opt->flux_mode = MGCFD_FLUX_SORTED_SEGMENT;
     opt->ordering = MGCFD_ORDER_PARTITION_RCM;
-    opt->tile_nodes = 256;
+    opt->tile_nodes = 128;
     opt->use_graph = 1;
     opt->timing = 0;
 }
@@ -413,7 +413,7 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     *out = nullptr;
     mgcfd_options o;
     if (opt) o = *opt; else mgcfd_default_options(&o);
-    if (o.tile_nodes == 0) o.tile_nodes = 256;
+    if (o.tile_nodes == 0) o.tile_nodes = 128;
     if (o.tile_nodes != 128 && o.tile_nodes != 256 && o.tile_nodes != 512) { g_err = "tile_nodes must be 128, 256 or 512"; return MGCFD_ERR_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -898,7 +898,7 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     const EdgeNb* e = (const EdgeNb*)edges;
     H.edges.assign(e, e + nI + nB + nW);
     if (coords) H.coords.assign(coords, coords + 3 * nel);
-    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 256; po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 128; po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
     LevelPlan P;
     try { build_level_plan(H, po, P); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }

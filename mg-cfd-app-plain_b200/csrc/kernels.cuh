@@ -29,13 +29,13 @@ struct Flux5 { double r, mx, my, mz, e; };
 __device__ __forceinline__ double sqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double g = x * y, h = 0.5 * y;
-    double r = fma(-h, g, 0.5);
-    g = fma(g, r, g); h = fma(h, r, h);
-    r = fma(-h, g, 0.5);
-    g = fma(g, r, g); h = fma(h, r, h);
-    const double d = fma(-g, g, x);
-    return fma(d, h, g);
+    double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
+    double r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+    const double d = __fma_rn(-g, g, x);
+    return __fma_rn(d, h, g);
 }
 
 // per-node derived quantities (cfd_loops.h:121-148): velocity = momentum / rho, speed_sqd, pressure, speed of sound.
@@ -99,19 +99,21 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 // Adds A's five flux increments (flux_kernel.elemfunc.c:130-162) to acc; B's increments are their exact negation (:170-189).
 // Algebra: sum_d h_d * flux_contribution_momentum_x[d] = mx*(h.v) + p*hx etc. (cfd_loops.h:57-83), with h.v = (h.m)/rho.
 __device__ __forceinline__ double edge_weight(double hx, double hy, double hz) {
-    return sqrt_pos(fma(hx, hx, fma(hy, hy, fma(hz, hz, 1e-300))));   // + 1e-300: exact no-op unless h == 0 (empty slot)
+    return sqrt_pos(__fma_rn(hx, hx, __fma_rn(hy, hy, __fma_rn(hz, hz, 1e-300))));   // + 1e-300: exact no-op unless h == 0 (empty slot)
 }
+// Written with explicit round-to-nearest intrinsics: the compiler can neither contract nor reassociate them, so every
+// instantiation (simple / pipelined kernel, scatter / segment rounds, atomic baseline) produces the same bits for the same edge.
 __device__ __forceinline__ void edge_flux_acc_w(const Rec& A, double A_ep, const Rec& B, double hx, double hy, double hz, double ewt, double k2, Flux5& acc) {
-    const double factor = (ewt * k2) * (A.s + B.s);
-    const double gA = hx * A.mx + hy * A.my + hz * A.mz;
-    const double gB = hx * B.mx + hy * B.my + hz * B.mz;
-    const double qA = gA * A.ir, qB = gB * B.ir;
-    const double ps = A.p + B.p;
-    acc.r  += factor * (A.rho - B.rho) + (gA + gB);
-    acc.e  += factor * (A.re - B.re) + (A_ep * qA + (B.re + B.p) * qB);
-    acc.mx += factor * (A.mx - B.mx) + (A.mx * qA + B.mx * qB + ps * hx);
-    acc.my += factor * (A.my - B.my) + (A.my * qA + B.my * qB + ps * hy);
-    acc.mz += factor * (A.mz - B.mz) + (A.mz * qA + B.mz * qB + ps * hz);
+    const double factor = __dmul_rn(__dmul_rn(ewt, k2), __dadd_rn(A.s, B.s));
+    const double gA = __fma_rn(hz, A.mz, __fma_rn(hy, A.my, __dmul_rn(hx, A.mx)));
+    const double gB = __fma_rn(hz, B.mz, __fma_rn(hy, B.my, __dmul_rn(hx, B.mx)));
+    const double qA = __dmul_rn(gA, A.ir), qB = __dmul_rn(gB, B.ir);
+    const double ps = __dadd_rn(A.p, B.p);
+    acc.r  = __fma_rn(factor, __dsub_rn(A.rho, B.rho), __dadd_rn(gA, __dadd_rn(gB, acc.r)));
+    acc.e  = __fma_rn(factor, __dsub_rn(A.re, B.re), __fma_rn(A_ep, qA, __fma_rn(__dadd_rn(B.re, B.p), qB, acc.e)));
+    acc.mx = __fma_rn(factor, __dsub_rn(A.mx, B.mx), __fma_rn(A.mx, qA, __fma_rn(B.mx, qB, __fma_rn(ps, hx, acc.mx))));
+    acc.my = __fma_rn(factor, __dsub_rn(A.my, B.my), __fma_rn(A.my, qA, __fma_rn(B.my, qB, __fma_rn(ps, hy, acc.my))));
+    acc.mz = __fma_rn(factor, __dsub_rn(A.mz, B.mz), __fma_rn(A.mz, qA, __fma_rn(B.mz, qB, __fma_rn(ps, hz, acc.mz))));
 }
 __device__ __forceinline__ void edge_flux_acc(const Rec& A, double A_ep, const Rec& B, double hx, double hy, double hz, double k2, Flux5& acc) {
     edge_flux_acc_w(A, A_ep, B, hx, hy, hz, edge_weight(hx, hy, hz), k2, acc);

@@ -151,8 +151,8 @@ def test_plan_invariants(kind, dims, ordering, tile_nodes, flux_mode):
 
 def test_partition_rcm_improves_locality_on_a_shuffled_mesh():
     shuffled = M.Mesh.generate(M.GEN_HEX_BOX, [[24, 24, 24]], ordering=1, seed=7)
-    as_given, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_AS_GIVEN)
-    rcm, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_RCM)
-    part, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_PARTITION_RCM)
+    as_given, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_AS_GIVEN, tile_nodes=256)
+    rcm, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_RCM, tile_nodes=256)
+    part, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_PARTITION_RCM, tile_nodes=256)
     assert part["cut_edges"] < rcm["cut_edges"] < as_given["cut_edges"]
     assert part["halo_entries"] < 0.5 * as_given["halo_entries"]

@@ -1,0 +1,30 @@
+/* mgcfd_dist.h -- multi-GPU runs of libmgcfd_b200.so: one process per GPU, the mesh split over the ranks by recursive
+ * coordinate bisection, a halo exchange of node records after every Runge-Kutta stage / restriction / prolongation and of
+ * coarse residuals before every prolongation (ncclSend/ncclRecv over NVLink, grouped per exchange), plus two scalar
+ * all-reduces (min dt per smoothing visit: src/Kernels/cfd_loops.cpp:138-150; RMS sums per cycle: validation.cpp:91-105).
+ * The reference has no distributed path at all (single process): nothing here replaces a reference
+ * interface, it extends mgcfd_b200.h.  NCCL is loaded at run time (dlopen), so single-GPU users do not need it.
+ *
+ * Call order per rank:  mgcfd_create -> mgcfd_dist_init -> mgcfd_mesh_upload_partition (or your own partition through
+ * mgcfd_upload_level + the lists) -> mgcfd_run_cycles / mgcfd_enqueue_cycles + mgcfd_collect (collective: every rank calls
+ * them with the same arguments) -> mgcfd_get_field (local nodes: owned first, then ghosts; mgcfd_dist_global_ids maps them). */
+#ifndef MGCFD_DIST_H
+#define MGCFD_DIST_H
+#include "mgcfd_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* rank 0 creates the NCCL unique id; the host program broadcasts the 128 bytes to the other ranks (torch.distributed, MPI, a file) */
+int mgcfd_dist_get_unique_id(char id[128]);
+/* joins the communicator; after mgcfd_create, before any upload. CUDA graphs are switched off for distributed contexts. */
+int mgcfd_dist_init(mgcfd_ctx* ctx, int rank, int nranks, const char id[128]);
+/* info[0..6]: owned nodes, ghost nodes, nodes sent per exchange, nodes of the level over all ranks, rank, nranks, exchanges so far */
+int mgcfd_dist_level_info(mgcfd_ctx* ctx, int level, long info[8]);
+/* global node id of every local node (owned + ghost) */
+int mgcfd_dist_global_ids(mgcfd_ctx* ctx, int level, long* gid);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -104,6 +104,12 @@ def lib() -> C.CDLL:
     L.mgcfd_mesh_apply_ewt.argtypes = [vp]
     L.mgcfd_mesh_upload.argtypes = [vp, vp]
     L.mgcfd_mesh_free.argtypes = [vp]
+    L.mgcfd_mesh_upload_partition.argtypes = [vp, vp]
+    L.mgcfd_mesh_partition_plan.argtypes = [vp, i, i, i, C.POINTER(l), vp, vp, vp, vp]
+    L.mgcfd_dist_get_unique_id.argtypes = [C.c_char_p]
+    L.mgcfd_dist_init.argtypes = [vp, i, i, C.c_char_p]
+    L.mgcfd_dist_level_info.argtypes = [vp, i, C.POINTER(l)]
+    L.mgcfd_dist_global_ids.argtypes = [vp, i, vp]
     L.mgcfd_mesh_free.restype = None
     _lib = L
     return L
@@ -226,6 +232,28 @@ class Solver:
         for l in range(mesh.levels):
             s._nel[l] = mesh.dims(l)[0]
         return s
+
+    @classmethod
+    def from_mesh_distributed(cls, mesh: Mesh, rank: int, nranks: int, unique_id: bytes, **kw) -> "Solver":
+        """One rank of a multi-GPU run (include/mgcfd_dist.h): joins the NCCL communicator identified by `unique_id`
+        (from `dist_unique_id()` on rank 0, broadcast by the caller), keeps this rank's part of `mesh` and uploads it."""
+        s = cls(mesh.levels, mesh.mesh_variant, **kw)
+        _check(lib().mgcfd_dist_init(s._h, rank, nranks, unique_id))
+        _check(lib().mgcfd_mesh_upload_partition(mesh._h, s._h), mesh=True)
+        for l in range(mesh.levels):
+            info = s.dist_level_info(l)
+            s._nel[l] = info["owned"] + info["ghosts"]
+        return s
+
+    def dist_level_info(self, level):
+        out = (C.c_long * 8)()
+        _check(lib().mgcfd_dist_level_info(self._h, level, out))
+        return dict(zip(("owned", "ghosts", "sent", "global_nodes", "rank", "nranks", "exchanges"), out))
+
+    def global_ids(self, level):
+        g = np.empty(self._nel[level], dtype=np.int64)
+        _check(lib().mgcfd_dist_global_ids(self._h, level, _ptr(g)))
+        return g
 
     def upload_level(self, level, volumes, coords, nI, nB, nW, edges, mg_map=None):
         volumes = np.ascontiguousarray(volumes, dtype=np.float64)
@@ -355,6 +383,27 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+def dist_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on rank 0, broadcast to the others)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().mgcfd_dist_get_unique_id(buf))
+    return buf.raw
+
+
+def partition_plan(mesh: Mesh, nranks: int, rank: int, level: int):
+    """Host-only: what `rank` of `nranks` holds of `level` (owned/ghost global ids, per-peer send/receive counts, send order)."""
+    L = lib()
+    info = (C.c_long * 8)()
+    _check(L.mgcfd_mesh_partition_plan(mesh._h, nranks, rank, level, info, None, None, None, None), mesh=True)
+    owned, ghosts, sent = info[0], info[1], info[2]
+    gid = np.empty(owned + ghosts, dtype=np.int64)
+    sc, rc = np.zeros(nranks, dtype=np.int64), np.zeros(nranks, dtype=np.int64)
+    sg = np.empty(max(sent, 1), dtype=np.int64)
+    _check(L.mgcfd_mesh_partition_plan(mesh._h, nranks, rank, level, info, _ptr(gid), _ptr(sc), _ptr(rc), _ptr(sg)), mesh=True)
+    return dict(owned=owned, ghosts=ghosts, sent=sent, global_nodes=info[3], nI=info[4], nB=info[5], nW=info[6], gid=gid,
+                send_counts=sc, recv_counts=rc, send_gids=sg[:sent])
 
 
 INFO_KEYS = ("nel", "nI", "nB", "nW", "npad", "ntiles", "tile_nodes", "max_rounds", "slots", "halo_entries", "cut_edges",

@@ -12,6 +12,11 @@
 #include "host_mesh.h"
 #include "kernels.cuh"
 #include "plan.h"
+#include "partition.h"
+#include "../../include/mgcfd_dist.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
 
 using namespace mgcfd;
 
@@ -45,6 +50,8 @@ struct Level {
     LevelPlan plan;
     bool uploaded = false;
     long nel = 0, npad = 0, ntiles = 0, nI = 0, nB = 0, nW = 0;
+    long ncomp = 0;            // rows this rank computes (the owned tiles, = ntiles * TN); rows [ncomp, npad) are ghosts
+    long nel_global = 0;       // nodes of the level over all ranks (RMS normalisation)
     int TN = 256, smem_nodes = 0;
     size_t smem_bytes = 0;        // simple stage kernel
     size_t pipe_smem = 0;         // pipelined stage kernel
@@ -64,13 +71,39 @@ struct Level {
     int* parent = nullptr; double* idist_own = nullptr; long* ent_off = nullptr; int* ent_src = nullptr; double* ent_w = nullptr;
     double* rms_partial = nullptr; long rms_parts = 0;
     double* io = nullptr;      // AoS staging for get/set_field
+    // distributed runs: halo exchange lists (partition.h)
+    std::vector<long> send_off, recv_off, gid, send_list;
+    long nsend = 0, nghost = 0, n_owned = 0;
+    int* d_send_idx = nullptr; double *sendbuf = nullptr, *recvtmp = nullptr;
     double* V(int i) const { return buf[i]; }
 };
 
 }  // namespace
 
+// NCCL is resolved at run time (dlopen) so that single-GPU users of the library need no NCCL at all
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+struct Dist {
+    bool active = false;
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    long exchanges = 0;
+};
+
 struct mgcfd_ctx {
     mgcfd_options opt;
+    Dist dist;
+    double* d_rms_sums = nullptr;
     int levels = 0, variant = 2;
     bool finalized = false;
     std::vector<Level> L;
@@ -151,6 +184,80 @@ struct Timed {
 int post_launch(mgcfd_ctx* c) {
     c->launches++;
     CK(cudaGetLastError());
+    return MGCFD_OK;
+}
+
+// ---- distributed runs: NCCL over NVLink ---------------------------------------------------
+NcclApi g_nccl;
+int nccl_load() {
+    if (g_nccl.handle) return MGCFD_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    void* h = nullptr;
+    for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+    if (!h) { g_err = std::string("cannot load NCCL (libnccl.so.2): ") + dlerror(); return MGCFD_ERR_COMM; }
+    bool ok = true;
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) ok = false; return p; };
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+    g_nccl.Send = (decltype(g_nccl.Send))sym("ncclSend");
+    g_nccl.Recv = (decltype(g_nccl.Recv))sym("ncclRecv");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+    g_nccl.GroupStart = (decltype(g_nccl.GroupStart))sym("ncclGroupStart");
+    g_nccl.GroupEnd = (decltype(g_nccl.GroupEnd))sym("ncclGroupEnd");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { g_err = "libnccl is missing a required symbol"; dlclose(h); return MGCFD_ERR_COMM; }
+    g_nccl.handle = h;
+    return MGCFD_OK;
+}
+#define NK(call)                                                                                          \
+    do {                                                                                                  \
+        ncclResult_t r_ = (call);                                                                         \
+        if (r_ != ncclSuccess) { g_err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return MGCFD_ERR_COMM; } \
+    } while (0)
+
+// global minimum of the per-rank min-dt bit patterns (positive doubles order like their bits)
+int dist_allreduce_min(mgcfd_ctx* c) {
+    if (!c->dist.active) return MGCFD_OK;
+    NK(g_nccl.AllReduce(c->d_minbits, c->d_minbits, 1, ncclUint64, ncclMin, c->dist.comm, c->stream));
+    return MGCFD_OK;
+}
+int dist_allreduce_sum5(mgcfd_ctx* c) {
+    if (!c->dist.active) return MGCFD_OK;
+    NK(g_nccl.AllReduce(c->d_rms_sums, c->d_rms_sums, 5, ncclDouble, ncclSum, c->dist.comm, c->stream));
+    return MGCFD_OK;
+}
+// ghost records of level l in buffer `recs` <- their owners' records: pack the rows every peer needs, one grouped
+// ncclSend/ncclRecv per peer, received straight into the ghost rows (contiguous per owner)
+int dist_exchange_records(mgcfd_ctx* c, int l, double* recs) {
+    if (!c->dist.active) return MGCFD_OK;
+    Level& v = c->L[l];
+    if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
+    if (v.nsend) { k_pack_records<<<(unsigned)blocks_for(4 * v.nsend, 256), 256, 0, c->stream>>>(recs, v.d_send_idx, v.nsend, v.sendbuf); CKRC(post_launch(c)); }
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < c->dist.nranks; p++) {
+        const long ns = v.send_off[p + 1] - v.send_off[p], nr = v.recv_off[p + 1] - v.recv_off[p];
+        if (ns) NK(g_nccl.Send(v.sendbuf + 8 * v.send_off[p], 8 * (size_t)ns, ncclDouble, p, c->dist.comm, c->stream));
+        if (nr) NK(g_nccl.Recv(recs + 8 * (v.ncomp + v.recv_off[p]), 8 * (size_t)nr, ncclDouble, p, c->dist.comm, c->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    c->dist.exchanges++;
+    return MGCFD_OK;
+}
+int dist_exchange_residuals(mgcfd_ctx* c, int l) {
+    if (!c->dist.active) return MGCFD_OK;
+    Level& v = c->L[l];
+    if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
+    if (v.nsend) { k_pack_soa5<<<(unsigned)blocks_for(v.nsend, 256), 256, 0, c->stream>>>(v.res, v.npad, v.d_send_idx, v.nsend, v.sendbuf); CKRC(post_launch(c)); }
+    NK(g_nccl.GroupStart());
+    for (int p = 0; p < c->dist.nranks; p++) {
+        const long ns = v.send_off[p + 1] - v.send_off[p], nr = v.recv_off[p + 1] - v.recv_off[p];
+        if (ns) NK(g_nccl.Send(v.sendbuf + 5 * v.send_off[p], 5 * (size_t)ns, ncclDouble, p, c->dist.comm, c->stream));
+        if (nr) NK(g_nccl.Recv(v.recvtmp + 5 * v.recv_off[p], 5 * (size_t)nr, ncclDouble, p, c->dist.comm, c->stream));
+    }
+    NK(g_nccl.GroupEnd());
+    if (v.nghost) { k_unpack_soa5<<<(unsigned)blocks_for(v.nghost, 256), 256, 0, c->stream>>>(v.res, v.npad, v.ncomp, v.nghost, v.recvtmp); CKRC(post_launch(c)); }
+    c->dist.exchanges++;
     return MGCFD_OK;
 }
 
@@ -261,23 +368,33 @@ int flux_granular(mgcfd_ctx* c, int l, int mask) {
 int step_factor(mgcfd_ctx* c, int l, int legacy) {
     Level& v = c->L[l];
     Timed tm(c, K_STEP, l, v.nel);
-    const unsigned nb = (unsigned)blocks_for(v.npad, 256);
+    const unsigned nb = (unsigned)blocks_for(v.ncomp, 256);
     if (legacy) {
-        k_step_factor<true><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.vol, v.sf, c->d_minbits);
+        k_step_factor<true><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.vol, v.sf, c->d_minbits);
         CKRC(post_launch(c));
     } else {
         CK(cudaMemsetAsync(c->d_minbits, 0x7F, sizeof(unsigned long long), c->stream));
-        k_step_factor<false><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.vol_root, v.sf, c->d_minbits);
+        k_step_factor<false><<<nb, 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.vol_root, v.sf, c->d_minbits);
         CKRC(post_launch(c));
-        k_apply_min_dt<<<nb, 256, 0, c->stream>>>(c->d_minbits, v.vol, v.sf, v.npad);
+        CKRC(dist_allreduce_min(c));             // global min over all ranks (cfd_loops.cpp:138-145)
+        k_apply_min_dt<<<nb, 256, 0, c->stream>>>(c->d_minbits, v.vol, v.sf, v.ncomp);
         CKRC(post_launch(c));
     }
     return MGCFD_OK;
 }
 
 int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
-    k_rms_final<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel, use_counter ? c->d_rms : c->d_rms + 6 * (c->rms_cap - 1),
-                                          use_counter ? c->d_rms_counter : nullptr, c->rms_cap - 1);
+    double* out = use_counter ? c->d_rms : c->d_rms + 6 * (c->rms_cap - 1);
+    int* counter = use_counter ? c->d_rms_counter : nullptr;
+    if (!c->dist.active) {
+        k_rms_final<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel, out, counter, c->rms_cap - 1);
+        return post_launch(c);
+    }
+    // distributed: local sums of squares -> all-reduce(sum) of 5 doubles -> square roots over the global node count
+    k_rms_sums<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, c->d_rms_sums);
+    CKRC(post_launch(c));
+    CKRC(dist_allreduce_sum5(c));
+    k_rms_finish<<<1, 32, 0, c->stream>>>(c->d_rms_sums, (double)v.nel_global, out, counter, c->rms_cap - 1);
     return post_launch(c);
 }
 
@@ -301,6 +418,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
             a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
         }
         CKRC(launch_stage(c, v, a, true));
+        CKRC(dist_exchange_records(c, l, a.vout));
     }
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
@@ -310,15 +428,18 @@ int smooth_fused(mgcfd_ctx* c, int l) {
 int do_restrict(mgcfd_ctx* c, int lc) {
     Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
     Timed tm(c, K_RESTRICT, lc, vf.nel);
-    k_restrict<<<(unsigned)blocks_for(vc.npad, 128), 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.npad, vc.child_off, vc.child_ids);
-    return post_launch(c);
+    k_restrict<<<(unsigned)blocks_for(vc.ncomp, 128), 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids);
+    CKRC(post_launch(c));
+    return dist_exchange_records(c, lc, vc.V(vc.i_var));
 }
 int do_prolong(mgcfd_ctx* c, int lf) {
     Level& vf = c->L[lf]; Level& vc = c->L[lf + 1];
     Timed tm(c, K_PROLONG, lf, vf.nI);
-    k_prolong<<<(unsigned)blocks_for(vf.npad, 128), 128, 0, c->stream>>>(vf.npad, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
-                                                                       vc.res, vf.res, vf.V(vf.i_var));
-    return post_launch(c);
+    CKRC(dist_exchange_residuals(c, lf + 1));
+    k_prolong<<<(unsigned)blocks_for(vf.ncomp, 128), 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
+                                                                        vc.res, vf.res, vf.V(vf.i_var));
+    CKRC(post_launch(c));
+    return dist_exchange_records(c, lf, vf.V(vf.i_var));
 }
 
 // one full iteration of main()'s loop body sequence for a V-cycle (euler3d_cpu_double.cpp:371-694)
@@ -362,7 +483,7 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
 void free_level(Level& v) {
     void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
-                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.io};
+                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.io, v.d_send_idx, v.sendbuf, v.recvtmp};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -435,6 +556,7 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     CK(cudaMemset(c->d_badkey, 0xFF, 8));
     c->rms_cap = 4096 + 1;
     CK(cudaMalloc((void**)&c->d_rms, sizeof(double) * 6 * c->rms_cap));
+    CK(cudaMalloc((void**)&c->d_rms_sums, sizeof(double) * 8));
     CK(cudaMalloc((void**)&c->d_rms_counter, sizeof(int)));
     CK(cudaMemset(c->d_rms_counter, 0, sizeof(int)));
     mgcfd_far_field_conditions(c->ff, c->ffc);
@@ -450,7 +572,8 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& v : c->L) free_level(v);
-    cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_rms); cudaFree(c->d_rms_counter);
+    cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_rms); cudaFree(c->d_rms_counter); cudaFree(c->d_rms_sums);
+    if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -503,7 +626,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
     for (int l = 0; l < c->levels; l++) {
         Level& v = c->L[l];
         LevelPlan& P = v.plan;
-        v.nel = P.nel; v.npad = P.npad; v.ntiles = P.ntiles; v.nI = P.nI; v.nB = P.nB; v.nW = P.nW; v.TN = P.TN;
+        v.nel = P.nel; v.npad = P.npad; v.ncomp = P.npad_owned; v.ntiles = P.ntiles; v.nI = P.nI; v.nB = P.nB; v.nW = P.nW; v.TN = P.TN;
         v.smem_nodes = P.TN + P.hpad;
         v.smem_bytes = 64 * (size_t)v.smem_nodes + (P.scatter ? 40 * (size_t)P.TN : 0);
         // pipelined kernel: ring of RING entries of chunk_rounds round blocks + two record buffers + three header buffers
@@ -537,6 +660,17 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         CKRC(dev_upload(&v.hdrs, P.hdrs, s)); CKRC(dev_upload(&v.slots, P.slots, s)); CKRC(dev_upload(&v.bslots, P.bslots, s));
         v.pipe = false;
         if (!c->opt.no_pipeline) CKRC(setup_pipe(c, v));
+        if (v.nel_global == 0) v.nel_global = v.nel;
+        v.n_owned = P.n_owned;
+        if (c->dist.active) {
+            // halo exchange lists in device numbering
+            v.nsend = (long)v.send_list.size(); v.nghost = v.nel - v.n_owned;
+            std::vector<int> sidx(v.nsend);
+            for (long k = 0; k < v.nsend; k++) sidx[k] = (int)P.new_of_old[v.send_list[k]];
+            CKRC(dev_upload(&v.d_send_idx, sidx, s));
+            CK(cudaMalloc((void**)&v.sendbuf, sizeof(double) * 8 * std::max<long>(v.nsend, 1)));
+            CK(cudaMalloc((void**)&v.recvtmp, sizeof(double) * 5 * std::max<long>(v.nghost, 1)));
+        }
         const long parts = std::max<long>(v.ntiles, blocks_for(v.npad, 256));
         CK(cudaMalloc((void**)&v.rms_partial, sizeof(double) * 5 * parts));
         CK(cudaStreamSynchronize(s));
@@ -550,9 +684,10 @@ int mgcfd_finalize(mgcfd_ctx* c) {
     for (int l = 0; l + 1 < c->levels; l++) {
         Level& vf = c->L[l]; Level& vc = c->L[l + 1];
         for (long i = 0; i < vf.nel; i++)
-            if (vf.host.mg[i] < 0 || vf.host.mg[i] >= vc.nel) { g_err = "mg_map entry out of range"; return MGCFD_ERR_ARG; }
+            if (vf.host.mg[i] >= vc.nel || (vf.host.mg[i] < 0 && !c->dist.active)) { g_err = "mg_map entry out of range"; return MGCFD_ERR_ARG; }
         TransferPlan T;
-        build_transfer_plan(vf.host, vc.host, vf.plan, vc.plan, T);
+        try { build_transfer_plan(vf.host, vc.host, vf.plan, vc.plan, T); }
+        catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
         CKRC(dev_upload(&vc.child_off, T.child_off, s)); CKRC(dev_upload(&vc.child_ids, T.child_ids, s));
         CKRC(dev_upload(&vf.parent, T.parent, s)); CKRC(dev_upload(&vf.idist_own, T.idist_own, s));
         CKRC(dev_upload(&vf.ent_off, T.ent_off, s)); CKRC(dev_upload(&vf.ent_src, T.ent_src, s)); CKRC(dev_upload(&vf.ent_w, T.ent_w, s));
@@ -601,7 +736,7 @@ int mgcfd_time_step(mgcfd_ctx* c, int l, int j) {
     Level& v = c->L[l];
     CKRC(ensure_flux(c, v));
     Timed tm(c, K_TIME, l, v.nel);
-    k_time_step<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(double(MGCFD_RK + 1 - j), v.npad, v.npad, v.sf, v.flux, v.V(v.i_old), v.V(v.i_var));
+    k_time_step<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(double(MGCFD_RK + 1 - j), v.ncomp, v.npad, v.sf, v.flux, v.V(v.i_old), v.V(v.i_var));
     return post_launch(c);
 }
 int mgcfd_zero_fluxes(mgcfd_ctx* c, int l) {
@@ -622,14 +757,14 @@ int mgcfd_indirect_rw(mgcfd_ctx* c, int l) {
 int mgcfd_residual(mgcfd_ctx* c, int l) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
-    k_residual<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.npad, v.npad, v.V(v.i_old), v.V(v.i_var), v.res);
+    k_residual<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.ncomp, v.npad, v.V(v.i_old), v.V(v.i_var), v.res);
     return post_launch(c);
 }
 int mgcfd_calc_rms(mgcfd_ctx* c, int l, double* rms_all, double rms_var[5]) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
-    const long nb = blocks_for(v.npad, 256);
-    k_rms_partial<<<(unsigned)nb, 256, 0, c->stream>>>(v.res, v.npad, v.npad, v.rms_partial);
+    const long nb = blocks_for(v.ncomp, 256);
+    k_rms_partial<<<(unsigned)nb, 256, 0, c->stream>>>(v.res, v.npad, v.ncomp, v.rms_partial);
     CKRC(post_launch(c));
     v.rms_parts = nb;
     CKRC(rms_final(c, v, false));
@@ -645,7 +780,7 @@ int mgcfd_check_for_invalid_variables(mgcfd_ctx* c, int l, long* first_bad_cell,
     Level& v = c->L[l];
     unsigned long long* key = c->d_minbits;   // scratch word; the step-factor kernel re-initialises it before use
     CK(cudaMemsetAsync(key, 0xFF, 8, c->stream));
-    k_check_invalid<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad, v.old_of_new, key);
+    k_check_invalid<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.old_of_new, key);
     CKRC(post_launch(c));
     unsigned long long h = 0;
     CK(cudaMemcpyAsync(&h, key, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -733,6 +868,7 @@ int mgcfd_collect(mgcfd_ctx* c, double* rms_all, double* rms_var) {
     std::vector<double> h(6 * (size_t)std::max(n, 1));
     unsigned long long key = 0;
     if (n) CK(cudaMemcpyAsync(h.data(), c->d_rms, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (c->dist.active) NK(g_nccl.AllReduce(c->d_badkey, c->d_badkey, 1, ncclUint64, ncclMin, c->dist.comm, c->stream));   // every rank learns of an invalid state anywhere
     CK(cudaMemcpyAsync(&key, c->d_badkey, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemsetAsync(c->d_rms_counter, 0, sizeof(int), c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -908,6 +1044,94 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off[P.ntiles] * P.TN;
     if (new_of_old) memcpy(new_of_old, P.new_of_old.data(), sizeof(long) * nel);
     if (conflicts) *conflicts = P.oversize ? -1 : check_colouring(P);
+    return MGCFD_OK;
+}
+
+// ---- distributed runs (include/mgcfd_dist.h) -----------------------------------------------------------------
+int mgcfd_dist_get_unique_id(char id[128]) {
+    if (!id) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    CKRC(nccl_load());
+    ncclUniqueId u;
+    NK(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return MGCFD_OK;
+}
+int mgcfd_dist_init(mgcfd_ctx* c, int rank, int nranks, const char id[128]) {
+    if (!c || !id || nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    if (c->finalized || c->dist.active) { g_err = "mgcfd_dist_init must be called once, before any level is uploaded"; return MGCFD_ERR_ARG; }
+    if (c->opt.flux_mode == MGCFD_FLUX_ATOMIC) { g_err = "distributed runs need a tiled flux mode"; return MGCFD_ERR_ARG; }
+    CKRC(nccl_load());
+    CK(cudaSetDevice(c->opt.device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    NK(g_nccl.CommInitRank(&c->dist.comm, nranks, u, rank));
+    c->dist.active = true; c->dist.rank = rank; c->dist.nranks = nranks;
+    c->opt.use_graph = 0;        // the cycle interleaves NCCL calls with kernels; launched eagerly
+    return MGCFD_OK;
+}
+// uploads one level of a partition (partition.h) and records its exchange lists
+static int upload_local_level(mgcfd_ctx* c, int l, const LocalLevel& LL, long nel_global) {
+    const HostLevel& M = LL.mesh;
+    int rc = mgcfd_upload_level(c, l, M.nel, M.volumes.data(), M.coords.empty() ? nullptr : M.coords.data(), M.nI, M.nB, M.nW, M.edges.data(),
+                                M.mg.empty() ? nullptr : M.mg.data(), (long)M.mg.size());
+    if (rc) return rc;
+    Level& v = c->L[l];
+    v.send_off = LL.send_off; v.recv_off = LL.recv_off; v.send_list = LL.send_idx; v.gid = LL.gid;
+    v.host.gid = LL.gid;
+    v.nel_global = nel_global;
+    return MGCFD_OK;
+}
+int mgcfd_dist_level_info(mgcfd_ctx* c, int l, long info[8]) {
+    CKRC(check_level(c, l, false));
+    const Level& v = c->L[l];
+    memset(info, 0, sizeof(long) * 8);
+    info[0] = v.plan.n_owned; info[1] = v.plan.nel - v.plan.n_owned; info[2] = (long)v.send_list.size(); info[3] = v.nel_global;
+    info[4] = c->dist.rank; info[5] = c->dist.nranks; info[6] = c->dist.exchanges;
+    return MGCFD_OK;
+}
+int mgcfd_dist_global_ids(mgcfd_ctx* c, int l, long* gid) {
+    CKRC(check_level(c, l, false));
+    const Level& v = c->L[l];
+    if (!gid) { g_err = "null buffer"; return MGCFD_ERR_ARG; }
+    if (v.gid.empty()) for (long i = 0; i < v.plan.nel; i++) gid[i] = i;
+    else memcpy(gid, v.gid.data(), sizeof(long) * v.gid.size());
+    return MGCFD_OK;
+}
+int mgcfd_upload_partition(mgcfd_ctx* c, int levels, int mesh_variant, const void* host_mesh_opaque) {
+    // host_mesh_opaque: const mgcfd::HostMesh* (called from mesh_api.cpp, which owns the mesh type)
+    if (!c || !host_mesh_opaque) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    if (!c->dist.active) { g_err = "mgcfd_dist_init has not been called"; return MGCFD_ERR_ARG; }
+    const HostMesh& full = *(const HostMesh*)host_mesh_opaque;
+    if ((int)full.levels.size() != c->levels || levels != c->levels || mesh_variant != c->variant) { g_err = "mesh does not match the context"; return MGCFD_ERR_ARG; }
+    LocalMesh loc;
+    try { partition_mesh(full, c->dist.nranks, c->dist.rank, loc); }
+    catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    for (int l = 0; l < c->levels; l++) {
+        // mgcfd_upload_level copies into Level::host; n_owned / gid ride along for the plan builder
+        c->L[l].host.n_owned = loc.levels[l].n_owned;
+        CKRC(upload_local_level(c, l, loc.levels[l], full.levels[l].nel));
+    }
+    return mgcfd_finalize(c);
+}
+// host-only: the partition of one level for one rank (tests, tooling); any output pointer may be NULL
+int mgcfd_partition_plan(int levels, const void* host_mesh_opaque, int nranks, int rank, int level, long info[8], long* gid,
+                         long* send_counts, long* recv_counts, long* send_gids) {
+    if (!host_mesh_opaque || !info) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    const HostMesh& full = *(const HostMesh*)host_mesh_opaque;
+    if (level < 0 || level >= (int)full.levels.size() || levels != (int)full.levels.size()) { g_err = "bad level"; return MGCFD_ERR_ARG; }
+    LocalMesh loc;
+    try { partition_mesh(full, nranks, rank, loc); }
+    catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    const LocalLevel& LL = loc.levels[level];
+    memset(info, 0, sizeof(long) * 8);
+    info[0] = LL.n_owned; info[1] = (long)LL.gid.size() - LL.n_owned; info[2] = (long)LL.send_idx.size(); info[3] = full.levels[level].nel;
+    info[4] = LL.mesh.nI; info[5] = LL.mesh.nB; info[6] = LL.mesh.nW;
+    if (gid) memcpy(gid, LL.gid.data(), sizeof(long) * LL.gid.size());
+    for (int p = 0; p < nranks; p++) {
+        if (send_counts) send_counts[p] = LL.send_off[p + 1] - LL.send_off[p];
+        if (recv_counts) recv_counts[p] = LL.recv_off[p + 1] - LL.recv_off[p];
+    }
+    if (send_gids) for (size_t k = 0; k < LL.send_idx.size(); k++) send_gids[k] = LL.gid[LL.send_idx[k]];
     return MGCFD_OK;
 }
 

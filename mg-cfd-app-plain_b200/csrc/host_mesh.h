@@ -18,6 +18,10 @@ struct HostLevel {
     std::vector<double> coords;    // 3*nel (xyz AoS) or empty
     std::vector<long> mg;          // fine->coarse map (size nel) or empty on the coarsest level
     std::string name;              // file name used by the writer
+    // distributed runs (partition.h): nodes [0, n_owned) are owned by this rank, the rest are ghosts (never computed here);
+    // gid = global node ids, used wherever the reference's ordering (ascending node / edge index) decides a summation order
+    long n_owned = -1;             // -1: every node is owned
+    std::vector<long> gid;
 };
 
 struct HostMesh {

@@ -751,6 +751,57 @@ __global__ void k_indirect_rw(long ne, const int* __restrict__ ea, const int* __
 }
 
 // ------------------------------------------------------------------------------------------------------
+// distributed runs: halo exchange staging and the split RMS reduction
+// ------------------------------------------------------------------------------------------------------
+// send buffer of node records: dst row k = record idx[k] (one thread per 16-byte chunk)
+__global__ void k_pack_records(const double* __restrict__ recs, const int* __restrict__ idx, long n, double* __restrict__ dst) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= 4 * n) return;
+    const long k = i >> 2; const int c = int(i & 3);
+    reinterpret_cast<double2*>(dst)[4 * k + c] = reinterpret_cast<const double2*>(recs)[4 * (long)idx[k] + c];
+}
+// residuals (SoA planes) of the listed nodes -> packed rows of 5
+__global__ void k_pack_soa5(const double* __restrict__ soa, long stride, const int* __restrict__ idx, long n, double* __restrict__ dst) {
+    const long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const long g = idx[k];
+#pragma unroll
+    for (int j = 0; j < 5; j++) dst[5 * k + j] = soa[j * stride + g];
+}
+// packed rows of 5 -> SoA planes at rows row0 .. row0+n (the ghost rows)
+__global__ void k_unpack_soa5(double* __restrict__ soa, long stride, long row0, long n, const double* __restrict__ src) {
+    const long k = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (k >= n) return;
+#pragma unroll
+    for (int j = 0; j < 5; j++) soa[j * stride + row0 + k] = src[5 * k + j];
+}
+// calc_rms split around an all-reduce: local sums of squares, then the roots over the global node count
+__global__ void k_rms_sums(const double* __restrict__ partial, long nparts, double* __restrict__ sums) {
+    __shared__ double ws[5][256];
+    const int t = threadIdx.x;
+    double s[5] = {0, 0, 0, 0, 0};
+    for (long p = t; p < nparts; p += 256)
+#pragma unroll
+        for (int k = 0; k < 5; k++) s[k] += partial[p * 5 + k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) ws[k][t] = s[k];
+    __syncthreads();
+    if (t < 5) {
+        double acc = 0.0;
+        for (int j = 0; j < 256; j++) acc += ws[t][j];
+        sums[t] = acc;
+    }
+}
+__global__ void k_rms_finish(const double* __restrict__ sums, double nel, double* __restrict__ out, int* counter, int cap) {
+    if (threadIdx.x != 0) return;
+    int slot = 0;
+    if (counter) { slot = *counter; *counter = slot + 1; if (slot >= cap) slot = cap - 1; }
+    double tot = 0.0;
+    for (int k = 0; k < 5; k++) { out[slot * 6 + 1 + k] = sqrt(sums[k] / nel); tot += sums[k]; }
+    out[slot * 6] = sqrt(tot / nel);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // layout conversion at the boundary: reference AoS (old order) <-> device (new order, padded)
 // ------------------------------------------------------------------------------------------------------
 __global__ void k_export_soa(const double* __restrict__ soa, long stride, int ncomp, long nel, const int* __restrict__ new_of_old, double* __restrict__ aos) {

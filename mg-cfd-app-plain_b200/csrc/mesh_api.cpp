@@ -103,6 +103,27 @@ int mgcfd_mesh_upload(mgcfd_mesh* m, mgcfd_ctx* ctx) {
     return rc;
 }
 
+// implemented in context.cu (they need the context's internals); the mesh travels as an opaque pointer
+int mgcfd_upload_partition(mgcfd_ctx* c, int levels, int mesh_variant, const void* host_mesh_opaque);
+int mgcfd_partition_plan(int levels, const void* host_mesh_opaque, int nranks, int rank, int level, long info[8], long* gid,
+                         long* send_counts, long* recv_counts, long* send_gids);
+
+int mgcfd_mesh_upload_partition(mgcfd_mesh* m, mgcfd_ctx* ctx) {
+    if (!m || !ctx) { g_mesh_err = "null argument"; return MGCFD_ERR_ARG; }
+    int rc = mgcfd_mesh_apply_ewt(m);
+    if (rc) return rc;
+    rc = mgcfd_upload_partition(ctx, int(m->m.levels.size()), m->m.mesh_variant, &m->m);
+    if (rc) g_mesh_err = mgcfd_last_error();
+    return rc;
+}
+int mgcfd_mesh_partition_plan(mgcfd_mesh* m, int nranks, int rank, int level, long info[8], long* gid, long* send_counts,
+                              long* recv_counts, long* send_gids) {
+    if (!m) { g_mesh_err = "null argument"; return MGCFD_ERR_ARG; }
+    int rc = mgcfd_partition_plan(int(m->m.levels.size()), &m->m, nranks, rank, level, info, gid, send_counts, recv_counts, send_gids);
+    if (rc) g_mesh_err = mgcfd_last_error();
+    return rc;
+}
+
 void mgcfd_mesh_free(mgcfd_mesh* m) { delete m; }
 
 }  // extern "C"

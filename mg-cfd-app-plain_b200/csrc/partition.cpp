@@ -1,0 +1,189 @@
+// partition.cpp -- domain decomposition of a multigrid mesh over ranks (see partition.h).
+#include "partition.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <numeric>
+#include <stdexcept>
+
+namespace mgcfd {
+
+namespace {
+
+struct Csr {
+    std::vector<long> off;
+    std::vector<int> idx;
+};
+
+// undirected adjacency over the internal edges (global ids)
+Csr adjacency(const HostLevel& L) {
+    Csr g;
+    g.off.assign(L.nel + 1, 0);
+    for (long e = 0; e < L.nI; e++) { g.off[L.edges[e].a + 1]++; g.off[L.edges[e].b + 1]++; }
+    for (long i = 0; i < L.nel; i++) g.off[i + 1] += g.off[i];
+    g.idx.resize(g.off[L.nel]);
+    std::vector<long> pos(g.off.begin(), g.off.end() - 1);
+    for (long e = 0; e < L.nI; e++) {
+        g.idx[pos[L.edges[e].a]++] = int(L.edges[e].b);
+        g.idx[pos[L.edges[e].b]++] = int(L.edges[e].a);
+    }
+    return g;
+}
+// children (fine ids) of every coarse node
+Csr children(const HostLevel& fine, long ncoarse) {
+    Csr c;
+    c.off.assign(ncoarse + 1, 0);
+    for (long i = 0; i < fine.nel; i++) c.off[fine.mg[i] + 1]++;
+    for (long k = 0; k < ncoarse; k++) c.off[k + 1] += c.off[k];
+    c.idx.resize(fine.nel);
+    std::vector<long> pos(c.off.begin(), c.off.end() - 1);
+    for (long i = 0; i < fine.nel; i++) c.idx[pos[fine.mg[i]]++] = int(i);
+    return c;
+}
+
+void rcb(const double* coords, long* idx, long n, int k, int rank0, std::vector<int>& owner) {
+    if (k == 1) { for (long i = 0; i < n; i++) owner[idx[i]] = rank0; return; }
+    const int kl = k / 2;
+    const long nl = (n * kl + k / 2) / k;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (long i = 0; i < n; i++) for (int d = 0; d < 3; d++) {
+        const double c = coords[3 * idx[i] + d];
+        lo[d] = std::min(lo[d], c); hi[d] = std::max(hi[d], c);
+    }
+    int ax = 0;
+    for (int d = 1; d < 3; d++) if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+    std::nth_element(idx, idx + nl, idx + n, [coords, ax](long x, long y) {
+        const double cx = coords[3 * x + ax], cy = coords[3 * y + ax];
+        return cx != cy ? cx < cy : x < y;
+    });
+    rcb(coords, idx, nl, kl, rank0, owner);
+    rcb(coords, idx + nl, n - nl, k - kl, rank0 + kl, owner);
+}
+
+}  // namespace
+
+void rcb_owners(const HostLevel& L, int nranks, std::vector<int>& owner) {
+    owner.assign(L.nel, 0);
+    if (nranks <= 1) return;
+    std::vector<long> idx(L.nel);
+    std::iota(idx.begin(), idx.end(), 0L);
+    if (L.coords.empty()) {      // no coordinates (single-level meshes may come without): contiguous blocks of node ids
+        for (long i = 0; i < L.nel; i++) owner[i] = int((i * nranks) / L.nel);
+        return;
+    }
+    rcb(L.coords.data(), idx.data(), L.nel, nranks, 0, owner);
+}
+
+void partition_mesh(const HostMesh& full, int nranks, int rank, LocalMesh& out) {
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) throw std::runtime_error("mgcfd: bad rank / nranks (1..64 ranks)");
+    const int nl = int(full.levels.size());
+    out = LocalMesh();
+    out.mesh_variant = full.mesh_variant; out.rank = rank; out.nranks = nranks;
+    out.levels.resize(nl);
+
+    std::vector<std::vector<int>> owner(nl);
+    std::vector<Csr> adj(nl), kids(nl);         // kids[l]: children in level l-1 of the nodes of level l
+    for (int l = 0; l < nl; l++) {
+        rcb_owners(full.levels[l], nranks, owner[l]);
+        adj[l] = adjacency(full.levels[l]);
+        if (l > 0) kids[l] = children(full.levels[l - 1], full.levels[l].nel);
+    }
+    // flux_local[l][i]: owned by `rank` or edge neighbour of a node owned by `rank`
+    std::vector<std::vector<char>> flux_local(nl);
+    for (int l = 0; l < nl; l++) {
+        const long n = full.levels[l].nel;
+        flux_local[l].assign(n, 0);
+        for (long i = 0; i < n; i++) {
+            if (owner[l][i] != rank) continue;
+            flux_local[l][i] = 1;
+            for (long k = adj[l].off[i]; k < adj[l].off[i + 1]; k++) flux_local[l][adj[l].idx[k]] = 1;
+        }
+    }
+    // local node sets + global -> local maps
+    std::vector<std::vector<int>> g2l(nl);
+    for (int l = 0; l < nl; l++) {
+        const HostLevel& G = full.levels[l];
+        const long n = G.nel;
+        std::vector<char> need(n, 0);
+        for (long i = 0; i < n; i++) if (flux_local[l][i]) need[i] = 1;
+        if (l + 1 < nl) for (long i = 0; i < n; i++) if (owner[l + 1][G.mg[i]] == rank) need[i] = 1;            // restrict
+        if (l >= 1) {                                                                                               // prolong
+            const HostLevel& F = full.levels[l - 1];
+            for (long j = 0; j < F.nel; j++) if (flux_local[l - 1][j]) need[F.mg[j]] = 1;
+        }
+        LocalLevel& LL = out.levels[l];
+        std::vector<long> ghosts;
+        for (long i = 0; i < n; i++) {
+            if (owner[l][i] == rank) LL.gid.push_back(i);
+            else if (need[i]) ghosts.push_back(i);
+        }
+        LL.n_owned = long(LL.gid.size());
+        std::stable_sort(ghosts.begin(), ghosts.end(), [&](long x, long y) { return owner[l][x] < owner[l][y]; });   // ids stay ascending per owner
+        LL.recv_off.assign(nranks + 1, 0);
+        for (long g : ghosts) LL.recv_off[owner[l][g] + 1]++;
+        for (int p = 0; p < nranks; p++) LL.recv_off[p + 1] += LL.recv_off[p];
+        LL.gid.insert(LL.gid.end(), ghosts.begin(), ghosts.end());
+        g2l[l].assign(n, -1);
+        for (size_t k = 0; k < LL.gid.size(); k++) g2l[l][LL.gid[k]] = int(k);
+        // what the peers need from this rank (the mirror image of the three rules above)
+        std::vector<uint64_t> wanted(LL.n_owned, 0);
+        for (long k = 0; k < LL.n_owned; k++) {
+            const long i = LL.gid[k];
+            uint64_t m = 0;
+            for (long q = adj[l].off[i]; q < adj[l].off[i + 1]; q++) m |= 1ull << owner[l][adj[l].idx[q]];
+            if (l + 1 < nl) m |= 1ull << owner[l + 1][G.mg[i]];
+            if (l >= 1) {
+                for (long c = kids[l].off[i]; c < kids[l].off[i + 1]; c++) {
+                    const long j = kids[l].idx[c];
+                    m |= 1ull << owner[l - 1][j];
+                    for (long q = adj[l - 1].off[j]; q < adj[l - 1].off[j + 1]; q++) m |= 1ull << owner[l - 1][adj[l - 1].idx[q]];
+                }
+            }
+            wanted[k] = m & ~(1ull << rank);
+        }
+        LL.send_off.assign(nranks + 1, 0);
+        for (int p = 0; p < nranks; p++) {
+            for (long k = 0; k < LL.n_owned; k++) if ((wanted[k] >> p) & 1) LL.send_idx.push_back(k);
+            LL.send_off[p + 1] = long(LL.send_idx.size());
+        }
+    }
+    // local meshes
+    for (int l = 0; l < nl; l++) {
+        const HostLevel& G = full.levels[l];
+        LocalLevel& LL = out.levels[l];
+        HostLevel& M = LL.mesh;
+        const long nloc = long(LL.gid.size());
+        M.nel = nloc; M.name = G.name;
+        M.volumes.resize(nloc);
+        if (!G.coords.empty()) M.coords.resize(3 * nloc);
+        for (long k = 0; k < nloc; k++) {
+            const long i = LL.gid[k];
+            M.volumes[k] = G.volumes[i];
+            if (!G.coords.empty()) for (int d = 0; d < 3; d++) M.coords[3 * k + d] = G.coords[3 * i + d];
+        }
+        for (long e = 0; e < G.nI; e++) {
+            const EdgeNb& ed = G.edges[e];
+            if (owner[l][ed.a] != rank && owner[l][ed.b] != rank) continue;
+            M.edges.push_back({long(g2l[l][ed.a]), long(g2l[l][ed.b]), ed.x, ed.y, ed.z});
+            LL.edge_gid.push_back(e);
+        }
+        M.nI = long(M.edges.size());
+        for (int cls = 0; cls < 2; cls++) {
+            const long e0 = cls == 0 ? G.nI : G.nI + G.nB, e1 = cls == 0 ? G.nI + G.nB : G.nI + G.nB + G.nW;
+            long cnt = 0;
+            for (long e = e0; e < e1; e++) {
+                const EdgeNb& ed = G.edges[e];
+                if (owner[l][ed.b] != rank) continue;
+                M.edges.push_back({ed.a, long(g2l[l][ed.b]), ed.x, ed.y, ed.z});
+                cnt++;
+            }
+            (cls == 0 ? M.nB : M.nW) = cnt;
+        }
+        if (l + 1 < nl) {
+            M.mg.resize(nloc);
+            for (long k = 0; k < nloc; k++) M.mg[k] = g2l[l + 1][G.mg[LL.gid[k]]];
+        }
+    }
+}
+
+}  // namespace mgcfd

@@ -1,0 +1,46 @@
+// partition.h -- host-side domain decomposition of a multigrid mesh over the GPUs of one node.
+// The reference is a single process (its only "scaling" mechanism is -m mesh duplication, io_enhanced.cpp:89-201), so
+// this is new integer work: the host implementation below is the definition, tests check its invariants
+// (owned sets partition every level, ghost closure for flux / restrict / prolong, matching send / receive lists).
+//
+// Owner computes: every level is split into `nranks` parts by recursive coordinate bisection; a rank holds its owned nodes
+// plus GHOST copies of every foreign node its kernels read:
+//   flux      : the other endpoint of every internal edge of an owned node;
+//   restrict  : every child (level l) of an owned coarse node (level l+1)          (mg_restrict reads all children);
+//   prolong   : the coarse parents (level l+1) of every owned fine node and of all its edge neighbours
+//               (prolong_residuals_interpolate_proper reads their residuals).
+// Ghost nodes are never computed locally: their records / residuals are received from the owner.
+#pragma once
+#include <vector>
+
+#include "host_mesh.h"
+
+namespace mgcfd {
+
+struct LocalLevel {
+    HostLevel mesh;                    // local numbering: owned nodes first (ascending global id), then ghosts grouped by
+                                       // owner rank (ascending), ascending global id inside a group.  Internal edges: every
+                                       // global internal edge with at least one owned endpoint, in GLOBAL edge order;
+                                       // boundary / wall edges of owned nodes.  mesh.mg: local fine -> local coarse (-1 if the
+                                       // parent is not held, only for ghosts that do not need it).
+    long n_owned = 0;
+    std::vector<long> gid;             // local -> global node id
+    std::vector<long> edge_gid;        // local internal edge -> global edge index (ascending)
+    std::vector<long> send_off;        // nranks+1: send_idx[send_off[p]..send_off[p+1]) goes to rank p
+    std::vector<long> send_idx;        // local (owned) node indices, ascending global id per peer
+    std::vector<long> recv_off;        // nranks+1: ghosts [n_owned + recv_off[p], n_owned + recv_off[p+1]) come from rank p
+};
+
+struct LocalMesh {
+    int mesh_variant = 2;
+    int rank = 0, nranks = 1;
+    std::vector<LocalLevel> levels;
+};
+
+// owner rank of every node of one level: recursive coordinate bisection (widest extent, proportional split, ties by id)
+void rcb_owners(const HostLevel& L, int nranks, std::vector<int>& owner);
+
+// the part of `full` that rank `rank` of `nranks` holds (edge weights are taken as they are: apply adjust/dampen first)
+void partition_mesh(const HostMesh& full, int nranks, int rank, LocalMesh& out);
+
+}  // namespace mgcfd

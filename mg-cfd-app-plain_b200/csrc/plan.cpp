@@ -167,12 +167,15 @@ struct Mask256 {
 }  // namespace
 
 void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) {
-    const long n = L.nel;
+    const long nall = L.nel;                                   // owned + ghosts
+    const long n = L.n_owned >= 0 ? L.n_owned : L.nel;         // owned: only these are tiled, ordered and computed
     const long TN = opt.tile_nodes;
     P = LevelPlan();
-    P.nel = n; P.nI = L.nI; P.nB = L.nB; P.nW = L.nW; P.TN = int(TN);
+    P.nel = nall; P.nI = L.nI; P.nB = L.nB; P.nW = L.nW; P.TN = int(TN);
+    P.n_owned = n;
     P.ntiles = std::max<long>(1, (n + TN - 1) / TN);
-    P.npad = P.ntiles * TN;
+    P.npad_owned = P.ntiles * TN;
+    P.npad = P.npad_owned + (((nall - n) + 7) & ~7L);
     if (P.npad > 0x7fffffffL) throw std::runtime_error("mgcfd: level too large for 32-bit node ids");
     const Csr g = adjacency_old(L);
 
@@ -184,9 +187,9 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
     } else if (opt.ordering == 1) {
         std::vector<long> nodes(n), order;
         std::iota(nodes.begin(), nodes.end(), 0L);
-        std::vector<int> stamp(n, 0);
+        std::vector<int> stamp(nall, 0);
         order.reserve(n);
-        cm_order(g, nodes, [](long) { return true; }, stamp, 1, order);
+        cm_order(g, nodes, [n](long v) { return v < n; }, stamp, 1, order);
         std::reverse(order.begin(), order.end());   // reverse Cuthill-McKee
         for (long r = 0; r < n; r++) { tile_of[order[r]] = r / TN; seq[order[r]] = r; }
     } else {
@@ -201,20 +204,21 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         for (long t = 0; t < P.ntiles; t++) toff[t + 1] += toff[t];
         std::vector<long> members(n), pos(toff.begin(), toff.end() - 1);
         for (long i = 0; i < n; i++) members[pos[tile_of[i]]++] = i;
-        std::vector<int> stamp(n, 0);
+        std::vector<int> stamp(nall, 0);
         std::vector<long> order, nodes;
         long r = 0;
         for (long t = 0; t < P.ntiles; t++) {
             nodes.assign(members.begin() + toff[t], members.begin() + toff[t + 1]);
             order.clear();
-            cm_order(g, nodes, [&](long v) { return tile_of[v] == t; }, stamp, int(t % 1000000000) + 1, order);
+            cm_order(g, nodes, [&](long v) { return v < n && tile_of[v] == t; }, stamp, int(t % 1000000000) + 1, order);
             for (long v : order) seq[v] = r++;
             // stamps are tile specific (t+1) and tiles are disjoint, so no reset is needed
         }
     }
     // rank inside tile by seq
-    P.new_of_old.assign(n, -1);
+    P.new_of_old.assign(nall, -1);
     P.old_of_new.assign(P.npad, -1);
+    for (long i = n; i < nall; i++) { P.new_of_old[i] = P.npad_owned + (i - n); P.old_of_new[P.npad_owned + (i - n)] = i; }
     P.tile_nown.assign(P.ntiles, 0);
     {
         std::vector<long> byseq(n);
@@ -478,20 +482,32 @@ long check_colouring(const LevelPlan& P) {
 void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const LevelPlan& Pf, const LevelPlan& Pc, TransferPlan& T) {
     T = TransferPlan();
     const long nf = fine.nel;
-    // restrict: stable counting sort of fine nodes (ascending original index) by coarse parent
+    const long nf_owned = fine.n_owned >= 0 ? fine.n_owned : fine.nel;
+    const long nc_owned = coarse.n_owned >= 0 ? coarse.n_owned : coarse.nel;
+    // fine nodes in ascending GLOBAL index: the reference's accumulation order in mg_restrict (mg_loops.cpp:101-154)
+    std::vector<long> by_gid(nf);
+    std::iota(by_gid.begin(), by_gid.end(), 0L);
+    if (!fine.gid.empty()) std::sort(by_gid.begin(), by_gid.end(), [&](long x, long y) { return fine.gid[x] < fine.gid[y]; });
+    // restrict: stable counting sort of the children of every OWNED coarse node
+    auto restricts = [&](long i) { return fine.mg[i] >= 0 && fine.mg[i] < nc_owned; };
     T.child_off.assign(Pc.npad + 1, 0);
-    for (long i = 0; i < nf; i++) T.child_off[Pc.new_of_old[fine.mg[i]] + 1]++;
+    long nchildren = 0;
+    for (long i = 0; i < nf; i++) if (restricts(i)) { T.child_off[Pc.new_of_old[fine.mg[i]] + 1]++; nchildren++; }
     for (long i = 0; i < Pc.npad; i++) T.child_off[i + 1] += T.child_off[i];
-    T.child_ids.resize(nf);
+    T.child_ids.resize(nchildren);
     {
         std::vector<long> pos(T.child_off.begin(), T.child_off.end() - 1);
-        for (long i = 0; i < nf; i++) T.child_ids[pos[Pc.new_of_old[fine.mg[i]]]++] = int(Pf.new_of_old[i]);
+        for (long i : by_gid) if (restricts(i)) T.child_ids[pos[Pc.new_of_old[fine.mg[i]]]++] = int(Pf.new_of_old[i]);
     }
-    // prolong
+    // prolong (owned fine nodes only)
     T.parent.assign(Pf.npad, -1);
     T.idist_own.assign(Pf.npad, 0.0);
     T.ent_off.assign(Pf.npad + 1, 0);
-    for (long i = 0; i < Pf.npad; i++) T.ent_off[i + 1] = T.ent_off[i] + (Pf.adj_off[i + 1] - Pf.adj_off[i]);
+    for (long i = 0; i < Pf.npad; i++) {
+        const long on = Pf.old_of_new[i];
+        const long cnt = (on >= 0 && on < nf_owned) ? (Pf.adj_off[i + 1] - Pf.adj_off[i]) : 0;
+        T.ent_off[i + 1] = T.ent_off[i] + cnt;
+    }
     T.ent_src.resize(T.ent_off[Pf.npad]);
     T.ent_w.resize(T.ent_off[Pf.npad]);
     const double* cf = fine.coords.data();
@@ -502,8 +518,9 @@ void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const L
     };
     for (long id = 0; id < Pf.npad; id++) {
         const long on = Pf.old_of_new[id];
-        if (on < 0) continue;
+        if (on < 0 || on >= nf_owned) continue;
         const long p = fine.mg[on];
+        if (p < 0) throw std::runtime_error("mgcfd: an owned fine node has no local coarse parent (partition closure violated)");
         T.parent[id] = int(Pc.new_of_old[p]);
         const double dx = cf[3 * on] - cc[3 * p], dy = cf[3 * on + 1] - cc[3 * p + 1], dz = cf[3 * on + 2] - cc[3 * p + 2];
         const bool coincident = (dx == 0.0 && dy == 0.0 && dz == 0.0);     // exact test, mg_loops.cpp:745,781
@@ -512,6 +529,7 @@ void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const L
             const bool node_is_b = Pf.adj_nbr[k] < 0;
             const long om = Pf.old_of_new[Pf.adj_nbr[k] & 0x7fffffff];
             const long q = fine.mg[om];
+            if (q < 0) throw std::runtime_error("mgcfd: the coarse parent of an edge neighbour is not local (partition closure violated)");
             T.ent_w[o] = idist(&cc[3 * q], &cf[3 * on]);
             // mg_loops.cpp:804-810: on the b side the neighbour-parent term multiplies residuals1[b1] (= own parent)
             T.ent_src[o] = int(Pc.new_of_old[node_is_b ? p : q]);

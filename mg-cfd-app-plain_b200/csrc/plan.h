@@ -23,7 +23,8 @@ struct PlanOptions {
 struct LevelPlan {
     long nel = 0, nI = 0, nB = 0, nW = 0;
     int TN = 256;
-    long ntiles = 0, npad = 0;
+    long ntiles = 0, npad = 0;             // npad = rows of every node array: owned tiles (ntiles*TN) + ghosts
+    long n_owned = 0, npad_owned = 0;      // tiles cover the owned nodes only; ghost g sits in row npad_owned + g
     std::vector<long> new_of_old;         // nel -> padded id
     std::vector<long> old_of_new;         // npad -> old id or -1 (padding)
     // ---- tiled, coloured flux structure -------------------------------------------------------

@@ -1,0 +1,21 @@
+"""Multi-GPU parity (needs >= 2 GPUs; skipped on a single-GPU box): tools/dist_check.py under torchrun, every rank running its
+part of the mesh over NCCL, compared on rank 0 with the single-GPU solver (1e-11)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_distributed_matches_single_gpu(nranks):
+    import torch
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    port = 29600 + nranks
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "dist_check PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

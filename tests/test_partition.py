@@ -1,0 +1,108 @@
+"""Domain decomposition (host side, no GPU): invariants of the partition every rank computes for itself, checked in one
+process and -- the way the ranks really run -- across a world_size-2 gloo group."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import mgcfd_b200 as M
+from conftest import mesh_levels
+
+MESHES = [(0, [[12, 11, 10], [6, 6, 5], [3, 3, 3]]), (1, [[9, 8, 7], [5, 4, 4]]), (2, [[5, 4, 4]])]
+
+
+@pytest.mark.parametrize("kind,dims", MESHES)
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4, 8])
+def test_partition_invariants(kind, dims, nranks):
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=0 if kind == 2 else 2)
+    lv = mesh_levels(mesh)
+    for l in range(mesh.levels):
+        plans = [M.partition_plan(mesh, nranks, r, l) for r in range(nranks)]
+        n = lv[l]["nel"]
+        owner = np.full(n, -1)
+        for r, p in enumerate(plans):
+            own = p["gid"][:p["owned"]]
+            assert np.all(owner[own] == -1)                       # owned sets are disjoint ...
+            owner[own] = r
+            assert np.all(np.diff(own) > 0)                       # ... ascending ...
+            assert len(np.unique(p["gid"])) == len(p["gid"])      # a node is local at most once
+            assert p["global_nodes"] == n
+        assert np.all(owner >= 0)                                  # ... and cover the level
+        sizes = np.bincount(owner, minlength=nranks)
+        assert sizes.max() - sizes.min() <= max(2, nranks)        # balanced bisection
+        e = lv[l]["edges"]
+        nI = lv[l]["nI"]
+        for r, p in enumerate(plans):
+            loc = np.zeros(n, bool); loc[p["gid"]] = True
+            own = owner == r
+            # flux closure: both ends of every edge of an owned node are local; the rank holds exactly those edges
+            touch = own[e["a"][:nI]] | own[e["b"][:nI]]
+            assert np.all(loc[e["a"][:nI]][touch]) and np.all(loc[e["b"][:nI]][touch])
+            assert p["nI"] == int(touch.sum())
+            assert p["nB"] + p["nW"] == int(own[e["b"][nI:]].sum())
+            # ghosts grouped by owner, ascending id inside a group; receive counts match
+            gh = p["gid"][p["owned"]:]
+            assert np.all(np.diff(owner[gh]) >= 0)
+            assert np.array_equal(np.bincount(owner[gh], minlength=nranks), p["recv_counts"])
+            assert p["recv_counts"][r] == 0 and p["send_counts"][r] == 0
+            # what r sends to q is exactly what q holds as ghosts of r, in the same order
+            off = 0
+            for q in range(nranks):
+                cnt = p["send_counts"][q]
+                sent = p["send_gids"][off:off + cnt]; off += cnt
+                ghq = plans[q]["gid"][plans[q]["owned"]:]
+                assert np.array_equal(sent, ghq[owner[ghq] == r])
+            if l + 1 < mesh.levels:                                # restrict closure: all children of owned coarse nodes are local
+                co = M.partition_plan(mesh, nranks, r, l + 1)
+                cown = np.zeros(lv[l + 1]["nel"], bool); cown[co["gid"][:co["owned"]]] = True
+                cloc = np.zeros(lv[l + 1]["nel"], bool); cloc[co["gid"]] = True
+                assert np.all(loc[cown[lv[l]["map"]]])
+                # prolong closure: parents of owned fine nodes and of their edge neighbours are local on the coarse level
+                nb = np.zeros(n, bool); nb[own] = True
+                nb[e["b"][:nI][own[e["a"][:nI]]]] = True; nb[e["a"][:nI][own[e["b"][:nI]]]] = True
+                assert np.all(cloc[lv[l]["map"][nb]])
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mesh = M.Mesh.generate(1, [[9, 8, 7], [5, 4, 4]], mesh_variant=2)
+        ok = True
+        for l in range(mesh.levels):
+            p = M.partition_plan(mesh, world, rank, l)
+            mine = {"gid": p["gid"].tolist(), "owned": p["owned"], "send_counts": p["send_counts"].tolist(), "send_gids": p["send_gids"].tolist(),
+                    "recv_counts": p["recv_counts"].tolist()}
+            allp = [None] * world
+            dist.all_gather_object(allp, mine)
+            # the rank-to-rank contract, checked with the peers' own data: my ghosts from q == q's send list to me
+            for qr in range(world):
+                if qr == rank:
+                    continue
+                o = allp[qr]
+                off = sum(o["send_counts"][:rank])
+                their_send = o["send_gids"][off:off + o["send_counts"][rank]]
+                start = p["owned"] + int(np.sum(p["recv_counts"][:qr]))
+                my_ghosts = p["gid"][start:start + p["recv_counts"][qr]].tolist()
+                ok = ok and (their_send == my_ghosts) and (o["recv_counts"][rank] == p["send_counts"][qr])
+            total = sum(a["owned"] for a in allp)
+            ok = ok and total == p["global_nodes"]
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_contract_across_two_gloo_ranks():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,68 @@
+"""Multi-GPU parity check, run under torchrun (one rank per GPU):
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+Every rank runs its part of the mesh; rank 0 also runs the whole mesh on its own GPU and compares (1e-11, per-variable Linf)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import mgcfd_b200 as M
+
+
+def bcast_id(rank):
+    buf = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        buf = torch.frombuffer(bytearray(M.dist_unique_id()), dtype=torch.uint8).clone()
+    dist.broadcast(buf, 0)
+    return bytes(buf.numpy().tobytes())
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    dist.init_process_group("gloo")
+    torch.cuda.set_device(local)
+    cases = [("hex4", 0, [[26, 24, 22], [13, 12, 11], [7, 6, 6], [4, 3, 3]], 2), ("tet3", 1, [[17, 15, 13], [9, 8, 7], [5, 4, 4]], 3), ("fvcorr", 2, [[9, 8, 7]], 0)]
+    cycles = 8
+    worst = 0.0
+    for name, kind, dims, variant in cases:
+        uid = bcast_id(rank)
+        mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+        s = M.Solver.from_mesh_distributed(mesh, rank, world, uid, device=local)
+        ra, rv = s.run_cycles(cycles)
+        pieces = []
+        for l in range(mesh.levels):
+            info = s.dist_level_info(l)
+            var = s.get_field(l, M.FIELD_VARIABLES)[:info["owned"]]
+            pieces.append((s.global_ids(l)[:info["owned"]], var.copy()))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, pieces)
+        ex = s.dist_level_info(0)["exchanges"]
+        s.close()
+        if rank == 0:
+            ref = M.Solver.from_mesh(M.Mesh.generate(kind, dims, mesh_variant=variant), device=local)
+            rra, rrv = ref.run_cycles(cycles)
+            e_rms = float(np.max(np.abs(ra - rra) / rra))
+            e_var = 0.0
+            for l in range(mesh.levels):
+                want = ref.get_field(l, M.FIELD_VARIABLES)
+                got = np.full_like(want, np.nan)
+                for p in gathered:
+                    got[p[l][0]] = p[l][1]
+                scale = np.max(np.abs(want), axis=0)
+                e_var = max(e_var, float(np.max(np.max(np.abs(got - want), axis=0) / scale)))
+            ref.close()
+            print(f"dist_check {name}: {world} ranks, {cycles} cycles, exchanges={ex}, max rel err rms={e_rms:.2e} variables={e_var:.2e}", flush=True)
+            worst = max(worst, e_rms, e_var)
+    ok = torch.tensor([1 if worst < 1e-11 else 0])
+    dist.broadcast(ok, 0)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("dist_check", "PASS" if worst < 1e-11 else "FAIL", f"worst={worst:.2e}", flush=True)
+    sys.exit(0 if int(ok) else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,9 @@ def main():
     torch.cuda.set_device(local)
     cases = [("hex4", 0, [[26, 24, 22], [13, 12, 11], [7, 6, 6], [4, 3, 3]], 2), ("tet3", 1, [[17, 15, 13], [9, 8, 7], [5, 4, 4]], 3), ("fvcorr", 2, [[9, 8, 7]], 0)]
     cycles = 8
+    if len(sys.argv) > 1 and sys.argv[1] == "big":      # one mid-size case: many tiles per persistent CTA, 100 KB-class messages
+        cases = [("hex4-big", 0, [[133, 67, 67], [109, 55, 55], [95, 48, 48], [85, 43, 43]], 2)]
+        cycles = 4
     worst = 0.0
     for name, kind, dims, variant in cases:
         uid = bcast_id(rank)

@@ -40,6 +40,8 @@ int mgcfd_mesh_upload_partition(mgcfd_mesh* m, mgcfd_ctx* ctx);
  * global ids in send order. Any output pointer may be NULL. */
 int mgcfd_mesh_partition_plan(mgcfd_mesh* m, int nranks, int rank, int level, long info[8], long* gid, long* send_counts,
                               long* recv_counts, long* send_gids);
+/* -m / --mesh-duplicate-count: `count` independent copies of every level, laid out as duplicate_mesh (io_enhanced.cpp:89-201) */
+int mgcfd_mesh_duplicate(mgcfd_mesh* m, int count);
 void mgcfd_mesh_free(mgcfd_mesh* m);
 const char* mgcfd_mesh_last_error(void);
 

@@ -16,6 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmgcfd_b200.so")
+DRIVER_PATH = os.path.join(_HERE, "euler3d_b200")     # the reference's euler3d driver on top of the C ABI
 
 NVAR = 5
 RK = 3
@@ -105,6 +106,7 @@ def lib() -> C.CDLL:
     L.mgcfd_mesh_upload.argtypes = [vp, vp]
     L.mgcfd_mesh_free.argtypes = [vp]
     L.mgcfd_mesh_upload_partition.argtypes = [vp, vp]
+    L.mgcfd_mesh_duplicate.argtypes = [vp, i]
     L.mgcfd_mesh_partition_plan.argtypes = [vp, i, i, i, C.POINTER(l), vp, vp, vp, vp]
     L.mgcfd_dist_get_unique_id.argtypes = [C.c_char_p]
     L.mgcfd_dist_init.argtypes = [vp, i, i, C.c_char_p]
@@ -191,6 +193,10 @@ class Mesh:
 
     def mg_map(self, level):
         return self._view(level, 3, np.int64, self.dims(level)[4])
+
+    def duplicate(self, count: int):
+        """-m / --mesh-duplicate-count: `count` independent copies, laid out as duplicate_mesh (io_enhanced.cpp:89-201)."""
+        _check(lib().mgcfd_mesh_duplicate(self._h, count), mesh=True)
 
     def apply_ewt(self):
         """adjust_ewt + dampen_ewt (src/Kernels/validation.cpp:28-75) as main() applies them per mesh variant."""

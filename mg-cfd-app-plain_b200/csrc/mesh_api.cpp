@@ -1,6 +1,8 @@
 // mesh_api.cpp -- extern "C" surface of the host mesh utilities (include/mgcfd_mesh.h)
+#include <algorithm>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/mgcfd_mesh.h"
 #include "host_mesh.h"
@@ -122,6 +124,45 @@ int mgcfd_mesh_partition_plan(mgcfd_mesh* m, int nranks, int rank, int level, lo
     int rc = mgcfd_partition_plan(int(m->m.levels.size()), &m->m, nranks, rank, level, info, gid, send_counts, recv_counts, send_gids);
     if (rc) g_mesh_err = mgcfd_last_error();
     return rc;
+}
+
+// -m / --mesh-duplicate-count: m independent copies of every level, laid out as duplicate_mesh does (io_enhanced.cpp:89-201):
+// nodes copy-major, each edge class copy-major inside its own range, MG maps shifted per copy
+int mgcfd_mesh_duplicate(mgcfd_mesh* m, int count) {
+    if (!m || count < 1) { g_mesh_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    if (count == 1) return MGCFD_OK;
+    const int nl = int(m->m.levels.size());
+    std::vector<long> nel0(nl);
+    for (int l = 0; l < nl; l++) nel0[l] = m->m.levels[l].nel;
+    for (int l = 0; l < nl; l++) {
+        HostLevel& L = m->m.levels[l];
+        const long n = L.nel, nI = L.nI, nB = L.nB, nW = L.nW;
+        HostLevel D;
+        D.name = L.name; D.nel = n * count; D.nI = nI * count; D.nB = nB * count; D.nW = nW * count;
+        D.volumes.resize(D.nel);
+        if (!L.coords.empty()) D.coords.resize(3 * D.nel);
+        for (int c = 0; c < count; c++) {
+            std::copy(L.volumes.begin(), L.volumes.end(), D.volumes.begin() + c * n);
+            if (!L.coords.empty()) std::copy(L.coords.begin(), L.coords.end(), D.coords.begin() + 3 * c * n);
+        }
+        D.edges.reserve(D.nI + D.nB + D.nW);
+        const long start[3] = {0, nI, nI + nB}, cnt[3] = {nI, nB, nW};
+        for (int cls = 0; cls < 3; cls++)
+            for (int c = 0; c < count; c++)
+                for (long e = 0; e < cnt[cls]; e++) {
+                    EdgeNb ed = L.edges[start[cls] + e];
+                    if (ed.a >= 0) ed.a += c * n;
+                    ed.b += c * n;
+                    D.edges.push_back(ed);
+                }
+        if (!L.mg.empty()) {
+            D.mg.resize(D.nel);
+            for (int c = 0; c < count; c++) for (long i = 0; i < n; i++) D.mg[c * n + i] = L.mg[i] + c * nel0[l + 1];
+        }
+        L = std::move(D);
+    }
+    m->m.size *= count;
+    return MGCFD_OK;
 }
 
 void mgcfd_mesh_free(mgcfd_mesh* m) { delete m; }

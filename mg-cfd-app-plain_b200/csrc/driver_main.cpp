@@ -194,8 +194,10 @@ const char* variant_name(int v) {
 // identification columns of prepare_csv_identification (io_enhanced.cpp:858-1016); CPU items carry the GPU equivalents
 void csv_identification(std::ostringstream& header, std::ostringstream& line, int size, int variant, int flux_mode) {
     header << "Size,Mesh,MG cycles,Flux variant,Flux options,CC,CC version,Opt level,Instruction set,SIMD,SIMD len,OpenMP,Num threads,Permit scatter OpenMP,Flux fission,CPU,";
+    std::string version(mgcfd_version());
+    for (char& ch : version) if (ch == ',') ch = ';';
     const char* fm = flux_mode == MGCFD_FLUX_TILED_COLOURED ? "TiledColoured;" : (flux_mode == MGCFD_FLUX_ATOMIC ? "Atomic;" : "SortedSegment;");
-    line << size << "," << variant_name(variant) << "," << conf.num_cycles << ",Normal," << fm << "FusedTimeStep;,nvcc," << mgcfd_version() << ",3,sm_100a,N,1,N,1,N,N,NVIDIA B200 (device " << conf.device << "),";
+    line << size << "," << variant_name(variant) << "," << conf.num_cycles << ",Normal," << fm << "FusedTimeStep;,nvcc," << version << ",3,sm_100a,N,1,N,1,N,N,NVIDIA B200 (device " << conf.device << "),";
 }
 
 }  // namespace

@@ -248,3 +248,41 @@ def test_pipelined_kernel_many_tiles_per_cta(M, oracle):
     assert np.array_equal(ra, rb)
     assert np.array_equal(s.get_field(0, M.FIELD_VARIABLES), s2.get_field(0, M.FIELD_VARIABLES))
     s.close(); s2.close()
+
+
+@pytest.mark.parametrize("workload,cycles", [("c1", 5), ("c2", 3)])
+def test_baseline_configs_at_full_size_match_oracle(M, oracle, workload, cycles):
+    """BASELINE.json configs[0] (fvcorr-shaped, 97.5 K cells, the reference's CPU-runnable validation case) and configs[1]
+    (Onera-M6-shaped 4-level, 300 K fine nodes) at FULL size against the CPU oracle, 1e-11 per variable."""
+    import bench
+    kind, dims, variant, _ = bench.WORKLOADS[workload]
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    ora, orv, st = oracle.run_cycles(variant, lv, cycles)
+    s = M.Solver.from_mesh(mesh)
+    ra, rv = s.run_cycles(cycles)
+    assert np.max(np.abs(ra - ora) / ora) < TOL
+    assert np.max(np.abs(rv - orv) / np.maximum(orv, 1e-300)) < TOL
+    for l in range(mesh.levels):
+        assert np.all(linf_rel(s.get_field(l, M.FIELD_VARIABLES), st[l]["var"]) < TOL), l
+    s.close()
+
+
+def test_large_mesh_properties(M):
+    """C3-class size (2.1 M-node tet box, 4 levels): size-independent properties instead of an oracle run --
+    bit-reproducibility run to run, agreement of the two tiled flux modes (different summation orders) to 1e-11,
+    a finite, slowly decaying RMS history and conservation of the uniform far-field state away from the walls."""
+    dims = [[129] * 3, [65] * 3, [33] * 3, [17] * 3]
+    outs = []
+    for fm in (1, 1, 0):
+        s = M.Solver.from_mesh(M.Mesh.generate(1, dims, mesh_variant=2), flux_mode=fm)
+        ra, _ = s.run_cycles(4)
+        outs.append((ra, s.get_field(0, M.FIELD_VARIABLES).copy()))
+        s.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.max(np.abs(outs[0][0] - outs[2][0]) / outs[0][0]) < TOL
+    assert np.all(linf_rel(outs[2][1], outs[0][1]) < TOL)
+    ra = outs[0][0]
+    assert np.all(np.isfinite(ra)) and np.all(ra > 0) and np.all(np.diff(ra) < 0) and ra[0] < 1e-5
+    ffv, _ = M.far_field_conditions()
+    assert np.max(np.abs(outs[0][1] - ffv) / np.abs(ffv[0])) < 1e-3

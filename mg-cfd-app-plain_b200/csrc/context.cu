@@ -1001,14 +1001,15 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
     Level& v = c->L[l];
     CKRC(ensure_flux(c, v));
     if (which == 2 || which == 3) CKRC(ensure_flat(c, v));
-    if ((which == 0 || which == 1) && c->opt.flux_mode == MGCFD_FLUX_ATOMIC) { g_err = "the stage kernel needs a tiled flux mode"; return MGCFD_ERR_ARG; }
+    if ((which == 0 || which == 1 || which == 5) && c->opt.flux_mode == MGCFD_FLUX_ATOMIC) { g_err = "the stage kernel needs a tiled flux mode"; return MGCFD_ERR_ARG; }
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int r = 0; r < reps; r++) {
-        if (which == 0 || which == 1) {
+        if (which == 0 || which == 1 || which == 5) {
             StageArgs a = base_args(c, v);
             a.vin = v.V(v.i_var); a.vold = v.V(v.i_var); a.rk_div = 4.0;
             if (which == 0) { a.vout = v.V(v.i_tmp); a.mask = 7; CKRC(launch_stage(c, v, a, true)); }
+            else if (which == 5) { a.vout = v.V(v.i_tmp); a.mask = 6; CKRC(launch_stage(c, v, a, true)); }   // no internal edges: staging + update only
             else { a.flux = v.flux; a.mask = 1; CKRC(launch_stage(c, v, a, false)); }
         } else if (which == 2) {
             k_indirect_rw<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux); CKRC(post_launch(c));

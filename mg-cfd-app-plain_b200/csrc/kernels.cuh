@@ -418,21 +418,22 @@ k_stage_pipe(const StageArgs a) {
         const TileHdr* hd = hdr_of(it);
         const int* ids = reinterpret_cast<const int*>(hd + 1);
         unsigned char* buf = recs + (it & 1) * 64 * (size_t)a.rec_rows;
+        // four lanes per record (one 16-byte chunk each): a warp instruction moves 8 whole 64-byte records, i.e. full sectors
+        const int k16 = (t & 3) << 4;
         {
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vin + 8 * (tile_of(it) * TN + t));
-            unsigned char* row = buf + 64 * t;
-            const int x = ((t >> 1) & 3) << 4;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vin + 8 * (tile_of(it) * TN));
 #pragma unroll
-            for (int k = 0; k < 4; k++) cp_async16(row + ((16 * k) ^ x), src + 16 * k);
+            for (int j = 0; j < 4; j++) {
+                const int row = (t >> 2) + j * (TN / 4);
+                cp_async16(buf + 64 * row + (k16 ^ (((row >> 1) & 3) << 4)), src + 64 * row + k16);
+            }
         }
         const int nh = hd->nh;
-        for (int h = t; h < nh; h += TN) {
+        for (int i = t; i < 4 * nh; i += TN) {
+            const int h = i >> 2;
             const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vin + 8 * (long)ids[h]);
             const int o = TN + h;
-            unsigned char* row = buf + 64 * o;
-            const int x = ((o >> 1) & 3) << 4;
-#pragma unroll
-            for (int k = 0; k < 4; k++) cp_async16(row + ((16 * k) ^ x), src + 16 * k);
+            cp_async16(buf + 64 * o + (k16 ^ (((o >> 1) & 3) << 4)), src + k16);
         }
         cp_async_mbar_arrive(&bar_recs[it & 1]);
     };

@@ -17,7 +17,7 @@ def probe(name, kind, dims, tn, ordering=2, cycles=20, modes=(0, 1), flux_mode=1
     alg = 32 * nI + 28 * (nB + nW) + 128 * nel
     out = {"mesh": name, "flux_mode": flux_mode, "pipeline": pf, "tile": tn, "ordering": ordering, "nel": nel, "nI": nI, "gen_s": round(tg, 2), "setup_s": round(tu, 2),
            "rounds": info["max_rounds"], "slot_util": round(info["used_slots"] / max(info["slots"], 1), 3), "smem": info["smem_bytes"]}
-    names = {0: "fused_stage", 1: "tile_flux_only", 2: "indirect_rw", 3: "flux_atomic"}
+    names = {0: "fused_stage", 1: "tile_flux_only", 2: "indirect_rw", 3: "flux_atomic", 5: "stage_without_edges"}
     for which in modes:
         s.time_kernel(0, which, 3)
         reps = 20
@@ -44,6 +44,10 @@ if __name__ == "__main__":
             probe("c2-hex", M.GEN_HEX_BOX, c2, tn, flux_mode=fm, pf=pf)
         for fm, tn, pf in ((1, 128, True), (1, 128, False), (1, 256, True), (0, 128, True)):
             probe("tet-2M", M.GEN_TET_BOX, tet, tn, cycles=5, flux_mode=fm, pf=pf)
+    elif what == "overhead":
+        for tn in (128, 256):
+            probe("c2-hex", M.GEN_HEX_BOX, c2, tn, modes=(0, 5))
+            probe("tet-2M", M.GEN_TET_BOX, tet, tn, cycles=5, modes=(0, 5))
     elif what == "orderings":
         for o in (0, 1, 2):
             probe("c2-hex-order%d" % o, M.GEN_HEX_BOX, c2, 128, ordering=o, modes=(0, 1, 2, 3))

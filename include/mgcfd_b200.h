@@ -68,7 +68,7 @@ typedef struct mgcfd_options {
     int device;     /* CUDA device ordinal (default 0) */
     int flux_mode;  /* MGCFD_FLUX_* (default MGCFD_FLUX_SORTED_SEGMENT: the faster of the two tiled modes on B200, profiles/) */
     int ordering;   /* MGCFD_ORDER_* */
-    int tile_nodes; /* owned nodes per tile = threads per CTA of the tiled kernel; 0 = default (128) */
+    int tile_nodes; /* owned nodes per tile = threads per CTA of the tiled kernel; 0 = auto (default): 256 below a million nodes per level, 128 above; else 128, 256 or 512 */
     int use_graph;  /* run_cycles replays one captured CUDA graph per V-cycle (default 1) */
     int timing;     /* record CUDA-event times per kernel per level (forces use_graph=0) */
     int no_pipeline; /* 1: fused stages use the simple one-CTA-per-tile kernel instead of the persistent kernel whose transfers

@@ -218,7 +218,7 @@ class Solver:
     """Device-resident multigrid state + the reference's kernel functions, one method per function."""
 
     def __init__(self, levels: int, mesh_variant: int, device: int = 0, flux_mode: int = FLUX_SORTED_SEGMENT,
-                 ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 128, use_graph: bool = True, timing: bool = False,
+                 ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0, use_graph: bool = True, timing: bool = False,
                  pipeline: bool = True):
         L = lib()
         opt = Options()
@@ -416,7 +416,7 @@ INFO_KEYS = ("nel", "nI", "nB", "nW", "npad", "ntiles", "tile_nodes", "max_round
              "used_slots", "max_halo", "bslots", "smem_bytes", "pipe_grid")
 
 
-def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 128, flux_mode: int = FLUX_SORTED_SEGMENT):
+def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0, flux_mode: int = FLUX_SORTED_SEGMENT):
     """Host-only integer preprocessing of one level: returns (info dict, new_of_old permutation, colouring conflicts)."""
     nel, nI, nB, nW, _ = mesh.dims(level)
     info = (C.c_long * 16)()

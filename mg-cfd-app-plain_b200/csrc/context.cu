@@ -70,6 +70,7 @@ struct Level {
     long* child_off = nullptr; int* child_ids = nullptr;       // stored on the COARSE level (children in level-1)
     int* parent = nullptr; double* idist_own = nullptr; long* ent_off = nullptr; int* ent_src = nullptr; double* ent_w = nullptr;
     double* rms_partial = nullptr; long rms_parts = 0;
+    double* blockmins = nullptr;
     double* io = nullptr;      // AoS staging for get/set_field
     // distributed runs: halo exchange lists (partition.h)
     std::vector<long> send_off, recv_off, gid, send_list;
@@ -111,6 +112,7 @@ struct mgcfd_ctx {
     double ff[5], ffc[12];
     bool have_ff = false;
     unsigned long long* d_minbits = nullptr;
+    unsigned int* d_ticket = nullptr;
     unsigned long long* d_badkey = nullptr;
     double* d_rms = nullptr;       // [cap][6]
     int* d_rms_counter = nullptr;
@@ -326,7 +328,7 @@ StageArgs base_args(mgcfd_ctx* c, Level& v) {
     a.chunk_rounds = v.chunk_rounds;
     a.k2 = 2.0 * c->kdiss;
     a.old_of_new = v.old_of_new;
-    a.sf = v.sf;
+    a.sf = v.sf; a.vol = v.vol; a.min_bits = c->d_minbits; a.legacy = (c->variant == MGCFD_MESH_FVCORR);
     return a;
 }
 
@@ -399,9 +401,20 @@ int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
 }
 
 // one smoothing visit (euler3d_cpu_double.cpp:383-512) on the fused path
+// fused path: only the global minimum is a kernel of its own (one launch); min/volume resp. the legacy local form are
+// evaluated inside the stage kernels (step_factor_of)
+int min_dt_fused(mgcfd_ctx* c, int l) {
+    if (c->variant == MGCFD_MESH_FVCORR) return MGCFD_OK;
+    Level& v = c->L[l];
+    Timed tm(c, K_STEP, l, v.nel);
+    k_min_dt<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.vol_root, v.blockmins, c->d_ticket, c->d_minbits);
+    CKRC(post_launch(c));
+    return dist_allreduce_min(c);
+}
+
 int smooth_fused(mgcfd_ctx* c, int l) {
     Level& v = c->L[l];
-    CKRC(step_factor(c, l, c->variant == MGCFD_MESH_FVCORR));
+    CKRC(min_dt_fused(c, l));
     const int X = v.i_var, A = v.i_tmp, B = v.i_old;   // the previous old_variables are dead once a smooth starts
     for (int j = 0; j < MGCFD_RK; j++) {
         Timed tm(c, K_FLUX, l, v.nI);
@@ -483,7 +496,7 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
 void free_level(Level& v) {
     void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
-                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.io, v.d_send_idx, v.sendbuf, v.recvtmp};
+                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -496,7 +509,7 @@ void mgcfd_default_options(mgcfd_options* opt) {
     opt->device = 0;
     opt->flux_mode = MGCFD_FLUX_SORTED_SEGMENT;
     opt->ordering = MGCFD_ORDER_PARTITION_RCM;
-    opt->tile_nodes = 128;
+    opt->tile_nodes = 0;     // auto
     opt->use_graph = 1;
     opt->timing = 0;
 }
@@ -534,8 +547,7 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     *out = nullptr;
     mgcfd_options o;
     if (opt) o = *opt; else mgcfd_default_options(&o);
-    if (o.tile_nodes == 0) o.tile_nodes = 128;
-    if (o.tile_nodes != 128 && o.tile_nodes != 256 && o.tile_nodes != 512) { g_err = "tile_nodes must be 128, 256 or 512"; return MGCFD_ERR_ARG; }
+    if (o.tile_nodes != 0 && o.tile_nodes != 128 && o.tile_nodes != 256 && o.tile_nodes != 512) { g_err = "tile_nodes must be 0 (auto), 128, 256 or 512"; return MGCFD_ERR_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev <= 0 || o.device >= ndev) {
@@ -553,6 +565,8 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0)); CK(cudaEventCreate(&c->ev1));
     CK(cudaMalloc((void**)&c->d_minbits, 8)); CK(cudaMalloc((void**)&c->d_badkey, 8));
+    CK(cudaMalloc((void**)&c->d_ticket, 4)); CK(cudaMemset(c->d_ticket, 0, 4));
+    { const double one = 1.0; CK(cudaMemcpy(c->d_minbits, &one, 8, cudaMemcpyHostToDevice)); }   // a finite value until the first k_min_dt
     CK(cudaMemset(c->d_badkey, 0xFF, 8));
     c->rms_cap = 4096 + 1;
     CK(cudaMalloc((void**)&c->d_rms, sizeof(double) * 6 * c->rms_cap));
@@ -572,7 +586,7 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& v : c->L) free_level(v);
-    cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_rms); cudaFree(c->d_rms_counter); cudaFree(c->d_rms_sums);
+    cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_ticket); cudaFree(c->d_rms); cudaFree(c->d_rms_counter); cudaFree(c->d_rms_sums);
     if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -610,7 +624,10 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     }
     if (coords) H.coords.assign(coords, coords + 3 * nel); else H.coords.clear();
     if (mg_map && l < c->levels - 1) H.mg.assign(mg_map, mg_map + mgc); else H.mg.clear();
-    PlanOptions po; po.ordering = c->opt.ordering; po.tile_nodes = c->opt.tile_nodes; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
+    PlanOptions po; po.ordering = c->opt.ordering; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
+    // auto tile size (measured, profiles/): 256-node tiles on levels that are latency-bound (fewer, fatter tiles, smaller halo
+    // share), 128-node tiles on multi-million-node levels (more CTAs in flight per SM)
+    po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : ((H.n_owned >= 0 ? H.n_owned : nel) < 1000000 ? 256 : 128);
     try { build_level_plan(H, po, v.plan); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     v.uploaded = true;
@@ -673,6 +690,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         }
         const long parts = std::max<long>(v.ntiles, blocks_for(v.npad, 256));
         CK(cudaMalloc((void**)&v.rms_partial, sizeof(double) * 5 * parts));
+        CK(cudaMalloc((void**)&v.blockmins, sizeof(double) * parts));
         CK(cudaStreamSynchronize(s));
         // node state: every buffer starts at the far-field state (what initialize_variables leaves, cfd_loops.h:44-55);
         // padding nodes keep it forever (no edges, zero residual), which keeps them finite in every stage
@@ -815,7 +833,7 @@ long launches_per_cycle(mgcfd_ctx* c) {
     long per_cycle = 0;
     for (int l = 0; l < c->levels; l++) {
         const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
-        per_cycle += visits * (MGCFD_RK + (c->variant == MGCFD_MESH_FVCORR ? 1 : 2)) + (l == 0 ? 1 : 0);
+        per_cycle += visits * (MGCFD_RK + (c->variant == MGCFD_MESH_FVCORR ? 0 : 1)) + (l == 0 ? 1 : 0);
     }
     return per_cycle + 2 * (c->levels - 1);
 }
@@ -1035,7 +1053,7 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     const EdgeNb* e = (const EdgeNb*)edges;
     H.edges.assign(e, e + nI + nB + nW);
     if (coords) H.coords.assign(coords, coords + 3 * nel);
-    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : 128; po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : (nel < 1000000 ? 256 : 128); po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
     LevelPlan P;
     try { build_level_plan(H, po, P); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }

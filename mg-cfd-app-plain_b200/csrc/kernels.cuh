@@ -170,7 +170,10 @@ struct StageArgs {
     double* vout;          // records: stage output state (FUSED)
     double* flux;          // SoA fluxes (+=) (!FUSED)
     double* res;           // SoA residuals (last stage) or nullptr
-    const double* sf;      // step factors
+    double* sf;            // step factors: written by stage 0 of a fused smooth (kept for mgcfd_get_field / --output-step-factors)
+    const double* vol;     // volumes
+    const unsigned long long* min_bits;   // bit pattern of the global minimum dt of this smoothing visit (k_min_dt)
+    int legacy;            // compute_step_factor_legacy (mesh_name = fvcorr): no global minimum
     long stride;           // npad
     const unsigned char* hdrs; int hdr_stride;    // TileHdr + halo ids, one per tile
     const unsigned char* slots;   // edge round blocks of TN*26 bytes
@@ -267,6 +270,11 @@ __device__ __forceinline__ void boundary_rounds(const unsigned char* blk, int br
         else wall_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
     }
 }
+// step factor of one node, evaluated where it is used (cfd_loops.cpp:146-156 / :60): min_dt / volume, or the legacy local form
+__device__ __forceinline__ double step_factor_of(const StageArgs& a, double vol, double s_old) {
+    if (a.legacy) return double(0.5) / (sqrt(vol) * s_old);
+    return __longlong_as_double((long long)*a.min_bits) / vol;
+}
 // phase 3 of a fused stage for node gid: time_step + record + validity + residual; returns the five squared residuals in q
 __device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5]) {
     const long S = a.stride;
@@ -352,15 +360,18 @@ k_stage(const StageArgs a) {
         const long S = a.stride;
         a.flux[gid] += f.r; a.flux[S + gid] += f.mx; a.flux[2 * S + gid] += f.my; a.flux[3 * S + gid] += f.mz; a.flux[4 * S + gid] += f.e;
     } else {
-        double o[5];
+        double o[5], s_old = me.s;
         if (a.vold == a.vin) { o[0] = me.rho; o[1] = me.mx; o[2] = me.my; o[3] = me.mz; o[4] = me.re; }
         else {
             const double2* p = reinterpret_cast<const double2*>(a.vold + 8 * gid);
             const double2 c0 = p[0], c1 = p[1];
             o[0] = c0.x; o[1] = c0.y; o[2] = c1.x; o[3] = c1.y; o[4] = a.vold[8 * gid + 4];
+            if (a.legacy) s_old = a.vold[8 * gid + 7];
         }
+        const double sf = step_factor_of(a, a.vol[gid], s_old);
+        if (a.vold == a.vin) a.sf[gid] = sf;
         double q[5] = {0, 0, 0, 0, 0};
-        fused_update(a, gid, a.sf[gid], o, f, q);
+        fused_update(a, gid, sf, o, f, q);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
     }
 }
@@ -469,15 +480,17 @@ k_stage_pipe(const StageArgs a) {
         mbar_wait(&bar_recs[it & 1], (it >> 1) & 1);       // records of T_it and the header of T_{it+1} have landed
         copy_recs(it + 1);
         if (t == 0) produce(it + 1);
-        const double sf = a.sf[gid];                       // early loads for the epilogue
+        const double vol = a.vol[gid];                     // early loads for the epilogue
         double o[5];
         const unsigned char* buf = recs + (it & 1) * 64 * (size_t)a.rec_rows;
         const Rec me = sm_load_rec_off(buf, (unsigned(t) << 6) | (((unsigned(t) >> 1) & 3u) << 4));
+        double s_old = me.s;
         if (a.vold == a.vin) { o[0] = me.rho; o[1] = me.mx; o[2] = me.my; o[3] = me.mz; o[4] = me.re; }
         else {
             const double2* p = reinterpret_cast<const double2*>(a.vold + 8 * gid);
             const double2 c0 = p[0], c1 = p[1];
             o[0] = c0.x; o[1] = c0.y; o[2] = c1.x; o[3] = c1.y; o[4] = a.vold[8 * gid + 4];
+            if (a.legacy) s_old = a.vold[8 * gid + 7];
         }
         if (SCATTER) {
 #pragma unroll
@@ -497,6 +510,8 @@ k_stage_pipe(const StageArgs a) {
         }
         if (a.mask & 6) boundary_rounds<TN>(a.bslots + hd->bslot_blk0 * (long)(TN * 25), hd->brounds, t, a.mask, me, f);
         if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
+        const double sf = step_factor_of(a, vol, s_old);
+        if (a.vold == a.vin) a.sf[gid] = sf;
         double q[5] = {0, 0, 0, 0, 0};
         fused_update(a, gid, sf, o, f, q);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
@@ -542,6 +557,44 @@ __global__ void k_step_factor(const double* __restrict__ recs, long n, const dou
 __global__ void k_apply_min_dt(const unsigned long long* __restrict__ min_bits, const double* __restrict__ vol, double* __restrict__ sf, long n) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i < n) sf[i] = __longlong_as_double((long long)*min_bits) / vol[i];
+}
+
+// fused path: the global minimum of 0.5 * cbrt(vol) / (|v| + c) (cfd_loops.cpp:123-145) in ONE launch -- block minima, then the
+// last block to finish (ticket counter) reduces them and publishes the bit pattern; nothing to reset between launches
+__global__ void k_min_dt(const double* __restrict__ recs, long n, const double* __restrict__ vol_root, double* __restrict__ blockmins,
+                         unsigned int* __restrict__ ticket, unsigned long long* __restrict__ min_bits) {
+    const double BIG = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
+    __shared__ double wmin[32];
+    __shared__ bool last;
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    double val = BIG;
+    if (i < n) val = 0.5 * (vol_root[i] / recs[8 * i + 7]);
+    auto block_min = [&](double v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = (threadIdx.x < (blockDim.x >> 5)) ? wmin[threadIdx.x] : BIG;
+        if (threadIdx.x < 32) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
+        }
+        __syncthreads();
+        return v;      // valid in thread 0
+    };
+    val = block_min(val);
+    if (threadIdx.x == 0) {
+        blockmins[blockIdx.x] = val;
+        __threadfence();
+        last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);     // wraps back to 0 for the next launch
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double v = BIG;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) v = fmin(v, ((volatile double*)blockmins)[b]);
+    v = block_min(v);
+    if (threadIdx.x == 0) *min_bits = (unsigned long long)__double_as_longlong(v);
 }
 
 // time_step (cfd_loops.cpp:215-280), granular API

@@ -42,7 +42,7 @@ def test_version_and_defaults():
     assert b"sm_100a" in L.mgcfd_version()
     o = M.Options()
     L.mgcfd_default_options(C.byref(o))
-    assert (o.flux_mode, o.ordering, o.tile_nodes, o.use_graph) == (M.FLUX_SORTED_SEGMENT, M.ORDER_PARTITION_RCM, 128, 1)
+    assert (o.flux_mode, o.ordering, o.tile_nodes, o.use_graph) == (M.FLUX_SORTED_SEGMENT, M.ORDER_PARTITION_RCM, 0, 1)
 
 
 def test_no_cpu_fallback_without_a_device():

@@ -73,7 +73,9 @@ typedef struct mgcfd_options {
     int timing;     /* record CUDA-event times per kernel per level (forces use_graph=0) */
     int no_pipeline; /* 1: fused stages use the simple one-CTA-per-tile kernel instead of the persistent kernel whose transfers
                         (TMA bulk copies of the edge stream, cp.async gathers of node records) run one tile ahead (default 0) */
-    int reserved[9];
+    int no_pdl;      /* 1: stage kernels are launched without programmatic dependent launch (default 0: the prologue of a stage
+                        kernel -- barrier set-up, header and edge-stream prefetch -- overlaps the tail of its predecessor) */
+    int reserved[8];
 } mgcfd_options;
 
 void mgcfd_default_options(mgcfd_options* opt);

@@ -40,7 +40,7 @@ class MgcfdError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("flux_mode", C.c_int), ("ordering", C.c_int), ("tile_nodes", C.c_int),
-                ("use_graph", C.c_int), ("timing", C.c_int), ("no_pipeline", C.c_int), ("reserved", C.c_int * 9)]
+                ("use_graph", C.c_int), ("timing", C.c_int), ("no_pipeline", C.c_int), ("no_pdl", C.c_int), ("reserved", C.c_int * 8)]
 
 
 _lib = None
@@ -219,13 +219,14 @@ class Solver:
 
     def __init__(self, levels: int, mesh_variant: int, device: int = 0, flux_mode: int = FLUX_SORTED_SEGMENT,
                  ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0, use_graph: bool = True, timing: bool = False,
-                 pipeline: bool = True):
+                 pipeline: bool = True, pdl: bool = True):
         L = lib()
         opt = Options()
         L.mgcfd_default_options(C.byref(opt))
         opt.device, opt.flux_mode, opt.ordering, opt.tile_nodes = device, flux_mode, ordering, tile_nodes
         opt.use_graph, opt.timing = int(use_graph), int(timing)
         opt.no_pipeline = int(not pipeline)
+        opt.no_pdl = int(not pdl)
         self._h = C.c_void_p()
         self.levels, self.mesh_variant = levels, mesh_variant
         _check(L.mgcfd_create(levels, mesh_variant, C.byref(opt), C.byref(self._h)))

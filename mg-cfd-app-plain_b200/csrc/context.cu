@@ -275,7 +275,20 @@ int launch_stage_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
 }
 template <int TN, bool SCATTER>
 int launch_pipe_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
-    k_stage_pipe<TN, SCATTER><<<(unsigned)v.pipe_grid, TN, v.pipe_smem, c->stream>>>(a);
+    if (c->opt.no_pdl) {
+        k_stage_pipe<TN, SCATTER><<<(unsigned)v.pipe_grid, TN, v.pipe_smem, c->stream>>>(a);
+        return post_launch(c);
+    }
+    // programmatic dependent launch: this kernel may start (barrier set-up, header + edge-stream prefetch: static data) while
+    // its predecessor in the stream drains; it synchronises with griddepcontrol.wait before reading node state
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)v.pipe_grid); cfg.blockDim = dim3(TN); cfg.dynamicSmemBytes = v.pipe_smem; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, k_stage_pipe<TN, SCATTER>, a));
     return post_launch(c);
 }
 // persistent grid of the pipelined kernel: as many CTAs as fit on the device at once (occupancy API), never more than tiles

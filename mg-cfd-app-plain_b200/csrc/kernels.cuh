@@ -465,12 +465,15 @@ k_stage_pipe(const StageArgs a) {
         }
     };
 
-    // prologue: headers of T_0 and T_1, then the records of T_0 and the first edge chunks
+    // prologue: headers of T_0 and T_1 and the first edge chunks are static data: with programmatic dependent launch they are
+    // fetched while the previous kernel of the stream is still draining; node state is touched only after griddepcontrol.wait
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     copy_hdr(0); copy_hdr(1);
     cp_async_wait_all();
     __syncthreads();
-    copy_recs(0);
     if (t == 0) produce(1);
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    copy_recs(0);
 
     for (int it = 0; it < my_count; it++) {
         const long tile = tile_of(it);

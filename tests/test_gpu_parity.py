@@ -286,3 +286,15 @@ def test_large_mesh_properties(M):
     assert np.all(np.isfinite(ra)) and np.all(ra > 0) and ra[-1] <= 1.01 * ra[0] and ra[0] < 1e-5
     ffv, _ = M.far_field_conditions()
     assert np.max(np.abs(outs[0][1] - ffv) / np.abs(ffv[0])) < 1e-3
+
+
+def test_programmatic_dependent_launch_changes_nothing(M):
+    """stage kernels launched with / without programmatic stream serialisation (and with / without the CUDA graph) are bit-identical"""
+    outs = []
+    for pdl, graph in ((True, True), (False, True), (True, False)):
+        s = M.Solver.from_mesh(make(M, "hex_nonnested"), pdl=pdl, use_graph=graph)
+        ra, _ = s.run_cycles(9)
+        outs.append((ra, s.get_field(0, M.FIELD_VARIABLES).copy()))
+        s.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])

@@ -274,7 +274,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    nl = mesh.levels
+    nl = len(ldims)
     info0 = s.level_info(0)
     nel, nI, nB, nW = info0["nel"], info0["nI"], info0["nB"], info0["nW"]      # this rank's level 0 (the whole level when N = 1)
     flux_ms0, flux_it0 = float(t_ms[1, 0]), int(t_it[1, 0])

@@ -140,6 +140,11 @@ namespace {
 
 inline long blocks_for(long n, int bs) { return (n + bs - 1) / bs; }
 
+// Tile size when the caller leaves it to the library (measured on B200, profiles/): 256-node tiles on levels below a million
+// nodes (smaller halo share per tile; faster on every level of the M6-shaped mesh, 2364 vs 2216 cycles/s), 128-node tiles on
+// multi-million-node levels (more CTAs in flight per SM; 202 vs 197 cycles/s on the 8 M-node mesh)
+inline int auto_tile_nodes(long n, int /*num_sms*/) { return n >= 1000000 ? 128 : 256; }
+
 // folds every recorded (start, stop) pair into the per-kernel per-level totals; synchronises the stream once
 void resolve_times(mgcfd_ctx* c) {
     if (c->pending.empty()) return;
@@ -638,9 +643,7 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     if (coords) H.coords.assign(coords, coords + 3 * nel); else H.coords.clear();
     if (mg_map && l < c->levels - 1) H.mg.assign(mg_map, mg_map + mgc); else H.mg.clear();
     PlanOptions po; po.ordering = c->opt.ordering; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
-    // auto tile size (measured, profiles/): 256-node tiles on levels that are latency-bound (fewer, fatter tiles, smaller halo
-    // share), 128-node tiles on multi-million-node levels (more CTAs in flight per SM)
-    po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : ((H.n_owned >= 0 ? H.n_owned : nel) < 1000000 ? 256 : 128);
+    po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : auto_tile_nodes(H.n_owned >= 0 ? H.n_owned : nel, c->num_sms);
     try { build_level_plan(H, po, v.plan); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     v.uploaded = true;
@@ -1066,7 +1069,7 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     const EdgeNb* e = (const EdgeNb*)edges;
     H.edges.assign(e, e + nI + nB + nW);
     if (coords) H.coords.assign(coords, coords + 3 * nel);
-    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : (nel < 1000000 ? 256 : 128); po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : auto_tile_nodes(nel, 148); po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
     LevelPlan P;
     try { build_level_plan(H, po, P); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }

@@ -39,6 +39,7 @@ WORKLOADS = {
            "C2: Onera-M6-shaped 4-level multigrid, hex-dual box 300763/166375/110592/79507 nodes, 888822 fine internal edges, mesh_name=m6wing"),
     "c1": (2, [[26, 25, 25]], 0, "C1: fvcorr.domn.097K-shaped single level, 97500 cell-centred tets, mesh_name=fvcorr"),
     "c3": (1, [[201] * 3, [101] * 3, [51] * 3, [26] * 3], 2, "C3: 8.1M-node Kuhn-tet box, 4 levels, 56.4M fine internal edges, mesh_name=m6wing"),
+    "c4": (1, [[161] * 3, [81] * 3, [41] * 3, [21] * 3], 2, "C4 (weak scaling unit): 4.2M-node Kuhn-tet box per GPU, 4 levels (8 GPUs: 33M nodes; 64M needs rank-local mesh generation, DESIGN.md 5)"),
     "c3s": (1, [[129] * 3, [65] * 3, [33] * 3, [17] * 3], 2, "2.1M-node Kuhn-tet box, 4 levels (reduced C3)"),
     "tiny": (0, [[21, 19, 17], [11, 10, 9], [6, 5, 5]], 2, "tiny 3-level hex box (smoke)"),
 }
@@ -150,6 +151,9 @@ def main():
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # NCCL prints "NCCL version ..." on STDOUT at NCCL_DEBUG=VERSION: keep stdout for the one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     kind, dims, variant, desc = WORKLOADS[args.workload]
@@ -193,9 +197,6 @@ def main():
     # N > 1: weak scaling -- the box grows N-fold along x (N times the nodes and edges), recursive coordinate bisection gives
     # every rank one workload-sized part, halo exchange over NCCL (include/mgcfd_dist.h)
     gdims = [[d[0] * world - (world - 1), d[1], d[2]] for d in dims] if (world > 1 and kind != 2) else [[d[0] * world, d[1], d[2]] for d in dims]
-    mesh = M.Mesh.generate(kind, gdims, mesh_variant=variant, lengths=(float(world), 1.0, 1.0))
-    ldims = [mesh.dims(l) for l in range(mesh.levels)]          # GLOBAL counts
-    units = units_per_cycle(ldims)
     kw = {}
     if args.flux_mode is not None:
         kw["flux_mode"] = args.flux_mode
@@ -204,15 +205,38 @@ def main():
     t0 = time.perf_counter()
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            idt = torch.frombuffer(bytearray(M.dist_unique_id()), dtype=torch.uint8).clone()
-        dist.broadcast(idt, 0)
-        s = M.Solver.from_mesh_distributed(mesh, rank, world, bytes(idt.numpy().tobytes()), device=local, **kw)
-        n_local0 = s.dist_level_info(0)["owned"] + s.dist_level_info(0)["ghosts"]
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)                     # NCCL prints its version banner on stdout: keep stdout for the one JSON line
+        try:
+            if rank == 0:
+                idt = torch.frombuffer(bytearray(M.dist_unique_id()), dtype=torch.uint8).clone()
+            dist.broadcast(idt, 0)
+            s = M.Solver(len(dims), variant, device=local, **kw)
+            M._check(M.lib().mgcfd_dist_init(s._h, rank, world, bytes(idt.numpy().tobytes())))
+            # every rank builds the whole (N-fold) mesh on the host and keeps its part: done in groups of 4 ranks to bound host memory
+            for g0 in range(0, world, 4):
+                if g0 <= rank < g0 + 4:
+                    mesh = M.Mesh.generate(kind, gdims, mesh_variant=variant, lengths=(float(world), 1.0, 1.0))
+                    ldims = [mesh.dims(l) for l in range(mesh.levels)]          # GLOBAL counts
+                    M._check(M.lib().mgcfd_mesh_upload_partition(mesh._h, s._h), mesh=True)
+                    mesh.close()
+                dist.barrier()
+            for l in range(len(dims)):
+                info = s.dist_level_info(l)
+                s._nel[l] = info["owned"] + info["ghosts"]
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
+        n_local0 = s._nel[0]
     else:
+        mesh = M.Mesh.generate(kind, gdims, mesh_variant=variant, lengths=(float(world), 1.0, 1.0))
+        ldims = [mesh.dims(l) for l in range(mesh.levels)]
         s = M.Solver.from_mesh(mesh, device=local, **kw)
         n_local0 = ldims[0][0]
-    mesh.close()
+        mesh.close()
+    units = units_per_cycle(ldims)
     setup_s = time.perf_counter() - t0
     stream = torch.cuda.ExternalStream(s.cuda_stream(), device=local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")      # > 126 MB of L2

@@ -3,6 +3,7 @@
 // CUDA kernels; without a device mgcfd_create fails.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -1101,7 +1102,9 @@ int mgcfd_dist_init(mgcfd_ctx* c, int rank, int nranks, const char id[128]) {
     memcpy(u.internal, id, 128);
     NK(g_nccl.CommInitRank(&c->dist.comm, nranks, u, rank));
     c->dist.active = true; c->dist.rank = rank; c->dist.nranks = nranks;
-    c->opt.use_graph = 0;        // the cycle interleaves NCCL calls with kernels; launched eagerly
+    // the cycle interleaves NCCL calls with kernels: launched eagerly unless MGCFD_DIST_GRAPH=1 asks for the captured form
+    // (NCCL supports stream capture; every rank must then capture the same sequence)
+    { const char* e = getenv("MGCFD_DIST_GRAPH"); if (!(e && e[0] == '1')) c->opt.use_graph = 0; }
     return MGCFD_OK;
 }
 // uploads one level of a partition (partition.h) and records its exchange lists

@@ -57,7 +57,7 @@ struct Level {
     size_t smem_bytes = 0;        // simple stage kernel
     size_t pipe_smem = 0;         // pipelined stage kernel
     int pipe_grid = 0, chunk_rounds = 0;
-    bool pipe = false;
+    bool pipe = false, untiled = false;   // untiled: the numbering has no locality (atomic baseline only)
     double* buf[3] = {nullptr, nullptr, nullptr};   // node records (8 doubles each), rotating roles
     int i_var = 0, i_old = 1, i_tmp = 2;
     double *res = nullptr, *flux = nullptr, *sf = nullptr, *vol = nullptr, *vol_root = nullptr;
@@ -322,6 +322,7 @@ int setup_pipe(mgcfd_ctx* c, Level& v) {
     return sc ? setup_pipe_t<512, true>(c, v) : setup_pipe_t<512, false>(c, v);
 }
 int launch_stage(mgcfd_ctx* c, Level& v, const StageArgs& a, bool fused) {
+    if (v.untiled) { g_err = "this level cannot be tiled (numbering without locality): only the atomic flux kernels run on it"; return MGCFD_ERR_ARG; }
     const bool sc = v.plan.scatter;
     if (fused && v.pipe) {
         if (v.TN == 128) return sc ? launch_pipe_t<128, true>(c, v, a) : launch_pipe_t<128, false>(c, v, a);
@@ -644,6 +645,7 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     if (coords) H.coords.assign(coords, coords + 3 * nel); else H.coords.clear();
     if (mg_map && l < c->levels - 1) H.mg.assign(mg_map, mg_map + mgc); else H.mg.clear();
     PlanOptions po; po.ordering = c->opt.ordering; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
+    po.strict = (c->opt.flux_mode != MGCFD_FLUX_ATOMIC);     // the atomic baseline runs on any numbering, tiled or not
     po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : auto_tile_nodes(H.n_owned >= 0 ? H.n_owned : nel, c->num_sms);
     try { build_level_plan(H, po, v.plan); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
@@ -677,7 +679,8 @@ int mgcfd_finalize(mgcfd_ctx* c) {
             v.chunk_rounds = std::max(1, (P.max_rounds + nchunks - 1) / nchunks);
             v.pipe_smem = fixed + (size_t)RING * v.chunk_rounds * P.TN * 26;
         }
-        if (v.smem_bytes > 227 * 1024) { g_err = "tile halo too large for shared memory; use a smaller tile_nodes or a locality-preserving ordering"; return MGCFD_ERR_ARG; }
+        v.untiled = P.oversize || v.smem_bytes > 227 * 1024;
+        if (v.untiled && c->opt.flux_mode != MGCFD_FLUX_ATOMIC) { g_err = "tile halo too large for shared memory; use a smaller tile_nodes or a locality-preserving ordering"; return MGCFD_ERR_ARG; }
         for (int b = 0; b < 3; b++) CK(cudaMalloc((void**)&v.buf[b], sizeof(double) * 8 * v.npad));
         CK(cudaMalloc((void**)&v.res, sizeof(double) * 5 * v.npad));
         CK(cudaMalloc((void**)&v.sf, sizeof(double) * v.npad));
@@ -693,7 +696,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         CKRC(dev_upload(&v.old_of_new, n2o, s)); CKRC(dev_upload(&v.new_of_old, o2n, s));
         CKRC(dev_upload(&v.hdrs, P.hdrs, s)); CKRC(dev_upload(&v.slots, P.slots, s)); CKRC(dev_upload(&v.bslots, P.bslots, s));
         v.pipe = false;
-        if (!c->opt.no_pipeline) CKRC(setup_pipe(c, v));
+        if (!c->opt.no_pipeline && !v.untiled) CKRC(setup_pipe(c, v));
         if (v.nel_global == 0) v.nel_global = v.nel;
         v.n_owned = P.n_owned;
         if (c->dist.active) {

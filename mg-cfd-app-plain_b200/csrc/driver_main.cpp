@@ -297,8 +297,9 @@ int main(int argc, char** argv) {
                     long it = iters[kid * levels + l];
                     // time_step is fused into the flux stage kernel: same number of node updates as the reference's loop
                     if (kid == 4 && it == 0) { long dl[5]; mgcfd_mesh_dims(mesh, l, dl); it = (iters[1 * levels + l] / (dl[1] > 0 ? dl[1] : 1)) * dl[0]; }
-                    // the legacy step factor (fvcorr) is evaluated inside the stage kernel as well: one pass over the nodes per smoothing visit
-                    if (kid == 0 && it == 0) { long dl[5]; mgcfd_mesh_dims(mesh, l, dl); it = (iters[1 * levels + l] / (dl[1] > 0 ? dl[1] : 1) / MGCFD_RK) * dl[0]; }
+                    // the step factor is evaluated inside the stage kernels and its global minimum inside the transfer kernels: the
+                    // reference's loop count is one pass over the nodes per smoothing visit
+                    if (kid == 0) { long dl[5]; mgcfd_mesh_dims(mesh, l, dl); it = (iters[1 * levels + l] / (dl[1] > 0 ? dl[1] : 1) / MGCFD_RK) * dl[0]; }
                     line << it << ",";
                 }
             }

@@ -64,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -142,8 +142,8 @@ def reference_cpu_run(workload, steps, warmup, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--flux-mode", type=int, default=None)
@@ -256,10 +256,10 @@ def main():
         barrier()
         return sum(a.elapsed_time(b) for a, b in ev), s.launch_count() - l0, ra
 
-    s.run_cycles(W)
     sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.start()           # clocks are sampled (20 ms) from the warm-up to the end of the second timed pass
+    s.run_cycles(W)
     ms_total, launches, rms = timed_pass()
     # second pass, same K cycles, every kernel bracketed by its own CUDA events (graphs bypassed): per-kernel durations
     s.set_timing(True)
@@ -276,7 +276,7 @@ def main():
     host_in = torch.empty(5 * n0, dtype=torch.float64).pin_memory()
     host_out = torch.empty(5 * n0, dtype=torch.float64).pin_memory()
     host_in.numpy()[:] = s.get_field(0, M.FIELD_VARIABLES).reshape(-1)
-    e2e_steps = max(3, min(K, 20))
+    e2e_steps = max(3, min(K, 50))
     for _ in range(2):
         s.set_field(0, M.FIELD_VARIABLES, host_in.numpy()); s.run_cycles(1); s.get_field(0, M.FIELD_VARIABLES, out=host_out.numpy())
     barrier()

@@ -507,7 +507,13 @@ k_stage_pipe(const StageArgs a) {
             const int e = consumed % RING;
             mbar_wait(&bar_ring[e], (consumed / RING) & 1);
             edge_rounds<TN, SCATTER>(ring + e * (size_t)ring_bytes, min(R, rounds - r0), buf, acc, t, me, me_ep, a.k2, f);
-            __syncthreads();                                // every thread is done with ring entry e
+            // hand the ring entry back.  Only the producer has to know that EVERY warp is done with it: warp 0 waits on a named
+            // barrier, the other warps just arrive and run on (two barrier ids alternate so that a fast warp's next arrival
+            // cannot be counted into a generation a slow warp has not reached; it cannot get further ahead than that because
+            // the entry after next is only refilled once this hand-over has completed)
+            if (SCATTER) __syncthreads();                   // the coloured rounds synchronise anyway
+            else if (t < 32) asm volatile("barrier.cta.sync %0, %1;" ::"r"(1 + (consumed & 1)), "n"(TN) : "memory");
+            else asm volatile("barrier.cta.arrive %0, %1;" ::"r"(1 + (consumed & 1)), "n"(TN) : "memory");
             consumed++;
             if (t == 0) produce(it + 1);
         }

@@ -510,6 +510,7 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
     if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
     if (l < 0 || l >= c->levels) { g_err = "level out of range"; return MGCFD_ERR_ARG; }
     if (need_final && !c->finalized) { g_err = "mgcfd_finalize has not been called"; return MGCFD_ERR_ARG; }
+    if (need_final) CK(cudaSetDevice(c->opt.device));     // every compute entry point runs on the context's device
     return MGCFD_OK;
 }
 

@@ -225,6 +225,23 @@ def main():
             for l in range(len(dims)):
                 info = s.dist_level_info(l)
                 s._nel[l] = info["owned"] + info["ghosts"]
+            if os.environ.get("MGCFD_NO_P2P", "0") != "1":      # direct peer-to-peer data path (CUDA IPC windows) instead of NCCL
+                mine = s.p2p_prepare()
+                allp = [None] * world
+                dist.all_gather_object(allp, mine)
+                ok = 1
+                try:
+                    s.p2p_attach([a[0] for a in allp], [a[1] for a in allp])
+                except M.MgcfdError as e:          # no peer access between these GPUs: stay on NCCL (every rank must agree)
+                    print(f"rank {rank}: peer-to-peer attach failed ({e}); using NCCL", file=sys.stderr)
+                    ok = 0
+                flag = torch.tensor([ok])
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag) == 0:
+                    raise SystemExit("bench.py: the ranks disagree on the peer-to-peer data path; rerun with MGCFD_NO_P2P=1")
+                data_plane = "direct peer-to-peer stores over NVLink (CUDA IPC windows, one kernel per exchange / all-reduce, cycle replayed as a CUDA graph)"
+            else:
+                data_plane = "NCCL send/recv + all-reduce" 
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
@@ -323,7 +340,7 @@ def main():
         "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "step": "one V-cycle (euler3d_cpu_double.cpp:371-694), all levels",
-                   "edge_updates_per_step": units, "parallelism": "single GPU" if world == 1 else f"{world} ranks, mesh split by recursive coordinate bisection (box {world}x longer in x), NCCL halo exchange of node records per RK stage / transfer + all-reduce(min dt, RMS)",
+                   "edge_updates_per_step": units, "parallelism": "single GPU" if world == 1 else f"{world} ranks, mesh split by recursive coordinate bisection (box {world}x longer in x), halo exchange of node records per RK stage / transfer + all-reduce(min dt, RMS): " + data_plane,
                    "l2": "256 MiB buffer written before every timed cycle (L2 flush)", "flux_mode": {0: "tiled coloured scatter", 1: "tiled sorted segment", 2: "atomic"}[int(kw.get("flux_mode", 1))], "pipelined": bool(info0["pipe_grid"]),
                    "tile_nodes": int(info0["tile_nodes"]), "setup_s": round(setup_s, 2)},
         "mg_cycles_per_sec": K / (ms_total * 1e-3),

@@ -24,6 +24,15 @@ int mgcfd_dist_level_info(mgcfd_ctx* ctx, int level, long info[8]);
 /* global node id of every local node (owned + ghost) */
 int mgcfd_dist_global_ids(mgcfd_ctx* ctx, int level, long* gid);
 
+/* Direct peer-to-peer data path (optional, after mgcfd_mesh_upload_partition): every halo exchange and scalar all-reduce becomes
+ * ONE kernel per rank that stores straight into the peers' memory over NVLink (CUDA IPC windows) and hand-shakes through
+ * system-scope flags, instead of a packing kernel + NCCL calls.  prepare: allocates this rank's window, returns its 64-byte
+ * cudaIpcMemHandle and a table of offsets (mgcfd_dist_p2p_table_len longs); the launcher all-gathers handles and tables in
+ * rank order; attach: maps the peers' windows and switches the data path.  One process per GPU, all GPUs peer-accessible. */
+long mgcfd_dist_p2p_table_len(mgcfd_ctx* ctx);
+int mgcfd_dist_p2p_prepare(mgcfd_ctx* ctx, char handle[64], long* table, long table_cap);
+int mgcfd_dist_p2p_attach(mgcfd_ctx* ctx, const char* handles, const long* tables, long table_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,10 @@ def lib() -> C.CDLL:
     L.mgcfd_dist_init.argtypes = [vp, i, i, C.c_char_p]
     L.mgcfd_dist_level_info.argtypes = [vp, i, C.POINTER(l)]
     L.mgcfd_dist_global_ids.argtypes = [vp, i, vp]
+    L.mgcfd_dist_p2p_table_len.argtypes = [vp]
+    L.mgcfd_dist_p2p_table_len.restype = l
+    L.mgcfd_dist_p2p_prepare.argtypes = [vp, C.c_char_p, vp, l]
+    L.mgcfd_dist_p2p_attach.argtypes = [vp, C.c_char_p, vp, l]
     L.mgcfd_mesh_free.restype = None
     _lib = L
     return L
@@ -251,6 +255,19 @@ class Solver:
             info = s.dist_level_info(l)
             s._nel[l] = info["owned"] + info["ghosts"]
         return s
+
+    def p2p_prepare(self):
+        """(64-byte CUDA IPC handle of this rank's window, offset table) for the direct peer-to-peer data path (mgcfd_dist.h)."""
+        n = lib().mgcfd_dist_p2p_table_len(self._h)
+        handle, table = C.create_string_buffer(64), np.zeros(n, dtype=np.int64)
+        _check(lib().mgcfd_dist_p2p_prepare(self._h, handle, _ptr(table), n))
+        return handle.raw, table
+
+    def p2p_attach(self, handles, tables):
+        """handles / tables: what every rank's p2p_prepare returned, in rank order (all-gathered by the caller)."""
+        hb = b"".join(handles)
+        tb = np.ascontiguousarray(np.stack(tables), dtype=np.int64)
+        _check(lib().mgcfd_dist_p2p_attach(self._h, hb, _ptr(tb), tb.shape[1]))
 
     def dist_level_info(self, level):
         out = (C.c_long * 8)()

@@ -77,6 +77,7 @@ struct Level {
     std::vector<long> send_off, recv_off, gid, send_list;
     long nsend = 0, nghost = 0, n_owned = 0;
     int* d_send_idx = nullptr; double *sendbuf = nullptr, *recvtmp = nullptr;
+    P2PPeer* d_peers = nullptr; int npeers = 0;    // p2p: peers of this level
     double* V(int i) const { return buf[i]; }
 };
 
@@ -100,7 +101,19 @@ struct Dist {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     long exchanges = 0;
+    // direct peer-to-peer exchange (CUDA IPC windows; mgcfd_dist_p2p_prepare / _attach): replaces NCCL on the data path
+    bool p2p = false, want_graph = false;
+    unsigned char* win = nullptr;              // my window: flags[64] | red[2][64][8] | staging per level (2 parities)
+    size_t win_bytes = 0;
+    std::vector<long> stage_off;               // per level: offset (in doubles, from the window's staging base) of parity 0; parity 1 follows
+    std::vector<void*> peer_win;               // [nranks] mapped windows (mine at [rank])
+    unsigned long long* d_op = nullptr;        // device: operation number (identical on every rank), bumped by each operation's kernel
+    unsigned int* d_ctr = nullptr;             // device: [0] reductions so far, [1 + level] exchanges of that level so far (staging parities)
+    double** d_red_of_rank = nullptr;          // device: [nranks] window reduction bases
+    unsigned long long** d_flag_of_rank = nullptr;   // device: [nranks] &window.flags[me]
+    unsigned int* d_ticket = nullptr;
 };
+constexpr size_t P2P_FLAGS_BYTES = 64 * 8, P2P_RED_BYTES = 2 * 64 * 8 * 8, P2P_HDR_BYTES = P2P_FLAGS_BYTES + P2P_RED_BYTES;
 
 struct mgcfd_ctx {
     mgcfd_options opt;
@@ -225,22 +238,44 @@ int nccl_load() {
     } while (0)
 
 // global minimum of the per-rank min-dt bit patterns (positive doubles order like their bits)
+int p2p_allreduce(mgcfd_ctx* c, double* vals, int n, int is_min) {
+    Dist& d = c->dist;
+    k_p2p_allreduce<<<1, 64, 0, c->stream>>>(vals, n, is_min, d.nranks, d.rank, d.d_red_of_rank, d.d_flag_of_rank, (const unsigned long long*)d.win,
+                                              (const double*)(d.win + P2P_FLAGS_BYTES), d.d_op, d.d_ctr);
+    return post_launch(c);
+}
 int dist_allreduce_min(mgcfd_ctx* c) {
     if (!c->dist.active) return MGCFD_OK;
+    if (c->dist.p2p) return p2p_allreduce(c, (double*)c->d_minbits, 1, 1);
     NK(g_nccl.AllReduce(c->d_minbits, c->d_minbits, 1, ncclUint64, ncclMin, c->dist.comm, c->stream));
     return MGCFD_OK;
 }
 int dist_allreduce_sum5(mgcfd_ctx* c) {
     if (!c->dist.active) return MGCFD_OK;
+    if (c->dist.p2p) return p2p_allreduce(c, c->d_rms_sums, 5, 0);
     NK(g_nccl.AllReduce(c->d_rms_sums, c->d_rms_sums, 5, ncclDouble, ncclSum, c->dist.comm, c->stream));
     return MGCFD_OK;
 }
 // ghost records of level l in buffer `recs` <- their owners' records: pack the rows every peer needs, one grouped
 // ncclSend/ncclRecv per peer, received straight into the ghost rows (contiguous per owner)
+// one kernel per exchange on every rank: put into the peers' staging buffers, signal, wait for the peers, unpack (kernels.cuh)
+template <int WIDTH, bool SOA>
+int p2p_exchange(mgcfd_ctx* c, int l, const double* src, double* dst) {
+    Dist& d = c->dist;
+    Level& v = c->L[l];
+    const double* stage = (const double*)(d.win + P2P_HDR_BYTES) + d.stage_off[l];
+    const long work = std::max(v.nsend, v.nghost) * WIDTH;
+    const unsigned grid = (unsigned)std::max<long>(1, std::min<long>(blocks_for(work, 256), 2L * c->num_sms));   // resident at once
+    k_p2p_exchange<WIDTH, SOA><<<grid, 256, 0, c->stream>>>(src, v.npad, v.d_send_idx, v.d_peers, v.npeers, d.d_op, d.d_ctr + 1 + l, d.d_ticket,
+                                                            (const unsigned long long*)d.win, stage, 8 * std::max<long>(v.nghost, 1), dst, v.ncomp);
+    d.exchanges++;
+    return post_launch(c);
+}
 int dist_exchange_records(mgcfd_ctx* c, int l, double* recs) {
     if (!c->dist.active) return MGCFD_OK;
     Level& v = c->L[l];
     if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
+    if (c->dist.p2p) return p2p_exchange<8, false>(c, l, recs, recs);
     if (v.nsend) { k_pack_records<<<(unsigned)blocks_for(4 * v.nsend, 256), 256, 0, c->stream>>>(recs, v.d_send_idx, v.nsend, v.sendbuf); CKRC(post_launch(c)); }
     NK(g_nccl.GroupStart());
     for (int p = 0; p < c->dist.nranks; p++) {
@@ -256,6 +291,7 @@ int dist_exchange_residuals(mgcfd_ctx* c, int l) {
     if (!c->dist.active) return MGCFD_OK;
     Level& v = c->L[l];
     if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
+    if (c->dist.p2p) return p2p_exchange<5, true>(c, l, v.res, v.res);
     if (v.nsend) { k_pack_soa5<<<(unsigned)blocks_for(v.nsend, 256), 256, 0, c->stream>>>(v.res, v.npad, v.d_send_idx, v.nsend, v.sendbuf); CKRC(post_launch(c)); }
     NK(g_nccl.GroupStart());
     for (int p = 0; p < c->dist.nranks; p++) {
@@ -517,7 +553,7 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
 void free_level(Level& v) {
     void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
-                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp};
+                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -609,6 +645,8 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     for (auto& v : c->L) free_level(v);
     cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_ticket); cudaFree(c->d_rms); cudaFree(c->d_rms_counter); cudaFree(c->d_rms_sums);
     if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
+    for (int p = 0; p < (int)c->dist.peer_win.size(); p++) if (p != c->dist.rank && c->dist.peer_win[p]) cudaIpcCloseMemHandle(c->dist.peer_win[p]);
+    cudaFree(c->dist.win); cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -907,7 +945,8 @@ int mgcfd_collect(mgcfd_ctx* c, double* rms_all, double* rms_var) {
     std::vector<double> h(6 * (size_t)std::max(n, 1));
     unsigned long long key = 0;
     if (n) CK(cudaMemcpyAsync(h.data(), c->d_rms, sizeof(double) * 6 * n, cudaMemcpyDeviceToHost, c->stream));
-    if (c->dist.active) NK(g_nccl.AllReduce(c->d_badkey, c->d_badkey, 1, ncclUint64, ncclMin, c->dist.comm, c->stream));   // every rank learns of an invalid state anywhere
+    if (c->dist.active && c->dist.p2p) CKRC(p2p_allreduce(c, (double*)c->d_badkey, 1, 1));
+    else if (c->dist.active) NK(g_nccl.AllReduce(c->d_badkey, c->d_badkey, 1, ncclUint64, ncclMin, c->dist.comm, c->stream));   // every rank learns of an invalid state anywhere
     CK(cudaMemcpyAsync(&key, c->d_badkey, 8, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemsetAsync(c->d_rms_counter, 0, sizeof(int), c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1108,6 +1147,7 @@ int mgcfd_dist_init(mgcfd_ctx* c, int rank, int nranks, const char id[128]) {
     c->dist.active = true; c->dist.rank = rank; c->dist.nranks = nranks;
     // the cycle interleaves NCCL calls with kernels: launched eagerly unless MGCFD_DIST_GRAPH=1 asks for the captured form
     // (NCCL supports stream capture; every rank must then capture the same sequence)
+    c->dist.want_graph = c->opt.use_graph != 0;
     { const char* e = getenv("MGCFD_DIST_GRAPH"); if (!(e && e[0] == '1')) c->opt.use_graph = 0; }
     return MGCFD_OK;
 }
@@ -1155,6 +1195,89 @@ int mgcfd_upload_partition(mgcfd_ctx* c, int levels, int mesh_variant, const voi
     }
     return mgcfd_finalize(c);
 }
+// ---- direct peer-to-peer data path (CUDA IPC) -------------------------------------------------------------------------------
+// table layout (longs): [0] = levels, then per level: stage_off (doubles), nghost, recv_off[0..nranks]
+long mgcfd_dist_p2p_table_len(mgcfd_ctx* c) { return c ? 1 + (long)c->levels * (2 + c->dist.nranks + 1) : -1; }
+int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long table_cap) {
+    if (!c || !handle || !table) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    if (!c->dist.active || !c->finalized) { g_err = "mgcfd_dist_p2p_prepare needs a finalized distributed context"; return MGCFD_ERR_ARG; }
+    Dist& d = c->dist;
+    const long need = 1 + (long)c->levels * (2 + d.nranks + 1);
+    if (table_cap < need) { g_err = "table too small"; return MGCFD_ERR_ARG; }
+    CK(cudaSetDevice(c->opt.device));
+    if (!d.win) {
+        d.stage_off.assign(c->levels, 0);
+        size_t doubles = 0;
+        for (int l = 0; l < c->levels; l++) { d.stage_off[l] = (long)doubles; doubles += 2 * 8 * (size_t)std::max<long>(c->L[l].nghost, 1); }
+        d.win_bytes = P2P_HDR_BYTES + doubles * sizeof(double);
+        CK(cudaMalloc((void**)&d.win, d.win_bytes));
+        CK(cudaMemset(d.win, 0, d.win_bytes));
+        CK(cudaMalloc((void**)&d.d_ticket, 4)); CK(cudaMemset(d.d_ticket, 0, 4));
+        CK(cudaMalloc((void**)&d.d_op, 8)); CK(cudaMemset(d.d_op, 0, 8));
+        CK(cudaMalloc((void**)&d.d_ctr, 4 * (c->levels + 1))); CK(cudaMemset(d.d_ctr, 0, 4 * (c->levels + 1)));
+        CK(cudaDeviceSynchronize());
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, d.win));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handle, &h, 64);
+    long k = 0;
+    table[k++] = c->levels;
+    for (int l = 0; l < c->levels; l++) {
+        table[k++] = d.stage_off[l]; table[k++] = c->L[l].nghost;
+        for (int p = 0; p <= d.nranks; p++) table[k++] = c->L[l].recv_off[p];
+    }
+    return MGCFD_OK;
+}
+// handles: nranks x 64 bytes, tables: nranks x table_len longs, both in rank order (what every rank's prepare returned)
+int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables, long table_len) {
+    if (!c || !handles || !tables) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    Dist& d = c->dist;
+    if (!d.active || !d.win) { g_err = "mgcfd_dist_p2p_prepare has not been called"; return MGCFD_ERR_ARG; }
+    CK(cudaSetDevice(c->opt.device));
+    d.peer_win.assign(d.nranks, nullptr);
+    for (int p = 0; p < d.nranks; p++) {
+        if (p == d.rank) { d.peer_win[p] = d.win; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * (size_t)p, 64);
+        CK(cudaIpcOpenMemHandle(&d.peer_win[p], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    std::vector<double*> red(d.nranks);
+    std::vector<unsigned long long*> flg(d.nranks);
+    for (int p = 0; p < d.nranks; p++) {
+        red[p] = (double*)((unsigned char*)d.peer_win[p] + P2P_FLAGS_BYTES);
+        flg[p] = (unsigned long long*)d.peer_win[p] + d.rank;
+    }
+    CKRC(dev_upload(&d.d_red_of_rank, red, c->stream)); CKRC(dev_upload(&d.d_flag_of_rank, flg, c->stream));
+    const long per_level = 2 + d.nranks + 1;
+    for (int l = 0; l < c->levels; l++) {
+        Level& v = c->L[l];
+        std::vector<P2PPeer> peers;
+        for (int p = 0; p < d.nranks; p++) {
+            const long ns = v.send_off[p + 1] - v.send_off[p], nr = v.recv_off[p + 1] - v.recv_off[p];
+            if (p == d.rank || (ns == 0 && nr == 0)) continue;
+            const long* tp = tables + (size_t)p * table_len + 1 + (size_t)l * per_level;     // peer p's entry for level l
+            const long p_stage_off = tp[0], p_nghost = tp[1], p_recv_me = tp[2 + d.rank], p_recv_me_n = tp[2 + d.rank + 1] - tp[2 + d.rank];
+            if (p_recv_me_n != ns) { g_err = "send / receive lists of two ranks do not match"; return MGCFD_ERR_COMM; }
+            P2PPeer e;
+            e.rank = p; e.send0 = v.send_off[p]; e.nsend = ns; e.recv0 = v.recv_off[p]; e.nrecv = nr;
+            double* pst = (double*)((unsigned char*)d.peer_win[p] + P2P_HDR_BYTES) + p_stage_off;
+            // the staging buffer of a level holds up to 8 doubles per ghost row; my rows start at the peer's recv_off[me]
+            e.dst[0] = pst + 8 * p_recv_me;
+            e.dst[1] = pst + 8 * (size_t)std::max<long>(p_nghost, 1) + 8 * p_recv_me;
+            e.flag = (unsigned long long*)d.peer_win[p] + d.rank;
+            peers.push_back(e);
+        }
+        v.npeers = (int)peers.size();
+        if (v.npeers > 64) { g_err = "too many peers"; return MGCFD_ERR_ARG; }
+        CKRC(dev_upload(&v.d_peers, peers, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    d.p2p = true;
+    c->opt.use_graph = c->dist.want_graph;     // operation numbers live on the device: the cycle, exchanges included, is graph-capturable
+    return MGCFD_OK;
+}
+
 // host-only: the partition of one level for one rank (tests, tooling); any output pointer may be NULL
 int mgcfd_partition_plan(int levels, const void* host_mesh_opaque, int nranks, int rank, int level, long info[8], long* gid,
                          long* send_counts, long* recv_counts, long* send_gids) {

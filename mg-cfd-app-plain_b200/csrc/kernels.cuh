@@ -838,6 +838,111 @@ __global__ void k_unpack_soa5(double* __restrict__ soa, long stride, long row0, 
 #pragma unroll
     for (int j = 0; j < 5; j++) soa[j * stride + row0 + k] = src[5 * k + j];
 }
+// ---- direct peer-to-peer halo exchange over NVLink (CUDA IPC windows), one kernel per exchange ----------------------------
+// Every rank owns a WINDOW other ranks can write: flags[64] (latest operation number completed by each source), reduction slots
+// and, per level, two staging buffers for incoming halo rows.  An operation number g grows by one per collective operation on
+// every rank alike.  k_p2p_exchange, on every rank at once:
+//   1. PUT   : gathers the rows each peer needs and stores them straight into that peer's staging buffer (peer pointers);
+//   2. SIGNAL: the last block to finish (ticket) fences system-wide and writes g into flags[me] of every peer;
+//   3. WAIT  : every block spins (ld.acquire.sys) until flags[src] >= g for every source rank of this level;
+//   4. UNPACK: copies its share of the staging buffer into the ghost rows.
+// The grid is capped to what is resident at once (spinning blocks must not keep unscheduled ones from running).
+struct P2PPeer {                   // one entry per peer of a level
+    int rank;
+    long send0, nsend;             // slice of the level's send list
+    long recv0, nrecv;             // slice of my ghost rows filled by this peer
+    double* dst[2];                // peer staging (parity 0/1) at the offset where my rows land
+    unsigned long long* flag;      // &peer_window.flags[my rank]
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// width = doubles per node in the message (8: records, 5: residuals).  src_is_soa: residual planes (stride) instead of record rows.
+template <int WIDTH, bool SOA>
+__global__ void k_p2p_exchange(const double* __restrict__ src, long stride, const int* __restrict__ send_idx, const P2PPeer* __restrict__ peers, int npeers,
+                               unsigned long long* op_counter, unsigned int* level_counter, unsigned int* ticket,
+                               const unsigned long long* my_flags, const double* __restrict__ my_stage0, long stage_parity_stride,
+                               double* __restrict__ dst, long ghost_row0) {
+    const long tid = blockIdx.x * (long)blockDim.x + threadIdx.x, nthreads = (long)gridDim.x * blockDim.x;
+    // operation number and staging parity live on the device (bumped by the last block of each operation), so the kernel's
+    // arguments never change and a whole V-cycle, exchanges included, can be replayed as one CUDA graph
+    const unsigned long long g = *(volatile unsigned long long*)op_counter + 1;
+    const int parity = int(*(volatile unsigned int*)level_counter & 1u);
+    const double* my_stage = my_stage0 + (size_t)parity * stage_parity_stride;
+    // 1. put
+    for (int p = 0; p < npeers; p++) {
+        const P2PPeer pe = peers[p];
+        double* out = pe.dst[parity];
+        for (long k = tid; k < pe.nsend * WIDTH; k += nthreads) {
+            const long row = k / WIDTH; const int j = int(k - row * WIDTH);
+            const long node = send_idx[pe.send0 + row];
+            out[k] = SOA ? src[j * stride + node] : src[8 * node + j];
+        }
+    }
+    // 2. signal
+    __shared__ bool last;
+    __syncthreads();                         // the block's stores are ordered before thread 0's system-scope fence (cumulativity,
+    if (threadIdx.x == 0) {                  // the pattern of a cooperative-groups grid barrier): one fence per block, not per thread
+        __threadfence_system();
+        last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x < npeers) { __threadfence_system(); st_release_sys(peers[threadIdx.x].flag, g); }
+    if (last && threadIdx.x == 0) { *op_counter = g; *level_counter += 1; }     // every block has read both (it passed the ticket)
+    // 3. wait for every source of this level
+    if (threadIdx.x < npeers && peers[threadIdx.x].nrecv >= 0) {
+        const unsigned long long* f = my_flags + peers[threadIdx.x].rank;
+        while (ld_acquire_sys(f) < g) { __nanosleep(64); }
+    }
+    __syncthreads();
+    // 4. unpack staging -> ghost rows (a source's rows start at 8 * recv0 doubles whatever the message width)
+    for (int p = 0; p < npeers; p++) {
+        const P2PPeer pe = peers[p];
+        const double* in = my_stage + 8 * pe.recv0;
+        for (long k = tid; k < pe.nrecv * WIDTH; k += nthreads) {
+            const long row = k / WIDTH; const int j = int(k - row * WIDTH);
+            const double v = __ldcg(in + k);
+            if (SOA) dst[j * stride + ghost_row0 + pe.recv0 + row] = v; else dst[8 * (ghost_row0 + pe.recv0 + row) + j] = v;
+        }
+    }
+}
+// all-reduce of n (<= 8) doubles (sum) or of one uint64 (min) over all ranks, one kernel on every rank: store my contribution into
+// slot [parity][me] of every window (mine included), signal, wait for everybody, combine in rank order (deterministic).
+__global__ void k_p2p_allreduce(double* __restrict__ vals, int n, int is_min, int nranks, int me, double* const* __restrict__ red_of_rank /*[nranks] window red bases*/,
+                                unsigned long long* const* __restrict__ flag_of_rank /*[nranks] &window.flags[me]*/, const unsigned long long* my_flags,
+                                const double* __restrict__ my_red, unsigned long long* op_counter, unsigned int* red_counter) {
+    const int t = threadIdx.x;
+    const unsigned long long g = *(volatile unsigned long long*)op_counter + 1;
+    const int parity = int(*(volatile unsigned int*)red_counter & 1u);
+    __syncthreads();
+    if (t < nranks) {
+        double* slot = red_of_rank[t] + ((size_t)parity * 64 + me) * 8;
+        for (int j = 0; j < n; j++) slot[j] = vals[j];
+        __threadfence_system();
+        st_release_sys(flag_of_rank[t], g);
+        while (ld_acquire_sys(my_flags + t) < g) { __nanosleep(64); }
+    }
+    __syncthreads();
+    if (t < n) {
+        const double* base = my_red + (size_t)parity * 64 * 8;
+        if (is_min) {
+            unsigned long long m = ~0ull;
+            for (int r = 0; r < nranks; r++) { const unsigned long long v = (unsigned long long)__double_as_longlong(__ldcg(base + r * 8 + t)); m = v < m ? v : m; }
+            vals[t] = __longlong_as_double((long long)m);
+        } else {
+            double acc = 0.0;
+            for (int r = 0; r < nranks; r++) acc += __ldcg(base + r * 8 + t);
+            vals[t] = acc;
+        }
+    }
+    if (t == 0) { *op_counter = g; *red_counter += 1; }
+}
+
 // calc_rms split around an all-reduce: local sums of squares, then the roots over the global node count
 __global__ void k_rms_sums(const double* __restrict__ partial, long nparts, double* __restrict__ sums) {
     __shared__ double ws[5][256];

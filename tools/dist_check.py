@@ -34,6 +34,11 @@ def main():
         uid = bcast_id(rank)
         mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
         s = M.Solver.from_mesh_distributed(mesh, rank, world, uid, device=local)
+        if os.environ.get("MGCFD_NO_P2P", "0") != "1":      # direct peer-to-peer data path (CUDA IPC) instead of NCCL send/recv
+            mine = s.p2p_prepare()
+            allp = [None] * world
+            dist.all_gather_object(allp, mine)
+            s.p2p_attach([a[0] for a in allp], [a[1] for a in allp])
         ra, rv = s.run_cycles(cycles)
         pieces = []
         for l in range(mesh.levels):

@@ -905,14 +905,12 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
     if (it == c->graphs.end()) {
         cudaGraph_t g = nullptr;
         const long launches_before = c->launches;
-        const unsigned long long seq_before = c->stage_seq;
         c->capturing = true;
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         int rc = cycle_fused(c);
         cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
         c->capturing = false;
         c->launches = launches_before;        // capture recorded the launches, it did not run them
-        (void)seq_before;
         if (rc != MGCFD_OK) { if (g) cudaGraphDestroy(g); return rc; }
         CK(ce);
         cudaGraphExec_t ge = nullptr;

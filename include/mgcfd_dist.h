@@ -19,10 +19,24 @@ extern "C" {
 int mgcfd_dist_get_unique_id(char id[128]);
 /* joins the communicator; after mgcfd_create, before any upload. CUDA graphs are switched off for distributed contexts. */
 int mgcfd_dist_init(mgcfd_ctx* ctx, int rank, int nranks, const char id[128]);
-/* info[0..6]: owned nodes, ghost nodes, nodes sent per exchange, nodes of the level over all ranks, rank, nranks, exchanges so far */
+/* info[0..7]: owned nodes, ghost nodes, nodes sent per exchange, nodes of the level over all ranks, rank, nranks, exchanges so far,
+ * internal edges of the level over all ranks */
 int mgcfd_dist_level_info(mgcfd_ctx* ctx, int level, long info[8]);
 /* global node id of every local node (owned + ghost) */
 int mgcfd_dist_global_ids(mgcfd_ctx* ctx, int level, long* gid);
+
+/* Rank-local generation of the synthetic meshes (mgcfd_mesh.h: MGCFD_GEN_*): generates only the part of the mesh this rank holds --
+ * its owned nodes, its ghosts, their edges and maps -- straight from the generator's node descriptions, never assembling the global
+ * edge list, applies adjust_ewt / dampen_ewt, uploads and finalizes.  Same partition, bit for bit, as mgcfd_mesh_generate +
+ * mgcfd_mesh_upload_partition (tests/test_partition.py), at a fraction of the host memory (what a 64 M-node mesh on 8 ranks needs).
+ * dims = levels x 3 as for mgcfd_mesh_generate; lexicographic node numbering. */
+int mgcfd_generate_upload_partition(mgcfd_ctx* ctx, int kind, int levels, const long* dims, const double lengths[3], int mesh_variant,
+                                    double tilt);
+/* host-only view of it (no device): the outputs of mgcfd_mesh_partition_plan; info[7] = a hash of everything the rank holds of the
+ * level (nodes, edges with their weights -- adjusted and dampened iff apply_ewt != 0 --, maps, exchange lists) */
+int mgcfd_generate_partition_plan(int kind, int levels, const long* dims, const double lengths[3], int mesh_variant, double tilt,
+                                  int apply_ewt, int nranks, int rank, int level, long info[8], long* gid, long* send_counts,
+                                  long* recv_counts, long* send_gids);
 
 /* Direct peer-to-peer data path (optional, after mgcfd_mesh_upload_partition): every halo exchange and scalar all-reduce becomes
  * ONE kernel per rank that stores straight into the peers' memory over NVLink (CUDA IPC windows) and hand-shakes through

@@ -35,8 +35,8 @@ int mgcfd_mesh_upload(mgcfd_mesh* m, mgcfd_ctx* ctx);
 /* distributed (mgcfd_dist.h): keeps only this rank's part of every level (owned nodes + ghosts), uploads it with its halo
  * exchange lists and finalizes; the context must have joined a communicator with mgcfd_dist_init */
 int mgcfd_mesh_upload_partition(mgcfd_mesh* m, mgcfd_ctx* ctx);
-/* host-only view of that partition for one rank and level (no device, no NCCL): info[0..6] = owned, ghosts, sent nodes, global
- * nodes, local internal / boundary / wall edges; gid[owned+ghosts]; send_counts / recv_counts[nranks]; send_gids[sent nodes] =
+/* host-only view of that partition for one rank and level (no device, no NCCL): info[0..7] = owned, ghosts, sent nodes, global
+ * nodes, local internal / boundary / wall edges, a hash of everything the rank holds of the level; gid[owned+ghosts]; send_counts / recv_counts[nranks]; send_gids[sent nodes] =
  * global ids in send order. Any output pointer may be NULL. */
 int mgcfd_mesh_partition_plan(mgcfd_mesh* m, int nranks, int rank, int level, long info[8], long* gid, long* send_counts,
                               long* recv_counts, long* send_gids);

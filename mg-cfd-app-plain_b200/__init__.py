@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
     L.mgcfd_dist_p2p_table_len.restype = l
     L.mgcfd_dist_p2p_prepare.argtypes = [vp, C.c_char_p, vp, l]
     L.mgcfd_dist_p2p_attach.argtypes = [vp, C.c_char_p, vp, l]
+    L.mgcfd_generate_upload_partition.argtypes = [vp, i, i, vp, dp, i, C.c_double]
+    L.mgcfd_generate_partition_plan.argtypes = [i, i, vp, dp, i, C.c_double, i, i, i, i, C.POINTER(l), vp, vp, vp, vp]
     L.mgcfd_mesh_free.restype = None
     _lib = L
     return L
@@ -256,6 +258,23 @@ class Solver:
             s._nel[l] = info["owned"] + info["ghosts"]
         return s
 
+    @classmethod
+    def generate_distributed(cls, kind: int, dims, rank: int, nranks: int, unique_id: bytes, mesh_variant: int = MESH_M6_WING,
+                             lengths=(1.0, 1.0, 1.0), tilt: float = 0.05, **kw) -> "Solver":
+        """One rank of a multi-GPU run on a synthetic mesh that no rank ever assembles as a whole: the rank generates its own part
+        (mgcfd_generate_upload_partition, include/mgcfd_dist.h) -- the same partition, bit for bit, as
+        `from_mesh_distributed(Mesh.generate(...))`."""
+        d = np.ascontiguousarray(np.asarray(dims, dtype=np.int64).reshape(-1, 3))
+        ln = np.asarray(lengths, dtype=np.float64)
+        s = cls(d.shape[0], mesh_variant, **kw)
+        _check(lib().mgcfd_dist_init(s._h, rank, nranks, unique_id))
+        _check(lib().mgcfd_generate_upload_partition(s._h, kind, d.shape[0], _ptr(d), ln.ctypes.data_as(C.POINTER(C.c_double)),
+                                                     mesh_variant, tilt))
+        for l in range(d.shape[0]):
+            info = s.dist_level_info(l)
+            s._nel[l] = info["owned"] + info["ghosts"]
+        return s
+
     def p2p_prepare(self):
         """(64-byte CUDA IPC handle of this rank's window, offset table) for the direct peer-to-peer data path (mgcfd_dist.h)."""
         n = lib().mgcfd_dist_p2p_table_len(self._h)
@@ -272,7 +291,7 @@ class Solver:
     def dist_level_info(self, level):
         out = (C.c_long * 8)()
         _check(lib().mgcfd_dist_level_info(self._h, level, out))
-        return dict(zip(("owned", "ghosts", "sent", "global_nodes", "rank", "nranks", "exchanges"), out))
+        return dict(zip(("owned", "ghosts", "sent", "global_nodes", "rank", "nranks", "exchanges", "global_internal_edges"), out))
 
     def global_ids(self, level):
         g = np.empty(self._nel[level], dtype=np.int64)
@@ -426,7 +445,27 @@ def partition_plan(mesh: Mesh, nranks: int, rank: int, level: int):
     sc, rc = np.zeros(nranks, dtype=np.int64), np.zeros(nranks, dtype=np.int64)
     sg = np.empty(max(sent, 1), dtype=np.int64)
     _check(L.mgcfd_mesh_partition_plan(mesh._h, nranks, rank, level, info, _ptr(gid), _ptr(sc), _ptr(rc), _ptr(sg)), mesh=True)
-    return dict(owned=owned, ghosts=ghosts, sent=sent, global_nodes=info[3], nI=info[4], nB=info[5], nW=info[6], gid=gid,
+    return dict(owned=owned, ghosts=ghosts, sent=sent, global_nodes=info[3], nI=info[4], nB=info[5], nW=info[6], hash=info[7], gid=gid,
+                send_counts=sc, recv_counts=rc, send_gids=sg[:sent])
+
+
+def generate_partition_plan(kind: int, dims, nranks: int, rank: int, level: int, mesh_variant: int = MESH_M6_WING,
+                            lengths=(1.0, 1.0, 1.0), tilt: float = 0.05, apply_ewt: bool = False):
+    """Host-only: `partition_plan` of the synthetic mesh `Mesh.generate(kind, dims, ...)` computed by rank-local generation, i.e.
+    without assembling the mesh (mgcfd_generate_partition_plan).  `hash` covers everything the rank holds of the level."""
+    L = lib()
+    d = np.ascontiguousarray(np.asarray(dims, dtype=np.int64).reshape(-1, 3))
+    ln = np.asarray(lengths, dtype=np.float64)
+    lp = ln.ctypes.data_as(C.POINTER(C.c_double))
+    info = (C.c_long * 8)()
+    args = (kind, d.shape[0], _ptr(d), lp, mesh_variant, tilt, int(apply_ewt), nranks, rank, level)
+    _check(L.mgcfd_generate_partition_plan(*args, info, None, None, None, None))
+    owned, ghosts, sent = info[0], info[1], info[2]
+    gid = np.empty(owned + ghosts, dtype=np.int64)
+    sc, rc = np.zeros(nranks, dtype=np.int64), np.zeros(nranks, dtype=np.int64)
+    sg = np.empty(max(sent, 1), dtype=np.int64)
+    _check(L.mgcfd_generate_partition_plan(*args, info, _ptr(gid), _ptr(sc), _ptr(rc), _ptr(sg)))
+    return dict(owned=owned, ghosts=ghosts, sent=sent, global_nodes=info[3], nI=info[4], nB=info[5], nW=info[6], hash=info[7], gid=gid,
                 send_counts=sc, recv_counts=rc, send_gids=sg[:sent])
 
 

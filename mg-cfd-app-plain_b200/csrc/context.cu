@@ -53,6 +53,7 @@ struct Level {
     long nel = 0, npad = 0, ntiles = 0, nI = 0, nB = 0, nW = 0;
     long ncomp = 0;            // rows this rank computes (the owned tiles, = ntiles * TN); rows [ncomp, npad) are ghosts
     long nel_global = 0;       // nodes of the level over all ranks (RMS normalisation)
+    long nI_global = 0;        // internal edges of the level over all ranks (work accounting of distributed runs)
     int TN = 256, smem_nodes = 0;
     size_t smem_bytes = 0;        // simple stage kernel
     size_t pipe_smem = 0;         // pipelined stage kernel
@@ -1159,6 +1160,7 @@ static int upload_local_level(mgcfd_ctx* c, int l, const LocalLevel& LL, long ne
     v.send_off = LL.send_off; v.recv_off = LL.recv_off; v.send_list = LL.send_idx; v.gid = LL.gid;
     v.host.gid = LL.gid;
     v.nel_global = nel_global;
+    v.nI_global = LL.nI_global;
     return MGCFD_OK;
 }
 int mgcfd_dist_level_info(mgcfd_ctx* c, int l, long info[8]) {
@@ -1166,7 +1168,7 @@ int mgcfd_dist_level_info(mgcfd_ctx* c, int l, long info[8]) {
     const Level& v = c->L[l];
     memset(info, 0, sizeof(long) * 8);
     info[0] = v.plan.n_owned; info[1] = v.plan.nel - v.plan.n_owned; info[2] = (long)v.send_list.size(); info[3] = v.nel_global;
-    info[4] = c->dist.rank; info[5] = c->dist.nranks; info[6] = c->dist.exchanges;
+    info[4] = c->dist.rank; info[5] = c->dist.nranks; info[6] = c->dist.exchanges; info[7] = v.nI_global ? v.nI_global : v.nI;
     return MGCFD_OK;
 }
 int mgcfd_dist_global_ids(mgcfd_ctx* c, int l, long* gid) {
@@ -1276,6 +1278,36 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
     return MGCFD_OK;
 }
 
+// FNV-1a over everything a rank holds of one level: two ways of computing a partition must agree on this bit for bit
+static unsigned long long hash_local_level(const LocalLevel& LL) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+    const HostLevel& M = LL.mesh;
+    const long hdr[5] = {M.nel, M.nI, M.nB, M.nW, LL.n_owned};
+    mix(hdr, sizeof(hdr));
+    mix(&LL.nI_global, sizeof(long));
+    mix(M.volumes.data(), M.volumes.size() * sizeof(double));
+    mix(M.coords.data(), M.coords.size() * sizeof(double));
+    mix(M.edges.data(), M.edges.size() * sizeof(EdgeNb));
+    mix(M.mg.data(), M.mg.size() * sizeof(long));
+    mix(LL.gid.data(), LL.gid.size() * sizeof(long));
+    mix(LL.edge_gid.data(), LL.edge_gid.size() * sizeof(long));
+    mix(LL.send_off.data(), LL.send_off.size() * sizeof(long));
+    mix(LL.send_idx.data(), LL.send_idx.size() * sizeof(long));
+    mix(LL.recv_off.data(), LL.recv_off.size() * sizeof(long));
+    return h;
+}
+static void fill_plan_outputs(const LocalLevel& LL, long nel_global, int nranks, long info[8], long* gid, long* send_counts, long* recv_counts, long* send_gids) {
+    memset(info, 0, sizeof(long) * 8);
+    info[0] = LL.n_owned; info[1] = (long)LL.gid.size() - LL.n_owned; info[2] = (long)LL.send_idx.size(); info[3] = nel_global;
+    info[4] = LL.mesh.nI; info[5] = LL.mesh.nB; info[6] = LL.mesh.nW; info[7] = (long)(hash_local_level(LL) >> 1);
+    if (gid) memcpy(gid, LL.gid.data(), sizeof(long) * LL.gid.size());
+    for (int p = 0; p < nranks; p++) {
+        if (send_counts) send_counts[p] = LL.send_off[p + 1] - LL.send_off[p];
+        if (recv_counts) recv_counts[p] = LL.recv_off[p + 1] - LL.recv_off[p];
+    }
+    if (send_gids) for (size_t k = 0; k < LL.send_idx.size(); k++) send_gids[k] = LL.gid[LL.send_idx[k]];
+}
 // host-only: the partition of one level for one rank (tests, tooling); any output pointer may be NULL
 int mgcfd_partition_plan(int levels, const void* host_mesh_opaque, int nranks, int rank, int level, long info[8], long* gid,
                          long* send_counts, long* recv_counts, long* send_gids) {
@@ -1285,17 +1317,45 @@ int mgcfd_partition_plan(int levels, const void* host_mesh_opaque, int nranks, i
     LocalMesh loc;
     try { partition_mesh(full, nranks, rank, loc); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
-    const LocalLevel& LL = loc.levels[level];
-    memset(info, 0, sizeof(long) * 8);
-    info[0] = LL.n_owned; info[1] = (long)LL.gid.size() - LL.n_owned; info[2] = (long)LL.send_idx.size(); info[3] = full.levels[level].nel;
-    info[4] = LL.mesh.nI; info[5] = LL.mesh.nB; info[6] = LL.mesh.nW;
-    if (gid) memcpy(gid, LL.gid.data(), sizeof(long) * LL.gid.size());
-    for (int p = 0; p < nranks; p++) {
-        if (send_counts) send_counts[p] = LL.send_off[p + 1] - LL.send_off[p];
-        if (recv_counts) recv_counts[p] = LL.recv_off[p + 1] - LL.recv_off[p];
-    }
-    if (send_gids) for (size_t k = 0; k < LL.send_idx.size(); k++) send_gids[k] = LL.gid[LL.send_idx[k]];
+    fill_plan_outputs(loc.levels[level], full.levels[level].nel, nranks, info, gid, send_counts, recv_counts, send_gids);
     return MGCFD_OK;
+}
+
+// ---- rank-local generation: the part of a synthetic mesh this rank holds, without assembling the global mesh ----------------
+static int make_spec(int kind, int levels, const long* dims, const double lengths[3], int mesh_variant, double tilt, MeshSpec& s) {
+    if (!dims || levels < 1 || levels > 8) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    s.kind = kind; s.levels = levels; s.mesh_variant = mesh_variant; s.ordering = 0; s.tilt = tilt;
+    for (int l = 0; l < levels; l++) for (int k = 0; k < 3; k++) s.dims[l][k] = dims[3 * l + k];
+    if (lengths) for (int k = 0; k < 3; k++) s.lengths[k] = lengths[k];
+    return MGCFD_OK;
+}
+int mgcfd_generate_partition_plan(int kind, int levels, const long* dims, const double lengths[3], int mesh_variant, double tilt, int apply_ewt_too,
+                                  int nranks, int rank, int level, long info[8], long* gid, long* send_counts, long* recv_counts, long* send_gids) {
+    MeshSpec spec;
+    CKRC(make_spec(kind, levels, dims, lengths, mesh_variant, tilt, spec));
+    if (!info || level < 0 || level >= levels) { g_err = "bad level"; return MGCFD_ERR_ARG; }
+    LocalMesh loc;
+    std::string err;
+    if (generate_partition(spec, nranks, rank, apply_ewt_too != 0, loc, err) != 0) { g_err = err; return MGCFD_ERR_ARG; }
+    long nglob = spec.dims[level][0] * spec.dims[level][1] * spec.dims[level][2] * (kind == 2 ? 6 : 1);
+    fill_plan_outputs(loc.levels[level], nglob, nranks, info, gid, send_counts, recv_counts, send_gids);
+    return MGCFD_OK;
+}
+int mgcfd_generate_upload_partition(mgcfd_ctx* c, int kind, int levels, const long* dims, const double lengths[3], int mesh_variant, double tilt) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    if (!c->dist.active) { g_err = "mgcfd_dist_init has not been called"; return MGCFD_ERR_ARG; }
+    if (levels != c->levels || mesh_variant != c->variant) { g_err = "mesh does not match the context"; return MGCFD_ERR_ARG; }
+    MeshSpec spec;
+    CKRC(make_spec(kind, levels, dims, lengths, mesh_variant, tilt, spec));
+    LocalMesh loc;
+    std::string err;
+    if (generate_partition(spec, c->dist.nranks, c->dist.rank, true, loc, err) != 0) { g_err = err; return MGCFD_ERR_ARG; }
+    for (int l = 0; l < c->levels; l++) {
+        c->L[l].host.n_owned = loc.levels[l].n_owned;
+        const long nglob = spec.dims[l][0] * spec.dims[l][1] * spec.dims[l][2] * (kind == 2 ? 6 : 1);
+        CKRC(upload_local_level(c, l, loc.levels[l], nglob));
+    }
+    return mgcfd_finalize(c);
 }
 
 void mgcfd_free(void* p) { free(p); }

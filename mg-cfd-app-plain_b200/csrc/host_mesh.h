@@ -75,5 +75,9 @@ struct MeshSpec {
     double tilt = 0.05;      // x-tilt of the z=0 wall normals on the patch 0.3 < x/Lx < 0.6
 };
 int generate_mesh(const MeshSpec& spec, HostMesh& out, std::string& err);
+// rank-local generation for multi-GPU runs (partition.h: partition_sources): the part of the mesh `spec` describes that rank `rank`
+// of `nranks` holds, without ever assembling the global edge list; apply_ewt != 0 applies adjust_ewt + dampen_ewt to the local edges
+struct LocalMesh;
+int generate_partition(const MeshSpec& spec, int nranks, int rank, bool apply_ewt_too, LocalMesh& out, std::string& err);
 
 }  // namespace mgcfd

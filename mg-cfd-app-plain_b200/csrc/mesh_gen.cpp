@@ -9,6 +9,7 @@
 #include <numeric>
 
 #include "host_mesh.h"
+#include "partition.h"
 
 namespace mgcfd {
 
@@ -324,6 +325,37 @@ int generate_mesh(const MeshSpec& spec, HostMesh& out, std::string& err) {
     long total = 0;
     for (auto& L : out.levels) total += L.nel;
     out.size = int(std::min<long>(total, 2000000000L));
+    return 0;
+}
+
+int generate_partition(const MeshSpec& spec, int nranks, int rank, bool apply_ewt_too, LocalMesh& out, std::string& err) {
+    if (spec.levels < 1 || spec.levels > 8) { err = "levels must be in 1..8"; return 2; }
+    if (spec.kind == 2 && spec.levels != 1) { err = "cell-centred tet meshes are single-level"; return 2; }
+    if (spec.ordering != 0) { err = "rank-local generation supports the lexicographic node numbering only"; return 2; }
+    std::vector<std::unique_ptr<NodeSource>> src(spec.levels);
+    std::vector<LevelSource> lv(spec.levels);
+    for (int l = 0; l < spec.levels; l++) {
+        const long* d = spec.dims[l];
+        if (spec.kind != 2 && (d[0] < 2 || d[1] < 2 || d[2] < 2)) { err = "box dims must be >= 2"; return 2; }
+        if (spec.kind == 2 && (d[0] < 1 || d[1] < 1 || d[2] < 1)) { err = "cube dims must be >= 1"; return 2; }
+        if (spec.kind == 2) src[l].reset(new TetCellSource(d, spec.lengths, spec.mesh_variant, spec.tilt));
+        else src[l].reset(new BoxSource(d, spec.lengths, spec.kind, spec.mesh_variant, spec.tilt));
+        lv[l].src = src[l].get();
+        lv[l].name = "synth.L" + std::to_string(l) + ".dat";
+    }
+    for (int l = 0; l + 1 < spec.levels; l++) {        // the same nearest-coarse-node map as generate_mesh
+        const long* df = spec.dims[l]; const long* dc = spec.dims[l + 1];
+        const long nf = src[l]->nel();
+        lv[l].mg.resize(nf);
+        for (long i = 0; i < nf; i++) {
+            const long q[3] = {i % df[0], (i / df[0]) % df[1], i / (df[0] * df[1])};
+            lv[l].mg[i] = int(nearest_1d(q[0], df[0], dc[0]) + dc[0] * (nearest_1d(q[1], df[1], dc[1]) + dc[1] * nearest_1d(q[2], df[2], dc[2])));
+        }
+    }
+    try { partition_sources(lv, spec.mesh_variant, nranks, rank, out); }
+    catch (const std::exception& ex) { err = ex.what(); return 2; }
+    if (apply_ewt_too)
+        for (auto& LL : out.levels) apply_ewt(spec.mesh_variant, LL.mesh.coords.data(), LL.mesh.nI + LL.mesh.nB + LL.mesh.nW, LL.mesh.edges.data());
     return 0;
 }
 

@@ -10,6 +10,8 @@ namespace mgcfd {
 
 namespace {
 
+const int MESH_FVCORR = 0;
+
 struct Csr {
     std::vector<long> off;
     std::vector<int> idx;
@@ -168,6 +170,7 @@ void partition_mesh(const HostMesh& full, int nranks, int rank, LocalMesh& out) 
             LL.edge_gid.push_back(e);
         }
         M.nI = long(M.edges.size());
+        LL.nI_global = G.nI;
         for (int cls = 0; cls < 2; cls++) {
             const long e0 = cls == 0 ? G.nI : G.nI + G.nB, e1 = cls == 0 ? G.nI + G.nB : G.nI + G.nB + G.nW;
             long cnt = 0;
@@ -182,6 +185,136 @@ void partition_mesh(const HostMesh& full, int nranks, int rank, LocalMesh& out) 
         if (l + 1 < nl) {
             M.mg.resize(nloc);
             for (long k = 0; k < nloc; k++) M.mg[k] = g2l[l + 1][G.mg[LL.gid[k]]];
+        }
+    }
+}
+
+void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant, int nranks, int rank, LocalMesh& out) {
+    if (nranks < 1 || nranks > 64 || rank < 0 || rank >= nranks) throw std::runtime_error("mgcfd: bad rank / nranks (1..64 ranks)");
+    const int nl = int(levels.size());
+    out = LocalMesh();
+    out.mesh_variant = mesh_variant; out.rank = rank; out.nranks = nranks;
+    out.levels.resize(nl);
+    std::vector<long> n(nl);
+    std::vector<std::vector<int>> owner(nl);
+    std::vector<Csr> kids(nl);
+    Entry ent[32];
+    for (int l = 0; l < nl; l++) {
+        const NodeSource& S = *levels[l].src;
+        n[l] = S.nel();
+        HostLevel tmp;                       // coordinates only, for the bisection
+        tmp.nel = n[l];
+        tmp.coords.resize(3 * n[l]);
+        for (long i = 0; i < n[l]; i++) S.coords(i, &tmp.coords[3 * i]);
+        rcb_owners(tmp, nranks, owner[l]);
+        if (l > 0) {
+            const std::vector<int>& mg = levels[l - 1].mg;
+            Csr& c = kids[l];
+            c.off.assign(n[l] + 1, 0);
+            for (long i = 0; i < n[l - 1]; i++) c.off[mg[i] + 1]++;
+            for (long k = 0; k < n[l]; k++) c.off[k + 1] += c.off[k];
+            c.idx.resize(n[l - 1]);
+            std::vector<long> pos(c.off.begin(), c.off.end() - 1);
+            for (long i = 0; i < n[l - 1]; i++) c.idx[pos[mg[i]]++] = int(i);
+        }
+    }
+    std::vector<std::vector<char>> flux_local(nl);
+    for (int l = 0; l < nl; l++) {
+        const NodeSource& S = *levels[l].src;
+        flux_local[l].assign(n[l], 0);
+        for (long i = 0; i < n[l]; i++) {
+            if (owner[l][i] != rank) continue;
+            flux_local[l][i] = 1;
+            const int deg = S.listing(i, ent);
+            for (int j = 0; j < deg; j++) if (ent[j].nbr >= 0) flux_local[l][ent[j].nbr] = 1;
+        }
+    }
+    std::vector<std::vector<int>> g2l(nl);
+    for (int l = 0; l < nl; l++) {
+        const NodeSource& S = *levels[l].src;
+        std::vector<char> need(n[l], 0);
+        for (long i = 0; i < n[l]; i++) if (flux_local[l][i]) need[i] = 1;
+        if (l + 1 < nl) for (long i = 0; i < n[l]; i++) if (owner[l + 1][levels[l].mg[i]] == rank) need[i] = 1;
+        if (l >= 1) for (long j = 0; j < n[l - 1]; j++) if (flux_local[l - 1][j]) need[levels[l - 1].mg[j]] = 1;
+        LocalLevel& LL = out.levels[l];
+        std::vector<long> ghosts;
+        for (long i = 0; i < n[l]; i++) {
+            if (owner[l][i] == rank) LL.gid.push_back(i);
+            else if (need[i]) ghosts.push_back(i);
+        }
+        LL.n_owned = long(LL.gid.size());
+        std::stable_sort(ghosts.begin(), ghosts.end(), [&](long x, long y) { return owner[l][x] < owner[l][y]; });
+        LL.recv_off.assign(nranks + 1, 0);
+        for (long g : ghosts) LL.recv_off[owner[l][g] + 1]++;
+        for (int p = 0; p < nranks; p++) LL.recv_off[p + 1] += LL.recv_off[p];
+        LL.gid.insert(LL.gid.end(), ghosts.begin(), ghosts.end());
+        g2l[l].assign(n[l], -1);
+        for (size_t k = 0; k < LL.gid.size(); k++) g2l[l][LL.gid[k]] = int(k);
+        std::vector<uint64_t> wanted(LL.n_owned, 0);
+        Entry e2[32];
+        for (long k = 0; k < LL.n_owned; k++) {
+            const long i = LL.gid[k];
+            uint64_t m = 0;
+            const int deg = S.listing(i, ent);
+            for (int j = 0; j < deg; j++) if (ent[j].nbr >= 0) m |= 1ull << owner[l][ent[j].nbr];
+            if (l + 1 < nl) m |= 1ull << owner[l + 1][levels[l].mg[i]];
+            if (l >= 1) {
+                const NodeSource& F = *levels[l - 1].src;
+                for (long c = kids[l].off[i]; c < kids[l].off[i + 1]; c++) {
+                    const long j = kids[l].idx[c];
+                    m |= 1ull << owner[l - 1][j];
+                    const int d2 = F.listing(j, e2);
+                    for (int q = 0; q < d2; q++) if (e2[q].nbr >= 0) m |= 1ull << owner[l - 1][e2[q].nbr];
+                }
+            }
+            wanted[k] = m & ~(1ull << rank);
+        }
+        LL.send_off.assign(nranks + 1, 0);
+        for (int p = 0; p < nranks; p++) {
+            for (long k = 0; k < LL.n_owned; k++) if ((wanted[k] >> p) & 1) LL.send_idx.push_back(k);
+            LL.send_off[p + 1] = long(LL.send_idx.size());
+        }
+    }
+    for (int l = 0; l < nl; l++) {
+        const NodeSource& S = *levels[l].src;
+        LocalLevel& LL = out.levels[l];
+        HostLevel& M = LL.mesh;
+        const long nloc = long(LL.gid.size());
+        M.nel = nloc; M.name = levels[l].name;
+        M.volumes.resize(nloc);
+        M.coords.resize(3 * nloc);
+        for (long k = 0; k < nloc; k++) { M.volumes[k] = S.volume(LL.gid[k]); S.coords(LL.gid[k], &M.coords[3 * k]); }
+        // edges exactly as read_grid creates them (io.cpp:84-181; build_level_like_read_grid): an edge per entry with nbr < i, in
+        // ascending i then listing order = the global edge order; the running count of internal entries is the global edge index
+        std::vector<EdgeNb> bnd, wall;
+        long global_edge = 0;
+        for (long i = 0; i < n[l]; i++) {
+            const int deg = S.listing(i, ent);
+            const bool mine = owner[l][i] == rank;
+            for (int j = 0; j < deg; j++) {
+                const long i2 = ent[j].nbr;
+                if (i2 >= i) continue;
+                if (i2 >= 0) {
+                    if (mine || owner[l][i2] == rank) {
+                        EdgeNb e = {long(g2l[l][i2]), long(g2l[l][i]), -ent[j].w[0], -ent[j].w[1], -ent[j].w[2]};
+                        M.edges.push_back(e);
+                        LL.edge_gid.push_back(global_edge);
+                    }
+                    global_edge++;
+                } else if (mine) {
+                    EdgeNb e = {i2, long(g2l[l][i]), ent[j].w[0], ent[j].w[1], ent[j].w[2]};
+                    if (mesh_variant == MESH_FVCORR) { e.x *= -1; e.y *= -1; e.z *= -1; }
+                    (i2 == -1 ? bnd : wall).push_back(e);
+                }
+            }
+        }
+        LL.nI_global = global_edge;
+        M.nI = long(M.edges.size()); M.nB = long(bnd.size()); M.nW = long(wall.size());
+        M.edges.insert(M.edges.end(), bnd.begin(), bnd.end());
+        M.edges.insert(M.edges.end(), wall.begin(), wall.end());
+        if (l + 1 < nl) {
+            M.mg.resize(nloc);
+            for (long k = 0; k < nloc; k++) M.mg[k] = g2l[l + 1][levels[l].mg[LL.gid[k]]];
         }
     }
 }

@@ -11,6 +11,7 @@
 //               (prolong_residuals_interpolate_proper reads their residuals).
 // Ghost nodes are never computed locally: their records / residuals are received from the owner.
 #pragma once
+#include <string>
 #include <vector>
 
 #include "host_mesh.h"
@@ -24,6 +25,7 @@ struct LocalLevel {
                                        // boundary / wall edges of owned nodes.  mesh.mg: local fine -> local coarse (-1 if the
                                        // parent is not held, only for ghosts that do not need it).
     long n_owned = 0;
+    long nI_global = 0;                // internal edges of the level over all ranks (work accounting)
     std::vector<long> gid;             // local -> global node id
     std::vector<long> edge_gid;        // local internal edge -> global edge index (ascending)
     std::vector<long> send_off;        // nranks+1: send_idx[send_off[p]..send_off[p+1]) goes to rank p
@@ -42,5 +44,17 @@ void rcb_owners(const HostLevel& L, int nranks, std::vector<int>& owner);
 
 // the part of `full` that rank `rank` of `nranks` holds (edge weights are taken as they are: apply adjust/dampen first)
 void partition_mesh(const HostMesh& full, int nranks, int rank, LocalMesh& out);
+
+// The same partition computed WITHOUT materialising the global mesh: every level is described by a streaming NodeSource (what a
+// text mesh file holds: per node volume, coordinates and neighbour listing, host_mesh.h) and the fine -> coarse map by a table of
+// ints; only per-node arrays (owners, coordinates for the bisection, maps) are held globally, never the edges.  Produces exactly
+// what partition_mesh() produces from the assembled mesh (tests/test_partition.py compares them), at ~1/8 of the host memory:
+// the way a 64 M-node level is split over 8 ranks.  Edge weights are raw (apply_ewt afterwards on the local edges).
+struct LevelSource {
+    const NodeSource* src = nullptr;
+    std::vector<int> mg;               // fine -> coarse (global ids); empty on the coarsest level
+    std::string name;
+};
+void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant, int nranks, int rank, LocalMesh& out);
 
 }  // namespace mgcfd

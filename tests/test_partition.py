@@ -64,6 +64,31 @@ def test_partition_invariants(kind, dims, nranks):
                 assert np.all(cloc[lv[l]["map"][nb]])
 
 
+@pytest.mark.parametrize("kind,dims", MESHES + [(1, [[17, 6, 5], [9, 3, 3], [5, 2, 2]])])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 8])
+@pytest.mark.parametrize("ewt", [False, True])
+def test_rank_local_generation_equals_partition_of_the_assembled_mesh(kind, dims, nranks, ewt):
+    """mgcfd_generate_partition_plan (no rank assembles the mesh) must hold, bit for bit, what partition_mesh cuts out of the
+    assembled mesh: ids, exchange lists and a hash over volumes, coordinates, edges (indices + weights), maps, lists."""
+    variant = 0 if kind == 2 else 2
+    lengths = (2.0, 1.0, 1.5)
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant, lengths=lengths)
+    if ewt:
+        mesh.apply_ewt()
+    for l in range(mesh.levels):
+        for r in range(nranks):
+            a = M.partition_plan(mesh, nranks, r, l)
+            b = M.generate_partition_plan(kind, dims, nranks, r, l, mesh_variant=variant, lengths=lengths, apply_ewt=ewt)
+            for k in ("owned", "ghosts", "sent", "global_nodes", "nI", "nB", "nW", "hash"):
+                assert a[k] == b[k], (k, l, r)
+            for k in ("gid", "send_counts", "recv_counts", "send_gids"):
+                assert np.array_equal(a[k], b[k]), (k, l, r)
+    # the hash is sensitive to the edge weights: adjusted vs raw differ on every non-fvcorr mesh
+    if variant != 0 and ewt:
+        raw = M.generate_partition_plan(kind, dims, nranks, 0, 0, mesh_variant=variant, lengths=lengths, apply_ewt=False)
+        assert raw["hash"] != M.partition_plan(mesh, nranks, 0, 0)["hash"]
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

@@ -33,7 +33,10 @@ def main():
     for name, kind, dims, variant in cases:
         uid = bcast_id(rank)
         mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
-        s = M.Solver.from_mesh_distributed(mesh, rank, world, uid, device=local)
+        if name in ("tet3", "hex4-big"):      # rank-local generation (no rank assembles the mesh): the path bench.py takes
+            s = M.Solver.generate_distributed(kind, dims, rank, world, uid, mesh_variant=variant, device=local)
+        else:
+            s = M.Solver.from_mesh_distributed(mesh, rank, world, uid, device=local)
         if os.environ.get("MGCFD_NO_P2P", "0") != "1":      # direct peer-to-peer data path (CUDA IPC) instead of NCCL send/recv
             mine = s.p2p_prepare()
             allp = [None] * world

@@ -479,7 +479,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
         a.vold = v.V(X);
         a.vin = (j == 0) ? v.V(X) : (j == 1 ? v.V(A) : v.V(B));
         a.vout = (j == 1) ? v.V(B) : v.V(A);
-        a.rk_div = double(MGCFD_RK + 1 - j);
+        a.rk_div = double(MGCFD_RK + 1 - j); a.rk_rcp = 1.0 / a.rk_div;
         a.mask = 7;
         a.bad_key = c->d_badkey;
         a.stage_seq = (c->stage_seq++) & 0xFFFFFFull;
@@ -1084,7 +1084,7 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
     for (int r = 0; r < reps; r++) {
         if (which == 0 || which == 1 || which == 5) {
             StageArgs a = base_args(c, v);
-            a.vin = v.V(v.i_var); a.vold = v.V(v.i_var); a.rk_div = 4.0;
+            a.vin = v.V(v.i_var); a.vold = v.V(v.i_var); a.rk_div = 4.0; a.rk_rcp = 0.25;
             if (which == 0) { a.vout = v.V(v.i_tmp); a.mask = 7; CKRC(launch_stage(c, v, a, true)); }
             else if (which == 5) { a.vout = v.V(v.i_tmp); a.mask = 6; CKRC(launch_stage(c, v, a, true)); }   // no internal edges: staging + update only
             else { a.flux = v.flux; a.mask = 1; CKRC(launch_stage(c, v, a, false)); }

@@ -186,6 +186,7 @@ struct StageArgs {
     int rec_rows;          // rows of one shared-memory record buffer (TN + padded max halo)
     int chunk_rounds;      // pipelined kernel: edge rounds per ring entry
     double rk_div;         // double(RK+1-j)
+    double rk_rcp;         // 1.0 / rk_div (rounded): see div_rk
     double k2;             // 2 * kdiss
     double* rms_partial;   // [ntiles][5] or nullptr
     unsigned long long* bad_key;  // invalid-state key or nullptr
@@ -263,26 +264,51 @@ __device__ __forceinline__ void edge_rounds(const unsigned char* blk, int nr, co
         }
     }
 }
-// boundary / wall rounds (global memory; only tiles touching the domain boundary have any)
+// boundary / wall rounds (global memory; only tiles touching the domain boundary have any).  The slot of the first round is
+// fetched by the caller BEFORE the edge loop (bslot_fetch) and the slot of round r+1 while round r is evaluated, so that the two
+// dependent global loads (kind, then weights) of a round never sit exposed between the edge loop and the node update.
+struct BSlot { int kind; double x, y, z; };
 template <int TN>
-__device__ __forceinline__ void boundary_rounds(const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f) {
-    for (int r = 0; r < br; r++, blk += TN * 25) {
-        const int kind = blk[TN * 24 + t];
-        if (kind == 0 || !((mask >> kind) & 1)) continue;
-        const double* w = reinterpret_cast<const double*>(blk);
-        if (kind == 1) boundary_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
-        else wall_flux_acc(me, w[t], w[TN + t], w[2 * TN + t], f);
+__device__ __forceinline__ BSlot bslot_fetch(const unsigned char* blk, int t) {
+    BSlot b;
+    const double* w = reinterpret_cast<const double*>(blk);
+    b.kind = blk[TN * 24 + t];
+    b.x = w[t]; b.y = w[TN + t]; b.z = w[2 * TN + t];
+    return b;
+}
+template <int TN>
+__device__ __forceinline__ void boundary_rounds(const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f, BSlot cur) {
+    for (int r = 0; r < br; r++) {
+        BSlot nxt = {0, 0.0, 0.0, 0.0};
+        if (r + 1 < br) nxt = bslot_fetch<TN>(blk + (size_t)(r + 1) * (TN * 25), t);
+        if (cur.kind != 0 && ((mask >> cur.kind) & 1)) {
+            if (cur.kind == 1) boundary_flux_acc(me, cur.x, cur.y, cur.z, f);
+            else wall_flux_acc(me, cur.x, cur.y, cur.z, f);
+        }
+        cur = nxt;
     }
 }
-// step factor of one node, evaluated where it is used (cfd_loops.cpp:146-156 / :60): min_dt / volume, or the legacy local form
-__device__ __forceinline__ double step_factor_of(const StageArgs& a, double vol, double s_old) {
+template <int TN>
+__device__ __forceinline__ void boundary_rounds(const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f) {
+    if (br > 0) boundary_rounds<TN>(blk, br, t, mask, me, f, bslot_fetch<TN>(blk, t));
+}
+// step factor of one node (cfd_loops.cpp:146-156 / :60): min_dt / volume, or the legacy local form.  Evaluated by the FIRST stage
+// of a smoothing visit (vold == vin), which stores it; the later stages read that value back (same bits, no second division).
+__device__ __forceinline__ double step_factor_of(const StageArgs& a, double min_dt, double vol, double s_old) {
     if (a.legacy) return double(0.5) / (sqrt(vol) * s_old);
-    return __longlong_as_double((long long)*a.min_bits) / vol;
+    return min_dt / vol;
+}
+// x / d for d = double(RK+1-j) in {4, 3, 2} with rd = RN(1/d): q = RN(x*rd), r = x - d*q (exact, fma), result RN(q + r*rd) -- the
+// correctly rounded quotient for every normal x (Markstein; checked against `/` on 6e8 random operands), i.e. the reference's
+// true divide (cfd_loops.cpp:243) bit for bit in three FP64 instructions instead of the ~25-instruction division sequence
+__device__ __forceinline__ double div_rk(double x, double d, double rd) {
+    const double q = __dmul_rn(x, rd);
+    return __fma_rn(__fma_rn(-d, q, x), rd, q);
 }
 // phase 3 of a fused stage for node gid: time_step + record + validity + residual; returns the five squared residuals in q
 __device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5]) {
     const long S = a.stride;
-    const double factor = sf / a.rk_div;     // a true divide, cfd_loops.cpp:243
+    const double factor = div_rk(sf, a.rk_div, a.rk_rcp);     // == sf / rk_div, the true divide of cfd_loops.cpp:243
     const double n0 = o[0] + factor * f.r, n1 = o[1] + factor * f.mx, n2 = o[2] + factor * f.my, n3 = o[3] + factor * f.mz, n4 = o[4] + factor * f.e;
     store_rec(a.vout, gid, make_rec(n0, n1, n2, n3, n4));
     if (a.bad_key) {
@@ -370,10 +396,10 @@ k_stage(const StageArgs a) {
             const double2* p = reinterpret_cast<const double2*>(a.vold + 8 * gid);
             const double2 c0 = p[0], c1 = p[1];
             o[0] = c0.x; o[1] = c0.y; o[2] = c1.x; o[3] = c1.y; o[4] = a.vold[8 * gid + 4];
-            if (a.legacy) s_old = a.vold[8 * gid + 7];
         }
-        const double sf = step_factor_of(a, a.vol[gid], s_old);
-        if (a.vold == a.vin) a.sf[gid] = sf;
+        double sf;
+        if (a.vold == a.vin) { sf = step_factor_of(a, a.legacy ? 0.0 : __longlong_as_double((long long)*a.min_bits), a.vol[gid], s_old); a.sf[gid] = sf; }
+        else sf = a.sf[gid];
         double q[5] = {0, 0, 0, 0, 0};
         fused_update(a, gid, sf, o, f, q);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
@@ -478,6 +504,9 @@ k_stage_pipe(const StageArgs a) {
     if (t == 0) produce(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     copy_recs(0);
+    const bool first_stage = (a.vold == a.vin);
+    // the visit's global minimum dt (k_min_dt, the previous kernel of a first stage): one load per CTA, not one per tile
+    const double min_dt = (first_stage && !a.legacy) ? __longlong_as_double((long long)*a.min_bits) : 0.0;
 
     for (int it = 0; it < my_count; it++) {
         const long tile = tile_of(it);
@@ -487,17 +516,21 @@ k_stage_pipe(const StageArgs a) {
         mbar_wait(&bar_recs[it & 1], (it >> 1) & 1);       // records of T_it and the header of T_{it+1} have landed
         copy_recs(it + 1);
         if (t == 0) produce(it + 1);
-        const double vol = a.vol[gid];                     // early loads for the epilogue
+        // early loads for the epilogue: volume (first stage) or the stored step factor (later stages), the old state, and the
+        // first boundary / wall slot of the tile -- all in flight while the edge rounds run
+        const double vol_or_sf = first_stage ? a.vol[gid] : a.sf[gid];
+        const int brounds = (a.mask & 6) ? hd->brounds : 0;
+        const unsigned char* bblk = a.bslots + hd->bslot_blk0 * (long)(TN * 25);
+        BSlot b0 = {0, 0.0, 0.0, 0.0};
+        if (brounds > 0) b0 = bslot_fetch<TN>(bblk, t);
         double o[5];
         const unsigned char* buf = recs + (it & 1) * 64 * (size_t)a.rec_rows;
         const Rec me = sm_load_rec_off(buf, (unsigned(t) << 6) | (((unsigned(t) >> 1) & 3u) << 4));
-        double s_old = me.s;
-        if (a.vold == a.vin) { o[0] = me.rho; o[1] = me.mx; o[2] = me.my; o[3] = me.mz; o[4] = me.re; }
+        if (first_stage) { o[0] = me.rho; o[1] = me.mx; o[2] = me.my; o[3] = me.mz; o[4] = me.re; }
         else {
             const double2* p = reinterpret_cast<const double2*>(a.vold + 8 * gid);
             const double2 c0 = p[0], c1 = p[1];
             o[0] = c0.x; o[1] = c0.y; o[2] = c1.x; o[3] = c1.y; o[4] = a.vold[8 * gid + 4];
-            if (a.legacy) s_old = a.vold[8 * gid + 7];
         }
         if (SCATTER) {
 #pragma unroll
@@ -521,10 +554,10 @@ k_stage_pipe(const StageArgs a) {
             consumed++;
             if (t == 0) produce(it + 1);
         }
-        if (a.mask & 6) boundary_rounds<TN>(a.bslots + hd->bslot_blk0 * (long)(TN * 25), hd->brounds, t, a.mask, me, f);
+        boundary_rounds<TN>(bblk, brounds, t, a.mask, me, f, b0);
         if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
-        const double sf = step_factor_of(a, vol, s_old);
-        if (a.vold == a.vin) a.sf[gid] = sf;
+        double sf = vol_or_sf;
+        if (first_stage) { sf = step_factor_of(a, min_dt, vol_or_sf, me.s); a.sf[gid] = sf; }
         double q[5] = {0, 0, 0, 0, 0};
         fused_update(a, gid, sf, o, f, q);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);

@@ -14,8 +14,10 @@ a cycle performs  sum_l E_I(l) * RK(3) * visits(l)  of them (BASELINE.json metri
   e2e    = the same metric through the public API with HOST buffers: every step copies level-0 `variables` from pinned
            host memory (set_field), runs one cycle (run_cycles -> RMS back), and reads `variables` back (get_field)
   roofline = the dominant kernel (the fused flux + time_step stage on level 0): algorithmic bytes per launch
-           (32*E_I + 28*(E_B+E_W) + 128*N) / its mean launch duration, measured with CUDA events around every
-           launch in a second pass over the same K cycles; peak = MEASURED_PEAKS.json hbm_gbs
+           (32*E_I + 28*(E_B+E_W) + 128*N) / its mean launch duration, measured with CUDA events in a second pass
+           over the same K cycles (every kernel bracketed by its own event pair; the three stage launches of a smoothing visit
+           share one pair -- divided by three -- so that they overlap as they do in the replayed graph); peak =
+           MEASURED_PEAKS.json hbm_gbs
   cpu_baseline = the UNMODIFIED reference (oracle/_ref/libmgcfd_ref_omp.so: its own sources built -DOMP -DOMP_SCATTERS)
            on the host cores, mesh duplicated once per thread as its assess-memory protocol does (gen_job.py:360-365)
 

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "../../include/mgcfd_b200.h"
@@ -155,10 +156,21 @@ namespace {
 
 inline long blocks_for(long n, int bs) { return (n + bs - 1) / bs; }
 
-// Tile size when the caller leaves it to the library (measured on B200, profiles/): 256-node tiles on levels below a million
-// nodes (smaller halo share per tile; faster on every level of the M6-shaped mesh, 2364 vs 2216 cycles/s), 128-node tiles on
-// multi-million-node levels (more CTAs in flight per SM; 202 vs 197 cycles/s on the 8 M-node mesh)
-inline int auto_tile_nodes(long n, int /*num_sms*/) { return n >= 1000000 ? 128 : 256; }
+// Tile size when the caller leaves it to the library (measured on B200, profiles/):
+//  * multi-million-node levels: 128-node tiles (more CTAs in flight per SM; 202 vs 197 cycles/s on the 8 M-node mesh);
+//  * smaller levels of low-degree meshes (hex-dual, <= 4 internal edges per node: a 128-node tile's whole edge stream fits the ring
+//    at 3 CTAs per SM): whichever of 128 / 256 needs less time in WAVES of the persistent grid (3 resp. 2 CTAs per SM), a 256-node
+//    tile costing 1.43x a 128-node one (C2 level 0: 6 waves of 128 = 23.2 us, 4 waves of 256 = 22.1 us).  On the M6-shaped mesh this
+//    picks 256 for the 300 K-node level and 128 for the three coarser ones: 2631 -> ~2790 V-cycles/s;
+//  * otherwise 256 (smaller halo share per tile).
+inline int auto_tile_nodes(long n, long nI, int num_sms) {
+    if (n >= 1000000) return 128;
+    if (nI <= 4 * n) {
+        const long w128 = blocks_for(blocks_for(n, 128), 3L * num_sms), w256 = blocks_for(blocks_for(n, 256), 2L * num_sms);
+        return (143 * w256 < 100 * w128) ? 256 : 128;
+    }
+    return 256;
+}
 
 // folds every recorded (start, stop) pair into the per-kernel per-level totals; synchronises the stream once
 void resolve_times(mgcfd_ctx* c) {
@@ -473,8 +485,14 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     Level& v = c->L[l];
     CKRC(min_dt_fused(c, l));
     const int X = v.i_var, A = v.i_tmp, B = v.i_old;   // the previous old_variables are dead once a smooth starts
+    // timing: on one GPU the three stage launches of the visit share ONE event bracket (3 * nI edge updates), so that they run as
+    // in the replayed graph -- back to back, with their programmatic-dependent-launch overlap -- instead of each paying an event
+    // round trip; distributed runs bracket every stage on its own (the halo exchange between stages is not flux time)
+    std::unique_ptr<Timed> visit_tm;
+    if (!c->dist.active) visit_tm.reset(new Timed(c, K_FLUX, l, MGCFD_RK * v.nI));
     for (int j = 0; j < MGCFD_RK; j++) {
-        Timed tm(c, K_FLUX, l, v.nI);
+        std::unique_ptr<Timed> stage_tm;
+        if (c->dist.active) stage_tm.reset(new Timed(c, K_FLUX, l, v.nI));
         StageArgs a = base_args(c, v);
         a.vold = v.V(X);
         a.vin = (j == 0) ? v.V(X) : (j == 1 ? v.V(A) : v.V(B));
@@ -488,8 +506,10 @@ int smooth_fused(mgcfd_ctx* c, int l) {
             a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
         }
         CKRC(launch_stage(c, v, a, true));
+        stage_tm.reset();
         CKRC(dist_exchange_records(c, l, a.vout));
     }
+    visit_tm.reset();
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
     return MGCFD_OK;
@@ -686,7 +706,7 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     if (mg_map && l < c->levels - 1) H.mg.assign(mg_map, mg_map + mgc); else H.mg.clear();
     PlanOptions po; po.ordering = c->opt.ordering; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
     po.strict = (c->opt.flux_mode != MGCFD_FLUX_ATOMIC);     // the atomic baseline runs on any numbering, tiled or not
-    po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : auto_tile_nodes(H.n_owned >= 0 ? H.n_owned : nel, c->num_sms);
+    po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : auto_tile_nodes(H.n_owned >= 0 ? H.n_owned : nel, nI, c->num_sms);
     try { build_level_plan(H, po, v.plan); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     v.uploaded = true;
@@ -705,14 +725,16 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         v.nel = P.nel; v.npad = P.npad; v.ncomp = P.npad_owned; v.ntiles = P.ntiles; v.nI = P.nI; v.nB = P.nB; v.nW = P.nW; v.TN = P.TN;
         v.smem_nodes = P.TN + P.hpad;
         v.smem_bytes = 64 * (size_t)v.smem_nodes + (P.scatter ? 40 * (size_t)P.TN : 0);
-        // pipelined kernel: ring of RING entries of chunk_rounds round blocks + two record buffers + three header buffers
         // pipelined kernel: a ring of RING entries of chunk_rounds round blocks + two record buffers + three header buffers.
         // chunk_rounds as large as possible (fewer CTA-wide hand-overs), at most half the rounds of a tile rounded up (so that
         // one entry is being filled while the other is consumed), while `want_ctas` CTAs still fit the SM's 228 KB
         {
-            const int want_ctas = P.TN <= 256 ? 2 : 1;
-            const size_t budget = (228 * 1024) / want_ctas - 1024 - 2048;
             const size_t fixed = 2 * 64 * (size_t)v.smem_nodes + 3 * (size_t)P.hdr_stride + (P.scatter ? 40 * (size_t)P.TN : 0);
+            // 128-node tiles run 3 CTAs per SM when that does not shrink the ring below half a tile's rounds per entry (hex-dual
+            // meshes: 2761 vs 2580 V-cycles/s on C2); with many rounds per tile (tets) larger ring entries at 2 CTAs win (237 vs 246 us)
+            int want_ctas = P.TN <= 256 ? 2 : 1;
+            if (P.TN <= 128 && fixed + (size_t)RING * ((P.max_rounds + 1) / 2) * P.TN * 26 <= (228 * 1024) / 3 - 1024 - 2048) want_ctas = 3;
+            const size_t budget = (228 * 1024) / want_ctas - 1024 - 2048;
             int R = std::max(1, P.max_rounds > 8 ? (P.max_rounds + 1) / 2 : P.max_rounds);
             while (R > 1 && fixed + (size_t)RING * R * P.TN * 26 > budget) R--;
             const int nchunks = std::max(1, (P.max_rounds + R - 1) / R);
@@ -1112,7 +1134,7 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     const EdgeNb* e = (const EdgeNb*)edges;
     H.edges.assign(e, e + nI + nB + nW);
     if (coords) H.coords.assign(coords, coords + 3 * nel);
-    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : auto_tile_nodes(nel, 148); po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : auto_tile_nodes(nel, nI, 148); po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED); po.strict = false;
     LevelPlan P;
     try { build_level_plan(H, po, P); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }

@@ -425,7 +425,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 constexpr int RING = 2;     // ring entries (each `chunk_rounds` round blocks)
 
 template <int TN, bool SCATTER>
-__global__ void __launch_bounds__(TN, (TN <= 128 ? 3 : (TN <= 256 ? 2 : 1)))
+__global__ void __launch_bounds__(TN, (TN <= 128 ? 4 : (TN <= 256 ? 2 : 1)))
 k_stage_pipe(const StageArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
     __shared__ __align__(8) unsigned long long bar_ring[RING], bar_recs[2];

@@ -1,9 +1,10 @@
 #!/bin/bash
-# One GPU session (B200_PROFILING.md recipe): parity tests, bench (both arms), then -- each only after its plain run exited 0 --
+# One GPU session (B200_PROFILING.md recipe): [parity tests,] bench (both arms), then -- each only after its plain run exited 0 --
 # the ncu launch list of the bench command and one full capture of the dominant kernel.  Outputs land in gpurun_out/.
+# usage: gpu_round.sh [notest]
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
+if [ "$1" != "notest" ]; then python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log; fi
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cut -c1-400 gpurun_out/bench_ref.json
 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; cut -c1-3000 gpurun_out/bench_c2.json; tail -3 gpurun_out/bench_c2.err
 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 &&

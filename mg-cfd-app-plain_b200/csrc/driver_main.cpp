@@ -514,6 +514,8 @@ int run_distributed(mgcfd_mesh* mesh) {
     double* vol = flux + 5 * (size_t)nel0;
     long* iters = reinterpret_cast<long*>(vol + nel0);
     long* dims = iters + n_ms;
+    // adjust_ewt + dampen_ewt once, here: the ranks then only read the mesh, so its pages stay shared between the processes
+    if (mgcfd_mesh_apply_ewt(mesh) != MGCFD_OK) { fprintf(stderr, "ERROR: %s\n", mgcfd_mesh_last_error()); munmap(map, bytes); return EXIT_FAILURE; }
     fflush(stdout); fflush(stderr);
     std::vector<pid_t> pids(N, -1);
     for (int r = 0; r < N; r++) {

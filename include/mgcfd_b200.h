@@ -174,6 +174,18 @@ int mgcfd_time_kernel(mgcfd_ctx* ctx, int level, int which, int reps, double* ms
 int mgcfd_plan_level(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall,
                      const void* edges_aos40, int ordering, int tile_nodes, int flux_mode, long info[16], long* new_of_old,
                      long* conflicts);
+/* Host-only checking aids (no device; NOT a compute path -- nothing in the solver calls them): the byte streams the plan hands to
+ * the device (tile headers, edge round blocks, boundary blocks; the restrict / prolong operators) walked on the host exactly as
+ * the kernels' threads walk them, with plain libm arithmetic.  Arrays are AoS in the reference's node order.
+ *   flux:      fluxes[nel*5] (overwritten) = what compute_flux_edge (mask bit 0), compute_boundary_flux_edge (bit 1) and
+ *              compute_wall_flux_edge (bit 2) accumulate from zero for `variables`;
+ *   transfers: var_c[nel_c*5] (in/out) = mg_restrict(var_f); var_f_out[nel_f*5] = prolong_residuals_interpolate_proper applied to
+ *              var_f with res_c / res_f. */
+int mgcfd_plan_emulate_flux(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall, const void* edges_aos40,
+                            int ordering, int tile_nodes, int flux_mode, const double* variables, int mask, double* fluxes);
+int mgcfd_plan_emulate_transfers(long nel_f, const double* coords_f, long nI_f, long nB_f, long nW_f, const void* edges_f, const long* mg_map,
+                                 long nel_c, const double* coords_c, long nI_c, long nB_c, long nW_c, const void* edges_c, int ordering,
+                                 int tile_nodes, const double* var_f, const double* res_f, const double* res_c, double* var_c, double* var_f_out);
 void mgcfd_free(void* p);
 
 #ifdef __cplusplus

@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
     L.mgcfd_launch_count.restype = l
     L.mgcfd_time_kernel.argtypes = [vp, i, i, i, dp]
     L.mgcfd_plan_level.argtypes = [l, vp, l, l, l, vp, i, i, i, C.POINTER(l), vp, C.POINTER(l)]
+    L.mgcfd_plan_emulate_flux.argtypes = [l, vp, l, l, l, vp, i, i, i, vp, i, vp]
+    L.mgcfd_plan_emulate_transfers.argtypes = [l, vp, l, l, l, vp, vp, l, vp, l, l, l, vp, i, i, vp, vp, vp, vp, vp]
     L.mgcfd_mesh_generate.argtypes = [i, i, vp, dp, i, i, C.c_ulong, C.c_double, C.POINTER(vp)]
     L.mgcfd_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
     L.mgcfd_mesh_write.argtypes = [vp, C.c_char_p, C.c_char_p, i]
@@ -483,6 +485,35 @@ def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile
     _check(lib().mgcfd_plan_level(nel, _ptr(c), nI, nB, nW, _ptr(mesh.edges(level)), ordering, tile_nodes, flux_mode, info, _ptr(perm),
                                   C.byref(conflicts)))
     return dict(zip(INFO_KEYS, info)), perm, conflicts.value
+
+
+def plan_emulate_flux(level: dict, variables, mask: int = 7, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0,
+                      flux_mode: int = FLUX_SORTED_SEGMENT):
+    """Host-only checking aid: the fluxes the stage kernel's threads accumulate from the plan's tile headers / round blocks for
+    `variables` (AoS [nel*5]), walked on the host (mgcfd_plan_emulate_flux).  `level` is a dict as conftest.mesh_levels makes them
+    (edge weights already adjusted)."""
+    var = np.ascontiguousarray(variables, dtype=np.float64).reshape(-1)
+    out = np.zeros(5 * level["nel"])
+    e = np.ascontiguousarray(level["edges"])
+    _check(lib().mgcfd_plan_emulate_flux(level["nel"], _ptr(level.get("coords")), level["nI"], level["nB"], level["nW"], _ptr(e), ordering, tile_nodes,
+                                         flux_mode, _ptr(var), mask, _ptr(out)))
+    return out
+
+
+def plan_emulate_transfers(fine: dict, coarse: dict, var_f, res_f, res_c, var_c, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0):
+    """Host-only checking aid: (restricted coarse variables, prolonged fine variables) computed from the transfer operators the
+    device receives (mgcfd_plan_emulate_transfers)."""
+    vf = np.ascontiguousarray(var_f, dtype=np.float64).reshape(-1)
+    rf = np.ascontiguousarray(res_f, dtype=np.float64).reshape(-1)
+    rc = np.ascontiguousarray(res_c, dtype=np.float64).reshape(-1)
+    vc = np.array(var_c, dtype=np.float64).reshape(-1).copy()
+    out_f = np.zeros_like(vf)
+    ef, ec = np.ascontiguousarray(fine["edges"]), np.ascontiguousarray(coarse["edges"])
+    mp = np.ascontiguousarray(fine["map"], dtype=np.int64)
+    _check(lib().mgcfd_plan_emulate_transfers(fine["nel"], _ptr(fine["coords"]), fine["nI"], fine["nB"], fine["nW"], _ptr(ef), _ptr(mp),
+                                              coarse["nel"], _ptr(coarse["coords"]), coarse["nI"], coarse["nB"], coarse["nW"], _ptr(ec),
+                                              ordering, tile_nodes, _ptr(vf), _ptr(rf), _ptr(rc), _ptr(vc), _ptr(out_f)))
+    return vc, out_f
 
 
 def smooth_granular(s: Solver, level: int, legacy: bool):

@@ -1147,6 +1147,54 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     return MGCFD_OK;
 }
 
+// host-only checking aids: the plan's byte streams walked on the host (plan.h: emulate_*)
+static int host_level(HostLevel& H, long nel, const double* coords, long nI, long nB, long nW, const void* edges, const long* mg_map) {
+    if (nel <= 0 || !edges || nI < 0 || nB < 0 || nW < 0) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    H.nel = nel; H.nI = nI; H.nB = nB; H.nW = nW;
+    H.volumes.assign(nel, 1.0);
+    const EdgeNb* e = (const EdgeNb*)edges;
+    H.edges.assign(e, e + nI + nB + nW);
+    if (coords) H.coords.assign(coords, coords + 3 * nel);
+    if (mg_map) H.mg.assign(mg_map, mg_map + nel);
+    return MGCFD_OK;
+}
+int mgcfd_plan_emulate_flux(long nel, const double* coords, long nI, long nB, long nW, const void* edges, int ordering, int tile_nodes,
+                            int flux_mode, const double* variables, int mask, double* fluxes) {
+    if (!variables || !fluxes || flux_mode == MGCFD_FLUX_ATOMIC) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    HostLevel H;
+    CKRC(host_level(H, nel, coords, nI, nB, nW, edges, nullptr));
+    PlanOptions po; po.ordering = ordering; po.tile_nodes = tile_nodes ? tile_nodes : auto_tile_nodes(nel, nI, 148); po.scatter = (flux_mode == MGCFD_FLUX_TILED_COLOURED);
+    double ff[5], ffc[12];
+    mgcfd_far_field_conditions(ff, ffc);
+    try {
+        LevelPlan P;
+        build_level_plan(H, po, P);
+        emulate_stage_flux(P, variables, mask, ff, ffc, 2.0 * (-0.5 * double(0.2f)), fluxes);
+    } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    return MGCFD_OK;
+}
+int mgcfd_plan_emulate_transfers(long nel_f, const double* coords_f, long nI_f, long nB_f, long nW_f, const void* edges_f, const long* mg_map,
+                                 long nel_c, const double* coords_c, long nI_c, long nB_c, long nW_c, const void* edges_c, int ordering,
+                                 int tile_nodes, const double* var_f, const double* res_f, const double* res_c, double* var_c, double* var_f_out) {
+    if (!coords_f || !coords_c || !mg_map || !var_f || !res_f || !res_c || !var_c || !var_f_out) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    HostLevel F, C;
+    CKRC(host_level(F, nel_f, coords_f, nI_f, nB_f, nW_f, edges_f, mg_map));
+    CKRC(host_level(C, nel_c, coords_c, nI_c, nB_c, nW_c, edges_c, nullptr));
+    for (long i = 0; i < nel_f; i++) if (mg_map[i] < 0 || mg_map[i] >= nel_c) { g_err = "mg_map entry out of range"; return MGCFD_ERR_ARG; }
+    try {
+        PlanOptions po; po.ordering = ordering;
+        LevelPlan Pf, Pc;
+        po.tile_nodes = tile_nodes ? tile_nodes : auto_tile_nodes(nel_f, nI_f, 148); build_level_plan(F, po, Pf);
+        po.tile_nodes = tile_nodes ? tile_nodes : auto_tile_nodes(nel_c, nI_c, 148); build_level_plan(C, po, Pc);
+        TransferPlan T;
+        build_transfer_plan(F, C, Pf, Pc, T);
+        emulate_restrict(Pf, Pc, T, var_f, var_c);
+        memcpy(var_f_out, var_f, sizeof(double) * 5 * nel_f);
+        emulate_prolong(Pf, Pc, T, res_c, res_f, var_f_out);
+    } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    return MGCFD_OK;
+}
+
 // ---- distributed runs (include/mgcfd_dist.h) -----------------------------------------------------------------
 int mgcfd_dist_get_unique_id(char id[128]) {
     if (!id) { g_err = "null argument"; return MGCFD_ERR_ARG; }

@@ -537,4 +537,142 @@ void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const L
     }
 }
 
+
+// ---- host walk of the device data structures ----------------------------------------------------------------------------------
+// What a thread of the stage / transfer kernels does (kernels.cuh), restated on the host over the SAME byte streams the device
+// receives (tile headers, round blocks, boundary blocks, transfer operators).  It exists so that the integer preprocessing can be
+// checked against the oracle without a GPU (tests/test_host_mesh.py); it is not a compute path of the product (no entry point
+// of the solver calls it) and uses plain libm arithmetic, so it agrees with the device to rounding, not bit for bit.
+namespace {
+struct HRec { double rho, mx, my, mz, re, ir, p, s; };
+HRec host_rec(const double* v) {
+    HRec n;
+    n.rho = v[0]; n.mx = v[1]; n.my = v[2]; n.mz = v[3]; n.re = v[4];
+    n.ir = 1.0 / n.rho;
+    const double vx = n.mx * n.ir, vy = n.my * n.ir, vz = n.mz * n.ir;
+    const double sq = vx * vx + vy * vy + vz * vz;
+    n.p = (1.4 - 1.0) * (n.re - 0.5 * n.rho * sq);
+    n.s = std::sqrt(sq) + std::sqrt(1.4 * n.p * n.ir);
+    return n;
+}
+// edge_flux_acc_w (kernels.cuh): A's five increments for the edge A -> B, h = -0.5 * edge vector oriented A -> B
+void host_edge_flux(const HRec& A, const HRec& B, double hx, double hy, double hz, double k2, double g[5]) {
+    const double ewt = std::sqrt(hx * hx + hy * hy + hz * hz);
+    const double factor = ewt * k2 * (A.s + B.s);
+    const double gA = hx * A.mx + hy * A.my + hz * A.mz, gB = hx * B.mx + hy * B.my + hz * B.mz;
+    const double qA = gA * A.ir, qB = gB * B.ir, ps = A.p + B.p;
+    g[0] = factor * (A.rho - B.rho) + (gA + gB);
+    g[4] = factor * (A.re - B.re) + ((A.re + A.p) * qA + (B.re + B.p) * qB);
+    g[1] = factor * (A.mx - B.mx) + (A.mx * qA + B.mx * qB + ps * hx);
+    g[2] = factor * (A.my - B.my) + (A.my * qA + B.my * qB + ps * hy);
+    g[3] = factor * (A.mz - B.mz) + (A.mz * qA + B.mz * qB + ps * hz);
+}
+}  // namespace
+
+void emulate_stage_flux(const LevelPlan& P, const double* var, int mask, const double ff[5], const double ffc[12], double k2, double* flux) {
+    const long TN = P.TN;
+    const size_t BLK = size_t(TN) * 26, BBLK = size_t(TN) * 25;
+    std::vector<HRec> rec(P.npad);
+    const double pad_state[5] = {ff[0], ff[1], ff[2], ff[3], ff[4]};
+    for (long g = 0; g < P.npad; g++) rec[g] = host_rec(P.old_of_new[g] >= 0 ? var + 5 * P.old_of_new[g] : pad_state);
+    std::vector<double> acc(5 * TN), f(5 * TN);
+    for (long t = 0; t < P.ntiles; t++) {
+        const unsigned char* h = P.hdrs.data() + size_t(t) * P.hdr_stride;
+        const int* hi = reinterpret_cast<const int*>(h);
+        const long long* hl = reinterpret_cast<const long long*>(h + 16);
+        const int rounds = hi[0], nh = hi[1], brounds = hi[2];
+        const int* ids = reinterpret_cast<const int*>(h + 32);
+        auto row = [&](int o) -> const HRec& {
+            if (o < TN) return rec[t * TN + o];
+            if (o - TN >= nh) throw std::runtime_error("mgcfd: slot points past the tile's halo");
+            return rec[ids[o - TN]];
+        };
+        std::fill(acc.begin(), acc.end(), 0.0);
+        std::fill(f.begin(), f.end(), 0.0);
+        if (mask & 1)
+            for (int r = 0; r < rounds; r++) {
+                const unsigned char* blk = P.slots.data() + size_t(hl[0] + r) * BLK;
+                const double* w = reinterpret_cast<const double*>(blk);
+                const uint16_t* oth = reinterpret_cast<const uint16_t*>(blk + size_t(TN) * 24);
+                for (long lu = 0; lu < TN; lu++) {
+                    const uint16_t code = oth[lu];
+                    if (P.scatter && code == 0xFFFF) continue;
+                    const int o = row_of_code(code);
+                    if (code != row_code(o)) throw std::runtime_error("mgcfd: slot row code does not follow the swizzle");
+                    double g[5];
+                    host_edge_flux(rec[t * TN + lu], row(o), w[lu], w[TN + lu], w[2 * TN + lu], k2, g);
+                    for (int k = 0; k < 5; k++) f[k * TN + lu] += g[k];
+                    if (P.scatter && o < TN) for (int k = 0; k < 5; k++) acc[k * TN + o] -= g[k];
+                }
+            }
+        if (mask & 6)
+            for (int r = 0; r < brounds; r++) {
+                const unsigned char* blk = P.bslots.data() + size_t(hl[1] + r) * BBLK;
+                const double* w = reinterpret_cast<const double*>(blk);
+                for (long lu = 0; lu < TN; lu++) {
+                    const int kind = blk[size_t(TN) * 24 + lu];
+                    if (kind == 0 || !((mask >> kind) & 1)) continue;
+                    const HRec& B = rec[t * TN + lu];
+                    const double x = w[lu], y = w[TN + lu], z = w[2 * TN + lu];
+                    if (kind == 1) { f[1 * TN + lu] += x * B.p; f[2 * TN + lu] += y * B.p; f[3 * TN + lu] += z * B.p; }
+                    else {            // flux_wall_kernel.elemfunc.c:47-69
+                        const double fx = 0.5 * x, fy = 0.5 * y, fz = 0.5 * z;
+                        const double g = fx * B.mx + fy * B.my + fz * B.mz, q = g * B.ir;
+                        f[0 * TN + lu] += (fx * ff[1] + fy * ff[2] + fz * ff[3]) + g;
+                        f[4 * TN + lu] += (fx * ffc[9] + fy * ffc[10] + fz * ffc[11]) + (B.re + B.p) * q;
+                        f[1 * TN + lu] += (fx * ffc[0] + fy * ffc[1] + fz * ffc[2]) + (B.mx * q + B.p * fx);
+                        f[2 * TN + lu] += (fx * ffc[3] + fy * ffc[4] + fz * ffc[5]) + (B.my * q + B.p * fy);
+                        f[3 * TN + lu] += (fx * ffc[6] + fy * ffc[7] + fz * ffc[8]) + (B.mz * q + B.p * fz);
+                    }
+                }
+            }
+        for (long lu = 0; lu < TN; lu++) {
+            const long on = P.old_of_new[t * TN + lu];
+            if (on < 0) {            // padding threads hold empty slots only: exact zeros
+                for (int k = 0; k < 5; k++) if (f[k * TN + lu] != 0.0) throw std::runtime_error("mgcfd: a padding thread accumulated flux");
+                continue;
+            }
+            for (int k = 0; k < 5; k++) flux[5 * on + k] = f[k * TN + lu] + (P.scatter ? acc[k * TN + lu] : 0.0);
+        }
+    }
+}
+
+void emulate_restrict(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* var_f, double* var_c) {
+    (void)Pf;
+    for (long c = 0; c < Pc.npad; c++) {
+        const long k0 = T.child_off[c], k1 = T.child_off[c + 1], oc = Pc.old_of_new[c];
+        if (k1 == k0 || oc < 0) continue;
+        double sum[5] = {0, 0, 0, 0, 0};
+        for (long k = k0; k < k1; k++) {
+            const long of = Pf.old_of_new[T.child_ids[k]];
+            for (int j = 0; j < 5; j++) sum[j] += var_f[5 * of + j];
+        }
+        const double average = 1.0 / double(k1 - k0);
+        for (int j = 0; j < 5; j++) var_c[5 * oc + j] = sum[j] * average;
+    }
+}
+
+void emulate_prolong(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* res_c, const double* res_f, double* var_f) {
+    for (long i = 0; i < Pf.npad; i++) {
+        const int p = T.parent[i];
+        const long on = Pf.old_of_new[i];
+        if (p < 0 || on < 0) continue;
+        const double* rp = res_c + 5 * Pc.old_of_new[p];
+        const double w0 = T.idist_own[i];
+        double acc[5] = {0, 0, 0, 0, 0}, wsum = 0.0;
+        const long k0 = T.ent_off[i], k1 = T.ent_off[i + 1];
+        if (w0 < 0.0) {
+            if (k1 > k0) { for (int j = 0; j < 5; j++) acc[j] = rp[j]; wsum = 1.0; }
+        } else {
+            for (long k = k0; k < k1; k++) {
+                const double* rq = res_c + 5 * Pc.old_of_new[T.ent_src[k]];
+                const double w = T.ent_w[k];
+                for (int j = 0; j < 5; j++) { acc[j] += w0 * rp[j]; acc[j] += w * rq[j]; }
+                wsum += w0; wsum += w;
+            }
+        }
+        for (int j = 0; j < 5; j++) var_f[5 * on + j] = var_f[5 * on + j] + (res_f[5 * on + j] - acc[j] / wsum);
+    }
+}
+
 }  // namespace mgcfd

@@ -74,4 +74,11 @@ struct TransferPlan {
 };
 void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const LevelPlan& Pf, const LevelPlan& Pc, TransferPlan& T);
 
+// Host walk of the device data structures (checking aid for the preprocessing, not a compute path): what the stage kernel's threads
+// accumulate from the tile headers / round blocks / boundary blocks of P for the state `var` (AoS, original node order) -> flux
+// (AoS, original order; mask: bit0 internal, bit1 boundary, bit2 wall edges), and what k_restrict / k_prolong compute from T.
+void emulate_stage_flux(const LevelPlan& P, const double* var, int mask, const double ff[5], const double ffc[12], double k2, double* flux);
+void emulate_restrict(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* var_f, double* var_c);
+void emulate_prolong(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* res_c, const double* res_f, double* var_f);
+
 }  // namespace mgcfd

@@ -156,3 +156,62 @@ def test_partition_rcm_improves_locality_on_a_shuffled_mesh():
     part, _, _ = M.plan_level(shuffled, 0, ordering=M.ORDER_PARTITION_RCM, tile_nodes=256)
     assert part["cut_edges"] < rcm["cut_edges"] < as_given["cut_edges"]
     assert part["halo_entries"] < 0.5 * as_given["halo_entries"]
+
+
+PLAN_MESHES = [(0, [[15, 14, 13], [8, 8, 7]], 2, 0), (1, [[11, 10, 9], [6, 5, 5]], 3, 0), (2, [[6, 5, 5]], 0, 0), (0, [[13, 12, 11], [7, 6, 6]], 4, 1)]
+
+
+@pytest.mark.parametrize("kind,dims,variant,node_order", PLAN_MESHES)
+@pytest.mark.parametrize("ordering", [M.ORDER_AS_GIVEN, M.ORDER_RCM, M.ORDER_PARTITION_RCM])
+@pytest.mark.parametrize("tile_nodes,flux_mode", [(128, M.FLUX_SORTED_SEGMENT), (256, M.FLUX_SORTED_SEGMENT), (0, M.FLUX_SORTED_SEGMENT),
+                                                  (128, M.FLUX_TILED_COLOURED), (256, M.FLUX_TILED_COLOURED)])
+def test_plan_byte_streams_reproduce_the_oracle_fluxes(kind, dims, variant, node_order, ordering, tile_nodes, flux_mode):
+    """No GPU: the tile headers, edge round blocks (weights, swizzled row codes, halo lists) and boundary blocks the device
+    receives, walked on the host the way the stage kernel's threads walk them, give the oracle's compute_flux_edge /
+    compute_boundary_flux_edge / compute_wall_flux_edge sums on every level (rounding apart: a different, fixed summation order)."""
+    from conftest import linf_rel, mesh_levels, perturbed_state
+    from oracle.loader import Oracle
+    orc = Oracle()
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant, ordering=node_order)
+    if node_order == 1 and ordering != M.ORDER_PARTITION_RCM:
+        pytest.skip("a shuffled numbering is only tiled after renumbering")
+    for l, L in enumerate(mesh_levels(mesh, apply_ewt_with=orc)):
+        var = perturbed_state(L["nel"], seed=300 + l)
+        want = np.zeros(5 * L["nel"])
+        orc.flux_edge(0, L["nI"], L["edges"], var, want)
+        got = M.plan_emulate_flux(L, var, mask=1, ordering=ordering, tile_nodes=tile_nodes, flux_mode=flux_mode)
+        assert np.all(linf_rel(got, want) < 1e-13), ("internal", l, linf_rel(got, want))
+        orc.boundary_flux_edge(L["nI"], L["nB"], L["edges"], var, want)
+        orc.wall_flux_edge(L["nI"] + L["nB"], L["nW"], L["edges"], var, want)
+        got = M.plan_emulate_flux(L, var, mask=7, ordering=ordering, tile_nodes=tile_nodes, flux_mode=flux_mode)
+        assert np.all(linf_rel(got, want) < 1e-13), ("all", l, linf_rel(got, want))
+        only_wall = M.plan_emulate_flux(L, var, mask=4, ordering=ordering, tile_nodes=tile_nodes, flux_mode=flux_mode)
+        ref_wall = np.zeros(5 * L["nel"])
+        orc.wall_flux_edge(L["nI"] + L["nB"], L["nW"], L["edges"], var, ref_wall)
+        assert np.allclose(only_wall, ref_wall, rtol=1e-13, atol=1e-22)
+
+
+@pytest.mark.parametrize("kind,dims,variant,node_order", [m for m in PLAN_MESHES if len(m[1]) > 1] + [(0, [[12, 11, 10], [9, 8, 7], [5, 5, 4]], 2, 0)])
+@pytest.mark.parametrize("tile_nodes", [0, 128, 256])
+def test_transfer_operators_reproduce_the_oracle_transfers(kind, dims, variant, node_order, tile_nodes):
+    """No GPU: the restrict child lists and the prolong operator (own-parent weights, entries with the b-side quirk of
+    mg_loops.cpp:804-810 baked in) applied on the host give mg_restrict bit for bit and prolong_residuals_interpolate_proper to rounding."""
+    from conftest import linf_rel, mesh_levels, perturbed_state
+    from oracle.loader import Oracle
+    orc = Oracle()
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant, ordering=node_order)
+    lv = mesh_levels(mesh, apply_ewt_with=orc)
+    rng = np.random.default_rng(11)
+    for l in range(mesh.levels - 1):
+        F, C = lv[l], lv[l + 1]
+        vf, vc = perturbed_state(F["nel"], seed=40 + l), perturbed_state(C["nel"], seed=50 + l)
+        r1, r2 = 1e-3 * rng.standard_normal(5 * C["nel"]), 1e-3 * rng.standard_normal(5 * F["nel"])
+        got_c, got_f = M.plan_emulate_transfers(F, C, vf, r2, r1, vc, tile_nodes=tile_nodes)
+        want_c = vc.copy()
+        orc.mg_restrict(vf, want_c, F["map"])
+        assert np.array_equal(got_c, want_c)
+        want_f = vf.copy()
+        orc.prolong(F["edges"], F["nI"], r1, r2, want_f, F["map"], C["coords"], F["coords"])
+        ok = np.isfinite(want_f)                   # nodes without an internal edge are 0/0 in the reference (and here)
+        assert np.array_equal(np.isfinite(got_f), ok)
+        assert np.all(linf_rel(np.where(ok, got_f, 0.0), np.where(ok, want_f, 0.0)) < 1e-14)

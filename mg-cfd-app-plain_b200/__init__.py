@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("MGCFD_B200_LIB") or os.path.join(_HERE, "libmgcfd_b200.so")   # override: A/B work on kernels only
+LIB_PATH = os.path.join(_HERE, "libmgcfd_b200.so")
 DRIVER_PATH = os.path.join(_HERE, "euler3d_b200")     # the reference's euler3d driver on top of the C ABI
 
 NVAR = 5

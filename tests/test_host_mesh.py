@@ -87,6 +87,35 @@ def test_load_errors_are_reported(tmp_path):
         M.Mesh.load("input.dat", str(tmp_path))
 
 
+def test_text_formats_as_other_tools_write_them(tmp_path):
+    """The text mesh is whitespace-separated numbers (the reference reads it with operator>>, io.cpp:56-137): fixed and
+    scientific notation, explicit '+' signs, tabs, CRLF and blank lines all parse to the same arrays; a damaged or
+    truncated file is reported instead of yielding garbage."""
+    mesh = M.Mesh.generate(M.GEN_TET_CELLS, [[2, 2, 1]], mesh_variant=M.MESH_FVCORR)
+    mesh.write(str(tmp_path))
+    ref = mesh_levels(M.Mesh.load("input.dat", str(tmp_path)))[0]
+    name = [f for f in os.listdir(tmp_path) if f.endswith(".dat") and f != "input.dat"][0]
+    toks = (tmp_path / name).read_text().split()
+    restyled = []
+    for k, t in enumerate(toks):
+        if "." in t or "e" in t:
+            v = float(t)
+            restyled.append(("+" if v >= 0 and k % 3 == 0 else "") + ("%.17e" % v if k % 2 else repr(v)))
+        else:
+            restyled.append(t)
+    (tmp_path / name).write_text("\r\n\t ".join(restyled) + "\r\n\r\n")
+    again = mesh_levels(M.Mesh.load("input.dat", str(tmp_path)))[0]
+    assert again["edges"].tobytes() == ref["edges"].tobytes() and np.array_equal(again["vol"], ref["vol"])
+    (tmp_path / name).write_text(" ".join(toks[:len(toks) // 2]))                     # truncated
+    with pytest.raises(M.MgcfdError, match="Corruption"):
+        M.Mesh.load("input.dat", str(tmp_path))
+    broken = list(toks)
+    broken[7] = "1.0.0x"
+    (tmp_path / name).write_text(" ".join(broken))
+    with pytest.raises(M.MgcfdError, match="Corruption"):
+        M.Mesh.load("input.dat", str(tmp_path))
+
+
 @pytest.mark.skipif(not reference_available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("kind,dims,variant", [(0, [[7, 6, 5], [4, 3, 3]], 2), (1, [[5, 5, 4], [3, 3, 2]], 3), (2, [[3, 3, 2]], 0)])
 def test_files_read_by_the_reference_loader_give_our_arrays(tmp_path, kind, dims, variant):

@@ -170,7 +170,9 @@ long mgcfd_launch_count(mgcfd_ctx* ctx);
 int mgcfd_time_kernel(mgcfd_ctx* ctx, int level, int which, int reps, double* ms_total);
 
 /* Host-only run of the integer preprocessing (no device needed): renumbering, tiling and colouring of one level.
- * info[] as mgcfd_level_info; new_of_old may be NULL; *conflicts = result of the colouring validity check. */
+ * info[] as mgcfd_level_info, except info[15] = a hash of everything the device would receive of the level (the plan is a pure
+ * function of the mesh: tests compare it across runs and thread counts); new_of_old may be NULL; *conflicts = result of the
+ * colouring validity check. */
 int mgcfd_plan_level(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall,
                      const void* edges_aos40, int ordering, int tile_nodes, int flux_mode, long info[16], long* new_of_old,
                      long* conflicts);

@@ -484,7 +484,9 @@ def plan_level(mesh: Mesh, level: int, ordering: int = ORDER_PARTITION_RCM, tile
     c = mesh.coords(level)
     _check(lib().mgcfd_plan_level(nel, _ptr(c), nI, nB, nW, _ptr(mesh.edges(level)), ordering, tile_nodes, flux_mode, info, _ptr(perm),
                                   C.byref(conflicts)))
-    return dict(zip(INFO_KEYS, info)), perm, conflicts.value
+    d = dict(zip(INFO_KEYS, info))
+    d["plan_hash"] = d.pop("pipe_grid")          # mgcfd_plan_level reports the plan's hash in the last slot
+    return d, perm, conflicts.value
 
 
 def plan_emulate_flux(level: dict, variables, mask: int = 7, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0,

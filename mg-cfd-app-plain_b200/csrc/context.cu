@@ -1142,6 +1142,17 @@ int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, 
     info[0] = P.nel; info[1] = P.nI; info[2] = P.nB; info[3] = P.nW; info[4] = P.npad; info[5] = P.ntiles; info[6] = P.TN;
     info[7] = P.max_rounds; info[8] = P.slot_off[P.ntiles] * P.TN; info[9] = (long)P.halo_ids.size();
     info[10] = P.cut_edges / 2; info[11] = P.used_slots; info[12] = P.max_halo; info[13] = P.bslot_off[P.ntiles] * P.TN;
+    {   // info[15]: FNV-1a over everything the device receives of the level -- the plan must be a pure function of the mesh
+        unsigned long long h = 1469598103934665603ull;
+        auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+        mix(P.new_of_old.data(), P.new_of_old.size() * sizeof(long));
+        mix(P.hdrs.data(), P.hdrs.size()); mix(P.slots.data(), P.slots.size()); mix(P.bslots.data(), P.bslots.size());
+        mix(P.halo_ids.data(), P.halo_ids.size() * sizeof(int)); mix(P.tile_nown.data(), P.tile_nown.size() * sizeof(int));
+        mix(P.adj_off.data(), P.adj_off.size() * sizeof(long)); mix(P.adj_nbr.data(), P.adj_nbr.size() * sizeof(int));
+        const long tail[4] = {P.cut_edges, P.used_slots, P.max_halo, P.max_rounds};
+        mix(tail, sizeof(tail));
+        info[15] = (long)(h >> 1);
+    }
     if (new_of_old) memcpy(new_of_old, P.new_of_old.data(), sizeof(long) * nel);
     if (conflicts) *conflicts = P.oversize ? -1 : check_colouring(P);
     return MGCFD_OK;

@@ -2,11 +2,17 @@
 #include "plan.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <future>
 #include <numeric>
 #include <stdexcept>
+#include <string>
+#include <thread>
 
 namespace mgcfd {
 
@@ -15,6 +21,25 @@ namespace {
 struct Csr {
     std::vector<long> off;
     std::vector<int> nbr;
+};
+
+// host threads the preprocessing may use: hardware concurrency, capped by MGCFD_PLAN_THREADS (1 = serial; the result never depends on it)
+unsigned plan_threads() {
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* e = getenv("MGCFD_PLAN_THREADS")) { const int v = atoi(e); if (v >= 1) hw = std::min<unsigned>(hw, unsigned(v)); }
+    return hw;
+}
+
+// MGCFD_PLAN_TIMING=1: wall time of the phases of build_level_plan on stderr (setup cost of large meshes)
+struct PhaseClock {
+    bool on = getenv("MGCFD_PLAN_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  plan: %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
 };
 
 // undirected adjacency of the internal edges, in OLD ids; per node, entries in ascending edge index
@@ -122,7 +147,7 @@ struct Bisector {
             const double cx = c[3 * x + ax], cy = c[3 * y + ax];
             return cx != cy ? cx < cy : x < y;
         });
-        if (depth < 3 && n > 200000) {
+        if (depth < 3 && n > 200000 && plan_threads() > 1) {
             auto fut = std::async(std::launch::async, [&] { rcb(idx, nl, kl, tile0, depth + 1); });
             rcb(idx + nl, n - nl, k - kl, tile0 + kl, depth + 1);
             fut.get();
@@ -177,7 +202,9 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
     P.npad_owned = P.ntiles * TN;
     P.npad = P.npad_owned + (((nall - n) + 7) & ~7L);
     if (P.npad > 0x7fffffffL) throw std::runtime_error("mgcfd: level too large for 32-bit node ids");
+    PhaseClock clk;
     const Csr g = adjacency_old(L);
+    clk.lap("adjacency");
 
     // ---- 1. node -> tile, and order inside tiles --------------------------------------------------
     std::vector<long> tile_of(n, 0);
@@ -198,6 +225,7 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         Bisector B(L, g, TN, tile_of);
         if (!L.coords.empty()) B.rcb(idx.data(), n, P.ntiles, 0, 0);
         else B.gbis(idx.data(), n, P.ntiles, 0);
+        clk.lap("bisection into tiles");
         // Cuthill-McKee inside every tile
         std::vector<long> toff(P.ntiles + 1, 0);
         for (long i = 0; i < n; i++) toff[tile_of[i] + 1]++;
@@ -205,16 +233,27 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         std::vector<long> members(n), pos(toff.begin(), toff.end() - 1);
         for (long i = 0; i < n; i++) members[pos[tile_of[i]]++] = i;
         std::vector<int> stamp(nall, 0);
-        std::vector<long> order, nodes;
-        long r = 0;
-        for (long t = 0; t < P.ntiles; t++) {
-            nodes.assign(members.begin() + toff[t], members.begin() + toff[t + 1]);
-            order.clear();
-            cm_order(g, nodes, [&](long v) { return v < n && tile_of[v] == t; }, stamp, int(t % 1000000000) + 1, order);
-            for (long v : order) seq[v] = r++;
-            // stamps are tile specific (t+1) and tiles are disjoint, so no reset is needed
-        }
+        // tiles are disjoint and cm_order only touches the stamps of its own tile's nodes (stamps are tile specific, t+1, so no
+        // reset is needed): tiles are ordered concurrently; tile t fills the sequence numbers toff[t] .. toff[t+1]
+        std::atomic<long> next_tile(0);
+        auto worker = [&]() {
+            std::vector<long> order, nodes;
+            for (long t0 = next_tile.fetch_add(64); t0 < P.ntiles; t0 = next_tile.fetch_add(64))
+                for (long t = t0; t < std::min(t0 + 64, P.ntiles); t++) {
+                    nodes.assign(members.begin() + toff[t], members.begin() + toff[t + 1]);
+                    order.clear();
+                    cm_order(g, nodes, [&](long v) { return v < n && tile_of[v] == t; }, stamp, int(t % 1000000000) + 1, order);
+                    long r = toff[t];
+                    for (long v : order) seq[v] = r++;
+                }
+        };
+        const unsigned nthreads = unsigned(std::max<long>(1, std::min<long>(plan_threads(), P.ntiles / 64)));
+        std::vector<std::future<void>> pool;
+        for (unsigned k = 1; k < nthreads; k++) pool.push_back(std::async(std::launch::async, worker));
+        worker();
+        for (auto& f : pool) f.get();
     }
+    clk.lap("ordering inside tiles");
     // rank inside tile by seq
     P.new_of_old.assign(nall, -1);
     P.old_of_new.assign(P.npad, -1);
@@ -234,6 +273,7 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
             if (P.tile_nown[t] > TN) throw std::runtime_error("mgcfd: internal error, tile overflow");
     }
 
+    clk.lap("renumbering");
     // ---- 2. flat edge list + CSR by node in new ids (entries in ascending original edge index) ------
     P.ea.resize(L.nI); P.eb.resize(L.nI); P.ew.resize(3 * L.nI);
     for (long e = 0; e < L.nI; e++) {
@@ -273,18 +313,33 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         for (long k = 0; k < nbw; k++) bn_idx[pos[P.bnode[k]]++] = k;
     }
 
+    clk.lap("edge lists + CSR");
     // ---- 3. tiles: halo lists, edge rounds ------------------------------------------------------------
+    // Tiles are independent: contiguous ranges of tiles are processed by a pool of host threads, each range into its own buffers,
+    // which are then laid end to end in tile order -- byte for byte what a serial pass produces (tests compare the plan's hash).
     P.scatter = opt.scatter;
     P.halo_off.assign(P.ntiles + 1, 0);
     P.slot_off.assign(P.ntiles + 1, 0);
     P.bslot_off.assign(P.ntiles + 1, 0);
     struct Slot { int owner; int round; int other; long e; bool owner_is_a; };
+    const size_t BLK = size_t(TN) * 26, BBLK = size_t(TN) * 25;
+    struct TileRange {
+        long t0 = 0, t1 = 0;
+        std::vector<unsigned char> slots, bslots;      // this range's round blocks / boundary blocks, tile after tile
+        std::vector<int> halo;                         // this range's halo ids, tile after tile
+        std::vector<int> rounds, brounds, nhalo;       // per tile
+        long cut_edges = 0, used_slots = 0;
+        int max_halo = 0, max_rounds = 0;
+        bool oversize = false;
+        std::string error;
+    };
+    auto process_range = [&](TileRange& C) {
     std::vector<Slot> slots;
     std::vector<int> halo;
     std::vector<Mask256> Lm(TN), Rm(TN);
     std::vector<int> nassigned(TN);
-    const size_t BLK = size_t(TN) * 26, BBLK = size_t(TN) * 25;
-    for (long t = 0; t < P.ntiles; t++) {
+    long blocks_done = 0, bblocks_done = 0;
+    for (long t = C.t0; t < C.t1; t++) {
         const long base = t * TN;
         const int nown = P.tile_nown[t];
         halo.clear();
@@ -298,11 +353,11 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         if (long(TN) + long(halo.size()) >= 1020) {
             // the 16-bit row code addresses at most 1020 rows of 64 bytes; a tile this scattered could not be staged anyway
             if (opt.strict) throw std::runtime_error("mgcfd: tile halo too large (TN + halo must stay below 1020 rows): use a smaller tile_nodes or a locality-preserving ordering (MGCFD_ORDER_PARTITION_RCM)");
-            P.oversize = true;
+            C.oversize = true;
         }
-        P.halo_off[t + 1] = P.halo_off[t] + long(halo.size());
-        P.halo_ids.insert(P.halo_ids.end(), halo.begin(), halo.end());
-        P.max_halo = std::max(P.max_halo, int(halo.size()));
+        C.nhalo.push_back(int(halo.size()));
+        C.halo.insert(C.halo.end(), halo.begin(), halo.end());
+        C.max_halo = std::max(C.max_halo, int(halo.size()));
         auto local_of = [&](int v) -> int {
             if (v >= base && v < base + TN) return int(v - base);
             return int(TN) + int(std::lower_bound(halo.begin(), halo.end(), v) - halo.begin());
@@ -318,7 +373,7 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
                     const int v = P.adj_nbr[k] & 0x7fffffff;
                     const bool cut = (v < base || v >= base + TN);
                     slots.push_back({lu, r, local_of(v), adj_eid[k], P.adj_nbr[k] >= 0});
-                    if (cut) P.cut_edges++;
+                    if (cut) C.cut_edges++;
                 }
                 tile_rounds = std::max(tile_rounds, r);
             }
@@ -386,22 +441,23 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
                     const int c = Mask256::first_free(Lm[lu], none);
                     Lm[lu].set(c); nassigned[lu]++;
                     slots.push_back({lu, c, local_of(v), adj_eid[k], P.adj_nbr[k] >= 0});
-                    P.cut_edges++;
+                    C.cut_edges++;
                 }
         }
         int rounds = 0;
         for (const Slot& s : slots) rounds = std::max(rounds, s.round + 1);
-        P.max_rounds = std::max(P.max_rounds, rounds);
-        const long b0 = P.slot_off[t];
-        P.slot_off[t + 1] = b0 + rounds;
-        P.slots.resize(size_t(P.slot_off[t + 1]) * BLK, 0);
+        C.max_rounds = std::max(C.max_rounds, rounds);
+        C.rounds.push_back(rounds);
+        const long b0 = blocks_done;
+        blocks_done += rounds;
+        C.slots.resize(size_t(blocks_done) * BLK, 0);
         // empty slots
         for (int r = 0; r < rounds; r++) {
-            uint16_t* oth = reinterpret_cast<uint16_t*>(P.slots.data() + size_t(b0 + r) * BLK + size_t(TN) * 24);
+            uint16_t* oth = reinterpret_cast<uint16_t*>(C.slots.data() + size_t(b0 + r) * BLK + size_t(TN) * 24);
             for (int lu = 0; lu < TN; lu++) oth[lu] = opt.scatter ? uint16_t(0xFFFF) : row_code(lu);
         }
         for (const Slot& s : slots) {
-            unsigned char* blk = P.slots.data() + size_t(b0 + s.round) * BLK;
+            unsigned char* blk = C.slots.data() + size_t(b0 + s.round) * BLK;
             double* w = reinterpret_cast<double*>(blk);
             uint16_t* oth = reinterpret_cast<uint16_t*>(blk + size_t(TN) * 24);
             const double sg = s.owner_is_a ? -0.5 : 0.5;      // h = -0.5 * vector(thread-node -> other); stored vector is a -> b
@@ -410,24 +466,75 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
             w[2 * TN + s.owner] = sg * P.ew[2 * L.nI + s.e];
             oth[s.owner] = row_code(s.other);
         }
-        P.used_slots += long(slots.size());
+        C.used_slots += long(slots.size());
         // boundary / wall rounds: round r of a node = its r-th boundary or wall edge in original order
         int br = 0;
         for (int lu = 0; lu < nown; lu++) br = std::max<int>(br, int(bn_off[base + lu + 1] - bn_off[base + lu]));
-        const long bb0 = P.bslot_off[t];
-        P.bslot_off[t + 1] = bb0 + br;
-        P.bslots.resize(size_t(P.bslot_off[t + 1]) * BBLK, 0);
+        C.brounds.push_back(br);
+        const long bb0 = bblocks_done;
+        bblocks_done += br;
+        C.bslots.resize(size_t(bblocks_done) * BBLK, 0);
         for (int lu = 0; lu < nown; lu++) {
             int r = 0;
             for (long k = bn_off[base + lu]; k < bn_off[base + lu + 1]; k++, r++) {
                 const long bi = bn_idx[k];
-                unsigned char* blk = P.bslots.data() + size_t(bb0 + r) * BBLK;
+                unsigned char* blk = C.bslots.data() + size_t(bb0 + r) * BBLK;
                 double* w = reinterpret_cast<double*>(blk);
                 w[lu] = P.bw[bi]; w[TN + lu] = P.bw[nbw + bi]; w[2 * TN + lu] = P.bw[2 * nbw + bi];
                 blk[size_t(TN) * 24 + lu] = P.bkind[bi];
             }
         }
     }
+    };   // process_range
+    {
+        const unsigned hw = plan_threads();
+        const long nranges = std::max<long>(1, std::min<long>(P.ntiles, P.ntiles < 64 ? 1 : 8L * hw));
+        std::vector<TileRange> ranges(nranges);
+        for (long r = 0; r < nranges; r++) { ranges[r].t0 = P.ntiles * r / nranges; ranges[r].t1 = P.ntiles * (r + 1) / nranges; }
+        std::atomic<long> next(0);
+        auto worker = [&]() {
+            for (long r = next.fetch_add(1); r < nranges; r = next.fetch_add(1)) {
+                try { process_range(ranges[r]); }
+                catch (const std::exception& ex) { ranges[r].error = ex.what(); if (ranges[r].error.empty()) ranges[r].error = "error"; }
+            }
+        };
+        const unsigned nthreads = unsigned(std::min<long>(hw, nranges));
+        std::vector<std::future<void>> pool;
+        for (unsigned k = 1; k < nthreads; k++) pool.push_back(std::async(std::launch::async, worker));
+        worker();
+        for (auto& f : pool) f.get();
+        for (const TileRange& C : ranges) if (!C.error.empty()) throw std::runtime_error(C.error);     // the first failing range, as a serial pass would
+        // lay the ranges end to end
+        for (const TileRange& C : ranges)
+            for (long t = C.t0; t < C.t1; t++) {
+                P.halo_off[t + 1] = P.halo_off[t] + C.nhalo[t - C.t0];
+                P.slot_off[t + 1] = P.slot_off[t] + C.rounds[t - C.t0];
+                P.bslot_off[t + 1] = P.bslot_off[t] + C.brounds[t - C.t0];
+            }
+        P.halo_ids.resize(size_t(P.halo_off[P.ntiles]));
+        P.slots.resize(size_t(P.slot_off[P.ntiles]) * BLK);
+        P.bslots.resize(size_t(P.bslot_off[P.ntiles]) * BBLK);
+        next.store(0);
+        auto copier = [&]() {
+            for (long r = next.fetch_add(1); r < nranges; r = next.fetch_add(1)) {
+                TileRange& C = ranges[r];
+                if (!C.halo.empty()) memcpy(P.halo_ids.data() + P.halo_off[C.t0], C.halo.data(), C.halo.size() * sizeof(int));
+                if (!C.slots.empty()) memcpy(P.slots.data() + size_t(P.slot_off[C.t0]) * BLK, C.slots.data(), C.slots.size());
+                if (!C.bslots.empty()) memcpy(P.bslots.data() + size_t(P.bslot_off[C.t0]) * BBLK, C.bslots.data(), C.bslots.size());
+                std::vector<unsigned char>().swap(C.slots); std::vector<unsigned char>().swap(C.bslots); std::vector<int>().swap(C.halo);
+            }
+        };
+        pool.clear();
+        for (unsigned k = 1; k < nthreads; k++) pool.push_back(std::async(std::launch::async, copier));
+        copier();
+        for (auto& f : pool) f.get();
+        for (const TileRange& C : ranges) {
+            P.cut_edges += C.cut_edges; P.used_slots += C.used_slots;
+            P.max_halo = std::max(P.max_halo, C.max_halo); P.max_rounds = std::max(P.max_rounds, C.max_rounds);
+            P.oversize = P.oversize || C.oversize;
+        }
+    }
+    clk.lap("tile rounds");
     // fixed-stride tile headers (+ halo ids) for the pipelined stage kernel
     P.hpad = (P.max_halo + 3) & ~3;
     P.hdr_stride = 32 + 4 * P.hpad;
@@ -480,6 +587,7 @@ long check_colouring(const LevelPlan& P) {
 }
 
 void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const LevelPlan& Pf, const LevelPlan& Pc, TransferPlan& T) {
+    PhaseClock clk;
     T = TransferPlan();
     const long nf = fine.nel;
     const long nf_owned = fine.n_owned >= 0 ? fine.n_owned : fine.nel;
@@ -499,6 +607,7 @@ void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const L
         std::vector<long> pos(T.child_off.begin(), T.child_off.end() - 1);
         for (long i : by_gid) if (restricts(i)) T.child_ids[pos[Pc.new_of_old[fine.mg[i]]]++] = int(Pf.new_of_old[i]);
     }
+    clk.lap("restrict operator");
     // prolong (owned fine nodes only)
     T.parent.assign(Pf.npad, -1);
     T.idist_own.assign(Pf.npad, 0.0);
@@ -535,6 +644,7 @@ void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const L
             T.ent_src[o] = int(Pc.new_of_old[node_is_b ? p : q]);
         }
     }
+    clk.lap("prolong operator");
 }
 
 

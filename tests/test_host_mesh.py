@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import mgcfd_b200 as M
-from conftest import GOLDEN_CASES, GOLDEN_SPECS, load_golden, mesh_levels
+from conftest import GOLDEN_CASES, GOLDEN_SPECS, ROOT, load_golden, mesh_levels
 from oracle.loader import HERE as ORACLE_DIR
 from oracle.loader import Reference, reference_available
 
@@ -244,3 +244,18 @@ def test_transfer_operators_reproduce_the_oracle_transfers(kind, dims, variant, 
         ok = np.isfinite(want_f)                   # nodes without an internal edge are 0/0 in the reference (and here)
         assert np.array_equal(np.isfinite(got_f), ok)
         assert np.all(linf_rel(np.where(ok, got_f, 0.0), np.where(ok, want_f, 0.0)) < 1e-14)
+
+
+def test_plan_does_not_depend_on_the_number_of_host_threads():
+    """The preprocessing runs tile ranges on a pool of host threads; the bytes handed to the device must not depend on it."""
+    import subprocess, sys, json
+    code = ("import sys, json; sys.path.insert(0, %r); import mgcfd_b200 as M\n"
+            "m = M.Mesh.generate(M.GEN_TET_BOX, [[45, 41, 37]])\n"
+            "print(json.dumps([M.plan_level(m, 0, tile_nodes=128, flux_mode=fm)[0]['plan_hash'] for fm in (0, 1)]))\n") % ROOT
+    out = []
+    for threads in ("1", "3", "64"):
+        env = dict(os.environ, MGCFD_PLAN_THREADS=threads)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr
+        out.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert out[0] == out[1] == out[2] and out[0][0] != out[0][1]

@@ -21,6 +21,7 @@ namespace {
 struct Csr {
     std::vector<long> off;
     std::vector<int> nbr;
+    std::vector<int> eid;    // edge index of every entry (ascending per node)
 };
 
 // host threads the preprocessing may use: hardware concurrency, capped by MGCFD_PLAN_THREADS (1 = serial; the result never depends on it)
@@ -28,6 +29,17 @@ unsigned plan_threads() {
     unsigned hw = std::max(1u, std::thread::hardware_concurrency());
     if (const char* e = getenv("MGCFD_PLAN_THREADS")) { const int v = atoi(e); if (v >= 1) hw = std::min<unsigned>(hw, unsigned(v)); }
     return hw;
+}
+
+// f(i0, i1) over [0, n) in contiguous pieces on the preprocessing threads
+template <class F>
+void parallel_ranges(long n, long grain, F f) {
+    const long pieces = std::max<long>(1, std::min<long>(plan_threads(), n / std::max<long>(grain, 1)));
+    if (pieces <= 1) { f(0L, n); return; }
+    std::vector<std::future<void>> pool;
+    for (long k = 1; k < pieces; k++) pool.push_back(std::async(std::launch::async, [=] { f(n * k / pieces, n * (k + 1) / pieces); }));
+    f(0L, n / pieces);
+    for (auto& x : pool) x.get();
 }
 
 // MGCFD_PLAN_TIMING=1: wall time of the phases of build_level_plan on stderr (setup cost of large meshes)
@@ -49,11 +61,12 @@ Csr adjacency_old(const HostLevel& L) {
     for (long e = 0; e < L.nI; e++) { g.off[L.edges[e].a + 1]++; g.off[L.edges[e].b + 1]++; }
     for (long i = 0; i < L.nel; i++) g.off[i + 1] += g.off[i];
     g.nbr.resize(g.off[L.nel]);
+    g.eid.resize(g.off[L.nel]);
     std::vector<long> pos(g.off.begin(), g.off.end() - 1);
     for (long e = 0; e < L.nI; e++) {
         const long a = L.edges[e].a, b = L.edges[e].b;
-        g.nbr[pos[a]++] = int(b);
-        g.nbr[pos[b]++] = int(a);
+        g.eid[pos[a]] = int(e); g.nbr[pos[a]++] = int(b);
+        g.eid[pos[b]] = int(e); g.nbr[pos[b]++] = int(a);
     }
     return g;
 }
@@ -260,9 +273,8 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
     for (long i = n; i < nall; i++) { P.new_of_old[i] = P.npad_owned + (i - n); P.old_of_new[P.npad_owned + (i - n)] = i; }
     P.tile_nown.assign(P.ntiles, 0);
     {
-        std::vector<long> byseq(n);
-        std::iota(byseq.begin(), byseq.end(), 0L);
-        std::sort(byseq.begin(), byseq.end(), [&](long x, long y) { return seq[x] < seq[y]; });
+        std::vector<long> byseq(n);                  // seq is a permutation of 0..n-1: its inverse lists the nodes in sequence
+        for (long i = 0; i < n; i++) byseq[seq[i]] = i;
         for (long i : byseq) {
             const long t = tile_of[i];
             const long id = t * TN + P.tile_nown[t]++;
@@ -276,11 +288,13 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
     clk.lap("renumbering");
     // ---- 2. flat edge list + CSR by node in new ids (entries in ascending original edge index) ------
     P.ea.resize(L.nI); P.eb.resize(L.nI); P.ew.resize(3 * L.nI);
-    for (long e = 0; e < L.nI; e++) {
-        P.ea[e] = int(P.new_of_old[L.edges[e].a]);
-        P.eb[e] = int(P.new_of_old[L.edges[e].b]);
-        P.ew[e] = L.edges[e].x; P.ew[L.nI + e] = L.edges[e].y; P.ew[2 * L.nI + e] = L.edges[e].z;
-    }
+    parallel_ranges(L.nI, 1 << 16, [&](long e0, long e1) {
+        for (long e = e0; e < e1; e++) {
+            P.ea[e] = int(P.new_of_old[L.edges[e].a]);
+            P.eb[e] = int(P.new_of_old[L.edges[e].b]);
+            P.ew[e] = L.edges[e].x; P.ew[L.nI + e] = L.edges[e].y; P.ew[2 * L.nI + e] = L.edges[e].z;
+        }
+    });
     const long nbw = L.nB + L.nW;
     P.bnode.resize(nbw); P.bkind.resize(nbw); P.bw.resize(3 * nbw);
     for (long k = 0; k < nbw; k++) {
@@ -289,20 +303,30 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         P.bkind[k] = uint8_t(k < L.nB ? 1 : 2);
         P.bw[k] = e.x; P.bw[nbw + k] = e.y; P.bw[2 * nbw + k] = e.z;
     }
+    // CSR by node in new ids: the old-id adjacency `g` (entries in ascending edge index) carried over node by node; bit 31 of an
+    // entry marks that this node is the edge's `b` end
     P.adj_off.assign(P.npad + 1, 0);
-    for (long e = 0; e < L.nI; e++) { P.adj_off[P.ea[e] + 1]++; P.adj_off[P.eb[e] + 1]++; }
-    for (long i = 0; i < P.npad; i++) P.adj_off[i + 1] += P.adj_off[i];
+    for (long i = 0; i < P.npad; i++) {
+        const long on = P.old_of_new[i];
+        P.adj_off[i + 1] = P.adj_off[i] + (on >= 0 ? g.off[on + 1] - g.off[on] : 0);
+    }
     P.adj_nbr.resize(2 * L.nI);
     std::vector<int> adj_eid(2 * L.nI);
-    {
-        std::vector<long> pos(P.adj_off.begin(), P.adj_off.end() - 1);
-        for (long e = 0; e < L.nI; e++) {
-            const int a = P.ea[e], b = P.eb[e];
-            long pa = pos[a]++, pb = pos[b]++;
-            P.adj_nbr[pa] = b;                       adj_eid[pa] = int(e);
-            P.adj_nbr[pb] = int(uint32_t(a) | 0x80000000u); adj_eid[pb] = int(e);
+    parallel_ranges(P.npad, 1 << 14, [&](long i0, long i1) {
+        for (long i = i0; i < i1; i++) {
+            const long on = P.old_of_new[i];
+            if (on < 0) continue;
+            long o = P.adj_off[i];
+            for (long k = g.off[on]; k < g.off[on + 1]; k++, o++) {
+                const int e = g.eid[k];
+                // the node is the edge's `b` end (a self-loop lists its `a` entry first)
+                const bool is_b = L.edges[e].a != on || (k > g.off[on] && g.eid[k - 1] == e);
+                const int nb = int(P.new_of_old[g.nbr[k]]);
+                P.adj_nbr[o] = is_b ? int(uint32_t(nb) | 0x80000000u) : nb;
+                adj_eid[o] = e;
+            }
         }
-    }
+    });
     // boundary/wall edges per node (CSR, original order)
     std::vector<long> bn_off(P.npad + 1, 0);
     for (long k = 0; k < nbw; k++) bn_off[P.bnode[k] + 1]++;

@@ -131,3 +131,24 @@ def test_partition_contract_across_two_gloo_ranks():
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_distributed_plans_are_unchanged(tmp_path):
+    """Regression guard (host only): level plans and transfer operators of every rank of 2 / 3 / 8-rank partitions, hashed by
+    tools/plan_hash_harness.cpp, equal the recorded hashes -- serial or threaded.  A deliberate change of the plan format
+    updates tests/golden/plan_hashes.txt (see the harness header)."""
+    import shutil
+    import subprocess
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "mg-cfd-app-plain_b200", "csrc")
+    exe = str(tmp_path / "plan_hash")
+    cmd = ["g++", "-O2", "-std=c++17", "-pthread", "-ffp-contract=off", "-fno-math-errno", "-I" + src, "-o", exe,
+           os.path.join(root, "tools", "plan_hash_harness.cpp")] + [os.path.join(src, f) for f in ("plan.cpp", "partition.cpp", "mesh_gen.cpp", "mesh_io.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    want = open(os.path.join(root, "tests", "golden", "plan_hashes.txt")).read().split()
+    for threads in ("1", "8"):
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=600, env=dict(os.environ, MGCFD_PLAN_THREADS=threads))
+        assert out.returncode == 0 and out.stdout.split() == want, out.stdout + out.stderr

@@ -42,7 +42,12 @@ int mgcfd_generate_partition_plan(int kind, int levels, const long* dims, const 
  * ONE kernel per rank that stores straight into the peers' memory over NVLink (CUDA IPC windows) and hand-shakes through
  * system-scope flags, instead of a packing kernel + NCCL calls.  prepare: allocates this rank's window, returns its 64-byte
  * cudaIpcMemHandle and a table of offsets (mgcfd_dist_p2p_table_len longs); the launcher all-gathers handles and tables in
- * rank order; attach: maps the peers' windows and switches the data path.  One process per GPU, all GPUs peer-accessible. */
+ * rank order; attach: maps the peers' windows and switches the data path.  One process per GPU, all GPUs peer-accessible.
+ * EXPERIMENTAL, off by default -- environment MGCFD_P2P_FUSED=1 on every rank: the Runge-Kutta stage kernels exchange their halo rows
+ * themselves (stores into the peers' record buffers from the kernel that computes the rows, signal when the grid is done, wait
+ * at the start of the next kernel that reads ghosts): no exchange kernel between the stages.  The offset table then also carries
+ * the IPC handles of the record buffers (mgcfd_dist_p2p_table_len grows accordingly; nothing changes for the launcher).
+ * Implemented and reviewed, not yet run on hardware. */
 long mgcfd_dist_p2p_table_len(mgcfd_ctx* ctx);
 int mgcfd_dist_p2p_prepare(mgcfd_ctx* ctx, char handle[64], long* table, long table_cap);
 int mgcfd_dist_p2p_attach(mgcfd_ctx* ctx, const char* handles, const long* tables, long table_len);

@@ -80,6 +80,14 @@ struct Level {
     long nsend = 0, nghost = 0, n_owned = 0;
     int* d_send_idx = nullptr; double *sendbuf = nullptr, *recvtmp = nullptr;
     P2PPeer* d_peers = nullptr; int npeers = 0;    // p2p: peers of this level
+    // in-kernel halo exchange (MGCFD_P2P_FUSED): node -> (peer, remote row) CSR, per-tile flags, the peers' record buffers
+    std::vector<int> h_send_idx;                   // send list in device numbering (host copy)
+    std::vector<P2PPeer> h_peers;                  // host copy of d_peers
+    int *d_tgt_off = nullptr, *d_tgt_peer = nullptr, *d_tgt_row = nullptr;
+    unsigned char* d_tile_sends = nullptr;
+    double** d_peer_bufs[3] = {nullptr, nullptr, nullptr};     // [npeers] peers' buf[b]
+    std::vector<void*> peer_buf_maps;              // IPC mappings to close
+    int pipe_grid_dist = 0;
     double* V(int i) const { return buf[i]; }
 };
 
@@ -105,6 +113,7 @@ struct Dist {
     long exchanges = 0;
     // direct peer-to-peer exchange (CUDA IPC windows; mgcfd_dist_p2p_prepare / _attach): replaces NCCL on the data path
     bool p2p = false, want_graph = false;
+    bool fused = false;                        // MGCFD_P2P_FUSED=1: the stage kernels exchange their halo rows themselves
     unsigned char* win = nullptr;              // my window: flags[64] | red[2][64][8] | staging per level (2 parities)
     size_t win_bytes = 0;
     std::vector<long> stage_off;               // per level: offset (in doubles, from the window's staging base) of parity 0; parity 1 follows
@@ -328,23 +337,46 @@ int launch_stage_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     k_stage<TN, SCATTER, FUSED><<<(unsigned)v.ntiles, TN, v.smem_bytes, c->stream>>>(a);
     return post_launch(c);
 }
-template <int TN, bool SCATTER>
+template <int TN, bool SCATTER, bool DIST = false>
 int launch_pipe_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
+    const int grid = DIST ? v.pipe_grid_dist : v.pipe_grid;
     if (c->opt.no_pdl) {
-        k_stage_pipe<TN, SCATTER><<<(unsigned)v.pipe_grid, TN, v.pipe_smem, c->stream>>>(a);
+        k_stage_pipe<TN, SCATTER, DIST><<<(unsigned)grid, TN, v.pipe_smem, c->stream>>>(a);
         return post_launch(c);
     }
     // programmatic dependent launch: this kernel may start (barrier set-up, header + edge-stream prefetch: static data) while
     // its predecessor in the stream drains; it synchronises with griddepcontrol.wait before reading node state
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)v.pipe_grid); cfg.blockDim = dim3(TN); cfg.dynamicSmemBytes = v.pipe_smem; cfg.stream = c->stream;
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(TN); cfg.dynamicSmemBytes = v.pipe_smem; cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, k_stage_pipe<TN, SCATTER>, a));
+    CK(cudaLaunchKernelEx(&cfg, k_stage_pipe<TN, SCATTER, DIST>, a));
     return post_launch(c);
+}
+// in-kernel halo exchange: occupancy and shared-memory attribute of the DIST instantiation (its register count differs)
+template <int TN, bool SCATTER>
+int setup_pipe_dist_t(mgcfd_ctx* c, Level& v) {
+    CK(cudaFuncSetAttribute(k_stage_pipe<TN, SCATTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(v.pipe_smem, 48 * 1024)));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stage_pipe<TN, SCATTER, true>, TN, v.pipe_smem));
+    if (per_sm < 1) { g_err = "the in-kernel exchange variant of the stage kernel does not fit an SM"; return MGCFD_ERR_ARG; }
+    v.pipe_grid_dist = (int)std::min<long>(v.ntiles, (long)per_sm * c->num_sms);
+    return MGCFD_OK;
+}
+int setup_pipe_dist(mgcfd_ctx* c, Level& v) {
+    const bool sc = v.plan.scatter;
+    if (v.TN == 128) return sc ? setup_pipe_dist_t<128, true>(c, v) : setup_pipe_dist_t<128, false>(c, v);
+    if (v.TN == 256) return sc ? setup_pipe_dist_t<256, true>(c, v) : setup_pipe_dist_t<256, false>(c, v);
+    return sc ? setup_pipe_dist_t<512, true>(c, v) : setup_pipe_dist_t<512, false>(c, v);
+}
+int launch_stage_dist(mgcfd_ctx* c, Level& v, const StageArgs& a) {
+    const bool sc = v.plan.scatter;
+    if (v.TN == 128) return sc ? launch_pipe_t<128, true, true>(c, v, a) : launch_pipe_t<128, false, true>(c, v, a);
+    if (v.TN == 256) return sc ? launch_pipe_t<256, true, true>(c, v, a) : launch_pipe_t<256, false, true>(c, v, a);
+    return sc ? launch_pipe_t<512, true, true>(c, v, a) : launch_pipe_t<512, false, true>(c, v, a);
 }
 // persistent grid of the pipelined kernel: as many CTAs as fit on the device at once (occupancy API), never more than tiles
 template <int TN, bool SCATTER>
@@ -505,6 +537,20 @@ int smooth_fused(mgcfd_ctx* c, int l) {
             a.res = v.res;
             a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
         }
+        if (c->dist.fused && v.npeers > 0) {
+            // the stage kernel stores the rows its peers hold as ghosts itself and signals them; the next stage kernel (or the
+            // wait kernel after the last stage) waits for the peers' signal: no exchange kernel between the stages
+            Dist& d = c->dist;
+            const int b = (a.vout == v.buf[0]) ? 0 : (a.vout == v.buf[1] ? 1 : 2);
+            a.tile_sends = v.d_tile_sends; a.tgt_off = v.d_tgt_off; a.tgt_peer = v.d_tgt_peer; a.tgt_row = v.d_tgt_row;
+            a.peer_out = v.d_peer_bufs[b]; a.peers = v.d_peers; a.npeers = v.npeers;
+            a.op_counter = d.d_op; a.ticket = d.d_ticket; a.my_flags = (const unsigned long long*)d.win;
+            CKRC(launch_stage_dist(c, v, a));
+            stage_tm.reset();
+            d.exchanges++;
+            if (j == MGCFD_RK - 1) { k_p2p_wait<<<1, 64, 0, c->stream>>>(v.d_peers, v.npeers, d.d_op, (const unsigned long long*)d.win); CKRC(post_launch(c)); }
+            continue;
+        }
         CKRC(launch_stage(c, v, a, true));
         stage_tm.reset();
         CKRC(dist_exchange_records(c, l, a.vout));
@@ -574,7 +620,9 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
 void free_level(Level& v) {
     void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
-                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers};
+                    v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers,
+                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_bufs[0], v.d_peer_bufs[1], v.d_peer_bufs[2]};
+    for (void* m : v.peer_buf_maps) if (m) cudaIpcCloseMemHandle(m);     // peers' record buffers (in-kernel exchange)
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -767,6 +815,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
             std::vector<int> sidx(v.nsend);
             for (long k = 0; k < v.nsend; k++) sidx[k] = (int)P.new_of_old[v.send_list[k]];
             CKRC(dev_upload(&v.d_send_idx, sidx, s));
+            v.h_send_idx = sidx;
             CK(cudaMalloc((void**)&v.sendbuf, sizeof(double) * 8 * std::max<long>(v.nsend, 1)));
             CK(cudaMalloc((void**)&v.recvtmp, sizeof(double) * 5 * std::max<long>(v.nghost, 1)));
         }
@@ -1278,12 +1327,19 @@ int mgcfd_upload_partition(mgcfd_ctx* c, int levels, int mesh_variant, const voi
 }
 // ---- direct peer-to-peer data path (CUDA IPC) -------------------------------------------------------------------------------
 // table layout (longs): [0] = levels, then per level: stage_off (doubles), nghost, recv_off[0..nranks]
-long mgcfd_dist_p2p_table_len(mgcfd_ctx* c) { return c ? 1 + (long)c->levels * (2 + c->dist.nranks + 1) : -1; }
+// MGCFD_P2P_FUSED=1 (every rank alike): the stage kernels exchange their halo rows themselves; the table then also
+// carries, per level, the first ghost row and the CUDA IPC handles of the three record buffers (8 longs each)
+static bool want_fused() { const char* e = getenv("MGCFD_P2P_FUSED"); return e && e[0] == '1'; }
+static const long FUSED_PER_LEVEL = 1 + 3 * 8;
+long mgcfd_dist_p2p_table_len(mgcfd_ctx* c) {
+    if (!c) return -1;
+    return 1 + (long)c->levels * (2 + c->dist.nranks + 1) + (want_fused() ? (long)c->levels * FUSED_PER_LEVEL : 0);
+}
 int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long table_cap) {
     if (!c || !handle || !table) { g_err = "null argument"; return MGCFD_ERR_ARG; }
     if (!c->dist.active || !c->finalized) { g_err = "mgcfd_dist_p2p_prepare needs a finalized distributed context"; return MGCFD_ERR_ARG; }
     Dist& d = c->dist;
-    const long need = 1 + (long)c->levels * (2 + d.nranks + 1);
+    const long need = mgcfd_dist_p2p_table_len(c);
     if (table_cap < need) { g_err = "table too small"; return MGCFD_ERR_ARG; }
     CK(cudaSetDevice(c->opt.device));
     if (!d.win) {
@@ -1308,6 +1364,16 @@ int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long tabl
         table[k++] = d.stage_off[l]; table[k++] = c->L[l].nghost;
         for (int p = 0; p <= d.nranks; p++) table[k++] = c->L[l].recv_off[p];
     }
+    if (want_fused())
+        for (int l = 0; l < c->levels; l++) {
+            table[k++] = c->L[l].ncomp;
+            for (int b = 0; b < 3; b++) {
+                cudaIpcMemHandle_t hb;
+                CK(cudaIpcGetMemHandle(&hb, c->L[l].buf[b]));
+                memcpy(&table[k], &hb, 64);
+                k += 8;
+            }
+        }
     return MGCFD_OK;
 }
 // handles: nranks x 64 bytes, tables: nranks x table_len longs, both in rank order (what every rank's prepare returned)
@@ -1352,6 +1418,50 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
         v.npeers = (int)peers.size();
         if (v.npeers > 64) { g_err = "too many peers"; return MGCFD_ERR_ARG; }
         CKRC(dev_upload(&v.d_peers, peers, c->stream));
+        v.h_peers = peers;
+    }
+    if (want_fused()) {
+        const long base_len = 1 + (long)c->levels * per_level;
+        if (table_len != base_len + (long)c->levels * FUSED_PER_LEVEL) { g_err = "MGCFD_P2P_FUSED must be set alike on every rank"; return MGCFD_ERR_COMM; }
+        for (int l = 0; l < c->levels; l++) {
+            Level& v = c->L[l];
+            if (!v.pipe) { g_err = "the in-kernel exchange needs the pipelined stage kernel on every level"; return MGCFD_ERR_ARG; }
+            if (v.npeers == 0) continue;
+            const std::vector<P2PPeer>& peers = v.h_peers;
+            // node -> (peer, row in the peer's record arrays): my k-th row for peer p is its ghost row ncomp_p + recv_off_p[me] + k
+            std::vector<int> cnt(v.ncomp + 1, 0), tpeer, trow;
+            std::vector<double*> pbuf[3];
+            for (int pi = 0; pi < v.npeers; pi++) for (long k = 0; k < peers[pi].nsend; k++) cnt[v.h_send_idx[peers[pi].send0 + k] + 1]++;
+            for (long i = 0; i < v.ncomp; i++) cnt[i + 1] += cnt[i];
+            tpeer.resize(cnt[v.ncomp]); trow.resize(cnt[v.ncomp]);
+            std::vector<int> pos(cnt.begin(), cnt.end() - 1);
+            std::vector<unsigned char> tile_sends(v.ntiles, 0);
+            for (int pi = 0; pi < v.npeers; pi++) {
+                const int p = peers[pi].rank;
+                const long* tp = tables + (size_t)p * table_len + 1 + (size_t)l * per_level;
+                const long* fp = tables + (size_t)p * table_len + base_len + (size_t)l * FUSED_PER_LEVEL;
+                const long p_ncomp = fp[0], p_recv_me = tp[2 + d.rank];
+                for (long k = 0; k < peers[pi].nsend; k++) {
+                    const int node = v.h_send_idx[peers[pi].send0 + k];
+                    if (node < 0 || node >= v.ncomp) { g_err = "send list entry is not an owned row"; return MGCFD_ERR_ARG; }
+                    tpeer[pos[node]] = pi; trow[pos[node]] = (int)(p_ncomp + p_recv_me + k); pos[node]++;
+                    tile_sends[node / v.TN] = 1;
+                }
+                for (int b = 0; b < 3; b++) {
+                    cudaIpcMemHandle_t hb;
+                    memcpy(&hb, fp + 1 + 8 * b, 64);
+                    void* m = nullptr;
+                    CK(cudaIpcOpenMemHandle(&m, hb, cudaIpcMemLazyEnablePeerAccess));
+                    v.peer_buf_maps.push_back(m);
+                    pbuf[b].push_back((double*)m);
+                }
+            }
+            CKRC(dev_upload(&v.d_tgt_off, cnt, c->stream)); CKRC(dev_upload(&v.d_tgt_peer, tpeer, c->stream)); CKRC(dev_upload(&v.d_tgt_row, trow, c->stream));
+            CKRC(dev_upload(&v.d_tile_sends, tile_sends, c->stream));
+            for (int b = 0; b < 3; b++) CKRC(dev_upload(&v.d_peer_bufs[b], pbuf[b], c->stream));
+            CKRC(setup_pipe_dist(c, v));
+        }
+        d.fused = true;
     }
     CK(cudaStreamSynchronize(c->stream));
     d.p2p = true;

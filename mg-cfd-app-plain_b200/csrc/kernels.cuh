@@ -161,6 +161,22 @@ __device__ __forceinline__ void wall_flux_acc(const Rec& B, double x, double y, 
 //            written once; on the last stage residual (validation.cpp:77-89), RMS partials (:91-105) and the validity
 //            check (:107-138) ride along.  !FUSED (granular API): fluxes[node] += total.
 // ------------------------------------------------------------------------------------------------------
+// ---- peers of a level in a multi-GPU run (direct peer-to-peer data plane, see k_p2p_exchange below) ----
+struct P2PPeer {                   // one entry per peer of a level
+    int rank;
+    long send0, nsend;             // slice of the level's send list
+    long recv0, nrecv;             // slice of my ghost rows filled by this peer
+    double* dst[2];                // peer staging (parity 0/1) at the offset where my rows land
+    unsigned long long* flag;      // &peer_window.flags[my rank]
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 // fixed-stride per-tile header (hdr_stride bytes per tile): what a CTA needs to know about a tile before it can fetch it
 struct TileHdr {
     int rounds, nh, brounds, pad;
@@ -193,6 +209,18 @@ struct StageArgs {
     const int* old_of_new;
     unsigned long long stage_seq;
     int mask;              // bit0 internal, bit1 boundary, bit2 wall
+    // in-kernel halo exchange (DIST instantiation of k_stage_pipe only, MGCFD_P2P_FUSED): the kernel stores the records of
+    // nodes other ranks hold as ghosts straight into those ranks' copies of vout, signals them when the whole grid is done, and
+    // waits for their previous signal before it reads a ghost row
+    const unsigned char* tile_sends;     // [ntiles] != 0: the tile owns nodes on a send list
+    const int* tgt_off;                  // [rows + 1] node -> its targets
+    const int* tgt_peer;                 // target: index into peer_out / peers ...
+    const int* tgt_row;                  // ... and the node's row in that peer's record arrays
+    double* const* peer_out;             // [npeers] the peers' buffers that play the role of vout
+    const P2PPeer* peers; int npeers;
+    unsigned long long* op_counter;      // operations completed so far (identical on every rank)
+    unsigned int* ticket;
+    const unsigned long long* my_flags;  // my window's flags: latest operation completed by each source rank
 };
 
 // A slot's `other` field is the byte offset of logical chunk 0 of the other endpoint's row in the shared record buffer,
@@ -306,11 +334,16 @@ __device__ __forceinline__ double div_rk(double x, double d, double rd) {
     return __fma_rn(__fma_rn(-d, q, x), rd, q);
 }
 // phase 3 of a fused stage for node gid: time_step + record + validity + residual; returns the five squared residuals in q
-__device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5]) {
+template <bool DIST = false>
+__device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5], bool sends = false) {
     const long S = a.stride;
     const double factor = div_rk(sf, a.rk_div, a.rk_rcp);     // == sf / rk_div, the true divide of cfd_loops.cpp:243
     const double n0 = o[0] + factor * f.r, n1 = o[1] + factor * f.mx, n2 = o[2] + factor * f.my, n3 = o[3] + factor * f.mz, n4 = o[4] + factor * f.e;
-    store_rec(a.vout, gid, make_rec(n0, n1, n2, n3, n4));
+    const Rec nrec = make_rec(n0, n1, n2, n3, n4);
+    store_rec(a.vout, gid, nrec);
+    if (DIST && sends) {      // the same record into the ghost row every other holder keeps of this node (over NVLink)
+        for (int k = a.tgt_off[gid]; k < a.tgt_off[gid + 1]; k++) store_rec(a.peer_out[a.tgt_peer[k]], a.tgt_row[k], nrec);
+    }
     if (a.bad_key) {
         // check_for_invalid_variables (validation.cpp:107-138): first offending cell of the first offending stage
         int reason = 0;
@@ -424,7 +457,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int RING = 2;     // ring entries (each `chunk_rounds` round blocks)
 
-template <int TN, bool SCATTER>
+template <int TN, bool SCATTER, bool DIST = false>
 __global__ void __launch_bounds__(TN, (TN <= 128 ? 4 : (TN <= 256 ? 2 : 1)))
 k_stage_pipe(const StageArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -503,6 +536,16 @@ k_stage_pipe(const StageArgs a) {
     __syncthreads();
     if (t == 0) produce(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (DIST) {
+        // ghost rows of vin were written by their owners' previous stage kernel: wait until every peer of the level has signalled the
+        // operation this rank completed last (operation numbers advance alike on all ranks)
+        if (t < a.npeers) {
+            const unsigned long long g = *(volatile unsigned long long*)a.op_counter;
+            const unsigned long long* f = a.my_flags + a.peers[t].rank;
+            while (ld_acquire_sys(f) < g) { __nanosleep(32); }
+        }
+        __syncthreads();
+    }
     copy_recs(0);
     const bool first_stage = (a.vold == a.vin);
     // the visit's global minimum dt (k_min_dt, the previous kernel of a first stage): one load per CTA, not one per tile
@@ -559,9 +602,33 @@ k_stage_pipe(const StageArgs a) {
         double sf = vol_or_sf;
         if (first_stage) { sf = step_factor_of(a, min_dt, vol_or_sf, me.s); a.sf[gid] = sf; }
         double q[5] = {0, 0, 0, 0, 0};
-        fused_update(a, gid, sf, o, f, q);
+        fused_update<DIST>(a, gid, sf, o, f, q, DIST && a.tile_sends[tile] != 0);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
         __syncthreads();      // record buffer (it & 1), header buffer (it % 3), acc and ws are free again
+    }
+    if (DIST) {
+        // signal: every CTA's remote stores are ordered before its thread 0's system-scope fence (the barrier at the end of the last
+        // tile); the last CTA to arrive publishes the operation number in every peer's window -- as k_p2p_exchange does
+        if (t == 0) {
+            __threadfence_system();
+            if (atomicInc(a.ticket, gridDim.x - 1) == gridDim.x - 1) {
+                __threadfence_system();
+                const unsigned long long g = *(volatile unsigned long long*)a.op_counter + 1;
+                for (int p = 0; p < a.npeers; p++) st_release_sys(a.peers[p].flag, g);
+                *a.op_counter = g;
+            }
+        }
+    }
+}
+
+// after the last stage kernel of a smoothing visit with the in-kernel exchange: wait for the peers' signal of that stage, so that
+// whatever runs next on the stream (restrict, prolong, the next visit) finds the ghost rows up to date
+__global__ void k_p2p_wait(const P2PPeer* __restrict__ peers, int npeers, const unsigned long long* op_counter, const unsigned long long* my_flags) {
+    const int t = threadIdx.x;
+    if (t < npeers) {
+        const unsigned long long g = *(volatile const unsigned long long*)op_counter;
+        const unsigned long long* f = my_flags + peers[t].rank;
+        while (ld_acquire_sys(f) < g) { __nanosleep(32); }
     }
 }
 
@@ -884,21 +951,6 @@ __global__ void k_unpack_soa5(double* __restrict__ soa, long stride, long row0, 
 //   3. WAIT  : every block spins (ld.acquire.sys) until flags[src] >= g for every source rank of this level;
 //   4. UNPACK: copies its share of the staging buffer into the ghost rows.
 // The grid is capped to what is resident at once (spinning blocks must not keep unscheduled ones from running).
-struct P2PPeer {                   // one entry per peer of a level
-    int rank;
-    long send0, nsend;             // slice of the level's send list
-    long recv0, nrecv;             // slice of my ghost rows filled by this peer
-    double* dst[2];                // peer staging (parity 0/1) at the offset where my rows land
-    unsigned long long* flag;      // &peer_window.flags[my rank]
-};
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 // width = doubles per node in the message (8: records, 5: residuals).  src_is_soa: residual planes (stride) instead of record rows.
 template <int WIDTH, bool SOA>
 __global__ void k_p2p_exchange(const double* __restrict__ src, long stride, const int* __restrict__ send_idx, const P2PPeer* __restrict__ peers, int npeers,

@@ -19,3 +19,16 @@ def test_distributed_matches_single_gpu(nranks):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "dist_check PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.skipif(os.environ.get("MGCFD_TEST_FUSED") != "1", reason="experimental in-kernel halo exchange: opt in with MGCFD_TEST_FUSED=1")
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_in_kernel_halo_exchange_matches_single_gpu(nranks):
+    """MGCFD_P2P_FUSED=1: the stage kernels store their halo rows into the peers' buffers themselves (include/mgcfd_dist.h)."""
+    import torch
+    if torch.cuda.device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
+                        "--master-port", str(29620 + nranks), os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, MGCFD_P2P_FUSED="1"))
+    assert r.returncode == 0 and "dist_check PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

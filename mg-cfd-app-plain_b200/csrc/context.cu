@@ -508,6 +508,16 @@ int min_dt_fused(mgcfd_ctx* c, int l) {
     if (c->variant == MGCFD_MESH_FVCORR) return MGCFD_OK;
     Level& v = c->L[l];
     Timed tm(c, K_STEP, l, v.nel);
+    if (c->dist.fused) {
+        // the last block of the reduction kernel all-reduces the minimum over the ranks itself (k_p2p_allreduce's protocol)
+        Dist& d = c->dist;
+        P2PReduce pr;
+        pr.nranks = d.nranks; pr.me = d.rank; pr.red_of_rank = d.d_red_of_rank; pr.flag_of_rank = d.d_flag_of_rank;
+        pr.my_flags = (const unsigned long long*)d.win; pr.my_red = (const double*)(d.win + P2P_FLAGS_BYTES);
+        pr.op_counter = d.d_op; pr.red_counter = d.d_ctr;
+        k_min_dt_p2p<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.vol_root, v.blockmins, c->d_ticket, c->d_minbits, pr);
+        return post_launch(c);
+    }
     k_min_dt<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.vol_root, v.blockmins, c->d_ticket, c->d_minbits);
     CKRC(post_launch(c));
     return dist_allreduce_min(c);

@@ -710,6 +710,74 @@ __global__ void k_min_dt(const double* __restrict__ recs, long n, const double* 
     if (threadIdx.x == 0) *min_bits = (unsigned long long)__double_as_longlong(v);
 }
 
+// k_min_dt for multi-GPU runs with MGCFD_P2P_FUSED: the last block goes on to all-reduce the minimum over the ranks itself -- the body of
+// k_p2p_allreduce (store my value into every rank's window, signal, wait for everybody, combine in rank order) -- so the visit
+// needs no separate reduction kernel; struct P2PReduce carries what k_p2p_allreduce takes as arguments.
+struct P2PReduce {
+    int nranks, me;
+    double* const* red_of_rank;                 // [nranks] window reduction bases
+    unsigned long long* const* flag_of_rank;    // [nranks] &window.flags[me]
+    const unsigned long long* my_flags;
+    const double* my_red;
+    unsigned long long* op_counter;
+    unsigned int* red_counter;
+};
+__global__ void k_min_dt_p2p(const double* __restrict__ recs, long n, const double* __restrict__ vol_root, double* __restrict__ blockmins,
+                           unsigned int* __restrict__ ticket, unsigned long long* __restrict__ min_bits, const P2PReduce pr) {
+    const double BIG = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
+    __shared__ double wmin[32];
+    __shared__ bool last;
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    double val = BIG;
+    if (i < n) val = 0.5 * (vol_root[i] / recs[8 * i + 7]);
+    auto block_min = [&](double v) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = v;
+        __syncthreads();
+        v = (threadIdx.x < (blockDim.x >> 5)) ? wmin[threadIdx.x] : BIG;
+        if (threadIdx.x < 32) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
+        }
+        __syncthreads();
+        return v;      // valid in thread 0
+    };
+    val = block_min(val);
+    if (threadIdx.x == 0) {
+        blockmins[blockIdx.x] = val;
+        __threadfence();
+        last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);     // wraps back to 0 for the next launch
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double v = BIG;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) v = fmin(v, ((volatile double*)blockmins)[b]);
+    v = block_min(v);
+    // all-reduce(min) of the bit pattern over the ranks (positive doubles order like their bits)
+    __shared__ double mine;
+    if (threadIdx.x == 0) mine = v;
+    const int t = threadIdx.x;
+    const unsigned long long g = *(volatile unsigned long long*)pr.op_counter + 1;
+    const int parity = int(*(volatile unsigned int*)pr.red_counter & 1u);
+    __syncthreads();
+    if (t < pr.nranks) {
+        double* slot = pr.red_of_rank[t] + ((size_t)parity * 64 + pr.me) * 8;
+        slot[0] = mine;
+        __threadfence_system();
+        st_release_sys(pr.flag_of_rank[t], g);
+        while (ld_acquire_sys(pr.my_flags + t) < g) { __nanosleep(64); }
+    }
+    __syncthreads();
+    if (t == 0) {
+        const double* base = pr.my_red + (size_t)parity * 64 * 8;
+        unsigned long long m = ~0ull;
+        for (int r = 0; r < pr.nranks; r++) { const unsigned long long x = (unsigned long long)__double_as_longlong(__ldcg(base + r * 8)); m = x < m ? x : m; }
+        *min_bits = m;
+        *pr.op_counter = g; *pr.red_counter += 1;
+    }
+}
 // time_step (cfd_loops.cpp:215-280), granular API
 __global__ void k_time_step(double rk_div, long n, long stride, const double* __restrict__ sf, double* __restrict__ flux,
                             const double* __restrict__ vold, double* __restrict__ v) {

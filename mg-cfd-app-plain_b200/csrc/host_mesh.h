@@ -27,6 +27,7 @@ struct HostLevel {
 struct HostMesh {
     int mesh_variant = 2;
     int size = 1;                  // input.dat `size=`
+    int copies = 1;                // mgcfd_mesh_duplicate: independent copies laid out copy-major on every level
     bool ewt_applied = false;
     std::vector<HostLevel> levels;
 };

@@ -162,6 +162,7 @@ int mgcfd_mesh_duplicate(mgcfd_mesh* m, int count) {
         L = std::move(D);
     }
     m->m.size *= count;
+    m->m.copies *= count;
     return MGCFD_OK;
 }
 

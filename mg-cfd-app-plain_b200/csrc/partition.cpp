@@ -85,8 +85,17 @@ void partition_mesh(const HostMesh& full, int nranks, int rank, LocalMesh& out) 
 
     std::vector<std::vector<int>> owner(nl);
     std::vector<Csr> adj(nl), kids(nl);         // kids[l]: children in level l-1 of the nodes of level l
+    // a mesh duplicated m times (-m, mgcfd_mesh_duplicate: copy-major node numbering on every level) with m a multiple of the
+    // number of ranks is dealt out copy by copy: independent replicas, no halo at all -- the reference's assess-memory protocol
+    // (one mesh copy per thread) across GPUs.  Any other mesh is cut by recursive coordinate bisection.
+    bool whole_copies = full.copies > 1 && full.copies % nranks == 0;
+    for (int l = 0; l < nl && whole_copies; l++) whole_copies = full.levels[l].nel % full.copies == 0;
     for (int l = 0; l < nl; l++) {
-        rcb_owners(full.levels[l], nranks, owner[l]);
+        if (whole_copies) {
+            const long per_copy = full.levels[l].nel / full.copies, copies_per_rank = full.copies / nranks;
+            owner[l].resize(full.levels[l].nel);
+            for (long i = 0; i < full.levels[l].nel; i++) owner[l][i] = int((i / per_copy) / copies_per_rank);
+        } else rcb_owners(full.levels[l], nranks, owner[l]);
         adj[l] = adjacency(full.levels[l]);
         if (l > 0) kids[l] = children(full.levels[l - 1], full.levels[l].nel);
     }

@@ -89,6 +89,24 @@ def test_rank_local_generation_equals_partition_of_the_assembled_mesh(kind, dims
         assert raw["hash"] != M.partition_plan(mesh, nranks, 0, 0)["hash"]
 
 
+@pytest.mark.parametrize("copies,nranks", [(4, 2), (4, 4), (6, 3), (3, 2)])
+def test_duplicated_meshes_are_dealt_out_copy_by_copy(copies, nranks):
+    """-m copies on N ranks with N | m: every rank holds whole copies (no ghosts, nothing to exchange) -- the reference's one mesh
+    copy per thread, across GPUs; otherwise the mesh is bisected as usual and the closure rules still hold."""
+    mesh = M.Mesh.generate(M.GEN_HEX_BOX, [[7, 6, 5], [4, 3, 3]], mesh_variant=2)
+    base = [mesh.dims(l)[0] for l in range(mesh.levels)]
+    mesh.duplicate(copies)
+    for l in range(mesh.levels):
+        plans = [M.partition_plan(mesh, nranks, r, l) for r in range(nranks)]
+        assert sum(p["owned"] for p in plans) == copies * base[l]
+        if copies % nranks == 0:
+            for r, p in enumerate(plans):
+                assert p["ghosts"] == 0 and p["sent"] == 0 and p["owned"] == copies // nranks * base[l]
+                assert np.array_equal(p["gid"], np.arange(r * p["owned"], (r + 1) * p["owned"]))
+        else:
+            assert any(p["ghosts"] > 0 for p in plans)
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

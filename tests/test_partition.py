@@ -107,15 +107,17 @@ def test_duplicated_meshes_are_dealt_out_copy_by_copy(copies, nranks):
             assert any(p["ghosts"] > 0 for p in plans)
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, rank_local=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        mesh = M.Mesh.generate(1, [[9, 8, 7], [5, 4, 4]], mesh_variant=2)
+        dims = [[9, 8, 7], [5, 4, 4]]
+        mesh = M.Mesh.generate(1, dims, mesh_variant=2)
         ok = True
         for l in range(mesh.levels):
-            p = M.partition_plan(mesh, world, rank, l)
+            # rank_local: the way bench.py's ranks build their parts (no rank assembles the mesh)
+            p = M.generate_partition_plan(1, dims, world, rank, l, mesh_variant=2) if rank_local else M.partition_plan(mesh, world, rank, l)
             mine = {"gid": p["gid"].tolist(), "owned": p["owned"], "send_counts": p["send_counts"].tolist(), "send_gids": p["send_gids"].tolist(),
                     "recv_counts": p["recv_counts"].tolist()}
             allp = [None] * world
@@ -137,12 +139,13 @@ def _gloo_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-def test_partition_contract_across_two_gloo_ranks():
+@pytest.mark.parametrize("rank_local", [False, True])
+def test_partition_contract_across_two_gloo_ranks(rank_local):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + os.getpid() % 2000 + (7 if rank_local else 0)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q, rank_local)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]

@@ -166,8 +166,16 @@ int mgcfd_set_timing(mgcfd_ctx* ctx, int on);
 long mgcfd_launch_count(mgcfd_ctx* ctx);
 /* time (ms, CUDA events on the context's stream) of `reps` back-to-back launches of one kernel on `level`:
  * which = 0 fused stage kernel (flux + boundary + wall + time_step) of the configured tiled mode, 1 its flux-only form
- * (internal edges, granular API), 2 indirect_rw, 3 atomic flux */
+ * (internal edges, granular API), 2 indirect_rw, 3 atomic flux, 5 the stage kernel without its edge rounds, 16 + bits the
+ * assess-compute variant `bits` (mgcfd_flux_variant) */
 int mgcfd_time_kernel(mgcfd_ctx* ctx, int level, int which, int reps, double* ms_total);
+
+/* The reference's assess-compute protocol (run-inputs/assess-compute*.json): compute_flux_edge's arithmetic in the forms
+ * its compile-time toggles select (src/Kernels/flux_kernel.elemfunc.c), as a benchmark kernel -- one thread per internal edge,
+ * atomics, the same memory traffic for every variant.  bits: 1 = FLUX_REUSE_DIV (:46-71), 2 = FLUX_REUSE_FACTOR + FLUX_REUSE_FLUX
+ * (:132-190), 4 = FLUX_PRECOMPUTE_EDGE_WEIGHTS (:24-28); 0 is the default build's arithmetic as written.  Accumulates into
+ * `fluxes` like mgcfd_compute_flux_edge; mgcfd_time_kernel times variant `bits` as selector 16 + bits. */
+int mgcfd_flux_variant(mgcfd_ctx* ctx, int level, int bits);
 
 /* Host-only run of the integer preprocessing (no device needed): renumbering, tiling and colouring of one level.
  * info[] as mgcfd_level_info, except info[15] = a hash of everything the device would receive of the level (the plan is a pure

@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
     for name in ("initialize_variables", "copy_old_variables", "compute_flux_edge", "compute_boundary_flux_edge",
                  "compute_wall_flux_edge", "zero_fluxes", "indirect_rw", "residual", "mg_restrict", "prolong"):
         getattr(L, "mgcfd_" + name).argtypes = [vp, i]
+    L.mgcfd_flux_variant.argtypes = [vp, i, i]
     L.mgcfd_compute_step_factor.argtypes = [vp, i, i]
     L.mgcfd_time_step.argtypes = [vp, i, i]
     L.mgcfd_calc_rms.argtypes = [vp, i, dp, dp]
@@ -323,6 +324,10 @@ class Solver:
     def time_step(self, level, j): _check(lib().mgcfd_time_step(self._h, level, j))
     def zero_fluxes(self, level): _check(lib().mgcfd_zero_fluxes(self._h, level))
     def indirect_rw(self, level): _check(lib().mgcfd_indirect_rw(self._h, level))
+
+    def flux_variant(self, level, bits):
+        """compute_flux_edge in the arithmetic form the reference's FLUX_* toggles select (assess-compute; include/mgcfd_b200.h)."""
+        _check(lib().mgcfd_flux_variant(self._h, level, bits))
     def residual(self, level): _check(lib().mgcfd_residual(self._h, level))
     def mg_restrict(self, coarse_level): _check(lib().mgcfd_mg_restrict(self._h, coarse_level))
     def prolong(self, fine_level): _check(lib().mgcfd_prolong(self._h, fine_level))

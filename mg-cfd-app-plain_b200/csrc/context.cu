@@ -13,6 +13,7 @@
 #include "../../include/mgcfd_b200.h"
 #include "host_mesh.h"
 #include "kernels.cuh"
+#include "assess_kernels.cuh"
 #include "plan.h"
 #include "partition.h"
 #include "../../include/mgcfd_dist.h"
@@ -69,6 +70,7 @@ struct Level {
     int *ea = nullptr, *eb = nullptr; double* ew = nullptr;
     int* bnode = nullptr; uint8_t* bkind = nullptr; double* bw = nullptr;
     bool flat_up = false;
+    double* ewt_pre = nullptr;                     // |e| per internal edge (assess-compute variants with precomputed weights)
     // transfers (operators between this level and the next coarser one)
     long* child_off = nullptr; int* child_ids = nullptr;       // stored on the COARSE level (children in level-1)
     int* parent = nullptr; double* idist_own = nullptr; long* ent_off = nullptr; int* ent_src = nullptr; double* ent_w = nullptr;
@@ -468,6 +470,30 @@ int flux_granular(mgcfd_ctx* c, int l, int mask) {
     return MGCFD_OK;
 }
 
+// assess-compute variants of the flux kernel (assess_kernels.cuh): bits = REUSE_DIV | REUSE_FACTOR+FLUX << 1 | PRECOMPUTE_EDGE_WEIGHTS << 2
+int launch_flux_variant(mgcfd_ctx* c, Level& v, int bits) {
+    if (bits < 0 || bits > 7) { g_err = "flux variant bits must be in 0..7"; return MGCFD_ERR_ARG; }
+    CKRC(ensure_flux(c, v));
+    CKRC(ensure_flat(c, v));
+    if (!v.nI) return MGCFD_OK;
+    const unsigned nb = (unsigned)blocks_for(v.nI, 256);
+    if ((bits & 4) && !v.ewt_pre) {
+        CK(cudaMalloc((void**)&v.ewt_pre, sizeof(double) * v.nI));
+        k_edge_weights<<<nb, 256, 0, c->stream>>>(v.nI, v.ew, v.ewt_pre);
+        CKRC(post_launch(c));
+    }
+    const double smoothing = double(0.2f);      // smoothing_coefficient, src/Base/common.h:24
+#define MG_ASSESS(D, F, P) k_flux_assess<D, F, P><<<nb, 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.ewt_pre, v.V(v.i_var), v.npad, v.flux, smoothing)
+    switch (bits) {
+        case 0: MG_ASSESS(false, false, false); break; case 1: MG_ASSESS(true, false, false); break;
+        case 2: MG_ASSESS(false, true, false); break;  case 3: MG_ASSESS(true, true, false); break;
+        case 4: MG_ASSESS(false, false, true); break;  case 5: MG_ASSESS(true, false, true); break;
+        case 6: MG_ASSESS(false, true, true); break;   default: MG_ASSESS(true, true, true); break;
+    }
+#undef MG_ASSESS
+    return post_launch(c);
+}
+
 int step_factor(mgcfd_ctx* c, int l, int legacy) {
     Level& v = c->L[l];
     Timed tm(c, K_STEP, l, v.nel);
@@ -631,7 +657,7 @@ void free_level(Level& v) {
     void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
                     v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers,
-                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_bufs[0], v.d_peer_bufs[1], v.d_peer_bufs[2]};
+                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_bufs[0], v.d_peer_bufs[1], v.d_peer_bufs[2], v.ewt_pre};
     for (void* m : v.peer_buf_maps) if (m) cudaIpcCloseMemHandle(m);     // peers' record buffers (in-kernel exchange)
     for (void* p : ptrs) if (p) cudaFree(p);
 }
@@ -1173,6 +1199,8 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
             k_indirect_rw<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux); CKRC(post_launch(c));
         } else if (which == 3) {
             k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, 2.0 * c->kdiss); CKRC(post_launch(c));
+        } else if (which >= 16 && which < 24) {
+            CKRC(launch_flux_variant(c, v, which - 16));
         } else { g_err = "unknown kernel selector"; return MGCFD_ERR_ARG; }
     }
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -1182,6 +1210,11 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
     *ms_total = ms;
     CK(cudaMemsetAsync(v.flux, 0, sizeof(double) * 5 * v.npad, c->stream));
     return MGCFD_OK;
+}
+
+int mgcfd_flux_variant(mgcfd_ctx* c, int l, int bits) {
+    CKRC(check_level(c, l));
+    return launch_flux_variant(c, c->L[l], bits);
 }
 
 int mgcfd_plan_level(long nel, const double* coords, long nI, long nB, long nW, const void* edges, int ordering, int tile_nodes,

@@ -298,3 +298,23 @@ def test_programmatic_dependent_launch_changes_nothing(M):
         s.close()
     for o in outs[1:]:
         assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+
+
+@pytest.mark.parametrize("name", ["hex3", "tet3", "fvcorr"])
+def test_assess_compute_flux_variants_match_oracle(M, oracle, name):
+    """The reference's FLUX_* arithmetic toggles as benchmark kernels (csrc/assess_kernels.cuh; their arithmetic is also checked on
+    the CPU by tests/test_host_mesh.py): every variant accumulates compute_flux_edge's fluxes."""
+    mesh = make(M, name)
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    s = M.Solver.from_mesh(mesh)
+    L = lv[0]
+    var = perturbed_state(L["nel"], seed=77)
+    want = np.zeros(5 * L["nel"])
+    oracle.flux_edge(0, L["nI"], L["edges"], var, want)
+    s.set_field(0, M.FIELD_VARIABLES, var)
+    for bits in range(8):
+        s.zero_fluxes(0)
+        s.flux_variant(0, bits)
+        got = s.get_field(0, M.FIELD_FLUXES)
+        assert np.all(linf_rel(got, want) < KTOL), (bits, linf_rel(got, want))
+    s.close()

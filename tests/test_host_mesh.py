@@ -259,3 +259,19 @@ def test_plan_does_not_depend_on_the_number_of_host_threads():
         assert r.returncode == 0, r.stderr
         out.append(json.loads(r.stdout.strip().splitlines()[-1]))
     assert out[0] == out[1] == out[2] and out[0][0] != out[0][1]
+
+
+def test_assess_compute_arithmetic_on_the_host(tmp_path):
+    """The flux arithmetic variants of csrc/assess_kernels.cuh (the reference's FLUX_REUSE_* toggles) are __host__ __device__: their
+    host instantiation reproduces the oracle's compute_flux_edge (default variant bit for bit) -- tools/assess_host_check.cu."""
+    import shutil
+    if shutil.which("nvcc") is None or shutil.which("gcc") is None:
+        pytest.skip("needs nvcc and gcc")
+    obj, exe = str(tmp_path / "orc.o"), str(tmp_path / "assess_check")
+    r = subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-c", "-o", obj, os.path.join(ROOT, "oracle", "mgcfd_oracle.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run(["nvcc", "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-I" + os.path.join(ROOT, "mg-cfd-app-plain_b200", "csrc"),
+                        "-o", exe, os.path.join(ROOT, "tools", "assess_host_check.cu"), obj], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "PASS" in out.stdout and "default 0.00e+00" in out.stdout, out.stdout + out.stderr

@@ -12,3 +12,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-fil
 python tools/ncu_target.py 0 c2 0 3 1 > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_stage -s 2 -c 2 -o gpurun_out/prof_final_c2 python tools/ncu_target.py 0 c2 0 3 1 > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
+python tools/assess_compute.py c2 > gpurun_out/assess_compute_c2.jsonl 2> gpurun_out/assess_compute.err; cat gpurun_out/assess_compute_c2.jsonl

@@ -1471,25 +1471,15 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
             if (!v.pipe) { g_err = "the in-kernel exchange needs the pipelined stage kernel on every level"; return MGCFD_ERR_ARG; }
             if (v.npeers == 0) continue;
             const std::vector<P2PPeer>& peers = v.h_peers;
-            // node -> (peer, row in the peer's record arrays): my k-th row for peer p is its ghost row ncomp_p + recv_off_p[me] + k
-            std::vector<int> cnt(v.ncomp + 1, 0), tpeer, trow;
+            // node -> (peer, row in the peer's record arrays): build_send_targets (partition.h)
+            std::vector<PeerSlice> slices(v.npeers);
             std::vector<double*> pbuf[3];
-            for (int pi = 0; pi < v.npeers; pi++) for (long k = 0; k < peers[pi].nsend; k++) cnt[v.h_send_idx[peers[pi].send0 + k] + 1]++;
-            for (long i = 0; i < v.ncomp; i++) cnt[i + 1] += cnt[i];
-            tpeer.resize(cnt[v.ncomp]); trow.resize(cnt[v.ncomp]);
-            std::vector<int> pos(cnt.begin(), cnt.end() - 1);
-            std::vector<unsigned char> tile_sends(v.ntiles, 0);
             for (int pi = 0; pi < v.npeers; pi++) {
                 const int p = peers[pi].rank;
                 const long* tp = tables + (size_t)p * table_len + 1 + (size_t)l * per_level;
                 const long* fp = tables + (size_t)p * table_len + base_len + (size_t)l * FUSED_PER_LEVEL;
-                const long p_ncomp = fp[0], p_recv_me = tp[2 + d.rank];
-                for (long k = 0; k < peers[pi].nsend; k++) {
-                    const int node = v.h_send_idx[peers[pi].send0 + k];
-                    if (node < 0 || node >= v.ncomp) { g_err = "send list entry is not an owned row"; return MGCFD_ERR_ARG; }
-                    tpeer[pos[node]] = pi; trow[pos[node]] = (int)(p_ncomp + p_recv_me + k); pos[node]++;
-                    tile_sends[node / v.TN] = 1;
-                }
+                slices[pi].send0 = peers[pi].send0; slices[pi].nsend = peers[pi].nsend;
+                slices[pi].first_ghost_row = fp[0]; slices[pi].recv_off_me = tp[2 + d.rank];
                 for (int b = 0; b < 3; b++) {
                     cudaIpcMemHandle_t hb;
                     memcpy(&hb, fp + 1 + 8 * b, 64);
@@ -1499,6 +1489,11 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
                     pbuf[b].push_back((double*)m);
                 }
             }
+            SendTargets st;
+            try { build_send_targets(v.ncomp, v.TN, v.h_send_idx, slices, st); }
+            catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+            const std::vector<int>&cnt = st.off, &tpeer = st.peer, &trow = st.row;
+            const std::vector<unsigned char>& tile_sends = st.tile_sends;
             CKRC(dev_upload(&v.d_tgt_off, cnt, c->stream)); CKRC(dev_upload(&v.d_tgt_peer, tpeer, c->stream)); CKRC(dev_upload(&v.d_tgt_row, trow, c->stream));
             CKRC(dev_upload(&v.d_tile_sends, tile_sends, c->stream));
             for (int b = 0; b < 3; b++) CKRC(dev_upload(&v.d_peer_bufs[b], pbuf[b], c->stream));

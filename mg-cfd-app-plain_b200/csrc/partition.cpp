@@ -328,4 +328,27 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
     }
 }
 
+void build_send_targets(long owned_rows, int tile_nodes, const std::vector<int>& send_rows, const std::vector<PeerSlice>& peers, SendTargets& out) {
+    out = SendTargets();
+    out.off.assign(owned_rows + 1, 0);
+    out.tile_sends.assign((owned_rows + tile_nodes - 1) / tile_nodes, 0);
+    for (const PeerSlice& p : peers)
+        for (long k = 0; k < p.nsend; k++) {
+            const int node = send_rows[p.send0 + k];
+            if (node < 0 || node >= owned_rows) throw std::runtime_error("mgcfd: send list entry is not an owned row");
+            out.off[node + 1]++;
+        }
+    for (long i = 0; i < owned_rows; i++) out.off[i + 1] += out.off[i];
+    out.peer.resize(out.off[owned_rows]); out.row.resize(out.off[owned_rows]);
+    std::vector<int> pos(out.off.begin(), out.off.end() - 1);
+    for (size_t pi = 0; pi < peers.size(); pi++)
+        for (long k = 0; k < peers[pi].nsend; k++) {
+            const int node = send_rows[peers[pi].send0 + k];
+            out.peer[pos[node]] = int(pi);
+            out.row[pos[node]] = int(peers[pi].first_ghost_row + peers[pi].recv_off_me + k);
+            pos[node]++;
+            out.tile_sends[node / tile_nodes] = 1;
+        }
+}
+
 }  // namespace mgcfd

@@ -57,4 +57,20 @@ struct LevelSource {
 };
 void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant, int nranks, int rank, LocalMesh& out);
 
+// In-kernel halo exchange (MGCFD_P2P_FUSED, kernels.cuh k_stage_pipe<.., DIST>): where the records of this rank's send-list nodes
+// go.  The k-th node this rank sends to peer p is p's ghost row  first_ghost_row_p + recv_off_p[this rank] + k  (ghost rows follow
+// the owned tiles, grouped by owner in rank order: partition.h).  Pure host arithmetic, shared by mgcfd_dist_p2p_attach and the
+// host regression harness.
+struct PeerSlice {
+    long send0 = 0, nsend = 0;         // slice of the level's send list (device rows)
+    long first_ghost_row = 0;          // the peer's first ghost row (its owned tiles * tile size)
+    long recv_off_me = 0;              // the peer's recv_off[this rank]
+};
+struct SendTargets {
+    std::vector<int> off, peer, row;   // CSR over this rank's owned rows: node -> (index into the peer list, row in that peer's arrays)
+    std::vector<unsigned char> tile_sends;   // per tile: any node with a target
+};
+// throws std::runtime_error when a send-list entry is not an owned row
+void build_send_targets(long owned_rows, int tile_nodes, const std::vector<int>& send_rows, const std::vector<PeerSlice>& peers, SendTargets& out);
+
 }  // namespace mgcfd

@@ -1,6 +1,10 @@
 // partition.cpp -- domain decomposition of a multigrid mesh over ranks (see partition.h).
 #include "partition.h"
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdint>
 #include <numeric>
@@ -11,6 +15,18 @@ namespace mgcfd {
 namespace {
 
 const int MESH_FVCORR = 0;
+
+// MGCFD_PLAN_TIMING=1: wall time of the phases of the rank-local partitioning on stderr
+struct PhaseClock {
+    bool on = getenv("MGCFD_PLAN_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "  partition: %-26s %8.3f s\n", what, std::chrono::duration<double>(now - t).count());
+        t = now;
+    }
+};
 
 struct Csr {
     std::vector<long> off;
@@ -208,6 +224,7 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
     std::vector<std::vector<int>> owner(nl);
     std::vector<Csr> kids(nl);
     Entry ent[32];
+    PhaseClock clk;
     for (int l = 0; l < nl; l++) {
         const NodeSource& S = *levels[l].src;
         n[l] = S.nel();
@@ -227,6 +244,7 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
             for (long i = 0; i < n[l - 1]; i++) c.idx[pos[mg[i]]++] = int(i);
         }
     }
+    clk.lap("coordinates + bisection");
     std::vector<std::vector<char>> flux_local(nl);
     for (int l = 0; l < nl; l++) {
         const NodeSource& S = *levels[l].src;
@@ -238,6 +256,7 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
             for (int j = 0; j < deg; j++) if (ent[j].nbr >= 0) flux_local[l][ent[j].nbr] = 1;
         }
     }
+    clk.lap("flux closure");
     std::vector<std::vector<int>> g2l(nl);
     for (int l = 0; l < nl; l++) {
         const NodeSource& S = *levels[l].src;
@@ -284,6 +303,7 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
             LL.send_off[p + 1] = long(LL.send_idx.size());
         }
     }
+    clk.lap("local sets + send lists");
     for (int l = 0; l < nl; l++) {
         const NodeSource& S = *levels[l].src;
         LocalLevel& LL = out.levels[l];
@@ -326,6 +346,7 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
             for (long k = 0; k < nloc; k++) M.mg[k] = g2l[l + 1][levels[l].mg[LL.gid[k]]];
         }
     }
+    clk.lap("local meshes");
 }
 
 void build_send_targets(long owned_rows, int tile_nodes, const std::vector<int>& send_rows, const std::vector<PeerSlice>& peers, SendTargets& out) {

@@ -21,7 +21,8 @@ a cycle performs  sum_l E_I(l) * RK(3) * visits(l)  of them (BASELINE.json metri
   cpu_baseline = the UNMODIFIED reference (oracle/_ref/libmgcfd_ref_omp.so: its own sources built -DOMP -DOMP_SCATTERS)
            on the host cores, mesh duplicated once per thread as its assess-memory protocol does (gen_job.py:360-365)
 
-`--impl reference` times that reference build alone (all host threads) and prints the same line with "impl": "reference".
+`--impl reference` times that reference build alone (all host threads) and prints the same line with "impl": "reference"; its
+timed sample is bounded to ~45 s of CPU work (MGCFD_REFERENCE_BUDGET_S) whatever --steps says -- the metric is a rate.
 """
 import argparse
 import json
@@ -125,20 +126,28 @@ def reference_cpu_run(workload, steps, warmup, threads):
         if t > 1:
             sess.duplicate(t)
         sess.prepare()
-        if warmup:
-            sess.run(warmup)
-        _, _, secs = sess.run(steps)
+        # bounded sample: a CPU V-cycle of C2 takes ~0.7 s on 16 threads, so at most `budget_s` seconds of cycles are timed (the
+        # metric is a rate: it does not depend on how many cycles the sample holds); the warm-up is capped likewise
+        budget_s = float(os.environ.get("MGCFD_REFERENCE_BUDGET_S", "45"))
+        _, _, first = sess.run(1)
+        if warmup > 1:
+            sess.run(min(warmup - 1, max(0, int(0.25 * budget_s / max(first, 1e-9)))))
+        n = max(1, min(steps, int(budget_s / max(first, 1e-9))))
+        _, _, secs = sess.run(n)
         sess.close()
-        return t * units * steps / secs, secs / steps, "reference", t, \
-            f"{steps} V-cycle(s) (+{warmup} warm-up) of {workload} duplicated x{t} (one copy per thread, -DOMP -DOMP_SCATTERS, -DPRECISE_FP), oracle/_ref/libmgcfd_ref_omp.so"
+        return t * units * n / secs, secs / n, "reference", t, \
+            f"{n} V-cycle(s) timed (of {steps} requested; bounded to ~{budget_s:.0f} s of CPU work, +warm-up) of {workload} duplicated x{t} (one copy per thread, -DOMP -DOMP_SCATTERS, -DPRECISE_FP), oracle/_ref/libmgcfd_ref_omp.so", n
     orc = Oracle()                      # scalar port, 1 thread
     lv = mesh_levels(mesh, apply_ewt_with=orc)
-    if warmup:
-        orc.run_cycles(variant, lv, warmup)
+    budget_s = float(os.environ.get("MGCFD_REFERENCE_BUDGET_S", "45"))
     t0 = time.perf_counter()
-    orc.run_cycles(variant, lv, steps)
+    orc.run_cycles(variant, lv, 1)
+    first = time.perf_counter() - t0
+    n = max(1, min(steps, int(budget_s / max(first, 1e-9))))
+    t0 = time.perf_counter()
+    orc.run_cycles(variant, lv, n)
     secs = time.perf_counter() - t0
-    return units * steps / secs, secs / steps, "port", 1, f"{steps} V-cycle(s) of {workload}, oracle/libmgcfd_oracle.so (scalar C port), 1 thread"
+    return units * n / secs, secs / n, "port", 1, f"{n} V-cycle(s) timed (of {steps} requested; bounded to ~{budget_s:.0f} s) of {workload}, oracle/libmgcfd_oracle.so (scalar C port), 1 thread", n
 
 
 def main():
@@ -166,12 +175,12 @@ def main():
         if rank != 0:
             return
         thr = host_threads()
-        v, spstep, kindname, cores, sample = reference_cpu_run(args.workload, args.steps, W, thr)
+        v, spstep, kindname, cores, sample, n_timed = reference_cpu_run(args.workload, args.steps, W, thr)
         print(json.dumps({
             "impl": "reference", "metric": "flux edge-updates/s", "value": v, "unit": "edge-updates/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": W, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "steps_timed": n_timed, "warmup": W, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "step": "one V-cycle", "note": "CPU only; the mesh is duplicated once per host thread"},
+            "config": {"workload": desc, "step": "one V-cycle", "note": "CPU only; the mesh is duplicated once per host thread; the timed sample is bounded (cpu_baseline.sample)"},
             "cpu_baseline": {"value": v, "unit": "edge-updates/s", "cores": cores, "kind": kindname, "sample": sample},
             "e2e": {"value": v, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))

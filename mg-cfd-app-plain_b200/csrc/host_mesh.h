@@ -41,7 +41,8 @@ struct NodeSource {
     virtual long nel() const = 0;
     virtual double volume(long i) const = 0;
     virtual void coords(long i, double* xyz) const = 0;
-    virtual int listing(long i, Entry* out) const = 0;   // returns degree (<= 32)
+    // the listing of node i (any degree): `deg` entries, valid until the next call on this source
+    virtual const Entry* listing(long i, int& deg) const = 0;
 };
 
 // Applies read_grid's rules (io.cpp:84-181) to a node source: an edge for every entry with nbr < i,

@@ -59,7 +59,9 @@ struct BoxSource : NodeSource {
         const double xr = double(ix) / double(nx - 1);
         return xr > 0.3 && xr < 0.6;
     }
-    int listing(long i, Entry* out) const override {
+    mutable Entry buf[32];      // a node of these meshes lists at most 14 neighbours + 6 boundary faces
+    const Entry* listing(long i, int& deg) const override { deg = fill(i, buf); return buf; }
+    int fill(long i, Entry* out) const {
         long q[3]; ijk(i, q);
         const long n[3] = {nx, ny, nz};
         const double sgn_bnd = (variant == MESH_FVCORR) ? 1.0 : -1.0;  // non-fvcorr: boundary normals written inward
@@ -151,7 +153,9 @@ struct TetCellSource : NodeSource {
         double v[4][3]; verts(i, v);
         for (int k = 0; k < 3; k++) xyz[k] = 0.25 * (v[0][k] + v[1][k] + v[2][k] + v[3][k]);
     }
-    int listing(long i, Entry* out) const override {
+    mutable Entry buf[8];
+    const Entry* listing(long i, int& deg) const override { deg = fill(i, buf); return buf; }
+    int fill(long i, Entry* out) const {
         const long cube = i / 6; const int p = int(i % 6);
         const long q[3] = {cube % cx, (cube / cx) % cy, cube / (cx * cy)};
         const long n[3] = {cx, cy, cz};
@@ -206,10 +210,12 @@ struct PermutedSource : NodeSource {
     long nel() const override { return base.nel(); }
     double volume(long i) const override { return base.volume(old_of_new[i]); }
     void coords(long i, double* xyz) const override { base.coords(old_of_new[i], xyz); }
-    int listing(long i, Entry* out) const override {
-        int d = base.listing(old_of_new[i], out);
-        for (int k = 0; k < d; k++) if (out[k].nbr >= 0) out[k].nbr = new_of_old[out[k].nbr];
-        return d;
+    mutable std::vector<Entry> buf;
+    const Entry* listing(long i, int& deg) const override {
+        const Entry* src = base.listing(old_of_new[i], deg);
+        buf.assign(src, src + deg);
+        for (int k = 0; k < deg; k++) if (buf[k].nbr >= 0) buf[k].nbr = new_of_old[buf[k].nbr];
+        return buf.data();
     }
 };
 
@@ -242,11 +248,11 @@ void build_level_like_read_grid(const NodeSource& src, int mesh_variant, bool wa
     if (want_coords) out.coords.resize(3 * n); else out.coords.clear();
     std::vector<EdgeNb> bnd, wall;
     out.edges.clear();
-    Entry ent[32];
     for (long i = 0; i < n; i++) {
         out.volumes[i] = src.volume(i);
         if (want_coords) src.coords(i, &out.coords[3 * i]);
-        const int deg = src.listing(i, ent);
+        int deg = 0;
+        const Entry* ent = src.listing(i, deg);
         for (int j = 0; j < deg; j++) {
             const long i2 = ent[j].nbr;
             if (i2 >= i) continue;

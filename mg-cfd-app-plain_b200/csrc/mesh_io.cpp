@@ -120,7 +120,7 @@ struct TextSource : NodeSource {
     long n = 0, ne_claimed = 0;
     mutable double vol = 0;
     mutable long cur = -1;
-    mutable Entry ent[32];
+    mutable std::vector<Entry> ent;   // the current node's listing, whatever its degree
     mutable int deg = 0;
     mutable double xyz[3] = {0, 0, 0};
     TextSource(const MappedFile& mesh, const MappedFile* coords, const char* mesh_name, const char* coords_name)
@@ -135,13 +135,12 @@ struct TextSource : NodeSource {
             const long d = m.integer();
             if (d < 0 || d > 1000000) m.fail();
             deg = int(d);
+            ent.resize(deg);
             for (int j = 0; j < deg; j++) {
-                Entry e;
+                Entry& e = ent[j];
                 e.nbr = m.integer();
                 e.w[0] = m.real(); e.w[1] = m.real(); e.w[2] = m.real();
-                if (j < 32) ent[j] = e;
             }
-            if (deg > 32) deg = 32;
             if (have_coords) { xyz[0] = c.real(); xyz[1] = c.real(); xyz[2] = c.real(); }
             cur++;
         }
@@ -149,7 +148,7 @@ struct TextSource : NodeSource {
     long nel() const override { return n; }
     double volume(long i) const override { advance(i); return vol; }
     void coords(long i, double* o) const override { advance(i); o[0] = xyz[0]; o[1] = xyz[1]; o[2] = xyz[2]; }
-    int listing(long i, Entry* out) const override { advance(i); memcpy(out, ent, sizeof(Entry) * deg); return deg; }
+    const Entry* listing(long i, int& d) const override { advance(i); d = deg; return ent.data(); }
 };
 
 }  // namespace

@@ -223,7 +223,6 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
     std::vector<long> n(nl);
     std::vector<std::vector<int>> owner(nl);
     std::vector<Csr> kids(nl);
-    Entry ent[32];
     PhaseClock clk;
     for (int l = 0; l < nl; l++) {
         const NodeSource& S = *levels[l].src;
@@ -252,7 +251,8 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
         for (long i = 0; i < n[l]; i++) {
             if (owner[l][i] != rank) continue;
             flux_local[l][i] = 1;
-            const int deg = S.listing(i, ent);
+            int deg = 0;
+            const Entry* ent = S.listing(i, deg);
             for (int j = 0; j < deg; j++) if (ent[j].nbr >= 0) flux_local[l][ent[j].nbr] = 1;
         }
     }
@@ -279,11 +279,11 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
         g2l[l].assign(n[l], -1);
         for (size_t k = 0; k < LL.gid.size(); k++) g2l[l][LL.gid[k]] = int(k);
         std::vector<uint64_t> wanted(LL.n_owned, 0);
-        Entry e2[32];
         for (long k = 0; k < LL.n_owned; k++) {
             const long i = LL.gid[k];
             uint64_t m = 0;
-            const int deg = S.listing(i, ent);
+            int deg = 0;
+            const Entry* ent = S.listing(i, deg);
             for (int j = 0; j < deg; j++) if (ent[j].nbr >= 0) m |= 1ull << owner[l][ent[j].nbr];
             if (l + 1 < nl) m |= 1ull << owner[l + 1][levels[l].mg[i]];
             if (l >= 1) {
@@ -291,7 +291,8 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
                 for (long c = kids[l].off[i]; c < kids[l].off[i + 1]; c++) {
                     const long j = kids[l].idx[c];
                     m |= 1ull << owner[l - 1][j];
-                    const int d2 = F.listing(j, e2);
+                    int d2 = 0;
+                    const Entry* e2 = F.listing(j, d2);
                     for (int q = 0; q < d2; q++) if (e2[q].nbr >= 0) m |= 1ull << owner[l - 1][e2[q].nbr];
                 }
             }
@@ -318,7 +319,8 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
         std::vector<EdgeNb> bnd, wall;
         long global_edge = 0;
         for (long i = 0; i < n[l]; i++) {
-            const int deg = S.listing(i, ent);
+            int deg = 0;
+            const Entry* ent = S.listing(i, deg);
             const bool mine = owner[l][i] == rank;
             for (int j = 0; j < deg; j++) {
                 const long i2 = ent[j].nbr;

@@ -350,3 +350,53 @@ def test_irregular_mesh_with_high_degree_nodes(tmp_path):
     for r in range(3):
         p = M.partition_plan(mesh, 3, r, 0)
         assert p["owned"] > 0 and p["ghosts"] > 0
+
+
+def _random_level(n, k, seed, isolated=0):
+    """Unstructured level in memory (read_grid's edge order): random points, k-nearest-neighbour edges, three hubs, boundary and wall
+    edges; the last `isolated` nodes have no internal edge at all."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    pts = rng.random((n, 3))
+    m = n - isolated
+    _, nb = cKDTree(pts[:m]).query(pts[:m], k=k + 1)
+    pairs = {(min(i, int(j)), max(i, int(j))) for i in range(m) for j in nb[i, 1:] if i != int(j)}
+    for hub in rng.choice(m, 3, replace=False):
+        pairs |= {(min(int(hub), int(j)), max(int(hub), int(j))) for j in rng.choice(m, 40, replace=False) if int(hub) != int(j)}
+    pairs = sorted(pairs, key=lambda p: (p[1], p[0]))
+    nI, nB, nW = len(pairs), n // 20, n // 20
+    e = np.zeros(nI + nB + nW, dtype=M.EDGE_DTYPE)
+    e["a"][:nI] = [p[0] for p in pairs]; e["b"][:nI] = [p[1] for p in pairs]
+    e["a"][nI:nI + nB] = -1; e["b"][nI:nI + nB] = np.sort(rng.choice(n, nB))
+    e["a"][nI + nB:] = -2; e["b"][nI + nB:] = np.sort(rng.choice(n, nW))
+    for f in ("x", "y", "z"):
+        e[f] = 1e-3 * (rng.random(len(e)) - 0.5)
+    return dict(nel=n, nI=nI, nB=nB, nW=nW, vol=rng.random(n) + 0.5, edges=e, coords=pts.copy(), map=None)
+
+
+@pytest.mark.parametrize("nf,nc,k", [(1500, 400, 5), (2400, 1900, 8), (700, 90, 4)])
+def test_transfer_operators_on_unstructured_levels(nf, nc, k):
+    """Arbitrary (nearest-node) multigrid maps between unstructured levels: coarse nodes without children keep their value
+    (mg_loops.cpp:43-90), fine nodes that coincide with their parent take its residual (:741-775), fine nodes without an internal
+    edge come out NaN as in the reference (0/0, :844-852) -- restriction bit for bit, prolongation to rounding."""
+    from scipy.spatial import cKDTree
+    from conftest import linf_rel, perturbed_state
+    from oracle.loader import Oracle
+    orc = Oracle()
+    rng = np.random.default_rng(nf)
+    F, C = _random_level(nf, k, 10 + nf, isolated=4), _random_level(nc, k, 20 + nc)
+    F["coords"][:40] = C["coords"][rng.choice(nc, 40)]                    # exact coincidences
+    F["map"] = cKDTree(C["coords"]).query(F["coords"])[1].astype(np.int64)
+    assert len(np.unique(F["map"])) < nc or nc < 200                      # some coarse nodes have no children
+    vf, vc = perturbed_state(nf, seed=1), perturbed_state(nc, seed=2)
+    r1, r2 = 1e-3 * rng.standard_normal(5 * nc), 1e-3 * rng.standard_normal(5 * nf)
+    for tile_nodes in (128, 256):
+        got_c, got_f = M.plan_emulate_transfers(F, C, vf, r2, r1, vc, tile_nodes=tile_nodes)
+        want_c = vc.copy()
+        orc.mg_restrict(vf, want_c, F["map"])
+        assert np.array_equal(got_c, want_c)
+        want_f = vf.copy()
+        orc.prolong(F["edges"], F["nI"], r1, r2, want_f, F["map"], C["coords"], F["coords"])
+        ok = np.isfinite(want_f)
+        assert (~ok).sum() == 5 * 4 and np.array_equal(np.isfinite(got_f), ok)
+        assert np.all(linf_rel(np.where(ok, got_f, 0.0), np.where(ok, want_f, 0.0)) < 1e-14)

@@ -318,3 +318,35 @@ def test_assess_compute_flux_variants_match_oracle(M, oracle, name):
         got = s.get_field(0, M.FIELD_FLUXES)
         assert np.all(linf_rel(got, want) < KTOL), (bits, linf_rel(got, want))
     s.close()
+
+
+@pytest.mark.xfail(strict=False, reason="written after this round's GPU budget was spent: first hardware run decides; the same meshes pass "
+                   "reference == oracle == host walk of the plan on the CPU (tests/test_oracle_golden.py, tests/test_host_mesh.py)")
+@pytest.mark.parametrize("variant,tile_nodes", [(4, 0), (4, 128), (0, 256)])
+def test_unstructured_levels_with_high_degree_nodes(M, oracle, variant, tile_nodes):
+    """Unstructured input through mgcfd_upload_level: k-nearest-neighbour edges, hub nodes with 40+ neighbours (tiles with many edge
+    rounds and several ring chunks), nearest-node multigrid maps -- V-cycles against the oracle."""
+    from scipy.spatial import cKDTree
+    from test_host_mesh import _random_level
+    rng = np.random.default_rng(variant)
+    raw = [_random_level(6000, 6, 1), _random_level(2500, 5, 2), _random_level(800, 4, 3)]
+    for lv in raw:
+        for f in ("x", "y", "z"):
+            lv["edges"][f] *= 1e-2 if variant == 0 else 1.0
+    for f, c in zip(raw[:-1], raw[1:]):
+        f["map"] = cKDTree(c["coords"]).query(f["coords"])[1].astype(np.int64)
+    adj = [dict(lv, edges=lv["edges"].copy()) for lv in raw]
+    for lv in adj:
+        oracle.adjust_dampen(variant, lv["coords"], lv["edges"])
+    cycles = 5
+    oa, ov, st = oracle.run_cycles(variant, [dict(lv, edges=lv["edges"].copy()) for lv in adj], cycles)
+    s = M.Solver(3, variant, tile_nodes=tile_nodes)
+    for l, lv in enumerate(adj):
+        s.upload_level(l, lv["vol"], lv["coords"], lv["nI"], lv["nB"], lv["nW"], lv["edges"], lv.get("map"))
+    s.finalize()
+    assert s.level_info(0)["max_rounds"] > 40
+    ra, rv = s.run_cycles(cycles)
+    assert np.max(np.abs(ra - oa) / oa) < TOL
+    for l in range(3):
+        assert np.all(linf_rel(s.get_field(l, M.FIELD_VARIABLES), st[l]["var"]) < TOL), l
+    s.close()

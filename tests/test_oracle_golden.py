@@ -102,3 +102,33 @@ def test_oracle_against_live_reference_larger_mesh(orc):
         assert adj[l]["edges"].tobytes() == sess.field(l, 6).tobytes()
         assert np.all(linf_rel(st[l]["var"], sess.field(l, 0)) < 1e-13)
     sess.close()
+
+
+@pytest.mark.skipif(not reference_available(), reason="oracle/_ref/libmgcfd_ref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("variant", [4, 0])
+def test_oracle_against_live_reference_unstructured_mesh(orc, variant):
+    """Pins the oracle on inputs no generator produces: three unstructured levels (k-nearest-neighbour edges, hub nodes, nearest-node
+    multigrid maps with childless coarse nodes and exact coincidences) run through the reference's own objects and the oracle."""
+    from scipy.spatial import cKDTree
+    from test_host_mesh import _random_level
+    ref = Reference()
+    rng = np.random.default_rng(variant)
+    raw = [_random_level(1200, 6, 1), _random_level(500, 5, 2), _random_level(160, 4, 3)]
+    for lv in raw:                                         # physical-ish scale so that six cycles stay well inside the valid states
+        for f in ("x", "y", "z"):
+            lv["edges"][f] *= 1e-2 if variant == 0 else 1.0
+    for f, c in zip(raw[:-1], raw[1:]):
+        f["coords"][:30] = c["coords"][rng.choice(c["nel"], 30)]
+        f["map"] = cKDTree(c["coords"]).query(f["coords"])[1].astype(np.int64)
+    sess = ref.session(variant, [dict(lv, edges=lv["edges"].copy()) for lv in raw])
+    sess.prepare()
+    ra, rv, _ = sess.run(6)
+    adj = [dict(lv, edges=lv["edges"].copy()) for lv in raw]
+    for lv in adj:
+        orc.adjust_dampen(variant, lv["coords"], lv["edges"])
+    oa, ov, st = orc.run_cycles(variant, adj, 6)
+    assert np.all(np.isfinite(ra)) and np.max(np.abs(oa - ra) / ra) < 1e-13
+    for l in range(3):
+        assert adj[l]["edges"].tobytes() == sess.field(l, 6).tobytes()
+        assert np.all(linf_rel(st[l]["var"], sess.field(l, 0)) < 1e-13)
+    sess.close()

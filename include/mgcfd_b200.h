@@ -68,14 +68,18 @@ typedef struct mgcfd_options {
     int device;     /* CUDA device ordinal (default 0) */
     int flux_mode;  /* MGCFD_FLUX_* (default MGCFD_FLUX_SORTED_SEGMENT: the faster of the two tiled modes on B200, profiles/) */
     int ordering;   /* MGCFD_ORDER_* */
-    int tile_nodes; /* owned nodes per tile = threads per CTA of the tiled kernel; 0 = auto (default): 256 below a million nodes per level, 128 above; else 128, 256 or 512 */
+    int tile_nodes; /* owned nodes per tile = threads per CTA of the stage kernels; 0 = auto (default: 128 for the visit kernel and for
+                       multi-million-node levels, else 128 or 256 by a wave model, see auto_tile_nodes in csrc/context.cu); else 128, 256 or 512 */
     int use_graph;  /* run_cycles replays one captured CUDA graph per V-cycle (default 1) */
     int timing;     /* record CUDA-event times per kernel per level (forces use_graph=0) */
     int no_pipeline; /* 1: fused stages use the simple one-CTA-per-tile kernel instead of the persistent kernel whose transfers
                         (TMA bulk copies of the edge stream, cp.async gathers of node records) run one tile ahead (default 0) */
     int no_pdl;      /* 1: stage kernels are launched without programmatic dependent launch (default 0: the prologue of a stage
                         kernel -- barrier set-up, header and edge-stream prefetch -- overlaps the tail of its predecessor) */
-    int reserved[8];
+    int no_visit;    /* 1: never use the persistent visit kernel (one launch per smoothing visit: minimum dt, the three RK stages, residual
+                        and RMS sums separated by grid barriers, node records resident in shared memory where they fit); default 0:
+                        levels of up to ~1.2 M nodes in sorted-segment mode run it, larger levels stream through the stage kernels */
+    int reserved[7];
 } mgcfd_options;
 
 void mgcfd_default_options(mgcfd_options* opt);
@@ -152,6 +156,9 @@ int mgcfd_get_stream(mgcfd_ctx* ctx, void** cuda_stream);
 /* info[0..15]: nel, nI, nB, nW, padded nodes, tiles, tile_nodes, max rounds, slots allocated, halo entries, cut edges,
  * slots used, max halo of a tile, boundary slots allocated, shared memory per CTA (bytes), persistent grid (0 = simple kernel) */
 int mgcfd_level_info(mgcfd_ctx* ctx, int level, long info[16]);
+/* the persistent visit kernel's configuration of a level: info[0..7] = in use (0/1), super-tiles per CTA, CTAs, edge rounds per ring
+ * entry, own rows resident in shared memory (0/1), rows of the largest super-tile, shared memory per CTA (bytes), halo rows in total */
+int mgcfd_visit_info(mgcfd_ctx* ctx, int level, long info[8]);
 /* new_of_old[nel]: the node renumbering (a bijection onto [0,padded) minus padding) */
 int mgcfd_get_permutation(mgcfd_ctx* ctx, int level, long* new_of_old);
 /* verifies on the host that no two edges of one colour round of one tile write the same node; returns #conflicts */
@@ -193,6 +200,14 @@ int mgcfd_plan_level(long nel, const double* coords_xyz, long num_internal, long
  *              var_f with res_c / res_f. */
 int mgcfd_plan_emulate_flux(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall, const void* edges_aos40,
                             int ordering, int tile_nodes, int flux_mode, const double* variables, int mask, double* fluxes);
+/* the same walk over the visit kernel's streams (super-tile descriptors, halo lists, re-addressed edge rounds): `supers` super-tiles
+ * of 128-node tiles; info[0..7] = super-tiles, most tiles in one, most halo rows of one, halo rows in total, most rounds, tiles, rows */
+int mgcfd_plan_emulate_visit_flux(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall, const void* edges_aos40,
+                                  int supers, const double* variables, int mask, double* fluxes, long info[8]);
+/* host-only: the visit-kernel configuration mgcfd_upload_level would choose for this level on a device with `num_sms` SMs; info[] as
+ * mgcfd_visit_info */
+int mgcfd_plan_visit_config(long nel, const double* coords_xyz, long num_internal, long num_boundary, long num_wall, const void* edges_aos40,
+                            int num_sms, long info[8]);
 int mgcfd_plan_emulate_transfers(long nel_f, const double* coords_f, long nI_f, long nB_f, long nW_f, const void* edges_f, const long* mg_map,
                                  long nel_c, const double* coords_c, long nI_c, long nB_c, long nW_c, const void* edges_c, int ordering,
                                  int tile_nodes, const double* var_f, const double* res_f, const double* res_c, double* var_c, double* var_f_out);

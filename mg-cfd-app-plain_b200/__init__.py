@@ -40,7 +40,7 @@ class MgcfdError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("flux_mode", C.c_int), ("ordering", C.c_int), ("tile_nodes", C.c_int),
-                ("use_graph", C.c_int), ("timing", C.c_int), ("no_pipeline", C.c_int), ("no_pdl", C.c_int), ("reserved", C.c_int * 8)]
+                ("use_graph", C.c_int), ("timing", C.c_int), ("no_pipeline", C.c_int), ("no_pdl", C.c_int), ("no_visit", C.c_int), ("reserved", C.c_int * 7)]
 
 
 _lib = None
@@ -86,6 +86,7 @@ def lib() -> C.CDLL:
     L.mgcfd_set_field.argtypes = [vp, i, i, vp]
     L.mgcfd_synchronize.argtypes = [vp]
     L.mgcfd_level_info.argtypes = [vp, i, C.POINTER(l)]
+    L.mgcfd_visit_info.argtypes = [vp, i, C.POINTER(l)]
     L.mgcfd_get_permutation.argtypes = [vp, i, vp]
     L.mgcfd_check_colouring.argtypes = [vp, i]
     L.mgcfd_check_colouring.restype = l
@@ -96,6 +97,8 @@ def lib() -> C.CDLL:
     L.mgcfd_time_kernel.argtypes = [vp, i, i, i, dp]
     L.mgcfd_plan_level.argtypes = [l, vp, l, l, l, vp, i, i, i, C.POINTER(l), vp, C.POINTER(l)]
     L.mgcfd_plan_emulate_flux.argtypes = [l, vp, l, l, l, vp, i, i, i, vp, i, vp]
+    L.mgcfd_plan_emulate_visit_flux.argtypes = [l, vp, l, l, l, vp, i, vp, i, vp, C.POINTER(l)]
+    L.mgcfd_plan_visit_config.argtypes = [l, vp, l, l, l, vp, i, C.POINTER(l)]
     L.mgcfd_plan_emulate_transfers.argtypes = [l, vp, l, l, l, vp, vp, l, vp, l, l, l, vp, i, i, vp, vp, vp, vp, vp]
     L.mgcfd_mesh_generate.argtypes = [i, i, vp, dp, i, i, C.c_ulong, C.c_double, C.POINTER(vp)]
     L.mgcfd_mesh_load.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp)]
@@ -228,7 +231,7 @@ class Solver:
 
     def __init__(self, levels: int, mesh_variant: int, device: int = 0, flux_mode: int = FLUX_SORTED_SEGMENT,
                  ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0, use_graph: bool = True, timing: bool = False,
-                 pipeline: bool = True, pdl: bool = True):
+                 pipeline: bool = True, pdl: bool = True, visit: bool = True):
         L = lib()
         opt = Options()
         L.mgcfd_default_options(C.byref(opt))
@@ -236,6 +239,7 @@ class Solver:
         opt.use_graph, opt.timing = int(use_graph), int(timing)
         opt.no_pipeline = int(not pipeline)
         opt.no_pdl = int(not pdl)
+        opt.no_visit = int(not visit)
         self._h = C.c_void_p()
         self.levels, self.mesh_variant = levels, mesh_variant
         _check(L.mgcfd_create(levels, mesh_variant, C.byref(opt), C.byref(self._h)))
@@ -399,6 +403,12 @@ class Solver:
                 "used_slots", "max_halo", "bslots", "smem_bytes", "pipe_grid")
         return dict(zip(keys, out))
 
+    def visit_info(self, level):
+        """Configuration of the persistent visit kernel on `level` (include/mgcfd_b200.h mgcfd_visit_info)."""
+        out = (C.c_long * 8)()
+        _check(lib().mgcfd_visit_info(self._h, level, out))
+        return dict(zip(("visit", "supers_per_cta", "ctas", "ring_rounds", "resident", "super_rows", "smem_bytes", "halo_rows"), out))
+
     def permutation(self, level):
         p = np.empty(self._nel[level], dtype=np.int64)
         _check(lib().mgcfd_get_permutation(self._h, level, _ptr(p)))
@@ -505,6 +515,27 @@ def plan_emulate_flux(level: dict, variables, mask: int = 7, ordering: int = ORD
     _check(lib().mgcfd_plan_emulate_flux(level["nel"], _ptr(level.get("coords")), level["nI"], level["nB"], level["nW"], _ptr(e), ordering, tile_nodes,
                                          flux_mode, _ptr(var), mask, _ptr(out)))
     return out
+
+
+def plan_emulate_visit_flux(level: dict, variables, supers: int, mask: int = 7):
+    """Host-only checking aid: the fluxes the visit kernel's threads accumulate from the super-tile descriptors / halo lists /
+    re-addressed edge rounds of a plan with `supers` super-tiles (mgcfd_plan_emulate_visit_flux).  Returns (fluxes, info dict)."""
+    var = np.ascontiguousarray(variables, dtype=np.float64).reshape(-1)
+    out = np.zeros(5 * level["nel"])
+    e = np.ascontiguousarray(level["edges"])
+    info = (C.c_long * 8)()
+    _check(lib().mgcfd_plan_emulate_visit_flux(level["nel"], _ptr(level.get("coords")), level["nI"], level["nB"], level["nW"], _ptr(e), supers,
+                                               _ptr(var), mask, _ptr(out), info))
+    keys = ("supers", "max_tiles", "max_halo", "halo_total", "max_rounds", "tiles", "rows")
+    return out, dict(zip(keys, info))
+
+
+def plan_visit_config(level: dict, num_sms: int = 148):
+    """Host-only: the visit-kernel configuration the library would choose for `level` on a device with `num_sms` SMs."""
+    e = np.ascontiguousarray(level["edges"])
+    info = (C.c_long * 8)()
+    _check(lib().mgcfd_plan_visit_config(level["nel"], _ptr(level.get("coords")), level["nI"], level["nB"], level["nW"], _ptr(e), num_sms, info))
+    return dict(zip(("visit", "supers_per_cta", "ctas", "ring_rounds", "resident", "super_rows", "smem_bytes", "halo_rows"), info))
 
 
 def plan_emulate_transfers(fine: dict, coarse: dict, var_f, res_f, res_c, var_c, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0):

@@ -13,6 +13,7 @@
 #include "../../include/mgcfd_b200.h"
 #include "host_mesh.h"
 #include "kernels.cuh"
+#include "visit_kernel.cuh"
 #include "assess_kernels.cuh"
 #include "plan.h"
 #include "partition.h"
@@ -82,14 +83,18 @@ struct Level {
     long nsend = 0, nghost = 0, n_owned = 0;
     int* d_send_idx = nullptr; double *sendbuf = nullptr, *recvtmp = nullptr;
     P2PPeer* d_peers = nullptr; int npeers = 0;    // p2p: peers of this level
-    // in-kernel halo exchange (MGCFD_P2P_FUSED): node -> (peer, remote row) CSR, per-tile flags, the peers' record buffers
+    // multi-GPU, peer-to-peer plane: node -> (peer, remote row) CSR, per-tile flags, where the peers keep their copies
     std::vector<int> h_send_idx;                   // send list in device numbering (host copy)
     std::vector<P2PPeer> h_peers;                  // host copy of d_peers
     int *d_tgt_off = nullptr, *d_tgt_peer = nullptr, *d_tgt_row = nullptr;
     unsigned char* d_tile_sends = nullptr;
-    double** d_peer_bufs[3] = {nullptr, nullptr, nullptr};     // [npeers] peers' buf[b]
-    std::vector<void*> peer_buf_maps;              // IPC mappings to close
-    int pipe_grid_dist = 0;
+    PeerOut* d_peer_out = nullptr;
+    // the persistent visit kernel (visit_kernel.cuh): one launch per smoothing visit
+    bool visit = false;
+    int vK = 1, vG = 0, vR = 1, v_resident = 0, v_srmax = 0;
+    size_t v_smem = 0;
+    unsigned char *d_desc = nullptr, *d_vslots = nullptr;
+    int* d_cta_rows = nullptr;
     double* V(int i) const { return buf[i]; }
 };
 
@@ -115,9 +120,9 @@ struct Dist {
     long exchanges = 0;
     // direct peer-to-peer exchange (CUDA IPC windows; mgcfd_dist_p2p_prepare / _attach): replaces NCCL on the data path
     bool p2p = false, want_graph = false;
-    bool fused = false;                        // MGCFD_P2P_FUSED=1: the stage kernels exchange their halo rows themselves
-    unsigned char* win = nullptr;              // my window: flags[64] | red[2][64][8] | staging per level (2 parities)
+    unsigned char* win = nullptr;              // my window: flags[64] | red[2][64][8] | staging per level (2 parities); the start of the slab
     size_t win_bytes = 0;
+    std::vector<size_t> buf_off;               // per level: byte offsets of buf[0..2] and res inside the slab (4 per level)
     std::vector<long> stage_off;               // per level: offset (in doubles, from the window's staging base) of parity 0; parity 1 follows
     std::vector<void*> peer_win;               // [nranks] mapped windows (mine at [rank])
     unsigned long long* d_op = nullptr;        // device: operation number (identical on every rank), bumped by each operation's kernel
@@ -132,6 +137,12 @@ struct mgcfd_ctx {
     mgcfd_options opt;
     Dist dist;
     double* d_rms_sums = nullptr;
+    unsigned char* slab = nullptr;             // ONE allocation: [peer-to-peer window |] record buffers and residual planes of every level
+    size_t slab_bytes = 0;                     // (one CUDA IPC handle exposes everything other ranks write)
+    unsigned int* d_bar = nullptr;             // grid barrier word of the visit kernel
+    double* d_cta_min = nullptr;               // [num_sms] per-CTA minima, [num_sms * 5] per-CTA RMS sums
+    double* d_cta_rms = nullptr;
+    std::map<std::string, long> graph_launches;
     int levels = 0, variant = 2;
     bool finalized = false;
     std::vector<Level> L;
@@ -261,6 +272,9 @@ int nccl_load() {
         if (r_ != ncclSuccess) { g_err = std::string(#call) + ": " + g_nccl.GetErrorString(r_); return MGCFD_ERR_COMM; } \
     } while (0)
 
+// multi-GPU with the peer-to-peer plane: the kernels deliver the rows they produce themselves
+bool dist_inkernel(mgcfd_ctx* c) { return c->dist.active && c->dist.p2p; }
+
 // global minimum of the per-rank min-dt bit patterns (positive doubles order like their bits)
 int p2p_allreduce(mgcfd_ctx* c, double* vals, int n, int is_min) {
     Dist& d = c->dist;
@@ -298,8 +312,10 @@ int p2p_exchange(mgcfd_ctx* c, int l, const double* src, double* dst) {
 int dist_exchange_records(mgcfd_ctx* c, int l, double* recs) {
     if (!c->dist.active) return MGCFD_OK;
     Level& v = c->L[l];
-    if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
+    // peer-to-peer plane: the epoch number (Dist::d_op) must advance alike on EVERY rank, so a rank without halo at this level
+    // still runs the (empty) operation -- skipping it would leave the rank one epoch behind for good
     if (c->dist.p2p) return p2p_exchange<8, false>(c, l, recs, recs);
+    if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
     if (v.nsend) { k_pack_records<<<(unsigned)blocks_for(4 * v.nsend, 256), 256, 0, c->stream>>>(recs, v.d_send_idx, v.nsend, v.sendbuf); CKRC(post_launch(c)); }
     NK(g_nccl.GroupStart());
     for (int p = 0; p < c->dist.nranks; p++) {
@@ -314,8 +330,8 @@ int dist_exchange_records(mgcfd_ctx* c, int l, double* recs) {
 int dist_exchange_residuals(mgcfd_ctx* c, int l) {
     if (!c->dist.active) return MGCFD_OK;
     Level& v = c->L[l];
-    if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
     if (c->dist.p2p) return p2p_exchange<5, true>(c, l, v.res, v.res);
+    if (v.nsend == 0 && v.nghost == 0) return MGCFD_OK;
     if (v.nsend) { k_pack_soa5<<<(unsigned)blocks_for(v.nsend, 256), 256, 0, c->stream>>>(v.res, v.npad, v.d_send_idx, v.nsend, v.sendbuf); CKRC(post_launch(c)); }
     NK(g_nccl.GroupStart());
     for (int p = 0; p < c->dist.nranks; p++) {
@@ -339,11 +355,11 @@ int launch_stage_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     k_stage<TN, SCATTER, FUSED><<<(unsigned)v.ntiles, TN, v.smem_bytes, c->stream>>>(a);
     return post_launch(c);
 }
-template <int TN, bool SCATTER, bool DIST = false>
+template <int TN, bool SCATTER>
 int launch_pipe_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
-    const int grid = DIST ? v.pipe_grid_dist : v.pipe_grid;
+    const int grid = v.pipe_grid;
     if (c->opt.no_pdl) {
-        k_stage_pipe<TN, SCATTER, DIST><<<(unsigned)grid, TN, v.pipe_smem, c->stream>>>(a);
+        k_stage_pipe<TN, SCATTER><<<(unsigned)grid, TN, v.pipe_smem, c->stream>>>(a);
         return post_launch(c);
     }
     // programmatic dependent launch: this kernel may start (barrier set-up, header + edge-stream prefetch: static data) while
@@ -355,30 +371,8 @@ int launch_pipe_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, k_stage_pipe<TN, SCATTER, DIST>, a));
+    CK(cudaLaunchKernelEx(&cfg, k_stage_pipe<TN, SCATTER>, a));
     return post_launch(c);
-}
-// in-kernel halo exchange: occupancy and shared-memory attribute of the DIST instantiation (its register count differs)
-template <int TN, bool SCATTER>
-int setup_pipe_dist_t(mgcfd_ctx* c, Level& v) {
-    CK(cudaFuncSetAttribute(k_stage_pipe<TN, SCATTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(v.pipe_smem, 48 * 1024)));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stage_pipe<TN, SCATTER, true>, TN, v.pipe_smem));
-    if (per_sm < 1) { g_err = "the in-kernel exchange variant of the stage kernel does not fit an SM"; return MGCFD_ERR_ARG; }
-    v.pipe_grid_dist = (int)std::min<long>(v.ntiles, (long)per_sm * c->num_sms);
-    return MGCFD_OK;
-}
-int setup_pipe_dist(mgcfd_ctx* c, Level& v) {
-    const bool sc = v.plan.scatter;
-    if (v.TN == 128) return sc ? setup_pipe_dist_t<128, true>(c, v) : setup_pipe_dist_t<128, false>(c, v);
-    if (v.TN == 256) return sc ? setup_pipe_dist_t<256, true>(c, v) : setup_pipe_dist_t<256, false>(c, v);
-    return sc ? setup_pipe_dist_t<512, true>(c, v) : setup_pipe_dist_t<512, false>(c, v);
-}
-int launch_stage_dist(mgcfd_ctx* c, Level& v, const StageArgs& a) {
-    const bool sc = v.plan.scatter;
-    if (v.TN == 128) return sc ? launch_pipe_t<128, true, true>(c, v, a) : launch_pipe_t<128, false, true>(c, v, a);
-    if (v.TN == 256) return sc ? launch_pipe_t<256, true, true>(c, v, a) : launch_pipe_t<256, false, true>(c, v, a);
-    return sc ? launch_pipe_t<512, true, true>(c, v, a) : launch_pipe_t<512, false, true>(c, v, a);
 }
 // persistent grid of the pipelined kernel: as many CTAs as fit on the device at once (occupancy API), never more than tiles
 template <int TN, bool SCATTER>
@@ -531,26 +525,84 @@ int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
 // fused path: only the global minimum is a kernel of its own (one launch); min/volume resp. the legacy local form are
 // evaluated inside the stage kernels (step_factor_of)
 int min_dt_fused(mgcfd_ctx* c, int l) {
-    if (c->variant == MGCFD_MESH_FVCORR) return MGCFD_OK;
+    if (c->variant == MGCFD_MESH_FVCORR) {
+        // no global minimum in the legacy form; with the in-kernel data plane the stage kernels still must not read ghost rows before
+        // their owners' last kernel has delivered them: an (otherwise unused) all-reduce is that synchronisation point
+        if (dist_inkernel(c)) return p2p_allreduce(c, c->d_rms_sums + 7, 1, 0);
+        return MGCFD_OK;
+    }
     Level& v = c->L[l];
     Timed tm(c, K_STEP, l, v.nel);
-    if (c->dist.fused) {
-        // the last block of the reduction kernel all-reduces the minimum over the ranks itself (k_p2p_allreduce's protocol)
-        Dist& d = c->dist;
-        P2PReduce pr;
-        pr.nranks = d.nranks; pr.me = d.rank; pr.red_of_rank = d.d_red_of_rank; pr.flag_of_rank = d.d_flag_of_rank;
-        pr.my_flags = (const unsigned long long*)d.win; pr.my_red = (const double*)(d.win + P2P_FLAGS_BYTES);
-        pr.op_counter = d.d_op; pr.red_counter = d.d_ctr;
-        k_min_dt_p2p<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.vol_root, v.blockmins, c->d_ticket, c->d_minbits, pr);
-        return post_launch(c);
-    }
     k_min_dt<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.vol_root, v.blockmins, c->d_ticket, c->d_minbits);
     CKRC(post_launch(c));
     return dist_allreduce_min(c);
 }
 
+// the whole visit as ONE persistent kernel (visit_kernel.cuh): minimum dt, three stages, residual, RMS sums; multi-GPU: the halo
+// exchange rides on its grid barriers
+DistArgs dist_args(mgcfd_ctx* c, Level& v, const P2PPeer* wait_peers, int nwait) {
+    DistArgs da;
+    memset(&da, 0, sizeof(da));
+    Dist& d = c->dist;
+    da.nranks = d.nranks; da.me = d.rank;
+    da.peers = v.d_peers; da.npeers = v.npeers; da.peer_out = v.d_peer_out;
+    da.tgt_off = v.d_tgt_off; da.tgt_peer = v.d_tgt_peer; da.tgt_row = v.d_tgt_row; da.tile_sends = v.d_tile_sends;
+    da.wait_peers = wait_peers; da.nwait = nwait;
+    da.red_of_rank = d.d_red_of_rank; da.flag_of_rank = d.d_flag_of_rank;
+    da.my_flags = (const unsigned long long*)d.win; da.my_red = (const double*)(d.win + P2P_FLAGS_BYTES);
+    da.op_counter = d.d_op; da.red_counter = d.d_ctr;
+    return da;
+}
+DistTail dist_tail(mgcfd_ctx* c, Level& out_level, int ib, const P2PPeer* wait_peers, int nwait) {
+    DistTail t;
+    memset(&t, 0, sizeof(t));
+    Dist& d = c->dist;
+    t.wait_peers = wait_peers; t.nwait = nwait;
+    t.peers = out_level.d_peers; t.npeers = out_level.npeers; t.peer_out = out_level.d_peer_out; t.ib = ib;
+    t.tgt_off = out_level.d_tgt_off; t.tgt_peer = out_level.d_tgt_peer; t.tgt_row = out_level.d_tgt_row;
+    t.op_counter = d.d_op; t.ticket = d.d_ticket; t.my_flags = (const unsigned long long*)d.win;
+    return t;
+}
+
+int smooth_visit(mgcfd_ctx* c, int l) {
+    Level& v = c->L[l];
+    const int X = v.i_var, A = v.i_tmp, B = v.i_old;
+    Timed tm(c, K_FLUX, l, MGCFD_RK * v.nI);
+    VisitArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bufX = v.V(X); a.bufA = v.V(A); a.bufB = v.V(B); a.ibX = X; a.ibA = A; a.ibB = B;
+    a.res = v.res; a.sf = v.sf; a.vol = v.vol; a.vol_root = v.vol_root; a.stride = v.npad;
+    a.legacy = (c->variant == MGCFD_MESH_FVCORR);
+    a.desc = v.d_desc; a.desc_stride = v.plan.visit.desc_stride; a.maxt = v.plan.visit.maxt; a.hpad = v.plan.visit.hpad;
+    a.vslots = v.d_vslots; a.bslots = v.bslots; a.cta_rows = v.d_cta_rows;
+    a.K = v.vK; a.sr_max = v.v_srmax; a.resident = v.v_resident; a.R = v.vR;
+    a.k2 = 2.0 * c->kdiss;
+    a.bad_key = c->d_badkey; a.old_of_new = v.old_of_new;
+    a.stage_seq0 = c->stage_seq & 0xFFFFFFull; c->stage_seq += MGCFD_RK;
+    a.bar = c->d_bar; a.cta_min = c->d_cta_min; a.min_bits = c->d_minbits;
+    if (l == 0) {
+        a.cta_rms = c->d_cta_rms; a.rms_out = c->d_rms; a.rms_counter = c->d_rms_counter; a.rms_cap = c->rms_cap - 1;
+        a.nel_global = (double)(c->dist.active ? v.nel_global : v.nel);
+    }
+    const bool dist = dist_inkernel(c);
+    if (dist) a.d = dist_args(c, v, v.d_peers, v.npeers);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)v.vG); cfg.blockDim = dim3(VNT); cfg.dynamicSmemBytes = v.v_smem; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = c->opt.no_pdl ? 0 : 1;
+    if (dist) CK(cudaLaunchKernelEx(&cfg, k_visit<true>, a)); else CK(cudaLaunchKernelEx(&cfg, k_visit<false>, a));
+    CKRC(post_launch(c));
+    if (dist) c->dist.exchanges += MGCFD_RK;
+    v.i_old = X; v.i_var = A; v.i_tmp = B;
+    return MGCFD_OK;
+}
+
 int smooth_fused(mgcfd_ctx* c, int l) {
     Level& v = c->L[l];
+    if (v.visit && (!c->dist.active || c->dist.p2p)) return smooth_visit(c, l);
     CKRC(min_dt_fused(c, l));
     const int X = v.i_var, A = v.i_tmp, B = v.i_old;   // the previous old_variables are dead once a smooth starts
     // timing: on one GPU the three stage launches of the visit share ONE event bracket (3 * nI edge updates), so that they run as
@@ -573,20 +625,6 @@ int smooth_fused(mgcfd_ctx* c, int l) {
             a.res = v.res;
             a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
         }
-        if (c->dist.fused && v.npeers > 0) {
-            // the stage kernel stores the rows its peers hold as ghosts itself and signals them; the next stage kernel (or the
-            // wait kernel after the last stage) waits for the peers' signal: no exchange kernel between the stages
-            Dist& d = c->dist;
-            const int b = (a.vout == v.buf[0]) ? 0 : (a.vout == v.buf[1] ? 1 : 2);
-            a.tile_sends = v.d_tile_sends; a.tgt_off = v.d_tgt_off; a.tgt_peer = v.d_tgt_peer; a.tgt_row = v.d_tgt_row;
-            a.peer_out = v.d_peer_bufs[b]; a.peers = v.d_peers; a.npeers = v.npeers;
-            a.op_counter = d.d_op; a.ticket = d.d_ticket; a.my_flags = (const unsigned long long*)d.win;
-            CKRC(launch_stage_dist(c, v, a));
-            stage_tm.reset();
-            d.exchanges++;
-            if (j == MGCFD_RK - 1) { k_p2p_wait<<<1, 64, 0, c->stream>>>(v.d_peers, v.npeers, d.d_op, (const unsigned long long*)d.win); CKRC(post_launch(c)); }
-            continue;
-        }
         CKRC(launch_stage(c, v, a, true));
         stage_tm.reset();
         CKRC(dist_exchange_records(c, l, a.vout));
@@ -600,16 +638,39 @@ int smooth_fused(mgcfd_ctx* c, int l) {
 int do_restrict(mgcfd_ctx* c, int lc) {
     Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
     Timed tm(c, K_RESTRICT, lc, vf.nel);
-    k_restrict<<<(unsigned)blocks_for(vc.ncomp, 128), 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids);
+    const unsigned nb = (unsigned)blocks_for(vc.ncomp, 128);
+    if (dist_inkernel(c)) {
+        // reads the fine level's ghost rows (wait for the fine level's peers), delivers the coarse rows itself
+        const DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers);
+        k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, t);
+        c->dist.exchanges++;
+        return post_launch(c);
+    }
+    DistTail none;
+    memset(&none, 0, sizeof(none));
+    k_restrict<false><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, none);
     CKRC(post_launch(c));
     return dist_exchange_records(c, lc, vc.V(vc.i_var));
 }
 int do_prolong(mgcfd_ctx* c, int lf) {
     Level& vf = c->L[lf]; Level& vc = c->L[lf + 1];
     Timed tm(c, K_PROLONG, lf, vf.nI);
+    const unsigned nb = (unsigned)blocks_for(vf.ncomp, 128);
+    if (dist_inkernel(c)) {
+        // the coarse residuals of ghost parents were delivered by the coarse visit's last stage when that level runs the visit
+        // kernel; otherwise they are exchanged here.  The prolonged rows are delivered by the kernel itself.
+        if (!vc.visit) CKRC(dist_exchange_residuals(c, lf + 1));
+        const DistTail t = dist_tail(c, vf, vf.i_var, vc.d_peers, vc.npeers);
+        k_prolong<true><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
+                                                   vc.res, vf.res, vf.V(vf.i_var), t);
+        c->dist.exchanges++;
+        return post_launch(c);
+    }
     CKRC(dist_exchange_residuals(c, lf + 1));
-    k_prolong<<<(unsigned)blocks_for(vf.ncomp, 128), 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
-                                                                        vc.res, vf.res, vf.V(vf.i_var));
+    DistTail none;
+    memset(&none, 0, sizeof(none));
+    k_prolong<false><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
+                                                vc.res, vf.res, vf.V(vf.i_var), none);
     CKRC(post_launch(c));
     return dist_exchange_records(c, lf, vf.V(vf.i_var));
 }
@@ -654,14 +715,79 @@ int check_level(mgcfd_ctx* c, int l, bool need_final = true) {
 }
 
 void free_level(Level& v) {
-    void* ptrs[] = {v.buf[0], v.buf[1], v.buf[2], v.res, v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
+    // buf[] and res live in the context's slab
+    void* ptrs[] = {v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
                     v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers,
-                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_bufs[0], v.d_peer_bufs[1], v.d_peer_bufs[2], v.ewt_pre};
-    for (void* m : v.peer_buf_maps) if (m) cudaIpcCloseMemHandle(m);     // peers' record buffers (in-kernel exchange)
+                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_out, v.ewt_pre, v.d_desc, v.d_vslots, v.d_cta_rows};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
+
+// ---- the visit kernel's configuration of a level (visit_kernel.cuh) ------------------------------------------------------------
+struct VisitCfg { bool ok = false; int K = 1, G = 0, R = 1, resident = 0, sr_max = 0; size_t smem = 0; };
+constexpr size_t VISIT_SMEM_LIMIT = 230000;      // 227 KB per CTA minus the kernel's static shared memory
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
+// shared memory of k_visit for a plan built with G * K super-tiles: ring (VG groups x VRING entries x R rounds) + record buffers
+// (resident: two own-row buffers + one halo buffer; streaming: two buffers of own + halo rows) + four descriptor buffers.
+// Picks the largest R <= half a tile's rounds that fits.
+VisitCfg visit_config(const LevelPlan& P, int G, int K) {
+    VisitCfg cfg;
+    const VisitPlan& V = P.visit;
+    if (V.ns <= 0 || V.ns != G * K) return cfg;
+    const size_t own = 64 * (size_t)VT * V.maxt, halo = 64 * (size_t)V.hpad, desc = (K == 1 ? 1 : 4) * (size_t)V.desc_stride;
+    const bool resident = (K == 1) && env_int("MGCFD_VISIT_RESIDENT", 1) != 0;
+    const size_t recs = resident ? 2 * own + halo : 2 * (own + halo);
+    int R = std::max(1, (V.max_rounds + 1) / 2);
+    R = std::min(R, std::max(1, env_int("MGCFD_VISIT_R", 1 << 20)));
+    auto total = [&](int r) { return (size_t)VG * VRING * r * VT * 26 + recs + desc; };
+    while (R > 1 && total(R) > VISIT_SMEM_LIMIT) R--;
+    if (total(R) > VISIT_SMEM_LIMIT) return cfg;
+    // equal chunks: ceil(max_rounds / R) chunks per tile
+    const int nchunks = std::max(1, (V.max_rounds + R - 1) / R);
+    R = std::max(1, (V.max_rounds + nchunks - 1) / nchunks);
+    cfg.ok = true; cfg.K = K; cfg.G = G; cfg.R = R; cfg.resident = resident ? 1 : 0; cfg.sr_max = VT * V.maxt; cfg.smem = total(R);
+    return cfg;
+}
+// Builds the level plan for the visit kernel: K = 1 (own rows resident) when that fits with a ring of at least two rounds per
+// entry, else the smallest K whose double-buffered super-tiles fit.  Returns false (plan untouched or rebuilt by the caller) when
+// the level cannot run the visit kernel.
+bool plan_for_visit(int num_sms, LevelPlan& plan_out, const HostLevel& H, PlanOptions po, VisitCfg& out) {
+    const long n_own = H.n_owned >= 0 ? H.n_owned : H.nel;
+    const long ntiles = std::max<long>(1, (n_own + VT - 1) / VT);
+    const int G = (int)std::min<long>(num_sms, ntiles);
+    po.tile_nodes = VT;
+    const int forceK = env_int("MGCFD_VISIT_K", 0);
+    auto good = [&](const VisitCfg& f, const LevelPlan& P) { return f.ok && f.R >= std::min(2, std::max(1, (P.visit.max_rounds + 1) / 2)); };
+    VisitCfg best; LevelPlan bestP;
+    int K = forceK > 0 ? forceK : 1;
+    // the own rows of a super-tile alone (double-buffered, 13-bit row index) bound K from below
+    if (forceK <= 0) while ((long)G * K < ntiles && (2 * 64 * (size_t)VT * ((ntiles + (long)G * K - 1) / ((long)G * K)) > VISIT_SMEM_LIMIT * 7 / 10 ||
+                                                      VT * ((ntiles + (long)G * K - 1) / ((long)G * K)) >= 8192)) K++;
+    for (int tries = 0; tries < 6; tries++) {
+        if ((long)G * K > ntiles) break;
+        po.supers = G * K;
+        LevelPlan P;
+        build_level_plan(H, po, P);
+        const VisitCfg f = visit_config(P, G, K);
+        if (f.ok && (!best.ok || f.R > best.R)) { best = f; bestP = P; }
+        if (forceK > 0 || good(f, P)) break;
+        if (K == 1) {
+            // estimate the smallest K that fits from this build: halo rows scale like rows^(2/3)
+            const double own1 = (double)VT * P.visit.maxt, h1 = (double)P.visit.hpad;
+            int k = 2;
+            for (; k < 64; k++) {
+                const double rows = std::ceil(own1 / k / VT) * VT + h1 * std::pow((double)k, -2.0 / 3.0);
+                if (2 * 64 * rows + (double)VG * VRING * 2 * VT * 26 + 4 * (32.0 * std::ceil(own1 / k / VT) + 4 * h1 * std::pow((double)k, -2.0 / 3.0) + 16) <= (double)VISIT_SMEM_LIMIT) break;
+            }
+            K = k;
+        } else K++;
+    }
+    if (!best.ok) return false;
+    plan_out = std::move(bestP);
+    out = best;
+    return true;
+}
 }  // namespace
 
 extern "C" {
@@ -733,6 +859,10 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     c->rms_cap = 4096 + 1;
     CK(cudaMalloc((void**)&c->d_rms, sizeof(double) * 6 * c->rms_cap));
     CK(cudaMalloc((void**)&c->d_rms_sums, sizeof(double) * 8));
+    CK(cudaMemset(c->d_rms_sums, 0, sizeof(double) * 8));
+    CK(cudaMalloc((void**)&c->d_bar, sizeof(unsigned int))); CK(cudaMemset(c->d_bar, 0, sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&c->d_cta_min, sizeof(double) * c->num_sms));
+    CK(cudaMalloc((void**)&c->d_cta_rms, sizeof(double) * 5 * c->num_sms));
     CK(cudaMalloc((void**)&c->d_rms_counter, sizeof(int)));
     CK(cudaMemset(c->d_rms_counter, 0, sizeof(int)));
     mgcfd_far_field_conditions(c->ff, c->ffc);
@@ -751,7 +881,8 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_ticket); cudaFree(c->d_rms); cudaFree(c->d_rms_counter); cudaFree(c->d_rms_sums);
     if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
     for (int p = 0; p < (int)c->dist.peer_win.size(); p++) if (p != c->dist.rank && c->dist.peer_win[p]) cudaIpcCloseMemHandle(c->dist.peer_win[p]);
-    cudaFree(c->dist.win); cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
+    cudaFree(c->slab); cudaFree(c->d_bar); cudaFree(c->d_cta_min); cudaFree(c->d_cta_rms);
+    cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -791,7 +922,19 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     PlanOptions po; po.ordering = c->opt.ordering; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
     po.strict = (c->opt.flux_mode != MGCFD_FLUX_ATOMIC);     // the atomic baseline runs on any numbering, tiled or not
     po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : auto_tile_nodes(H.n_owned >= 0 ? H.n_owned : nel, nI, c->num_sms);
-    try { build_level_plan(H, po, v.plan); }
+    // levels up to ~1 M nodes run the persistent visit kernel (one launch per smoothing visit, visit_kernel.cuh): sorted-segment
+    // mode, the partitioning order, 128-node tiles grouped into super-tiles; larger levels stream through the stage kernels
+    v.visit = false;
+    const long n_own = H.n_owned >= 0 ? H.n_owned : nel;
+    const bool want_visit = !c->opt.no_visit && env_int("MGCFD_VISIT", 1) != 0 && c->opt.flux_mode == MGCFD_FLUX_SORTED_SEGMENT &&
+                            c->opt.ordering == MGCFD_ORDER_PARTITION_RCM && (c->opt.tile_nodes == 0 || c->opt.tile_nodes == VT) &&
+                            !c->opt.no_pipeline && n_own <= (long)env_int("MGCFD_VISIT_MAX_NODES", 1200000);
+    try {
+        VisitCfg cfg;
+        if (want_visit && plan_for_visit(c->num_sms, v.plan, H, po, cfg)) {
+            v.visit = true; v.vK = cfg.K; v.vG = cfg.G; v.vR = cfg.R; v.v_resident = cfg.resident; v.v_srmax = cfg.sr_max; v.v_smem = cfg.smem;
+        } else build_level_plan(H, po, v.plan);
+    }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     v.uploaded = true;
     return MGCFD_OK;
@@ -803,6 +946,31 @@ int mgcfd_finalize(mgcfd_ctx* c) {
     for (auto& v : c->L) if (!v.uploaded) { g_err = "not every level has been uploaded"; return MGCFD_ERR_ARG; }
     CK(cudaSetDevice(c->opt.device));
     cudaStream_t s = c->stream;
+    {   // one slab: [peer-to-peer window |] three record buffers + residual planes per level (what other ranks write into)
+        auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+        Dist& d = c->dist;
+        size_t off = 0;
+        if (d.active) {
+            d.stage_off.assign(c->levels, 0);
+            size_t doubles = 0;
+            for (int l = 0; l < c->levels; l++) { const LevelPlan& P = c->L[l].plan; d.stage_off[l] = (long)doubles; doubles += 2 * 8 * (size_t)std::max<long>(P.nel - P.n_owned, 1); }
+            d.win_bytes = P2P_HDR_BYTES + doubles * sizeof(double);
+            off = up(d.win_bytes);
+        }
+        d.buf_off.assign(4 * (size_t)c->levels, 0);
+        for (int l = 0; l < c->levels; l++) {
+            const size_t npad = (size_t)c->L[l].plan.npad;
+            for (int b = 0; b < 3; b++) { d.buf_off[4 * l + b] = off; off += up(sizeof(double) * 8 * npad); }
+            d.buf_off[4 * l + 3] = off; off += up(sizeof(double) * 5 * npad);
+        }
+        c->slab_bytes = off;
+        CK(cudaMalloc((void**)&c->slab, c->slab_bytes));
+        if (d.active) { d.win = c->slab; CK(cudaMemsetAsync(d.win, 0, up(d.win_bytes), s)); }
+        for (int l = 0; l < c->levels; l++) {
+            for (int b = 0; b < 3; b++) c->L[l].buf[b] = (double*)(c->slab + d.buf_off[4 * l + b]);
+            c->L[l].res = (double*)(c->slab + d.buf_off[4 * l + 3]);
+        }
+    }
     for (int l = 0; l < c->levels; l++) {
         Level& v = c->L[l];
         LevelPlan& P = v.plan;
@@ -827,8 +995,6 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         }
         v.untiled = P.oversize || v.smem_bytes > 227 * 1024;
         if (v.untiled && c->opt.flux_mode != MGCFD_FLUX_ATOMIC) { g_err = "tile halo too large for shared memory; use a smaller tile_nodes or a locality-preserving ordering"; return MGCFD_ERR_ARG; }
-        for (int b = 0; b < 3; b++) CK(cudaMalloc((void**)&v.buf[b], sizeof(double) * 8 * v.npad));
-        CK(cudaMalloc((void**)&v.res, sizeof(double) * 5 * v.npad));
         CK(cudaMalloc((void**)&v.sf, sizeof(double) * v.npad));
         // volumes in new order; padding: volume 1, root +inf so that padded nodes never win the min-dt reduction
         std::vector<double> vol(v.npad, 1.0), root(v.npad, INFINITY);
@@ -843,6 +1009,23 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         CKRC(dev_upload(&v.hdrs, P.hdrs, s)); CKRC(dev_upload(&v.slots, P.slots, s)); CKRC(dev_upload(&v.bslots, P.bslots, s));
         v.pipe = false;
         if (!c->opt.no_pipeline && !v.untiled) CKRC(setup_pipe(c, v));
+        if (v.visit) {
+            // the visit kernel's streams; its grid must be co-resident (one CTA per SM)
+            const VisitPlan& V = P.visit;
+            CKRC(dev_upload(&v.d_desc, V.desc, s)); CKRC(dev_upload(&v.d_vslots, V.vslots, s));
+            std::vector<int> rows(v.vG + 1);
+            for (int g = 0; g <= v.vG; g++) rows[g] = int(V.super_off[(size_t)std::min<long>((long)g * v.vK, V.ns)] * VT);
+            CKRC(dev_upload(&v.d_cta_rows, rows, s));
+            static size_t attr_bytes = 0;
+            if (v.v_smem > attr_bytes) {
+                CK(cudaFuncSetAttribute(k_visit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
+                CK(cudaFuncSetAttribute(k_visit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
+                attr_bytes = v.v_smem;
+            }
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_visit<true>, VNT, v.v_smem));
+            if (per_sm < 1 || v.vG > c->num_sms) { g_err = "the visit kernel does not fit an SM with this level's configuration"; return MGCFD_ERR_ARG; }
+        }
         if (v.nel_global == 0) v.nel_global = v.nel;
         v.n_owned = P.n_owned;
         if (c->dist.active) {
@@ -882,6 +1065,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
     // host copies are no longer needed, except the plan pieces used lazily (flat/CSR) and by introspection
     for (auto& v : c->L) {
         v.host = HostLevel();
+        v.plan.visit.vslots.clear(); v.plan.visit.vslots.shrink_to_fit();
         if (v.npad > 2000000) {   // big levels: drop the host copy of the edge stream (introspection needs it only on small meshes)
             v.plan.slots.clear(); v.plan.slots.shrink_to_fit();
             v.plan.bslots.clear(); v.plan.bslots.shrink_to_fit();
@@ -996,14 +1180,6 @@ void advance_roles_one_cycle(mgcfd_ctx* c) {
         for (int k = 0; k < visits; k++) { Level& v = c->L[l]; const int X = v.i_var, A = v.i_tmp, B = v.i_old; v.i_old = X; v.i_var = A; v.i_tmp = B; }
     }
 }
-long launches_per_cycle(mgcfd_ctx* c) {
-    long per_cycle = 0;
-    for (int l = 0; l < c->levels; l++) {
-        const int visits = (c->levels == 1 || l == 0 || l == c->levels - 1) ? 1 : 2;
-        per_cycle += visits * (MGCFD_RK + (c->variant == MGCFD_MESH_FVCORR ? 0 : 1)) + (l == 0 ? 1 : 0);
-    }
-    return per_cycle + 2 * (c->levels - 1);
-}
 // enqueues one V-cycle on the context's stream (a graph replay when enabled); no host synchronisation
 int enqueue_one_cycle(mgcfd_ctx* c) {
     const bool graph = c->opt.use_graph && !c->opt.timing;
@@ -1018,6 +1194,7 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
         int rc = cycle_fused(c);
         cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
         c->capturing = false;
+        c->graph_launches[key] = c->launches - launches_before;
         c->launches = launches_before;        // capture recorded the launches, it did not run them
         if (rc != MGCFD_OK) { if (g) cudaGraphDestroy(g); return rc; }
         CK(ce);
@@ -1031,7 +1208,7 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
     }
     CK(cudaGraphLaunch(it->second, c->stream));
     advance_roles_one_cycle(c);
-    c->launches += launches_per_cycle(c);
+    c->launches += c->graph_launches[key];
     return MGCFD_OK;
 }
 }  // namespace
@@ -1159,6 +1336,17 @@ int mgcfd_get_permutation(mgcfd_ctx* c, int l, long* new_of_old) {
     memcpy(new_of_old, P.new_of_old.data(), sizeof(long) * P.nel);
     return MGCFD_OK;
 }
+int mgcfd_visit_info(mgcfd_ctx* c, int l, long info[8]) {
+    CKRC(check_level(c, l, false));
+    const Level& v = c->L[l];
+    memset(info, 0, sizeof(long) * 8);
+    info[0] = v.visit ? 1 : 0;
+    if (v.visit) {
+        info[1] = v.vK; info[2] = v.vG; info[3] = v.vR; info[4] = v.v_resident; info[5] = v.v_srmax; info[6] = (long)v.v_smem;
+        info[7] = v.plan.visit.halo_total;
+    }
+    return MGCFD_OK;
+}
 long mgcfd_check_colouring(mgcfd_ctx* c, int l) {
     if (check_level(c, l, false) != MGCFD_OK) return -1;
     return check_colouring(c->L[l].plan);
@@ -1276,6 +1464,45 @@ int mgcfd_plan_emulate_flux(long nel, const double* coords, long nI, long nB, lo
     } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     return MGCFD_OK;
 }
+// the visit kernel's streams of the same level (plan.h VisitPlan), grouped into `supers` super-tiles; info[0..7] = super-tiles, most
+// tiles per super-tile, most halo rows of a super-tile, halo rows in total, most rounds of a tile, tiles, padded rows, 0
+int mgcfd_plan_emulate_visit_flux(long nel, const double* coords, long nI, long nB, long nW, const void* edges, int supers,
+                                  const double* variables, int mask, double* fluxes, long info[8]) {
+    if (!variables || !fluxes || supers < 1) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    HostLevel H;
+    CKRC(host_level(H, nel, coords, nI, nB, nW, edges, nullptr));
+    PlanOptions po; po.ordering = MGCFD_ORDER_PARTITION_RCM; po.tile_nodes = VT; po.scatter = false; po.supers = supers;
+    double ff[5], ffc[12];
+    mgcfd_far_field_conditions(ff, ffc);
+    try {
+        LevelPlan P;
+        build_level_plan(H, po, P);
+        emulate_visit_flux(P, variables, mask, ff, ffc, 2.0 * (-0.5 * double(0.2f)), fluxes);
+        if (info) {
+            memset(info, 0, sizeof(long) * 8);
+            info[0] = P.visit.ns; info[1] = P.visit.maxt; info[2] = P.visit.max_halo; info[3] = P.visit.halo_total; info[4] = P.visit.max_rounds;
+            info[5] = P.ntiles; info[6] = P.npad;
+        }
+    } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    return MGCFD_OK;
+}
+// host-only: the configuration the library would choose for the visit kernel on a device with `num_sms` SMs;
+// info[0..7] = usable (0/1), super-tiles per CTA, CTAs, rounds per ring entry, resident, rows of the largest super-tile, shared memory, halo rows
+int mgcfd_plan_visit_config(long nel, const double* coords, long nI, long nB, long nW, const void* edges, int num_sms, long info[8]) {
+    if (!info || num_sms < 1) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    HostLevel H;
+    CKRC(host_level(H, nel, coords, nI, nB, nW, edges, nullptr));
+    PlanOptions po; po.ordering = MGCFD_ORDER_PARTITION_RCM; po.scatter = false;
+    memset(info, 0, sizeof(long) * 8);
+    try {
+        LevelPlan P; VisitCfg cfg;
+        if (plan_for_visit(num_sms, P, H, po, cfg)) {
+            info[0] = 1; info[1] = cfg.K; info[2] = cfg.G; info[3] = cfg.R; info[4] = cfg.resident; info[5] = cfg.sr_max; info[6] = (long)cfg.smem;
+            info[7] = P.visit.halo_total;
+        }
+    } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+    return MGCFD_OK;
+}
 int mgcfd_plan_emulate_transfers(long nel_f, const double* coords_f, long nI_f, long nB_f, long nW_f, const void* edges_f, const long* mg_map,
                                  long nel_c, const double* coords_c, long nI_c, long nB_c, long nW_c, const void* edges_c, int ordering,
                                  int tile_nodes, const double* var_f, const double* res_f, const double* res_c, double* var_c, double* var_f_out) {
@@ -1369,14 +1596,13 @@ int mgcfd_upload_partition(mgcfd_ctx* c, int levels, int mesh_variant, const voi
     return mgcfd_finalize(c);
 }
 // ---- direct peer-to-peer data path (CUDA IPC) -------------------------------------------------------------------------------
-// table layout (longs): [0] = levels, then per level: stage_off (doubles), nghost, recv_off[0..nranks]
-// MGCFD_P2P_FUSED=1 (every rank alike): the stage kernels exchange their halo rows themselves; the table then also
-// carries, per level, the first ghost row and the CUDA IPC handles of the three record buffers (8 longs each)
-static bool want_fused() { const char* e = getenv("MGCFD_P2P_FUSED"); return e && e[0] == '1'; }
-static const long FUSED_PER_LEVEL = 1 + 3 * 8;
+// table layout (longs): [0] = levels, then per level: stage_off (doubles), nghost, recv_off[0..nranks], then per level: first ghost
+// row, npad, byte offsets of the three record buffers and of the residual planes inside the slab.  ONE CUDA IPC handle per rank
+// exposes its slab (window + record buffers + residual planes of every level): that is everything other ranks ever write.
+static const long SLAB_PER_LEVEL = 6;
 long mgcfd_dist_p2p_table_len(mgcfd_ctx* c) {
     if (!c) return -1;
-    return 1 + (long)c->levels * (2 + c->dist.nranks + 1) + (want_fused() ? (long)c->levels * FUSED_PER_LEVEL : 0);
+    return 1 + (long)c->levels * (2 + c->dist.nranks + 1) + (long)c->levels * SLAB_PER_LEVEL;
 }
 int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long table_cap) {
     if (!c || !handle || !table) { g_err = "null argument"; return MGCFD_ERR_ARG; }
@@ -1385,20 +1611,14 @@ int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long tabl
     const long need = mgcfd_dist_p2p_table_len(c);
     if (table_cap < need) { g_err = "table too small"; return MGCFD_ERR_ARG; }
     CK(cudaSetDevice(c->opt.device));
-    if (!d.win) {
-        d.stage_off.assign(c->levels, 0);
-        size_t doubles = 0;
-        for (int l = 0; l < c->levels; l++) { d.stage_off[l] = (long)doubles; doubles += 2 * 8 * (size_t)std::max<long>(c->L[l].nghost, 1); }
-        d.win_bytes = P2P_HDR_BYTES + doubles * sizeof(double);
-        CK(cudaMalloc((void**)&d.win, d.win_bytes));
-        CK(cudaMemset(d.win, 0, d.win_bytes));
+    if (!d.d_op) {
         CK(cudaMalloc((void**)&d.d_ticket, 4)); CK(cudaMemset(d.d_ticket, 0, 4));
         CK(cudaMalloc((void**)&d.d_op, 8)); CK(cudaMemset(d.d_op, 0, 8));
         CK(cudaMalloc((void**)&d.d_ctr, 4 * (c->levels + 1))); CK(cudaMemset(d.d_ctr, 0, 4 * (c->levels + 1)));
         CK(cudaDeviceSynchronize());
     }
     cudaIpcMemHandle_t h;
-    CK(cudaIpcGetMemHandle(&h, d.win));
+    CK(cudaIpcGetMemHandle(&h, c->slab));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     memcpy(handle, &h, 64);
     long k = 0;
@@ -1407,23 +1627,18 @@ int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long tabl
         table[k++] = d.stage_off[l]; table[k++] = c->L[l].nghost;
         for (int p = 0; p <= d.nranks; p++) table[k++] = c->L[l].recv_off[p];
     }
-    if (want_fused())
-        for (int l = 0; l < c->levels; l++) {
-            table[k++] = c->L[l].ncomp;
-            for (int b = 0; b < 3; b++) {
-                cudaIpcMemHandle_t hb;
-                CK(cudaIpcGetMemHandle(&hb, c->L[l].buf[b]));
-                memcpy(&table[k], &hb, 64);
-                k += 8;
-            }
-        }
+    for (int l = 0; l < c->levels; l++) {
+        table[k++] = c->L[l].ncomp; table[k++] = c->L[l].npad;
+        for (int b = 0; b < 4; b++) table[k++] = (long)d.buf_off[4 * l + b];
+    }
     return MGCFD_OK;
 }
 // handles: nranks x 64 bytes, tables: nranks x table_len longs, both in rank order (what every rank's prepare returned)
 int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables, long table_len) {
     if (!c || !handles || !tables) { g_err = "null argument"; return MGCFD_ERR_ARG; }
     Dist& d = c->dist;
-    if (!d.active || !d.win) { g_err = "mgcfd_dist_p2p_prepare has not been called"; return MGCFD_ERR_ARG; }
+    if (!d.active || !d.win || !d.d_op) { g_err = "mgcfd_dist_p2p_prepare has not been called"; return MGCFD_ERR_ARG; }
+    if (table_len != mgcfd_dist_p2p_table_len(c)) { g_err = "table length does not match this build of the library"; return MGCFD_ERR_COMM; }
     CK(cudaSetDevice(c->opt.device));
     d.peer_win.assign(d.nranks, nullptr);
     for (int p = 0; p < d.nranks; p++) {
@@ -1440,13 +1655,17 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
     }
     CKRC(dev_upload(&d.d_red_of_rank, red, c->stream)); CKRC(dev_upload(&d.d_flag_of_rank, flg, c->stream));
     const long per_level = 2 + d.nranks + 1;
+    const long base_len = 1 + (long)c->levels * per_level;
     for (int l = 0; l < c->levels; l++) {
         Level& v = c->L[l];
         std::vector<P2PPeer> peers;
+        std::vector<PeerOut> pouts;
+        std::vector<PeerSlice> slices;
         for (int p = 0; p < d.nranks; p++) {
             const long ns = v.send_off[p + 1] - v.send_off[p], nr = v.recv_off[p + 1] - v.recv_off[p];
             if (p == d.rank || (ns == 0 && nr == 0)) continue;
             const long* tp = tables + (size_t)p * table_len + 1 + (size_t)l * per_level;     // peer p's entry for level l
+            const long* sp = tables + (size_t)p * table_len + base_len + (size_t)l * SLAB_PER_LEVEL;
             const long p_stage_off = tp[0], p_nghost = tp[1], p_recv_me = tp[2 + d.rank], p_recv_me_n = tp[2 + d.rank + 1] - tp[2 + d.rank];
             if (p_recv_me_n != ns) { g_err = "send / receive lists of two ranks do not match"; return MGCFD_ERR_COMM; }
             P2PPeer e;
@@ -1457,53 +1676,31 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
             e.dst[1] = pst + 8 * (size_t)std::max<long>(p_nghost, 1) + 8 * p_recv_me;
             e.flag = (unsigned long long*)d.peer_win[p] + d.rank;
             peers.push_back(e);
+            // where the peer keeps its copies of my rows: its record buffers / residual planes inside its slab
+            PeerOut po;
+            for (int b = 0; b < 3; b++) po.rec[b] = (double*)((unsigned char*)d.peer_win[p] + sp[2 + b]);
+            po.res = (double*)((unsigned char*)d.peer_win[p] + sp[5]);
+            po.res_stride = sp[1];
+            pouts.push_back(po);
+            PeerSlice sl;
+            sl.send0 = e.send0; sl.nsend = ns; sl.first_ghost_row = sp[0]; sl.recv_off_me = p_recv_me;
+            slices.push_back(sl);
         }
         v.npeers = (int)peers.size();
         if (v.npeers > 64) { g_err = "too many peers"; return MGCFD_ERR_ARG; }
         CKRC(dev_upload(&v.d_peers, peers, c->stream));
+        CKRC(dev_upload(&v.d_peer_out, pouts, c->stream));
         v.h_peers = peers;
-    }
-    if (want_fused()) {
-        const long base_len = 1 + (long)c->levels * per_level;
-        if (table_len != base_len + (long)c->levels * FUSED_PER_LEVEL) { g_err = "MGCFD_P2P_FUSED must be set alike on every rank"; return MGCFD_ERR_COMM; }
-        for (int l = 0; l < c->levels; l++) {
-            Level& v = c->L[l];
-            if (!v.pipe) { g_err = "the in-kernel exchange needs the pipelined stage kernel on every level"; return MGCFD_ERR_ARG; }
-            if (v.npeers == 0) continue;
-            const std::vector<P2PPeer>& peers = v.h_peers;
-            // node -> (peer, row in the peer's record arrays): build_send_targets (partition.h)
-            std::vector<PeerSlice> slices(v.npeers);
-            std::vector<double*> pbuf[3];
-            for (int pi = 0; pi < v.npeers; pi++) {
-                const int p = peers[pi].rank;
-                const long* tp = tables + (size_t)p * table_len + 1 + (size_t)l * per_level;
-                const long* fp = tables + (size_t)p * table_len + base_len + (size_t)l * FUSED_PER_LEVEL;
-                slices[pi].send0 = peers[pi].send0; slices[pi].nsend = peers[pi].nsend;
-                slices[pi].first_ghost_row = fp[0]; slices[pi].recv_off_me = tp[2 + d.rank];
-                for (int b = 0; b < 3; b++) {
-                    cudaIpcMemHandle_t hb;
-                    memcpy(&hb, fp + 1 + 8 * b, 64);
-                    void* m = nullptr;
-                    CK(cudaIpcOpenMemHandle(&m, hb, cudaIpcMemLazyEnablePeerAccess));
-                    v.peer_buf_maps.push_back(m);
-                    pbuf[b].push_back((double*)m);
-                }
-            }
-            SendTargets st;
-            try { build_send_targets(v.ncomp, v.TN, v.h_send_idx, slices, st); }
-            catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
-            const std::vector<int>&cnt = st.off, &tpeer = st.peer, &trow = st.row;
-            const std::vector<unsigned char>& tile_sends = st.tile_sends;
-            CKRC(dev_upload(&v.d_tgt_off, cnt, c->stream)); CKRC(dev_upload(&v.d_tgt_peer, tpeer, c->stream)); CKRC(dev_upload(&v.d_tgt_row, trow, c->stream));
-            CKRC(dev_upload(&v.d_tile_sends, tile_sends, c->stream));
-            for (int b = 0; b < 3; b++) CKRC(dev_upload(&v.d_peer_bufs[b], pbuf[b], c->stream));
-            CKRC(setup_pipe_dist(c, v));
-        }
-        d.fused = true;
+        // row -> (peer, row in the peer's arrays): build_send_targets (partition.h); every rank builds them, peers or not
+        SendTargets st;
+        try { build_send_targets(v.ncomp, v.TN, v.h_send_idx, slices, st); }
+        catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
+        CKRC(dev_upload(&v.d_tgt_off, st.off, c->stream)); CKRC(dev_upload(&v.d_tgt_peer, st.peer, c->stream)); CKRC(dev_upload(&v.d_tgt_row, st.row, c->stream));
+        CKRC(dev_upload(&v.d_tile_sends, st.tile_sends, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
     d.p2p = true;
-    c->opt.use_graph = c->dist.want_graph;     // operation numbers live on the device: the cycle, exchanges included, is graph-capturable
+    c->opt.use_graph = c->dist.want_graph;     // epoch numbers live on the device: the cycle, exchanges included, is graph-capturable
     return MGCFD_OK;
 }
 

@@ -209,18 +209,6 @@ struct StageArgs {
     const int* old_of_new;
     unsigned long long stage_seq;
     int mask;              // bit0 internal, bit1 boundary, bit2 wall
-    // in-kernel halo exchange (DIST instantiation of k_stage_pipe only, MGCFD_P2P_FUSED): the kernel stores the records of
-    // nodes other ranks hold as ghosts straight into those ranks' copies of vout, signals them when the whole grid is done, and
-    // waits for their previous signal before it reads a ghost row
-    const unsigned char* tile_sends;     // [ntiles] != 0: the tile owns nodes on a send list
-    const int* tgt_off;                  // [rows + 1] node -> its targets
-    const int* tgt_peer;                 // target: index into peer_out / peers ...
-    const int* tgt_row;                  // ... and the node's row in that peer's record arrays
-    double* const* peer_out;             // [npeers] the peers' buffers that play the role of vout
-    const P2PPeer* peers; int npeers;
-    unsigned long long* op_counter;      // operations completed so far (identical on every rank)
-    unsigned int* ticket;
-    const unsigned long long* my_flags;  // my window's flags: latest operation completed by each source rank
 };
 
 // A slot's `other` field is the byte offset of logical chunk 0 of the other endpoint's row in the shared record buffer,
@@ -334,16 +322,12 @@ __device__ __forceinline__ double div_rk(double x, double d, double rd) {
     return __fma_rn(__fma_rn(-d, q, x), rd, q);
 }
 // phase 3 of a fused stage for node gid: time_step + record + validity + residual; returns the five squared residuals in q
-template <bool DIST = false>
-__device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5], bool sends = false) {
+__device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5]) {
     const long S = a.stride;
     const double factor = div_rk(sf, a.rk_div, a.rk_rcp);     // == sf / rk_div, the true divide of cfd_loops.cpp:243
     const double n0 = o[0] + factor * f.r, n1 = o[1] + factor * f.mx, n2 = o[2] + factor * f.my, n3 = o[3] + factor * f.mz, n4 = o[4] + factor * f.e;
     const Rec nrec = make_rec(n0, n1, n2, n3, n4);
     store_rec(a.vout, gid, nrec);
-    if (DIST && sends) {      // the same record into the ghost row every other holder keeps of this node (over NVLink)
-        for (int k = a.tgt_off[gid]; k < a.tgt_off[gid + 1]; k++) store_rec(a.peer_out[a.tgt_peer[k]], a.tgt_row[k], nrec);
-    }
     if (a.bad_key) {
         // check_for_invalid_variables (validation.cpp:107-138): first offending cell of the first offending stage
         int reason = 0;
@@ -457,7 +441,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int RING = 2;     // ring entries (each `chunk_rounds` round blocks)
 
-template <int TN, bool SCATTER, bool DIST = false>
+template <int TN, bool SCATTER>
 __global__ void __launch_bounds__(TN, (TN <= 128 ? 4 : (TN <= 256 ? 2 : 1)))
 k_stage_pipe(const StageArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -536,16 +520,6 @@ k_stage_pipe(const StageArgs a) {
     __syncthreads();
     if (t == 0) produce(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (DIST) {
-        // ghost rows of vin were written by their owners' previous stage kernel: wait until every peer of the level has signalled the
-        // operation this rank completed last (operation numbers advance alike on all ranks)
-        if (t < a.npeers) {
-            const unsigned long long g = *(volatile unsigned long long*)a.op_counter;
-            const unsigned long long* f = a.my_flags + a.peers[t].rank;
-            while (ld_acquire_sys(f) < g) { __nanosleep(32); }
-        }
-        __syncthreads();
-    }
     copy_recs(0);
     const bool first_stage = (a.vold == a.vin);
     // the visit's global minimum dt (k_min_dt, the previous kernel of a first stage): one load per CTA, not one per tile
@@ -602,33 +576,9 @@ k_stage_pipe(const StageArgs a) {
         double sf = vol_or_sf;
         if (first_stage) { sf = step_factor_of(a, min_dt, vol_or_sf, me.s); a.sf[gid] = sf; }
         double q[5] = {0, 0, 0, 0, 0};
-        fused_update<DIST>(a, gid, sf, o, f, q, DIST && a.tile_sends[tile] != 0);
+        fused_update(a, gid, sf, o, f, q);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
         __syncthreads();      // record buffer (it & 1), header buffer (it % 3), acc and ws are free again
-    }
-    if (DIST) {
-        // signal: every CTA's remote stores are ordered before its thread 0's system-scope fence (the barrier at the end of the last
-        // tile); the last CTA to arrive publishes the operation number in every peer's window -- as k_p2p_exchange does
-        if (t == 0) {
-            __threadfence_system();
-            if (atomicInc(a.ticket, gridDim.x - 1) == gridDim.x - 1) {
-                __threadfence_system();
-                const unsigned long long g = *(volatile unsigned long long*)a.op_counter + 1;
-                for (int p = 0; p < a.npeers; p++) st_release_sys(a.peers[p].flag, g);
-                *a.op_counter = g;
-            }
-        }
-    }
-}
-
-// after the last stage kernel of a smoothing visit with the in-kernel exchange: wait for the peers' signal of that stage, so that
-// whatever runs next on the stream (restrict, prolong, the next visit) finds the ghost rows up to date
-__global__ void k_p2p_wait(const P2PPeer* __restrict__ peers, int npeers, const unsigned long long* op_counter, const unsigned long long* my_flags) {
-    const int t = threadIdx.x;
-    if (t < npeers) {
-        const unsigned long long g = *(volatile const unsigned long long*)op_counter;
-        const unsigned long long* f = my_flags + peers[t].rank;
-        while (ld_acquire_sys(f) < g) { __nanosleep(32); }
     }
 }
 
@@ -710,74 +660,6 @@ __global__ void k_min_dt(const double* __restrict__ recs, long n, const double* 
     if (threadIdx.x == 0) *min_bits = (unsigned long long)__double_as_longlong(v);
 }
 
-// k_min_dt for multi-GPU runs with MGCFD_P2P_FUSED: the last block goes on to all-reduce the minimum over the ranks itself -- the body of
-// k_p2p_allreduce (store my value into every rank's window, signal, wait for everybody, combine in rank order) -- so the visit
-// needs no separate reduction kernel; struct P2PReduce carries what k_p2p_allreduce takes as arguments.
-struct P2PReduce {
-    int nranks, me;
-    double* const* red_of_rank;                 // [nranks] window reduction bases
-    unsigned long long* const* flag_of_rank;    // [nranks] &window.flags[me]
-    const unsigned long long* my_flags;
-    const double* my_red;
-    unsigned long long* op_counter;
-    unsigned int* red_counter;
-};
-__global__ void k_min_dt_p2p(const double* __restrict__ recs, long n, const double* __restrict__ vol_root, double* __restrict__ blockmins,
-                           unsigned int* __restrict__ ticket, unsigned long long* __restrict__ min_bits, const P2PReduce pr) {
-    const double BIG = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
-    __shared__ double wmin[32];
-    __shared__ bool last;
-    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    double val = BIG;
-    if (i < n) val = 0.5 * (vol_root[i] / recs[8 * i + 7]);
-    auto block_min = [&](double v) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
-        if ((threadIdx.x & 31) == 0) wmin[threadIdx.x >> 5] = v;
-        __syncthreads();
-        v = (threadIdx.x < (blockDim.x >> 5)) ? wmin[threadIdx.x] : BIG;
-        if (threadIdx.x < 32) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, d));
-        }
-        __syncthreads();
-        return v;      // valid in thread 0
-    };
-    val = block_min(val);
-    if (threadIdx.x == 0) {
-        blockmins[blockIdx.x] = val;
-        __threadfence();
-        last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1);     // wraps back to 0 for the next launch
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    double v = BIG;
-    for (unsigned b = threadIdx.x; b < gridDim.x; b += blockDim.x) v = fmin(v, ((volatile double*)blockmins)[b]);
-    v = block_min(v);
-    // all-reduce(min) of the bit pattern over the ranks (positive doubles order like their bits)
-    __shared__ double mine;
-    if (threadIdx.x == 0) mine = v;
-    const int t = threadIdx.x;
-    const unsigned long long g = *(volatile unsigned long long*)pr.op_counter + 1;
-    const int parity = int(*(volatile unsigned int*)pr.red_counter & 1u);
-    __syncthreads();
-    if (t < pr.nranks) {
-        double* slot = pr.red_of_rank[t] + ((size_t)parity * 64 + pr.me) * 8;
-        slot[0] = mine;
-        __threadfence_system();
-        st_release_sys(pr.flag_of_rank[t], g);
-        while (ld_acquire_sys(pr.my_flags + t) < g) { __nanosleep(64); }
-    }
-    __syncthreads();
-    if (t == 0) {
-        const double* base = pr.my_red + (size_t)parity * 64 * 8;
-        unsigned long long m = ~0ull;
-        for (int r = 0; r < pr.nranks; r++) { const unsigned long long x = (unsigned long long)__double_as_longlong(__ldcg(base + r * 8)); m = x < m ? x : m; }
-        *min_bits = m;
-        *pr.op_counter = g; *pr.red_counter += 1;
-    }
-}
 // time_step (cfd_loops.cpp:215-280), granular API
 __global__ void k_time_step(double rk_div, long n, long stride, const double* __restrict__ sf, double* __restrict__ flux,
                             const double* __restrict__ vold, double* __restrict__ v) {
@@ -875,68 +757,128 @@ __global__ void k_check_invalid(const double* __restrict__ recs, long n, const i
 // ------------------------------------------------------------------------------------------------------
 // multigrid transfers
 // ------------------------------------------------------------------------------------------------------
+// ---- multi-GPU: the kernel that PRODUCES a row also delivers it --------------------------------------------------
+// where the copies other ranks hold of this rank's rows live (one entry per peer of the level)
+struct PeerOut {
+    double* rec[3];                // the peer's three record buffers (same rotation as ours)
+    double* res;                   // the peer's residual planes
+    long res_stride;               // the peer's npad
+};
+// remote stores + start / end synchronisation of a many-CTA kernel (restrict, prolong).  Every collective step of a distributed
+// run carries an EPOCH number that advances alike on all ranks (op_counter, on the device, so that graphs can be replayed):
+// a kernel waits at its start until the ranks it reads ghost rows from have signalled the epoch it starts in, stores the rows
+// it produces straight into the peers' copies, and its last CTA (ticket) fences system-wide and signals epoch + 1.
+struct DistTail {
+    const P2PPeer* wait_peers; int nwait;      // whose rows this kernel reads
+    const P2PPeer* peers; int npeers;          // who holds copies of the rows it writes
+    const PeerOut* peer_out; int ib;           // the peers' record buffer that mirrors the output buffer
+    const int* tgt_off; const int* tgt_peer; const int* tgt_row;      // row -> (peer index, row in the peer's arrays)
+    unsigned long long* op_counter; unsigned int* ticket; const unsigned long long* my_flags;
+};
+__device__ __forceinline__ unsigned long long dist_kernel_begin(const DistTail& d) {
+    const unsigned long long e0 = *(volatile unsigned long long*)d.op_counter;
+    if ((int)threadIdx.x < d.nwait) {
+        const unsigned long long* f = d.my_flags + d.wait_peers[threadIdx.x].rank;
+        while (ld_acquire_sys(f) < e0) { __nanosleep(20); }
+    }
+    __syncthreads();
+    return e0;
+}
+__device__ __forceinline__ void dist_kernel_end(const DistTail& d, unsigned long long e0) {
+    __syncthreads();             // the CTA's remote stores are ordered before thread 0's system-scope fence
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicInc(d.ticket, gridDim.x - 1) == gridDim.x - 1) {
+            __threadfence_system();
+            for (int p = 0; p < d.npeers; p++) st_release_sys(d.peers[p].flag, e0 + 1);
+            *d.op_counter = e0 + 1;
+        }
+    }
+}
+__device__ __forceinline__ void dist_push_rec(const DistTail& d, long row, const Rec& n) {
+    for (int k = d.tgt_off[row]; k < d.tgt_off[row + 1]; k++) store_rec(d.peer_out[d.tgt_peer[k]].rec[d.ib], d.tgt_row[k], n);
+}
+
 // mg_restrict (mg_loops.cpp:30-202) as a gather: children summed in ascending original fine index (the reference's
 // accumulation order, bit for bit), then multiplied by 1.0/count; coarse nodes without children keep their value.
+template <bool DIST>
 __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ vc, long ncoarse,
-                           const long* __restrict__ child_off, const int* __restrict__ child_ids) {
+                           const long* __restrict__ child_off, const int* __restrict__ child_ids, const DistTail d) {
+    unsigned long long e0 = 0;
+    if (DIST) e0 = dist_kernel_begin(d);
     const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (c >= ncoarse) return;
-    const long k0 = child_off[c], k1 = child_off[c + 1];
-    if (k1 == k0) return;
-    double s[5] = {0, 0, 0, 0, 0};
-    for (long k = k0; k < k1; k++) {
-        const double2* p = reinterpret_cast<const double2*>(vf + 8 * (long)child_ids[k]);
-        const double2 c0 = p[0], c1 = p[1];
-        const double e = vf[8 * (long)child_ids[k] + 4];
-        s[0] += c0.x; s[1] += c0.y; s[2] += c1.x; s[3] += c1.y; s[4] += e;
+    if (c < ncoarse) {
+        const long k0 = child_off[c], k1 = child_off[c + 1];
+        if (k1 > k0) {
+            double s[5] = {0, 0, 0, 0, 0};
+            for (long k = k0; k < k1; k++) {
+                const double2* p = reinterpret_cast<const double2*>(vf + 8 * (long)child_ids[k]);
+                const double2 c0 = p[0], c1 = p[1];
+                const double e = vf[8 * (long)child_ids[k] + 4];
+                s[0] += c0.x; s[1] += c0.y; s[2] += c1.x; s[3] += c1.y; s[4] += e;
+            }
+            const double average = 1.0 / (double)(k1 - k0);
+            const Rec n = make_rec(s[0] * average, s[1] * average, s[2] * average, s[3] * average, s[4] * average);
+            store_rec(vc, c, n);
+            if (DIST) dist_push_rec(d, c, n);
+        } else if (DIST) {
+            // a childless coarse node keeps its value; the copies other ranks hold of it must keep up with whatever the last
+            // visit left in THIS buffer of theirs (their ghost rows are only ever written by the owner)
+            if (d.tgt_off[c + 1] > d.tgt_off[c]) dist_push_rec(d, c, load_rec(vc, c));
+        }
     }
-    const double average = 1.0 / (double)(k1 - k0);
-    store_rec(vc, c, make_rec(s[0] * average, s[1] * average, s[2] * average, s[3] * average, s[4] * average));
+    if (DIST) dist_kernel_end(d, e0);
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
 // edges in original edge order: per edge the own-parent term then the neighbour-parent term (whose source is the own
 // parent on the `b` side -- the reference's quirk at :804-810, baked into ent_src by the host).
+template <bool DIST>
 __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __restrict__ parent, const double* __restrict__ idist_own,
                           const long* __restrict__ ent_off, const int* __restrict__ ent_src, const double* __restrict__ ent_w,
-                          const double* __restrict__ res_c, const double* __restrict__ res_f, double* __restrict__ var_f) {
+                          const double* __restrict__ res_c, const double* __restrict__ res_f, double* __restrict__ var_f, const DistTail d) {
+    unsigned long long e0 = 0;
+    if (DIST) e0 = dist_kernel_begin(d);
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-    if (i >= nfine) return;
-    const int p = parent[i];
-    if (p < 0) return;
-    double rp[5];
+    const int p = (i < nfine) ? parent[i] : -1;
+    if (p >= 0) {
+        double rp[5];
 #pragma unroll
-    for (int j = 0; j < 5; j++) rp[j] = res_c[j * scoarse + p];
-    const double w0 = idist_own[i];
-    double acc[5] = {0, 0, 0, 0, 0};
-    double wsum = 0.0;
-    const long k0 = ent_off[i], k1 = ent_off[i + 1];
-    if (w0 < 0.0) {
-        // coincident with its parent: assignment, w_sums = 1 (only if the node has an internal edge at all)
-        if (k1 > k0) {
+        for (int j = 0; j < 5; j++) rp[j] = res_c[j * scoarse + p];
+        const double w0 = idist_own[i];
+        double acc[5] = {0, 0, 0, 0, 0};
+        double wsum = 0.0;
+        const long k0 = ent_off[i], k1 = ent_off[i + 1];
+        if (w0 < 0.0) {
+            // coincident with its parent: assignment, w_sums = 1 (only if the node has an internal edge at all)
+            if (k1 > k0) {
 #pragma unroll
-            for (int j = 0; j < 5; j++) acc[j] = rp[j];
-            wsum = 1.0;
-        }
-    } else {
-        for (long k = k0; k < k1; k++) {
-            const int q = ent_src[k];
-            const double w = ent_w[k];
-#pragma unroll
-            for (int j = 0; j < 5; j++) {
-                acc[j] += w0 * rp[j];
-                acc[j] += w * res_c[j * scoarse + q];
+                for (int j = 0; j < 5; j++) acc[j] = rp[j];
+                wsum = 1.0;
             }
-            wsum += w0;
-            wsum += w;
-        }
-    }
-    double nv[5];
+        } else {
+            for (long k = k0; k < k1; k++) {
+                const int q = ent_src[k];
+                const double w = ent_w[k];
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const double avg = acc[j] / wsum;
-        nv[j] = var_f[8 * i + j] + (res_f[j * sfine + i] - avg);
+                for (int j = 0; j < 5; j++) {
+                    acc[j] += w0 * rp[j];
+                    acc[j] += w * res_c[j * scoarse + q];
+                }
+                wsum += w0;
+                wsum += w;
+            }
+        }
+        double nv[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const double avg = acc[j] / wsum;
+            nv[j] = var_f[8 * i + j] + (res_f[j * sfine + i] - avg);
+        }
+        const Rec n = make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]);
+        store_rec(var_f, i, n);
+        if (DIST) dist_push_rec(d, i, n);
     }
-    store_rec(var_f, i, make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]));
+    if (DIST) dist_kernel_end(d, e0);
 }
 
 // ------------------------------------------------------------------------------------------------------

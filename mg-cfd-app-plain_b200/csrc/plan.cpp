@@ -169,6 +169,58 @@ struct Bisector {
             rcb(idx + nl, n - nl, k - kl, tile0 + kl, depth + 1);
         }
     }
+    // ---- two-level bisection (PlanOptions::supers): first into super-tiles [s0, s0 + k) whose capacities are whole numbers of
+    // tiles (cap[s] .. cap[s+1], prefix sums in tiles), then every super-tile into its own tiles -- a super-tile is a compact
+    // block of consecutive tiles, which keeps its halo (rows outside the block that its edges touch) small
+    const std::vector<long>* cap = nullptr;
+    long left_count_cap(long n, long s0, long k, long kl) const {
+        const long capL = ((*cap)[s0 + kl] - (*cap)[s0]) * TN, capT = ((*cap)[s0 + k] - (*cap)[s0]) * TN, capR = capT - capL;
+        long nl = (long)(((__int128)n * capL + capT / 2) / capT);
+        nl = std::min(nl, capL);
+        nl = std::max(nl, n - capR);
+        return nl;
+    }
+    void split_widest(long* idx, long n, long nl) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (long i = 0; i < n; i++) for (int d = 0; d < 3; d++) {
+            const double c = L.coords[3 * idx[i] + d];
+            lo[d] = std::min(lo[d], c); hi[d] = std::max(hi[d], c);
+        }
+        int ax = 0;
+        for (int d = 1; d < 3; d++) if (hi[d] - lo[d] > hi[ax] - lo[ax]) ax = d;
+        const double* c = L.coords.data();
+        std::nth_element(idx, idx + nl, idx + n, [c, ax](long x, long y) {
+            const double cx = c[3 * x + ax], cy = c[3 * y + ax];
+            return cx != cy ? cx < cy : x < y;
+        });
+    }
+    void rcb_super(long* idx, long n, long s0, long k, int depth) {
+        if (k == 1) { rcb(idx, n, (*cap)[s0 + 1] - (*cap)[s0], (*cap)[s0], depth); return; }
+        const long kl = k / 2, nl = left_count_cap(n, s0, k, kl);
+        split_widest(idx, n, nl);
+        if (depth < 3 && n > 200000 && plan_threads() > 1) {
+            auto fut = std::async(std::launch::async, [&] { rcb_super(idx, nl, s0, kl, depth + 1); });
+            rcb_super(idx + nl, n - nl, s0 + kl, k - kl, depth + 1);
+            fut.get();
+        } else {
+            rcb_super(idx, nl, s0, kl, depth + 1);
+            rcb_super(idx + nl, n - nl, s0 + kl, k - kl, depth + 1);
+        }
+    }
+    void gbis_super(long* idx, long n, long s0, long k) {
+        if (k == 1) { gbis(idx, n, (*cap)[s0 + 1] - (*cap)[s0], (*cap)[s0]); return; }
+        const long kl = k / 2, nl = left_count_cap(n, s0, k, kl);
+        if (sub.empty()) { sub.assign(L.nel, 0); stamp.assign(L.nel, 0); }
+        const int s = next_mark++;
+        for (long i = 0; i < n; i++) sub[idx[i]] = s;
+        std::vector<long> nodes(idx, idx + n), order;
+        order.reserve(n);
+        const int mark = next_mark++;
+        cm_order(g, nodes, [&](long v) { return sub[v] == s; }, stamp, mark, order);
+        std::copy(order.begin(), order.end(), idx);
+        gbis_super(idx, nl, s0, kl);
+        gbis_super(idx + nl, n - nl, s0 + kl, k - kl);
+    }
     // graph bisection: BFS order of the subset from a pseudo-peripheral node, first nl nodes go left
     void gbis(long* idx, long n, long k, long tile0) {
         if (k == 1) { for (long i = 0; i < n; i++) tile_of[idx[i]] = tile0; return; }
@@ -204,6 +256,8 @@ struct Mask256 {
 
 }  // namespace
 
+static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, LevelPlan& P, const std::vector<int>& adj_eid);
+
 void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) {
     const long nall = L.nel;                                   // owned + ghosts
     const long n = L.n_owned >= 0 ? L.n_owned : L.nel;         // owned: only these are tiled, ordered and computed
@@ -236,7 +290,19 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         std::vector<long> idx(n);
         std::iota(idx.begin(), idx.end(), 0L);
         Bisector B(L, g, TN, tile_of);
-        if (!L.coords.empty()) B.rcb(idx.data(), n, P.ntiles, 0, 0);
+        std::vector<long> cap;
+        if (opt.supers > 0 && !opt.scatter && TN == 128) {
+            // super-tile s holds ntiles / ns tiles, the first ntiles % ns of them one more
+            const long ns = std::min<long>(opt.supers, P.ntiles);
+            cap.assign(ns + 1, 0);
+            for (long s = 0; s < ns; s++) cap[s + 1] = cap[s] + P.ntiles / ns + (s < P.ntiles % ns ? 1 : 0);
+            B.cap = &cap;
+            if (!L.coords.empty()) B.rcb_super(idx.data(), n, 0, ns, 0);
+            else B.gbis_super(idx.data(), n, 0, ns);
+            P.visit.ns = int(ns);
+            P.visit.super_off = cap;
+        }
+        else if (!L.coords.empty()) B.rcb(idx.data(), n, P.ntiles, 0, 0);
         else B.gbis(idx.data(), n, P.ntiles, 0);
         clk.lap("bisection into tiles");
         // Cuthill-McKee inside every tile
@@ -357,6 +423,44 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         bool oversize = false;
         std::string error;
     };
+    // segment rounds: the ROUND in which each edge of a node is taken (see process_range): greedy list schedule per group of 8
+    // consecutive nodes so that the 8 lanes of a quarter-warp read rows with distinct (row mod 8)
+    auto schedule_rounds = [](std::vector<Slot>& slots, int tile_rounds) {
+                size_t s0 = 0;
+                while (s0 < slots.size()) {
+                    const int g = slots[s0].owner / 8;
+                    size_t s1 = s0;
+                    while (s1 < slots.size() && slots[s1].owner / 8 == g) s1++;
+                    // remaining edges per lane
+                    std::vector<size_t> lane_edges[8];
+                    for (size_t k = s0; k < s1; k++) lane_edges[slots[k].owner % 8].push_back(k);
+                    for (int r = 0; r < tile_rounds; r++) {
+                        int used_by[8];                       // residue -> row using it in this round (-1 free)
+                        for (int q = 0; q < 8; q++) used_by[q] = -1;
+                        int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                        std::stable_sort(order, order + 8, [&](int x, int y) { return lane_edges[x].size() > lane_edges[y].size(); });
+                        const int rounds_left = tile_rounds - r;
+                        for (int oi = 0; oi < 8; oi++) {
+                            auto& le = lane_edges[order[oi]];
+                            if (le.empty()) continue;
+                            int pick = -1;
+                            for (size_t c = 0; c < le.size(); c++) {
+                                const int row = slots[le[c]].other;
+                                if (used_by[row & 7] == -1 || used_by[row & 7] == row) { pick = int(c); break; }
+                            }
+                            if (pick < 0) {
+                                if (int(le.size()) < rounds_left) continue;     // can wait: leave this round empty
+                                pick = 0;                                        // must go now: accept the conflict
+                            }
+                            const size_t k = le[pick];
+                            slots[k].round = r;
+                            used_by[slots[k].other & 7] = slots[k].other;
+                            le.erase(le.begin() + pick);
+                        }
+                    }
+                    s0 = s1;
+                }
+    };
     auto process_range = [&](TileRange& C) {
     std::vector<Slot> slots;
     std::vector<int> halo;
@@ -405,42 +509,7 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
             // (which share one 128-bit shared-memory transaction) read rows with distinct (row mod 8), i.e. distinct bank
             // groups under the 64B swizzle: a greedy list schedule per group of 8 consecutive nodes.  Only the order of a
             // node's additions changes (still a fixed, reproducible order).
-            if (opt.conflict_free_rounds) {
-                size_t s0 = 0;
-                while (s0 < slots.size()) {
-                    const int g = slots[s0].owner / 8;
-                    size_t s1 = s0;
-                    while (s1 < slots.size() && slots[s1].owner / 8 == g) s1++;
-                    // remaining edges per lane
-                    std::vector<size_t> lane_edges[8];
-                    for (size_t k = s0; k < s1; k++) lane_edges[slots[k].owner % 8].push_back(k);
-                    for (int r = 0; r < tile_rounds; r++) {
-                        int used_by[8];                       // residue -> row using it in this round (-1 free)
-                        for (int q = 0; q < 8; q++) used_by[q] = -1;
-                        int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-                        std::stable_sort(order, order + 8, [&](int x, int y) { return lane_edges[x].size() > lane_edges[y].size(); });
-                        const int rounds_left = tile_rounds - r;
-                        for (int oi = 0; oi < 8; oi++) {
-                            auto& le = lane_edges[order[oi]];
-                            if (le.empty()) continue;
-                            int pick = -1;
-                            for (size_t c = 0; c < le.size(); c++) {
-                                const int row = slots[le[c]].other;
-                                if (used_by[row & 7] == -1 || used_by[row & 7] == row) { pick = int(c); break; }
-                            }
-                            if (pick < 0) {
-                                if (int(le.size()) < rounds_left) continue;     // can wait: leave this round empty
-                                pick = 0;                                        // must go now: accept the conflict
-                            }
-                            const size_t k = le[pick];
-                            slots[k].round = r;
-                            used_by[slots[k].other & 7] = slots[k].other;
-                            le.erase(le.begin() + pick);
-                        }
-                    }
-                    s0 = s1;
-                }
-            }
+            if (opt.conflict_free_rounds) schedule_rounds(slots, tile_rounds);
         } else {
             for (int i = 0; i < nown; i++) { Lm[i] = Mask256(); Rm[i] = Mask256(); nassigned[i] = 0; }
             // internal-to-tile edges first (visited from their `a` end, ascending edge index per node)
@@ -573,6 +642,163 @@ void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P) 
         hl[0] = P.slot_off[t]; hl[1] = P.bslot_off[t];
         int* ids = reinterpret_cast<int*>(h + 32);
         for (long k = P.halo_off[t]; k < P.halo_off[t + 1]; k++) ids[k - P.halo_off[t]] = P.halo_ids[k];
+    }
+    if (P.visit.ns > 0) { build_visit_streams(L, opt, P, adj_eid); clk.lap("visit streams"); }
+}
+
+namespace {
+inline uint16_t visit_code(int idx, bool halo) { return uint16_t(((idx << 2) | ((idx >> 1) & 3)) | (halo ? 0x8000 : 0)); }
+}
+
+// The visit kernel's streams (VisitPlan): per super-tile the halo list and descriptor, per tile the edge rounds with the other
+// endpoint addressed inside the super-tile.  Called at the end of build_level_plan when PlanOptions::supers > 0.
+static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, LevelPlan& P, const std::vector<int>& adj_eid) {
+    VisitPlan& V = P.visit;
+    const long TN = P.TN;
+    const long ns = V.ns;
+    const size_t BLK = size_t(TN) * 26;
+    struct VSlot { int owner; int round; int other; long e; bool owner_is_a; };     // other = idx | halo << 20
+    struct SuperOut {
+        std::vector<int> halo;
+        std::vector<int> rounds;                  // per tile
+        std::vector<unsigned char> blocks;        // the super-tile's round blocks, tile after tile
+        std::string error;
+    };
+    std::vector<SuperOut> out(ns);
+    auto process_super = [&](long s) {
+        SuperOut& O = out[s];
+        const long t0 = V.super_off[s], t1 = V.super_off[s + 1];
+        const long row0 = t0 * TN, row1 = t1 * TN;
+        std::vector<int>& halo = O.halo;
+        for (long t = t0; t < t1; t++)
+            for (int lu = 0; lu < P.tile_nown[t]; lu++)
+                for (long k = P.adj_off[t * TN + lu]; k < P.adj_off[t * TN + lu + 1]; k++) {
+                    const int v = P.adj_nbr[k] & 0x7fffffff;
+                    if (v < row0 || v >= row1) halo.push_back(v);
+                }
+        std::sort(halo.begin(), halo.end());
+        halo.erase(std::unique(halo.begin(), halo.end()), halo.end());
+        if (row1 - row0 >= 8192 || long(halo.size()) >= 8192) { O.error = "mgcfd: super-tile too large for the 13-bit row index of the visit kernel"; return; }
+        std::vector<VSlot> slots;
+        long blocks_done = 0;
+        for (long t = t0; t < t1; t++) {
+            const long base = t * TN;
+            const int nown = P.tile_nown[t];
+            slots.clear();
+            int tile_rounds = 0;
+            for (int lu = 0; lu < nown; lu++) {
+                int r = 0;
+                for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++, r++) {
+                    const int v = P.adj_nbr[k] & 0x7fffffff;
+                    const bool is_halo = (v < row0 || v >= row1);
+                    const int idx = is_halo ? int(std::lower_bound(halo.begin(), halo.end(), v) - halo.begin()) : int(v - row0);
+                    slots.push_back({lu, r, idx | (is_halo ? (1 << 20) : 0), adj_eid[k], P.adj_nbr[k] >= 0});
+                }
+                tile_rounds = std::max(tile_rounds, r);
+            }
+            if (opt.conflict_free_rounds) {
+                // same greedy list schedule as the stage kernel's rounds (build_level_plan), on the rows of the super-tile's buffer:
+                // the 8 lanes of a quarter-warp should read rows with distinct (index mod 8) -- own and halo rows both start at a
+                // 128-byte boundary, so (index mod 8) decides the bank group in either region
+                size_t s0 = 0;
+                while (s0 < slots.size()) {
+                    const int g = slots[s0].owner / 8;
+                    size_t s1 = s0;
+                    while (s1 < slots.size() && slots[s1].owner / 8 == g) s1++;
+                    std::vector<size_t> lane_edges[8];
+                    for (size_t k = s0; k < s1; k++) lane_edges[slots[k].owner % 8].push_back(k);
+                    for (int r = 0; r < tile_rounds; r++) {
+                        int used_by[8];
+                        for (int q = 0; q < 8; q++) used_by[q] = -1;
+                        int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                        std::stable_sort(order, order + 8, [&](int x, int y) { return lane_edges[x].size() > lane_edges[y].size(); });
+                        const int rounds_left = tile_rounds - r;
+                        for (int oi = 0; oi < 8; oi++) {
+                            auto& le = lane_edges[order[oi]];
+                            if (le.empty()) continue;
+                            int pick = -1;
+                            for (size_t c = 0; c < le.size(); c++) {
+                                const int row = slots[le[c]].other;
+                                if (used_by[row & 7] == -1 || used_by[row & 7] == row) { pick = int(c); break; }
+                            }
+                            if (pick < 0) {
+                                if (int(le.size()) < rounds_left) continue;
+                                pick = 0;
+                            }
+                            const size_t k = le[pick];
+                            slots[k].round = r;
+                            used_by[slots[k].other & 7] = slots[k].other;
+                            le.erase(le.begin() + pick);
+                        }
+                    }
+                    s0 = s1;
+                }
+            }
+            int rounds = 0;
+            for (const VSlot& sl : slots) rounds = std::max(rounds, sl.round + 1);
+            O.rounds.push_back(rounds);
+            const long b0 = blocks_done;
+            blocks_done += rounds;
+            O.blocks.resize(size_t(blocks_done) * BLK, 0);
+            const int own0 = int(base - row0);          // the tile's first row inside the super-tile
+            for (int r = 0; r < rounds; r++) {
+                uint16_t* oth = reinterpret_cast<uint16_t*>(O.blocks.data() + size_t(b0 + r) * BLK + size_t(TN) * 24);
+                for (int lu = 0; lu < TN; lu++) oth[lu] = visit_code(own0 + lu, false);      // empty slot: the node itself, h = 0
+            }
+            for (const VSlot& sl : slots) {
+                unsigned char* blk = O.blocks.data() + size_t(b0 + sl.round) * BLK;
+                double* w = reinterpret_cast<double*>(blk);
+                uint16_t* oth = reinterpret_cast<uint16_t*>(blk + size_t(TN) * 24);
+                const double sg = sl.owner_is_a ? -0.5 : 0.5;
+                w[sl.owner] = sg * P.ew[sl.e];
+                w[TN + sl.owner] = sg * P.ew[L.nI + sl.e];
+                w[2 * TN + sl.owner] = sg * P.ew[2 * L.nI + sl.e];
+                oth[sl.owner] = visit_code(sl.other & 0xFFFFF, (sl.other >> 20) != 0);
+            }
+        }
+    };
+    {
+        std::atomic<long> next(0);
+        auto worker = [&]() { for (long s = next.fetch_add(1); s < ns; s = next.fetch_add(1)) process_super(s); };
+        const unsigned nthreads = unsigned(std::max<long>(1, std::min<long>(plan_threads(), ns / 4)));
+        std::vector<std::future<void>> pool;
+        for (unsigned k = 1; k < nthreads; k++) pool.push_back(std::async(std::launch::async, worker));
+        worker();
+        for (auto& f : pool) f.get();
+    }
+    for (const SuperOut& O : out) if (!O.error.empty()) throw std::runtime_error(O.error);
+    V.maxt = 0; V.max_halo = 0; V.max_rounds = 0; V.halo_total = 0;
+    V.vslot_off.assign(P.ntiles + 1, 0);
+    for (long s = 0; s < ns; s++) {
+        V.maxt = std::max<int>(V.maxt, int(V.super_off[s + 1] - V.super_off[s]));
+        V.max_halo = std::max<int>(V.max_halo, int(out[s].halo.size()));
+        V.halo_total += long(out[s].halo.size());
+        for (long t = V.super_off[s]; t < V.super_off[s + 1]; t++) {
+            const int r = out[s].rounds[t - V.super_off[s]];
+            V.max_rounds = std::max(V.max_rounds, r);
+            V.vslot_off[t + 1] = V.vslot_off[t] + r;
+        }
+    }
+    V.vslots.resize(size_t(V.vslot_off[P.ntiles]) * BLK);
+    V.hpad = (V.max_halo + 3) & ~3;
+    V.desc_stride = (16 + 32 * V.maxt + 4 * V.hpad + 15) & ~15;
+    V.desc.assign(size_t(ns) * V.desc_stride, 0);
+    for (long s = 0; s < ns; s++) {
+        const long t0 = V.super_off[s], t1 = V.super_off[s + 1];
+        if (!out[s].blocks.empty()) memcpy(V.vslots.data() + size_t(V.vslot_off[t0]) * BLK, out[s].blocks.data(), out[s].blocks.size());
+        unsigned char* d = V.desc.data() + size_t(s) * V.desc_stride;
+        int* di = reinterpret_cast<int*>(d);
+        di[0] = int(t0 * TN); di[1] = int(t1 - t0); di[2] = int(out[s].halo.size()); di[3] = int(t0);
+        for (long t = t0; t < t1; t++) {
+            unsigned char* th = d + 16 + 32 * (t - t0);
+            reinterpret_cast<int*>(th)[0] = int(V.vslot_off[t + 1] - V.vslot_off[t]);
+            reinterpret_cast<int*>(th)[1] = int(P.bslot_off[t + 1] - P.bslot_off[t]);
+            reinterpret_cast<long long*>(th)[1] = V.vslot_off[t];
+            reinterpret_cast<long long*>(th)[2] = P.bslot_off[t];
+        }
+        int* ids = reinterpret_cast<int*>(d + 16 + 32 * V.maxt);
+        for (size_t k = 0; k < out[s].halo.size(); k++) ids[k] = out[s].halo[k];
+        std::vector<unsigned char>().swap(out[s].blocks);
     }
 }
 
@@ -769,6 +995,81 @@ void emulate_stage_flux(const LevelPlan& P, const double* var, int mask, const d
             for (int k = 0; k < 5; k++) flux[5 * on + k] = f[k * TN + lu] + (P.scatter ? acc[k * TN + lu] : 0.0);
         }
     }
+}
+
+// the visit kernel's view of the same level: super-tile descriptors, their halo lists, the re-addressed edge rounds
+void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const double ff[5], const double ffc[12], double k2, double* flux) {
+    const VisitPlan& V = P.visit;
+    if (V.ns <= 0) throw std::runtime_error("mgcfd: the level has no visit plan");
+    const long TN = P.TN;
+    const size_t BLK = size_t(TN) * 26, BBLK = size_t(TN) * 25;
+    std::vector<HRec> rec(P.npad);
+    const double pad_state[5] = {ff[0], ff[1], ff[2], ff[3], ff[4]};
+    for (long g = 0; g < P.npad; g++) rec[g] = host_rec(P.old_of_new[g] >= 0 ? var + 5 * P.old_of_new[g] : pad_state);
+    std::vector<char> seen(P.npad, 0);
+    long tiles_seen = 0;
+    for (long s = 0; s < V.ns; s++) {
+        const unsigned char* d = V.desc.data() + size_t(s) * V.desc_stride;
+        const int* di = reinterpret_cast<const int*>(d);
+        const long row0 = di[0]; const int ntile = di[1], nhalo = di[2]; const long tile0 = di[3];
+        if (row0 != tile0 * TN || ntile < 1 || ntile > V.maxt || nhalo > V.hpad) throw std::runtime_error("mgcfd: bad super-tile descriptor");
+        const int* ids = reinterpret_cast<const int*>(d + 16 + 32 * V.maxt);
+        for (int k = 0; k < nhalo; k++) {
+            if (ids[k] < 0 || ids[k] >= P.npad || (ids[k] >= row0 && ids[k] < row0 + ntile * TN)) throw std::runtime_error("mgcfd: bad halo id in a super-tile");
+            if (k && ids[k] <= ids[k - 1]) throw std::runtime_error("mgcfd: halo ids of a super-tile are not strictly ascending");
+        }
+        for (int i = 0; i < ntile; i++) {
+            const unsigned char* th = d + 16 + 32 * i;
+            const int rounds = reinterpret_cast<const int*>(th)[0], brounds = reinterpret_cast<const int*>(th)[1];
+            const long long vblk0 = reinterpret_cast<const long long*>(th)[1], bblk0 = reinterpret_cast<const long long*>(th)[2];
+            tiles_seen++;
+            for (long lu = 0; lu < TN; lu++) {
+                const long gid = row0 + i * TN + lu;
+                if (seen[gid]++) throw std::runtime_error("mgcfd: a row belongs to two super-tiles");
+                const HRec& me = rec[gid];
+                double f[5] = {0, 0, 0, 0, 0};
+                if (mask & 1)
+                    for (int r = 0; r < rounds; r++) {
+                        const unsigned char* blk = V.vslots.data() + size_t(vblk0 + r) * BLK;
+                        const double* w = reinterpret_cast<const double*>(blk);
+                        const uint16_t code = reinterpret_cast<const uint16_t*>(blk + size_t(TN) * 24)[lu];
+                        const bool is_halo = (code & 0x8000) != 0;
+                        const int idx = (code & 0x7fff) >> 2;
+                        if ((code & 3) != ((idx >> 1) & 3)) throw std::runtime_error("mgcfd: visit slot code does not follow the swizzle");
+                        if (is_halo ? idx >= nhalo : idx >= ntile * TN) throw std::runtime_error("mgcfd: visit slot points outside the super-tile");
+                        const HRec& B = is_halo ? rec[ids[idx]] : rec[row0 + idx];
+                        double g[5];
+                        host_edge_flux(me, B, w[lu], w[TN + lu], w[2 * TN + lu], k2, g);
+                        for (int k = 0; k < 5; k++) f[k] += g[k];
+                    }
+                if (mask & 6)
+                    for (int r = 0; r < brounds; r++) {
+                        const unsigned char* blk = P.bslots.data() + size_t(bblk0 + r) * BBLK;
+                        const double* w = reinterpret_cast<const double*>(blk);
+                        const int kind = blk[size_t(TN) * 24 + lu];
+                        if (kind == 0 || !((mask >> kind) & 1)) continue;
+                        const double x = w[lu], y = w[TN + lu], z = w[2 * TN + lu];
+                        if (kind == 1) { f[1] += x * me.p; f[2] += y * me.p; f[3] += z * me.p; }
+                        else {
+                            const double fx = 0.5 * x, fy = 0.5 * y, fz = 0.5 * z;
+                            const double g = fx * me.mx + fy * me.my + fz * me.mz, q = g * me.ir;
+                            f[0] += (fx * ff[1] + fy * ff[2] + fz * ff[3]) + g;
+                            f[4] += (fx * ffc[9] + fy * ffc[10] + fz * ffc[11]) + (me.re + me.p) * q;
+                            f[1] += (fx * ffc[0] + fy * ffc[1] + fz * ffc[2]) + (me.mx * q + me.p * fx);
+                            f[2] += (fx * ffc[3] + fy * ffc[4] + fz * ffc[5]) + (me.my * q + me.p * fy);
+                            f[3] += (fx * ffc[6] + fy * ffc[7] + fz * ffc[8]) + (me.mz * q + me.p * fz);
+                        }
+                    }
+                const long on = P.old_of_new[gid];
+                if (on < 0) {
+                    for (int k = 0; k < 5; k++) if (f[k] != 0.0) throw std::runtime_error("mgcfd: a padding thread accumulated flux");
+                    continue;
+                }
+                for (int k = 0; k < 5; k++) flux[5 * on + k] = f[k];
+            }
+        }
+    }
+    if (tiles_seen != P.ntiles) throw std::runtime_error("mgcfd: the super-tiles do not cover the tiles");
 }
 
 void emulate_restrict(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* var_f, double* var_c) {

@@ -18,6 +18,30 @@ struct PlanOptions {
     bool strict = true;   // false (introspection only): tiles whose halo cannot be staged are flagged (LevelPlan::oversize) instead of rejected
     bool conflict_free_rounds = true;  // segment mode: schedule each node's edges over the rounds so that quarter-warps avoid shared-memory bank conflicts
     bool scatter = false; // true: coloured-scatter rounds (each in-tile edge once); false: sorted-segment rounds (every edge from both ends)
+    int supers = 0;       // > 0 (segment mode, tile_nodes 128): group the tiles into this many SUPER-TILES (two-level bisection: first into
+                          // super-tiles, then each into its tiles) and build the visit kernel's streams (VisitPlan below)
+};
+
+// What the persistent visit kernel (kernels.cuh k_visit) reads of a level.  A super-tile is a run of consecutive tiles (= consecutive
+// rows) whose records are staged in shared memory TOGETHER: its halo is the set of rows outside the run that its edges touch, far
+// fewer per owned row than the tile-by-tile halos of the stage kernel.
+struct VisitPlan {
+    int ns = 0;                            // super-tiles (0: not built)
+    int maxt = 0;                          // most tiles in one super-tile
+    int max_halo = 0, hpad = 0;            // most halo rows of one super-tile, padded to a multiple of 4
+    int max_rounds = 0;
+    long halo_total = 0;
+    std::vector<long> super_off;           // ns+1: super-tile s = tiles [super_off[s], super_off[s+1])
+    // edge rounds, same block format as LevelPlan::slots (TN = 128) except the u16 of a slot:
+    //   code = (idx << 2) | ((idx >> 1) & 3) | (halo ? 0x8000 : 0), idx = row of the other endpoint inside the super-tile's own rows
+    //   (halo = 0) or inside its halo list (halo = 1); (code & 0x7fff) << 4 is the byte offset of chunk 0 of that 64-byte row under
+    //   the 64B swizzle, relative to the own-row / halo-row base.  Empty slot: the thread's own row, h = 0.
+    std::vector<long> vslot_off;           // ntiles+1, in blocks
+    std::vector<unsigned char> vslots;
+    // fixed-stride super-tile descriptors: {int row0, ntile, nhalo, tile0;
+    //   maxt x {int rounds, brounds; long long vslot_blk0, bslot_blk0, pad};  int halo_ids[hpad]}
+    std::vector<unsigned char> desc;
+    int desc_stride = 0;
 };
 
 struct LevelPlan {
@@ -55,6 +79,7 @@ struct LevelPlan {
     // ---- CSR by node, original edge order (segment rounds + prolong) -----------------------------
     std::vector<long> adj_off;            // npad+1
     std::vector<int> adj_nbr;             // neighbour padded id, bit31 set when this node is the edge's `b`
+    VisitPlan visit;                      // PlanOptions::supers > 0
 };
 
 void build_level_plan(const HostLevel& L, const PlanOptions& opt, LevelPlan& P);
@@ -78,6 +103,7 @@ void build_transfer_plan(const HostLevel& fine, const HostLevel& coarse, const L
 // accumulate from the tile headers / round blocks / boundary blocks of P for the state `var` (AoS, original node order) -> flux
 // (AoS, original order; mask: bit0 internal, bit1 boundary, bit2 wall edges), and what k_restrict / k_prolong compute from T.
 void emulate_stage_flux(const LevelPlan& P, const double* var, int mask, const double ff[5], const double ffc[12], double k2, double* flux);
+void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const double ff[5], const double ffc[12], double k2, double* flux);
 void emulate_restrict(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* var_f, double* var_c);
 void emulate_prolong(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* res_c, const double* res_f, double* var_f);
 

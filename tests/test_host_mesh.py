@@ -246,6 +246,64 @@ def test_transfer_operators_reproduce_the_oracle_transfers(kind, dims, variant, 
         assert np.all(linf_rel(np.where(ok, got_f, 0.0), np.where(ok, want_f, 0.0)) < 1e-14)
 
 
+@pytest.mark.parametrize("kind,dims,variant,node_order", PLAN_MESHES)
+@pytest.mark.parametrize("supers", [1, 3, 8, 1000])
+def test_visit_plan_byte_streams_reproduce_the_oracle_fluxes(kind, dims, variant, node_order, supers):
+    """No GPU: the visit kernel's view of a level -- super-tile descriptors (consecutive 128-node tiles grouped by a two-level
+    bisection), their halo lists and the edge rounds re-addressed inside the super-tile (plan.h VisitPlan) -- walked on the host
+    the way k_visit's threads walk them, gives the oracle's flux sums; every row belongs to exactly one super-tile."""
+    from conftest import linf_rel, mesh_levels, perturbed_state
+    from oracle.loader import Oracle
+    orc = Oracle()
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant, ordering=node_order)
+    for l, L in enumerate(mesh_levels(mesh, apply_ewt_with=orc)):
+        var = perturbed_state(L["nel"], seed=500 + l)
+        want = np.zeros(5 * L["nel"])
+        orc.flux_edge(0, L["nI"], L["edges"], var, want)
+        got, info = M.plan_emulate_visit_flux(L, var, supers, mask=1)
+        assert np.all(linf_rel(got, want) < 1e-13), ("internal", l, linf_rel(got, want))
+        orc.boundary_flux_edge(L["nI"], L["nB"], L["edges"], var, want)
+        orc.wall_flux_edge(L["nI"] + L["nB"], L["nW"], L["edges"], var, want)
+        got, info = M.plan_emulate_visit_flux(L, var, supers, mask=7)
+        assert np.all(linf_rel(got, want) < 1e-13), ("all", l, linf_rel(got, want))
+        assert info["supers"] == min(supers, info["tiles"]) and info["rows"] >= info["tiles"] * 128
+        assert info["max_tiles"] == -(-info["tiles"] // info["supers"])
+        cfg = M.plan_visit_config(L, num_sms=4)
+        assert cfg["visit"] == 1 and cfg["smem_bytes"] <= 230000 and cfg["ring_rounds"] >= 1 and cfg["ctas"] * cfg["supers_per_cta"] <= info["tiles"]
+
+
+def test_visit_plan_on_unstructured_levels_with_hub_nodes():
+    """k-nearest-neighbour levels with 40+-neighbour hubs (tiles with many rounds, several ring chunks): visit streams vs oracle."""
+    from conftest import linf_rel, perturbed_state
+    from oracle.loader import Oracle
+    orc = Oracle()
+    for n, k, seed in ((6000, 6, 1), (2500, 5, 2)):
+        L = _random_level(n, k, seed)
+        orc.adjust_dampen(4, L["coords"], L["edges"])
+        var = perturbed_state(L["nel"], seed=seed)
+        want = np.zeros(5 * L["nel"])
+        orc.flux_edge(0, L["nI"], L["edges"], var, want)
+        orc.boundary_flux_edge(L["nI"], L["nB"], L["edges"], var, want)
+        orc.wall_flux_edge(L["nI"] + L["nB"], L["nW"], L["edges"], var, want)
+        for supers in (2, 148):
+            got, info = M.plan_emulate_visit_flux(L, var, supers)
+            assert np.all(linf_rel(got, want) < 1e-13), (n, supers, linf_rel(got, want))
+
+
+def test_visit_configuration_of_the_baseline_workload():
+    """BASELINE.json configs[1] (C2) on a 148-SM device: every level runs the visit kernel; the two coarsest keep their own rows
+    resident in shared memory, the finer ones stream double-buffered super-tiles; the super-tile halo is well below the owned rows."""
+    import bench
+    from conftest import mesh_levels
+    kind, dims, variant, _ = bench.WORKLOADS["c2"]
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+    cfgs = [M.plan_visit_config(L) for L in mesh_levels(mesh)]
+    assert all(c["visit"] == 1 and c["ctas"] == 148 and c["smem_bytes"] <= 230000 for c in cfgs)
+    assert [c["resident"] for c in cfgs] == [0, 0, 1, 1] and all(c["ring_rounds"] >= 2 for c in cfgs)
+    for c, L in zip(cfgs, mesh_levels(mesh)):
+        assert c["halo_rows"] < 0.75 * L["nel"]
+
+
 def test_plan_does_not_depend_on_the_number_of_host_threads():
     """The preprocessing runs tile ranges on a pool of host threads; the bytes handed to the device must not depend on it."""
     import subprocess, sys, json

@@ -13,13 +13,20 @@ a cycle performs  sum_l E_I(l) * RK(3) * visits(l)  of them (BASELINE.json metri
            state resident in HBM, L2 flushed before every timed cycle, max over ranks)
   e2e    = the same metric through the public API with HOST buffers: every step copies level-0 `variables` from pinned
            host memory (set_field), runs one cycle (run_cycles -> RMS back), and reads `variables` back (get_field)
-  roofline = the dominant kernel (the fused flux + time_step stage on level 0): algorithmic bytes per launch
-           (32*E_I + 28*(E_B+E_W) + 128*N) / its mean launch duration, measured with CUDA events in a second pass
-           over the same K cycles (every kernel bracketed by its own event pair; the three stage launches of a smoothing visit
-           share one pair -- divided by three -- so that they overlap as they do in the replayed graph); peak =
-           MEASURED_PEAKS.json hbm_gbs
+  roofline = the dominant kernel, the persistent visit kernel on level 0 (k_visit: minimum dt + the three RK stages
+           compute_flux_edge + boundary + wall flux + time_step + residual in ONE launch): algorithmic bytes per launch
+           3 * (32*E_I + 28*(E_B+E_W) + 128*N) / its mean launch duration, measured with CUDA events in a second pass over
+           the same K cycles (every kernel bracketed by its own event pair); peak = MEASURED_PEAKS.json hbm_gbs.  When the level
+           is too large for the visit kernel the stage kernel (one launch per RK stage) is reported the same way.
+  roofline_other = the same for the multigrid transfers on level 0/1 (prolong: 8*E_I + 148*N_f + 64*N_c; restrict: 44*N_f + 40*N_c)
+  sustained = ms per step and SM clock over a >= 2 s back-to-back replay of the same cycle (the headline region is short enough to
+           run at burst clocks)
   cpu_baseline = the UNMODIFIED reference (oracle/_ref/libmgcfd_ref_omp.so: its own sources built -DOMP -DOMP_SCATTERS)
-           on the host cores, mesh duplicated once per thread as its assess-memory protocol does (gen_job.py:360-365)
+           on the host cores, mesh duplicated once per thread as its assess-memory protocol does (gen_job.py:360-365), plus its
+           serial build and the per-level flux rates from its own loop timers
+  N > 1: "parity" = the same data plane on N ranks against one GPU on a small 4-level mesh before anything is timed (the run
+           aborts when it fails); "north_star_c4" (and, on 8 GPUs, "north_star_c3" = the 64 M-node mesh) = the weak-scaling
+           unit BASELINE.json's north star names, with the 1-GPU unit timed by rank 0 in the same run
 
 `--impl reference` times that reference build alone (all host threads) and prints the same line with "impl": "reference"; its
 timed sample is bounded to ~45 s of CPU work (MGCFD_REFERENCE_BUDGET_S) whatever --steps says -- the metric is a rate.
@@ -45,6 +52,7 @@ WORKLOADS = {
     "c4": (1, [[161] * 3, [81] * 3, [41] * 3, [21] * 3], 2, "C4 (weak scaling unit): 4.2M-node Kuhn-tet box per GPU, 4 levels (8 GPUs: 33M nodes; --workload c3 on 8 GPUs is the 64M-node mesh)"),
     "c3s": (1, [[129] * 3, [65] * 3, [33] * 3, [17] * 3], 2, "2.1M-node Kuhn-tet box, 4 levels (reduced C3)"),
     "tiny": (0, [[21, 19, 17], [11, 10, 9], [6, 5, 5]], 2, "tiny 3-level hex box (smoke)"),
+    "parity": (0, [[40, 24, 22], [20, 12, 11], [10, 6, 6], [5, 3, 3]], 2, "small 4-level hex box (multi-GPU parity check)"),
 }
 
 
@@ -107,9 +115,21 @@ def host_threads():
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def reference_cpu_run(workload, steps, warmup, threads):
+def cpu_model_name():
+    """What the reference's get_cpu_model_name reports (src/Base/common.h:114-143): the `model name` line of /proc/cpuinfo."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def reference_cpu_run(workload, steps, warmup, threads, with_serial=False):
     """The unmodified reference on `threads` host threads over `threads` copies of the mesh (its OMP_SCATTERS protocol).
-    Returns (edge-updates/s aggregated over the copies, seconds per step, kind, description)."""
+    Returns a dict: value (edge-updates/s aggregated over the copies), seconds per step, kind, cores, sample, steps timed,
+    per-level flux rates from the reference's own loop timers and (with_serial) the serial build's rate."""
     os.environ["OMP_NUM_THREADS"] = str(threads)
     os.environ.setdefault("OMP_PROC_BIND", "spread")
     import mgcfd_b200 as M
@@ -118,7 +138,10 @@ def reference_cpu_run(workload, steps, warmup, threads):
     from conftest import mesh_levels
     kind, dims, variant, desc = WORKLOADS[workload]
     mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
-    units = units_per_cycle([mesh.dims(l) for l in range(mesh.levels)])
+    ldims = [mesh.dims(l) for l in range(mesh.levels)]
+    units = units_per_cycle(ldims)
+    budget_s = float(os.environ.get("MGCFD_REFERENCE_BUDGET_S", "45"))
+    build = "-O3 -fno-fast-math (-DPRECISE_FP: the oracle build; the reference's default -ffast-math build is ~13% faster, SURVEY.md 6), -march=x86-64-v3, without the indirect_rw probe the stock main() also runs"
     if reference_available(omp=True):
         ref = Reference(omp=True)
         t = ref.threads()
@@ -128,18 +151,34 @@ def reference_cpu_run(workload, steps, warmup, threads):
         sess.prepare()
         # bounded sample: a CPU V-cycle of C2 takes ~0.7 s on 16 threads, so at most `budget_s` seconds of cycles are timed (the
         # metric is a rate: it does not depend on how many cycles the sample holds); the warm-up is capped likewise
-        budget_s = float(os.environ.get("MGCFD_REFERENCE_BUDGET_S", "45"))
         _, _, first = sess.run(1)
         if warmup > 1:
             sess.run(min(warmup - 1, max(0, int(0.25 * budget_s / max(first, 1e-9)))))
         n = max(1, min(steps, int(budget_s / max(first, 1e-9))))
         _, _, secs = sess.run(n)
+        tf = sess.times()["flux"]
+        per_level = {f"L{l}": t * ldims[l][1] * RK * visits(l, len(ldims)) * n / tf[l] for l in range(len(ldims)) if tf[l] > 0}
         sess.close()
-        return t * units * n / secs, secs / n, "reference", t, \
-            f"{n} V-cycle(s) timed (of {steps} requested; bounded to ~{budget_s:.0f} s of CPU work, +warm-up) of {workload} duplicated x{t} (one copy per thread, -DOMP -DOMP_SCATTERS, -DPRECISE_FP), oracle/_ref/libmgcfd_ref_omp.so", n
+        out = dict(value=t * units * n / secs, s_per_step=secs / n, kind="reference", cores=t, steps_timed=n, cpu_model=cpu_model_name(),
+                   flux_edge_updates_per_sec_by_level=per_level,
+                   sample=f"{n} V-cycle(s) timed (of {steps} requested; bounded to ~{budget_s:.0f} s of CPU work, +warm-up) of {workload} duplicated x{t} "
+                          f"(one copy per thread, -DOMP -DOMP_SCATTERS), oracle/_ref/libmgcfd_ref_omp.so = the reference's own sources, {build}; "
+                          "per-level rates from its loop timers (flux<l>, src/Monitoring/timer.cpp:106-195)")
+        if with_serial and reference_available(omp=False):
+            sref = Reference(omp=False)
+            ss = sref.session(variant, mesh_levels(mesh))
+            ss.prepare()
+            _, _, first = ss.run(1)
+            ns = max(1, min(3, int(0.3 * budget_s / max(first, 1e-9))))
+            _, _, ssecs = ss.run(ns)
+            tfs = ss.times()["flux"]
+            out["serial"] = {"value": units * ns / ssecs, "unit": "edge-updates/s", "cores": 1, "ms_per_step": ssecs / ns * 1e3, "steps_timed": ns,
+                             "flux_edge_updates_per_sec_by_level": {f"L{l}": ldims[l][1] * RK * visits(l, len(ldims)) * ns / tfs[l] for l in range(len(ldims)) if tfs[l] > 0},
+                             "build": "oracle/_ref/libmgcfd_ref.so (serial, same flags)"}
+            ss.close()
+        return out
     orc = Oracle()                      # scalar port, 1 thread
     lv = mesh_levels(mesh, apply_ewt_with=orc)
-    budget_s = float(os.environ.get("MGCFD_REFERENCE_BUDGET_S", "45"))
     t0 = time.perf_counter()
     orc.run_cycles(variant, lv, 1)
     first = time.perf_counter() - t0
@@ -147,7 +186,8 @@ def reference_cpu_run(workload, steps, warmup, threads):
     t0 = time.perf_counter()
     orc.run_cycles(variant, lv, n)
     secs = time.perf_counter() - t0
-    return units * n / secs, secs / n, "port", 1, f"{n} V-cycle(s) timed (of {steps} requested; bounded to ~{budget_s:.0f} s) of {workload}, oracle/libmgcfd_oracle.so (scalar C port), 1 thread", n
+    return dict(value=units * n / secs, s_per_step=secs / n, kind="port", cores=1, steps_timed=n, cpu_model=cpu_model_name(),
+                sample=f"{n} V-cycle(s) timed (of {steps} requested; bounded to ~{budget_s:.0f} s) of {workload}, oracle/libmgcfd_oracle.so (scalar C port), 1 thread")
 
 
 def main():
@@ -161,7 +201,10 @@ def main():
     ap.add_argument("--tile-nodes", type=int, default=None)
     ap.add_argument("--cpu-baseline-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-north-star", action="store_true", help="N > 1: skip the c4 / c3 weak-scaling units")
+    ap.add_argument("--with-serial", action="store_true", help="(reference arm) also time the serial build")
     args = ap.parse_args()
+    t_start = time.perf_counter()
     # NCCL prints "NCCL version ..." on STDOUT at NCCL_DEBUG=VERSION: keep stdout for the one JSON line
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
         os.environ["NCCL_DEBUG"] = "WARN"
@@ -175,14 +218,18 @@ def main():
         if rank != 0:
             return
         thr = host_threads()
-        v, spstep, kindname, cores, sample, n_timed = reference_cpu_run(args.workload, args.steps, W, thr)
+        r = reference_cpu_run(args.workload, args.steps, W, thr, with_serial=args.with_serial)
+        cb = {"value": r["value"], "unit": "edge-updates/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"], "cpu_model": r["cpu_model"]}
+        for k in ("flux_edge_updates_per_sec_by_level", "serial"):
+            if k in r:
+                cb[k] = r[k]
         print(json.dumps({
-            "impl": "reference", "metric": "flux edge-updates/s", "value": v, "unit": "edge-updates/s", "n_gpus": args.gpus,
-            "steps": args.steps, "steps_timed": n_timed, "warmup": W, "ms_per_step": spstep * 1e3, "higher_is_better": True, "scaling": "weak",
+            "impl": "reference", "metric": "flux edge-updates/s", "value": r["value"], "unit": "edge-updates/s", "n_gpus": args.gpus,
+            "steps": args.steps, "steps_timed": r["steps_timed"], "warmup": W, "ms_per_step": r["s_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "step": "one V-cycle", "note": "CPU only; the mesh is duplicated once per host thread; the timed sample is bounded (cpu_baseline.sample)"},
-            "cpu_baseline": {"value": v, "unit": "edge-updates/s", "cores": cores, "kind": kindname, "sample": sample},
-            "e2e": {"value": v, "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": cb,
+            "e2e": {"value": r["value"], "unit": "edge-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
 
@@ -195,8 +242,8 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
-        # control plane (barriers, the max over ranks, the NCCL id broadcast) on gloo; the data plane -- halo exchanges and
-        # scalar all-reduces between kernels -- is the library's own NCCL communicator (include/mgcfd_dist.h)
+        # control plane (barriers, the max over ranks, the NCCL id broadcast) on gloo; the data plane -- halo rows and scalar
+        # all-reduces -- is the library's own: peer-to-peer stores over NVLink from the kernels that produce the rows, or NCCL
         import torch.distributed as dist
         dist.init_process_group("gloo")
 
@@ -205,16 +252,28 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # N > 1: weak scaling -- the box grows N-fold along x (N times the nodes and edges), recursive coordinate bisection gives
-    # every rank one workload-sized part, halo exchange over NCCL (include/mgcfd_dist.h)
-    gdims = [[d[0] * world - (world - 1), d[1], d[2]] for d in dims] if (world > 1 and kind != 2) else [[d[0] * world, d[1], d[2]] for d in dims]
     kw = {}
     if args.flux_mode is not None:
         kw["flux_mode"] = args.flux_mode
     if args.tile_nodes is not None:
         kw["tile_nodes"] = args.tile_nodes
-    t0 = time.perf_counter()
-    if world > 1:
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")      # > 126 MB of L2
+    plane = {"text": "single GPU"}
+
+    def grown(d, n, knd):
+        # N > 1: weak scaling -- the box grows N-fold along x (N times the nodes and edges)
+        return [[x[0] * n - (n - 1), x[1], x[2]] for x in d] if (n > 1 and knd != 2) else [[x[0] * n, x[1], x[2]] for x in d]
+
+    def make_solver(workload, nranks):
+        """this rank's solver for `workload` grown nranks-fold; (solver, global (nodes, internal edges) per level, nodes held on level 0)"""
+        knd, dm, var, _ = WORKLOADS[workload]
+        gd = grown(dm, nranks, knd)
+        if nranks == 1:
+            mesh = M.Mesh.generate(knd, gd, mesh_variant=var)
+            ld = [mesh.dims(l) for l in range(mesh.levels)]
+            s = M.Solver.from_mesh(mesh, device=local, **kw)
+            mesh.close()
+            return s, ld, ld[0][0]
         idt = torch.zeros(128, dtype=torch.uint8)
         sys.stdout.flush()
         saved_stdout = os.dup(1)
@@ -225,15 +284,15 @@ def main():
             dist.broadcast(idt, 0)
             # every rank generates ITS part of the N-fold mesh (mgcfd_generate_upload_partition: bit for bit the partition of the
             # assembled mesh, tests/test_partition.py) -- no rank ever holds the global edge list, so 64 M nodes fit 8 ranks' hosts
-            s = M.Solver.generate_distributed(kind, gdims, rank, world, bytes(idt.numpy().tobytes()), mesh_variant=variant,
-                                              lengths=(float(world), 1.0, 1.0), device=local, **kw)
-            ldims = []
-            for l in range(len(dims)):
+            s = M.Solver.generate_distributed(knd, gd, rank, nranks, bytes(idt.numpy().tobytes()), mesh_variant=var,
+                                              lengths=(float(nranks), 1.0, 1.0), device=local, **kw)
+            ld = []
+            for l in range(len(dm)):
                 info = s.dist_level_info(l)
-                ldims.append((info["global_nodes"], info["global_internal_edges"]))          # GLOBAL counts
-            if os.environ.get("MGCFD_NO_P2P", "0") != "1":      # direct peer-to-peer data path (CUDA IPC windows) instead of NCCL
+                ld.append((info["global_nodes"], info["global_internal_edges"]))          # GLOBAL counts
+            if os.environ.get("MGCFD_NO_P2P", "0") != "1":      # direct peer-to-peer data path (CUDA IPC) instead of NCCL
                 mine = s.p2p_prepare()
-                allp = [None] * world
+                allp = [None] * nranks
                 dist.all_gather_object(allp, mine)
                 ok = 1
                 try:
@@ -245,27 +304,18 @@ def main():
                 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
                 if int(flag) == 0:
                     raise SystemExit("bench.py: the ranks disagree on the peer-to-peer data path; rerun with MGCFD_NO_P2P=1")
-                data_plane = "direct peer-to-peer stores over NVLink (CUDA IPC windows, one kernel per exchange / all-reduce, cycle replayed as a CUDA graph)"
+                plane["text"] = ("peer-to-peer stores over NVLink (one CUDA IPC slab per rank): every kernel delivers the rows it produces into the "
+                                 "other ranks' arrays itself, the visit kernel's grid barriers double as the halo exchange; cycle replayed as a CUDA graph")
             else:
-                data_plane = "NCCL send/recv + all-reduce" 
+                plane["text"] = "NCCL send/recv + all-reduce between the stage kernels"
         finally:
             sys.stdout.flush()
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
-        n_local0 = s._nel[0]
-    else:
-        mesh = M.Mesh.generate(kind, gdims, mesh_variant=variant, lengths=(float(world), 1.0, 1.0))
-        ldims = [mesh.dims(l) for l in range(mesh.levels)]
-        s = M.Solver.from_mesh(mesh, device=local, **kw)
-        n_local0 = ldims[0][0]
-        mesh.close()
-    units = units_per_cycle(ldims)
-    setup_s = time.perf_counter() - t0
-    stream = torch.cuda.ExternalStream(s.cuda_stream(), device=local)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")      # > 126 MB of L2
-    K = args.steps
+        return s, ld, s._nel[0]
 
-    def timed_pass():
+    def timed_pass(s, K):
+        stream = torch.cuda.ExternalStream(s.cuda_stream(), device=local)
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         l0 = s.launch_count()
         barrier()
@@ -279,20 +329,89 @@ def main():
         barrier()
         return sum(a.elapsed_time(b) for a, b in ev), s.launch_count() - l0, ra
 
+    def max_over_ranks(vals):
+        if dist is None:
+            return list(vals)
+        t = torch.tensor(list(vals), dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.tolist()
+
+    # ------------------------------------------------------------------ N > 1: parity of this data plane before anything is timed
+    parity = None
+    if world > 1:
+        cycles = 6
+        s, _, _ = make_solver("parity", world)
+        ra, _ = s.run_cycles(cycles)
+        pieces = []
+        nl = len(WORKLOADS["parity"][1])
+        for l in range(nl):
+            info = s.dist_level_info(l)
+            pieces.append((s.global_ids(l)[:info["owned"]], s.get_field(l, M.FIELD_VARIABLES)[:info["owned"]].copy()))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, pieces)
+        s.close()
+        err = 0.0
+        if rank == 0:
+            knd, dm, var, _ = WORKLOADS["parity"]
+            ref = M.Solver.from_mesh(M.Mesh.generate(knd, grown(dm, world, knd), mesh_variant=var), device=local, **kw)
+            rra, _ = ref.run_cycles(cycles)
+            err = float(np.max(np.abs(ra - rra) / rra))
+            for l in range(nl):
+                want = ref.get_field(l, M.FIELD_VARIABLES)
+                got = np.full_like(want, np.nan)
+                for p in gathered:
+                    got[p[l][0]] = p[l][1]
+                e = np.max(np.abs(got - want), axis=0) / np.max(np.abs(want), axis=0)
+                err = max(err, float(np.max(e)) if np.all(np.isfinite(e)) else float("inf"))
+            ref.close()
+        (err,) = max_over_ranks([err])
+        parity = {"max_rel_err": err, "tol": 1e-11, "nranks": world, "cycles": cycles,
+                  "what": "rms history + final variables of every level, N ranks vs one GPU, " + WORKLOADS["parity"][3] + f" grown {world}-fold"}
+        if not (err < 1e-11):
+            if rank == 0:
+                print(json.dumps({"error": "multi-GPU parity check failed", "parity": parity}))
+            raise SystemExit(3)
+
+    # ------------------------------------------------------------------ the headline unit
+    t0 = time.perf_counter()
+    s, ldims, n_local0 = make_solver(args.workload, world)
+    units = units_per_cycle(ldims)
+    setup_s = time.perf_counter() - t0
+    K = args.steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()           # clocks are sampled (20 ms) from the warm-up to the end of the second timed pass
     s.run_cycles(W)
-    ms_total, launches, rms = timed_pass()
+    ms_total, launches, rms = timed_pass(s, K)
     # second pass, same K cycles, every kernel bracketed by its own CUDA events (graphs bypassed): per-kernel durations
     s.set_timing(True)
     s.reset_times()
     s.run_cycles(2)
     s.reset_times()
-    ms_total_timed, _, _ = timed_pass()
+    ms_total_timed, _, _ = timed_pass(s, K)
     t_ms, t_it = s.times()
     s.set_timing(False)
     clocks = sampler.stop() if rank == 0 else None
+    # sustained: the same cycle replayed back to back for >= 2 s (no event pairs, no flush between cycles: the steady-state rate
+    # at the clocks the device settles to)
+    sus = None
+    if world == 1:
+        n_sus = int(min(4000, max(50, 2.2e3 / max(ms_total / K, 1e-3))))
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        stream = torch.cuda.ExternalStream(s.cuda_stream(), device=local)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.run_cycles(5)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            s.enqueue_cycles(n_sus)
+            e1.record(stream)
+        s.collect()
+        torch.cuda.synchronize()
+        c2 = sampler2.stop()
+        sus_ms = e0.elapsed_time(e1)
+        sus = {"ms_per_step": sus_ms / n_sus, "steps": n_sus, "seconds": sus_ms * 1e-3, "value": units * n_sus / (sus_ms * 1e-3),
+               "sm_mhz_median": c2.get("sm_mhz"), "reasons": c2.get("reasons"), "l2": "not flushed between cycles (back-to-back replay)"}
 
     # e2e: host buffers through the public API
     n0 = n_local0
@@ -311,29 +430,83 @@ def main():
         host_in, host_out = host_out, host_in
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    ms_total, e2e_s, ms_total_timed = max_over_ranks([ms_total, e2e_s, ms_total_timed])
 
-    if dist is not None:
-        t = torch.tensor([ms_total, e2e_s, ms_total_timed], dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, ms_total_timed = t.tolist()
+    nl = len(ldims)
+    info0 = s.level_info(0)
+    vinfo = [s.visit_info(l) for l in range(nl)]
+    linfo = [s.level_info(l) for l in range(nl)]
+    s.close()
+
+    # ------------------------------------------------------------------ N > 1: the north-star weak-scaling units
+    north = {}
+    if world > 1 and not args.no_north_star:
+        todo = ["c4"] + (["c3"] if world == 8 else [])
+        for wl in todo:
+            key = "north_star_" + wl
+            if time.perf_counter() - t_start > (420 if wl == "c4" else 520):
+                north[key] = {"skipped": "time budget of this run"}
+                continue
+            try:
+                nk = 10 if wl == "c4" else 6
+                one = None
+                if rank == 0:                      # the 1-GPU unit, timed by rank 0 alone in this same run
+                    s1, ld1, _ = make_solver(wl, 1)
+                    s1.run_cycles(3)
+                    stream = torch.cuda.ExternalStream(s1.cuda_stream(), device=local)
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    with torch.cuda.stream(stream):
+                        e0.record(stream); s1.enqueue_cycles(nk); e1.record(stream)
+                    s1.collect(); torch.cuda.synchronize()
+                    one = (e0.elapsed_time(e1) / nk, units_per_cycle(ld1), ld1[0][0])
+                    s1.close()
+                sN, ldN, _ = make_solver(wl, world)
+                sN.run_cycles(3)
+                stream = torch.cuda.ExternalStream(sN.cuda_stream(), device=local)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
+                with torch.cuda.stream(stream):
+                    e0.record(stream); sN.enqueue_cycles(nk); e1.record(stream)
+                raN, _ = sN.collect(); barrier()
+                (msN,) = max_over_ranks([e0.elapsed_time(e1) / nk])
+                vis = [sN.visit_info(l)["visit"] for l in range(len(ldN))]
+                sN.close()
+                if rank == 0:
+                    valN = units_per_cycle(ldN) / (msN * 1e-3)
+                    val1 = one[1] / (one[0] * 1e-3)
+                    north[key] = {"workload": WORKLOADS[wl][3], "nodes": int(ldN[0][0]), "internal_edges_level0": int(ldN[0][1]), "n_gpus": world, "steps": nk,
+                                  "ms_per_step": msN, "value": valN, "unit": "edge-updates/s", "mg_cycles_per_sec": 1e3 / msN,
+                                  "one_gpu_unit": {"nodes": int(one[2]), "ms_per_step": one[0], "value": val1},
+                                  "efficiency_vs_same_run_1gpu_unit": valN / (world * val1), "final_rms": float(raN[-1]), "visit_kernel_levels": vis,
+                                  "l2": "not flushed (working set far above L2)"}
+            except Exception as e:          # the headline line is printed whatever happens here
+                north[key] = {"error": repr(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    nl = len(ldims)
-    info0 = s.level_info(0)
     nel, nI, nB, nW = info0["nel"], info0["nI"], info0["nB"], info0["nW"]      # this rank's level 0 (the whole level when N = 1)
     flux_ms0, flux_it0 = float(t_ms[1, 0]), int(t_it[1, 0])
-    flux_launches0 = flux_it0 // max(nI, 1)
     peak, peak_src = measured_peak()
-    alg_bytes = 32 * nI + 28 * (nB + nW) + 128 * nel
-    avg_launch_ms = flux_ms0 / max(flux_launches0, 1)
+    use_visit = bool(vinfo[0]["visit"])
+    stage_launches0 = flux_it0 // max(nI, 1)                 # RK stages timed on level 0
+    stage_bytes = 32 * nI + 28 * (nB + nW) + 128 * nel
+    if use_visit:
+        launches_timed = stage_launches0 // RK                # one launch = one visit = three stages
+        alg_bytes = RK * stage_bytes
+        kname = ("k_visit level 0 (persistent: minimum dt + 3 x [compute_flux_edge + boundary + wall flux + time_step] + residual/RMS, ONE launch per "
+                 "smoothing visit; algorithmic bytes = 3 stages x (32 E_I + 28 (E_B+E_W) + 128 N))")
+    else:
+        launches_timed = stage_launches0
+        alg_bytes = stage_bytes
+        kname = "k_stage_pipe level 0 (compute_flux_edge + boundary + wall flux + time_step fused, one launch per RK stage)"
+    avg_launch_ms = flux_ms0 / max(launches_timed, 1)
     achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9 if avg_launch_ms > 0 else 0.0
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
+        traffic = tj.get(args.workload + ("_visit" if use_visit else ""), {}).get("dram_bytes_per_launch")
     except Exception:
         pass
     per_level = {}
@@ -341,28 +514,46 @@ def main():
         if t_ms[1, l] > 0:
             per_level[f"L{l}"] = float(t_it[1, l]) / (float(t_ms[1, l]) * 1e-3)
     kernel_share = {name: float(t_ms[k].sum()) for k, name in enumerate(M.KERNEL_NAMES) if t_ms[k].sum() > 0}
+    other = {}
+    if nl > 1 and world == 1:
+        nf, nc = linfo[0]["nel"], linfo[1]["nel"]
+        # prolong level 1 -> 0 (timer index 6, level 0) and restrict level 0 -> 1 (timer index 5, level 1); iters = nI resp. nel_fine per launch
+        for name, k, lev, nbytes, per in (("k_prolong level 1->0 (prolong_residuals_interpolate_proper)", 6, 0, 8 * linfo[0]["nI"] + 148 * nf + 64 * nc, linfo[0]["nI"]),
+                                          ("k_restrict level 0->1 (mg_restrict)", 5, 1, 44 * nf + 40 * nc, nf)):
+            n_l = int(t_it[k, lev]) // max(per, 1)
+            if n_l > 0 and t_ms[k, lev] > 0:
+                us = float(t_ms[k, lev]) / n_l * 1e3
+                other[name] = {"achieved": nbytes / (us * 1e-6) / 1e9, "unit": "GB/s", "frac": nbytes / (us * 1e-6) / 1e9 / peak, "algorithmic_bytes_per_launch": nbytes,
+                               "avg_launch_us": us, "launches_timed": n_l}
     out = {
         "metric": "flux edge-updates/s", "value": units * K / (ms_total * 1e-3), "unit": "edge-updates/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc, "step": "one V-cycle (euler3d_cpu_double.cpp:371-694), all levels",
-                   "edge_updates_per_step": units, "parallelism": "single GPU" if world == 1 else f"{world} ranks, mesh split by recursive coordinate bisection (box {world}x longer in x), halo exchange of node records per RK stage / transfer + all-reduce(min dt, RMS): " + data_plane,
-                   "l2": "256 MiB buffer written before every timed cycle (L2 flush)", "flux_mode": {0: "tiled coloured scatter", 1: "tiled sorted segment", 2: "atomic"}[int(kw.get("flux_mode", 1))], "pipelined": bool(info0["pipe_grid"]),
-                   "tile_nodes": int(info0["tile_nodes"]), "setup_s": round(setup_s, 2)},
+                   "edge_updates_per_step": units, "parallelism": "single GPU" if world == 1 else f"{world} ranks, mesh split by recursive coordinate bisection (box {world}x longer in x): " + plane["text"],
+                   "l2": "256 MiB buffer written before every timed cycle (L2 flush)", "flux_mode": {0: "tiled coloured scatter", 1: "tiled sorted segment", 2: "atomic"}[int(kw.get("flux_mode", 1))],
+                   "visit_kernel": [{"level": l, "on": bool(v["visit"]), "supers_per_cta": int(v["supers_per_cta"]), "ctas": int(v["ctas"]), "ring_rounds": int(v["ring_rounds"]), "ring_entries": int(v["ring_entries"]),
+                                     "resident": bool(v["resident"]), "smem_bytes": int(v["smem_bytes"])} for l, v in enumerate(vinfo)],
+                   "pipelined": bool(info0["pipe_grid"]), "tile_nodes": int(info0["tile_nodes"]), "setup_s": round(setup_s, 2)},
         "mg_cycles_per_sec": K / (ms_total * 1e-3),
         "flux_edge_updates_per_sec_by_level": per_level,
         "kernel_ms_timed_pass": kernel_share, "ms_per_step_timed_pass": ms_total_timed / K,
         "final_rms": float(rms[-1]) if len(rms) else None,
-        "roofline": {"bound": "hbm", "kernel": "k_stage_pipe level 0 (compute_flux_edge + boundary + wall flux + time_step fused, one launch per RK stage)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_launch_ms * 1e3, "launches_timed": flux_launches0,
-                     "edge_updates_per_sec": nI / (avg_launch_ms * 1e-3) if avg_launch_ms > 0 else 0.0},
+                     "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": avg_launch_ms * 1e3, "launches_timed": launches_timed,
+                     "edge_updates_per_sec": flux_it0 / (flux_ms0 * 1e-3) if flux_ms0 > 0 else 0.0},
+        "roofline_other": other,
         "e2e": {"value": units * e2e_steps / e2e_s, "unit": "edge-updates/s", "h2d_bytes_per_step": 40 * n0, "d2h_bytes_per_step": 40 * n0 + 48,
                 "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
                 "path": "Solver.set_field(pinned host) -> Solver.run_cycles(1) -> Solver.get_field(pinned host), C ABI mgcfd_set_field/mgcfd_run_cycles/mgcfd_get_field"},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    s.close()
+    if sus is not None:
+        out["sustained"] = sus
+    if parity is not None:
+        out["parity"] = parity
+    out.update(north)
     del flush
     if not args.no_cpu_baseline:
         try:
@@ -371,7 +562,7 @@ def main():
             for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
                 env.pop(k, None)
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload, "--steps",
-                                str(args.cpu_baseline_steps), "--warmup", "1"], capture_output=True, text=True, env=env, timeout=900)
+                                str(args.cpu_baseline_steps), "--warmup", "1", "--with-serial"], capture_output=True, text=True, env=env, timeout=900)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
             cb = json.loads(line)
             out["cpu_baseline"] = dict(cb["cpu_baseline"], ms_per_step=cb["ms_per_step"])

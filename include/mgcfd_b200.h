@@ -159,6 +159,9 @@ int mgcfd_level_info(mgcfd_ctx* ctx, int level, long info[16]);
 /* the persistent visit kernel's configuration of a level: info[0..7] = in use (0/1), super-tiles per CTA, CTAs, edge rounds per ring
  * entry, own rows resident in shared memory (0/1), rows of the largest super-tile, shared memory per CTA (bytes), halo rows in total */
 int mgcfd_visit_info(mgcfd_ctx* ctx, int level, long info[8]);
+/* development aid (MGCFD_VISIT_DEBUG=1 in the environment at mgcfd_create): clock stamps of the most recent visit-kernel launch, 64
+ * per CTA (tools/visit_timeline.py decodes them); returns the number of CTAs' worth of stamps copied or a negative error */
+int mgcfd_visit_debug(mgcfd_ctx* ctx, long long* out, long cap);
 /* new_of_old[nel]: the node renumbering (a bijection onto [0,padded) minus padding) */
 int mgcfd_get_permutation(mgcfd_ctx* ctx, int level, long* new_of_old);
 /* verifies on the host that no two edges of one colour round of one tile write the same node; returns #conflicts */

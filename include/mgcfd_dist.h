@@ -1,13 +1,19 @@
 /* mgcfd_dist.h -- multi-GPU runs of libmgcfd_b200.so: one process per GPU, the mesh split over the ranks by recursive
- * coordinate bisection, a halo exchange of node records after every Runge-Kutta stage / restriction / prolongation and of
- * coarse residuals before every prolongation (ncclSend/ncclRecv over NVLink, grouped per exchange), plus two scalar
- * all-reduces (min dt per smoothing visit: src/Kernels/cfd_loops.cpp:138-150; RMS sums per cycle: validation.cpp:91-105).
+ * coordinate bisection.  What crosses ranks: the node records of ghost nodes after every Runge-Kutta stage, restriction and
+ * prolongation, the coarse residuals of ghost nodes before a prolongation, and two scalar all-reduces (min dt per smoothing
+ * visit: src/Kernels/cfd_loops.cpp:138-150; RMS sums per cycle: validation.cpp:91-105).  Two data planes, same results:
+ *   - peer-to-peer (mgcfd_dist_p2p_prepare / _attach, the default of bench.py and the driver): every kernel that PRODUCES a row
+ *     stores it straight into the other ranks' copies over NVLink (one CUDA IPC slab per rank); the persistent visit kernel's
+ *     grid barriers double as the halo exchange; the whole distributed V-cycle is one replayed CUDA graph;
+ *   - NCCL (no attach): packing kernels + grouped ncclSend/ncclRecv + ncclAllReduce between the stage kernels, launched eagerly
+ *     (MGCFD_DIST_GRAPH=1 captures them too).
  * The reference has no distributed path at all (single process): nothing here replaces a reference
  * interface, it extends mgcfd_b200.h.  NCCL is loaded at run time (dlopen), so single-GPU users do not need it.
  *
- * Call order per rank:  mgcfd_create -> mgcfd_dist_init -> mgcfd_mesh_upload_partition (or your own partition through
- * mgcfd_upload_level + the lists) -> mgcfd_run_cycles / mgcfd_enqueue_cycles + mgcfd_collect (collective: every rank calls
- * them with the same arguments) -> mgcfd_get_field (local nodes: owned first, then ghosts; mgcfd_dist_global_ids maps them). */
+ * Call order per rank:  mgcfd_create -> mgcfd_dist_init -> mgcfd_mesh_upload_partition (or mgcfd_generate_upload_partition)
+ * [-> mgcfd_dist_p2p_prepare, all-gather, mgcfd_dist_p2p_attach] -> mgcfd_run_cycles / mgcfd_enqueue_cycles + mgcfd_collect
+ * (collective: every rank calls them with the same arguments) -> mgcfd_get_field (local nodes: owned first, then ghosts;
+ * mgcfd_dist_global_ids maps them). */
 #ifndef MGCFD_DIST_H
 #define MGCFD_DIST_H
 #include "mgcfd_b200.h"
@@ -17,7 +23,8 @@ extern "C" {
 
 /* rank 0 creates the NCCL unique id; the host program broadcasts the 128 bytes to the other ranks (torch.distributed, MPI, a file) */
 int mgcfd_dist_get_unique_id(char id[128]);
-/* joins the communicator; after mgcfd_create, before any upload. CUDA graphs are switched off for distributed contexts. */
+/* joins the communicator; after mgcfd_create, before any upload.  Until mgcfd_dist_p2p_attach the cycle is launched eagerly (NCCL
+ * calls between kernels; MGCFD_DIST_GRAPH=1 captures them); after the attach it is replayed as a CUDA graph like a single-GPU run. */
 int mgcfd_dist_init(mgcfd_ctx* ctx, int rank, int nranks, const char id[128]);
 /* info[0..7]: owned nodes, ghost nodes, nodes sent per exchange, nodes of the level over all ranks, rank, nranks, exchanges so far,
  * internal edges of the level over all ranks */
@@ -38,16 +45,13 @@ int mgcfd_generate_partition_plan(int kind, int levels, const long* dims, const 
                                   int apply_ewt, int nranks, int rank, int level, long info[8], long* gid, long* send_counts,
                                   long* recv_counts, long* send_gids);
 
-/* Direct peer-to-peer data path (optional, after mgcfd_mesh_upload_partition): every halo exchange and scalar all-reduce becomes
- * ONE kernel per rank that stores straight into the peers' memory over NVLink (CUDA IPC windows) and hand-shakes through
- * system-scope flags, instead of a packing kernel + NCCL calls.  prepare: allocates this rank's window, returns its 64-byte
- * cudaIpcMemHandle and a table of offsets (mgcfd_dist_p2p_table_len longs); the launcher all-gathers handles and tables in
- * rank order; attach: maps the peers' windows and switches the data path.  One process per GPU, all GPUs peer-accessible.
- * EXPERIMENTAL, off by default -- environment MGCFD_P2P_FUSED=1 on every rank: the Runge-Kutta stage kernels exchange their halo rows
- * themselves (stores into the peers' record buffers from the kernel that computes the rows, signal when the grid is done, wait
- * at the start of the next kernel that reads ghosts): no exchange kernel between the stages.  The offset table then also carries
- * the IPC handles of the record buffers (mgcfd_dist_p2p_table_len grows accordingly; nothing changes for the launcher).
- * Implemented and reviewed, not yet run on hardware. */
+/* Direct peer-to-peer data path (after the upload): prepare returns the 64-byte cudaIpcMemHandle of this rank's slab (window of
+ * flags / reduction slots / staging + the record buffers and residual planes of every level) and a table of offsets
+ * (mgcfd_dist_p2p_table_len longs); the launcher all-gathers handles and tables in rank order; attach maps the peers' slabs, builds
+ * the row -> (peer, remote row) tables and switches the data plane.  From then on restrict, prolong and the visit kernel deliver the
+ * rows they produce themselves and synchronise through epoch numbers in system-scope flags (every rank runs the same kernel
+ * sequence, so the epochs advance alike on all ranks -- also on a rank that has no halo at some level).  One process per GPU, all
+ * GPUs peer-accessible (NVLink / NVSwitch).  MGCFD_NO_P2P=1 in the launchers keeps the NCCL plane. */
 long mgcfd_dist_p2p_table_len(mgcfd_ctx* ctx);
 int mgcfd_dist_p2p_prepare(mgcfd_ctx* ctx, char handle[64], long* table, long table_cap);
 int mgcfd_dist_p2p_attach(mgcfd_ctx* ctx, const char* handles, const long* tables, long table_len);

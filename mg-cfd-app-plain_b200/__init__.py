@@ -87,6 +87,7 @@ def lib() -> C.CDLL:
     L.mgcfd_synchronize.argtypes = [vp]
     L.mgcfd_level_info.argtypes = [vp, i, C.POINTER(l)]
     L.mgcfd_visit_info.argtypes = [vp, i, C.POINTER(l)]
+    L.mgcfd_visit_debug.argtypes = [vp, vp, l]
     L.mgcfd_get_permutation.argtypes = [vp, i, vp]
     L.mgcfd_check_colouring.argtypes = [vp, i]
     L.mgcfd_check_colouring.restype = l
@@ -127,6 +128,13 @@ def lib() -> C.CDLL:
     L.mgcfd_mesh_free.restype = None
     _lib = L
     return L
+
+
+def _visit_dict(info):
+    d = dict(zip(("visit", "supers_per_cta", "ctas", "ring_rounds", "resident", "super_rows", "smem_bytes", "halo_rows"), info))
+    d["ring_entries"] = d["ring_rounds"] >> 8          # per-warp ring: entries x rounds per entry
+    d["ring_rounds"] &= 0xFF
+    return d
 
 
 def _check(rc: int, mesh: bool = False):
@@ -407,7 +415,15 @@ class Solver:
         """Configuration of the persistent visit kernel on `level` (include/mgcfd_b200.h mgcfd_visit_info)."""
         out = (C.c_long * 8)()
         _check(lib().mgcfd_visit_info(self._h, level, out))
-        return dict(zip(("visit", "supers_per_cta", "ctas", "ring_rounds", "resident", "super_rows", "smem_bytes", "halo_rows"), out))
+        return _visit_dict(out)
+
+    def visit_debug(self):
+        """Clock stamps of the most recent visit-kernel launch, [ctas, 64] (MGCFD_VISIT_DEBUG=1 at construction)."""
+        out = np.zeros(64 * 256, dtype=np.int64)
+        n = lib().mgcfd_visit_debug(self._h, _ptr(out), out.size)
+        if n < 16:           # an error code, not a CTA count
+            _check(n or 2)
+        return out[:64 * n].reshape(n, 64)
 
     def permutation(self, level):
         p = np.empty(self._nel[level], dtype=np.int64)
@@ -526,7 +542,7 @@ def plan_emulate_visit_flux(level: dict, variables, supers: int, mask: int = 7):
     info = (C.c_long * 8)()
     _check(lib().mgcfd_plan_emulate_visit_flux(level["nel"], _ptr(level.get("coords")), level["nI"], level["nB"], level["nW"], _ptr(e), supers,
                                                _ptr(var), mask, _ptr(out), info))
-    keys = ("supers", "max_tiles", "max_halo", "halo_total", "max_rounds", "tiles", "rows")
+    keys = ("supers", "max_tiles", "max_halo", "halo_total", "max_rounds", "tiles", "rows", "warp_tiles")
     return out, dict(zip(keys, info))
 
 
@@ -535,7 +551,7 @@ def plan_visit_config(level: dict, num_sms: int = 148):
     e = np.ascontiguousarray(level["edges"])
     info = (C.c_long * 8)()
     _check(lib().mgcfd_plan_visit_config(level["nel"], _ptr(level.get("coords")), level["nI"], level["nB"], level["nW"], _ptr(e), num_sms, info))
-    return dict(zip(("visit", "supers_per_cta", "ctas", "ring_rounds", "resident", "super_rows", "smem_bytes", "halo_rows"), info))
+    return _visit_dict(info)
 
 
 def plan_emulate_transfers(fine: dict, coarse: dict, var_f, res_f, res_c, var_c, ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0):

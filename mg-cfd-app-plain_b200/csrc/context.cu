@@ -91,7 +91,8 @@ struct Level {
     PeerOut* d_peer_out = nullptr;
     // the persistent visit kernel (visit_kernel.cuh): one launch per smoothing visit
     bool visit = false;
-    int vK = 1, vG = 0, vR = 1, v_resident = 0, v_srmax = 0;
+    int vK = 1, vG = 0, vR = 1, vD = 2, v_resident = 0, v_srmax = 0;
+    bool premin_valid = false;                     // blockmins holds the per-block minima of dt of the CURRENT state (left by restrict / prolong)
     size_t v_smem = 0;
     unsigned char *d_desc = nullptr, *d_vslots = nullptr;
     int* d_cta_rows = nullptr;
@@ -143,6 +144,8 @@ struct mgcfd_ctx {
     double* d_cta_min = nullptr;               // [num_sms] per-CTA minima, [num_sms * 5] per-CTA RMS sums
     double* d_cta_rms = nullptr;
     std::map<std::string, long> graph_launches;
+    std::map<std::string, std::string> graph_flags_end;
+    long long* d_visit_dbg = nullptr;          // MGCFD_VISIT_DEBUG=1: clock stamps of the last visit-kernel launch (64 per CTA)
     int levels = 0, variant = 2;
     bool finalized = false;
     std::vector<Level> L;
@@ -177,6 +180,7 @@ struct mgcfd_ctx {
 namespace {
 
 inline long blocks_for(long n, int bs) { return (n + bs - 1) / bs; }
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
 
 // Tile size when the caller leaves it to the library (measured on B200, profiles/):
 //  * multi-million-node levels: 128-node tiles (more CTAs in flight per SM; 202 vs 197 cycles/s on the 8 M-node mesh);
@@ -573,9 +577,10 @@ int smooth_visit(mgcfd_ctx* c, int l) {
     a.bufX = v.V(X); a.bufA = v.V(A); a.bufB = v.V(B); a.ibX = X; a.ibA = A; a.ibB = B;
     a.res = v.res; a.sf = v.sf; a.vol = v.vol; a.vol_root = v.vol_root; a.stride = v.npad;
     a.legacy = (c->variant == MGCFD_MESH_FVCORR);
-    a.desc = v.d_desc; a.desc_stride = v.plan.visit.desc_stride; a.maxt = v.plan.visit.maxt; a.hpad = v.plan.visit.hpad;
+    a.desc = v.d_desc; a.desc_stride = v.plan.visit.desc_stride; a.max_ent = v.plan.visit.max_ent; a.hpad = v.plan.visit.hpad;
     a.vslots = v.d_vslots; a.bslots = v.bslots; a.cta_rows = v.d_cta_rows;
-    a.K = v.vK; a.sr_max = v.v_srmax; a.resident = v.v_resident; a.R = v.vR;
+    a.K = v.vK; a.sr_max = v.v_srmax; a.resident = v.v_resident; a.R = v.vR; a.D = v.vD;
+    if (v.premin_valid) { a.premin = v.blockmins; a.npremin = (int)blocks_for(v.ncomp, 128); }
     a.k2 = 2.0 * c->kdiss;
     a.bad_key = c->d_badkey; a.old_of_new = v.old_of_new;
     a.stage_seq0 = c->stage_seq & 0xFFFFFFull; c->stage_seq += MGCFD_RK;
@@ -593,10 +598,14 @@ int smooth_visit(mgcfd_ctx* c, int l) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = c->opt.no_pdl ? 0 : 1;
-    if (dist) CK(cudaLaunchKernelEx(&cfg, k_visit<true>, a)); else CK(cudaLaunchKernelEx(&cfg, k_visit<false>, a));
+    if (c->d_visit_dbg && !dist) {
+        a.dbg = c->d_visit_dbg;
+        CK(cudaLaunchKernelEx(&cfg, k_visit<false, true>, a));
+    } else if (dist) CK(cudaLaunchKernelEx(&cfg, k_visit<true>, a)); else CK(cudaLaunchKernelEx(&cfg, k_visit<false>, a));
     CKRC(post_launch(c));
     if (dist) c->dist.exchanges += MGCFD_RK;
     v.i_old = X; v.i_var = A; v.i_tmp = B;
+    v.premin_valid = false;
     return MGCFD_OK;
 }
 
@@ -631,6 +640,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     }
     visit_tm.reset();
     v.i_old = X; v.i_var = A; v.i_tmp = B;
+    v.premin_valid = false;
     if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
     return MGCFD_OK;
 }
@@ -639,39 +649,46 @@ int do_restrict(mgcfd_ctx* c, int lc) {
     Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
     Timed tm(c, K_RESTRICT, lc, vf.nel);
     const unsigned nb = (unsigned)blocks_for(vc.ncomp, 128);
+    // a level that runs the visit kernel gets the per-block minima of dt of its new state (never for the legacy step factor)
+    double* bm = (vc.visit && c->variant != MGCFD_MESH_FVCORR && env_int("MGCFD_PREMIN", 1)) ? vc.blockmins : nullptr;
     if (dist_inkernel(c)) {
         // reads the fine level's ghost rows (wait for the fine level's peers), delivers the coarse rows itself
         const DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers);
-        k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, t);
+        k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, t);
         c->dist.exchanges++;
+        vc.premin_valid = (bm != nullptr);
         return post_launch(c);
     }
     DistTail none;
     memset(&none, 0, sizeof(none));
-    k_restrict<false><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, none);
+    k_restrict<false><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, none);
     CKRC(post_launch(c));
+    vc.premin_valid = (bm != nullptr);
     return dist_exchange_records(c, lc, vc.V(vc.i_var));
 }
 int do_prolong(mgcfd_ctx* c, int lf) {
     Level& vf = c->L[lf]; Level& vc = c->L[lf + 1];
     Timed tm(c, K_PROLONG, lf, vf.nI);
     const unsigned nb = (unsigned)blocks_for(vf.ncomp, 128);
+    double* bm = (vf.visit && c->variant != MGCFD_MESH_FVCORR && env_int("MGCFD_PREMIN", 1)) ? vf.blockmins : nullptr;
     if (dist_inkernel(c)) {
         // the coarse residuals of ghost parents were delivered by the coarse visit's last stage when that level runs the visit
         // kernel; otherwise they are exchanged here.  The prolonged rows are delivered by the kernel itself.
         if (!vc.visit) CKRC(dist_exchange_residuals(c, lf + 1));
         const DistTail t = dist_tail(c, vf, vf.i_var, vc.d_peers, vc.npeers);
         k_prolong<true><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
-                                                   vc.res, vf.res, vf.V(vf.i_var), t);
+                                                   vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, bm, t);
         c->dist.exchanges++;
+        vf.premin_valid = (bm != nullptr);
         return post_launch(c);
     }
     CKRC(dist_exchange_residuals(c, lf + 1));
     DistTail none;
     memset(&none, 0, sizeof(none));
     k_prolong<false><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
-                                                vc.res, vf.res, vf.V(vf.i_var), none);
+                                                vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, bm, none);
     CKRC(post_launch(c));
+    vf.premin_valid = (bm != nullptr);
     return dist_exchange_records(c, lf, vf.V(vf.i_var));
 }
 
@@ -689,6 +706,7 @@ int cycle_fused(mgcfd_ctx* c) {
 std::string role_key(mgcfd_ctx* c) {
     std::string k;
     for (auto& v : c->L) { k += char('0' + v.i_var); k += char('0' + v.i_old); }
+    for (auto& v : c->L) k += v.premin_valid ? 'v' : '-';      // a captured visit kernel has the source of its minimum dt baked in
     return k;
 }
 
@@ -725,12 +743,11 @@ void free_level(Level& v) {
 
 
 // ---- the visit kernel's configuration of a level (visit_kernel.cuh) ------------------------------------------------------------
-struct VisitCfg { bool ok = false; int K = 1, G = 0, R = 1, resident = 0, sr_max = 0; size_t smem = 0; };
+struct VisitCfg { bool ok = false; bool roomy = false; int K = 1, G = 0, R = 1, D = 2, resident = 0, sr_max = 0; size_t smem = 0; };
 constexpr size_t VISIT_SMEM_LIMIT = 230000;      // 227 KB per CTA minus the kernel's static shared memory
-int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
-// shared memory of k_visit for a plan built with G * K super-tiles: ring (VG groups x VRING entries x R rounds) + record buffers
-// (resident: two own-row buffers + one halo buffer; streaming: two buffers of own + halo rows) + four descriptor buffers.
-// Picks the largest R <= half a tile's rounds that fits.
+// shared memory of k_visit for a plan built with G * K super-tiles: 16 per-warp rings (D entries x R rounds x 832 bytes) + record
+// buffers (resident: two own-row buffers + one halo buffer; streaming: two buffers of own + halo rows) + descriptor buffers (one
+// when K == 1, else four).  Ring shapes are tried from the roomiest down; `roomy` = at least four rounds buffered per warp.
 VisitCfg visit_config(const LevelPlan& P, int G, int K) {
     VisitCfg cfg;
     const VisitPlan& V = P.visit;
@@ -738,15 +755,17 @@ VisitCfg visit_config(const LevelPlan& P, int G, int K) {
     const size_t own = 64 * (size_t)VT * V.maxt, halo = 64 * (size_t)V.hpad, desc = (K == 1 ? 1 : 4) * (size_t)V.desc_stride;
     const bool resident = (K == 1) && env_int("MGCFD_VISIT_RESIDENT", 1) != 0;
     const size_t recs = resident ? 2 * own + halo : 2 * (own + halo);
-    int R = std::max(1, (V.max_rounds + 1) / 2);
-    R = std::min(R, std::max(1, env_int("MGCFD_VISIT_R", 1 << 20)));
-    auto total = [&](int r) { return (size_t)VG * VRING * r * VT * 26 + recs + desc; };
-    while (R > 1 && total(R) > VISIT_SMEM_LIMIT) R--;
-    if (total(R) > VISIT_SMEM_LIMIT) return cfg;
-    // equal chunks: ceil(max_rounds / R) chunks per tile
-    const int nchunks = std::max(1, (V.max_rounds + R - 1) / R);
-    R = std::max(1, (V.max_rounds + nchunks - 1) / nchunks);
-    cfg.ok = true; cfg.K = K; cfg.G = G; cfg.R = R; cfg.resident = resident ? 1 : 0; cfg.sr_max = VT * V.maxt; cfg.smem = total(R);
+    const int forceR = env_int("MGCFD_VISIT_R", 0), forceD = env_int("MGCFD_VISIT_D", 0);
+    const int shapes[5][2] = {{3, 2}, {2, 2}, {4, 1}, {3, 1}, {2, 1}};       // {D, R}
+    for (const auto& sh : shapes) {
+        int D = forceD > 0 ? std::min(forceD, VRING_MAX) : sh[0], R = forceR > 0 ? forceR : sh[1];
+        R = std::max(1, std::min(R, std::max(1, V.max_rounds)));
+        const size_t ring = (((size_t)VNW * D * R * VW * 26) + 127) & ~size_t(127);
+        if (ring + recs + desc > VISIT_SMEM_LIMIT) { if (forceD > 0 && forceR > 0) break; continue; }
+        cfg.ok = true; cfg.roomy = D * R >= 4 || R >= V.max_rounds; cfg.K = K; cfg.G = G; cfg.R = R; cfg.D = D; cfg.resident = resident ? 1 : 0;
+        cfg.sr_max = VT * V.maxt; cfg.smem = ring + recs + desc;
+        break;
+    }
     return cfg;
 }
 // Builds the level plan for the visit kernel: K = 1 (own rows resident) when that fits with a ring of at least two rounds per
@@ -758,7 +777,7 @@ bool plan_for_visit(int num_sms, LevelPlan& plan_out, const HostLevel& H, PlanOp
     const int G = (int)std::min<long>(num_sms, ntiles);
     po.tile_nodes = VT;
     const int forceK = env_int("MGCFD_VISIT_K", 0);
-    auto good = [&](const VisitCfg& f, const LevelPlan& P) { return f.ok && f.R >= std::min(2, std::max(1, (P.visit.max_rounds + 1) / 2)); };
+    auto good = [&](const VisitCfg& f, const LevelPlan&) { return f.ok && f.roomy; };
     VisitCfg best; LevelPlan bestP;
     int K = forceK > 0 ? forceK : 1;
     // the own rows of a super-tile alone (double-buffered, 13-bit row index) bound K from below
@@ -770,7 +789,7 @@ bool plan_for_visit(int num_sms, LevelPlan& plan_out, const HostLevel& H, PlanOp
         LevelPlan P;
         build_level_plan(H, po, P);
         const VisitCfg f = visit_config(P, G, K);
-        if (f.ok && (!best.ok || f.R > best.R)) { best = f; bestP = P; }
+        if (f.ok && (!best.ok || f.D * f.R > best.D * best.R)) { best = f; bestP = P; }
         if (forceK > 0 || good(f, P)) break;
         if (K == 1) {
             // estimate the smallest K that fits from this build: halo rows scale like rows^(2/3)
@@ -778,7 +797,7 @@ bool plan_for_visit(int num_sms, LevelPlan& plan_out, const HostLevel& H, PlanOp
             int k = 2;
             for (; k < 64; k++) {
                 const double rows = std::ceil(own1 / k / VT) * VT + h1 * std::pow((double)k, -2.0 / 3.0);
-                if (2 * 64 * rows + (double)VG * VRING * 2 * VT * 26 + 4 * (32.0 * std::ceil(own1 / k / VT) + 4 * h1 * std::pow((double)k, -2.0 / 3.0) + 16) <= (double)VISIT_SMEM_LIMIT) break;
+                if (2 * 64 * rows + (double)VNW * 4 * VW * 26 + 4 * (128.0 * std::ceil(own1 / k / VT) + 4 * h1 * std::pow((double)k, -2.0 / 3.0) + 32) <= (double)VISIT_SMEM_LIMIT) break;
             }
             K = k;
         } else K++;
@@ -863,6 +882,7 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     CK(cudaMalloc((void**)&c->d_bar, sizeof(unsigned int))); CK(cudaMemset(c->d_bar, 0, sizeof(unsigned int)));
     CK(cudaMalloc((void**)&c->d_cta_min, sizeof(double) * c->num_sms));
     CK(cudaMalloc((void**)&c->d_cta_rms, sizeof(double) * 5 * c->num_sms));
+    if (env_int("MGCFD_VISIT_DEBUG", 0)) { CK(cudaMalloc((void**)&c->d_visit_dbg, sizeof(long long) * 64 * c->num_sms)); CK(cudaMemset(c->d_visit_dbg, 0, sizeof(long long) * 64 * c->num_sms)); }
     CK(cudaMalloc((void**)&c->d_rms_counter, sizeof(int)));
     CK(cudaMemset(c->d_rms_counter, 0, sizeof(int)));
     mgcfd_far_field_conditions(c->ff, c->ffc);
@@ -881,7 +901,7 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_ticket); cudaFree(c->d_rms); cudaFree(c->d_rms_counter); cudaFree(c->d_rms_sums);
     if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
     for (int p = 0; p < (int)c->dist.peer_win.size(); p++) if (p != c->dist.rank && c->dist.peer_win[p]) cudaIpcCloseMemHandle(c->dist.peer_win[p]);
-    cudaFree(c->slab); cudaFree(c->d_bar); cudaFree(c->d_cta_min); cudaFree(c->d_cta_rms);
+    cudaFree(c->d_visit_dbg); cudaFree(c->slab); cudaFree(c->d_bar); cudaFree(c->d_cta_min); cudaFree(c->d_cta_rms);
     cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -932,7 +952,7 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     try {
         VisitCfg cfg;
         if (want_visit && plan_for_visit(c->num_sms, v.plan, H, po, cfg)) {
-            v.visit = true; v.vK = cfg.K; v.vG = cfg.G; v.vR = cfg.R; v.v_resident = cfg.resident; v.v_srmax = cfg.sr_max; v.v_smem = cfg.smem;
+            v.visit = true; v.vK = cfg.K; v.vG = cfg.G; v.vR = cfg.R; v.vD = cfg.D; v.v_resident = cfg.resident; v.v_srmax = cfg.sr_max; v.v_smem = cfg.smem;
         } else build_level_plan(H, po, v.plan);
     }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
@@ -1020,6 +1040,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
             if (v.v_smem > attr_bytes) {
                 CK(cudaFuncSetAttribute(k_visit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
                 CK(cudaFuncSetAttribute(k_visit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
+                CK(cudaFuncSetAttribute(k_visit<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
                 attr_bytes = v.v_smem;
             }
             int per_sm = 0;
@@ -1079,6 +1100,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
 int mgcfd_initialize_variables(mgcfd_ctx* c, int l) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
+    v.premin_valid = false;
     k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad);
     return post_launch(c);
 }
@@ -1104,6 +1126,7 @@ int mgcfd_time_step(mgcfd_ctx* c, int l, int j) {
     if (j < 0 || j >= MGCFD_RK) { g_err = "rk_stage out of range"; return MGCFD_ERR_ARG; }
     Level& v = c->L[l];
     CKRC(ensure_flux(c, v));
+    v.premin_valid = false;
     Timed tm(c, K_TIME, l, v.nel);
     k_time_step<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(double(MGCFD_RK + 1 - j), v.ncomp, v.npad, v.sf, v.flux, v.V(v.i_old), v.V(v.i_var));
     return post_launch(c);
@@ -1190,11 +1213,18 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
         cudaGraph_t g = nullptr;
         const long launches_before = c->launches;
         c->capturing = true;
+        std::vector<char> flags0;
+        for (auto& v : c->L) flags0.push_back(v.premin_valid);
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         int rc = cycle_fused(c);
         cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
         c->capturing = false;
         c->graph_launches[key] = c->launches - launches_before;
+        {   // what the cycle leaves behind of the minimum-dt bookkeeping; rolled back like the buffer roles, re-applied by every replay
+            std::string end;
+            for (size_t l = 0; l < c->L.size(); l++) { end += c->L[l].premin_valid ? 'v' : '-'; c->L[l].premin_valid = flags0[l] != 0; }
+            c->graph_flags_end[key] = end;
+        }
         c->launches = launches_before;        // capture recorded the launches, it did not run them
         if (rc != MGCFD_OK) { if (g) cudaGraphDestroy(g); return rc; }
         CK(ce);
@@ -1209,6 +1239,7 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
     CK(cudaGraphLaunch(it->second, c->stream));
     advance_roles_one_cycle(c);
     c->launches += c->graph_launches[key];
+    { const std::string& end = c->graph_flags_end[key]; for (size_t l = 0; l < c->L.size() && l < end.size(); l++) c->L[l].premin_valid = (end[l] == 'v'); }
     return MGCFD_OK;
 }
 }  // namespace
@@ -1301,6 +1332,7 @@ int mgcfd_set_field(mgcfd_ctx* c, int l, int field, const double* host_in) {
     CKRC(check_level(c, l));
     if (!host_in) { g_err = "null buffer"; return MGCFD_ERR_ARG; }
     Level& v = c->L[l];
+    v.premin_valid = false;
     double* p; int nc;
     CKRC(field_ptr(c, v, field, &p, &nc, true));
     if (!v.io) CK(cudaMalloc((void**)&v.io, sizeof(double) * 5 * v.nel));
@@ -1342,10 +1374,19 @@ int mgcfd_visit_info(mgcfd_ctx* c, int l, long info[8]) {
     memset(info, 0, sizeof(long) * 8);
     info[0] = v.visit ? 1 : 0;
     if (v.visit) {
-        info[1] = v.vK; info[2] = v.vG; info[3] = v.vR; info[4] = v.v_resident; info[5] = v.v_srmax; info[6] = (long)v.v_smem;
+        info[1] = v.vK; info[2] = v.vG; info[3] = v.vR | (v.vD << 8); info[4] = v.v_resident; info[5] = v.v_srmax; info[6] = (long)v.v_smem;
         info[7] = v.plan.visit.halo_total;
     }
     return MGCFD_OK;
+}
+// MGCFD_VISIT_DEBUG=1 (read at mgcfd_create): per-CTA clock stamps of the most recent visit-kernel launch, out[num_sms * 64]
+int mgcfd_visit_debug(mgcfd_ctx* c, long long* out, long cap) {
+    if (!c || !out) { g_err = "null argument"; return MGCFD_ERR_ARG; }
+    if (!c->d_visit_dbg) { g_err = "MGCFD_VISIT_DEBUG was not set when the context was created"; return MGCFD_ERR_ARG; }
+    if (cap < 64L * c->num_sms) { g_err = "buffer too small"; return MGCFD_ERR_ARG; }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(out, c->d_visit_dbg, sizeof(long long) * 64 * c->num_sms, cudaMemcpyDeviceToHost));
+    return c->num_sms;
 }
 long mgcfd_check_colouring(mgcfd_ctx* c, int l) {
     if (check_level(c, l, false) != MGCFD_OK) return -1;
@@ -1481,7 +1522,7 @@ int mgcfd_plan_emulate_visit_flux(long nel, const double* coords, long nI, long 
         if (info) {
             memset(info, 0, sizeof(long) * 8);
             info[0] = P.visit.ns; info[1] = P.visit.maxt; info[2] = P.visit.max_halo; info[3] = P.visit.halo_total; info[4] = P.visit.max_rounds;
-            info[5] = P.ntiles; info[6] = P.npad;
+            info[5] = P.ntiles; info[6] = P.npad; info[7] = P.visit.went_off[P.visit.ns];
         }
     } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     return MGCFD_OK;
@@ -1497,7 +1538,7 @@ int mgcfd_plan_visit_config(long nel, const double* coords, long nI, long nB, lo
     try {
         LevelPlan P; VisitCfg cfg;
         if (plan_for_visit(num_sms, P, H, po, cfg)) {
-            info[0] = 1; info[1] = cfg.K; info[2] = cfg.G; info[3] = cfg.R; info[4] = cfg.resident; info[5] = cfg.sr_max; info[6] = (long)cfg.smem;
+            info[0] = 1; info[1] = cfg.K; info[2] = cfg.G; info[3] = cfg.R | (cfg.D << 8); info[4] = cfg.resident; info[5] = cfg.sr_max; info[6] = (long)cfg.smem;
             info[7] = P.visit.halo_total;
         }
     } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }

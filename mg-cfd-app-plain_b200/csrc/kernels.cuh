@@ -799,14 +799,28 @@ __device__ __forceinline__ void dist_push_rec(const DistTail& d, long row, const
     for (int k = d.tgt_off[row]; k < d.tgt_off[row + 1]; k++) store_rec(d.peer_out[d.tgt_peer[k]].rec[d.ib], d.tgt_row[k], n);
 }
 
+// The transfer kernels leave the per-block minima of 0.5 * cbrt(vol) / (|v| + c) of the state they produce behind (blockDim.x = 128):
+// the next smoothing visit of that level needs exactly this minimum (compute_step_factor, cfd_loops.cpp:123-145) and no longer has to
+// pass over the nodes for it.  One shuffle reduction, one barrier and one store per block -- no atomics, no ticket.
+__device__ __forceinline__ void block_min_store(double val, double* __restrict__ out) {
+    __shared__ double wm[4];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, d));
+    if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = val;
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = fmin(fmin(wm[0], wm[1]), fmin(wm[2], wm[3]));
+}
+
 // mg_restrict (mg_loops.cpp:30-202) as a gather: children summed in ascending original fine index (the reference's
 // accumulation order, bit for bit), then multiplied by 1.0/count; coarse nodes without children keep their value.
 template <bool DIST>
 __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ vc, long ncoarse,
-                           const long* __restrict__ child_off, const int* __restrict__ child_ids, const DistTail d) {
+                           const long* __restrict__ child_off, const int* __restrict__ child_ids, const double* __restrict__ vol_root,
+                           double* __restrict__ blockmins, const DistTail d) {
     unsigned long long e0 = 0;
     if (DIST) e0 = dist_kernel_begin(d);
     const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    double s_new = 0.0;          // |v| + c of the node's state after this kernel
     if (c < ncoarse) {
         const long k0 = child_off[c], k1 = child_off[c + 1];
         if (k1 > k0) {
@@ -820,13 +834,16 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
             const double average = 1.0 / (double)(k1 - k0);
             const Rec n = make_rec(s[0] * average, s[1] * average, s[2] * average, s[3] * average, s[4] * average);
             store_rec(vc, c, n);
+            s_new = n.s;
             if (DIST) dist_push_rec(d, c, n);
-        } else if (DIST) {
+        } else {
+            if (blockmins) s_new = vc[8 * c + 7];
             // a childless coarse node keeps its value; the copies other ranks hold of it must keep up with whatever the last
             // visit left in THIS buffer of theirs (their ghost rows are only ever written by the owner)
-            if (d.tgt_off[c + 1] > d.tgt_off[c]) dist_push_rec(d, c, load_rec(vc, c));
+            if (DIST) { if (d.tgt_off[c + 1] > d.tgt_off[c]) dist_push_rec(d, c, load_rec(vc, c)); }
         }
     }
+    if (blockmins) block_min_store(c < ncoarse ? 0.5 * (vol_root[c] / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), blockmins);
     if (DIST) dist_kernel_end(d, e0);
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
@@ -835,11 +852,13 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
 template <bool DIST>
 __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __restrict__ parent, const double* __restrict__ idist_own,
                           const long* __restrict__ ent_off, const int* __restrict__ ent_src, const double* __restrict__ ent_w,
-                          const double* __restrict__ res_c, const double* __restrict__ res_f, double* __restrict__ var_f, const DistTail d) {
+                          const double* __restrict__ res_c, const double* __restrict__ res_f, double* __restrict__ var_f,
+                          const double* __restrict__ vol_root, double* __restrict__ blockmins, const DistTail d) {
     unsigned long long e0 = 0;
     if (DIST) e0 = dist_kernel_begin(d);
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int p = (i < nfine) ? parent[i] : -1;
+    double dt_new = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);      // padding rows (no parent) never win the minimum
     if (p >= 0) {
         double rp[5];
 #pragma unroll
@@ -876,8 +895,10 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
         }
         const Rec n = make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]);
         store_rec(var_f, i, n);
+        if (blockmins) dt_new = 0.5 * (vol_root[i] / n.s);
         if (DIST) dist_push_rec(d, i, n);
     }
+    if (blockmins) block_min_store(dt_new, blockmins);
     if (DIST) dist_kernel_end(d, e0);
 }
 

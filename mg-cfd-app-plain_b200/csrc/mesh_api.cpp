@@ -33,7 +33,9 @@ int mgcfd_mesh_generate(int kind, int levels, const long* dims, const double len
 int mgcfd_mesh_load(const char* input_dat, const char* dir, mgcfd_mesh** out) {
     if (!out || !input_dat) { g_mesh_err = "bad arguments"; return MGCFD_ERR_ARG; }
     mgcfd_mesh* m = new mgcfd_mesh();
-    int rc = load_mesh(input_dat, dir ? dir : "", m->m, g_mesh_err);
+    int rc;
+    try { rc = load_mesh(input_dat, dir ? dir : "", m->m, g_mesh_err); }      // no exception may cross the C ABI
+    catch (const std::exception& ex) { g_mesh_err = std::string("cannot load the mesh: ") + ex.what(); rc = MGCFD_ERR_IO; }
     if (rc) { delete m; *out = nullptr; return rc; }
     *out = m;
     return MGCFD_OK;

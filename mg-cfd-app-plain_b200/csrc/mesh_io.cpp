@@ -294,7 +294,10 @@ int read_input_dat(const std::string& path, int& size, int& levels, int& variant
         const std::string key = trim(line.substr(0, eq)), value = trim(line.substr(eq + 1));
         if (value.empty()) continue;
         if (key == "size") { size = atoi(value.c_str()); have_size = true; }
-        else if (key == "num_levels") { levels = atoi(value.c_str()); have_levels = true; }
+        else if (key == "num_levels") {
+            levels = atoi(value.c_str()); have_levels = true;
+            if (levels < 1 || levels > 8) { err = "Error parsing '" + path + "': num_levels must be between 1 and 8"; return 5; }
+        }
         else if (key == "mesh_name") {
             if (value == "la_cascade") variant = 3;
             else if (value == "rotor37") variant = 4;
@@ -306,6 +309,7 @@ int read_input_dat(const std::string& path, int& size, int& levels, int& variant
     }
     if (!have_size) { err = "Error parsing '" + path + "': size not present"; return 5; }
     if (!have_levels) { err = "Error parsing '" + path + "': number of levels not present"; return 5; }
+    if (levels < 1 || levels > 8) { err = "Error parsing '" + path + "': num_levels must be between 1 and 8"; return 5; }
     if (!have_name) { err = "Error parsing '" + path + "': mesh name not present"; return 5; }
     if (!have_files) { err = "Error parsing '" + path + "': mesh filenames not present"; return 5; }
     if (int(mgfiles.size()) != levels - 1) mgfiles.assign(levels > 0 ? levels - 1 : 0, "");
@@ -334,26 +338,37 @@ int read_level_bin(const std::string& path, HostLevel& out, std::string& err) {
     if (!f) { err = "'" + path + "' binary file cannot be read"; return 5; }
     long hdr[8];
     auto bad = [&]() { fclose(f); err = "Corruption detected in '" + path + "'"; return 5; };
+    // every size in the header is checked against what the file can still hold BEFORE anything is allocated or indexed: a corrupt
+    // cache file must come back as an error, never as a crash (load_mesh tries the .bin cache first)
+    if (fseek(f, 0, SEEK_END) != 0) return bad();
+    const long fsize = ftell(f);
+    if (fsize < 0 || fseek(f, 0, SEEK_SET) != 0) return bad();
     if (fread(hdr, sizeof(long), 8, f) != 8) return bad();
     for (int k = 0; k < 8; k++) if (hdr[k] < 0) return bad();
-    if (hdr[2] + hdr[3] + hdr[4] > hdr[1]) return bad();
-    out.nel = hdr[0]; out.nI = hdr[2]; out.nB = hdr[3]; out.nW = hdr[4];
-    const long ne = hdr[1];
-    out.volumes.resize(out.nel);
-    if (fread(out.volumes.data(), sizeof(double), out.nel, f) != size_t(out.nel)) return bad();
-    std::vector<EdgeNb> all(ne);
-    if (fread(all.data(), sizeof(EdgeNb), ne, f) != size_t(ne)) return bad();
-    // the header allows gaps between the three ranges; we store them contiguously
-    out.edges.clear();
-    out.edges.insert(out.edges.end(), all.begin() + hdr[5], all.begin() + hdr[5] + out.nI);
-    out.edges.insert(out.edges.end(), all.begin() + hdr[6], all.begin() + hdr[6] + out.nB);
-    out.edges.insert(out.edges.end(), all.begin() + hdr[7], all.begin() + hdr[7] + out.nW);
-    out.coords.resize(3 * out.nel);
-    if (fread(out.coords.data(), sizeof(double), 3 * out.nel, f) != size_t(3 * out.nel)) return bad();
-    long mgs = 0;
-    if (fread(&mgs, sizeof(long), 1, f) != 1 || mgs < 0) return bad();
-    out.mg.resize(mgs);   // (the reference casts the POINTER mg_size here, io_enhanced.cpp:341; not reproduced)
-    if (mgs && fread(out.mg.data(), sizeof(long), mgs, f) != size_t(mgs)) return bad();
+    const long nel = hdr[0], ne = hdr[1], nI = hdr[2], nB = hdr[3], nW = hdr[4];
+    const long cap = fsize / 8;                              // nothing in the file can count more items than this
+    if (nel > cap || ne > cap || nI > ne || nB > ne || nW > ne || nI + nB + nW > ne) return bad();
+    if (hdr[5] > ne - nI || hdr[6] > ne - nB || hdr[7] > ne - nW) return bad();      // the three ranges lie inside the edge array
+    const __int128 need = (__int128)64 + (__int128)8 * nel + (__int128)40 * ne + (__int128)24 * nel + 8;
+    if (need > (__int128)fsize) return bad();
+    try {
+        out.nel = nel; out.nI = nI; out.nB = nB; out.nW = nW;
+        out.volumes.resize(nel);
+        if (fread(out.volumes.data(), sizeof(double), nel, f) != size_t(nel)) return bad();
+        std::vector<EdgeNb> all(ne);
+        if (fread(all.data(), sizeof(EdgeNb), ne, f) != size_t(ne)) return bad();
+        // the header allows gaps between the three ranges; we store them contiguously
+        out.edges.clear();
+        out.edges.insert(out.edges.end(), all.begin() + hdr[5], all.begin() + hdr[5] + nI);
+        out.edges.insert(out.edges.end(), all.begin() + hdr[6], all.begin() + hdr[6] + nB);
+        out.edges.insert(out.edges.end(), all.begin() + hdr[7], all.begin() + hdr[7] + nW);
+        out.coords.resize(3 * nel);
+        if (fread(out.coords.data(), sizeof(double), 3 * nel, f) != size_t(3 * nel)) return bad();
+        long mgs = 0;
+        if (fread(&mgs, sizeof(long), 1, f) != 1 || mgs < 0 || mgs > cap) return bad();
+        out.mg.resize(mgs);   // (the reference casts the POINTER mg_size here, io_enhanced.cpp:341; not reproduced)
+        if (mgs && fread(out.mg.data(), sizeof(long), mgs, f) != size_t(mgs)) return bad();
+    } catch (const std::exception&) { return bad(); }
     fclose(f);
     return 0;
 }
@@ -382,6 +397,12 @@ int load_mesh(const std::string& input_dat, const std::string& dir, HostMesh& ou
             }
         }
         L.name = layers[l];
+    }
+    // fine -> coarse maps must point into the next level (partitioning indexes per-node arrays with them before anything else looks)
+    for (int l = 0; l + 1 < levels; l++) {
+        const HostLevel& L = out.levels[l];
+        if (long(L.mg.size()) != L.nel) { err = "multigrid map of level " + std::to_string(l) + " does not have one entry per node"; return 5; }
+        for (long v : L.mg) if (v < 0 || v >= out.levels[l + 1].nel) { err = "multigrid map of level " + std::to_string(l) + " points outside level " + std::to_string(l + 1); return 5; }
     }
     return 0;
 }

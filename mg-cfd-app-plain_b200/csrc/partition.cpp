@@ -99,6 +99,12 @@ void partition_mesh(const HostMesh& full, int nranks, int rank, LocalMesh& out) 
     out.mesh_variant = full.mesh_variant; out.rank = rank; out.nranks = nranks;
     out.levels.resize(nl);
 
+    // the fine -> coarse maps index per-node arrays of the next level below: validate them before anything does
+    for (int l = 0; l + 1 < nl; l++) {
+        const HostLevel& F = full.levels[l];
+        if (long(F.mg.size()) != F.nel) throw std::runtime_error("mgcfd: level " + std::to_string(l) + " has no fine -> coarse map of one entry per node");
+        for (long v : F.mg) if (v < 0 || v >= full.levels[l + 1].nel) throw std::runtime_error("mgcfd: mg_map entry of level " + std::to_string(l) + " out of range");
+    }
     std::vector<std::vector<int>> owner(nl);
     std::vector<Csr> adj(nl), kids(nl);         // kids[l]: children in level l-1 of the nodes of level l
     // a mesh duplicated m times (-m, mgcfd_mesh_duplicate: copy-major node numbering on every level) with m a multiple of the
@@ -234,6 +240,8 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
         rcb_owners(tmp, nranks, owner[l]);
         if (l > 0) {
             const std::vector<int>& mg = levels[l - 1].mg;
+            if (long(mg.size()) != n[l - 1]) throw std::runtime_error("mgcfd: level " + std::to_string(l - 1) + " has no fine -> coarse map of one entry per node");
+            for (int v : mg) if (v < 0 || v >= n[l]) throw std::runtime_error("mgcfd: mg_map entry of level " + std::to_string(l - 1) + " out of range");
             Csr& c = kids[l];
             c.off.assign(n[l] + 1, 0);
             for (long i = 0; i < n[l - 1]; i++) c.off[mg[i] + 1]++;

@@ -650,18 +650,20 @@ namespace {
 inline uint16_t visit_code(int idx, bool halo) { return uint16_t(((idx << 2) | ((idx >> 1) & 3)) | (halo ? 0x8000 : 0)); }
 }
 
-// The visit kernel's streams (VisitPlan): per super-tile the halo list and descriptor, per tile the edge rounds with the other
-// endpoint addressed inside the super-tile.  Called at the end of build_level_plan when PlanOptions::supers > 0.
+// The visit kernel's streams (VisitPlan): per super-tile the halo list and descriptor, per warp-tile (32 rows) the edge rounds with
+// the other endpoint addressed inside the super-tile.  Called at the end of build_level_plan when PlanOptions::supers > 0.
 static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, LevelPlan& P, const std::vector<int>& adj_eid) {
     VisitPlan& V = P.visit;
     const long TN = P.TN;
     const long ns = V.ns;
-    const size_t BLK = size_t(TN) * 26;
+    const int WT = 32;                              // rows of a warp-tile
+    const size_t BLK = size_t(WT) * 26;
     struct VSlot { int owner; int round; int other; long e; bool owner_is_a; };     // other = idx | halo << 20
+    struct Ent { int orow0, rounds, blane0; long tile; long blk0; };                // blk0 relative to the super-tile's first block
     struct SuperOut {
         std::vector<int> halo;
-        std::vector<int> rounds;                  // per tile
-        std::vector<unsigned char> blocks;        // the super-tile's round blocks, tile after tile
+        std::vector<Ent> ents;
+        std::vector<unsigned char> blocks;        // the super-tile's round blocks, warp-tile after warp-tile
         std::string error;
     };
     std::vector<SuperOut> out(ns);
@@ -681,81 +683,83 @@ static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, Leve
         if (row1 - row0 >= 8192 || long(halo.size()) >= 8192) { O.error = "mgcfd: super-tile too large for the 13-bit row index of the visit kernel"; return; }
         std::vector<VSlot> slots;
         long blocks_done = 0;
-        for (long t = t0; t < t1; t++) {
-            const long base = t * TN;
-            const int nown = P.tile_nown[t];
-            slots.clear();
-            int tile_rounds = 0;
-            for (int lu = 0; lu < nown; lu++) {
-                int r = 0;
-                for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++, r++) {
-                    const int v = P.adj_nbr[k] & 0x7fffffff;
-                    const bool is_halo = (v < row0 || v >= row1);
-                    const int idx = is_halo ? int(std::lower_bound(halo.begin(), halo.end(), v) - halo.begin()) : int(v - row0);
-                    slots.push_back({lu, r, idx | (is_halo ? (1 << 20) : 0), adj_eid[k], P.adj_nbr[k] >= 0});
-                }
-                tile_rounds = std::max(tile_rounds, r);
-            }
-            if (opt.conflict_free_rounds) {
-                // same greedy list schedule as the stage kernel's rounds (build_level_plan), on the rows of the super-tile's buffer:
-                // the 8 lanes of a quarter-warp should read rows with distinct (index mod 8) -- own and halo rows both start at a
-                // 128-byte boundary, so (index mod 8) decides the bank group in either region
-                size_t s0 = 0;
-                while (s0 < slots.size()) {
-                    const int g = slots[s0].owner / 8;
-                    size_t s1 = s0;
-                    while (s1 < slots.size() && slots[s1].owner / 8 == g) s1++;
-                    std::vector<size_t> lane_edges[8];
-                    for (size_t k = s0; k < s1; k++) lane_edges[slots[k].owner % 8].push_back(k);
-                    for (int r = 0; r < tile_rounds; r++) {
-                        int used_by[8];
-                        for (int q = 0; q < 8; q++) used_by[q] = -1;
-                        int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-                        std::stable_sort(order, order + 8, [&](int x, int y) { return lane_edges[x].size() > lane_edges[y].size(); });
-                        const int rounds_left = tile_rounds - r;
-                        for (int oi = 0; oi < 8; oi++) {
-                            auto& le = lane_edges[order[oi]];
-                            if (le.empty()) continue;
-                            int pick = -1;
-                            for (size_t c = 0; c < le.size(); c++) {
-                                const int row = slots[le[c]].other;
-                                if (used_by[row & 7] == -1 || used_by[row & 7] == row) { pick = int(c); break; }
-                            }
-                            if (pick < 0) {
-                                if (int(le.size()) < rounds_left) continue;
-                                pick = 0;
-                            }
-                            const size_t k = le[pick];
-                            slots[k].round = r;
-                            used_by[slots[k].other & 7] = slots[k].other;
-                            le.erase(le.begin() + pick);
-                        }
+        for (long t = t0; t < t1; t++)
+            for (int w4 = 0; w4 < TN / WT; w4++) {
+                const long base = t * TN + w4 * WT;
+                const int nown = std::max(0, std::min(WT, P.tile_nown[t] - w4 * WT));
+                if (nown == 0) continue;                  // nothing but padding rows: no work, no entry
+                slots.clear();
+                int wt_rounds = 0;
+                for (int lu = 0; lu < nown; lu++) {
+                    int r = 0;
+                    for (long k = P.adj_off[base + lu]; k < P.adj_off[base + lu + 1]; k++, r++) {
+                        const int v = P.adj_nbr[k] & 0x7fffffff;
+                        const bool is_halo = (v < row0 || v >= row1);
+                        const int idx = is_halo ? int(std::lower_bound(halo.begin(), halo.end(), v) - halo.begin()) : int(v - row0);
+                        slots.push_back({lu, r, idx | (is_halo ? (1 << 20) : 0), adj_eid[k], P.adj_nbr[k] >= 0});
                     }
-                    s0 = s1;
+                    wt_rounds = std::max(wt_rounds, r);
+                }
+                if (opt.conflict_free_rounds) {
+                    // the greedy list schedule of the stage kernel's rounds (build_level_plan) on the rows of the super-tile's buffers:
+                    // the 8 lanes of a quarter-warp should read rows with distinct (index mod 8) -- own and halo rows both start at a
+                    // 128-byte boundary, so (index mod 8) decides the bank group in either region
+                    size_t s0 = 0;
+                    while (s0 < slots.size()) {
+                        const int g = slots[s0].owner / 8;
+                        size_t s1 = s0;
+                        while (s1 < slots.size() && slots[s1].owner / 8 == g) s1++;
+                        std::vector<size_t> lane_edges[8];
+                        for (size_t k = s0; k < s1; k++) lane_edges[slots[k].owner % 8].push_back(k);
+                        for (int r = 0; r < wt_rounds; r++) {
+                            int used_by[8];
+                            for (int q = 0; q < 8; q++) used_by[q] = -1;
+                            int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                            std::stable_sort(order, order + 8, [&](int x, int y) { return lane_edges[x].size() > lane_edges[y].size(); });
+                            const int rounds_left = wt_rounds - r;
+                            for (int oi = 0; oi < 8; oi++) {
+                                auto& le = lane_edges[order[oi]];
+                                if (le.empty()) continue;
+                                int pick = -1;
+                                for (size_t c = 0; c < le.size(); c++) {
+                                    const int row = slots[le[c]].other;
+                                    if (used_by[row & 7] == -1 || used_by[row & 7] == row) { pick = int(c); break; }
+                                }
+                                if (pick < 0) {
+                                    if (int(le.size()) < rounds_left) continue;
+                                    pick = 0;
+                                }
+                                const size_t k = le[pick];
+                                slots[k].round = r;
+                                used_by[slots[k].other & 7] = slots[k].other;
+                                le.erase(le.begin() + pick);
+                            }
+                        }
+                        s0 = s1;
+                    }
+                }
+                int rounds = 0;
+                for (const VSlot& sl : slots) rounds = std::max(rounds, sl.round + 1);
+                const long b0 = blocks_done;
+                blocks_done += rounds;
+                O.blocks.resize(size_t(blocks_done) * BLK, 0);
+                const int orow0 = int(base - row0);          // the warp-tile's first row inside the super-tile
+                O.ents.push_back({orow0, rounds, w4 * WT, t, b0});
+                for (int r = 0; r < rounds; r++) {
+                    uint16_t* oth = reinterpret_cast<uint16_t*>(O.blocks.data() + size_t(b0 + r) * BLK + size_t(WT) * 24);
+                    for (int lu = 0; lu < WT; lu++) oth[lu] = visit_code(orow0 + lu, false);      // empty slot: the node itself, h = 0
+                }
+                for (const VSlot& sl : slots) {
+                    unsigned char* blk = O.blocks.data() + size_t(b0 + sl.round) * BLK;
+                    double* w = reinterpret_cast<double*>(blk);
+                    uint16_t* oth = reinterpret_cast<uint16_t*>(blk + size_t(WT) * 24);
+                    const double sg = sl.owner_is_a ? -0.5 : 0.5;
+                    w[sl.owner] = sg * P.ew[sl.e];
+                    w[WT + sl.owner] = sg * P.ew[L.nI + sl.e];
+                    w[2 * WT + sl.owner] = sg * P.ew[2 * L.nI + sl.e];
+                    oth[sl.owner] = visit_code(sl.other & 0xFFFFF, (sl.other >> 20) != 0);
                 }
             }
-            int rounds = 0;
-            for (const VSlot& sl : slots) rounds = std::max(rounds, sl.round + 1);
-            O.rounds.push_back(rounds);
-            const long b0 = blocks_done;
-            blocks_done += rounds;
-            O.blocks.resize(size_t(blocks_done) * BLK, 0);
-            const int own0 = int(base - row0);          // the tile's first row inside the super-tile
-            for (int r = 0; r < rounds; r++) {
-                uint16_t* oth = reinterpret_cast<uint16_t*>(O.blocks.data() + size_t(b0 + r) * BLK + size_t(TN) * 24);
-                for (int lu = 0; lu < TN; lu++) oth[lu] = visit_code(own0 + lu, false);      // empty slot: the node itself, h = 0
-            }
-            for (const VSlot& sl : slots) {
-                unsigned char* blk = O.blocks.data() + size_t(b0 + sl.round) * BLK;
-                double* w = reinterpret_cast<double*>(blk);
-                uint16_t* oth = reinterpret_cast<uint16_t*>(blk + size_t(TN) * 24);
-                const double sg = sl.owner_is_a ? -0.5 : 0.5;
-                w[sl.owner] = sg * P.ew[sl.e];
-                w[TN + sl.owner] = sg * P.ew[L.nI + sl.e];
-                w[2 * TN + sl.owner] = sg * P.ew[2 * L.nI + sl.e];
-                oth[sl.owner] = visit_code(sl.other & 0xFFFFF, (sl.other >> 20) != 0);
-            }
-        }
     };
     {
         std::atomic<long> next(0);
@@ -767,36 +771,38 @@ static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, Leve
         for (auto& f : pool) f.get();
     }
     for (const SuperOut& O : out) if (!O.error.empty()) throw std::runtime_error(O.error);
-    V.maxt = 0; V.max_halo = 0; V.max_rounds = 0; V.halo_total = 0;
-    V.vslot_off.assign(P.ntiles + 1, 0);
+    V.maxt = 0; V.max_halo = 0; V.max_rounds = 0; V.halo_total = 0; V.max_ent = 0; V.vblocks = 0;
+    V.went_off.assign(ns + 1, 0);
+    std::vector<long> blk_off(ns + 1, 0);
     for (long s = 0; s < ns; s++) {
         V.maxt = std::max<int>(V.maxt, int(V.super_off[s + 1] - V.super_off[s]));
         V.max_halo = std::max<int>(V.max_halo, int(out[s].halo.size()));
         V.halo_total += long(out[s].halo.size());
-        for (long t = V.super_off[s]; t < V.super_off[s + 1]; t++) {
-            const int r = out[s].rounds[t - V.super_off[s]];
-            V.max_rounds = std::max(V.max_rounds, r);
-            V.vslot_off[t + 1] = V.vslot_off[t] + r;
-        }
+        V.max_ent = std::max<int>(V.max_ent, int(out[s].ents.size()));
+        V.went_off[s + 1] = V.went_off[s] + long(out[s].ents.size());
+        for (const Ent& e : out[s].ents) V.max_rounds = std::max(V.max_rounds, e.rounds);
+        blk_off[s + 1] = blk_off[s] + long(out[s].blocks.size() / BLK);
     }
-    V.vslots.resize(size_t(V.vslot_off[P.ntiles]) * BLK);
+    V.vblocks = blk_off[ns];
+    V.vslots.resize(size_t(V.vblocks) * BLK);
     V.hpad = (V.max_halo + 3) & ~3;
-    V.desc_stride = (16 + 32 * V.maxt + 4 * V.hpad + 15) & ~15;
+    V.desc_stride = (32 + 32 * V.max_ent + 4 * V.hpad + 15) & ~15;
     V.desc.assign(size_t(ns) * V.desc_stride, 0);
     for (long s = 0; s < ns; s++) {
         const long t0 = V.super_off[s], t1 = V.super_off[s + 1];
-        if (!out[s].blocks.empty()) memcpy(V.vslots.data() + size_t(V.vslot_off[t0]) * BLK, out[s].blocks.data(), out[s].blocks.size());
+        if (!out[s].blocks.empty()) memcpy(V.vslots.data() + size_t(blk_off[s]) * BLK, out[s].blocks.data(), out[s].blocks.size());
         unsigned char* d = V.desc.data() + size_t(s) * V.desc_stride;
         int* di = reinterpret_cast<int*>(d);
-        di[0] = int(t0 * TN); di[1] = int(t1 - t0); di[2] = int(out[s].halo.size()); di[3] = int(t0);
-        for (long t = t0; t < t1; t++) {
-            unsigned char* th = d + 16 + 32 * (t - t0);
-            reinterpret_cast<int*>(th)[0] = int(V.vslot_off[t + 1] - V.vslot_off[t]);
-            reinterpret_cast<int*>(th)[1] = int(P.bslot_off[t + 1] - P.bslot_off[t]);
-            reinterpret_cast<long long*>(th)[1] = V.vslot_off[t];
-            reinterpret_cast<long long*>(th)[2] = P.bslot_off[t];
+        di[0] = int(t0 * TN); di[1] = int(t1 - t0); di[2] = int(out[s].halo.size()); di[3] = int(t0); di[4] = int(out[s].ents.size());
+        for (size_t k = 0; k < out[s].ents.size(); k++) {
+            const Ent& e = out[s].ents[k];
+            unsigned char* eh = d + 32 + 32 * k;
+            int* ei = reinterpret_cast<int*>(eh);
+            ei[0] = e.orow0; ei[1] = e.rounds; ei[2] = int(P.bslot_off[e.tile + 1] - P.bslot_off[e.tile]); ei[3] = e.blane0;
+            reinterpret_cast<long long*>(eh)[2] = blk_off[s] + e.blk0;
+            reinterpret_cast<long long*>(eh)[3] = P.bslot_off[e.tile];
         }
-        int* ids = reinterpret_cast<int*>(d + 16 + 32 * V.maxt);
+        int* ids = reinterpret_cast<int*>(d + 32 + 32 * V.max_ent);
         for (size_t k = 0; k < out[s].halo.size(); k++) ids[k] = out[s].halo[k];
         std::vector<unsigned char>().swap(out[s].blocks);
     }
@@ -997,12 +1003,13 @@ void emulate_stage_flux(const LevelPlan& P, const double* var, int mask, const d
     }
 }
 
-// the visit kernel's view of the same level: super-tile descriptors, their halo lists, the re-addressed edge rounds
+// the visit kernel's view of the same level: super-tile descriptors, their halo lists, warp-tile entries and re-addressed edge rounds
 void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const double ff[5], const double ffc[12], double k2, double* flux) {
     const VisitPlan& V = P.visit;
     if (V.ns <= 0) throw std::runtime_error("mgcfd: the level has no visit plan");
     const long TN = P.TN;
-    const size_t BLK = size_t(TN) * 26, BBLK = size_t(TN) * 25;
+    const int WT = 32;
+    const size_t BLK = size_t(WT) * 26, BBLK = size_t(TN) * 25;
     std::vector<HRec> rec(P.npad);
     const double pad_state[5] = {ff[0], ff[1], ff[2], ff[3], ff[4]};
     for (long g = 0; g < P.npad; g++) rec[g] = host_rec(P.old_of_new[g] >= 0 ? var + 5 * P.old_of_new[g] : pad_state);
@@ -1011,44 +1018,47 @@ void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const d
     for (long s = 0; s < V.ns; s++) {
         const unsigned char* d = V.desc.data() + size_t(s) * V.desc_stride;
         const int* di = reinterpret_cast<const int*>(d);
-        const long row0 = di[0]; const int ntile = di[1], nhalo = di[2]; const long tile0 = di[3];
-        if (row0 != tile0 * TN || ntile < 1 || ntile > V.maxt || nhalo > V.hpad) throw std::runtime_error("mgcfd: bad super-tile descriptor");
-        const int* ids = reinterpret_cast<const int*>(d + 16 + 32 * V.maxt);
+        const long row0 = di[0]; const int ntile = di[1], nhalo = di[2]; const long tile0 = di[3]; const int nent = di[4];
+        if (row0 != tile0 * TN || ntile < 1 || ntile > V.maxt || nhalo > V.hpad || nent > V.max_ent || nent > 4 * ntile) throw std::runtime_error("mgcfd: bad super-tile descriptor");
+        const int* ids = reinterpret_cast<const int*>(d + 32 + 32 * V.max_ent);
         for (int k = 0; k < nhalo; k++) {
             if (ids[k] < 0 || ids[k] >= P.npad || (ids[k] >= row0 && ids[k] < row0 + ntile * TN)) throw std::runtime_error("mgcfd: bad halo id in a super-tile");
             if (k && ids[k] <= ids[k - 1]) throw std::runtime_error("mgcfd: halo ids of a super-tile are not strictly ascending");
         }
-        for (int i = 0; i < ntile; i++) {
-            const unsigned char* th = d + 16 + 32 * i;
-            const int rounds = reinterpret_cast<const int*>(th)[0], brounds = reinterpret_cast<const int*>(th)[1];
-            const long long vblk0 = reinterpret_cast<const long long*>(th)[1], bblk0 = reinterpret_cast<const long long*>(th)[2];
-            tiles_seen++;
-            for (long lu = 0; lu < TN; lu++) {
-                const long gid = row0 + i * TN + lu;
-                if (seen[gid]++) throw std::runtime_error("mgcfd: a row belongs to two super-tiles");
+        tiles_seen += ntile;
+        for (int k = 0; k < nent; k++) {
+            const unsigned char* eh = d + 32 + 32 * k;
+            const int* ei = reinterpret_cast<const int*>(eh);
+            const int orow0 = ei[0], rounds = ei[1], brounds = ei[2], blane0 = ei[3];
+            const long long vblk0 = reinterpret_cast<const long long*>(eh)[2], bblk0 = reinterpret_cast<const long long*>(eh)[3];
+            if (orow0 < 0 || orow0 + WT > ntile * TN || (orow0 % WT) || blane0 != orow0 % TN || vblk0 < 0 || vblk0 + rounds > V.vblocks) throw std::runtime_error("mgcfd: bad warp-tile entry");
+            for (int lu = 0; lu < WT; lu++) {
+                const long gid = row0 + orow0 + lu;
+                if (seen[gid]++) throw std::runtime_error("mgcfd: a row belongs to two warp-tiles");
                 const HRec& me = rec[gid];
                 double f[5] = {0, 0, 0, 0, 0};
                 if (mask & 1)
                     for (int r = 0; r < rounds; r++) {
                         const unsigned char* blk = V.vslots.data() + size_t(vblk0 + r) * BLK;
                         const double* w = reinterpret_cast<const double*>(blk);
-                        const uint16_t code = reinterpret_cast<const uint16_t*>(blk + size_t(TN) * 24)[lu];
+                        const uint16_t code = reinterpret_cast<const uint16_t*>(blk + size_t(WT) * 24)[lu];
                         const bool is_halo = (code & 0x8000) != 0;
                         const int idx = (code & 0x7fff) >> 2;
                         if ((code & 3) != ((idx >> 1) & 3)) throw std::runtime_error("mgcfd: visit slot code does not follow the swizzle");
                         if (is_halo ? idx >= nhalo : idx >= ntile * TN) throw std::runtime_error("mgcfd: visit slot points outside the super-tile");
                         const HRec& B = is_halo ? rec[ids[idx]] : rec[row0 + idx];
                         double g[5];
-                        host_edge_flux(me, B, w[lu], w[TN + lu], w[2 * TN + lu], k2, g);
-                        for (int k = 0; k < 5; k++) f[k] += g[k];
+                        host_edge_flux(me, B, w[lu], w[WT + lu], w[2 * WT + lu], k2, g);
+                        for (int v = 0; v < 5; v++) f[v] += g[v];
                     }
                 if (mask & 6)
                     for (int r = 0; r < brounds; r++) {
                         const unsigned char* blk = P.bslots.data() + size_t(bblk0 + r) * BBLK;
                         const double* w = reinterpret_cast<const double*>(blk);
-                        const int kind = blk[size_t(TN) * 24 + lu];
+                        const int bl = blane0 + lu;
+                        const int kind = blk[size_t(TN) * 24 + bl];
                         if (kind == 0 || !((mask >> kind) & 1)) continue;
-                        const double x = w[lu], y = w[TN + lu], z = w[2 * TN + lu];
+                        const double x = w[bl], y = w[TN + bl], z = w[2 * TN + bl];
                         if (kind == 1) { f[1] += x * me.p; f[2] += y * me.p; f[3] += z * me.p; }
                         else {
                             const double fx = 0.5 * x, fy = 0.5 * y, fz = 0.5 * z;
@@ -1062,14 +1072,16 @@ void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const d
                     }
                 const long on = P.old_of_new[gid];
                 if (on < 0) {
-                    for (int k = 0; k < 5; k++) if (f[k] != 0.0) throw std::runtime_error("mgcfd: a padding thread accumulated flux");
+                    for (int v = 0; v < 5; v++) if (f[v] != 0.0) throw std::runtime_error("mgcfd: a padding thread accumulated flux");
                     continue;
                 }
-                for (int k = 0; k < 5; k++) flux[5 * on + k] = f[k];
+                for (int v = 0; v < 5; v++) flux[5 * on + v] = f[v];
             }
         }
     }
     if (tiles_seen != P.ntiles) throw std::runtime_error("mgcfd: the super-tiles do not cover the tiles");
+    // every node must have been visited (rows never listed are padding)
+    for (long g = 0; g < P.npad_owned; g++) if (!seen[g] && P.old_of_new[g] >= 0) throw std::runtime_error("mgcfd: a node belongs to no warp-tile");
 }
 
 void emulate_restrict(const LevelPlan& Pf, const LevelPlan& Pc, const TransferPlan& T, const double* var_f, double* var_c) {

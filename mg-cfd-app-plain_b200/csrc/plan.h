@@ -29,17 +29,23 @@ struct VisitPlan {
     int ns = 0;                            // super-tiles (0: not built)
     int maxt = 0;                          // most tiles in one super-tile
     int max_halo = 0, hpad = 0;            // most halo rows of one super-tile, padded to a multiple of 4
-    int max_rounds = 0;
+    int max_rounds = 0;                    // most rounds of one warp-tile
     long halo_total = 0;
     std::vector<long> super_off;           // ns+1: super-tile s = tiles [super_off[s], super_off[s+1])
-    // edge rounds, same block format as LevelPlan::slots (TN = 128) except the u16 of a slot:
+    // The unit of work is a WARP-TILE: 32 consecutive rows (a quarter of a 128-row tile) that hold at least one node.  Edge rounds
+    // per warp-tile, blocks of 32*26 bytes [hx[32] | hy[32] | hz[32] | code[32] (u16)], h as in LevelPlan::slots;
     //   code = (idx << 2) | ((idx >> 1) & 3) | (halo ? 0x8000 : 0), idx = row of the other endpoint inside the super-tile's own rows
     //   (halo = 0) or inside its halo list (halo = 1); (code & 0x7fff) << 4 is the byte offset of chunk 0 of that 64-byte row under
     //   the 64B swizzle, relative to the own-row / halo-row base.  Empty slot: the thread's own row, h = 0.
-    std::vector<long> vslot_off;           // ntiles+1, in blocks
+    std::vector<long> went_off;            // ns+1: warp-tiles (entries) of super-tile s = [went_off[s], went_off[s+1])
+    long vblocks = 0;                      // 32-lane round blocks in total
+    int max_ent = 0;                       // most warp-tiles in one super-tile
     std::vector<unsigned char> vslots;
-    // fixed-stride super-tile descriptors: {int row0, ntile, nhalo, tile0;
-    //   maxt x {int rounds, brounds; long long vslot_blk0, bslot_blk0, pad};  int halo_ids[hpad]}
+    // fixed-stride super-tile descriptors:
+    //   {int row0, ntile, nhalo, tile0, nent, 0, 0, 0;                                             (32 bytes)
+    //    max_ent x {int orow0, rounds, brounds, blane0; long long vblk0, bblk0, pad};              (32 bytes each; orow0 = first row
+    //                 inside the super-tile, blane0 = first lane inside the 128-wide boundary blocks of its tile)
+    //    int halo_ids[hpad]}
     std::vector<unsigned char> desc;
     int desc_stride = 0;
 };

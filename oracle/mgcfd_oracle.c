@@ -4,7 +4,7 @@
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg.  The product (libmgcfd_b200.so) never links,
  * imports or calls anything in this directory.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_reference.py checks every function below against the unmodified
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks every function below against the unmodified
  * reference compiled from /root/reference (oracle/_ref/libmgcfd_ref.so, built by oracle/Makefile `ref`) on seeded
  * inputs, and tests/golden/ holds outputs of the reference itself for the GPU box where /root/reference is absent.
  * The reference tree ships no golden vectors of its own.

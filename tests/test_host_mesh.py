@@ -5,6 +5,7 @@ import os
 import subprocess
 
 import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import pytest
 
 import mgcfd_b200 as M
@@ -85,6 +86,61 @@ def test_load_errors_are_reported(tmp_path):
     (tmp_path / "input.dat").write_text("size = 1\nnum_levels = 1\nmesh_name = m6wing\n[levels]\n0 = missing.mesh\n")
     with pytest.raises(M.MgcfdError):
         M.Mesh.load("input.dat", str(tmp_path))
+
+
+def test_corrupt_input_is_an_error_never_a_crash(tmp_path):
+    """A damaged .bin cache (header offsets or sizes pointing outside the file), an absurd num_levels and a multigrid map that
+    points outside the coarse level all come back as MgcfdError through the C ABI -- no exception, no out-of-bounds access."""
+    import subprocess, sys, textwrap
+    mesh = M.Mesh.generate(M.GEN_HEX_BOX, [[6, 5, 4], [3, 3, 2]], mesh_variant=M.MESH_M6_WING)
+    mesh.write(str(tmp_path), "input.dat", binary=True)
+    bins = sorted(f for f in os.listdir(tmp_path) if f.endswith(".bin"))
+    good = (tmp_path / bins[0]).read_bytes()
+    texts = [f for f in os.listdir(tmp_path) if not f.endswith((".bin", ".dat"))]
+    saved = {f: (tmp_path / f).read_bytes() for f in texts}
+    for f in texts:                                      # force the .bin cache to be the only source
+        os.remove(tmp_path / f)
+    assert M.Mesh.load("input.dat", str(tmp_path)).levels == 2
+    hdr = np.frombuffer(good[:64], dtype=np.int64).copy()
+    # each damaged file is loaded in a child process: a crash would show up as a signal, not as an exception here
+    code = textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r)
+        import mgcfd_b200 as M
+        try:
+            M.Mesh.load("input.dat", sys.argv[1])
+            print("LOADED")
+        except M.MgcfdError as e:
+            print("ERROR", e)
+    """) % ROOT
+    for k, v in ((5, 10 ** 9), (6, hdr[1] + 1), (0, 2 ** 40), (1, 2 ** 40), (2, hdr[1] + 5), (7, 2 ** 62)):
+        h = hdr.copy()
+        h[k] = v
+        (tmp_path / bins[0]).write_bytes(h.tobytes() + good[64:])
+        r = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout.startswith("ERROR"), (k, v, r.returncode, r.stdout, r.stderr[-500:])
+    (tmp_path / bins[0]).write_bytes(good[:len(good) // 2])                                   # truncated
+    r = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ERROR")
+    (tmp_path / bins[0]).write_bytes(good)
+    # num_levels out of range
+    dat = (tmp_path / "input.dat").read_text()
+    import re
+    (tmp_path / "input.dat").write_text(re.sub(r"num_levels\s*=\s*\d+", "num_levels = -1", dat))
+    r = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ERROR") and "num_levels" in r.stdout, (r.stdout, r.stderr[-500:])
+    (tmp_path / "input.dat").write_text(dat)
+    # a multigrid map that points outside the coarse level (text files, no cache)
+    for f in bins:
+        os.remove(tmp_path / f)
+    for f, b in saved.items():
+        (tmp_path / f).write_bytes(b)
+    mgf = [f for f in texts if f.endswith(".mg")][0]
+    toks = (tmp_path / mgf).read_text().split()
+    toks[3] = "99999"
+    (tmp_path / mgf).write_text(" ".join(toks))
+    r = subprocess.run([sys.executable, "-c", code, str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.startswith("ERROR") and "multigrid map" in r.stdout, (r.stdout, r.stderr[-500:])
 
 
 def test_text_formats_as_other_tools_write_them(tmp_path):

@@ -24,8 +24,14 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     dist.init_process_group("gloo")
     torch.cuda.set_device(local)
-    cases = [("hex4", 0, [[26, 24, 22], [13, 12, 11], [7, 6, 6], [4, 3, 3]], 2), ("tet3", 1, [[17, 15, 13], [9, 8, 7], [5, 4, 4]], 3), ("fvcorr", 2, [[9, 8, 7]], 0)]
+    # "coarse2": a coarsest level of 2 nodes -- with more than two ranks some ranks own nothing there and have no halo at that level;
+    # every rank must still take part in every collective step (the epoch numbers advance alike on all ranks)
+    cases = [("hex4", 0, [[26, 24, 22], [13, 12, 11], [7, 6, 6], [4, 3, 3]], 2), ("tet3", 1, [[17, 15, 13], [9, 8, 7], [5, 4, 4]], 3), ("fvcorr", 2, [[9, 8, 7]], 0),
+             ("coarse2", 0, [[16, 8, 8], [8, 4, 4], [2, 1, 1]], 2)]
     cycles = 8
+    if len(sys.argv) > 1 and sys.argv[1] == "c2":       # the bench.py unit: BASELINE config C2 grown `world`-fold along x, rank-local generation
+        cases = [("c2-unit", 0, [[67 * world - (world - 1), 67, 67], [55 * world - (world - 1), 55, 55], [48 * world - (world - 1), 48, 48], [43 * world - (world - 1), 43, 43]], 2)]
+        cycles = 3
     if len(sys.argv) > 1 and sys.argv[1] == "big":      # one mid-size case: many tiles per persistent CTA, 100 KB-class messages
         cases = [("hex4-big", 0, [[133, 67, 67], [109, 55, 55], [95, 48, 48], [85, 43, 43]], 2)]
         cycles = 4
@@ -33,7 +39,7 @@ def main():
     for name, kind, dims, variant in cases:
         uid = bcast_id(rank)
         mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
-        if name in ("tet3", "hex4-big"):      # rank-local generation (no rank assembles the mesh): the path bench.py takes
+        if name in ("tet3", "hex4-big", "c2-unit"):      # rank-local generation (no rank assembles the mesh): the path bench.py takes
             s = M.Solver.generate_distributed(kind, dims, rank, world, uid, mesh_variant=variant, device=local)
         else:
             s = M.Solver.from_mesh_distributed(mesh, rank, world, uid, device=local)

@@ -269,7 +269,7 @@ def main():
         knd, dm, var, _ = WORKLOADS[workload]
         gd = grown(dm, nranks, knd)
         if nranks == 1:
-            mesh = M.Mesh.generate(knd, gd, mesh_variant=var)
+            mesh = M.Mesh.generate(knd, gd, mesh_variant=var, lengths=(1.0, 1.0, 1.0))
             ld = [mesh.dims(l) for l in range(mesh.levels)]
             s = M.Solver.from_mesh(mesh, device=local, **kw)
             mesh.close()
@@ -353,7 +353,7 @@ def main():
         err = 0.0
         if rank == 0:
             knd, dm, var, _ = WORKLOADS["parity"]
-            ref = M.Solver.from_mesh(M.Mesh.generate(knd, grown(dm, world, knd), mesh_variant=var), device=local, **kw)
+            ref = M.Solver.from_mesh(M.Mesh.generate(knd, grown(dm, world, knd), mesh_variant=var, lengths=(float(world), 1.0, 1.0)), device=local, **kw)
             rra, _ = ref.run_cycles(cycles)
             err = float(np.max(np.abs(ra - rra) / rra))
             for l in range(nl):

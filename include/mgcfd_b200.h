@@ -76,9 +76,11 @@ typedef struct mgcfd_options {
                         (TMA bulk copies of the edge stream, cp.async gathers of node records) run one tile ahead (default 0) */
     int no_pdl;      /* 1: stage kernels are launched without programmatic dependent launch (default 0: the prologue of a stage
                         kernel -- barrier set-up, header and edge-stream prefetch -- overlaps the tail of its predecessor) */
-    int no_visit;    /* 1: never use the persistent visit kernel (one launch per smoothing visit: minimum dt, the three RK stages, residual
-                        and RMS sums separated by grid barriers, node records resident in shared memory where they fit); default 0:
-                        levels of up to ~1.2 M nodes in sorted-segment mode run it, larger levels stream through the stage kernels */
+    int visit;       /* 1: smoothing visits of levels up to ~1.2 M nodes run the persistent visit kernel (ONE launch per visit: minimum dt,
+                        the three RK stages, residual and RMS sums separated by grid barriers, node records resident in shared memory
+                        where they fit; multi-GPU: the grid barriers double as the halo exchange).  Default 0: one stage kernel per RK
+                        stage -- measured faster on B200 for the BASELINE workloads (profiles/r02*).  The environment
+                        variable MGCFD_VISIT=0/1 overrides it. */
     int reserved[7];
 } mgcfd_options;
 

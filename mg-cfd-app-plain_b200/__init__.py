@@ -40,7 +40,7 @@ class MgcfdError(RuntimeError):
 
 class Options(C.Structure):
     _fields_ = [("device", C.c_int), ("flux_mode", C.c_int), ("ordering", C.c_int), ("tile_nodes", C.c_int),
-                ("use_graph", C.c_int), ("timing", C.c_int), ("no_pipeline", C.c_int), ("no_pdl", C.c_int), ("no_visit", C.c_int), ("reserved", C.c_int * 7)]
+                ("use_graph", C.c_int), ("timing", C.c_int), ("no_pipeline", C.c_int), ("no_pdl", C.c_int), ("visit", C.c_int), ("reserved", C.c_int * 7)]
 
 
 _lib = None
@@ -132,7 +132,8 @@ def lib() -> C.CDLL:
 
 def _visit_dict(info):
     d = dict(zip(("visit", "supers_per_cta", "ctas", "ring_rounds", "resident", "super_rows", "smem_bytes", "halo_rows"), info))
-    d["ring_entries"] = d["ring_rounds"] >> 8          # per-warp ring: entries x rounds per entry
+    d["warps"] = d["ring_rounds"] >> 16                # warps per CTA (16: one CTA per SM, 8: two)
+    d["ring_entries"] = (d["ring_rounds"] >> 8) & 0xFF  # per-warp ring: entries x rounds per entry
     d["ring_rounds"] &= 0xFF
     return d
 
@@ -239,7 +240,7 @@ class Solver:
 
     def __init__(self, levels: int, mesh_variant: int, device: int = 0, flux_mode: int = FLUX_SORTED_SEGMENT,
                  ordering: int = ORDER_PARTITION_RCM, tile_nodes: int = 0, use_graph: bool = True, timing: bool = False,
-                 pipeline: bool = True, pdl: bool = True, visit: bool = True):
+                 pipeline: bool = True, pdl: bool = True, visit: bool = False):
         L = lib()
         opt = Options()
         L.mgcfd_default_options(C.byref(opt))
@@ -247,7 +248,7 @@ class Solver:
         opt.use_graph, opt.timing = int(use_graph), int(timing)
         opt.no_pipeline = int(not pipeline)
         opt.no_pdl = int(not pdl)
-        opt.no_visit = int(not visit)
+        opt.visit = int(visit)
         self._h = C.c_void_p()
         self.levels, self.mesh_variant = levels, mesh_variant
         _check(L.mgcfd_create(levels, mesh_variant, C.byref(opt), C.byref(self._h)))
@@ -419,7 +420,7 @@ class Solver:
 
     def visit_debug(self):
         """Clock stamps of the most recent visit-kernel launch, [ctas, 64] (MGCFD_VISIT_DEBUG=1 at construction)."""
-        out = np.zeros(64 * 256, dtype=np.int64)
+        out = np.zeros(64 * 512, dtype=np.int64)
         n = lib().mgcfd_visit_debug(self._h, _ptr(out), out.size)
         if n < 16:           # an error code, not a CTA count
             _check(n or 2)

@@ -60,7 +60,7 @@ struct Level {
     int TN = 256, smem_nodes = 0;
     size_t smem_bytes = 0;        // simple stage kernel
     size_t pipe_smem = 0;         // pipelined stage kernel
-    int pipe_grid = 0, chunk_rounds = 0;
+    int pipe_grid = 0, pipe_grid_dist = 0, chunk_rounds = 0;
     bool pipe = false, untiled = false;   // untiled: the numbering has no locality (atomic baseline only)
     double* buf[3] = {nullptr, nullptr, nullptr};   // node records (8 doubles each), rotating roles
     int i_var = 0, i_old = 1, i_tmp = 2;
@@ -89,12 +89,15 @@ struct Level {
     int *d_tgt_off = nullptr, *d_tgt_peer = nullptr, *d_tgt_row = nullptr;
     unsigned char* d_tile_sends = nullptr;
     PeerOut* d_peer_out = nullptr;
+    int *d_order_tiles = nullptr, *d_order_blk = nullptr;      // work units in delivery-first order: tiles of TN rows (stage kernels), 128-row blocks (transfers)
+    int n_send_tiles = 0, n_send_blk = 0;
     // the persistent visit kernel (visit_kernel.cuh): one launch per smoothing visit
     bool visit = false;
-    int vK = 1, vG = 0, vR = 1, vD = 2, v_resident = 0, v_srmax = 0;
+    int vK = 1, vG = 0, vR = 1, vD = 2, vW = 16, v_resident = 0, v_srmax = 0;
     bool premin_valid = false;                     // blockmins holds the per-block minima of dt of the CURRENT state (left by restrict / prolong)
     size_t v_smem = 0;
     unsigned char *d_desc = nullptr, *d_vslots = nullptr;
+    double* d_hsum = nullptr;
     int* d_cta_rows = nullptr;
     double* V(int i) const { return buf[i]; }
 };
@@ -131,6 +134,7 @@ struct Dist {
     double** d_red_of_rank = nullptr;          // device: [nranks] window reduction bases
     unsigned long long** d_flag_of_rank = nullptr;   // device: [nranks] &window.flags[me]
     unsigned int* d_ticket = nullptr;
+    unsigned int* d_send_ticket = nullptr;     // counts off the CTAs that deliver rows (kernels.cuh dist_send_done)
 };
 constexpr size_t P2P_FLAGS_BYTES = 64 * 8, P2P_RED_BYTES = 2 * 64 * 8 * 8, P2P_HDR_BYTES = P2P_FLAGS_BYTES + P2P_RED_BYTES;
 
@@ -143,6 +147,7 @@ struct mgcfd_ctx {
     unsigned int* d_bar = nullptr;             // grid barrier word of the visit kernel
     double* d_cta_min = nullptr;               // [num_sms] per-CTA minima, [num_sms * 5] per-CTA RMS sums
     double* d_cta_rms = nullptr;
+    int gmin_level = -1;                       // multi-GPU: level whose global minimum dt (of its CURRENT state) is in d_minbits, or -1
     std::map<std::string, long> graph_launches;
     std::map<std::string, std::string> graph_flags_end;
     long long* d_visit_dbg = nullptr;          // MGCFD_VISIT_DEBUG=1: clock stamps of the last visit-kernel launch (64 per CTA)
@@ -282,6 +287,7 @@ bool dist_inkernel(mgcfd_ctx* c) { return c->dist.active && c->dist.p2p; }
 // global minimum of the per-rank min-dt bit patterns (positive doubles order like their bits)
 int p2p_allreduce(mgcfd_ctx* c, double* vals, int n, int is_min) {
     Dist& d = c->dist;
+    c->gmin_level = -1;       // the epoch moves on: a minimum a transfer kernel has tagged with its own epoch can no longer be picked up
     k_p2p_allreduce<<<1, 64, 0, c->stream>>>(vals, n, is_min, d.nranks, d.rank, d.d_red_of_rank, d.d_flag_of_rank, (const unsigned long long*)d.win,
                                               (const double*)(d.win + P2P_FLAGS_BYTES), d.d_op, d.d_ctr);
     return post_launch(c);
@@ -306,6 +312,7 @@ int p2p_exchange(mgcfd_ctx* c, int l, const double* src, double* dst) {
     Dist& d = c->dist;
     Level& v = c->L[l];
     const double* stage = (const double*)(d.win + P2P_HDR_BYTES) + d.stage_off[l];
+    c->gmin_level = -1;
     const long work = std::max(v.nsend, v.nghost) * WIDTH;
     const unsigned grid = (unsigned)std::max<long>(1, std::min<long>(blocks_for(work, 256), 2L * c->num_sms));   // resident at once
     k_p2p_exchange<WIDTH, SOA><<<grid, 256, 0, c->stream>>>(src, v.npad, v.d_send_idx, v.d_peers, v.npeers, d.d_op, d.d_ctr + 1 + l, d.d_ticket,
@@ -359,11 +366,11 @@ int launch_stage_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     k_stage<TN, SCATTER, FUSED><<<(unsigned)v.ntiles, TN, v.smem_bytes, c->stream>>>(a);
     return post_launch(c);
 }
-template <int TN, bool SCATTER>
+template <int TN, bool SCATTER, bool DIST = false>
 int launch_pipe_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
-    const int grid = v.pipe_grid;
+    const int grid = DIST ? v.pipe_grid_dist : v.pipe_grid;
     if (c->opt.no_pdl) {
-        k_stage_pipe<TN, SCATTER><<<(unsigned)grid, TN, v.pipe_smem, c->stream>>>(a);
+        k_stage_pipe<TN, SCATTER, DIST><<<(unsigned)grid, TN, v.pipe_smem, c->stream>>>(a);
         return post_launch(c);
     }
     // programmatic dependent launch: this kernel may start (barrier set-up, header + edge-stream prefetch: static data) while
@@ -375,8 +382,28 @@ int launch_pipe_t(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    CK(cudaLaunchKernelEx(&cfg, k_stage_pipe<TN, SCATTER>, a));
+    CK(cudaLaunchKernelEx(&cfg, k_stage_pipe<TN, SCATTER, DIST>, a));
     return post_launch(c);
+}
+// in-kernel delivery: occupancy and shared-memory attribute of the DIST instantiation (its register count differs)
+template <int TN, bool SCATTER>
+int setup_pipe_dist_t(mgcfd_ctx* c, Level& v) {
+    static size_t attr_bytes = 0;       // per instantiation: the attribute only ever grows (levels differ in shared memory)
+    if (v.pipe_smem > attr_bytes) {
+        CK(cudaFuncSetAttribute(k_stage_pipe<TN, SCATTER, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.pipe_smem));
+        attr_bytes = v.pipe_smem;
+    }
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_stage_pipe<TN, SCATTER, true>, TN, v.pipe_smem));
+    if (per_sm < 1) { v.pipe_grid_dist = 0; return MGCFD_OK; }
+    v.pipe_grid_dist = (int)std::min<long>(v.ntiles, (long)per_sm * c->num_sms);
+    return MGCFD_OK;
+}
+int setup_pipe_dist(mgcfd_ctx* c, Level& v) {
+    const bool sc = v.plan.scatter;
+    if (v.TN == 128) return sc ? setup_pipe_dist_t<128, true>(c, v) : setup_pipe_dist_t<128, false>(c, v);
+    if (v.TN == 256) return sc ? setup_pipe_dist_t<256, true>(c, v) : setup_pipe_dist_t<256, false>(c, v);
+    return sc ? setup_pipe_dist_t<512, true>(c, v) : setup_pipe_dist_t<512, false>(c, v);
 }
 // persistent grid of the pipelined kernel: as many CTAs as fit on the device at once (occupancy API), never more than tiles
 template <int TN, bool SCATTER>
@@ -416,6 +443,13 @@ int launch_stage(mgcfd_ctx* c, Level& v, const StageArgs& a, bool fused) {
                                : (fused ? launch_stage_t<256, false, true>(c, v, a) : launch_stage_t<256, false, false>(c, v, a));
     return sc ? (fused ? launch_stage_t<512, true, true>(c, v, a) : launch_stage_t<512, true, false>(c, v, a))
               : (fused ? launch_stage_t<512, false, true>(c, v, a) : launch_stage_t<512, false, false>(c, v, a));
+}
+
+int launch_stage_dist(mgcfd_ctx* c, Level& v, const StageArgs& a) {
+    const bool sc = v.plan.scatter;
+    if (v.TN == 128) return sc ? launch_pipe_t<128, true, true>(c, v, a) : launch_pipe_t<128, false, true>(c, v, a);
+    if (v.TN == 256) return sc ? launch_pipe_t<256, true, true>(c, v, a) : launch_pipe_t<256, false, true>(c, v, a);
+    return sc ? launch_pipe_t<512, true, true>(c, v, a) : launch_pipe_t<512, false, true>(c, v, a);
 }
 
 StageArgs base_args(mgcfd_ctx* c, Level& v) {
@@ -494,6 +528,7 @@ int launch_flux_variant(mgcfd_ctx* c, Level& v, int bits) {
 
 int step_factor(mgcfd_ctx* c, int l, int legacy) {
     Level& v = c->L[l];
+    c->gmin_level = -1;
     Timed tm(c, K_STEP, l, v.nel);
     const unsigned nb = (unsigned)blocks_for(v.ncomp, 256);
     if (legacy) {
@@ -544,27 +579,38 @@ int min_dt_fused(mgcfd_ctx* c, int l) {
 
 // the whole visit as ONE persistent kernel (visit_kernel.cuh): minimum dt, three stages, residual, RMS sums; multi-GPU: the halo
 // exchange rides on its grid barriers
+AllRed allred_of(mgcfd_ctx* c) {
+    AllRed ar;
+    Dist& d = c->dist;
+    ar.nranks = d.nranks; ar.me = d.rank; ar.red_of_rank = d.d_red_of_rank; ar.flag_of_rank = d.d_flag_of_rank;
+    ar.my_flags = (const unsigned long long*)d.win; ar.my_red = (const double*)(d.win + P2P_FLAGS_BYTES); ar.red_counter = d.d_ctr;
+    return ar;
+}
 DistArgs dist_args(mgcfd_ctx* c, Level& v, const P2PPeer* wait_peers, int nwait) {
     DistArgs da;
     memset(&da, 0, sizeof(da));
     Dist& d = c->dist;
-    da.nranks = d.nranks; da.me = d.rank;
     da.peers = v.d_peers; da.npeers = v.npeers; da.peer_out = v.d_peer_out;
     da.tgt_off = v.d_tgt_off; da.tgt_peer = v.d_tgt_peer; da.tgt_row = v.d_tgt_row; da.tile_sends = v.d_tile_sends;
     da.wait_peers = wait_peers; da.nwait = nwait;
-    da.red_of_rank = d.d_red_of_rank; da.flag_of_rank = d.d_flag_of_rank;
-    da.my_flags = (const unsigned long long*)d.win; da.my_red = (const double*)(d.win + P2P_FLAGS_BYTES);
-    da.op_counter = d.d_op; da.red_counter = d.d_ctr;
+    da.ar = allred_of(c);
+    da.my_flags = (const unsigned long long*)d.win;
+    da.op_counter = d.d_op;
     return da;
 }
-DistTail dist_tail(mgcfd_ctx* c, Level& out_level, int ib, const P2PPeer* wait_peers, int nwait) {
+// `transfer`: the kernel works in 128-row blocks (restrict / prolong), else in the level's tiles (stage kernels)
+DistTail dist_tail(mgcfd_ctx* c, Level& out_level, int ib, const P2PPeer* wait_peers, int nwait, bool transfer) {
     DistTail t;
     memset(&t, 0, sizeof(t));
     Dist& d = c->dist;
     t.wait_peers = wait_peers; t.nwait = nwait;
     t.peers = out_level.d_peers; t.npeers = out_level.npeers; t.peer_out = out_level.d_peer_out; t.ib = ib;
-    t.tgt_off = out_level.d_tgt_off; t.tgt_peer = out_level.d_tgt_peer; t.tgt_row = out_level.d_tgt_row;
-    t.op_counter = d.d_op; t.ticket = d.d_ticket; t.my_flags = (const unsigned long long*)d.win;
+    t.tgt_off = out_level.d_tgt_off; t.tgt_peer = out_level.d_tgt_peer; t.tgt_row = out_level.d_tgt_row; t.tile_sends = out_level.d_tile_sends;
+    t.order = transfer ? out_level.d_order_blk : out_level.d_order_tiles;
+    t.n_send = transfer ? out_level.n_send_blk : out_level.n_send_tiles;
+    t.op_counter = d.d_op; t.ticket = d.d_ticket; t.send_ticket = d.d_send_ticket; t.my_flags = (const unsigned long long*)d.win;
+    t.ar = allred_of(c);
+    t.dbg = env_int("MGCFD_DIST_DEBUG", 0);
     return t;
 }
 
@@ -576,11 +622,13 @@ int smooth_visit(mgcfd_ctx* c, int l) {
     memset(&a, 0, sizeof(a));
     a.bufX = v.V(X); a.bufA = v.V(A); a.bufB = v.V(B); a.ibX = X; a.ibA = A; a.ibB = B;
     a.res = v.res; a.sf = v.sf; a.vol = v.vol; a.vol_root = v.vol_root; a.stride = v.npad;
+    a.hsum = v.d_hsum; a.hs_stride = v.ncomp;
     a.legacy = (c->variant == MGCFD_MESH_FVCORR);
     a.desc = v.d_desc; a.desc_stride = v.plan.visit.desc_stride; a.max_ent = v.plan.visit.max_ent; a.hpad = v.plan.visit.hpad;
     a.vslots = v.d_vslots; a.bslots = v.bslots; a.cta_rows = v.d_cta_rows;
-    a.K = v.vK; a.sr_max = v.v_srmax; a.resident = v.v_resident; a.R = v.vR; a.D = v.vD;
-    if (v.premin_valid) { a.premin = v.blockmins; a.npremin = (int)blocks_for(v.ncomp, 128); }
+    a.K = v.vK; a.sr_max = v.v_srmax; a.resident = v.v_resident; a.max_chunk = v.plan.visit.max_chunk;
+    if (!c->dist.active && v.premin_valid) { a.premin = v.blockmins; a.npremin = (int)blocks_for(v.ncomp, 128); }
+    if (c->gmin_level == l) c->gmin_level = -1;
     a.k2 = 2.0 * c->kdiss;
     a.bad_key = c->d_badkey; a.old_of_new = v.old_of_new;
     a.stage_seq0 = c->stage_seq & 0xFFFFFFull; c->stage_seq += MGCFD_RK;
@@ -593,26 +641,50 @@ int smooth_visit(mgcfd_ctx* c, int l) {
     if (dist) a.d = dist_args(c, v, v.d_peers, v.npeers);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)v.vG); cfg.blockDim = dim3(VNT); cfg.dynamicSmemBytes = v.v_smem; cfg.stream = c->stream;
+    cfg.gridDim = dim3((unsigned)v.vG); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = v.v_smem; cfg.stream = c->stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = c->opt.no_pdl ? 0 : 1;
-    if (c->d_visit_dbg && !dist) {
-        a.dbg = c->d_visit_dbg;
-        CK(cudaLaunchKernelEx(&cfg, k_visit<false, true>, a));
-    } else if (dist) CK(cudaLaunchKernelEx(&cfg, k_visit<true>, a)); else CK(cudaLaunchKernelEx(&cfg, k_visit<false>, a));
+    // instantiations: warps per CTA (16: one CTA per SM, 8: two), multi-GPU delivery, debug stamps
+    const bool dbg = c->d_visit_dbg && !dist;
+    if (dbg) a.dbg = c->d_visit_dbg;
+    cfg.blockDim = dim3(32 * v.vW);
+    if (v.vW == 8) {
+        if (dbg) CK(cudaLaunchKernelEx(&cfg, k_visit<false, true, 2, 8>, a));
+        else if (dist) CK(cudaLaunchKernelEx(&cfg, k_visit<true, false, 2, 8>, a));
+        else CK(cudaLaunchKernelEx(&cfg, k_visit<false, false, 2, 8>, a));
+    } else {
+        if (dbg) CK(cudaLaunchKernelEx(&cfg, k_visit<false, true, 2, 16>, a));
+        else if (dist) CK(cudaLaunchKernelEx(&cfg, k_visit<true, false, 2, 16>, a));
+        else CK(cudaLaunchKernelEx(&cfg, k_visit<false, false, 2, 16>, a));
+    }
     CKRC(post_launch(c));
     if (dist) c->dist.exchanges += MGCFD_RK;
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     v.premin_valid = false;
+    if (c->gmin_level == l) c->gmin_level = -1;
     return MGCFD_OK;
 }
+
+int launch_stage_dist(mgcfd_ctx* c, Level& v, const StageArgs& a);
 
 int smooth_fused(mgcfd_ctx* c, int l) {
     Level& v = c->L[l];
     if (v.visit && (!c->dist.active || c->dist.p2p)) return smooth_visit(c, l);
-    CKRC(min_dt_fused(c, l));
+    const bool legacy = (c->variant == MGCFD_MESH_FVCORR);
+    // multi-GPU, peer-to-peer plane, pipelined stage kernel: the stage kernels deliver their rows themselves (start-wait on the
+    // level's peers, remote stores from the update, end signal): no exchange kernel between the stages
+    const bool deliver = dist_inkernel(c) && v.pipe;
+    // the visit's minimum dt: already all-reduced by the transfer kernel that produced this state (multi-GPU), or reduced by every
+    // CTA of the first stage from the per-block minima that kernel left behind (one GPU), or -- the state came from elsewhere --
+    // by k_min_dt (+ all-reduce)
+    bool use_premin = false, recv_min = false;
+    if (!legacy) {
+        if (c->dist.active) { if (deliver && c->gmin_level == l) recv_min = true; else CKRC(min_dt_fused(c, l)); }
+        else if (v.premin_valid && v.pipe) use_premin = true;      // (the simple one-CTA-per-tile kernel reads *min_bits only)
+        else CKRC(min_dt_fused(c, l));
+    } else if (!deliver) CKRC(min_dt_fused(c, l));
     const int X = v.i_var, A = v.i_tmp, B = v.i_old;   // the previous old_variables are dead once a smooth starts
     // timing: on one GPU the three stage launches of the visit share ONE event bracket (3 * nI edge updates), so that they run as
     // in the replayed graph -- back to back, with their programmatic-dependent-launch overlap -- instead of each paying an event
@@ -634,6 +706,15 @@ int smooth_fused(mgcfd_ctx* c, int l) {
             a.res = v.res;
             a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
         }
+        if (j == 0 && use_premin) { a.premin = v.blockmins; a.npremin = (int)blocks_for(v.ncomp, 128); }
+        if (deliver) {
+            const int ib = (a.vout == v.buf[0]) ? 0 : (a.vout == v.buf[1] ? 1 : 2);
+            a.d = dist_tail(c, v, ib, v.d_peers, v.npeers, false);
+            a.d.recv_min = (j == 0 && recv_min) ? 1 : 0;
+            CKRC(launch_stage_dist(c, v, a));
+            c->dist.exchanges++;
+            continue;
+        }
         CKRC(launch_stage(c, v, a, true));
         stage_tm.reset();
         CKRC(dist_exchange_records(c, l, a.vout));
@@ -641,6 +722,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     visit_tm.reset();
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     v.premin_valid = false;
+    if (c->gmin_level == l) c->gmin_level = -1;
     if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
     return MGCFD_OK;
 }
@@ -649,14 +731,18 @@ int do_restrict(mgcfd_ctx* c, int lc) {
     Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
     Timed tm(c, K_RESTRICT, lc, vf.nel);
     const unsigned nb = (unsigned)blocks_for(vc.ncomp, 128);
-    // a level that runs the visit kernel gets the per-block minima of dt of its new state (never for the legacy step factor)
-    double* bm = (vc.visit && c->variant != MGCFD_MESH_FVCORR && env_int("MGCFD_PREMIN", 1)) ? vc.blockmins : nullptr;
+    // the per-block minima of dt of the new state (never for the legacy step factor): the next smoothing visit of the level needs
+    // their minimum; multi-GPU the kernel's last CTA all-reduces it over the ranks into d_minbits
+    double* bm = (c->variant != MGCFD_MESH_FVCORR && env_int("MGCFD_PREMIN", 1)) ? vc.blockmins : nullptr;
     if (dist_inkernel(c)) {
         // reads the fine level's ghost rows (wait for the fine level's peers), delivers the coarse rows itself
-        const DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers);
+        DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers, true);
+        if (vc.visit || !vc.pipe) bm = nullptr;             // only a level whose stage kernels deliver their rows themselves picks the minimum up
+        if (bm) { t.blockmins = bm; t.nblocks = (int)nb; t.send_min = 1; }
         k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, t);
         c->dist.exchanges++;
-        vc.premin_valid = (bm != nullptr);
+        vc.premin_valid = false;
+        c->gmin_level = bm ? lc : -1;
         return post_launch(c);
     }
     DistTail none;
@@ -670,16 +756,19 @@ int do_prolong(mgcfd_ctx* c, int lf) {
     Level& vf = c->L[lf]; Level& vc = c->L[lf + 1];
     Timed tm(c, K_PROLONG, lf, vf.nI);
     const unsigned nb = (unsigned)blocks_for(vf.ncomp, 128);
-    double* bm = (vf.visit && c->variant != MGCFD_MESH_FVCORR && env_int("MGCFD_PREMIN", 1)) ? vf.blockmins : nullptr;
+    double* bm = (c->variant != MGCFD_MESH_FVCORR && env_int("MGCFD_PREMIN", 1)) ? vf.blockmins : nullptr;
     if (dist_inkernel(c)) {
         // the coarse residuals of ghost parents were delivered by the coarse visit's last stage when that level runs the visit
         // kernel; otherwise they are exchanged here.  The prolonged rows are delivered by the kernel itself.
-        if (!vc.visit) CKRC(dist_exchange_residuals(c, lf + 1));
-        const DistTail t = dist_tail(c, vf, vf.i_var, vc.d_peers, vc.npeers);
+        if (!vc.visit && !vc.pipe) CKRC(dist_exchange_residuals(c, lf + 1));
+        DistTail t = dist_tail(c, vf, vf.i_var, vc.d_peers, vc.npeers, true);
+        if (vf.visit || !vf.pipe) bm = nullptr;
+        if (bm) { t.blockmins = bm; t.nblocks = (int)nb; t.send_min = 1; }
         k_prolong<true><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
                                                    vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, bm, t);
         c->dist.exchanges++;
-        vf.premin_valid = (bm != nullptr);
+        vf.premin_valid = false;
+        c->gmin_level = bm ? lf : -1;
         return post_launch(c);
     }
     CKRC(dist_exchange_residuals(c, lf + 1));
@@ -706,7 +795,8 @@ int cycle_fused(mgcfd_ctx* c) {
 std::string role_key(mgcfd_ctx* c) {
     std::string k;
     for (auto& v : c->L) { k += char('0' + v.i_var); k += char('0' + v.i_old); }
-    for (auto& v : c->L) k += v.premin_valid ? 'v' : '-';      // a captured visit kernel has the source of its minimum dt baked in
+    for (auto& v : c->L) k += v.premin_valid ? 'v' : '-';      // a captured kernel has the source of its minimum dt baked in
+    k += char('0' + (c->gmin_level + 1));
     return k;
 }
 
@@ -737,14 +827,17 @@ void free_level(Level& v) {
     void* ptrs[] = {v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
                     v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers,
-                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_out, v.ewt_pre, v.d_desc, v.d_vslots, v.d_cta_rows};
+                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_out, v.ewt_pre, v.d_desc, v.d_vslots, v.d_cta_rows, v.d_hsum,
+                    v.d_order_tiles, v.d_order_blk};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
 
 // ---- the visit kernel's configuration of a level (visit_kernel.cuh) ------------------------------------------------------------
-struct VisitCfg { bool ok = false; bool roomy = false; int K = 1, G = 0, R = 1, D = 2, resident = 0, sr_max = 0; size_t smem = 0; };
-constexpr size_t VISIT_SMEM_LIMIT = 230000;      // 227 KB per CTA minus the kernel's static shared memory
+struct VisitCfg { bool ok = false; bool roomy = false; int K = 1, G = 0, R = 1, D = 2, W = 16, resident = 0, sr_max = 0; size_t smem = 0; };
+// dynamic shared memory a CTA may use: one CTA per SM (16 warps) 227 KB minus the kernel's static shared memory; two CTAs per SM
+// (8 warps each) half of the SM's 228 KB minus the 1 KB the system reserves per CTA and the static part
+inline size_t visit_smem_limit(int warps) { return warps == 8 ? 114000 : 230000; }
 // shared memory of k_visit for a plan built with G * K super-tiles: 16 per-warp rings (D entries x R rounds x 832 bytes) + record
 // buffers (resident: two own-row buffers + one halo buffer; streaming: two buffers of own + halo rows) + descriptor buffers (one
 // when K == 1, else four).  Ring shapes are tried from the roomiest down; `roomy` = at least four rounds buffered per warp.
@@ -755,16 +848,13 @@ VisitCfg visit_config(const LevelPlan& P, int G, int K) {
     const size_t own = 64 * (size_t)VT * V.maxt, halo = 64 * (size_t)V.hpad, desc = (K == 1 ? 1 : 4) * (size_t)V.desc_stride;
     const bool resident = (K == 1) && env_int("MGCFD_VISIT_RESIDENT", 1) != 0;
     const size_t recs = resident ? 2 * own + halo : 2 * (own + halo);
-    const int forceR = env_int("MGCFD_VISIT_R", 0), forceD = env_int("MGCFD_VISIT_D", 0);
-    const int shapes[5][2] = {{3, 2}, {2, 2}, {4, 1}, {3, 1}, {2, 1}};       // {D, R}
-    for (const auto& sh : shapes) {
-        int D = forceD > 0 ? std::min(forceD, VRING_MAX) : sh[0], R = forceR > 0 ? forceR : sh[1];
-        R = std::max(1, std::min(R, std::max(1, V.max_rounds)));
-        const size_t ring = (((size_t)VNW * D * R * VW * 26) + 127) & ~size_t(127);
-        if (ring + recs + desc > VISIT_SMEM_LIMIT) { if (forceD > 0 && forceR > 0) break; continue; }
-        cfg.ok = true; cfg.roomy = D * R >= 4 || R >= V.max_rounds; cfg.K = K; cfg.G = G; cfg.R = R; cfg.D = D; cfg.resident = resident ? 1 : 0;
+    const int R = V.rounds_per_chunk;                     // the descriptors' chunk lists are built for it (PlanOptions::visit_rounds)
+    const int D = 2;
+    const int W = V.warps;
+    const size_t ring = (((size_t)W * D * R * VW * VSLOT) + 127) & ~size_t(127);
+    if (R == 2 && ring + recs + desc <= visit_smem_limit(W)) {
+        cfg.ok = true; cfg.roomy = true; cfg.K = K; cfg.G = G; cfg.R = R; cfg.D = D; cfg.W = W; cfg.resident = resident ? 1 : 0;
         cfg.sr_max = VT * V.maxt; cfg.smem = ring + recs + desc;
-        break;
     }
     return cfg;
 }
@@ -774,8 +864,11 @@ VisitCfg visit_config(const LevelPlan& P, int G, int K) {
 bool plan_for_visit(int num_sms, LevelPlan& plan_out, const HostLevel& H, PlanOptions po, VisitCfg& out) {
     const long n_own = H.n_owned >= 0 ? H.n_owned : H.nel;
     const long ntiles = std::max<long>(1, (n_own + VT - 1) / VT);
-    const int G = (int)std::min<long>(num_sms, ntiles);
+    po.visit_warps = (env_int("MGCFD_VISIT_WARPS", 16) == 8) ? 8 : 16;
+    const size_t VISIT_SMEM_LIMIT = visit_smem_limit(po.visit_warps);
+    const int G = (int)std::min<long>((long)num_sms * (16 / po.visit_warps), ntiles);
     po.tile_nodes = VT;
+    po.visit_rounds = 2;
     const int forceK = env_int("MGCFD_VISIT_K", 0);
     auto good = [&](const VisitCfg& f, const LevelPlan&) { return f.ok && f.roomy; };
     VisitCfg best; LevelPlan bestP;
@@ -797,7 +890,7 @@ bool plan_for_visit(int num_sms, LevelPlan& plan_out, const HostLevel& H, PlanOp
             int k = 2;
             for (; k < 64; k++) {
                 const double rows = std::ceil(own1 / k / VT) * VT + h1 * std::pow((double)k, -2.0 / 3.0);
-                if (2 * 64 * rows + (double)VNW * 4 * VW * 26 + 4 * (128.0 * std::ceil(own1 / k / VT) + 4 * h1 * std::pow((double)k, -2.0 / 3.0) + 32) <= (double)VISIT_SMEM_LIMIT) break;
+                if (2 * 64 * rows + (double)po.visit_warps * 4 * VW * VSLOT + 4 * (128.0 * std::ceil(own1 / k / VT) + 4 * h1 * std::pow((double)k, -2.0 / 3.0) + 32) <= (double)VISIT_SMEM_LIMIT) break;
             }
             K = k;
         } else K++;
@@ -880,9 +973,9 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     CK(cudaMalloc((void**)&c->d_rms_sums, sizeof(double) * 8));
     CK(cudaMemset(c->d_rms_sums, 0, sizeof(double) * 8));
     CK(cudaMalloc((void**)&c->d_bar, sizeof(unsigned int))); CK(cudaMemset(c->d_bar, 0, sizeof(unsigned int)));
-    CK(cudaMalloc((void**)&c->d_cta_min, sizeof(double) * c->num_sms));
-    CK(cudaMalloc((void**)&c->d_cta_rms, sizeof(double) * 5 * c->num_sms));
-    if (env_int("MGCFD_VISIT_DEBUG", 0)) { CK(cudaMalloc((void**)&c->d_visit_dbg, sizeof(long long) * 64 * c->num_sms)); CK(cudaMemset(c->d_visit_dbg, 0, sizeof(long long) * 64 * c->num_sms)); }
+    CK(cudaMalloc((void**)&c->d_cta_min, sizeof(double) * 2 * c->num_sms));
+    CK(cudaMalloc((void**)&c->d_cta_rms, sizeof(double) * 5 * 2 * c->num_sms));
+    if (env_int("MGCFD_VISIT_DEBUG", 0)) { CK(cudaMalloc((void**)&c->d_visit_dbg, sizeof(long long) * 64 * 2 * c->num_sms)); CK(cudaMemset(c->d_visit_dbg, 0, sizeof(long long) * 64 * 2 * c->num_sms)); }
     CK(cudaMalloc((void**)&c->d_rms_counter, sizeof(int)));
     CK(cudaMemset(c->d_rms_counter, 0, sizeof(int)));
     mgcfd_far_field_conditions(c->ff, c->ffc);
@@ -902,7 +995,7 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
     for (int p = 0; p < (int)c->dist.peer_win.size(); p++) if (p != c->dist.rank && c->dist.peer_win[p]) cudaIpcCloseMemHandle(c->dist.peer_win[p]);
     cudaFree(c->d_visit_dbg); cudaFree(c->slab); cudaFree(c->d_bar); cudaFree(c->d_cta_min); cudaFree(c->d_cta_rms);
-    cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
+    cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_send_ticket); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -942,17 +1035,17 @@ int mgcfd_upload_level(mgcfd_ctx* c, int l, long nel, const double* volumes, con
     PlanOptions po; po.ordering = c->opt.ordering; po.scatter = (c->opt.flux_mode == MGCFD_FLUX_TILED_COLOURED);
     po.strict = (c->opt.flux_mode != MGCFD_FLUX_ATOMIC);     // the atomic baseline runs on any numbering, tiled or not
     po.tile_nodes = c->opt.tile_nodes ? c->opt.tile_nodes : auto_tile_nodes(H.n_owned >= 0 ? H.n_owned : nel, nI, c->num_sms);
-    // levels up to ~1 M nodes run the persistent visit kernel (one launch per smoothing visit, visit_kernel.cuh): sorted-segment
-    // mode, the partitioning order, 128-node tiles grouped into super-tiles; larger levels stream through the stage kernels
+    // on request (mgcfd_options::visit, MGCFD_VISIT=1) levels up to ~1.2 M nodes run the persistent visit kernel (one launch per
+    // smoothing visit, visit_kernel.cuh): sorted-segment mode, the partitioning order, 128-node tiles grouped into super-tiles
     v.visit = false;
     const long n_own = H.n_owned >= 0 ? H.n_owned : nel;
-    const bool want_visit = !c->opt.no_visit && env_int("MGCFD_VISIT", 1) != 0 && c->opt.flux_mode == MGCFD_FLUX_SORTED_SEGMENT &&
+    const bool want_visit = env_int("MGCFD_VISIT", c->opt.visit) != 0 && c->opt.flux_mode == MGCFD_FLUX_SORTED_SEGMENT &&
                             c->opt.ordering == MGCFD_ORDER_PARTITION_RCM && (c->opt.tile_nodes == 0 || c->opt.tile_nodes == VT) &&
                             !c->opt.no_pipeline && n_own <= (long)env_int("MGCFD_VISIT_MAX_NODES", 1200000);
     try {
         VisitCfg cfg;
         if (want_visit && plan_for_visit(c->num_sms, v.plan, H, po, cfg)) {
-            v.visit = true; v.vK = cfg.K; v.vG = cfg.G; v.vR = cfg.R; v.vD = cfg.D; v.v_resident = cfg.resident; v.v_srmax = cfg.sr_max; v.v_smem = cfg.smem;
+            v.visit = true; v.vK = cfg.K; v.vG = cfg.G; v.vR = cfg.R; v.vD = cfg.D; v.vW = cfg.W; v.v_resident = cfg.resident; v.v_srmax = cfg.sr_max; v.v_smem = cfg.smem;
         } else build_level_plan(H, po, v.plan);
     }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
@@ -1032,20 +1125,29 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         if (v.visit) {
             // the visit kernel's streams; its grid must be co-resident (one CTA per SM)
             const VisitPlan& V = P.visit;
-            CKRC(dev_upload(&v.d_desc, V.desc, s)); CKRC(dev_upload(&v.d_vslots, V.vslots, s));
+            CKRC(dev_upload(&v.d_desc, V.desc, s)); CKRC(dev_upload(&v.d_vslots, V.vslots, s)); CKRC(dev_upload(&v.d_hsum, V.hsum, s));
             std::vector<int> rows(v.vG + 1);
             for (int g = 0; g <= v.vG; g++) rows[g] = int(V.super_off[(size_t)std::min<long>((long)g * v.vK, V.ns)] * VT);
             CKRC(dev_upload(&v.d_cta_rows, rows, s));
-            static size_t attr_bytes = 0;
-            if (v.v_smem > attr_bytes) {
-                CK(cudaFuncSetAttribute(k_visit<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
-                CK(cudaFuncSetAttribute(k_visit<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
-                CK(cudaFuncSetAttribute(k_visit<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.v_smem));
-                attr_bytes = v.v_smem;
+            static size_t attr_bytes[2] = {0, 0};
+            const int wi = (v.vW == 8) ? 1 : 0;
+            if (v.v_smem > attr_bytes[wi]) {
+                const int sm = (int)v.v_smem;
+                if (wi) {
+                    CK(cudaFuncSetAttribute(k_visit<false, false, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                    CK(cudaFuncSetAttribute(k_visit<true, false, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                    CK(cudaFuncSetAttribute(k_visit<false, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                } else {
+                    CK(cudaFuncSetAttribute(k_visit<false, false, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                    CK(cudaFuncSetAttribute(k_visit<true, false, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                    CK(cudaFuncSetAttribute(k_visit<false, true, 2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+                }
+                attr_bytes[wi] = v.v_smem;
             }
             int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_visit<true>, VNT, v.v_smem));
-            if (per_sm < 1 || v.vG > c->num_sms) { g_err = "the visit kernel does not fit an SM with this level's configuration"; return MGCFD_ERR_ARG; }
+            if (wi) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_visit<true, false, 2, 8>, 256, v.v_smem));
+            else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_visit<true, false, 2, 16>, 512, v.v_smem));
+            if (per_sm < 16 / v.vW || v.vG > per_sm * c->num_sms) { g_err = "the visit kernel does not fit an SM with this level's configuration"; return MGCFD_ERR_ARG; }
         }
         if (v.nel_global == 0) v.nel_global = v.nel;
         v.n_owned = P.n_owned;
@@ -1087,6 +1189,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
     for (auto& v : c->L) {
         v.host = HostLevel();
         v.plan.visit.vslots.clear(); v.plan.visit.vslots.shrink_to_fit();
+        v.plan.visit.hsum.clear(); v.plan.visit.hsum.shrink_to_fit();
         if (v.npad > 2000000) {   // big levels: drop the host copy of the edge stream (introspection needs it only on small meshes)
             v.plan.slots.clear(); v.plan.slots.shrink_to_fit();
             v.plan.bslots.clear(); v.plan.bslots.shrink_to_fit();
@@ -1101,6 +1204,7 @@ int mgcfd_initialize_variables(mgcfd_ctx* c, int l) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
     v.premin_valid = false;
+    if (c->gmin_level == l) c->gmin_level = -1;
     k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad);
     return post_launch(c);
 }
@@ -1127,6 +1231,7 @@ int mgcfd_time_step(mgcfd_ctx* c, int l, int j) {
     Level& v = c->L[l];
     CKRC(ensure_flux(c, v));
     v.premin_valid = false;
+    if (c->gmin_level == l) c->gmin_level = -1;
     Timed tm(c, K_TIME, l, v.nel);
     k_time_step<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(double(MGCFD_RK + 1 - j), v.ncomp, v.npad, v.sf, v.flux, v.V(v.i_old), v.V(v.i_var));
     return post_launch(c);
@@ -1171,6 +1276,7 @@ int mgcfd_check_for_invalid_variables(mgcfd_ctx* c, int l, long* first_bad_cell,
     CKRC(check_level(c, l));
     Level& v = c->L[l];
     unsigned long long* key = c->d_minbits;   // scratch word; the step-factor kernel re-initialises it before use
+    c->gmin_level = -1;
     CK(cudaMemsetAsync(key, 0xFF, 8, c->stream));
     k_check_invalid<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.old_of_new, key);
     CKRC(post_launch(c));
@@ -1215,6 +1321,7 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
         c->capturing = true;
         std::vector<char> flags0;
         for (auto& v : c->L) flags0.push_back(v.premin_valid);
+        const int gmin0 = c->gmin_level;
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         int rc = cycle_fused(c);
         cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
@@ -1223,6 +1330,8 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
         {   // what the cycle leaves behind of the minimum-dt bookkeeping; rolled back like the buffer roles, re-applied by every replay
             std::string end;
             for (size_t l = 0; l < c->L.size(); l++) { end += c->L[l].premin_valid ? 'v' : '-'; c->L[l].premin_valid = flags0[l] != 0; }
+            end += char('0' + (c->gmin_level + 1));
+            c->gmin_level = gmin0;
             c->graph_flags_end[key] = end;
         }
         c->launches = launches_before;        // capture recorded the launches, it did not run them
@@ -1239,7 +1348,11 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
     CK(cudaGraphLaunch(it->second, c->stream));
     advance_roles_one_cycle(c);
     c->launches += c->graph_launches[key];
-    { const std::string& end = c->graph_flags_end[key]; for (size_t l = 0; l < c->L.size() && l < end.size(); l++) c->L[l].premin_valid = (end[l] == 'v'); }
+    {
+        const std::string& end = c->graph_flags_end[key];
+        for (size_t l = 0; l < c->L.size() && l < end.size(); l++) c->L[l].premin_valid = (end[l] == 'v');
+        if (end.size() > c->L.size()) c->gmin_level = int(end[c->L.size()] - '0') - 1;
+    }
     return MGCFD_OK;
 }
 }  // namespace
@@ -1333,6 +1446,7 @@ int mgcfd_set_field(mgcfd_ctx* c, int l, int field, const double* host_in) {
     if (!host_in) { g_err = "null buffer"; return MGCFD_ERR_ARG; }
     Level& v = c->L[l];
     v.premin_valid = false;
+    if (c->gmin_level == l) c->gmin_level = -1;
     double* p; int nc;
     CKRC(field_ptr(c, v, field, &p, &nc, true));
     if (!v.io) CK(cudaMalloc((void**)&v.io, sizeof(double) * 5 * v.nel));
@@ -1374,7 +1488,7 @@ int mgcfd_visit_info(mgcfd_ctx* c, int l, long info[8]) {
     memset(info, 0, sizeof(long) * 8);
     info[0] = v.visit ? 1 : 0;
     if (v.visit) {
-        info[1] = v.vK; info[2] = v.vG; info[3] = v.vR | (v.vD << 8); info[4] = v.v_resident; info[5] = v.v_srmax; info[6] = (long)v.v_smem;
+        info[1] = v.vK; info[2] = v.vG; info[3] = v.vR | (v.vD << 8) | (v.vW << 16); info[4] = v.v_resident; info[5] = v.v_srmax; info[6] = (long)v.v_smem;
         info[7] = v.plan.visit.halo_total;
     }
     return MGCFD_OK;
@@ -1383,10 +1497,10 @@ int mgcfd_visit_info(mgcfd_ctx* c, int l, long info[8]) {
 int mgcfd_visit_debug(mgcfd_ctx* c, long long* out, long cap) {
     if (!c || !out) { g_err = "null argument"; return MGCFD_ERR_ARG; }
     if (!c->d_visit_dbg) { g_err = "MGCFD_VISIT_DEBUG was not set when the context was created"; return MGCFD_ERR_ARG; }
-    if (cap < 64L * c->num_sms) { g_err = "buffer too small"; return MGCFD_ERR_ARG; }
+    if (cap < 128L * c->num_sms) { g_err = "buffer too small"; return MGCFD_ERR_ARG; }
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaMemcpy(out, c->d_visit_dbg, sizeof(long long) * 64 * c->num_sms, cudaMemcpyDeviceToHost));
-    return c->num_sms;
+    CK(cudaMemcpy(out, c->d_visit_dbg, sizeof(long long) * 128 * c->num_sms, cudaMemcpyDeviceToHost));
+    return 2 * c->num_sms;
 }
 long mgcfd_check_colouring(mgcfd_ctx* c, int l) {
     if (check_level(c, l, false) != MGCFD_OK) return -1;
@@ -1538,7 +1652,7 @@ int mgcfd_plan_visit_config(long nel, const double* coords, long nI, long nB, lo
     try {
         LevelPlan P; VisitCfg cfg;
         if (plan_for_visit(num_sms, P, H, po, cfg)) {
-            info[0] = 1; info[1] = cfg.K; info[2] = cfg.G; info[3] = cfg.R | (cfg.D << 8); info[4] = cfg.resident; info[5] = cfg.sr_max; info[6] = (long)cfg.smem;
+            info[0] = 1; info[1] = cfg.K; info[2] = cfg.G; info[3] = cfg.R | (cfg.D << 8) | (cfg.W << 16); info[4] = cfg.resident; info[5] = cfg.sr_max; info[6] = (long)cfg.smem;
             info[7] = P.visit.halo_total;
         }
     } catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
@@ -1654,6 +1768,7 @@ int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long tabl
     CK(cudaSetDevice(c->opt.device));
     if (!d.d_op) {
         CK(cudaMalloc((void**)&d.d_ticket, 4)); CK(cudaMemset(d.d_ticket, 0, 4));
+        CK(cudaMalloc((void**)&d.d_send_ticket, 4)); CK(cudaMemset(d.d_send_ticket, 0, 4));
         CK(cudaMalloc((void**)&d.d_op, 8)); CK(cudaMemset(d.d_op, 0, 8));
         CK(cudaMalloc((void**)&d.d_ctr, 4 * (c->levels + 1))); CK(cudaMemset(d.d_ctr, 0, 4 * (c->levels + 1)));
         CK(cudaDeviceSynchronize());
@@ -1738,6 +1853,22 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
         catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
         CKRC(dev_upload(&v.d_tgt_off, st.off, c->stream)); CKRC(dev_upload(&v.d_tgt_peer, st.peer, c->stream)); CKRC(dev_upload(&v.d_tgt_row, st.row, c->stream));
         CKRC(dev_upload(&v.d_tile_sends, st.tile_sends, c->stream));
+        if (v.pipe) { CKRC(setup_pipe_dist(c, v)); if (v.pipe_grid_dist < 1) v.pipe = false; }
+        // work units in delivery-first order (stable: units that own rows on send lists, then the others)
+        auto order_of = [&](int unit, std::vector<int>& order) {
+            const long nu = (v.ncomp + unit - 1) / unit;
+            std::vector<char> sends(nu, 0);
+            for (long r = 0; r < v.ncomp; r++) if (st.off[r + 1] > st.off[r]) sends[r / unit] = 1;
+            order.clear();
+            for (long u = 0; u < nu; u++) if (sends[u]) order.push_back((int)u);
+            const int ns = (int)order.size();
+            for (long u = 0; u < nu; u++) if (!sends[u]) order.push_back((int)u);
+            return ns;
+        };
+        std::vector<int> ot, ob;
+        v.n_send_tiles = order_of(v.TN, ot);
+        v.n_send_blk = order_of(128, ob);
+        CKRC(dev_upload(&v.d_order_tiles, ot, c->stream)); CKRC(dev_upload(&v.d_order_blk, ob, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
     d.p2p = true;

@@ -23,27 +23,36 @@ __device__ __constant__ double c_ffc[12];    // ff_flux_contribution_{momentum_x
 struct Rec { double rho, mx, my, mz, re, ir, p, s; };   // ir = 1/rho, s = |v| + speed of sound
 struct Flux5 { double r, mx, my, mz, e; };
 
-// sqrt for the edge weight |h|: MUFU.RSQ64H seed (2^-22) + two coupled Newton steps + one residual correction, branch-free.
-// x is a sum of squares >= 1e-300 here (never 0, inf or denormal), so the special-case paths of sqrt() are dead weight;
-// the result is within 1 ulp of the correctly rounded root.
+// sqrt for positive normal x: MUFU.RSQ64H seed (2^-22) + ONE coupled Newton step (2^-43) + one residual correction, branch-free.
+// x is a sum of squares >= 1e-300 here (never 0, inf or denormal), so the special-case paths of sqrt() are dead weight; the
+// result is within 1 ulp of the correctly rounded root.  (A second Newton step, as in round 1, adds three dependent FP64
+// instructions for nothing: the correction step already squares the error.  FP64 dependent-issue latency is what bounds the
+// per-node update, profiles/r02*_timeline_c2.jsonl.)
 __device__ __forceinline__ double sqrt_pos(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
-    double r = __fma_rn(-h, g, 0.5);
-    g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
-    r = __fma_rn(-h, g, 0.5);
+    const double r = __fma_rn(-h, g, 0.5);
     g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
     const double d = __fma_rn(-g, g, x);
     return __fma_rn(d, h, g);
 }
+// 1 / x for positive normal x: MUFU.RCP64H seed (2^-23) + two Newton steps, branch-free, within 1 ulp of the correctly rounded
+// reciprocal (the IEEE division it replaces is a ~25-instruction sequence with a 15-deep dependent chain)
+__device__ __forceinline__ double rcp_pos(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = __fma_rn(__fma_rn(-x, y, 1.0), y, y);
+    y = __fma_rn(__fma_rn(-x, y, 1.0), y, y);
+    return y;
+}
 
 // per-node derived quantities (cfd_loops.h:121-148): velocity = momentum / rho, speed_sqd, pressure, speed of sound.
-// The reference divides three times by rho; here one correctly rounded reciprocal and three products (<= 1 ulp apart).
+// The reference divides three times by rho; here one reciprocal (<= 1 ulp) and three products.
 __device__ __forceinline__ Rec make_rec(double rho, double mx, double my, double mz, double re) {
     Rec n;
     n.rho = rho; n.mx = mx; n.my = my; n.mz = mz; n.re = re;
-    n.ir = 1.0 / rho;
+    n.ir = rcp_pos(rho);
     const double vx = mx * n.ir, vy = my * n.ir, vz = mz * n.ir;
     const double sq = vx * vx + vy * vy + vz * vz;
     n.p = (double(MG_GAMMA) - double(1.0)) * (re - double(0.5) * rho * sq);
@@ -177,6 +186,179 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// Every cross-GPU wait is bounded: a flag that has not arrived after a few seconds (4 M polls of ~1 us: nanosleep + a system-scope
+// load) means the ranks disagree on the protocol (or a rank has died) -- the kernel reports and traps, the host sees a CUDA error
+// instead of a hung device.
+__device__ __forceinline__ bool spin_expired(unsigned& n, const char* what) {
+    __nanosleep(40);
+    if (++n < 4000000u) return false;
+    printf("mgcfd: a multi-GPU wait timed out (%s): block %d thread %d\n", what, (int)blockIdx.x, (int)threadIdx.x);
+    __trap();
+    return true;
+}
+// ---- multi-GPU: the kernel that PRODUCES a row also delivers it (DESIGN.md 5) --------------------------------------------------
+// where the copies other ranks hold of this rank's rows live (one entry per peer of the level)
+struct PeerOut {
+    double* rec[3];                // the peer's three record buffers (same rotation as ours)
+    double* res;                   // the peer's residual planes
+    long res_stride;               // the peer's npad
+};
+// remote stores + start / end synchronisation of a many-CTA kernel (restrict, prolong).  Every collective step of a distributed
+// run carries an EPOCH number that advances alike on all ranks (op_counter, on the device, so that graphs can be replayed):
+// a kernel waits at its start until the ranks it reads ghost rows from have signalled the epoch it starts in, stores the rows
+// it produces straight into the peers' copies, and its last CTA (ticket) fences system-wide and signals epoch + 1.
+// all-reduce plumbing of a rank (as k_p2p_allreduce): every rank's window has reduction slots [parity][source rank][8]
+struct AllRed {
+    int nranks, me;
+    double* const* red_of_rank; unsigned long long* const* flag_of_rank;      // [nranks]: window reduction bases, &window.flags[me]
+    const unsigned long long* my_flags; const double* my_red;
+    unsigned int* red_counter;
+};
+// all-reduce over ALL ranks of n <= 8 doubles held by lane 0 in v[] (is_min: one positive double, compared as a bit pattern), run by
+// one warp (all 32 lanes); deterministic rank order.  epoch = the number this synchronisation carries.
+__device__ __forceinline__ void dist_allreduce(const AllRed& d, unsigned long long epoch, double* v, int n, bool is_min) {
+    const int lane = threadIdx.x & 31;
+    const int parity = int(*(volatile unsigned int*)d.red_counter & 1u);
+    double mine[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) mine[j] = __shfl_sync(0xffffffffu, j < n ? v[j] : 0.0, 0);
+    for (int p = lane; p < d.nranks; p += 32) {
+        double* slot = d.red_of_rank[p] + ((size_t)parity * 64 + d.me) * 8;
+        for (int j = 0; j < n; j++) slot[j] = mine[j];
+        __threadfence_system();
+        st_release_sys(d.flag_of_rank[p], epoch);
+    }
+    for (int p = lane; p < d.nranks; p += 32) {
+        unsigned spins = 0;
+        while (ld_acquire_sys(d.my_flags + p) < epoch) { if (spin_expired(spins, "all-reduce")) break; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const double* base = d.my_red + (size_t)parity * 64 * 8;
+        if (is_min) {
+            unsigned long long m = ~0ull;
+            for (int r = 0; r < d.nranks; r++) { const unsigned long long x = (unsigned long long)__double_as_longlong(__ldcg(base + r * 8)); m = x < m ? x : m; }
+            v[0] = __longlong_as_double((long long)m);
+        } else {
+            for (int j = 0; j < n; j++) { double acc = 0.0; for (int r = 0; r < d.nranks; r++) acc += __ldcg(base + r * 8 + j); v[j] = acc; }
+        }
+        *d.red_counter += 1;
+    }
+    __syncwarp();
+}
+struct DistTail {
+    const P2PPeer* wait_peers; int nwait;      // whose rows this kernel reads
+    const P2PPeer* peers; int npeers;          // who holds copies of the rows it writes
+    const PeerOut* peer_out; int ib;           // the peers' record buffer that mirrors the output buffer
+    const int* tgt_off; const int* tgt_peer; const int* tgt_row;      // row -> (peer index, row in the peer's arrays)
+    const unsigned char* tile_sends;           // per tile of the kernel's granularity: any row with a target
+    // Work units (tiles of the stage kernel, 128-row blocks of the transfer kernels) are taken in `order`: the n_send units that own
+    // rows other ranks hold copies of come FIRST; the CTAs that own such units count themselves off on send_ticket when their last
+    // one is done, and the last of them signals the peers -- while the interior units are still being computed.  The epoch number
+    // itself (op_counter) advances when the whole grid is done (ticket).
+    const int* order; int n_send;
+    unsigned long long* op_counter; unsigned int* ticket; unsigned int* send_ticket; const unsigned long long* my_flags;
+    // the minimum dt of the state a transfer kernel leaves behind: its last CTA reduces the per-block minima and SENDS the rank's
+    // minimum, tagged with the epoch, into every rank's reduction slot (send_min); the first stage kernel of the next smoothing visit
+    // waits for the tags and combines the values itself (recv_min) -- nobody blocks inside the transfer kernel
+    AllRed ar; const double* blockmins; int nblocks; int send_min, recv_min;
+    int dbg;       // measurement only (MGCFD_DIST_DEBUG, results become wrong): 1 no start wait, 2 no remote stores, 4 no early signal, 8 no signal at all
+};
+__device__ __forceinline__ unsigned long long dist_kernel_begin(const DistTail& d) {
+    const unsigned long long e0 = *(volatile unsigned long long*)d.op_counter;
+    if ((int)threadIdx.x < d.nwait && !(d.dbg & 1)) {
+        const unsigned long long* f = d.my_flags + d.wait_peers[threadIdx.x].rank;
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < e0) { if (spin_expired(spins, "kernel start: peer epoch")) break; }
+    }
+    __syncthreads();
+    return e0;
+}
+// a CTA has finished the last of its units that deliver rows to other ranks (call after a __syncthreads that follows those units):
+// the last such CTA signals epoch e0 + 1 to the peers.  nsenders = CTAs that own at least one sending unit.
+__device__ __forceinline__ void dist_send_done(const DistTail& d, unsigned long long e0, unsigned nsenders) {
+    if (threadIdx.x == 0 && !(d.dbg & 12)) {
+        __threadfence_system();              // this CTA's remote stores (ordered before by the barrier) are delivered before ...
+        if (atomicInc(d.send_ticket, nsenders - 1) == nsenders - 1) {
+            __threadfence_system();
+            for (int p = 0; p < d.npeers; p++) st_release_sys(d.peers[p].flag, e0 + 1);      // ... the signal
+        }
+    }
+}
+// end of a distributed kernel: the last CTA of the whole grid advances the epoch; it signals the peers if no CTA had anything to
+// deliver (they wait for the epoch all the same) and, for a transfer kernel, sends the rank's minimum dt to every rank
+__device__ __forceinline__ void dist_kernel_end(const DistTail& d, unsigned long long e0, unsigned nsenders) {
+    __shared__ int s_last;
+    __shared__ double s_wm[32];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicInc(d.ticket, gridDim.x - 1) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (d.send_min) {
+        __threadfence();
+        double v = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
+        for (int b = threadIdx.x; b < d.nblocks; b += blockDim.x) v = fmin(v, __ldcg(d.blockmins + b));
+#pragma unroll
+        for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
+        if ((threadIdx.x & 31) == 0) s_wm[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            v = (threadIdx.x < (blockDim.x >> 5)) ? s_wm[threadIdx.x] : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
+#pragma unroll
+            for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
+            const int parity = int(*(volatile unsigned int*)d.ar.red_counter & 1u);
+            for (int p = threadIdx.x; p < d.ar.nranks; p += 32) {
+                double* slot = d.ar.red_of_rank[p] + ((size_t)parity * 64 + d.ar.me) * 8;
+                slot[0] = v;
+                st_release_sys(reinterpret_cast<unsigned long long*>(slot + 1), e0 + 1);      // the tag: value delivered
+            }
+            __syncwarp();
+            if (threadIdx.x == 0) *d.ar.red_counter += 1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        if ((nsenders == 0 || (d.dbg & 4)) && !(d.dbg & 8)) { __threadfence_system(); for (int p = 0; p < d.npeers; p++) st_release_sys(d.peers[p].flag, e0 + 1); }
+        *d.op_counter = e0 + 1;
+    }
+}
+// first stage of a smoothing visit: the minimum over the ranks of the values their last transfer kernel sent (tag = this kernel's
+// starting epoch); every thread returns the minimum
+__device__ __forceinline__ double dist_recv_min(const DistTail& d, unsigned long long e0) {
+    __shared__ unsigned long long s_min;
+    if (threadIdx.x < 32) {
+        const int parity = int((*(volatile unsigned int*)d.ar.red_counter - 1u) & 1u);
+        unsigned long long m = ~0ull;
+        for (int r = threadIdx.x; r < d.ar.nranks; r += 32) {
+            const double* slot = d.ar.my_red + ((size_t)parity * 64 + r) * 8;
+            unsigned spins = 0;
+            while (!(d.dbg & 1) && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(slot + 1)) != e0) { if (spin_expired(spins, "minimum dt tag")) break; }
+            const unsigned long long x = (unsigned long long)__double_as_longlong(__ldcg(slot));
+            m = x < m ? x : m;
+        }
+#pragma unroll
+        for (int dl = 16; dl > 0; dl >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, dl); m = o < m ? o : m; }
+        if (threadIdx.x == 0) s_min = m;
+    }
+    __syncthreads();
+    return __longlong_as_double((long long)s_min);
+}
+__device__ __forceinline__ void dist_push_rec(const DistTail& d, long row, const Rec& n) {
+    if (d.dbg & 2) return;
+    for (int k = d.tgt_off[row]; k < d.tgt_off[row + 1]; k++) store_rec(d.peer_out[d.tgt_peer[k]].rec[d.ib], d.tgt_row[k], n);
+}
+__device__ __forceinline__ void dist_push_res(const DistTail& d, long row, const double r[5]) {
+    if (d.dbg & 2) return;
+    for (int k = d.tgt_off[row]; k < d.tgt_off[row + 1]; k++) {
+        const PeerOut& po = d.peer_out[d.tgt_peer[k]];
+        double* pr = po.res + d.tgt_row[k];
+        pr[0] = r[0]; pr[po.res_stride] = r[1]; pr[2 * po.res_stride] = r[2]; pr[3 * po.res_stride] = r[3]; pr[4 * po.res_stride] = r[4];
+    }
+}
+
 // fixed-stride per-tile header (hdr_stride bytes per tile): what a CTA needs to know about a tile before it can fetch it
 struct TileHdr {
     int rounds, nh, brounds, pad;
@@ -209,6 +391,8 @@ struct StageArgs {
     const int* old_of_new;
     unsigned long long stage_seq;
     int mask;              // bit0 internal, bit1 boundary, bit2 wall
+    const double* premin; int npremin;     // first stage: per-block minima of dt left by the transfer kernel that produced vin (or nullptr: *min_bits holds the minimum)
+    DistTail d;            // DIST instantiation of k_stage_pipe: rows are delivered by the kernel itself
 };
 
 // A slot's `other` field is the byte offset of logical chunk 0 of the other endpoint's row in the shared record buffer,
@@ -322,12 +506,14 @@ __device__ __forceinline__ double div_rk(double x, double d, double rd) {
     return __fma_rn(__fma_rn(-d, q, x), rd, q);
 }
 // phase 3 of a fused stage for node gid: time_step + record + validity + residual; returns the five squared residuals in q
-__device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5]) {
+template <bool DIST = false>
+__device__ __forceinline__ void fused_update(const StageArgs& a, long gid, double sf, const double o[5], const Flux5& f, double q[5], bool sends = false) {
     const long S = a.stride;
     const double factor = div_rk(sf, a.rk_div, a.rk_rcp);     // == sf / rk_div, the true divide of cfd_loops.cpp:243
     const double n0 = o[0] + factor * f.r, n1 = o[1] + factor * f.mx, n2 = o[2] + factor * f.my, n3 = o[3] + factor * f.mz, n4 = o[4] + factor * f.e;
     const Rec nrec = make_rec(n0, n1, n2, n3, n4);
     store_rec(a.vout, gid, nrec);
+    if (DIST && sends) dist_push_rec(a.d, gid, nrec);      // the same record into the copies other ranks hold of this node (over NVLink)
     if (a.bad_key) {
         // check_for_invalid_variables (validation.cpp:107-138): first offending cell of the first offending stage
         int reason = 0;
@@ -342,6 +528,7 @@ __device__ __forceinline__ void fused_update(const StageArgs& a, long gid, doubl
     if (a.res) {
         const double r0 = n0 - o[0], r1 = n1 - o[1], r2 = n2 - o[2], r3 = n3 - o[3], r4 = n4 - o[4];   // residual(), validation.cpp:77-89
         a.res[gid] = r0; a.res[S + gid] = r1; a.res[2 * S + gid] = r2; a.res[3 * S + gid] = r3; a.res[4 * S + gid] = r4;
+        if (DIST && sends) { const double rr[5] = {r0, r1, r2, r3, r4}; dist_push_res(a.d, gid, rr); }      // prolong on the other ranks reads them
         q[0] = r0 * r0; q[1] = r1 * r1; q[2] = r2 * r2; q[3] = r3 * r3; q[4] = r4 * r4;
     }
 }
@@ -441,7 +628,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 constexpr int RING = 2;     // ring entries (each `chunk_rounds` round blocks)
 
-template <int TN, bool SCATTER>
+template <int TN, bool SCATTER, bool DIST = false>
 __global__ void __launch_bounds__(TN, (TN <= 128 ? 4 : (TN <= 256 ? 2 : 1)))
 k_stage_pipe(const StageArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
@@ -463,7 +650,10 @@ k_stage_pipe(const StageArgs a) {
     }
     __syncthreads();
 
-    auto tile_of = [&](int it) -> long { return (long)blockIdx.x + (long)it * G; };
+    // DIST: tiles are taken in an order that puts the tiles with rows on send lists first (DistTail::order)
+    auto tile_of = [&](int it) -> long { const long k = (long)blockIdx.x + (long)it * G; return DIST ? (long)a.d.order[k] : k; };
+    const unsigned nsenders = DIST ? unsigned(min(a.d.n_send, G)) : 0u;
+    const int my_send_iters = (DIST && (int)blockIdx.x < a.d.n_send) ? (a.d.n_send - (int)blockIdx.x + G - 1) / G : 0;
     auto hdr_of = [&](int it) -> const TileHdr* { return reinterpret_cast<const TileHdr*>(hdrs + (it % 3) * (size_t)a.hdr_stride); };
     auto copy_hdr = [&](int it) {
         if (it >= my_count) return;
@@ -520,10 +710,29 @@ k_stage_pipe(const StageArgs a) {
     __syncthreads();
     if (t == 0) produce(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    unsigned long long e0 = 0;
+    if (DIST) e0 = dist_kernel_begin(a.d);       // ghost rows of vin were delivered by their owners' previous kernel: wait for its epoch
     copy_recs(0);
     const bool first_stage = (a.vold == a.vin);
-    // the visit's global minimum dt (k_min_dt, the previous kernel of a first stage): one load per CTA, not one per tile
-    const double min_dt = (first_stage && !a.legacy) ? __longlong_as_double((long long)*a.min_bits) : 0.0;
+    // the visit's global minimum dt: *min_bits (k_min_dt, or -- multi-GPU -- the all-reduce at the end of the transfer kernel that
+    // produced this state), or the per-block minima that transfer kernel left behind, reduced here by every CTA for itself
+    double min_dt = 0.0;
+    if (first_stage && !a.legacy) {
+        if (DIST && a.d.recv_min) min_dt = dist_recv_min(a.d, e0);
+        else if (a.premin) {
+            double v = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
+            for (int b = t; b < a.npremin; b += TN) v = fmin(v, __ldcg(a.premin + b));
+#pragma unroll
+            for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
+            if ((t & 31) == 0) ws[0][t >> 5] = v;
+            __syncthreads();
+            v = ((t & 31) < TN / 32) ? ws[0][t & 31] : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
+#pragma unroll
+            for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
+            min_dt = v;
+            __syncthreads();          // ws is reused by the RMS sums
+        } else min_dt = __longlong_as_double((long long)*a.min_bits);
+    }
 
     for (int it = 0; it < my_count; it++) {
         const long tile = tile_of(it);
@@ -576,10 +785,12 @@ k_stage_pipe(const StageArgs a) {
         double sf = vol_or_sf;
         if (first_stage) { sf = step_factor_of(a, min_dt, vol_or_sf, me.s); a.sf[gid] = sf; }
         double q[5] = {0, 0, 0, 0, 0};
-        fused_update(a, gid, sf, o, f, q);
+        fused_update<DIST>(a, gid, sf, o, f, q, DIST && a.d.tile_sends[tile] != 0);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
         __syncthreads();      // record buffer (it & 1), header buffer (it % 3), acc and ws are free again
+        if (DIST && it == my_send_iters - 1) dist_send_done(a.d, e0, nsenders);      // this CTA's last delivering tile: the interior tiles follow
     }
+    if (DIST) dist_kernel_end(a.d, e0, nsenders);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -757,48 +968,6 @@ __global__ void k_check_invalid(const double* __restrict__ recs, long n, const i
 // ------------------------------------------------------------------------------------------------------
 // multigrid transfers
 // ------------------------------------------------------------------------------------------------------
-// ---- multi-GPU: the kernel that PRODUCES a row also delivers it (DESIGN.md 5) --------------------------------------------------
-// where the copies other ranks hold of this rank's rows live (one entry per peer of the level)
-struct PeerOut {
-    double* rec[3];                // the peer's three record buffers (same rotation as ours)
-    double* res;                   // the peer's residual planes
-    long res_stride;               // the peer's npad
-};
-// remote stores + start / end synchronisation of a many-CTA kernel (restrict, prolong).  Every collective step of a distributed
-// run carries an EPOCH number that advances alike on all ranks (op_counter, on the device, so that graphs can be replayed):
-// a kernel waits at its start until the ranks it reads ghost rows from have signalled the epoch it starts in, stores the rows
-// it produces straight into the peers' copies, and its last CTA (ticket) fences system-wide and signals epoch + 1.
-struct DistTail {
-    const P2PPeer* wait_peers; int nwait;      // whose rows this kernel reads
-    const P2PPeer* peers; int npeers;          // who holds copies of the rows it writes
-    const PeerOut* peer_out; int ib;           // the peers' record buffer that mirrors the output buffer
-    const int* tgt_off; const int* tgt_peer; const int* tgt_row;      // row -> (peer index, row in the peer's arrays)
-    unsigned long long* op_counter; unsigned int* ticket; const unsigned long long* my_flags;
-};
-__device__ __forceinline__ unsigned long long dist_kernel_begin(const DistTail& d) {
-    const unsigned long long e0 = *(volatile unsigned long long*)d.op_counter;
-    if ((int)threadIdx.x < d.nwait) {
-        const unsigned long long* f = d.my_flags + d.wait_peers[threadIdx.x].rank;
-        while (ld_acquire_sys(f) < e0) { __nanosleep(20); }
-    }
-    __syncthreads();
-    return e0;
-}
-__device__ __forceinline__ void dist_kernel_end(const DistTail& d, unsigned long long e0) {
-    __syncthreads();             // the CTA's remote stores are ordered before thread 0's system-scope fence
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicInc(d.ticket, gridDim.x - 1) == gridDim.x - 1) {
-            __threadfence_system();
-            for (int p = 0; p < d.npeers; p++) st_release_sys(d.peers[p].flag, e0 + 1);
-            *d.op_counter = e0 + 1;
-        }
-    }
-}
-__device__ __forceinline__ void dist_push_rec(const DistTail& d, long row, const Rec& n) {
-    for (int k = d.tgt_off[row]; k < d.tgt_off[row + 1]; k++) store_rec(d.peer_out[d.tgt_peer[k]].rec[d.ib], d.tgt_row[k], n);
-}
-
 // The transfer kernels leave the per-block minima of 0.5 * cbrt(vol) / (|v| + c) of the state they produce behind (blockDim.x = 128):
 // the next smoothing visit of that level needs exactly this minimum (compute_step_factor, cfd_loops.cpp:123-145) and no longer has to
 // pass over the nodes for it.  One shuffle reduction, one barrier and one store per block -- no atomics, no ticket.
@@ -819,7 +988,7 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
                            double* __restrict__ blockmins, const DistTail d) {
     unsigned long long e0 = 0;
     if (DIST) e0 = dist_kernel_begin(d);
-    const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long c = (DIST ? (long)d.order[blockIdx.x] : (long)blockIdx.x) * (long)blockDim.x + threadIdx.x;      // DIST: delivering blocks first
     double s_new = 0.0;          // |v| + c of the node's state after this kernel
     if (c < ncoarse) {
         const long k0 = child_off[c], k1 = child_off[c + 1];
@@ -844,7 +1013,10 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
         }
     }
     if (blockmins) block_min_store(c < ncoarse ? 0.5 * (vol_root[c] / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), blockmins);
-    if (DIST) dist_kernel_end(d, e0);
+    if (DIST) {
+        if ((int)blockIdx.x < d.n_send) { __syncthreads(); dist_send_done(d, e0, (unsigned)d.n_send); }
+        dist_kernel_end(d, e0, (unsigned)d.n_send);
+    }
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
 // edges in original edge order: per edge the own-parent term then the neighbour-parent term (whose source is the own
@@ -856,7 +1028,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
                           const double* __restrict__ vol_root, double* __restrict__ blockmins, const DistTail d) {
     unsigned long long e0 = 0;
     if (DIST) e0 = dist_kernel_begin(d);
-    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long i = (DIST ? (long)d.order[blockIdx.x] : (long)blockIdx.x) * (long)blockDim.x + threadIdx.x;      // DIST: delivering blocks first
     const int p = (i < nfine) ? parent[i] : -1;
     double dt_new = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);      // padding rows (no parent) never win the minimum
     if (p >= 0) {
@@ -899,7 +1071,10 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
         if (DIST) dist_push_rec(d, i, n);
     }
     if (blockmins) block_min_store(dt_new, blockmins);
-    if (DIST) dist_kernel_end(d, e0);
+    if (DIST) {
+        if ((int)blockIdx.x < d.n_send) { __syncthreads(); dist_send_done(d, e0, (unsigned)d.n_send); }
+        dist_kernel_end(d, e0, (unsigned)d.n_send);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1017,7 +1192,8 @@ __global__ void k_p2p_exchange(const double* __restrict__ src, long stride, cons
     // 3. wait for every source of this level
     if (threadIdx.x < npeers && peers[threadIdx.x].nrecv >= 0) {
         const unsigned long long* f = my_flags + peers[threadIdx.x].rank;
-        while (ld_acquire_sys(f) < g) { __nanosleep(64); }
+        unsigned spins = 0;
+        while (ld_acquire_sys(f) < g) { if (spin_expired(spins, "halo exchange")) break; }
     }
     __syncthreads();
     // 4. unpack staging -> ghost rows (a source's rows start at 8 * recv0 doubles whatever the message width)
@@ -1045,7 +1221,8 @@ __global__ void k_p2p_allreduce(double* __restrict__ vals, int n, int is_min, in
         for (int j = 0; j < n; j++) slot[j] = vals[j];
         __threadfence_system();
         st_release_sys(flag_of_rank[t], g);
-        while (ld_acquire_sys(my_flags + t) < g) { __nanosleep(64); }
+        unsigned spins = 0;
+        while (ld_acquire_sys(my_flags + t) < g) { if (spin_expired(spins, "all-reduce kernel")) break; }
     }
     __syncthreads();
     if (t < n) {

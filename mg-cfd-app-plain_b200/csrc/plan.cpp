@@ -657,7 +657,10 @@ static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, Leve
     const long TN = P.TN;
     const long ns = V.ns;
     const int WT = 32;                              // rows of a warp-tile
-    const size_t BLK = size_t(WT) * 26;
+    const size_t BLK = size_t(WT) * 34;
+    const double k2 = 2.0 * (-0.5 * double(0.2f));      // 2 * kdiss, kdiss = -0.5 * smoothing_coefficient (src/Base/common.h:24)
+    const int RC = std::max(1, opt.visit_rounds);       // rounds per ring chunk
+    V.hsum.assign(3 * size_t(P.npad_owned), 0.0);
     struct VSlot { int owner; int round; int other; long e; bool owner_is_a; };     // other = idx | halo << 20
     struct Ent { int orow0, rounds, blane0; long tile; long blk0; };                // blk0 relative to the super-tile's first block
     struct SuperOut {
@@ -740,24 +743,33 @@ static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, Leve
                 }
                 int rounds = 0;
                 for (const VSlot& sl : slots) rounds = std::max(rounds, sl.round + 1);
+                rounds = (rounds + RC - 1) / RC * RC;        // whole chunks: the kernel's chunk loop has a compile-time trip count
                 const long b0 = blocks_done;
                 blocks_done += rounds;
                 O.blocks.resize(size_t(blocks_done) * BLK, 0);
                 const int orow0 = int(base - row0);          // the warp-tile's first row inside the super-tile
                 O.ents.push_back({orow0, rounds, w4 * WT, t, b0});
                 for (int r = 0; r < rounds; r++) {
-                    uint16_t* oth = reinterpret_cast<uint16_t*>(O.blocks.data() + size_t(b0 + r) * BLK + size_t(WT) * 24);
-                    for (int lu = 0; lu < WT; lu++) oth[lu] = visit_code(orow0 + lu, false);      // empty slot: the node itself, h = 0
+                    uint16_t* oth = reinterpret_cast<uint16_t*>(O.blocks.data() + size_t(b0 + r) * BLK + size_t(WT) * 32);
+                    for (int lu = 0; lu < WT; lu++) oth[lu] = visit_code(orow0 + lu, false);      // empty slot: the node itself, h = 0, wk = 0
                 }
                 for (const VSlot& sl : slots) {
                     unsigned char* blk = O.blocks.data() + size_t(b0 + sl.round) * BLK;
                     double* w = reinterpret_cast<double*>(blk);
-                    uint16_t* oth = reinterpret_cast<uint16_t*>(blk + size_t(WT) * 24);
+                    uint16_t* oth = reinterpret_cast<uint16_t*>(blk + size_t(WT) * 32);
                     const double sg = sl.owner_is_a ? -0.5 : 0.5;
-                    w[sl.owner] = sg * P.ew[sl.e];
-                    w[WT + sl.owner] = sg * P.ew[L.nI + sl.e];
-                    w[2 * WT + sl.owner] = sg * P.ew[2 * L.nI + sl.e];
+                    const double hx = sg * P.ew[sl.e], hy = sg * P.ew[L.nI + sl.e], hz = sg * P.ew[2 * L.nI + sl.e];
+                    w[sl.owner] = hx; w[WT + sl.owner] = hy; w[2 * WT + sl.owner] = hz;
+                    w[3 * WT + sl.owner] = std::sqrt(std::fma(hx, hx, std::fma(hy, hy, hz * hz))) * k2;
                     oth[sl.owner] = visit_code(sl.other & 0xFFFFF, (sl.other >> 20) != 0);
+                }
+                // per-row sums of h in round order (rows of different super-tiles are disjoint: no two workers write the same entry)
+                for (int r = 0; r < rounds; r++) {
+                    const double* w = reinterpret_cast<const double*>(O.blocks.data() + size_t(b0 + r) * BLK);
+                    for (int lu = 0; lu < WT; lu++) {
+                        const size_t row = size_t(base + lu);
+                        V.hsum[row] += w[lu]; V.hsum[P.npad_owned + row] += w[WT + lu]; V.hsum[2 * size_t(P.npad_owned) + row] += w[2 * WT + lu];
+                    }
                 }
             }
     };
@@ -784,9 +796,21 @@ static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, Leve
         blk_off[s + 1] = blk_off[s] + long(out[s].blocks.size() / BLK);
     }
     V.vblocks = blk_off[ns];
+    if (V.vblocks >= (1L << 32)) throw std::runtime_error("mgcfd: too many edge round blocks for the visit kernel's 32-bit chunk index");
     V.vslots.resize(size_t(V.vblocks) * BLK);
     V.hpad = (V.max_halo + 3) & ~3;
-    V.desc_stride = (32 + 32 * V.max_ent + 4 * V.hpad + 15) & ~15;
+    // chunk lists: warp w (of 16) takes the entries w, w+16, ... of a super-tile, each cut into chunks of R rounds
+    const int NW = (opt.visit_warps == 8) ? 8 : 16, R = std::max(1, opt.visit_rounds);
+    V.rounds_per_chunk = R; V.warps = NW;
+    V.max_chunk = 0;
+    for (long s = 0; s < ns; s++) {
+        long n = 0;
+        for (const Ent& e : out[s].ents) n += (e.rounds + R - 1) / R;
+        V.max_chunk = std::max<int>(V.max_chunk, int(n));
+    }
+    if (V.max_chunk >= 65536) throw std::runtime_error("mgcfd: too many chunks in one super-tile");
+    V.max_chunk = (V.max_chunk + 3) & ~3;
+    V.desc_stride = (32 + 32 * V.max_ent + 48 + 4 * V.max_chunk + 4 * V.hpad + 15) & ~15;
     V.desc.assign(size_t(ns) * V.desc_stride, 0);
     for (long s = 0; s < ns; s++) {
         const long t0 = V.super_off[s], t1 = V.super_off[s + 1];
@@ -802,7 +826,19 @@ static void build_visit_streams(const HostLevel& L, const PlanOptions& opt, Leve
             reinterpret_cast<long long*>(eh)[2] = blk_off[s] + e.blk0;
             reinterpret_cast<long long*>(eh)[3] = P.bslot_off[e.tile];
         }
-        int* ids = reinterpret_cast<int*>(d + 32 + 32 * V.max_ent);
+        unsigned short* coff = reinterpret_cast<unsigned short*>(d + 32 + 32 * V.max_ent);
+        unsigned* cl = reinterpret_cast<unsigned*>(d + 32 + 32 * V.max_ent + 48);
+        int nch = 0;
+        for (int w = 0; w < NW; w++) {
+            coff[w] = (unsigned short)nch;
+            for (size_t k = w; k < out[s].ents.size(); k += NW) {
+                const Ent& e = out[s].ents[k];
+                for (int r0 = 0; r0 < e.rounds; r0 += R, nch++) cl[nch] = unsigned(blk_off[s] + e.blk0 + r0);
+            }
+        }
+        coff[NW] = (unsigned short)nch;
+        di[5] = nch;
+        int* ids = reinterpret_cast<int*>(d + 32 + 32 * V.max_ent + 48 + 4 * V.max_chunk);
         for (size_t k = 0; k < out[s].halo.size(); k++) ids[k] = out[s].halo[k];
         std::vector<unsigned char>().swap(out[s].blocks);
     }
@@ -1009,7 +1045,8 @@ void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const d
     if (V.ns <= 0) throw std::runtime_error("mgcfd: the level has no visit plan");
     const long TN = P.TN;
     const int WT = 32;
-    const size_t BLK = size_t(WT) * 26, BBLK = size_t(TN) * 25;
+    const size_t BLK = size_t(WT) * 34, BBLK = size_t(TN) * 25;
+    if (V.hsum.size() != 3 * size_t(P.npad_owned)) throw std::runtime_error("mgcfd: the visit plan has no per-row edge-vector sums");
     std::vector<HRec> rec(P.npad);
     const double pad_state[5] = {ff[0], ff[1], ff[2], ff[3], ff[4]};
     for (long g = 0; g < P.npad; g++) rec[g] = host_rec(P.old_of_new[g] >= 0 ? var + 5 * P.old_of_new[g] : pad_state);
@@ -1020,7 +1057,26 @@ void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const d
         const int* di = reinterpret_cast<const int*>(d);
         const long row0 = di[0]; const int ntile = di[1], nhalo = di[2]; const long tile0 = di[3]; const int nent = di[4];
         if (row0 != tile0 * TN || ntile < 1 || ntile > V.maxt || nhalo > V.hpad || nent > V.max_ent || nent > 4 * ntile) throw std::runtime_error("mgcfd: bad super-tile descriptor");
-        const int* ids = reinterpret_cast<const int*>(d + 32 + 32 * V.max_ent);
+        const int* ids = reinterpret_cast<const int*>(d + 32 + 32 * V.max_ent + 48 + 4 * V.max_chunk);
+        {   // the chunk lists: what warp w's lane 0 feeds the warp's ring with must be, in order, what the warp then consumes
+            const unsigned short* coff = reinterpret_cast<const unsigned short*>(d + 32 + 32 * V.max_ent);
+            const unsigned* cl = reinterpret_cast<const unsigned*>(d + 32 + 32 * V.max_ent + 48);
+            const int R = V.rounds_per_chunk;
+            const int NW = V.warps;
+            if (coff[0] != 0 || coff[NW] != di[5] || di[5] > V.max_chunk) throw std::runtime_error("mgcfd: bad chunk offsets in a super-tile");
+            for (int w = 0; w < NW; w++) {
+                int pos = coff[w];
+                for (int k = w; k < nent; k += NW) {
+                    const unsigned char* eh = d + 32 + 32 * k;
+                    const int rounds = reinterpret_cast<const int*>(eh)[1];
+                    const long long vblk0 = reinterpret_cast<const long long*>(eh)[2];
+                    if (rounds % R) throw std::runtime_error("mgcfd: a warp-tile's rounds are not whole chunks");
+                    for (int r0 = 0; r0 < rounds; r0 += R, pos++)
+                        if (pos >= coff[w + 1] || cl[pos] != unsigned(vblk0 + r0)) throw std::runtime_error("mgcfd: a warp's chunk list does not match its warp-tiles");
+                }
+                if (pos != coff[w + 1]) throw std::runtime_error("mgcfd: a warp's chunk list is longer than its warp-tiles");
+            }
+        }
         for (int k = 0; k < nhalo; k++) {
             if (ids[k] < 0 || ids[k] >= P.npad || (ids[k] >= row0 && ids[k] < row0 + ntile * TN)) throw std::runtime_error("mgcfd: bad halo id in a super-tile");
             if (k && ids[k] <= ids[k - 1]) throw std::runtime_error("mgcfd: halo ids of a super-tile are not strictly ascending");
@@ -1037,11 +1093,16 @@ void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const d
                 if (seen[gid]++) throw std::runtime_error("mgcfd: a row belongs to two warp-tiles");
                 const HRec& me = rec[gid];
                 double f[5] = {0, 0, 0, 0, 0};
+                double hs[3] = {0, 0, 0};
                 if (mask & 1)
                     for (int r = 0; r < rounds; r++) {
                         const unsigned char* blk = V.vslots.data() + size_t(vblk0 + r) * BLK;
                         const double* w = reinterpret_cast<const double*>(blk);
-                        const uint16_t code = reinterpret_cast<const uint16_t*>(blk + size_t(WT) * 24)[lu];
+                        const uint16_t code = reinterpret_cast<const uint16_t*>(blk + size_t(WT) * 32)[lu];
+                        const double hx = w[lu], hy = w[WT + lu], hz = w[2 * WT + lu], wk = w[3 * WT + lu];
+                        // the stream's precomputed |h| * k2 against its definition (one rounding each: exact equality)
+                        if (wk != std::sqrt(std::fma(hx, hx, std::fma(hy, hy, hz * hz))) * k2) throw std::runtime_error("mgcfd: visit slot weight is not |h| * k2");
+                        hs[0] += hx; hs[1] += hy; hs[2] += hz;
                         const bool is_halo = (code & 0x8000) != 0;
                         const int idx = (code & 0x7fff) >> 2;
                         if ((code & 3) != ((idx >> 1) & 3)) throw std::runtime_error("mgcfd: visit slot code does not follow the swizzle");
@@ -1070,6 +1131,8 @@ void emulate_visit_flux(const LevelPlan& P, const double* var, int mask, const d
                             f[3] += (fx * ffc[6] + fy * ffc[7] + fz * ffc[8]) + (me.mz * q + me.p * fz);
                         }
                     }
+                if (mask & 1)       // the hoisted A-side terms use these sums: same additions in the same (round) order
+                    for (int v = 0; v < 3; v++) if (hs[v] != V.hsum[size_t(v) * P.npad_owned + gid]) throw std::runtime_error("mgcfd: per-row edge-vector sum does not match the slots");
                 const long on = P.old_of_new[gid];
                 if (on < 0) {
                     for (int v = 0; v < 5; v++) if (f[v] != 0.0) throw std::runtime_error("mgcfd: a padding thread accumulated flux");

@@ -18,6 +18,8 @@ struct PlanOptions {
     bool strict = true;   // false (introspection only): tiles whose halo cannot be staged are flagged (LevelPlan::oversize) instead of rejected
     bool conflict_free_rounds = true;  // segment mode: schedule each node's edges over the rounds so that quarter-warps avoid shared-memory bank conflicts
     bool scatter = false; // true: coloured-scatter rounds (each in-tile edge once); false: sorted-segment rounds (every edge from both ends)
+    int visit_rounds = 2; // edge rounds per ring chunk of the visit kernel (the chunk lists in the descriptors are built for it)
+    int visit_warps = 16; // warps per CTA of the visit kernel (16: one CTA per SM; 8: two): warp w takes the warp-tiles w, w + warps, ...
     int supers = 0;       // > 0 (segment mode, tile_nodes 128): group the tiles into this many SUPER-TILES (two-level bisection: first into
                           // super-tiles, then each into its tiles) and build the visit kernel's streams (VisitPlan below)
 };
@@ -33,7 +35,9 @@ struct VisitPlan {
     long halo_total = 0;
     std::vector<long> super_off;           // ns+1: super-tile s = tiles [super_off[s], super_off[s+1])
     // The unit of work is a WARP-TILE: 32 consecutive rows (a quarter of a 128-row tile) that hold at least one node.  Edge rounds
-    // per warp-tile, blocks of 32*26 bytes [hx[32] | hy[32] | hz[32] | code[32] (u16)], h as in LevelPlan::slots;
+    // per warp-tile, blocks of 32*34 bytes [hx[32] | hy[32] | hz[32] | wk[32] | code[32] (u16)], h as in LevelPlan::slots,
+    //   wk = RN(sqrt(hx^2 + hy^2 + hz^2) * k2) with the IEEE square root (|e| * kdiss of flux_kernel.elemfunc.c:130 up to one rounding):
+    //   the visit kernel's edge loop has no square root;
     //   code = (idx << 2) | ((idx >> 1) & 3) | (halo ? 0x8000 : 0), idx = row of the other endpoint inside the super-tile's own rows
     //   (halo = 0) or inside its halo list (halo = 1); (code & 0x7fff) << 4 is the byte offset of chunk 0 of that 64-byte row under
     //   the 64B swizzle, relative to the own-row / halo-row base.  Empty slot: the thread's own row, h = 0.
@@ -41,11 +45,17 @@ struct VisitPlan {
     long vblocks = 0;                      // 32-lane round blocks in total
     int max_ent = 0;                       // most warp-tiles in one super-tile
     std::vector<unsigned char> vslots;
+    std::vector<double> hsum;              // [3][npad_owned]: sum of h over a row's internal edges (the A-side terms of the flux are hoisted out of the edge loop)
     // fixed-stride super-tile descriptors:
-    //   {int row0, ntile, nhalo, tile0, nent, 0, 0, 0;                                             (32 bytes)
-    //    max_ent x {int orow0, rounds, brounds, blane0; long long vblk0, bblk0, pad};              (32 bytes each; orow0 = first row
+    //   {int row0, ntile, nhalo, tile0, nent, nchunk, 0, 0;                                        (32 bytes)
+    //    max_ent x {int orow0, rounds, brounds, blane0; long long vblk0, bblk0};                   (32 bytes each; orow0 = first row
     //                 inside the super-tile, blane0 = first lane inside the 128-wide boundary blocks of its tile)
+    //    unsigned short coff[warps + 1 (padded to 48 bytes)]; chunks of warp w = clist[coff[w] .. coff[w+1])
+    //    max_chunk x unsigned vblk;                           the ring refills of warp w in the order it consumes them: warp w takes the
+    //                 warp-tiles w, w + warps, ...; each is cut into chunks of exactly `rounds_per_chunk` rounds (a warp-tile's rounds are
+    //                 padded with empty slots to a whole number of chunks)
     //    int halo_ids[hpad]}
+    int rounds_per_chunk = 2, max_chunk = 0, warps = 16;
     std::vector<unsigned char> desc;
     int desc_stride = 0;
 };

@@ -1,7 +1,7 @@
 """Multi-GPU parity (needs >= 2 GPUs; skipped on a single-GPU box): tools/dist_check.py under torchrun, every rank running its
 part of the mesh, compared on rank 0 with the single-GPU solver (1e-11).  Data planes: the default (peer-to-peer: every kernel
-delivers the rows it produces straight into the other ranks' arrays, the visit kernel's grid barriers double as the halo
-exchange), the same plane with the stage-per-launch kernels (MGCFD_VISIT=0) and NCCL send/recv (MGCFD_NO_P2P=1)."""
+delivers the rows it produces straight into the other ranks' arrays and synchronises through epoch flags), the same plane with the
+persistent visit kernel (MGCFD_VISIT=1: its grid barriers double as the halo exchange) and NCCL send/recv (MGCFD_NO_P2P=1)."""
 import os
 import subprocess
 import sys
@@ -20,8 +20,8 @@ def test_distributed_matches_single_gpu(nranks, plane):
         pytest.skip(f"needs {nranks} GPUs")
     port = 29600 + nranks + {"p2p-visit": 0, "p2p-stage": 10, "nccl": 20}[plane]
     env = dict(os.environ)
-    if plane == "p2p-stage":
-        env["MGCFD_VISIT"] = "0"
+    if plane == "p2p-visit":
+        env["MGCFD_VISIT"] = "1"
     if plane == "nccl":
         env["MGCFD_NO_P2P"] = "1"
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",

@@ -370,23 +370,37 @@ def _env(**kw):
     return cm()
 
 
-def test_default_path_is_the_visit_kernel(M):
-    """levels of this size run the visit kernel by default: 6 visits + 3 restrictions + 3 prolongations = 12 launches per 4-level cycle"""
-    s = M.Solver.from_mesh(make(M, "hex_nonnested"))
-    assert all(s.visit_info(l)["visit"] == 1 for l in range(4))
-    s.run_cycles(1)
-    l0 = s.launch_count()
-    s.run_cycles(3)
-    assert s.launch_count() - l0 == 3 * 12
-    s.close()
+def test_launches_per_cycle_of_both_fused_paths(M):
+    """stage path (default): 18 stage kernels + 3 restrictions + 3 prolongations + the RMS reduction = 25 launches per 4-level cycle once
+    the transfer kernels supply the minimum dt (the first cycle also runs k_min_dt for level 0); visit path: 6 visits + 6 transfers = 12"""
+    for visit, want in ((False, 25), (True, 12)):
+        s = M.Solver.from_mesh(make(M, "hex_nonnested"), visit=visit)
+        assert all(s.visit_info(l)["visit"] == int(visit) for l in range(4))
+        s.run_cycles(1)
+        l0 = s.launch_count()
+        s.run_cycles(3)
+        assert s.launch_count() - l0 == 3 * want, (visit, s.launch_count() - l0)
+        s.close()
+
+
+def test_min_dt_from_the_transfer_kernels_changes_nothing(M):
+    """the per-block minima restrict / prolong leave behind give the same global minimum as k_min_dt: bit-identical runs"""
+    outs = []
+    for premin in (1, 0):
+        with _env(MGCFD_PREMIN=premin):
+            s = M.Solver.from_mesh(make(M, "hex_nonnested"))
+            ra, rv = s.run_cycles(7)
+            outs.append((ra, s.get_field(0, M.FIELD_VARIABLES).copy(), s.get_field(1, M.FIELD_STEP_FACTORS).copy()))
+            s.close()
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][2], outs[1][2])
 
 
 @pytest.mark.parametrize("name", ["hex_nonnested", "tet3", "fvcorr", "hex_random"])
-@pytest.mark.parametrize("env", [dict(MGCFD_VISIT_K=1), dict(MGCFD_VISIT_K=1, MGCFD_VISIT_RESIDENT=0), dict(MGCFD_VISIT_K=2), dict(MGCFD_VISIT_K=3, MGCFD_VISIT_R=1),
-                                 dict(MGCFD_VISIT_K=2, MGCFD_VISIT_R=2)])
+@pytest.mark.parametrize("env", [dict(MGCFD_VISIT_K=1), dict(MGCFD_VISIT_K=1, MGCFD_VISIT_RESIDENT=0), dict(MGCFD_VISIT_K=2), dict(MGCFD_VISIT_K=3),
+                                 dict(MGCFD_VISIT_K=1, MGCFD_VISIT_WARPS=8), dict(MGCFD_VISIT_K=2, MGCFD_VISIT_WARPS=8)])
 def test_visit_kernel_configurations_match_oracle_and_stage_kernels(M, oracle, name, env):
     """every way the visit kernel can be configured -- own rows resident (K = 1) or re-read per stage, several double-buffered
-    super-tiles per CTA (K > 1), ring entries of one / two / more rounds -- against the oracle (1e-11) and against the stage-per-launch
+    super-tiles per CTA (K > 1), 16 warps (one CTA per SM) or 8 (two) -- against the oracle (1e-11) and against the stage-per-launch
     path (different summation order inside a node's edge list only: 1e-13), and bit-reproducible run to run."""
     cycles = 6
     mesh = make(M, name)
@@ -395,7 +409,7 @@ def test_visit_kernel_configurations_match_oracle_and_stage_kernels(M, oracle, n
     outs = []
     with _env(**env):
         for rep in range(2):
-            s = M.Solver.from_mesh(make(M, name))
+            s = M.Solver.from_mesh(make(M, name), visit=True)
             vi = s.visit_info(0)
             if vi["visit"] == 0:
                 s.close()

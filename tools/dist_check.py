@@ -24,10 +24,11 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
     dist.init_process_group("gloo")
     torch.cuda.set_device(local)
-    # "coarse2": a coarsest level of 2 nodes -- with more than two ranks some ranks own nothing there and have no halo at that level;
-    # every rank must still take part in every collective step (the epoch numbers advance alike on all ranks)
+    # "coarse8": a coarsest level of 8 nodes (one or two per rank on 4 / 8 ranks); "replicas": the mesh duplicated once per rank (-m), dealt
+    # out copy by copy -- NO rank has a halo at any level, yet every rank must still take part in every collective step (the epoch
+    # numbers advance alike on all ranks)
     cases = [("hex4", 0, [[26, 24, 22], [13, 12, 11], [7, 6, 6], [4, 3, 3]], 2), ("tet3", 1, [[17, 15, 13], [9, 8, 7], [5, 4, 4]], 3), ("fvcorr", 2, [[9, 8, 7]], 0),
-             ("coarse2", 0, [[16, 8, 8], [8, 4, 4], [2, 1, 1]], 2)]
+             ("coarse8", 0, [[16, 8, 8], [8, 4, 4], [2, 2, 2]], 2), ("replicas", 0, [[12, 10, 8], [6, 5, 4]], 2)]
     cycles = 8
     if len(sys.argv) > 1 and sys.argv[1] == "c2":       # the bench.py unit: BASELINE config C2 grown `world`-fold along x, rank-local generation
         cases = [("c2-unit", 0, [[67 * world - (world - 1), 67, 67], [55 * world - (world - 1), 55, 55], [48 * world - (world - 1), 48, 48], [43 * world - (world - 1), 43, 43]], 2)]
@@ -39,6 +40,8 @@ def main():
     for name, kind, dims, variant in cases:
         uid = bcast_id(rank)
         mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+        if name == "replicas":
+            mesh.duplicate(world)
         if name in ("tet3", "hex4-big", "c2-unit"):      # rank-local generation (no rank assembles the mesh): the path bench.py takes
             s = M.Solver.generate_distributed(kind, dims, rank, world, uid, mesh_variant=variant, device=local)
         else:
@@ -59,7 +62,10 @@ def main():
         ex = s.dist_level_info(0)["exchanges"]
         s.close()
         if rank == 0:
-            ref = M.Solver.from_mesh(M.Mesh.generate(kind, dims, mesh_variant=variant), device=local)
+            rmesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+            if name == "replicas":
+                rmesh.duplicate(world)
+            ref = M.Solver.from_mesh(rmesh, device=local)
             rra, rrv = ref.run_cycles(cycles)
             e_rms = float(np.max(np.abs(ra - rra) / rra))
             e_var = 0.0

@@ -33,10 +33,10 @@ def run(tag, **kw):
 
 outs = []
 if what in ("visit", "all"):
-    outs.append(run("visit K=1 resident"))
-    outs.append(run("visit K=1 reload", env=dict(MGCFD_VISIT_RESIDENT=0)))
-    outs.append(run("visit K=2 R=1", env=dict(MGCFD_VISIT_K=2, MGCFD_VISIT_R=1)))
-    outs.append(run("visit K=3", env=dict(MGCFD_VISIT_K=3)))
+    outs.append(run("visit K=1 resident", visit=True))
+    outs.append(run("visit K=1 reload", visit=True, env=dict(MGCFD_VISIT_RESIDENT=0)))
+    outs.append(run("visit K=2 8 warps", visit=True, env=dict(MGCFD_VISIT_K=2, MGCFD_VISIT_WARPS=8)))
+    outs.append(run("visit K=3", visit=True, env=dict(MGCFD_VISIT_K=3)))
 if what in ("stage", "all"):
     outs.append(run("stage TN=128 segment", visit=False, tile_nodes=128))
     outs.append(run("stage TN=256 segment", visit=False, tile_nodes=256))

@@ -17,7 +17,7 @@ levels = [int(x) for x in sys.argv[2:]] or list(range(len(dims)))
 GHZ = 1.965
 for l in levels:
     mesh = M.Mesh.generate(kind, [dims[l]], mesh_variant=variant)
-    s = M.Solver.from_mesh(mesh, use_graph=False)
+    s = M.Solver.from_mesh(mesh, use_graph=False, visit=True)
     vi = s.visit_info(0)
     if not vi["visit"]:
         print(json.dumps({"level": l, "visit": 0}))
@@ -30,7 +30,8 @@ for l in levels:
     out = {"level": l, "nodes": int(np.prod(dims[l])) * (6 if kind == 2 else 1), "cfg": {k: int(v) for k, v in vi.items()}, "premin": os.environ.get("MGCFD_PREMIN", "1"),
            "total_us": us(0, 59), "prologue_to_wait_us": us(0, 1), "min_dt_and_barrier0_arrive_us": us(1, 2),
            "sum_ring_wait_us(thread0)": float(np.median(d[:, 56])) / GHZ / 1e3, "sum_edge_rounds_us(thread0)": float(np.median(d[:, 57])) / GHZ / 1e3,
-           "sum_boundary_update_us(thread0)": float(np.median(d[:, 58])) / GHZ / 1e3, "iterations": []}
+           "sum_boundary_update_us(thread0)": float(np.median(d[:, 58])) / GHZ / 1e3, "sum_produce_us(thread0)": float(np.median(d[:, 62])) / GHZ / 1e3,
+           "sum_tile_prologue_us(thread0)": float(np.median(d[:, 63])) / GHZ / 1e3, "iterations": []}
     for q in range(min(Q, 13)):
         b = 3 + 4 * q
         nxt = (3 + 4 * (q + 1)) if q + 1 < min(Q, 13) else 59

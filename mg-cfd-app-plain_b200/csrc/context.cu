@@ -89,8 +89,9 @@ struct Level {
     int *d_tgt_off = nullptr, *d_tgt_peer = nullptr, *d_tgt_row = nullptr;
     unsigned char* d_tile_sends = nullptr;
     PeerOut* d_peer_out = nullptr;
-    int *d_order_tiles = nullptr, *d_order_blk = nullptr;      // work units in delivery-first order: tiles of TN rows (stage kernels), 128-row blocks (transfers)
-    int n_send_tiles = 0, n_send_blk = 0;
+    int* d_order_tiles = nullptr;                  // tiles in the order the distributed stage kernel takes them (ghost-reading tiles last)
+    unsigned char *d_rblk_wait = nullptr, *d_pblk_wait = nullptr;   // per 128-row block: restrict INTO this level reads a fine ghost row / prolong INTO this level reads a coarse ghost residual
+    int n_send_tiles = 0;
     // the persistent visit kernel (visit_kernel.cuh): one launch per smoothing visit
     bool visit = false;
     int vK = 1, vG = 0, vR = 1, vD = 2, vW = 16, v_resident = 0, v_srmax = 0;
@@ -134,7 +135,8 @@ struct Dist {
     double** d_red_of_rank = nullptr;          // device: [nranks] window reduction bases
     unsigned long long** d_flag_of_rank = nullptr;   // device: [nranks] &window.flags[me]
     unsigned int* d_ticket = nullptr;
-    unsigned int* d_send_ticket = nullptr;     // counts off the CTAs that deliver rows (kernels.cuh dist_send_done)
+    int off = 0;                               // epochs used by kernels enqueued since the last k_epoch_advance (kernels.cuh "Epochs")
+    P2PPeer* d_sig = nullptr; int nsig = 0;    // every neighbour rank (any level): the announcement targets
 };
 constexpr size_t P2P_FLAGS_BYTES = 64 * 8, P2P_RED_BYTES = 2 * 64 * 8 * 8, P2P_HDR_BYTES = P2P_FLAGS_BYTES + P2P_RED_BYTES;
 
@@ -284,9 +286,20 @@ int nccl_load() {
 // multi-GPU with the peer-to-peer plane: the kernels deliver the rows they produce themselves
 bool dist_inkernel(mgcfd_ctx* c) { return c->dist.active && c->dist.p2p; }
 
+// the kernels enqueued since the last advance have used d.off epochs: move the base word on (kernels.cuh "Epochs")
+int dist_flush_epoch(mgcfd_ctx* c) {
+    Dist& d = c->dist;
+    if (!d.p2p || d.off == 0) return MGCFD_OK;
+    k_epoch_advance<<<1, 1, 0, c->stream>>>(d.d_op, d.off);
+    d.off = 0;
+    c->launches++;
+    CK(cudaGetLastError());
+    return MGCFD_OK;
+}
 // global minimum of the per-rank min-dt bit patterns (positive doubles order like their bits)
 int p2p_allreduce(mgcfd_ctx* c, double* vals, int n, int is_min) {
     Dist& d = c->dist;
+    CKRC(dist_flush_epoch(c));      // this kernel works with the absolute epoch
     c->gmin_level = -1;       // the epoch moves on: a minimum a transfer kernel has tagged with its own epoch can no longer be picked up
     k_p2p_allreduce<<<1, 64, 0, c->stream>>>(vals, n, is_min, d.nranks, d.rank, d.d_red_of_rank, d.d_flag_of_rank, (const unsigned long long*)d.win,
                                               (const double*)(d.win + P2P_FLAGS_BYTES), d.d_op, d.d_ctr);
@@ -312,6 +325,7 @@ int p2p_exchange(mgcfd_ctx* c, int l, const double* src, double* dst) {
     Dist& d = c->dist;
     Level& v = c->L[l];
     const double* stage = (const double*)(d.win + P2P_HDR_BYTES) + d.stage_off[l];
+    CKRC(dist_flush_epoch(c));
     c->gmin_level = -1;
     const long work = std::max(v.nsend, v.nghost) * WIDTH;
     const unsigned grid = (unsigned)std::max<long>(1, std::min<long>(blocks_for(work, 256), 2L * c->num_sms));   // resident at once
@@ -545,11 +559,18 @@ int step_factor(mgcfd_ctx* c, int l, int legacy) {
     return MGCFD_OK;
 }
 
+AllRed allred_of(mgcfd_ctx* c);
 int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
     double* out = use_counter ? c->d_rms : c->d_rms + 6 * (c->rms_cap - 1);
     int* counter = use_counter ? c->d_rms_counter : nullptr;
     if (!c->dist.active) {
         k_rms_final<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel, out, counter, c->rms_cap - 1);
+        return post_launch(c);
+    }
+    if (c->dist.p2p) {      // one kernel: local sums, all-reduce over the ranks, square roots
+        CKRC(dist_flush_epoch(c));
+        c->gmin_level = -1;
+        k_rms_dist<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel_global, out, counter, c->rms_cap - 1, allred_of(c), c->dist.d_op);
         return post_launch(c);
     }
     // distributed: local sums of squares -> all-reduce(sum) of 5 doubles -> square roots over the global node count
@@ -593,22 +614,24 @@ DistArgs dist_args(mgcfd_ctx* c, Level& v, const P2PPeer* wait_peers, int nwait)
     da.peers = v.d_peers; da.npeers = v.npeers; da.peer_out = v.d_peer_out;
     da.tgt_off = v.d_tgt_off; da.tgt_peer = v.d_tgt_peer; da.tgt_row = v.d_tgt_row; da.tile_sends = v.d_tile_sends;
     da.wait_peers = wait_peers; da.nwait = nwait;
+    da.sig_peers = d.d_sig; da.nsig = d.nsig;
     da.ar = allred_of(c);
     da.my_flags = (const unsigned long long*)d.win;
-    da.op_counter = d.d_op;
+    da.op_counter = d.d_op; da.epoch_off = d.off;
     return da;
 }
-// `transfer`: the kernel works in 128-row blocks (restrict / prolong), else in the level's tiles (stage kernels)
-DistTail dist_tail(mgcfd_ctx* c, Level& out_level, int ib, const P2PPeer* wait_peers, int nwait, bool transfer) {
+// one epoch per kernel: the tail of a distributed stage / transfer kernel (kernels.cuh "Epochs")
+DistTail dist_tail(mgcfd_ctx* c, Level& out_level, int ib, const P2PPeer* wait_peers, int nwait) {
     DistTail t;
     memset(&t, 0, sizeof(t));
     Dist& d = c->dist;
     t.wait_peers = wait_peers; t.nwait = nwait;
+    t.sig_peers = d.d_sig; t.nsig = d.nsig;
     t.peers = out_level.d_peers; t.npeers = out_level.npeers; t.peer_out = out_level.d_peer_out; t.ib = ib;
     t.tgt_off = out_level.d_tgt_off; t.tgt_peer = out_level.d_tgt_peer; t.tgt_row = out_level.d_tgt_row; t.tile_sends = out_level.d_tile_sends;
-    t.order = transfer ? out_level.d_order_blk : out_level.d_order_tiles;
-    t.n_send = transfer ? out_level.n_send_blk : out_level.n_send_tiles;
-    t.op_counter = d.d_op; t.ticket = d.d_ticket; t.send_ticket = d.d_send_ticket; t.my_flags = (const unsigned long long*)d.win;
+    t.order = out_level.d_order_tiles; t.n_send = out_level.n_send_tiles;
+    t.op_counter = d.d_op; t.epoch_off = d.off++; t.my_flags = (const unsigned long long*)d.win;
+    t.ticket = d.d_ticket;
     t.ar = allred_of(c);
     t.dbg = env_int("MGCFD_DIST_DEBUG", 0);
     return t;
@@ -638,7 +661,7 @@ int smooth_visit(mgcfd_ctx* c, int l) {
         a.nel_global = (double)(c->dist.active ? v.nel_global : v.nel);
     }
     const bool dist = dist_inkernel(c);
-    if (dist) a.d = dist_args(c, v, v.d_peers, v.npeers);
+    if (dist) { a.d = dist_args(c, v, v.d_peers, v.npeers); c->dist.off += 4; }      // barrier 0, two stage barriers, the end signal
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)v.vG); cfg.blockDim = dim3(512); cfg.dynamicSmemBytes = v.v_smem; cfg.stream = c->stream;
@@ -709,7 +732,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
         if (j == 0 && use_premin) { a.premin = v.blockmins; a.npremin = (int)blocks_for(v.ncomp, 128); }
         if (deliver) {
             const int ib = (a.vout == v.buf[0]) ? 0 : (a.vout == v.buf[1] ? 1 : 2);
-            a.d = dist_tail(c, v, ib, v.d_peers, v.npeers, false);
+            a.d = dist_tail(c, v, ib, v.d_peers, v.npeers);
             a.d.recv_min = (j == 0 && recv_min) ? 1 : 0;
             CKRC(launch_stage_dist(c, v, a));
             c->dist.exchanges++;
@@ -736,7 +759,8 @@ int do_restrict(mgcfd_ctx* c, int lc) {
     double* bm = (c->variant != MGCFD_MESH_FVCORR && env_int("MGCFD_PREMIN", 1)) ? vc.blockmins : nullptr;
     if (dist_inkernel(c)) {
         // reads the fine level's ghost rows (wait for the fine level's peers), delivers the coarse rows itself
-        DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers, true);
+        DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers);
+        t.blk_wait = vc.d_rblk_wait;
         if (vc.visit || !vc.pipe) bm = nullptr;             // only a level whose stage kernels deliver their rows themselves picks the minimum up
         if (bm) { t.blockmins = bm; t.nblocks = (int)nb; t.send_min = 1; }
         k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, t);
@@ -761,7 +785,9 @@ int do_prolong(mgcfd_ctx* c, int lf) {
         // the coarse residuals of ghost parents were delivered by the coarse visit's last stage when that level runs the visit
         // kernel; otherwise they are exchanged here.  The prolonged rows are delivered by the kernel itself.
         if (!vc.visit && !vc.pipe) CKRC(dist_exchange_residuals(c, lf + 1));
-        DistTail t = dist_tail(c, vf, vf.i_var, vc.d_peers, vc.npeers, true);
+        DistTail t = dist_tail(c, vf, vf.i_var, vc.d_peers, vc.npeers);
+        // (when the coarse level's residuals came through an exchange kernel just above, every block may run at once)
+        t.blk_wait = vf.d_pblk_wait;
         if (vf.visit || !vf.pipe) bm = nullptr;
         if (bm) { t.blockmins = bm; t.nblocks = (int)nb; t.send_min = 1; }
         k_prolong<true><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
@@ -785,11 +811,11 @@ int do_prolong(mgcfd_ctx* c, int lf) {
 int cycle_fused(mgcfd_ctx* c) {
     const int nl = c->levels;
     CKRC(smooth_fused(c, 0));
-    if (nl == 1) return MGCFD_OK;
+    if (nl == 1) return dist_flush_epoch(c);
     for (int l = 1; l < nl; l++) { CKRC(do_restrict(c, l)); CKRC(smooth_fused(c, l)); }
     for (int l = nl - 2; l >= 1; l--) { CKRC(do_prolong(c, l)); CKRC(smooth_fused(c, l)); }
     CKRC(do_prolong(c, 0));
-    return MGCFD_OK;
+    return dist_flush_epoch(c);
 }
 
 std::string role_key(mgcfd_ctx* c) {
@@ -828,7 +854,7 @@ void free_level(Level& v) {
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
                     v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers,
                     v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_out, v.ewt_pre, v.d_desc, v.d_vslots, v.d_cta_rows, v.d_hsum,
-                    v.d_order_tiles, v.d_order_blk};
+                    v.d_order_tiles, v.d_rblk_wait, v.d_pblk_wait};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -995,7 +1021,7 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
     for (int p = 0; p < (int)c->dist.peer_win.size(); p++) if (p != c->dist.rank && c->dist.peer_win[p]) cudaIpcCloseMemHandle(c->dist.peer_win[p]);
     cudaFree(c->d_visit_dbg); cudaFree(c->slab); cudaFree(c->d_bar); cudaFree(c->d_cta_min); cudaFree(c->d_cta_rms);
-    cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_send_ticket); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
+    cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_sig); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -1182,6 +1208,18 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         CKRC(dev_upload(&vc.child_off, T.child_off, s)); CKRC(dev_upload(&vc.child_ids, T.child_ids, s));
         CKRC(dev_upload(&vf.parent, T.parent, s)); CKRC(dev_upload(&vf.idist_own, T.idist_own, s));
         CKRC(dev_upload(&vf.ent_off, T.ent_off, s)); CKRC(dev_upload(&vf.ent_src, T.ent_src, s)); CKRC(dev_upload(&vf.ent_w, T.ent_w, s));
+        if (c->dist.active) {
+            // which 128-row blocks of the transfer kernels read rows other ranks own: only those wait for the owners' epoch
+            std::vector<unsigned char> rw(std::max<long>(1, blocks_for(vc.ncomp, 128)), 0), pw(std::max<long>(1, blocks_for(vf.ncomp, 128)), 0);
+            for (long cc = 0; cc < vc.ncomp; cc++)
+                for (long k = T.child_off[cc]; k < T.child_off[cc + 1]; k++) if (T.child_ids[k] >= vf.ncomp) { rw[cc / 128] = 1; break; }
+            for (long i = 0; i < vf.ncomp; i++) {
+                bool g = T.parent[i] >= vc.ncomp;
+                for (long k = T.ent_off[i]; k < T.ent_off[i + 1] && !g; k++) g = T.ent_src[k] >= vc.ncomp;
+                if (g) pw[i / 128] = 1;
+            }
+            CKRC(dev_upload(&vc.d_rblk_wait, rw, s)); CKRC(dev_upload(&vf.d_pblk_wait, pw, s));
+        }
         CK(cudaStreamSynchronize(s));
     }
     CK(cudaStreamSynchronize(s));
@@ -1292,12 +1330,14 @@ int mgcfd_check_for_invalid_variables(mgcfd_ctx* c, int l, long* first_bad_cell,
 int mgcfd_mg_restrict(mgcfd_ctx* c, int lc) {
     CKRC(check_level(c, lc));
     if (lc < 1) { g_err = "coarse_level must be >= 1"; return MGCFD_ERR_ARG; }
-    return do_restrict(c, lc);
+    CKRC(do_restrict(c, lc));
+    return dist_flush_epoch(c);
 }
 int mgcfd_prolong(mgcfd_ctx* c, int lf) {
     CKRC(check_level(c, lf));
     if (lf >= c->levels - 1) { g_err = "fine_level must have a coarser level"; return MGCFD_ERR_ARG; }
-    return do_prolong(c, lf);
+    CKRC(do_prolong(c, lf));
+    return dist_flush_epoch(c);
 }
 
 // ---- fused path ----------------------------------------------------------------------------------------
@@ -1767,8 +1807,7 @@ int mgcfd_dist_p2p_prepare(mgcfd_ctx* c, char handle[64], long* table, long tabl
     if (table_cap < need) { g_err = "table too small"; return MGCFD_ERR_ARG; }
     CK(cudaSetDevice(c->opt.device));
     if (!d.d_op) {
-        CK(cudaMalloc((void**)&d.d_ticket, 4)); CK(cudaMemset(d.d_ticket, 0, 4));
-        CK(cudaMalloc((void**)&d.d_send_ticket, 4)); CK(cudaMemset(d.d_send_ticket, 0, 4));
+        CK(cudaMalloc((void**)&d.d_ticket, 4 * 4096)); CK(cudaMemset(d.d_ticket, 0, 4 * 4096));      // [0] + one word per group of 32 blocks
         CK(cudaMalloc((void**)&d.d_op, 8)); CK(cudaMemset(d.d_op, 0, 8));
         CK(cudaMalloc((void**)&d.d_ctr, 4 * (c->levels + 1))); CK(cudaMemset(d.d_ctr, 0, 4 * (c->levels + 1)));
         CK(cudaDeviceSynchronize());
@@ -1794,6 +1833,7 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
     if (!c || !handles || !tables) { g_err = "null argument"; return MGCFD_ERR_ARG; }
     Dist& d = c->dist;
     if (!d.active || !d.win || !d.d_op) { g_err = "mgcfd_dist_p2p_prepare has not been called"; return MGCFD_ERR_ARG; }
+    d.off = 0;
     if (table_len != mgcfd_dist_p2p_table_len(c)) { g_err = "table length does not match this build of the library"; return MGCFD_ERR_COMM; }
     CK(cudaSetDevice(c->opt.device));
     d.peer_win.assign(d.nranks, nullptr);
@@ -1854,21 +1894,36 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
         CKRC(dev_upload(&v.d_tgt_off, st.off, c->stream)); CKRC(dev_upload(&v.d_tgt_peer, st.peer, c->stream)); CKRC(dev_upload(&v.d_tgt_row, st.row, c->stream));
         CKRC(dev_upload(&v.d_tile_sends, st.tile_sends, c->stream));
         if (v.pipe) { CKRC(setup_pipe_dist(c, v)); if (v.pipe_grid_dist < 1) v.pipe = false; }
-        // work units in delivery-first order (stable: units that own rows on send lists, then the others)
-        auto order_of = [&](int unit, std::vector<int>& order) {
-            const long nu = (v.ncomp + unit - 1) / unit;
+        // tiles in the order the stage kernel takes them: the tiles that own rows on send lists -- the only ones that read ghost
+        // rows, flux halos being symmetric -- LAST (stable otherwise)
+        {
+            const long nu = (v.ncomp + v.TN - 1) / v.TN;
             std::vector<char> sends(nu, 0);
-            for (long r = 0; r < v.ncomp; r++) if (st.off[r + 1] > st.off[r]) sends[r / unit] = 1;
-            order.clear();
-            for (long u = 0; u < nu; u++) if (sends[u]) order.push_back((int)u);
-            const int ns = (int)order.size();
+            for (long r = 0; r < v.ncomp; r++) if (st.off[r + 1] > st.off[r]) sends[r / v.TN] = 1;
+            // a tile that reads a ghost row without owning a sent row would break the late wait: check the halo lists
+            for (long t = 0; t < (long)v.plan.ntiles && t < nu; t++)
+                for (long k = v.plan.halo_off[t]; k < v.plan.halo_off[t + 1]; k++) if (v.plan.halo_ids[k] >= v.ncomp) sends[t] = 1;
+            std::vector<int> order;
             for (long u = 0; u < nu; u++) if (!sends[u]) order.push_back((int)u);
-            return ns;
-        };
-        std::vector<int> ot, ob;
-        v.n_send_tiles = order_of(v.TN, ot);
-        v.n_send_blk = order_of(128, ob);
-        CKRC(dev_upload(&v.d_order_tiles, ot, c->stream)); CKRC(dev_upload(&v.d_order_blk, ob, c->stream));
+            v.n_send_tiles = (int)(nu - (long)order.size());
+            for (long u = 0; u < nu; u++) if (sends[u]) order.push_back((int)u);
+            CKRC(dev_upload(&v.d_order_tiles, order, c->stream));
+        }
+    }
+    {   // every neighbour rank of this rank, whatever the level: who is told at the start of a kernel that the previous one is complete
+        std::vector<P2PPeer> sig;
+        for (int p = 0; p < d.nranks; p++) {
+            if (p == d.rank) continue;
+            bool nb = false;
+            for (int l = 0; l < c->levels; l++) for (const P2PPeer& e : c->L[l].h_peers) if (e.rank == p) nb = true;
+            if (!nb) continue;
+            P2PPeer e;
+            memset(&e, 0, sizeof(e));
+            e.rank = p; e.flag = (unsigned long long*)d.peer_win[p] + d.rank;
+            sig.push_back(e);
+        }
+        d.nsig = (int)sig.size();
+        CKRC(dev_upload(&d.d_sig, sig, c->stream));
     }
     CK(cudaStreamSynchronize(c->stream));
     d.p2p = true;

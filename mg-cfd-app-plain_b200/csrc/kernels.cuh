@@ -246,87 +246,91 @@ __device__ __forceinline__ void dist_allreduce(const AllRed& d, unsigned long lo
     }
     __syncwarp();
 }
+// Epochs.  Every kernel of a distributed run that produces rows other ranks hold copies of owns one epoch number; all ranks run the
+// same kernel sequence, so the numbers agree.  epoch = *op_counter (a base word on the device, advanced by the host-enqueued
+// k_epoch_advance once per V-cycle) + epoch_off (baked into the launch): a replayed CUDA graph needs no per-launch argument.
+// A kernel with epoch e
+//   * ANNOUNCES, at its start, that this rank's kernels up to e - 1 are complete: block 0 writes e into flags[me] of every
+//     neighbour rank.  The completion of a grid makes its stores -- remote ones included -- visible before the next grid of the
+//     stream starts, so nothing has to be fenced or counted inside the producing kernel (the first versions did: a system-scope
+//     fence per CTA and a grid-wide ticket per kernel cost more than the NVLink latency they guarded, profiles/r02t_distperf.jsonl);
+//   * WAITS until flags[p] >= e for the ranks p it reads ghost rows of -- as late as it can: the stage kernel takes the tiles that
+//     read no ghost row first and checks the flags only before it prefetches its first ghost-reading tile, so the one-way flag
+//     latency (3.2 us, profiles/r02q_p2p_pingpong.txt) hides behind interior tiles;
+//   * stores the rows it produces straight into the peers' copies (dist_push_rec / dist_push_res).
 struct DistTail {
     const P2PPeer* wait_peers; int nwait;      // whose rows this kernel reads
-    const P2PPeer* peers; int npeers;          // who holds copies of the rows it writes
+    const P2PPeer* sig_peers; int nsig;        // every neighbour rank of this rank (any level): who gets the announcement
+    const P2PPeer* peers; int npeers;          // who holds copies of the rows it writes (index space of tgt_peer)
     const PeerOut* peer_out; int ib;           // the peers' record buffer that mirrors the output buffer
     const int* tgt_off; const int* tgt_peer; const int* tgt_row;      // row -> (peer index, row in the peer's arrays)
     const unsigned char* tile_sends;           // per tile of the kernel's granularity: any row with a target
-    // Work units (tiles of the stage kernel, 128-row blocks of the transfer kernels) are taken in `order`: the n_send units that own
-    // rows other ranks hold copies of come FIRST; the CTAs that own such units count themselves off on send_ticket when their last
-    // one is done, and the last of them signals the peers -- while the interior units are still being computed.  The epoch number
-    // itself (op_counter) advances when the whole grid is done (ticket).
-    const int* order; int n_send;
-    unsigned long long* op_counter; unsigned int* ticket; unsigned int* send_ticket; const unsigned long long* my_flags;
-    // the minimum dt of the state a transfer kernel leaves behind: its last CTA reduces the per-block minima and SENDS the rank's
-    // minimum, tagged with the epoch, into every rank's reduction slot (send_min); the first stage kernel of the next smoothing visit
-    // waits for the tags and combines the values itself (recv_min) -- nobody blocks inside the transfer kernel
+    const int* order; int n_send;              // stage kernels: tiles in the order they are taken, the n_send ghost-reading (= delivering) tiles LAST
+    const unsigned char* blk_wait;             // transfer kernels: per 128-row block, does it read a ghost row (only those blocks wait); nullptr: all wait
+    const unsigned long long* op_counter; int epoch_off; const unsigned long long* my_flags;
+    // the minimum dt of the state a transfer kernel leaves behind: its last CTA (ticket) reduces the per-block minima and SENDS the
+    // rank's minimum, tagged with the epoch, into every rank's reduction slot (send_min); the first stage kernel of the next
+    // smoothing visit waits for the tags and combines the values itself (recv_min) -- nobody blocks inside the transfer kernel
+    unsigned int* ticket;
     AllRed ar; const double* blockmins; int nblocks; int send_min, recv_min;
-    int dbg;       // measurement only (MGCFD_DIST_DEBUG, results become wrong): 1 no start wait, 2 no remote stores, 4 no early signal, 8 no signal at all
+    int dbg;       // measurement only (MGCFD_DIST_DEBUG, results become wrong): 1 no waits, 2 no remote stores, 8 no announcements
 };
-__device__ __forceinline__ unsigned long long dist_kernel_begin(const DistTail& d) {
-    const unsigned long long e0 = *(volatile unsigned long long*)d.op_counter;
+__device__ __forceinline__ void dist_wait(const DistTail& d, unsigned long long e0) {
     if ((int)threadIdx.x < d.nwait && !(d.dbg & 1)) {
         const unsigned long long* f = d.my_flags + d.wait_peers[threadIdx.x].rank;
         unsigned spins = 0;
-        while (ld_acquire_sys(f) < e0) { if (spin_expired(spins, "kernel start: peer epoch")) break; }
+        while (ld_acquire_sys(f) < e0) { if (spin_expired(spins, "peer epoch")) break; }
     }
     __syncthreads();
+}
+// start of a distributed kernel: the epoch, the announcement (block 0) and -- unless the caller waits later -- the wait
+__device__ __forceinline__ unsigned long long dist_kernel_begin(const DistTail& d, bool wait_now) {
+    const unsigned long long e0 = *(volatile const unsigned long long*)d.op_counter + (unsigned long long)d.epoch_off;
+    if (blockIdx.x == 0 && (int)threadIdx.x < d.nsig && !(d.dbg & 8)) st_release_sys(d.sig_peers[threadIdx.x].flag, e0);
+    if (wait_now) dist_wait(d, e0);
     return e0;
 }
-// a CTA has finished the last of its units that deliver rows to other ranks (call after a __syncthreads that follows those units):
-// the last such CTA signals epoch e0 + 1 to the peers.  nsenders = CTAs that own at least one sending unit.
-__device__ __forceinline__ void dist_send_done(const DistTail& d, unsigned long long e0, unsigned nsenders) {
-    if (threadIdx.x == 0 && !(d.dbg & 12)) {
-        __threadfence_system();              // this CTA's remote stores (ordered before by the barrier) are delivered before ...
-        if (atomicInc(d.send_ticket, nsenders - 1) == nsenders - 1) {
-            __threadfence_system();
-            for (int p = 0; p < d.npeers; p++) st_release_sys(d.peers[p].flag, e0 + 1);      // ... the signal
-        }
-    }
-}
-// end of a distributed kernel: the last CTA of the whole grid advances the epoch; it signals the peers if no CTA had anything to
-// deliver (they wait for the epoch all the same) and, for a transfer kernel, sends the rank's minimum dt to every rank
-__device__ __forceinline__ void dist_kernel_end(const DistTail& d, unsigned long long e0, unsigned nsenders) {
+// end of a transfer kernel that owes the next smoothing visit its minimum dt: the last CTA reduces the block minima and sends
+__device__ __forceinline__ void dist_send_min(const DistTail& d, unsigned long long e0) {
     __shared__ int s_last;
     __shared__ double s_wm[32];
     __syncthreads();
     if (threadIdx.x == 0) {
+        // two-level ticket (groups of 32 blocks, then the groups): thousands of blocks counting off on ONE word serialise in L2
         __threadfence();
-        s_last = (atomicInc(d.ticket, gridDim.x - 1) == gridDim.x - 1);
+        const unsigned grp = blockIdx.x >> 5, ngrp = (gridDim.x + 31) >> 5;
+        const unsigned gsize = min(32u, gridDim.x - (grp << 5));
+        s_last = 0;
+        if (atomicInc(d.ticket + 1 + grp, gsize - 1) == gsize - 1) {
+            __threadfence();
+            s_last = (atomicInc(d.ticket, ngrp - 1) == ngrp - 1);
+        }
     }
     __syncthreads();
     if (!s_last) return;
-    if (d.send_min) {
-        __threadfence();
-        double v = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
-        for (int b = threadIdx.x; b < d.nblocks; b += blockDim.x) v = fmin(v, __ldcg(d.blockmins + b));
+    __threadfence();
+    double v = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
+    for (int b = threadIdx.x; b < d.nblocks; b += blockDim.x) v = fmin(v, __ldcg(d.blockmins + b));
+#pragma unroll
+    for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
+    if ((threadIdx.x & 31) == 0) s_wm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = (threadIdx.x < (blockDim.x >> 5)) ? s_wm[threadIdx.x] : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
 #pragma unroll
         for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
-        if ((threadIdx.x & 31) == 0) s_wm[threadIdx.x >> 5] = v;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            v = (threadIdx.x < (blockDim.x >> 5)) ? s_wm[threadIdx.x] : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
-#pragma unroll
-            for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
-            const int parity = int(*(volatile unsigned int*)d.ar.red_counter & 1u);
-            for (int p = threadIdx.x; p < d.ar.nranks; p += 32) {
-                double* slot = d.ar.red_of_rank[p] + ((size_t)parity * 64 + d.ar.me) * 8;
-                slot[0] = v;
-                st_release_sys(reinterpret_cast<unsigned long long*>(slot + 1), e0 + 1);      // the tag: value delivered
-            }
-            __syncwarp();
-            if (threadIdx.x == 0) *d.ar.red_counter += 1;
+        const int parity = int(*(volatile unsigned int*)d.ar.red_counter & 1u);
+        for (int p = threadIdx.x; p < d.ar.nranks; p += 32) {
+            double* slot = d.ar.red_of_rank[p] + ((size_t)parity * 64 + d.ar.me) * 8;
+            slot[0] = v;
+            st_release_sys(reinterpret_cast<unsigned long long*>(slot + 1), e0 + 1);      // the tag: value delivered (same thread: ordered by the release)
         }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        if ((nsenders == 0 || (d.dbg & 4)) && !(d.dbg & 8)) { __threadfence_system(); for (int p = 0; p < d.npeers; p++) st_release_sys(d.peers[p].flag, e0 + 1); }
-        *d.op_counter = e0 + 1;
+        __syncwarp();
+        if (threadIdx.x == 0) *d.ar.red_counter += 1;
     }
 }
 // first stage of a smoothing visit: the minimum over the ranks of the values their last transfer kernel sent (tag = this kernel's
-// starting epoch); every thread returns the minimum
+// epoch); every thread returns the minimum
 __device__ __forceinline__ double dist_recv_min(const DistTail& d, unsigned long long e0) {
     __shared__ unsigned long long s_min;
     if (threadIdx.x < 32) {
@@ -346,6 +350,8 @@ __device__ __forceinline__ double dist_recv_min(const DistTail& d, unsigned long
     __syncthreads();
     return __longlong_as_double((long long)s_min);
 }
+// advances the epoch base by the epochs the kernels enqueued since the last advance have used (one thread, enqueued by the host)
+__global__ void k_epoch_advance(unsigned long long* op_counter, int n) { *op_counter += (unsigned long long)n; }
 __device__ __forceinline__ void dist_push_rec(const DistTail& d, long row, const Rec& n) {
     if (d.dbg & 2) return;
     for (int k = d.tgt_off[row]; k < d.tgt_off[row + 1]; k++) store_rec(d.peer_out[d.tgt_peer[k]].rec[d.ib], d.tgt_row[k], n);
@@ -650,10 +656,23 @@ k_stage_pipe(const StageArgs a) {
     }
     __syncthreads();
 
-    // DIST: tiles are taken in an order that puts the tiles with rows on send lists first (DistTail::order)
-    auto tile_of = [&](int it) -> long { const long k = (long)blockIdx.x + (long)it * G; return DIST ? (long)a.d.order[k] : k; };
-    const unsigned nsenders = DIST ? unsigned(min(a.d.n_send, G)) : 0u;
-    const int my_send_iters = (DIST && (int)blockIdx.x < a.d.n_send) ? (a.d.n_send - (int)blockIdx.x + G - 1) / G : 0;
+    // DIST: tiles are taken in an order that puts the tiles that read ghost rows (= the tiles that deliver rows) LAST (DistTail::order):
+    // the CTA checks the peers' flags only before it prefetches the records of its first such tile
+    // (the CTA's slice of the order table is staged in shared memory by the static prologue: a global load per tile_of() call sat
+    // on the header-prefetch chain of every tile, profiles/r02u_distperf.jsonl)
+    constexpr int ORDER_CACHE = 96;
+    __shared__ int s_order[DIST ? ORDER_CACHE : 1];
+    if (DIST) {
+        for (int k = t; k < my_count && k < ORDER_CACHE; k += TN) s_order[k] = a.d.order[(long)blockIdx.x + (long)k * G];
+        __syncthreads();
+    }
+    auto tile_of = [&](int it) -> long {
+        const long k = (long)blockIdx.x + (long)it * G;
+        if (!DIST) return k;
+        return it < ORDER_CACHE ? (long)s_order[it] : (long)a.d.order[k];
+    };
+    const long first_ghost_pos = DIST ? (long)a.ntiles - a.d.n_send : 0;
+    bool waited = false;
     auto hdr_of = [&](int it) -> const TileHdr* { return reinterpret_cast<const TileHdr*>(hdrs + (it % 3) * (size_t)a.hdr_stride); };
     auto copy_hdr = [&](int it) {
         if (it >= my_count) return;
@@ -711,15 +730,18 @@ k_stage_pipe(const StageArgs a) {
     if (t == 0) produce(1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
     unsigned long long e0 = 0;
-    if (DIST) e0 = dist_kernel_begin(a.d);       // ghost rows of vin were delivered by their owners' previous kernel: wait for its epoch
+    if (DIST) {
+        e0 = dist_kernel_begin(a.d, false);
+        if ((long)blockIdx.x >= first_ghost_pos) { dist_wait(a.d, e0); waited = true; }      // the very first tile already reads ghost rows
+    }
     copy_recs(0);
     const bool first_stage = (a.vold == a.vin);
     // the visit's global minimum dt: *min_bits (k_min_dt, or -- multi-GPU -- the all-reduce at the end of the transfer kernel that
     // produced this state), or the per-block minima that transfer kernel left behind, reduced here by every CTA for itself
     double min_dt = 0.0;
-    if (first_stage && !a.legacy) {
-        if (DIST && a.d.recv_min) min_dt = dist_recv_min(a.d, e0);
-        else if (a.premin) {
+    const bool recv_min_late = DIST && first_stage && !a.legacy && a.d.recv_min;      // picked up before the first update, behind the first edge rounds
+    if (first_stage && !a.legacy && !recv_min_late) {
+        if (a.premin) {
             double v = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
             for (int b = t; b < a.npremin; b += TN) v = fmin(v, __ldcg(a.premin + b));
 #pragma unroll
@@ -740,6 +762,7 @@ k_stage_pipe(const StageArgs a) {
         const TileHdr* hd = hdr_of(it);
         copy_hdr(it + 2);
         mbar_wait(&bar_recs[it & 1], (it >> 1) & 1);       // records of T_it and the header of T_{it+1} have landed
+        if (DIST && !waited && it + 1 < my_count && (long)blockIdx.x + (long)(it + 1) * G >= first_ghost_pos) { dist_wait(a.d, e0); waited = true; }
         copy_recs(it + 1);
         if (t == 0) produce(it + 1);
         // early loads for the epilogue: volume (first stage) or the stored step factor (later stages), the old state, and the
@@ -782,15 +805,14 @@ k_stage_pipe(const StageArgs a) {
         }
         boundary_rounds<TN>(bblk, brounds, t, a.mask, me, f, b0);
         if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
+        if (DIST && recv_min_late && it == 0) min_dt = dist_recv_min(a.d, e0);       // the ranks' minima, sent by their last transfer kernel
         double sf = vol_or_sf;
         if (first_stage) { sf = step_factor_of(a, min_dt, vol_or_sf, me.s); a.sf[gid] = sf; }
         double q[5] = {0, 0, 0, 0, 0};
         fused_update<DIST>(a, gid, sf, o, f, q, DIST && a.d.tile_sends[tile] != 0);
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
         __syncthreads();      // record buffer (it & 1), header buffer (it % 3), acc and ws are free again
-        if (DIST && it == my_send_iters - 1) dist_send_done(a.d, e0, nsenders);      // this CTA's last delivering tile: the interior tiles follow
     }
-    if (DIST) dist_kernel_end(a.d, e0, nsenders);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -987,8 +1009,8 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
                            const long* __restrict__ child_off, const int* __restrict__ child_ids, const double* __restrict__ vol_root,
                            double* __restrict__ blockmins, const DistTail d) {
     unsigned long long e0 = 0;
-    if (DIST) e0 = dist_kernel_begin(d);
-    const long c = (DIST ? (long)d.order[blockIdx.x] : (long)blockIdx.x) * (long)blockDim.x + threadIdx.x;      // DIST: delivering blocks first
+    if (DIST) e0 = dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks with ghost children wait for the fine level's owners
+    const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double s_new = 0.0;          // |v| + c of the node's state after this kernel
     if (c < ncoarse) {
         const long k0 = child_off[c], k1 = child_off[c + 1];
@@ -1013,10 +1035,7 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
         }
     }
     if (blockmins) block_min_store(c < ncoarse ? 0.5 * (vol_root[c] / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), blockmins);
-    if (DIST) {
-        if ((int)blockIdx.x < d.n_send) { __syncthreads(); dist_send_done(d, e0, (unsigned)d.n_send); }
-        dist_kernel_end(d, e0, (unsigned)d.n_send);
-    }
+    if (DIST && d.send_min) dist_send_min(d, e0);
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
 // edges in original edge order: per edge the own-parent term then the neighbour-parent term (whose source is the own
@@ -1027,8 +1046,8 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
                           const double* __restrict__ res_c, const double* __restrict__ res_f, double* __restrict__ var_f,
                           const double* __restrict__ vol_root, double* __restrict__ blockmins, const DistTail d) {
     unsigned long long e0 = 0;
-    if (DIST) e0 = dist_kernel_begin(d);
-    const long i = (DIST ? (long)d.order[blockIdx.x] : (long)blockIdx.x) * (long)blockDim.x + threadIdx.x;      // DIST: delivering blocks first
+    if (DIST) e0 = dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks that read a ghost parent's residual wait
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int p = (i < nfine) ? parent[i] : -1;
     double dt_new = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);      // padding rows (no parent) never win the minimum
     if (p >= 0) {
@@ -1071,10 +1090,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
         if (DIST) dist_push_rec(d, i, n);
     }
     if (blockmins) block_min_store(dt_new, blockmins);
-    if (DIST) {
-        if ((int)blockIdx.x < d.n_send) { __syncthreads(); dist_send_done(d, e0, (unsigned)d.n_send); }
-        dist_kernel_end(d, e0, (unsigned)d.n_send);
-    }
+    if (DIST && d.send_min) dist_send_min(d, e0);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1238,6 +1254,43 @@ __global__ void k_p2p_allreduce(double* __restrict__ vals, int n, int is_min, in
         }
     }
     if (t == 0) { *op_counter = g; *red_counter += 1; }
+}
+
+// calc_rms of a distributed run in ONE kernel (one block): local sums of the per-tile partials in index order, all-reduce(sum) of the
+// five sums over the ranks (k_p2p_allreduce's protocol, absolute epoch), square roots over the global node count
+__global__ void k_rms_dist(const double* __restrict__ partial, long nparts, double nel_global, double* __restrict__ out, int* counter, int cap,
+                           const AllRed ar, unsigned long long* op_counter) {
+    __shared__ double ws[5][256];
+    __shared__ double sums[8];
+    const int t = threadIdx.x;
+    double s[5] = {0, 0, 0, 0, 0};
+    for (long p = t; p < nparts; p += 256)
+#pragma unroll
+        for (int k = 0; k < 5; k++) s[k] += partial[p * 5 + k];
+#pragma unroll
+    for (int k = 0; k < 5; k++) ws[k][t] = s[k];
+    __syncthreads();
+    if (t < 5) {
+        double acc = 0.0;
+        for (int j = 0; j < 256; j++) acc += ws[t][j];
+        sums[t] = acc;
+    }
+    __syncthreads();
+    if (t < 32) {
+        const unsigned long long g = *(volatile unsigned long long*)op_counter + 1;
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 5; k++) v[k] = sums[k];
+        dist_allreduce(ar, g, v, 5, false);
+        if (t == 0) {
+            int slot = 0;
+            if (counter) { slot = *counter; *counter = slot + 1; if (slot >= cap) slot = cap - 1; }
+            double tot = 0.0;
+            for (int k = 0; k < 5; k++) { out[slot * 6 + 1 + k] = sqrt(v[k] / nel_global); tot += v[k]; }
+            out[slot * 6] = sqrt(tot / nel_global);
+            *op_counter = g;
+        }
+    }
 }
 
 // calc_rms split around an all-reduce: local sums of squares, then the roots over the global node count

@@ -46,11 +46,12 @@ struct DistArgs {
     const PeerOut* peer_out;
     const int* tgt_off; const int* tgt_peer; const int* tgt_row;       // node -> (peer index, row in the peer's arrays)
     const unsigned char* tile_sends;                                    // per tile: any node with a target
-    // start-of-kernel wait (may be another level's peers)
+    // start-of-kernel wait (may be another level's peers) and the announcement targets (kernels.cuh "Epochs")
     const P2PPeer* wait_peers; int nwait;
+    const P2PPeer* sig_peers; int nsig;
     AllRed ar;                                                          // all-reduce plumbing (kernels.cuh)
     const unsigned long long* my_flags;
-    unsigned long long* op_counter;
+    const unsigned long long* op_counter; int epoch_off;                // epoch of the kernel's first synchronisation = *op_counter + epoch_off (kernels.cuh)
 };
 
 struct VisitArgs {
@@ -298,7 +299,8 @@ k_visit(const VisitArgs a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     unsigned long long E0 = 0;
     if (DIST) {
-        E0 = *(volatile unsigned long long*)a.d.op_counter;
+        E0 = *(volatile const unsigned long long*)a.d.op_counter + (unsigned long long)a.d.epoch_off;
+        if (c == 0 && t < a.d.nsig) st_release_sys(a.d.sig_peers[t].flag, E0);      // this rank's kernels up to E0 - 1 are complete
         if (t < a.d.nwait) {
             const unsigned long long* f = a.d.my_flags + a.d.wait_peers[t].rank;
             unsigned spins = 0;
@@ -556,7 +558,6 @@ k_visit(const VisitArgs a) {
                     dist_signal_wait_peers(a.d, E0 + nsync + 1, false);
                 }
                 if (t == 0) {
-                    if (DIST) *a.d.op_counter = E0 + nsync + 1;
                     __threadfence();
                     atomicAdd(a.bar, 0x10000u - unsigned(G));
                 }

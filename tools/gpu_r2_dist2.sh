@@ -15,6 +15,7 @@ run p2p_mixed MGCFD_VISIT=1 MGCFD_VISIT_MAX_NODES=3000
 run nccl MGCFD_NO_P2P=1
 fi
 if [ "$2" = "mixed" ]; then
+run p2p_visit MGCFD_VISIT=1
 run p2p_mixed MGCFD_VISIT=1 MGCFD_VISIT_MAX_NODES=3000
 fi
 timeout -k 10 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29911 bench.py --gpus 2 --steps 50 --warmup 5 --no-cpu-baseline --no-north-star > gpurun_out/${T}_bench_n2.json 2> gpurun_out/${T}_bench_n2.err; echo "bench n2 rc=$?"; tail -5 gpurun_out/${T}_bench_n2.err

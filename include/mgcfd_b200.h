@@ -87,6 +87,14 @@ typedef struct mgcfd_options {
 void mgcfd_default_options(mgcfd_options* opt);
 const char* mgcfd_last_error(void);
 const char* mgcfd_version(void);
+/* Debugging aid (no reference counterpart).  With MGCFD_GUARD=1 in the environment when contexts are created, every device
+   allocation of the library is bracketed by 64 KB zones of a known byte pattern; this call reads the zones of all live contexts
+   back and returns how many were written to (0 = no kernel wrote past the end or before the start of an array), with a short
+   description of each in report[0..cap).  Without MGCFD_GUARD it returns 0. */
+int mgcfd_guard_check(char* report, int cap);
+/* the check's own test: damages one guard zone of the context (one byte, 100 bytes past the end of a 64-byte array); an error
+   unless the context was created under MGCFD_GUARD=1 */
+int mgcfd_guard_selftest(mgcfd_ctx* ctx);
 
 /* ---- lifetime --------------------------------------------------------------------------------- */
 /* replaces the per-level array set-up in main() (euler3d_cpu_double.cpp:138-243) */

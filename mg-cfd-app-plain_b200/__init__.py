@@ -57,6 +57,10 @@ def lib() -> C.CDLL:
     L = C.CDLL(LIB_PATH)
     vp, i, l, dp = C.c_void_p, C.c_int, C.c_long, C.POINTER(C.c_double)
     L.mgcfd_last_error.restype = C.c_char_p
+    L.mgcfd_guard_check.restype = C.c_int
+    L.mgcfd_guard_check.argtypes = [C.c_char_p, C.c_int]
+    L.mgcfd_guard_selftest.restype = C.c_int
+    L.mgcfd_guard_selftest.argtypes = [C.c_void_p]
     L.mgcfd_mesh_last_error.restype = C.c_char_p
     L.mgcfd_version.restype = C.c_char_p
     L.mgcfd_default_options.argtypes = [C.POINTER(Options)]
@@ -460,6 +464,14 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+def guard_check():
+    """(number of damaged guard zones, description) over all live solvers; needs MGCFD_GUARD=1 in the environment when the solvers
+    were created (mgcfd_guard_check, include/mgcfd_b200.h) -- the library's stand-in for a memcheck run."""
+    buf = C.create_string_buffer(4096)
+    n = lib().mgcfd_guard_check(buf, 4096)
+    return n, buf.value.decode()
 
 
 def dist_unique_id() -> bytes:

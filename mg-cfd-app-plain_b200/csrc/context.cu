@@ -8,6 +8,7 @@
 #include <map>
 #include <string>
 #include <memory>
+#include <mutex>
 #include <vector>
 
 #include "../../include/mgcfd_b200.h"
@@ -37,6 +38,81 @@ thread_local std::string g_err;
         }                                                                                                \
     } while (0)
 #define CKRC(call) do { int rc_ = (call); if (rc_ != MGCFD_OK) return rc_; } while (0)
+
+// ---- guard zones (MGCFD_GUARD=1; a debugging aid, off by default) ---------------------------------------------------------------
+// Every device allocation of this file gets GUARD bytes of a known pattern on both sides (and the pattern in the allocation itself
+// until it is first written); mgcfd_guard_check() reads the zones back and reports the allocations whose zones were written to.
+// A linear overrun of a per-level array -- the one class of bug compute-sanitizer's memcheck finds that parity tests do not --
+// shows up as a damaged zone with the source line of the allocation.  (The peer-to-peer slab is exempt: its address travels as
+// a CUDA IPC handle.)
+const size_t GUARD_BYTES = 64 << 10;
+struct GuardRec { char* base; size_t bytes, padded; int line; bool gap; };      // gap: a zone inside the slab (nothing to free)
+std::mutex g_guard_mu;
+std::map<void*, GuardRec> g_guard;
+inline bool guard_on() { const char* e = getenv("MGCFD_GUARD"); return e && atoi(e) != 0; }
+cudaError_t guarded_malloc(void** p, size_t bytes, int line) {
+    if (!guard_on()) return cudaMalloc(p, bytes);
+    const size_t padded = (bytes + 255) & ~size_t(255);
+    char* base = nullptr;
+    cudaError_t e = cudaMalloc((void**)&base, padded + 2 * GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(base, 0xA5, padded + 2 * GUARD_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceSynchronize();      // the fill runs on the null stream, the uploads that follow on the context's non-blocking stream: order them
+    if (e != cudaSuccess) return e;
+    *p = base + GUARD_BYTES;
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guard[*p] = GuardRec{base, bytes, padded, line, false};
+    return cudaSuccess;
+}
+cudaError_t guarded_free(void* p) {
+    if (p) {
+        std::lock_guard<std::mutex> lk(g_guard_mu);
+        auto it = g_guard.find(p);
+        if (it != g_guard.end()) { char* base = it->second.base; g_guard.erase(it); return cudaFree(base); }
+    }
+    return cudaFree(p);
+}
+void guard_gap_add(char* at, int line) {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    g_guard[at] = GuardRec{at, 0, 0, line, true};
+}
+void guard_gaps_drop(char* lo, size_t len) {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    for (auto it = g_guard.begin(); it != g_guard.end();) {
+        if (it->second.gap && it->second.base >= lo && it->second.base < lo + len) it = g_guard.erase(it); else ++it;
+    }
+}
+// damaged zones, as text ("line L: first damaged byte at <offset relative to the allocation>"); returns their number
+int guard_check(std::string& report) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    std::vector<unsigned char> h(GUARD_BYTES + 256);
+    int bad = 0;
+    for (const auto& kv : g_guard) {
+        const GuardRec& r = kv.second;
+        struct Zone { const char* at; size_t len; long long rel; };      // rel: offset of the zone's first byte from the allocation's first
+        std::vector<Zone> zones;
+        if (r.gap) zones.push_back({r.base, GUARD_BYTES, 0});
+        else {
+            zones.push_back({r.base, GUARD_BYTES, -(long long)GUARD_BYTES});
+            zones.push_back({r.base + GUARD_BYTES + r.bytes, r.padded - r.bytes + GUARD_BYTES, (long long)r.bytes});
+        }
+        for (const Zone& z : zones) {
+            if (cudaMemcpy(h.data(), z.at, z.len, cudaMemcpyDeviceToHost) != cudaSuccess) { report += "guard zone unreadable; "; bad++; continue; }
+            for (size_t i = 0; i < z.len; i++)
+                if (h[i] != 0xA5) {
+                    report += std::string(r.gap ? "slab gap after sub-buffer, line " : "allocation at line ") + std::to_string(r.line) + ": first damaged byte at offset " +
+                              std::to_string(z.rel + (long long)i) + (r.gap ? " of the gap; " : " (size " + std::to_string(r.bytes) + "); ");
+                    bad++;
+                    break;
+                }
+        }
+    }
+    return bad;
+}
+#define cudaMalloc(p, n) guarded_malloc((void**)(p), (n), __LINE__)
+#define cudaFree(p) guarded_free(p)
 
 template <class T>
 int dev_upload(T** dptr, const std::vector<T>& h, cudaStream_t s) {
@@ -95,6 +171,8 @@ struct Level {
     // the persistent visit kernel (visit_kernel.cuh): one launch per smoothing visit
     bool visit = false;
     int vK = 1, vG = 0, vR = 1, vD = 2, vW = 16, v_resident = 0, v_srmax = 0;
+    unsigned long long* d_minword = nullptr;       // multi-GPU: the minimum dt the transfer kernels fold their blocks' minima into (kernels.cuh, DistTail::minword)
+    int minword_state = 0;                         // 0: +inf (clean)  1: holds the minimum of the level's CURRENT state  2: holds something stale
     bool premin_valid = false;                     // blockmins holds the per-block minima of dt of the CURRENT state (left by restrict / prolong)
     size_t v_smem = 0;
     unsigned char *d_desc = nullptr, *d_vslots = nullptr;
@@ -149,7 +227,6 @@ struct mgcfd_ctx {
     unsigned int* d_bar = nullptr;             // grid barrier word of the visit kernel
     double* d_cta_min = nullptr;               // [num_sms] per-CTA minima, [num_sms * 5] per-CTA RMS sums
     double* d_cta_rms = nullptr;
-    int gmin_level = -1;                       // multi-GPU: level whose global minimum dt (of its CURRENT state) is in d_minbits, or -1
     std::map<std::string, long> graph_launches;
     std::map<std::string, std::string> graph_flags_end;
     long long* d_visit_dbg = nullptr;          // MGCFD_VISIT_DEBUG=1: clock stamps of the last visit-kernel launch (64 per CTA)
@@ -300,7 +377,6 @@ int dist_flush_epoch(mgcfd_ctx* c) {
 int p2p_allreduce(mgcfd_ctx* c, double* vals, int n, int is_min) {
     Dist& d = c->dist;
     CKRC(dist_flush_epoch(c));      // this kernel works with the absolute epoch
-    c->gmin_level = -1;       // the epoch moves on: a minimum a transfer kernel has tagged with its own epoch can no longer be picked up
     k_p2p_allreduce<<<1, 64, 0, c->stream>>>(vals, n, is_min, d.nranks, d.rank, d.d_red_of_rank, d.d_flag_of_rank, (const unsigned long long*)d.win,
                                               (const double*)(d.win + P2P_FLAGS_BYTES), d.d_op, d.d_ctr);
     return post_launch(c);
@@ -326,7 +402,6 @@ int p2p_exchange(mgcfd_ctx* c, int l, const double* src, double* dst) {
     Level& v = c->L[l];
     const double* stage = (const double*)(d.win + P2P_HDR_BYTES) + d.stage_off[l];
     CKRC(dist_flush_epoch(c));
-    c->gmin_level = -1;
     const long work = std::max(v.nsend, v.nghost) * WIDTH;
     const unsigned grid = (unsigned)std::max<long>(1, std::min<long>(blocks_for(work, 256), 2L * c->num_sms));   // resident at once
     k_p2p_exchange<WIDTH, SOA><<<grid, 256, 0, c->stream>>>(src, v.npad, v.d_send_idx, v.d_peers, v.npeers, d.d_op, d.d_ctr + 1 + l, d.d_ticket,
@@ -542,7 +617,6 @@ int launch_flux_variant(mgcfd_ctx* c, Level& v, int bits) {
 
 int step_factor(mgcfd_ctx* c, int l, int legacy) {
     Level& v = c->L[l];
-    c->gmin_level = -1;
     Timed tm(c, K_STEP, l, v.nel);
     const unsigned nb = (unsigned)blocks_for(v.ncomp, 256);
     if (legacy) {
@@ -569,7 +643,6 @@ int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
     }
     if (c->dist.p2p) {      // one kernel: local sums, all-reduce over the ranks, square roots
         CKRC(dist_flush_epoch(c));
-        c->gmin_level = -1;
         k_rms_dist<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel_global, out, counter, c->rms_cap - 1, allred_of(c), c->dist.d_op);
         return post_launch(c);
     }
@@ -631,7 +704,6 @@ DistTail dist_tail(mgcfd_ctx* c, Level& out_level, int ib, const P2PPeer* wait_p
     t.tgt_off = out_level.d_tgt_off; t.tgt_peer = out_level.d_tgt_peer; t.tgt_row = out_level.d_tgt_row; t.tile_sends = out_level.d_tile_sends;
     t.order = out_level.d_order_tiles; t.n_send = out_level.n_send_tiles;
     t.op_counter = d.d_op; t.epoch_off = d.off++; t.my_flags = (const unsigned long long*)d.win;
-    t.ticket = d.d_ticket;
     t.ar = allred_of(c);
     t.dbg = env_int("MGCFD_DIST_DEBUG", 0);
     return t;
@@ -651,7 +723,7 @@ int smooth_visit(mgcfd_ctx* c, int l) {
     a.vslots = v.d_vslots; a.bslots = v.bslots; a.cta_rows = v.d_cta_rows;
     a.K = v.vK; a.sr_max = v.v_srmax; a.resident = v.v_resident; a.max_chunk = v.plan.visit.max_chunk;
     if (!c->dist.active && v.premin_valid) { a.premin = v.blockmins; a.npremin = (int)blocks_for(v.ncomp, 128); }
-    if (c->gmin_level == l) c->gmin_level = -1;
+    if (v.minword_state == 1) v.minword_state = 2;
     a.k2 = 2.0 * c->kdiss;
     a.bad_key = c->d_badkey; a.old_of_new = v.old_of_new;
     a.stage_seq0 = c->stage_seq & 0xFFFFFFull; c->stage_seq += MGCFD_RK;
@@ -686,7 +758,7 @@ int smooth_visit(mgcfd_ctx* c, int l) {
     if (dist) c->dist.exchanges += MGCFD_RK;
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     v.premin_valid = false;
-    if (c->gmin_level == l) c->gmin_level = -1;
+    if (v.minword_state == 1) v.minword_state = 2;
     return MGCFD_OK;
 }
 
@@ -704,7 +776,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     // by k_min_dt (+ all-reduce)
     bool use_premin = false, recv_min = false;
     if (!legacy) {
-        if (c->dist.active) { if (deliver && c->gmin_level == l) recv_min = true; else CKRC(min_dt_fused(c, l)); }
+        if (c->dist.active) { if (deliver && v.minword_state == 1) recv_min = true; else CKRC(min_dt_fused(c, l)); }
         else if (v.premin_valid && v.pipe) use_premin = true;      // (the simple one-CTA-per-tile kernel reads *min_bits only)
         else CKRC(min_dt_fused(c, l));
     } else if (!deliver) CKRC(min_dt_fused(c, l));
@@ -733,7 +805,9 @@ int smooth_fused(mgcfd_ctx* c, int l) {
         if (deliver) {
             const int ib = (a.vout == v.buf[0]) ? 0 : (a.vout == v.buf[1] ? 1 : 2);
             a.d = dist_tail(c, v, ib, v.d_peers, v.npeers);
-            a.d.recv_min = (j == 0 && recv_min) ? 1 : 0;
+            a.d.minword = v.d_minword;
+            a.d.recv_min = (j == 0 && recv_min) ? 1 : 0;          // block 0 sends the level's word, every CTA picks the ranks' minima up
+            a.d.finish_min = (j == 1 && recv_min) ? 1 : 0;        // the word goes back to +inf, the reduction is counted
             CKRC(launch_stage_dist(c, v, a));
             c->dist.exchanges++;
             continue;
@@ -745,8 +819,17 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     visit_tm.reset();
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     v.premin_valid = false;
-    if (c->gmin_level == l) c->gmin_level = -1;
+    if (recv_min) v.minword_state = 0; else if (v.minword_state == 1) v.minword_state = 2;
     if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
+    return MGCFD_OK;
+}
+
+// a transfer kernel is about to fold its blocks' minima of dt into the level's word: the word must be +inf (it is, unless the last
+// minimum was never picked up -- the state was changed through the API in between)
+int minword_arm(mgcfd_ctx* c, Level& v, DistTail& t) {
+    if (v.minword_state != 0) CK(cudaMemsetAsync(v.d_minword, 0x7F, sizeof(unsigned long long), c->stream));
+    t.minword = v.d_minword;
+    v.minword_state = 1;
     return MGCFD_OK;
 }
 
@@ -762,11 +845,10 @@ int do_restrict(mgcfd_ctx* c, int lc) {
         DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers);
         t.blk_wait = vc.d_rblk_wait;
         if (vc.visit || !vc.pipe) bm = nullptr;             // only a level whose stage kernels deliver their rows themselves picks the minimum up
-        if (bm) { t.blockmins = bm; t.nblocks = (int)nb; t.send_min = 1; }
-        k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, t);
+        if (bm) CKRC(minword_arm(c, vc, t)); else if (vc.minword_state == 1) vc.minword_state = 2;
+        k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, nullptr, t);
         c->dist.exchanges++;
         vc.premin_valid = false;
-        c->gmin_level = bm ? lc : -1;
         return post_launch(c);
     }
     DistTail none;
@@ -789,12 +871,11 @@ int do_prolong(mgcfd_ctx* c, int lf) {
         // (when the coarse level's residuals came through an exchange kernel just above, every block may run at once)
         t.blk_wait = vf.d_pblk_wait;
         if (vf.visit || !vf.pipe) bm = nullptr;
-        if (bm) { t.blockmins = bm; t.nblocks = (int)nb; t.send_min = 1; }
+        if (bm) CKRC(minword_arm(c, vf, t)); else if (vf.minword_state == 1) vf.minword_state = 2;
         k_prolong<true><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
-                                                   vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, bm, t);
+                                                   vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, nullptr, t);
         c->dist.exchanges++;
         vf.premin_valid = false;
-        c->gmin_level = bm ? lf : -1;
         return post_launch(c);
     }
     CKRC(dist_exchange_residuals(c, lf + 1));
@@ -822,7 +903,7 @@ std::string role_key(mgcfd_ctx* c) {
     std::string k;
     for (auto& v : c->L) { k += char('0' + v.i_var); k += char('0' + v.i_old); }
     for (auto& v : c->L) k += v.premin_valid ? 'v' : '-';      // a captured kernel has the source of its minimum dt baked in
-    k += char('0' + (c->gmin_level + 1));
+    for (auto& v : c->L) k += char('0' + v.minword_state);
     return k;
 }
 
@@ -854,7 +935,7 @@ void free_level(Level& v) {
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
                     v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers,
                     v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_out, v.ewt_pre, v.d_desc, v.d_vslots, v.d_cta_rows, v.d_hsum,
-                    v.d_order_tiles, v.d_rblk_wait, v.d_pblk_wait};
+                    v.d_order_tiles, v.d_rblk_wait, v.d_pblk_wait, v.d_minword};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -940,6 +1021,20 @@ void mgcfd_default_options(mgcfd_options* opt) {
     opt->timing = 0;
 }
 const char* mgcfd_last_error(void) { return g_err.c_str(); }
+int mgcfd_guard_selftest(mgcfd_ctx* c) {
+    if (!c) { g_err = "null context"; return MGCFD_ERR_ARG; }
+    bool guarded;
+    { std::lock_guard<std::mutex> lk(g_guard_mu); guarded = g_guard.count(c->d_rms_sums) != 0; }
+    if (!guarded) { g_err = "the context was created without MGCFD_GUARD=1"; return MGCFD_ERR_ARG; }
+    CK(cudaMemset((char*)c->d_rms_sums + sizeof(double) * 8 + 100, 7, 1));
+    return MGCFD_OK;
+}
+int mgcfd_guard_check(char* report, int cap) {
+    std::string r;
+    const int bad = guard_check(r);
+    if (report && cap > 0) { snprintf(report, (size_t)cap, "%s", r.c_str()); }
+    return bad;
+}
 const char* mgcfd_version(void) { return "mgcfd-b200 0.1 (sm_100a, fp64)"; }
 
 void mgcfd_far_field_conditions(double ffv[5], double ffc[12]) {
@@ -1020,7 +1115,7 @@ int mgcfd_destroy(mgcfd_ctx* c) {
     cudaFree(c->d_minbits); cudaFree(c->d_badkey); cudaFree(c->d_ticket); cudaFree(c->d_rms); cudaFree(c->d_rms_counter); cudaFree(c->d_rms_sums);
     if (c->dist.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->dist.comm);
     for (int p = 0; p < (int)c->dist.peer_win.size(); p++) if (p != c->dist.rank && c->dist.peer_win[p]) cudaIpcCloseMemHandle(c->dist.peer_win[p]);
-    cudaFree(c->d_visit_dbg); cudaFree(c->slab); cudaFree(c->d_bar); cudaFree(c->d_cta_min); cudaFree(c->d_cta_rms);
+    cudaFree(c->d_visit_dbg); if (c->slab) guard_gaps_drop((char*)c->slab, c->slab_bytes); (cudaFree)(c->slab); cudaFree(c->d_bar); cudaFree(c->d_cta_min); cudaFree(c->d_cta_rms);
     cudaFree(c->dist.d_ticket); cudaFree(c->dist.d_sig); cudaFree(c->dist.d_op); cudaFree(c->dist.d_ctr); cudaFree(c->dist.d_red_of_rank); cudaFree(c->dist.d_flag_of_rank);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -1099,12 +1194,19 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         d.buf_off.assign(4 * (size_t)c->levels, 0);
         for (int l = 0; l < c->levels; l++) {
             const size_t npad = (size_t)c->L[l].plan.npad;
-            for (int b = 0; b < 3; b++) { d.buf_off[4 * l + b] = off; off += up(sizeof(double) * 8 * npad); }
-            d.buf_off[4 * l + 3] = off; off += up(sizeof(double) * 5 * npad);
+            const size_t gap = guard_on() ? GUARD_BYTES : 0;          // MGCFD_GUARD=1: a checked zone after every sub-buffer
+            for (int b = 0; b < 3; b++) { d.buf_off[4 * l + b] = off; off += up(sizeof(double) * 8 * npad) + gap; }
+            d.buf_off[4 * l + 3] = off; off += up(sizeof(double) * 5 * npad) + gap;
         }
         c->slab_bytes = off;
-        CK(cudaMalloc((void**)&c->slab, c->slab_bytes));
+        CK((cudaMalloc)((void**)&c->slab, c->slab_bytes));      // (no guard zones: the address travels as an IPC handle)
+        if (guard_on()) CK(cudaMemsetAsync(c->slab, 0xA5, c->slab_bytes, s));
         if (d.active) { d.win = c->slab; CK(cudaMemsetAsync(d.win, 0, up(d.win_bytes), s)); }
+        for (int l = 0; guard_on() && l < c->levels; l++) {
+            const size_t npad = (size_t)c->L[l].plan.npad;
+            for (int b = 0; b < 3; b++) guard_gap_add((char*)c->slab + d.buf_off[4 * l + b] + up(sizeof(double) * 8 * npad), __LINE__);
+            guard_gap_add((char*)c->slab + d.buf_off[4 * l + 3] + up(sizeof(double) * 5 * npad), __LINE__);
+        }
         for (int l = 0; l < c->levels; l++) {
             for (int b = 0; b < 3; b++) c->L[l].buf[b] = (double*)(c->slab + d.buf_off[4 * l + b]);
             c->L[l].res = (double*)(c->slab + d.buf_off[4 * l + 3]);
@@ -1189,7 +1291,9 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         }
         const long parts = std::max<long>(v.ntiles, blocks_for(v.npad, 256));
         CK(cudaMalloc((void**)&v.rms_partial, sizeof(double) * 5 * parts));
-        CK(cudaMalloc((void**)&v.blockmins, sizeof(double) * parts));
+        // per-block minima of dt: k_min_dt writes one per 256 rows, the transfer kernels one per 128 rows whatever the tile size
+        CK(cudaMalloc((void**)&v.blockmins, sizeof(double) * std::max<long>(parts, blocks_for(v.npad, 128))));
+        CK(cudaMalloc((void**)&v.d_minword, sizeof(unsigned long long))); CK(cudaMemsetAsync(v.d_minword, 0x7F, sizeof(unsigned long long), s));
         CK(cudaStreamSynchronize(s));
         // node state: every buffer starts at the far-field state (what initialize_variables leaves, cfd_loops.h:44-55);
         // padding nodes keep it forever (no edges, zero residual), which keeps them finite in every stage
@@ -1242,7 +1346,7 @@ int mgcfd_initialize_variables(mgcfd_ctx* c, int l) {
     CKRC(check_level(c, l));
     Level& v = c->L[l];
     v.premin_valid = false;
-    if (c->gmin_level == l) c->gmin_level = -1;
+    if (v.minword_state == 1) v.minword_state = 2;
     k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad);
     return post_launch(c);
 }
@@ -1269,7 +1373,7 @@ int mgcfd_time_step(mgcfd_ctx* c, int l, int j) {
     Level& v = c->L[l];
     CKRC(ensure_flux(c, v));
     v.premin_valid = false;
-    if (c->gmin_level == l) c->gmin_level = -1;
+    if (v.minword_state == 1) v.minword_state = 2;
     Timed tm(c, K_TIME, l, v.nel);
     k_time_step<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(double(MGCFD_RK + 1 - j), v.ncomp, v.npad, v.sf, v.flux, v.V(v.i_old), v.V(v.i_var));
     return post_launch(c);
@@ -1314,7 +1418,6 @@ int mgcfd_check_for_invalid_variables(mgcfd_ctx* c, int l, long* first_bad_cell,
     CKRC(check_level(c, l));
     Level& v = c->L[l];
     unsigned long long* key = c->d_minbits;   // scratch word; the step-factor kernel re-initialises it before use
-    c->gmin_level = -1;
     CK(cudaMemsetAsync(key, 0xFF, 8, c->stream));
     k_check_invalid<<<(unsigned)blocks_for(v.ncomp, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.ncomp, v.old_of_new, key);
     CKRC(post_launch(c));
@@ -1359,9 +1462,8 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
         cudaGraph_t g = nullptr;
         const long launches_before = c->launches;
         c->capturing = true;
-        std::vector<char> flags0;
-        for (auto& v : c->L) flags0.push_back(v.premin_valid);
-        const int gmin0 = c->gmin_level;
+        std::vector<char> flags0, mw0;
+        for (auto& v : c->L) { flags0.push_back(v.premin_valid); mw0.push_back((char)v.minword_state); }
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         int rc = cycle_fused(c);
         cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
@@ -1370,8 +1472,7 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
         {   // what the cycle leaves behind of the minimum-dt bookkeeping; rolled back like the buffer roles, re-applied by every replay
             std::string end;
             for (size_t l = 0; l < c->L.size(); l++) { end += c->L[l].premin_valid ? 'v' : '-'; c->L[l].premin_valid = flags0[l] != 0; }
-            end += char('0' + (c->gmin_level + 1));
-            c->gmin_level = gmin0;
+            for (size_t l = 0; l < c->L.size(); l++) { end += char('0' + c->L[l].minword_state); c->L[l].minword_state = mw0[l]; }
             c->graph_flags_end[key] = end;
         }
         c->launches = launches_before;        // capture recorded the launches, it did not run them
@@ -1391,7 +1492,7 @@ int enqueue_one_cycle(mgcfd_ctx* c) {
     {
         const std::string& end = c->graph_flags_end[key];
         for (size_t l = 0; l < c->L.size() && l < end.size(); l++) c->L[l].premin_valid = (end[l] == 'v');
-        if (end.size() > c->L.size()) c->gmin_level = int(end[c->L.size()] - '0') - 1;
+        for (size_t l = 0; l < c->L.size() && c->L.size() + l < end.size(); l++) c->L[l].minword_state = end[c->L.size() + l] - '0';
     }
     return MGCFD_OK;
 }
@@ -1486,7 +1587,7 @@ int mgcfd_set_field(mgcfd_ctx* c, int l, int field, const double* host_in) {
     if (!host_in) { g_err = "null buffer"; return MGCFD_ERR_ARG; }
     Level& v = c->L[l];
     v.premin_valid = false;
-    if (c->gmin_level == l) c->gmin_level = -1;
+    if (v.minword_state == 1) v.minword_state = 2;
     double* p; int nc;
     CKRC(field_ptr(c, v, field, &p, &nc, true));
     if (!v.io) CK(cudaMalloc((void**)&v.io, sizeof(double) * 5 * v.nel));

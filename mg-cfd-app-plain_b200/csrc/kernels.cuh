@@ -268,11 +268,13 @@ struct DistTail {
     const int* order; int n_send;              // stage kernels: tiles in the order they are taken, the n_send ghost-reading (= delivering) tiles LAST
     const unsigned char* blk_wait;             // transfer kernels: per 128-row block, does it read a ghost row (only those blocks wait); nullptr: all wait
     const unsigned long long* op_counter; int epoch_off; const unsigned long long* my_flags;
-    // the minimum dt of the state a transfer kernel leaves behind: its last CTA (ticket) reduces the per-block minima and SENDS the
-    // rank's minimum, tagged with the epoch, into every rank's reduction slot (send_min); the first stage kernel of the next
-    // smoothing visit waits for the tags and combines the values itself (recv_min) -- nobody blocks inside the transfer kernel
-    unsigned int* ticket;
-    AllRed ar; const double* blockmins; int nblocks; int send_min, recv_min;
+    // the minimum dt of the state a transfer kernel leaves behind: every block of the transfer kernel folds its minimum into ONE word
+    // of the level (atomicMin on the bit pattern of a positive double: fire and forget, no fence, no ticket).  The first stage
+    // kernel of the next smoothing visit (recv_min) has its block 0 send that word, tagged with the kernel's epoch, into every
+    // rank's reduction slot at its very start; every CTA picks the ranks' values up just before its first update, one NVLink flag
+    // latency later.  The second stage kernel of the visit (finish_min) puts the word back to +inf and counts the reduction.
+    unsigned long long* minword;
+    AllRed ar; int recv_min, finish_min;
     int dbg;       // measurement only (MGCFD_DIST_DEBUG, results become wrong): 1 no waits, 2 no remote stores, 8 no announcements
 };
 __device__ __forceinline__ void dist_wait(const DistTail& d, unsigned long long e0) {
@@ -285,61 +287,44 @@ __device__ __forceinline__ void dist_wait(const DistTail& d, unsigned long long 
 }
 // start of a distributed kernel: the epoch, the announcement (block 0) and -- unless the caller waits later -- the wait
 __device__ __forceinline__ unsigned long long dist_kernel_begin(const DistTail& d, bool wait_now) {
-    const unsigned long long e0 = *(volatile const unsigned long long*)d.op_counter + (unsigned long long)d.epoch_off;
+    unsigned long long e0 = 0;
+    if (blockIdx.x == 0 || wait_now) e0 = *(volatile const unsigned long long*)d.op_counter + (unsigned long long)d.epoch_off;      // (block-uniform: other blocks never need it)
     if (blockIdx.x == 0 && (int)threadIdx.x < d.nsig && !(d.dbg & 8)) st_release_sys(d.sig_peers[threadIdx.x].flag, e0);
     if (wait_now) dist_wait(d, e0);
     return e0;
 }
-// end of a transfer kernel that owes the next smoothing visit its minimum dt: the last CTA reduces the block minima and sends
-__device__ __forceinline__ void dist_send_min(const DistTail& d, unsigned long long e0) {
-    __shared__ int s_last;
-    __shared__ double s_wm[32];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // two-level ticket (groups of 32 blocks, then the groups): thousands of blocks counting off on ONE word serialise in L2
-        __threadfence();
-        const unsigned grp = blockIdx.x >> 5, ngrp = (gridDim.x + 31) >> 5;
-        const unsigned gsize = min(32u, gridDim.x - (grp << 5));
-        s_last = 0;
-        if (atomicInc(d.ticket + 1 + grp, gsize - 1) == gsize - 1) {
-            __threadfence();
-            s_last = (atomicInc(d.ticket, ngrp - 1) == ngrp - 1);
-        }
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    double v = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
-    for (int b = threadIdx.x; b < d.nblocks; b += blockDim.x) v = fmin(v, __ldcg(d.blockmins + b));
-#pragma unroll
-    for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
-    if ((threadIdx.x & 31) == 0) s_wm[threadIdx.x >> 5] = v;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        v = (threadIdx.x < (blockDim.x >> 5)) ? s_wm[threadIdx.x] : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
-#pragma unroll
-        for (int dl = 16; dl > 0; dl >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, dl));
-        const int parity = int(*(volatile unsigned int*)d.ar.red_counter & 1u);
-        for (int p = threadIdx.x; p < d.ar.nranks; p += 32) {
-            double* slot = d.ar.red_of_rank[p] + ((size_t)parity * 64 + d.ar.me) * 8;
-            slot[0] = v;
-            st_release_sys(reinterpret_cast<unsigned long long*>(slot + 1), e0 + 1);      // the tag: value delivered (same thread: ordered by the release)
-        }
-        __syncwarp();
-        if (threadIdx.x == 0) *d.ar.red_counter += 1;
+// the epoch of a stage kernel (every CTA needs it)
+__device__ __forceinline__ unsigned long long dist_epoch(const DistTail& d) {
+    return *(volatile const unsigned long long*)d.op_counter + (unsigned long long)d.epoch_off;
+}
+// first stage of a smoothing visit, block 0, first warp: this rank's minimum (left in d.minword by the transfer kernel that produced
+// the state) goes to every rank, tagged with this kernel's epoch
+__device__ __forceinline__ void dist_min_send(const DistTail& d, unsigned long long e0) {
+    const int parity = int(*(volatile unsigned int*)d.ar.red_counter & 1u);
+    const double v = __longlong_as_double((long long)*(volatile const unsigned long long*)d.minword);
+    for (int p = threadIdx.x; p < d.ar.nranks; p += 32) {
+        double* slot = d.ar.red_of_rank[p] + ((size_t)parity * 64 + d.ar.me) * 8;
+        slot[0] = v;
+        st_release_sys(reinterpret_cast<unsigned long long*>(slot + 1), e0);      // the tag: value delivered (same thread: ordered by the release)
     }
 }
-// first stage of a smoothing visit: the minimum over the ranks of the values their last transfer kernel sent (tag = this kernel's
-// epoch); every thread returns the minimum
+// ... and every CTA: the minimum over the ranks of the values tagged e0; every thread returns it.  The slot pair alternates with
+// every reduction of the rank (red_counter, advanced by the visit's SECOND stage kernel: no CTA of this one may see it move)
 __device__ __forceinline__ double dist_recv_min(const DistTail& d, unsigned long long e0) {
     __shared__ unsigned long long s_min;
     if (threadIdx.x < 32) {
-        const int parity = int((*(volatile unsigned int*)d.ar.red_counter - 1u) & 1u);
+        const int parity = int(*(volatile unsigned int*)d.ar.red_counter & 1u);
         unsigned long long m = ~0ull;
         for (int r = threadIdx.x; r < d.ar.nranks; r += 32) {
             const double* slot = d.ar.my_red + ((size_t)parity * 64 + r) * 8;
             unsigned spins = 0;
-            while (!(d.dbg & 1) && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(slot + 1)) != e0) { if (spin_expired(spins, "minimum dt tag")) break; }
+            while (!(d.dbg & 1) && ld_acquire_sys(reinterpret_cast<const unsigned long long*>(slot + 1)) != e0) {
+                if (spins == 3999998u)
+                    printf("mgcfd: rank %d waits for the minimum-dt tag %llu of rank %d: slot holds %llu, reductions so far %u, epoch base %llu off %d\n", d.ar.me, e0, r,
+                           *reinterpret_cast<const volatile unsigned long long*>(slot + 1), *(volatile unsigned int*)d.ar.red_counter,
+                           *(volatile const unsigned long long*)d.op_counter, d.epoch_off);
+                if (spin_expired(spins, "minimum dt tag")) break;
+            }
             const unsigned long long x = (unsigned long long)__double_as_longlong(__ldcg(slot));
             m = x < m ? x : m;
         }
@@ -731,7 +716,10 @@ k_stage_pipe(const StageArgs a) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     unsigned long long e0 = 0;
     if (DIST) {
-        e0 = dist_kernel_begin(a.d, false);
+        e0 = dist_epoch(a.d);
+        if (blockIdx.x == 0 && t < a.d.nsig && !(a.d.dbg & 8)) st_release_sys(a.d.sig_peers[t].flag, e0);      // the announcement
+        if (blockIdx.x == 0 && t < 32 && a.d.recv_min) dist_min_send(a.d, e0);
+        if (blockIdx.x == 0 && t == 0 && a.d.finish_min) { *a.d.minword = 0x7F7F7F7F7F7F7F7FULL; *a.d.ar.red_counter += 1; }
         if ((long)blockIdx.x >= first_ghost_pos) { dist_wait(a.d, e0); waited = true; }      // the very first tile already reads ghost rows
     }
     copy_recs(0);
@@ -1002,14 +990,23 @@ __device__ __forceinline__ void block_min_store(double val, double* __restrict__
     if (threadIdx.x == 0) out[blockIdx.x] = fmin(fmin(wm[0], wm[1]), fmin(wm[2], wm[3]));
 }
 
+// ... or (multi-GPU) folded into one word of the level: atomicMin on the bit pattern (positive doubles order like unsigned integers)
+__device__ __forceinline__ void block_min_atomic(double val, unsigned long long* __restrict__ word) {
+    __shared__ double wm2[4];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) val = fmin(val, __shfl_xor_sync(0xffffffffu, val, d));
+    if ((threadIdx.x & 31) == 0) wm2[threadIdx.x >> 5] = val;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMin(word, (unsigned long long)__double_as_longlong(fmin(fmin(wm2[0], wm2[1]), fmin(wm2[2], wm2[3]))));
+}
+
 // mg_restrict (mg_loops.cpp:30-202) as a gather: children summed in ascending original fine index (the reference's
 // accumulation order, bit for bit), then multiplied by 1.0/count; coarse nodes without children keep their value.
 template <bool DIST>
 __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ vc, long ncoarse,
                            const long* __restrict__ child_off, const int* __restrict__ child_ids, const double* __restrict__ vol_root,
                            double* __restrict__ blockmins, const DistTail d) {
-    unsigned long long e0 = 0;
-    if (DIST) e0 = dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks with ghost children wait for the fine level's owners
+    if (DIST) dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks with ghost children wait for the fine level's owners
     const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double s_new = 0.0;          // |v| + c of the node's state after this kernel
     if (c < ncoarse) {
@@ -1028,14 +1025,14 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
             s_new = n.s;
             if (DIST) dist_push_rec(d, c, n);
         } else {
-            if (blockmins) s_new = vc[8 * c + 7];
+            if (blockmins || (DIST && d.minword)) s_new = vc[8 * c + 7];
             // a childless coarse node keeps its value; the copies other ranks hold of it must keep up with whatever the last
             // visit left in THIS buffer of theirs (their ghost rows are only ever written by the owner)
             if (DIST) { if (d.tgt_off[c + 1] > d.tgt_off[c]) dist_push_rec(d, c, load_rec(vc, c)); }
         }
     }
     if (blockmins) block_min_store(c < ncoarse ? 0.5 * (vol_root[c] / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), blockmins);
-    if (DIST && d.send_min) dist_send_min(d, e0);
+    if (DIST && d.minword) block_min_atomic(c < ncoarse ? 0.5 * (vol_root[c] / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), d.minword);
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
 // edges in original edge order: per edge the own-parent term then the neighbour-parent term (whose source is the own
@@ -1045,8 +1042,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
                           const long* __restrict__ ent_off, const int* __restrict__ ent_src, const double* __restrict__ ent_w,
                           const double* __restrict__ res_c, const double* __restrict__ res_f, double* __restrict__ var_f,
                           const double* __restrict__ vol_root, double* __restrict__ blockmins, const DistTail d) {
-    unsigned long long e0 = 0;
-    if (DIST) e0 = dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks that read a ghost parent's residual wait
+    if (DIST) dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks that read a ghost parent's residual wait
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int p = (i < nfine) ? parent[i] : -1;
     double dt_new = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);      // padding rows (no parent) never win the minimum
@@ -1086,11 +1082,11 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
         }
         const Rec n = make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]);
         store_rec(var_f, i, n);
-        if (blockmins) dt_new = 0.5 * (vol_root[i] / n.s);
+        if (blockmins || (DIST && d.minword)) dt_new = 0.5 * (vol_root[i] / n.s);
         if (DIST) dist_push_rec(d, i, n);
     }
     if (blockmins) block_min_store(dt_new, blockmins);
-    if (DIST && d.send_min) dist_send_min(d, e0);
+    if (DIST && d.minword) block_min_atomic(dt_new, d.minword);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -482,13 +482,13 @@ def test_c3_class_mesh_matches_the_serial_reference(M, oracle):
     kind, dims, variant, _ = bench.WORKLOADS["c3"]
     cycles = 2
     mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
+    ref = Reference(omp=False)
+    sess = ref.session(variant, mesh_levels(mesh))      # RAW edge weights, so before Solver.from_mesh (the upload adjusts the mesh's in place, as the reference's loader does)
     s = M.Solver.from_mesh(mesh)
     assert s.level_info(0)["tile_nodes"] == 128 and s.level_info(0)["nel"] > 8000000
     ra, rv = s.run_cycles(cycles)
     got = [s.get_field(l, M.FIELD_VARIABLES).copy() for l in range(mesh.levels)]
     s.close()
-    ref = Reference(omp=False)
-    sess = ref.session(variant, mesh_levels(mesh))
     mesh.close()
     sess.prepare()
     rra, _, _ = sess.run(cycles)
@@ -496,3 +496,48 @@ def test_c3_class_mesh_matches_the_serial_reference(M, oracle):
     for l in range(len(got)):
         assert np.all(linf_rel(got[l], sess.field(l, 0)) < TOL), l
     sess.close()
+
+
+# ---- guard zones: the stand-in for a memcheck run (compute-sanitizer is not available on this GPU pool) ----------------------------
+@pytest.mark.parametrize("name,kw", [("hex_nonnested", dict()), ("hex_nonnested", dict(tile_nodes=256)), ("hex_nonnested", dict(tile_nodes=128, flux_mode=0)),
+                                     ("tet3", dict(tile_nodes=256)), ("tet3", dict(flux_mode=2)), ("fvcorr", dict()), ("hex_random", dict(tile_nodes=512)),
+                                     ("hex_nonnested", dict(visit=True)), ("tet3", dict(visit=True))])
+def test_no_kernel_writes_outside_its_arrays(M, oracle, name, kw):
+    """MGCFD_GUARD=1 brackets every device allocation (and every sub-buffer of the node-state slab) with 64 KB of a byte pattern;
+    after graph-replayed cycles, granular cycles, the flux variants and field transfers no zone may have changed -- and the results
+    still match the oracle (the pattern also fills the allocations themselves: nothing reads memory it has not written).
+    Round 2 found a real overrun this way: the per-block minima the transfer kernels leave (one per 128 rows) in an array sized
+    one per 256 rows (levels with 256-node tiles)."""
+    from mgcfd_b200 import run_cycles_granular
+    with _env(MGCFD_GUARD=1):
+        mesh = make(M, name)
+        lv = mesh_levels(mesh, apply_ewt_with=oracle)
+        ora, _, st = oracle.run_cycles(mesh.mesh_variant, lv, 5)
+        s = M.Solver.from_mesh(mesh, **kw)
+        ra, _ = s.run_cycles(5)
+        assert np.max(np.abs(ra - ora) / ora) < TOL
+        for l in range(mesh.levels):
+            assert np.all(linf_rel(s.get_field(l, M.FIELD_VARIABLES), st[l]["var"]) < TOL)
+        run_cycles_granular(s, 2)
+        for l in range(mesh.levels):
+            s.zero_fluxes(l); s.compute_flux_edge(l); s.compute_boundary_flux_edge(l); s.compute_wall_flux_edge(l)
+            s.set_field(l, M.FIELD_VARIABLES, perturbed_state(lv[l]["nel"], seed=5 + l))
+        s.run_cycles(2)
+        bad, report = M.guard_check()
+        s.close()
+    assert bad == 0, report
+
+
+def test_guard_zones_do_report_an_overrun(M):
+    """the check itself: mgcfd_guard_selftest writes one byte 100 bytes past the end of the context's 64-byte RMS-sums array"""
+    with _env(MGCFD_GUARD=1):
+        s = M.Solver.from_mesh(make(M, "hex3"))
+        s.run_cycles(1)
+        assert M.guard_check()[0] == 0
+        assert M.lib().mgcfd_guard_selftest(s._h) == 0
+        bad, report = M.guard_check()
+        s.close()
+    assert bad == 1 and "offset 164" in report and "size 64" in report, report
+    s = M.Solver.from_mesh(make(M, "hex3"))          # without MGCFD_GUARD there are no zones: the self-test refuses, the check returns 0
+    assert M.lib().mgcfd_guard_selftest(s._h) != 0 and M.guard_check()[0] == 0
+    s.close()

@@ -36,13 +36,17 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "big":      # one mid-size case: many tiles per persistent CTA, 100 KB-class messages
         cases = [("hex4-big", 0, [[133, 67, 67], [109, 55, 55], [95, 48, 48], [85, 43, 43]], 2)]
         cycles = 4
+    if len(sys.argv) > 1 and sys.argv[1] == "tet":      # tets, 275 K nodes per rank: 256-node tiles, thousands of transfer-kernel blocks (two-level ticket)
+        g = lambda n: n * world - (world - 1)
+        cases = [("tet-mid", 1, [[g(65), 65, 65], [g(33), 33, 33], [g(17), 17, 17]], 2)]
+        cycles = 4
     worst = 0.0
     for name, kind, dims, variant in cases:
         uid = bcast_id(rank)
         mesh = M.Mesh.generate(kind, dims, mesh_variant=variant)
         if name == "replicas":
             mesh.duplicate(world)
-        if name in ("tet3", "hex4-big", "c2-unit"):      # rank-local generation (no rank assembles the mesh): the path bench.py takes
+        if name in ("tet3", "hex4-big", "c2-unit", "tet-mid"):      # rank-local generation (no rank assembles the mesh): the path bench.py takes
             s = M.Solver.generate_distributed(kind, dims, rank, world, uid, mesh_variant=variant, device=local)
         else:
             s = M.Solver.from_mesh_distributed(mesh, rank, world, uid, device=local)
@@ -60,6 +64,14 @@ def main():
         gathered = [None] * world
         dist.all_gather_object(gathered, pieces)
         ex = s.dist_level_info(0)["exchanges"]
+        if os.environ.get("MGCFD_GUARD", "0") == "1":       # guard zones around every device array (mgcfd_guard_check): none may be damaged
+            zones = [None] * world
+            dist.all_gather_object(zones, M.guard_check())
+            if rank == 0:
+                nbad = sum(z[0] for z in zones)
+                print(f"dist_check {name}: guard zones damaged on all ranks: {nbad}", "".join(z[1] for z in zones), flush=True)
+                if nbad:
+                    worst = float("inf")
         s.close()
         if rank == 0:
             rmesh = M.Mesh.generate(kind, dims, mesh_variant=variant)

@@ -1,6 +1,6 @@
 """Multi-GPU timing probe (under torchrun): the bench.py unit (C2 grown N-fold, rank-local generation, peer-to-peer plane), V-cycles
 replayed as a graph, device time per cycle (max over ranks).  MGCFD_DIST_DEBUG switches parts of the protocol off (results wrong,
-timing only).   usage: dist_perf.py [cycles]"""
+timing only).   usage: dist_perf.py [cycles [workload]]"""
 import json
 import os
 import sys
@@ -14,7 +14,8 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 dist.init_process_group("gloo")
 torch.cuda.set_device(local)
 cycles = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-kind, dims, variant, _ = bench.WORKLOADS["c2"]
+wl = sys.argv[2] if len(sys.argv) > 2 else "c2"
+kind, dims, variant, _ = bench.WORKLOADS[wl]
 gd = [[d[0] * world - (world - 1), d[1], d[2]] for d in dims]
 idt = torch.zeros(128, dtype=torch.uint8)
 if rank == 0:
@@ -42,5 +43,5 @@ torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / cycles], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    print(json.dumps({"ranks": world, "dbg": os.environ.get("MGCFD_DIST_DEBUG", "0"), "visit": os.environ.get("MGCFD_VISIT", "0"), "ms_per_cycle": float(t)}), flush=True)
+    print(json.dumps({"ranks": world, "dbg": os.environ.get("MGCFD_DIST_DEBUG", "0"), "visit": os.environ.get("MGCFD_VISIT", "0"), "workload": wl, "ms_per_cycle": float(t)}), flush=True)
 dist.destroy_process_group()

@@ -642,8 +642,7 @@ int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
         return post_launch(c);
     }
     if (c->dist.p2p) {      // one kernel: local sums, all-reduce over the ranks, square roots
-        CKRC(dist_flush_epoch(c));
-        k_rms_dist<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel_global, out, counter, c->rms_cap - 1, allred_of(c), c->dist.d_op);
+        k_rms_dist<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel_global, out, counter, c->rms_cap - 1, allred_of(c), c->dist.d_op, c->dist.off++);
         return post_launch(c);
     }
     // distributed: local sums of squares -> all-reduce(sum) of 5 doubles -> square roots over the global node count

@@ -797,7 +797,7 @@ k_stage_pipe(const StageArgs a) {
         double sf = vol_or_sf;
         if (first_stage) { sf = step_factor_of(a, min_dt, vol_or_sf, me.s); a.sf[gid] = sf; }
         double q[5] = {0, 0, 0, 0, 0};
-        fused_update<DIST>(a, gid, sf, o, f, q, DIST && a.d.tile_sends[tile] != 0);
+        fused_update<DIST>(a, gid, sf, o, f, q, DIST && (long)blockIdx.x + (long)it * G >= first_ghost_pos);      // (the delivering tiles are the last n_send of the order)
         if (a.res && a.rms_partial) rms_block<TN>(q, ws, t, a.rms_partial + tile * 5);
         __syncthreads();      // record buffer (it & 1), header buffer (it % 3), acc and ws are free again
     }
@@ -1253,9 +1253,10 @@ __global__ void k_p2p_allreduce(double* __restrict__ vals, int n, int is_min, in
 }
 
 // calc_rms of a distributed run in ONE kernel (one block): local sums of the per-tile partials in index order, all-reduce(sum) of the
-// five sums over the ranks (k_p2p_allreduce's protocol, absolute epoch), square roots over the global node count
+// five sums over the ranks (k_p2p_allreduce's protocol; the kernel owns one epoch like every other: base + epoch_off), square roots
+// over the global node count
 __global__ void k_rms_dist(const double* __restrict__ partial, long nparts, double nel_global, double* __restrict__ out, int* counter, int cap,
-                           const AllRed ar, unsigned long long* op_counter) {
+                           const AllRed ar, const unsigned long long* op_counter, int epoch_off) {
     __shared__ double ws[5][256];
     __shared__ double sums[8];
     const int t = threadIdx.x;
@@ -1273,7 +1274,7 @@ __global__ void k_rms_dist(const double* __restrict__ partial, long nparts, doub
     }
     __syncthreads();
     if (t < 32) {
-        const unsigned long long g = *(volatile unsigned long long*)op_counter + 1;
+        const unsigned long long g = *(volatile const unsigned long long*)op_counter + (unsigned long long)epoch_off;
         double v[8];
 #pragma unroll
         for (int k = 0; k < 5; k++) v[k] = sums[k];
@@ -1284,7 +1285,6 @@ __global__ void k_rms_dist(const double* __restrict__ partial, long nparts, doub
             double tot = 0.0;
             for (int k = 0; k < 5; k++) { out[slot * 6 + 1 + k] = sqrt(v[k] / nel_global); tot += v[k]; }
             out[slot * 6] = sqrt(tot / nel_global);
-            *op_counter = g;
         }
     }
 }

@@ -194,7 +194,9 @@ int mgcfd_time_kernel(mgcfd_ctx* ctx, int level, int which, int reps, double* ms
  * its compile-time toggles select (src/Kernels/flux_kernel.elemfunc.c), as a benchmark kernel -- one thread per internal edge,
  * atomics, the same memory traffic for every variant.  bits: 1 = FLUX_REUSE_DIV (:46-71), 2 = FLUX_REUSE_FACTOR + FLUX_REUSE_FLUX
  * (:132-190), 4 = FLUX_PRECOMPUTE_EDGE_WEIGHTS (:24-28); 0 is the default build's arithmetic as written.  Accumulates into
- * `fluxes` like mgcfd_compute_flux_edge; mgcfd_time_kernel times variant `bits` as selector 16 + bits. */
+ * `fluxes` like mgcfd_compute_flux_edge; mgcfd_time_kernel times variant `bits` as selector 16 + bits.
+ * bits = 8: all three toggles with the node state gathered from an SoA copy (five planes) instead of the 64-byte node records --
+ * the layout A/B of DESIGN.md 3 (no reference counterpart; same results as bits = 7, bit for bit). */
 int mgcfd_flux_variant(mgcfd_ctx* ctx, int level, int bits);
 
 /* Host-only run of the integer preprocessing (no device needed): renumbering, tiling and colouring of one level.

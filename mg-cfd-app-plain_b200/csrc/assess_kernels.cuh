@@ -15,12 +15,18 @@ namespace mgcfd {
 
 struct APoint { double rho, mx, my, mz, re, vx, vy, vz, sq, speed, p, c; };
 
-template <bool REUSE_DIV>
-__host__ __device__ __forceinline__ APoint assess_point(const double* __restrict__ recs, long i) {
+// SOA: the node state as five planes of `stride` doubles (the layout BASELINE.json's north star names) instead of 64-byte records --
+// the A/B behind the choice of records: same arithmetic, same edges, same scatters, only the gathers differ
+template <bool REUSE_DIV, bool SOA = false>
+__host__ __device__ __forceinline__ APoint assess_point(const double* __restrict__ recs, long i, long stride = 0) {
     APoint s;
-    const double2* q = reinterpret_cast<const double2*>(recs + 8 * i);
-    const double2 a = q[0], b = q[1];
-    s.rho = a.x; s.mx = a.y; s.my = b.x; s.mz = b.y; s.re = recs[8 * i + 4];
+    if (SOA) {
+        s.rho = recs[i]; s.mx = recs[stride + i]; s.my = recs[2 * stride + i]; s.mz = recs[3 * stride + i]; s.re = recs[4 * stride + i];
+    } else {
+        const double2* q = reinterpret_cast<const double2*>(recs + 8 * i);
+        const double2 a = q[0], b = q[1];
+        s.rho = a.x; s.mx = a.y; s.my = b.x; s.mz = b.y; s.re = recs[8 * i + 4];
+    }
     if (REUSE_DIV) {
         const double r = 1.0 / s.rho;                       // compute_velocity_reciprocal / compute_speed_of_sound_reciprocal
         s.vx = s.mx * r; s.vy = s.my * r; s.vz = s.mz * r;
@@ -48,12 +54,12 @@ __host__ __device__ __forceinline__ void assess_contribution(const APoint& s, do
 
 // the increments of one internal edge for its end a (av) and its end b (bv), flux_kernel.elemfunc.c:18-190; ewt = |e| (computed
 // by the caller or read from the precomputed array)
-template <bool REUSE_DIV, bool REUSE_FLUX>
+template <bool REUSE_DIV, bool REUSE_FLUX, bool SOA = false>
 __host__ __device__ __forceinline__ void assess_edge(const double* __restrict__ recs, long a, long b, double ex, double ey, double ez, double ewt,
-                                                     double smoothing, double av[5], double bv[5]) {
-    const APoint B = assess_point<REUSE_DIV>(recs, b);
+                                                     double smoothing, double av[5], double bv[5], long stride = 0) {
+    const APoint B = assess_point<REUSE_DIV, SOA>(recs, b, stride);
     double fb[4][3]; assess_contribution(B, fb);
-    const APoint A = assess_point<REUSE_DIV>(recs, a);
+    const APoint A = assess_point<REUSE_DIV, SOA>(recs, a, stride);
     double fa[4][3]; assess_contribution(A, fa);
     const double factor_a = -ewt * smoothing * 0.5 * (A.speed + B.speed + A.c + B.c);
     const double fx = -0.5 * ex, fy = -0.5 * ey, fz = -0.5 * ez;
@@ -71,7 +77,7 @@ __host__ __device__ __forceinline__ void assess_edge(const double* __restrict__ 
     }
 }
 
-template <bool REUSE_DIV, bool REUSE_FLUX, bool PRE_EW>
+template <bool REUSE_DIV, bool REUSE_FLUX, bool PRE_EW, bool SOA = false>
 __global__ void k_flux_assess(long ne, const int* __restrict__ ea, const int* __restrict__ eb, const double* __restrict__ ew,
                               const double* __restrict__ ewt_pre, const double* __restrict__ recs, long stride, double* __restrict__ flux,
                               double smoothing) {
@@ -81,11 +87,19 @@ __global__ void k_flux_assess(long ne, const int* __restrict__ ea, const int* __
     const double ex = ew[e], ey = ew[ne + e], ez = ew[2 * ne + e];
     const double ewt = PRE_EW ? ewt_pre[e] : sqrt(ex * ex + ey * ey + ez * ez);
     double av[5], bv[5];
-    assess_edge<REUSE_DIV, REUSE_FLUX>(recs, a, b, ex, ey, ez, ewt, smoothing, av, bv);
+    assess_edge<REUSE_DIV, REUSE_FLUX, SOA>(recs, a, b, ex, ey, ez, ewt, smoothing, av, bv, stride);
 #pragma unroll
     for (int k = 0; k < 5; k++) atomicAdd(&flux[k * stride + a], av[k]);
 #pragma unroll
     for (int k = 0; k < 5; k++) atomicAdd(&flux[k * stride + b], bv[k]);
+}
+
+// the five conserved variables of every node as planes (for the SOA variant)
+__global__ void k_records_to_planes(long n, const double* __restrict__ recs, long stride, double* __restrict__ planes) {
+    const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 5; k++) planes[k * stride + i] = recs[8 * i + k];
 }
 
 // |e| of every internal edge (FLUX_PRECOMPUTE_EDGE_WEIGHTS: computed once, as the reference does at start-up)

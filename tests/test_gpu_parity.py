@@ -312,7 +312,7 @@ def test_assess_compute_flux_variants_match_oracle(M, oracle, name):
     want = np.zeros(5 * L["nel"])
     oracle.flux_edge(0, L["nI"], L["edges"], var, want)
     s.set_field(0, M.FIELD_VARIABLES, var)
-    for bits in range(8):
+    for bits in range(9):          # 8: all toggles, node state gathered from SoA planes (the layout A/B)
         s.zero_fluxes(0)
         s.flux_variant(0, bits)
         got = s.get_field(0, M.FIELD_FLUXES)

@@ -267,6 +267,30 @@ namespace {
 inline long blocks_for(long n, int bs) { return (n + bs - 1) / bs; }
 int env_int(const char* name, int dflt) { const char* e = getenv(name); return (e && *e) ? atoi(e) : dflt; }
 
+// Launch of a many-block kernel (transfers, RMS), optionally (MGCFD_PDL_TRANSFERS=1) as a programmatic dependent of its predecessor
+// in the stream: its blocks are then scheduled while the predecessor -- a stage kernel, which releases its dependents at its start --
+// still runs, and sit in griddepcontrol.wait (pdl_wait) until it has completed; the kernel never releases ITS dependents early.
+// Measured on B200 (profiles/r02H_pdl_transfers_ab.txt): 0.3695 vs 0.3494 ms per C2 cycle -- SLOWER, like round 1's variant that
+// also released early: blocks parked in the wait hold warp slots and registers next to the persistent stage CTAs for the whole
+// stage.  Hence off by default; kept as a measured switch.
+template <class... KArgs, class... Args>
+int launch_dependent(mgcfd_ctx* c, void (*kernel)(KArgs...), unsigned grid, unsigned block, Args&&... args) {
+    static const int on = env_int("MGCFD_PDL_TRANSFERS", 0);
+    if (!on || c->opt.no_pdl) {
+        kernel<<<grid, block, 0, c->stream>>>(KArgs(args)...);
+        return MGCFD_OK;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+    return MGCFD_OK;
+}
+
 // Tile size when the caller leaves it to the library (measured on B200, profiles/):
 //  * multi-million-node levels: 128-node tiles (more CTAs in flight per SM; 202 vs 197 cycles/s on the 8 M-node mesh);
 //  * smaller levels of low-degree meshes (hex-dual, <= 4 internal edges per node: a 128-node tile's whole edge stream fits the ring
@@ -646,11 +670,11 @@ int rms_final(mgcfd_ctx* c, Level& v, bool use_counter) {
     double* out = use_counter ? c->d_rms : c->d_rms + 6 * (c->rms_cap - 1);
     int* counter = use_counter ? c->d_rms_counter : nullptr;
     if (!c->dist.active) {
-        k_rms_final<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel, out, counter, c->rms_cap - 1);
+        CKRC(launch_dependent(c, k_rms_final, 1u, 256u, v.rms_partial, v.rms_parts, (double)v.nel, out, counter, c->rms_cap - 1));
         return post_launch(c);
     }
     if (c->dist.p2p) {      // one kernel: local sums, all-reduce over the ranks, square roots
-        k_rms_dist<<<1, 256, 0, c->stream>>>(v.rms_partial, v.rms_parts, (double)v.nel_global, out, counter, c->rms_cap - 1, allred_of(c), c->dist.d_op, c->dist.off++);
+        CKRC(launch_dependent(c, k_rms_dist, 1u, 256u, v.rms_partial, v.rms_parts, (double)v.nel_global, out, counter, c->rms_cap - 1, allred_of(c), c->dist.d_op, c->dist.off++));
         return post_launch(c);
     }
     // distributed: local sums of squares -> all-reduce(sum) of 5 doubles -> square roots over the global node count
@@ -840,6 +864,13 @@ int minword_arm(mgcfd_ctx* c, Level& v, DistTail& t) {
     return MGCFD_OK;
 }
 
+// a transfer kernel whose blocks are all resident at once (one wave) may release the stage kernel behind it early: the stage
+// CTAs then only ever take the place of transfer blocks that have exited (MGCFD_EARLY_RELEASE=0 switches it off)
+inline int release_early(mgcfd_ctx* c, unsigned nb) {
+    static const int on = env_int("MGCFD_EARLY_RELEASE", 1);
+    return (on && !c->opt.no_pdl && nb <= 12u * (unsigned)c->num_sms) ? 1 : 0;
+}
+
 int do_restrict(mgcfd_ctx* c, int lc) {
     Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
     Timed tm(c, K_RESTRICT, lc, vf.nel);
@@ -850,17 +881,18 @@ int do_restrict(mgcfd_ctx* c, int lc) {
     if (dist_inkernel(c)) {
         // reads the fine level's ghost rows (wait for the fine level's peers), delivers the coarse rows itself
         DistTail t = dist_tail(c, vc, vc.i_var, vf.d_peers, vf.npeers);
-        t.blk_wait = vc.d_rblk_wait;
+        t.blk_wait = vc.d_rblk_wait; t.release_early = release_early(c, nb);
         if (vc.visit || !vc.pipe) bm = nullptr;             // only a level whose stage kernels deliver their rows themselves picks the minimum up
         if (bm) CKRC(minword_arm(c, vc, t)); else if (vc.minword_state == 1) vc.minword_state = 2;
-        k_restrict<true><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, nullptr, t);
+        CKRC(launch_dependent(c, k_restrict<true>, nb, 128u, vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, nullptr, t));
         c->dist.exchanges++;
         vc.premin_valid = false;
         return post_launch(c);
     }
     DistTail none;
     memset(&none, 0, sizeof(none));
-    k_restrict<false><<<nb, 128, 0, c->stream>>>(vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, none);
+    none.release_early = release_early(c, nb);
+    CKRC(launch_dependent(c, k_restrict<false>, nb, 128u, vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, none));
     CKRC(post_launch(c));
     vc.premin_valid = (bm != nullptr);
     return dist_exchange_records(c, lc, vc.V(vc.i_var));
@@ -876,11 +908,11 @@ int do_prolong(mgcfd_ctx* c, int lf) {
         if (!vc.visit && !vc.pipe) CKRC(dist_exchange_residuals(c, lf + 1));
         DistTail t = dist_tail(c, vf, vf.i_var, vc.d_peers, vc.npeers);
         // (when the coarse level's residuals came through an exchange kernel just above, every block may run at once)
-        t.blk_wait = vf.d_pblk_wait;
+        t.blk_wait = vf.d_pblk_wait; t.release_early = release_early(c, nb);
         if (vf.visit || !vf.pipe) bm = nullptr;
         if (bm) CKRC(minword_arm(c, vf, t)); else if (vf.minword_state == 1) vf.minword_state = 2;
-        k_prolong<true><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
-                                                   vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, nullptr, t);
+        CKRC(launch_dependent(c, k_prolong<true>, nb, 128u, vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
+                              vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, nullptr, t));
         c->dist.exchanges++;
         vf.premin_valid = false;
         return post_launch(c);
@@ -888,8 +920,9 @@ int do_prolong(mgcfd_ctx* c, int lf) {
     CKRC(dist_exchange_residuals(c, lf + 1));
     DistTail none;
     memset(&none, 0, sizeof(none));
-    k_prolong<false><<<nb, 128, 0, c->stream>>>(vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
-                                                vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, bm, none);
+    none.release_early = release_early(c, nb);
+    CKRC(launch_dependent(c, k_prolong<false>, nb, 128u, vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
+                          vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, bm, none));
     CKRC(post_launch(c));
     vf.premin_valid = (bm != nullptr);
     return dist_exchange_records(c, lf, vf.V(vf.i_var));

@@ -186,6 +186,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// A kernel launched as a programmatic dependent (cudaLaunchAttributeProgrammaticStreamSerialization) may be scheduled while its
+// predecessor in the stream still runs: nothing the predecessor writes may be touched before this returns (it returns at once when
+// the kernel was launched the ordinary way).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // Every cross-GPU wait is bounded: a flag that has not arrived after a few seconds (4 M polls of ~1 us: nanosleep + a system-scope
 // load) means the ranks disagree on the protocol (or a rank has died) -- the kernel reports and traps, the host sees a CUDA error
 // instead of a hung device.
@@ -267,6 +271,8 @@ struct DistTail {
     const unsigned char* tile_sends;           // per tile of the kernel's granularity: any row with a target
     const int* order; int n_send;              // stage kernels: tiles in the order they are taken, the n_send ghost-reading (= delivering) tiles LAST
     const unsigned char* blk_wait;             // transfer kernels: per 128-row block, does it read a ghost row (only those blocks wait); nullptr: all wait
+    int release_early;                         // transfer kernels (one GPU too): let the next kernel of the stream -- a stage kernel launched as a programmatic
+                                               // dependent -- be scheduled as blocks of this one exit (its static prologue overlaps this kernel's tail)
     const unsigned long long* op_counter; int epoch_off; const unsigned long long* my_flags;
     // the minimum dt of the state a transfer kernel leaves behind: every block of the transfer kernel folds its minimum into ONE word
     // of the level (atomicMin on the bit pattern of a positive double: fire and forget, no fence, no ticket).  The first stage
@@ -940,6 +946,7 @@ __global__ void k_rms_partial(const double* __restrict__ r, long stride, long n,
 __global__ void k_rms_final(const double* __restrict__ partial, long nparts, double nel, double* __restrict__ out, int* counter, int cap) {
     __shared__ double ws[5][256];
     const int t = threadIdx.x;
+    pdl_wait();
     double s[5] = {0, 0, 0, 0, 0};
     for (long p = t; p < nparts; p += 256)
 #pragma unroll
@@ -1006,6 +1013,8 @@ template <bool DIST>
 __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ vc, long ncoarse,
                            const long* __restrict__ child_off, const int* __restrict__ child_ids, const double* __restrict__ vol_root,
                            double* __restrict__ blockmins, const DistTail d) {
+    pdl_wait();
+    if (d.release_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (DIST) dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks with ghost children wait for the fine level's owners
     const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double s_new = 0.0;          // |v| + c of the node's state after this kernel
@@ -1042,6 +1051,8 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
                           const long* __restrict__ ent_off, const int* __restrict__ ent_src, const double* __restrict__ ent_w,
                           const double* __restrict__ res_c, const double* __restrict__ res_f, double* __restrict__ var_f,
                           const double* __restrict__ vol_root, double* __restrict__ blockmins, const DistTail d) {
+    pdl_wait();
+    if (d.release_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (DIST) dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks that read a ghost parent's residual wait
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     const int p = (i < nfine) ? parent[i] : -1;
@@ -1260,6 +1271,7 @@ __global__ void k_rms_dist(const double* __restrict__ partial, long nparts, doub
     __shared__ double ws[5][256];
     __shared__ double sums[8];
     const int t = threadIdx.x;
+    pdl_wait();
     double s[5] = {0, 0, 0, 0, 0};
     for (long p = t; p < nparts; p += 256)
 #pragma unroll

@@ -1018,6 +1018,8 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
     if (DIST) dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks with ghost children wait for the fine level's owners
     const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double s_new = 0.0;          // |v| + c of the node's state after this kernel
+    const bool want_min = blockmins || (DIST && d.minword);
+    const double vroot = (want_min && c < ncoarse) ? vol_root[c] : 0.0;      // requested first: in flight behind the gather chain
     if (c < ncoarse) {
         const long k0 = child_off[c], k1 = child_off[c + 1];
         if (k1 > k0) {
@@ -1034,14 +1036,14 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
             s_new = n.s;
             if (DIST) dist_push_rec(d, c, n);
         } else {
-            if (blockmins || (DIST && d.minword)) s_new = vc[8 * c + 7];
+            if (want_min) s_new = vc[8 * c + 7];
             // a childless coarse node keeps its value; the copies other ranks hold of it must keep up with whatever the last
             // visit left in THIS buffer of theirs (their ghost rows are only ever written by the owner)
             if (DIST) { if (d.tgt_off[c + 1] > d.tgt_off[c]) dist_push_rec(d, c, load_rec(vc, c)); }
         }
     }
-    if (blockmins) block_min_store(c < ncoarse ? 0.5 * (vol_root[c] / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), blockmins);
-    if (DIST && d.minword) block_min_atomic(c < ncoarse ? 0.5 * (vol_root[c] / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), d.minword);
+    if (blockmins) block_min_store(c < ncoarse ? 0.5 * (vroot / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), blockmins);
+    if (DIST && d.minword) block_min_atomic(c < ncoarse ? 0.5 * (vroot / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), d.minword);
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
 // edges in original edge order: per edge the own-parent term then the neighbour-parent term (whose source is the own
@@ -1058,6 +1060,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
     const int p = (i < nfine) ? parent[i] : -1;
     double dt_new = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);      // padding rows (no parent) never win the minimum
     if (p >= 0) {
+        const bool want_min = blockmins || (DIST && d.minword);
         double rp[5];
 #pragma unroll
         for (int j = 0; j < 5; j++) rp[j] = res_c[j * scoarse + p];
@@ -1093,7 +1096,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
         }
         const Rec n = make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]);
         store_rec(var_f, i, n);
-        if (blockmins || (DIST && d.minword)) dt_new = 0.5 * (vol_root[i] / n.s);
+        if (want_min) dt_new = 0.5 * (vol_root[i] / n.s);
         if (DIST) dist_push_rec(d, i, n);
     }
     if (blockmins) block_min_store(dt_new, blockmins);

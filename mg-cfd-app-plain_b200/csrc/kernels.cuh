@@ -1088,15 +1088,26 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
                 wsum += w;
             }
         }
+        // the row's own state and residual: all ten loads requested together, ahead of the five divisions (one exposed latency
+        // instead of one per variable: the compiler kept each load next to its use, ncu source page of round 2)
+        double vf0[5], rf0[5];
+        {
+            const double2* q = reinterpret_cast<const double2*>(var_f + 8 * i);
+            const double2 a = q[0], b = q[1];
+            vf0[0] = a.x; vf0[1] = a.y; vf0[2] = b.x; vf0[3] = b.y; vf0[4] = var_f[8 * i + 4];
+        }
+#pragma unroll
+        for (int j = 0; j < 5; j++) rf0[j] = res_f[j * sfine + i];
+        const double vroot = want_min ? vol_root[i] : 0.0;
         double nv[5];
 #pragma unroll
         for (int j = 0; j < 5; j++) {
             const double avg = acc[j] / wsum;
-            nv[j] = var_f[8 * i + j] + (res_f[j * sfine + i] - avg);
+            nv[j] = vf0[j] + (rf0[j] - avg);
         }
         const Rec n = make_rec(nv[0], nv[1], nv[2], nv[3], nv[4]);
         store_rec(var_f, i, n);
-        if (want_min) dt_new = 0.5 * (vol_root[i] / n.s);
+        if (want_min) dt_new = 0.5 * (vroot / n.s);
         if (DIST) dist_push_rec(d, i, n);
     }
     if (blockmins) block_min_store(dt_new, blockmins);

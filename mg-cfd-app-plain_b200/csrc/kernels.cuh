@@ -1076,6 +1076,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
                 wsum = 1.0;
             }
         } else {
+#pragma unroll 4
             for (long k = k0; k < k1; k++) {
                 const int q = ent_src[k];
                 const double w = ent_w[k];

@@ -867,8 +867,8 @@ int minword_arm(mgcfd_ctx* c, Level& v, DistTail& t) {
 // a transfer kernel whose blocks are all resident at once (one wave) may release the stage kernel behind it early: the stage
 // CTAs then only ever take the place of transfer blocks that have exited (MGCFD_EARLY_RELEASE=0 switches it off)
 inline int release_early(mgcfd_ctx* c, unsigned nb) {
-    static const int on = env_int("MGCFD_EARLY_RELEASE", 1);
-    return (on && !c->opt.no_pdl && nb <= 12u * (unsigned)c->num_sms) ? 1 : 0;
+    static const int on = env_int("MGCFD_EARLY_RELEASE", 1), per_sm = env_int("MGCFD_EARLY_RELEASE_BLOCKS", 12);
+    return (on && !c->opt.no_pdl && nb <= (unsigned)per_sm * (unsigned)c->num_sms) ? 1 : 0;
 }
 
 int do_restrict(mgcfd_ctx* c, int lc) {

@@ -102,7 +102,9 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
 int mgcfd_destroy(mgcfd_ctx* ctx);
 
 /* globals ff_variable[5] and ff_flux_contribution_{momentum_x,momentum_y,momentum_z,density_energy}
- * (src/Base/globals.h:10-14) made explicit; ffc = 4 x double3 in that order. */
+ * (src/Base/globals.h:10-14) made explicit; ffc = 4 x double3 in that order.  Per context (the values travel in the kernel
+ * arguments): contexts on one device may hold different far fields.  mgcfd_create sets the reference's values
+ * (mgcfd_far_field_conditions); call this before mgcfd_finalize if the initial node state is to start from other ones. */
 int mgcfd_set_farfield(mgcfd_ctx* ctx, const double ff_variable[5], const double ff_flux_contribution[12]);
 /* host evaluation of initialize_far_field_conditions (src/Kernels/cfd_loops.h:85-119) */
 void mgcfd_far_field_conditions(double ff_variable[5], double ff_flux_contribution[12]);

@@ -393,6 +393,13 @@ class Solver:
         _check(lib().mgcfd_get_stream(self._h, C.byref(p)))
         return p.value or 0
 
+    def set_farfield(self, ff_variable, ff_flux_contribution):
+        """The far-field state of THIS solver (mgcfd_set_farfield; the reference's globals, globals.h:10-14): 5 + 12 doubles."""
+        v = np.ascontiguousarray(ff_variable, dtype=np.float64); c = np.ascontiguousarray(ff_flux_contribution, dtype=np.float64)
+        assert v.size == 5 and c.size == 12
+        dp = C.POINTER(C.c_double)
+        _check(lib().mgcfd_set_farfield(self._h, v.ctypes.data_as(dp), c.ctypes.data_as(dp)))
+
     def set_timing(self, on: bool): _check(lib().mgcfd_set_timing(self._h, int(on)))
 
     def get_field(self, level, field, out: Optional[np.ndarray] = None):

@@ -566,9 +566,15 @@ int launch_stage_dist(mgcfd_ctx* c, Level& v, const StageArgs& a) {
     return sc ? launch_pipe_t<512, true, true>(c, v, a) : launch_pipe_t<512, false, true>(c, v, a);
 }
 
+FarField far_field_of(const mgcfd_ctx* c) {
+    FarField F;
+    memcpy(F.v, c->ff, sizeof(F.v)); memcpy(F.c, c->ffc, sizeof(F.c));
+    return F;
+}
 StageArgs base_args(mgcfd_ctx* c, Level& v) {
     StageArgs a;
     memset(&a, 0, sizeof(a));
+    a.ff = far_field_of(c);
     a.stride = v.npad;
     a.hdrs = v.hdrs; a.hdr_stride = v.plan.hdr_stride;
     a.slots = v.slots; a.bslots = v.bslots;
@@ -610,7 +616,7 @@ int flux_granular(mgcfd_ctx* c, int l, int mask) {
         CKRC(post_launch(c));
     }
     if ((mask & 6) && (v.nB + v.nW)) {
-        k_bflux_atomic<<<(unsigned)blocks_for(v.nB + v.nW, 256), 256, 0, c->stream>>>(v.nB + v.nW, v.bnode, v.bkind, v.bw, v.V(v.i_var), v.npad, v.flux, mask);
+        k_bflux_atomic<<<(unsigned)blocks_for(v.nB + v.nW, 256), 256, 0, c->stream>>>(v.nB + v.nW, v.bnode, v.bkind, v.bw, v.V(v.i_var), v.npad, v.flux, mask, far_field_of(c));
         CKRC(post_launch(c));
     }
     return MGCFD_OK;
@@ -746,6 +752,7 @@ int smooth_visit(mgcfd_ctx* c, int l) {
     Timed tm(c, K_FLUX, l, MGCFD_RK * v.nI);
     VisitArgs a;
     memset(&a, 0, sizeof(a));
+    a.ff = far_field_of(c);
     a.bufX = v.V(X); a.bufA = v.V(A); a.bufB = v.V(B); a.ibX = X; a.ibA = A; a.ibB = B;
     a.res = v.res; a.sf = v.sf; a.vol = v.vol; a.vol_root = v.vol_root; a.stride = v.npad;
     a.hsum = v.d_hsum; a.hs_stride = v.ncomp;
@@ -1140,8 +1147,6 @@ int mgcfd_create(int levels, int mesh_variant, const mgcfd_options* opt, mgcfd_c
     CK(cudaMalloc((void**)&c->d_rms_counter, sizeof(int)));
     CK(cudaMemset(c->d_rms_counter, 0, sizeof(int)));
     mgcfd_far_field_conditions(c->ff, c->ffc);
-    CK(cudaMemcpyToSymbol(c_ff, c->ff, sizeof(c->ff)));
-    CK(cudaMemcpyToSymbol(c_ffc, c->ffc, sizeof(c->ffc)));
     *out = c;
     return MGCFD_OK;
 }
@@ -1167,8 +1172,8 @@ int mgcfd_destroy(mgcfd_ctx* c) {
 int mgcfd_set_farfield(mgcfd_ctx* c, const double ffv[5], const double ffc[12]) {
     if (!c || !ffv || !ffc) { g_err = "null argument"; return MGCFD_ERR_ARG; }
     memcpy(c->ff, ffv, sizeof(c->ff)); memcpy(c->ffc, ffc, sizeof(c->ffc));
-    CK(cudaMemcpyToSymbol(c_ff, c->ff, sizeof(c->ff)));
-    CK(cudaMemcpyToSymbol(c_ffc, c->ffc, sizeof(c->ffc)));
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);      // captured launches carry the far field in their arguments
+    c->graphs.clear(); c->graph_launches.clear(); c->graph_flags_end.clear();
     return MGCFD_OK;
 }
 
@@ -1337,7 +1342,7 @@ int mgcfd_finalize(mgcfd_ctx* c) {
         CK(cudaStreamSynchronize(s));
         // node state: every buffer starts at the far-field state (what initialize_variables leaves, cfd_loops.h:44-55);
         // padding nodes keep it forever (no edges, zero residual), which keeps them finite in every stage
-        for (int b = 0; b < 3; b++) { k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, s>>>(v.buf[b], v.npad); CKRC(post_launch(c)); }
+        for (int b = 0; b < 3; b++) { k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, s>>>(v.buf[b], v.npad, far_field_of(c)); CKRC(post_launch(c)); }
         CK(cudaMemsetAsync(v.res, 0, sizeof(double) * 5 * v.npad, s));
         CK(cudaMemsetAsync(v.sf, 0, sizeof(double) * v.npad, s));
     }
@@ -1387,7 +1392,7 @@ int mgcfd_initialize_variables(mgcfd_ctx* c, int l) {
     Level& v = c->L[l];
     v.premin_valid = false;
     if (v.minword_state == 1) v.minword_state = 2;
-    k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad);
+    k_fill_state<<<(unsigned)blocks_for(v.npad, 256), 256, 0, c->stream>>>(v.V(v.i_var), v.npad, far_field_of(c));
     return post_launch(c);
 }
 int mgcfd_copy_old_variables(mgcfd_ctx* c, int l) {

@@ -17,8 +17,10 @@
 namespace mgcfd {
 
 #define MG_GAMMA 1.4
-__device__ __constant__ double c_ff[5];      // ff_variable
-__device__ __constant__ double c_ffc[12];    // ff_flux_contribution_{momentum_x,y,z,density_energy}
+// the far-field state: ff_variable and ff_flux_contribution_{momentum_x,y,z,density_energy} (globals.h:10-14).  Travels by value in
+// the kernel arguments (the parameter constant bank: as cheap as a __constant__ symbol), so that two contexts on one device can hold
+// different far fields (the module-wide symbols of round 1 were shared by all contexts)
+struct FarField { double v[5]; double c[12]; };
 
 struct Rec { double rho, mx, my, mz, re, ir, p, s; };   // ir = 1/rho, s = |v| + speed of sound
 struct Flux5 { double r, mx, my, mz, e; };
@@ -141,15 +143,15 @@ __device__ __forceinline__ void boundary_flux_acc(const Rec& B, double x, double
     acc.mx += x * B.p; acc.my += y * B.p; acc.mz += z * B.p;
 }
 // wall edge (neighbour -2, far field): flux_wall_kernel.elemfunc.c:47-69
-__device__ __forceinline__ void wall_flux_acc(const Rec& B, double x, double y, double z, Flux5& acc) {
+__device__ __forceinline__ void wall_flux_acc(const FarField& F, const Rec& B, double x, double y, double z, Flux5& acc) {
     const double fx = 0.5 * x, fy = 0.5 * y, fz = 0.5 * z;
     const double g = fx * B.mx + fy * B.my + fz * B.mz;
     const double q = g * B.ir;
-    acc.r  += (fx * c_ff[1] + fy * c_ff[2] + fz * c_ff[3]) + g;
-    acc.e  += (fx * c_ffc[9] + fy * c_ffc[10] + fz * c_ffc[11]) + (B.re + B.p) * q;
-    acc.mx += (fx * c_ffc[0] + fy * c_ffc[1] + fz * c_ffc[2]) + (B.mx * q + B.p * fx);
-    acc.my += (fx * c_ffc[3] + fy * c_ffc[4] + fz * c_ffc[5]) + (B.my * q + B.p * fy);
-    acc.mz += (fx * c_ffc[6] + fy * c_ffc[7] + fz * c_ffc[8]) + (B.mz * q + B.p * fz);
+    acc.r  += (fx * F.v[1] + fy * F.v[2] + fz * F.v[3]) + g;
+    acc.e  += (fx * F.c[9] + fy * F.c[10] + fz * F.c[11]) + (B.re + B.p) * q;
+    acc.mx += (fx * F.c[0] + fy * F.c[1] + fz * F.c[2]) + (B.mx * q + B.p * fx);
+    acc.my += (fx * F.c[3] + fy * F.c[4] + fz * F.c[5]) + (B.my * q + B.p * fy);
+    acc.mz += (fx * F.c[6] + fy * F.c[7] + fz * F.c[8]) + (B.mz * q + B.p * fz);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -364,6 +366,7 @@ struct TileHdr {
 };
 
 struct StageArgs {
+    FarField ff;           // the context's far-field state (wall edges)
     const double* vin;     // records: stage input state
     const double* vold;    // records: old_variables (FUSED)
     double* vout;          // records: stage output state (FUSED)
@@ -474,20 +477,20 @@ __device__ __forceinline__ BSlot bslot_fetch(const unsigned char* blk, int t) {
     return b;
 }
 template <int TN>
-__device__ __forceinline__ void boundary_rounds(const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f, BSlot cur) {
+__device__ __forceinline__ void boundary_rounds(const FarField& F, const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f, BSlot cur) {
     for (int r = 0; r < br; r++) {
         BSlot nxt = {0, 0.0, 0.0, 0.0};
         if (r + 1 < br) nxt = bslot_fetch<TN>(blk + (size_t)(r + 1) * (TN * 25), t);
         if (cur.kind != 0 && ((mask >> cur.kind) & 1)) {
             if (cur.kind == 1) boundary_flux_acc(me, cur.x, cur.y, cur.z, f);
-            else wall_flux_acc(me, cur.x, cur.y, cur.z, f);
+            else wall_flux_acc(F, me, cur.x, cur.y, cur.z, f);
         }
         cur = nxt;
     }
 }
 template <int TN>
-__device__ __forceinline__ void boundary_rounds(const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f) {
-    if (br > 0) boundary_rounds<TN>(blk, br, t, mask, me, f, bslot_fetch<TN>(blk, t));
+__device__ __forceinline__ void boundary_rounds(const FarField& F, const unsigned char* blk, int br, int t, int mask, const Rec& me, Flux5& f) {
+    if (br > 0) boundary_rounds<TN>(F, blk, br, t, mask, me, f, bslot_fetch<TN>(blk, t));
 }
 // step factor of one node (cfd_loops.cpp:146-156 / :60): min_dt / volume, or the legacy local form.  Evaluated by the FIRST stage
 // of a smoothing visit (vold == vin), which stores it; the later stages read that value back (same bits, no second division).
@@ -584,7 +587,7 @@ k_stage(const StageArgs a) {
 
     Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (a.mask & 1) edge_rounds<TN, SCATTER>(a.slots + hdr->slot_blk0 * (long)(TN * 26), hdr->rounds, smraw, acc, t, me, me.re + me.p, a.k2, f);
-    if (a.mask & 6) boundary_rounds<TN>(a.bslots + hdr->bslot_blk0 * (long)(TN * 25), hdr->brounds, t, a.mask, me, f);
+    if (a.mask & 6) boundary_rounds<TN>(a.ff, a.bslots + hdr->bslot_blk0 * (long)(TN * 25), hdr->brounds, t, a.mask, me, f);
     if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
 
     if (!FUSED) {
@@ -797,7 +800,7 @@ k_stage_pipe(const StageArgs a) {
             consumed++;
             if (t == 0) produce(it + 1);
         }
-        boundary_rounds<TN>(bblk, brounds, t, a.mask, me, f, b0);
+        boundary_rounds<TN>(a.ff, bblk, brounds, t, a.mask, me, f, b0);
         if (SCATTER) { f.r += acc[0 * TN + t]; f.mx += acc[1 * TN + t]; f.my += acc[2 * TN + t]; f.mz += acc[3 * TN + t]; f.e += acc[4 * TN + t]; }
         if (DIST && recv_min_late && it == 0) min_dt = dist_recv_min(a.d, e0);       // the ranks' minima, sent by their last transfer kernel
         double sf = vol_or_sf;
@@ -905,10 +908,10 @@ __global__ void k_fill(double* __restrict__ p, long n, double val) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i < n) p[i] = val;
 }
-__global__ void k_fill_state(double* __restrict__ recs, long n) {
+__global__ void k_fill_state(double* __restrict__ recs, long n, const FarField F) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    store_rec(recs, i, make_rec(c_ff[0], c_ff[1], c_ff[2], c_ff[3], c_ff[4]));
+    store_rec(recs, i, make_rec(F.v[0], F.v[1], F.v[2], F.v[3], F.v[4]));
 }
 __global__ void k_copy(double* __restrict__ dst, const double* __restrict__ src, long n) {
     const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -1134,7 +1137,7 @@ __global__ void k_flux_atomic(long ne, const int* __restrict__ ea, const int* __
 }
 // boundary + wall edges, one thread per edge (a node can carry several, hence atomics)
 __global__ void k_bflux_atomic(long nb, const int* __restrict__ bnode, const uint8_t* __restrict__ bkind, const double* __restrict__ bw,
-                               const double* __restrict__ recs, long stride, double* __restrict__ flux, int mask) {
+                               const double* __restrict__ recs, long stride, double* __restrict__ flux, int mask, const FarField F) {
     const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
     if (e >= nb) return;
     const int kind = bkind[e];
@@ -1143,7 +1146,7 @@ __global__ void k_bflux_atomic(long nb, const int* __restrict__ bnode, const uin
     const Rec B = load_rec(recs, b);
     Flux5 f = {0.0, 0.0, 0.0, 0.0, 0.0};
     if (kind == 1) boundary_flux_acc(B, bw[e], bw[nb + e], bw[2 * nb + e], f);
-    else wall_flux_acc(B, bw[e], bw[nb + e], bw[2 * nb + e], f);
+    else wall_flux_acc(F, B, bw[e], bw[nb + e], bw[2 * nb + e], f);
     atomicAdd(&flux[b], f.r); atomicAdd(&flux[stride + b], f.mx); atomicAdd(&flux[2 * stride + b], f.my);
     atomicAdd(&flux[3 * stride + b], f.mz); atomicAdd(&flux[4 * stride + b], f.e);
 }

@@ -55,6 +55,7 @@ struct DistArgs {
 };
 
 struct VisitArgs {
+    FarField ff;                                  // the context's far-field state (wall edges)
     double* bufX; double* bufA; double* bufB;     // records: state at visit start (= old_variables), stage 0/2 output, stage 1 output
     int ibX, ibA, ibB;                            // their indices in the level's buffer triple (DIST: which peer buffer mirrors them)
     double* res; double* sf; const double* vol; const double* vol_root;
@@ -430,7 +431,7 @@ k_visit(const VisitArgs a) {
             }
             if (DBG) dbg_t = clock64();
             Flux5 f = edge_acc_finish(me, acc, hsx, hsy, hsz);
-            boundary_rounds<VT>(bblk, brounds, bl, 7, me, f, b0);
+            boundary_rounds<VT>(a.ff, bblk, brounds, bl, 7, me, f, b0);
             double sfv = vol_or_sf;
             if (first_stage) {
                 if (!have_min) {          // first update of the visit: barrier 0 must have completed

@@ -541,3 +541,26 @@ def test_guard_zones_do_report_an_overrun(M):
     s = M.Solver.from_mesh(make(M, "hex3"))          # without MGCFD_GUARD there are no zones: the self-test refuses, the check returns 0
     assert M.lib().mgcfd_guard_selftest(s._h) != 0 and M.guard_check()[0] == 0
     s.close()
+
+
+def test_two_contexts_keep_their_own_far_field(M, oracle):
+    """the far-field state used to live in module-wide __constant__ symbols, so mgcfd_set_farfield on one context
+    changed every context of the device.  It now travels in the kernel arguments: a second solver with another far field, driven
+    in alternation (graph replays included), leaves the first one's results on the oracle's."""
+    mesh = make(M, "hex_nonnested")
+    lv = mesh_levels(mesh, apply_ewt_with=oracle)
+    ora, _, st = oracle.run_cycles(mesh.mesh_variant, lv, 6)
+    s1 = M.Solver.from_mesh(mesh)
+    mesh2 = make(M, "hex_nonnested")
+    s2 = M.Solver.from_mesh(mesh2)
+    ffv, ffc = M.far_field_conditions()
+    s2.set_farfield(ffv * np.array([1.0, 0.5, 0.5, 0.5, 1.0]), ffc * 0.5)
+    ra1, ra2 = [], []
+    for _ in range(3):
+        ra1.append(s1.run_cycles(2)[0]); ra2.append(s2.run_cycles(2)[0])
+    ra1, ra2 = np.concatenate(ra1), np.concatenate(ra2)
+    assert np.max(np.abs(ra1 - ora) / ora) < TOL
+    for l in range(mesh.levels):
+        assert np.all(linf_rel(s1.get_field(l, M.FIELD_VARIABLES), st[l]["var"]) < TOL)
+    assert np.max(np.abs(ra2 - ora) / ora) > 1e-3          # the other far field did take effect on the second solver
+    s1.close(); s2.close()

@@ -40,6 +40,13 @@ int mgcfd_mesh_upload_partition(mgcfd_mesh* m, mgcfd_ctx* ctx);
  * global ids in send order. Any output pointer may be NULL. */
 int mgcfd_mesh_partition_plan(mgcfd_mesh* m, int nranks, int rank, int level, long info[8], long* gid, long* send_counts,
                               long* recv_counts, long* send_gids);
+/* Host-only check of the in-kernel halo exchange's tables for the whole partition at once (no device, one process): every rank's
+ * levels are numbered as mgcfd_finalize numbers them, every rank's row -> (peer, remote row) targets and tile order are built as
+ * mgcfd_dist_p2p_attach builds them, and the delivery is replayed on global node ids.  out[0] rows delivered, out[1] ghost rows over
+ * all ranks and levels (equal when every ghost row has exactly one producer), out[2] errors (a row delivered to a ghost row holding
+ * another node, a ghost row hit twice or never, a broken tile order), out[3] tiles that read a ghost row without being among the
+ * tiles the stage kernel takes last, out[4] transfer-kernel blocks that wait for a peer.  tile_nodes = 0: the automatic choice. */
+int mgcfd_mesh_delivery_check(mgcfd_mesh* m, int nranks, int tile_nodes, long out[5]);
 /* -m / --mesh-duplicate-count: `count` independent copies of every level, laid out as duplicate_mesh (io_enhanced.cpp:89-201) */
 int mgcfd_mesh_duplicate(mgcfd_mesh* m, int count);
 void mgcfd_mesh_free(mgcfd_mesh* m);

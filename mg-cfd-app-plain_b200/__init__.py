@@ -119,6 +119,7 @@ def lib() -> C.CDLL:
     L.mgcfd_mesh_upload_partition.argtypes = [vp, vp]
     L.mgcfd_mesh_duplicate.argtypes = [vp, i]
     L.mgcfd_mesh_partition_plan.argtypes = [vp, i, i, i, C.POINTER(l), vp, vp, vp, vp]
+    L.mgcfd_mesh_delivery_check.argtypes = [vp, i, i, C.POINTER(l)]
     L.mgcfd_dist_get_unique_id.argtypes = [C.c_char_p]
     L.mgcfd_dist_init.argtypes = [vp, i, i, C.c_char_p]
     L.mgcfd_dist_level_info.argtypes = [vp, i, C.POINTER(l)]
@@ -500,6 +501,14 @@ def partition_plan(mesh: Mesh, nranks: int, rank: int, level: int):
     _check(L.mgcfd_mesh_partition_plan(mesh._h, nranks, rank, level, info, _ptr(gid), _ptr(sc), _ptr(rc), _ptr(sg)), mesh=True)
     return dict(owned=owned, ghosts=ghosts, sent=sent, global_nodes=info[3], nI=info[4], nB=info[5], nW=info[6], hash=info[7], gid=gid,
                 send_counts=sc, recv_counts=rc, send_gids=sg[:sent])
+
+
+def delivery_check(mesh: Mesh, nranks: int, tile_nodes: int = 0):
+    """Host-only: the tables of the in-kernel halo exchange for all `nranks` ranks at once, replayed on global node ids
+    (mgcfd_mesh_delivery_check, include/mgcfd_mesh.h)."""
+    out = (C.c_long * 5)()
+    _check(lib().mgcfd_mesh_delivery_check(mesh._h, nranks, tile_nodes, out), mesh=True)
+    return dict(delivered=out[0], ghost_rows=out[1], errors=out[2], ghost_reading_tiles_not_last=out[3], waiting_transfer_blocks=out[4])
 
 
 def generate_partition_plan(kind: int, dims, nranks: int, rank: int, level: int, mesh_variant: int = MESH_M6_WING,

@@ -9,6 +9,7 @@
 #include <string>
 #include <memory>
 #include <mutex>
+#include <stdexcept>
 #include <vector>
 
 #include "../../include/mgcfd_b200.h"
@@ -2042,18 +2043,10 @@ int mgcfd_dist_p2p_attach(mgcfd_ctx* c, const char* handles, const long* tables,
         CKRC(dev_upload(&v.d_tile_sends, st.tile_sends, c->stream));
         if (v.pipe) { CKRC(setup_pipe_dist(c, v)); if (v.pipe_grid_dist < 1) v.pipe = false; }
         // tiles in the order the stage kernel takes them: the tiles that own rows on send lists -- the only ones that read ghost
-        // rows, flux halos being symmetric -- LAST (stable otherwise)
+        // rows, flux halos being symmetric -- LAST (stable otherwise); build_tile_order (partition.h) also looks at the halo lists
         {
-            const long nu = (v.ncomp + v.TN - 1) / v.TN;
-            std::vector<char> sends(nu, 0);
-            for (long r = 0; r < v.ncomp; r++) if (st.off[r + 1] > st.off[r]) sends[r / v.TN] = 1;
-            // a tile that reads a ghost row without owning a sent row would break the late wait: check the halo lists
-            for (long t = 0; t < (long)v.plan.ntiles && t < nu; t++)
-                for (long k = v.plan.halo_off[t]; k < v.plan.halo_off[t + 1]; k++) if (v.plan.halo_ids[k] >= v.ncomp) sends[t] = 1;
             std::vector<int> order;
-            for (long u = 0; u < nu; u++) if (!sends[u]) order.push_back((int)u);
-            v.n_send_tiles = (int)(nu - (long)order.size());
-            for (long u = 0; u < nu; u++) if (sends[u]) order.push_back((int)u);
+            v.n_send_tiles = build_tile_order(v.ncomp, v.TN, st, v.plan.halo_off, v.plan.halo_ids, (long)v.plan.ntiles, order);
             CKRC(dev_upload(&v.d_order_tiles, order, c->stream));
         }
     }
@@ -2118,6 +2111,106 @@ int mgcfd_partition_plan(int levels, const void* host_mesh_opaque, int nranks, i
     try { partition_mesh(full, nranks, rank, loc); }
     catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     fill_plan_outputs(loc.levels[level], full.levels[level].nel, nranks, info, gid, send_counts, recv_counts, send_gids);
+    return MGCFD_OK;
+}
+
+// Host-only check of the in-kernel halo exchange's tables (no device is touched): the mesh is split over `nranks` ranks in this one
+// process, every rank's levels are planned as mgcfd_finalize would (same numbering), every rank builds its row -> (peer, remote row)
+// targets and its tile order as mgcfd_dist_p2p_attach does -- from what the OTHER ranks would publish (first ghost row, recv_off) --
+// and the delivery is replayed on global node ids: a producer "stores" the id of each of its rows into the target rows.
+//   out[0] rows delivered   out[1] ghost rows over all ranks and levels
+//   out[2] errors: a row delivered to a ghost row that holds another node, a ghost row hit twice or never
+//   out[3] tiles that read a ghost row in their halo but are not among the tiles taken last (the late wait would miss them)
+//   out[4] transfer-kernel blocks that read a ghost row (children of owned coarse rows / parents and operator sources of owned fine rows)
+int mgcfd_mesh_delivery_check_impl(const void* host_mesh_opaque, int nranks, int tile_nodes, long out[5]) {
+    if (!host_mesh_opaque || !out || nranks < 1) { g_err = "bad arguments"; return MGCFD_ERR_ARG; }
+    const HostMesh& full = *(const HostMesh*)host_mesh_opaque;
+    const int nl = (int)full.levels.size();
+    for (int k = 0; k < 5; k++) out[k] = 0;
+    try {
+        std::vector<LocalMesh> loc(nranks);
+        for (int r = 0; r < nranks; r++) partition_mesh(full, nranks, r, loc[r]);
+        std::vector<std::vector<LevelPlan>> plans(nranks, std::vector<LevelPlan>(nl));
+        for (int l = 0; l < nl; l++) {
+            std::vector<std::vector<long>> row_gid(nranks);      // device row -> global node id (-1: padding)
+            for (int r = 0; r < nranks; r++) {
+                const LocalLevel& LL = loc[r].levels[l];
+                HostLevel H = LL.mesh;
+                H.n_owned = LL.n_owned;
+                PlanOptions po;
+                po.ordering = MGCFD_ORDER_PARTITION_RCM; po.scatter = false; po.strict = false;
+                po.tile_nodes = tile_nodes ? tile_nodes : auto_tile_nodes(LL.n_owned, H.nI, 148);
+                build_level_plan(H, po, plans[r][l]);
+                const LevelPlan& P = plans[r][l];
+                row_gid[r].assign(P.npad, -1);
+                for (long i = 0; i < P.nel; i++) row_gid[r][P.new_of_old[i]] = LL.gid[i];
+                for (long j = 0; j < P.nel - P.n_owned; j++)
+                    if (P.new_of_old[P.n_owned + j] != P.npad_owned + j) throw std::runtime_error("ghost rows do not follow the owned tiles in order");
+                out[1] += P.nel - P.n_owned;
+            }
+            std::vector<std::vector<int>> hits(nranks);
+            for (int r = 0; r < nranks; r++) hits[r].assign(plans[r][l].npad, 0);
+            for (int r = 0; r < nranks; r++) {
+                const LocalLevel& LL = loc[r].levels[l];
+                const LevelPlan& P = plans[r][l];
+                std::vector<int> send_rows(LL.send_idx.size());
+                for (size_t k = 0; k < send_rows.size(); k++) send_rows[k] = (int)P.new_of_old[LL.send_idx[k]];
+                std::vector<PeerSlice> slices;
+                std::vector<int> peer_rank;
+                for (int p = 0; p < nranks; p++) {
+                    const long ns = LL.send_off[p + 1] - LL.send_off[p], nr = LL.recv_off[p + 1] - LL.recv_off[p];
+                    if (p == r || (ns == 0 && nr == 0)) continue;
+                    const LocalLevel& PL = loc[p].levels[l];
+                    if (PL.recv_off[r + 1] - PL.recv_off[r] != ns) throw std::runtime_error("send / receive lists of two ranks do not match");
+                    PeerSlice sl;
+                    sl.send0 = LL.send_off[p]; sl.nsend = ns; sl.first_ghost_row = plans[p][l].npad_owned; sl.recv_off_me = PL.recv_off[r];
+                    slices.push_back(sl); peer_rank.push_back(p);
+                }
+                SendTargets st;
+                build_send_targets(P.npad_owned, P.TN, send_rows, slices, st);
+                for (long row = 0; row < P.npad_owned; row++)
+                    for (int k = st.off[row]; k < st.off[row + 1]; k++) {
+                        const int p = peer_rank[st.peer[k]];
+                        const long tr = st.row[k];
+                        out[0]++;
+                        if (tr < plans[p][l].npad_owned || tr >= plans[p][l].npad || row_gid[p][tr] != row_gid[r][row] || row_gid[r][row] < 0) out[2]++;
+                        else hits[p][tr]++;
+                    }
+                std::vector<int> order;
+                const int n_last = build_tile_order(P.npad_owned, P.TN, st, P.halo_off, P.halo_ids, (long)P.ntiles, order);
+                std::vector<char> last(order.size(), 0);
+                for (size_t k = order.size() - (size_t)n_last; k < order.size(); k++) last[order[k]] = 1;
+                for (long t = 0; t < (long)P.ntiles; t++)
+                    for (long k = P.halo_off[t]; k < P.halo_off[t + 1]; k++) if (P.halo_ids[k] >= P.npad_owned && !last[t]) { out[3]++; break; }
+                std::vector<char> seen(order.size(), 0);
+                for (int u : order) { if (u < 0 || u >= (int)order.size() || seen[u]) out[2]++; else seen[u] = 1; }
+            }
+            for (int r = 0; r < nranks; r++) {
+                const LevelPlan& P = plans[r][l];
+                for (long row = P.npad_owned; row < P.npad_owned + (P.nel - P.n_owned); row++) if (hits[r][row] != 1) out[2]++;
+            }
+        }
+        // the transfer kernels' per-block wait flags (mgcfd_finalize): count the 128-row blocks that read a ghost row
+        for (int r = 0; r < nranks; r++)
+            for (int l = 0; l + 1 < nl; l++) {
+                HostLevel Hf = loc[r].levels[l].mesh, Hc = loc[r].levels[l + 1].mesh;
+                Hf.n_owned = loc[r].levels[l].n_owned; Hc.n_owned = loc[r].levels[l + 1].n_owned;
+                TransferPlan T;
+                build_transfer_plan(Hf, Hc, plans[r][l], plans[r][l + 1], T);
+                const long ncf = plans[r][l].npad_owned, ncc = plans[r][l + 1].npad_owned;
+                std::vector<char> rw(std::max<long>(1, (ncc + 127) / 128), 0), pw(std::max<long>(1, (ncf + 127) / 128), 0);
+                for (long cc = 0; cc < ncc; cc++)
+                    for (long k = T.child_off[cc]; k < T.child_off[cc + 1]; k++) if (T.child_ids[k] >= ncf) { rw[cc / 128] = 1; break; }
+                for (long i = 0; i < ncf; i++) {
+                    bool g = T.parent[i] >= ncc;
+                    for (long k = T.ent_off[i]; k < T.ent_off[i + 1] && !g; k++) g = T.ent_src[k] >= ncc;
+                    if (g) pw[i / 128] = 1;
+                }
+                for (char x : rw) out[4] += x;
+                for (char x : pw) out[4] += x;
+            }
+    }
+    catch (const std::exception& ex) { g_err = ex.what(); return MGCFD_ERR_ARG; }
     return MGCFD_OK;
 }
 

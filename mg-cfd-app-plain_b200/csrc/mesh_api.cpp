@@ -112,6 +112,14 @@ int mgcfd_upload_partition(mgcfd_ctx* c, int levels, int mesh_variant, const voi
 int mgcfd_partition_plan(int levels, const void* host_mesh_opaque, int nranks, int rank, int level, long info[8], long* gid,
                          long* send_counts, long* recv_counts, long* send_gids);
 
+int mgcfd_mesh_delivery_check_impl(const void* host_mesh_opaque, int nranks, int tile_nodes, long out[5]);
+int mgcfd_mesh_delivery_check(mgcfd_mesh* m, int nranks, int tile_nodes, long out[5]) {
+    if (!m) { g_mesh_err = "null argument"; return MGCFD_ERR_ARG; }
+    int rc = mgcfd_mesh_delivery_check_impl(&m->m, nranks, tile_nodes, out);
+    if (rc) g_mesh_err = mgcfd_last_error();
+    return rc;
+}
+
 int mgcfd_mesh_upload_partition(mgcfd_mesh* m, mgcfd_ctx* ctx) {
     if (!m || !ctx) { g_mesh_err = "null argument"; return MGCFD_ERR_ARG; }
     int rc = mgcfd_mesh_apply_ewt(m);

@@ -359,6 +359,21 @@ void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant,
     clk.lap("local meshes");
 }
 
+int build_tile_order(long owned_rows, int tile_nodes, const SendTargets& st, const std::vector<long>& halo_off, const std::vector<int>& halo_ids,
+                     long ntiles, std::vector<int>& order) {
+    const long nu = (owned_rows + tile_nodes - 1) / tile_nodes;
+    std::vector<char> sends(nu, 0);
+    for (long r = 0; r < owned_rows; r++) if (st.off[r + 1] > st.off[r]) sends[r / tile_nodes] = 1;
+    // a tile that reads a ghost row without owning a delivered row would break the late wait: look at the halo lists as well
+    for (long t = 0; t < ntiles && t < nu; t++)
+        for (long k = halo_off[t]; k < halo_off[t + 1]; k++) if (halo_ids[k] >= owned_rows) sends[t] = 1;
+    order.clear();
+    for (long u = 0; u < nu; u++) if (!sends[u]) order.push_back((int)u);
+    const int n_last = (int)(nu - (long)order.size());
+    for (long u = 0; u < nu; u++) if (sends[u]) order.push_back((int)u);
+    return n_last;
+}
+
 void build_send_targets(long owned_rows, int tile_nodes, const std::vector<int>& send_rows, const std::vector<PeerSlice>& peers, SendTargets& out) {
     out = SendTargets();
     out.off.assign(owned_rows + 1, 0);

@@ -70,6 +70,11 @@ struct SendTargets {
     std::vector<int> off, peer, row;   // CSR over this rank's owned rows: node -> (index into the peer list, row in that peer's arrays)
     std::vector<unsigned char> tile_sends;   // per tile: any node with a target
 };
+// the order in which the distributed stage kernel takes its tiles: the tiles that deliver rows or read a ghost row in their halo
+// LAST (stable otherwise); returns how many those are.  halo_off / halo_ids: the plan's per-tile halo lists (device rows; rows
+// >= owned_rows are ghosts).
+int build_tile_order(long owned_rows, int tile_nodes, const SendTargets& st, const std::vector<long>& halo_off, const std::vector<int>& halo_ids,
+                     long ntiles, std::vector<int>& order);
 // throws std::runtime_error when a send-list entry is not an owned row
 void build_send_targets(long owned_rows, int tile_nodes, const std::vector<int>& send_rows, const std::vector<PeerSlice>& peers, SendTargets& out);
 

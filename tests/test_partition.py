@@ -107,6 +107,27 @@ def test_duplicated_meshes_are_dealt_out_copy_by_copy(copies, nranks):
             assert any(p["ghosts"] > 0 for p in plans)
 
 
+@pytest.mark.parametrize("kind,dims", MESHES + [(0, [[26, 24, 22], [13, 12, 11], [7, 6, 6], [4, 3, 3]]), (0, [[16, 8, 8], [8, 4, 4], [2, 2, 2]])])
+@pytest.mark.parametrize("nranks", [2, 3, 4, 8])
+@pytest.mark.parametrize("tile_nodes", [0, 128, 256])
+def test_in_kernel_delivery_tables(kind, dims, nranks, tile_nodes):
+    """The multi-GPU V-cycle has no exchange kernel: the kernel that produces a row stores it into the peers' ghost rows
+    (DESIGN.md 5).  The tables behind that -- row -> (peer, remote row) from what the peers publish, the tile order with the
+    ghost-reading tiles last, the transfer kernels' per-block wait flags -- are built here for every rank of the partition by the
+    code mgcfd_dist_p2p_attach runs, and the delivery is replayed on global node ids: every ghost row of every rank and level is
+    written exactly once, with the node it holds; no tile outside the last group reads a ghost row."""
+    mesh = M.Mesh.generate(kind, dims, mesh_variant=0 if kind == 2 else 2)
+    r = M.delivery_check(mesh, nranks, tile_nodes)
+    assert r["errors"] == 0 and r["ghost_reading_tiles_not_last"] == 0, r
+    assert r["delivered"] == r["ghost_rows"] > 0, r
+    ghosts = sum(M.partition_plan(mesh, nranks, rk, l)["ghosts"] for rk in range(nranks) for l in range(mesh.levels))
+    assert r["ghost_rows"] == ghosts
+    if mesh.levels > 1:
+        assert r["waiting_transfer_blocks"] > 0          # some restrict / prolong blocks read rows of other ranks, most do not
+    one = M.delivery_check(mesh, 1, tile_nodes)
+    assert one == dict(delivered=0, ghost_rows=0, errors=0, ghost_reading_tiles_not_last=0, waiting_transfer_blocks=0)
+
+
 def _gloo_worker(rank, world, port, q, rank_local=False):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))

@@ -384,7 +384,7 @@ int run_single(mgcfd_mesh* mesh) {
 }
 
 // ---- N GPUs: one forked process per GPU ------------------------------------------------------------------------------------------
-const int MAX_RANKS = 64, MAX_TABLE = 1 + 8 * (2 + MAX_RANKS + 1) + 8 * 25;      // 8 levels; + the in-kernel-exchange block (MGCFD_P2P_FUSED)
+const int MAX_RANKS = 64, MAX_TABLE = 1 + 8 * (2 + MAX_RANKS + 1) + 8 * 25;      // 8 levels; + the slab block of the in-kernel exchange (mgcfd_dist_p2p_table_len)
 struct Shared {                                   // lives in an anonymous MAP_SHARED mapping created before the fork
     std::atomic<int> arrived, generation, abort_flag;
     char nccl_id[128];

@@ -209,10 +209,7 @@ struct PeerOut {
     double* res;                   // the peer's residual planes
     long res_stride;               // the peer's npad
 };
-// remote stores + start / end synchronisation of a many-CTA kernel (restrict, prolong).  Every collective step of a distributed
-// run carries an EPOCH number that advances alike on all ranks (op_counter, on the device, so that graphs can be replayed):
-// a kernel waits at its start until the ranks it reads ghost rows from have signalled the epoch it starts in, stores the rows
-// it produces straight into the peers' copies, and its last CTA (ticket) fences system-wide and signals epoch + 1.
+// (the protocol -- epochs, announcements, late waits -- is described at struct DistTail below)
 // all-reduce plumbing of a rank (as k_p2p_allreduce): every rank's window has reduction slots [parity][source rank][8]
 struct AllRed {
     int nranks, me;
@@ -259,7 +256,7 @@ __device__ __forceinline__ void dist_allreduce(const AllRed& d, unsigned long lo
 //   * ANNOUNCES, at its start, that this rank's kernels up to e - 1 are complete: block 0 writes e into flags[me] of every
 //     neighbour rank.  The completion of a grid makes its stores -- remote ones included -- visible before the next grid of the
 //     stream starts, so nothing has to be fenced or counted inside the producing kernel (the first versions did: a system-scope
-//     fence per CTA and a grid-wide ticket per kernel cost more than the NVLink latency they guarded, profiles/r02t_distperf.jsonl);
+//     fence per CTA and a grid-wide ticket per kernel cost more than the NVLink latency they guarded, profiles/r02_dist_overhead_history.jsonl);
 //   * WAITS until flags[p] >= e for the ranks p it reads ghost rows of -- as late as it can: the stage kernel takes the tiles that
 //     read no ghost row first and checks the flags only before it prefetches its first ghost-reading tile, so the one-way flag
 //     latency (3.2 us, profiles/r02q_p2p_pingpong.txt) hides behind interior tiles;

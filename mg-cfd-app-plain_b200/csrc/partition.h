@@ -57,7 +57,7 @@ struct LevelSource {
 };
 void partition_sources(const std::vector<LevelSource>& levels, int mesh_variant, int nranks, int rank, LocalMesh& out);
 
-// In-kernel halo exchange (MGCFD_P2P_FUSED, kernels.cuh k_stage_pipe<.., DIST>): where the records of this rank's send-list nodes
+// In-kernel halo exchange (kernels.cuh: k_stage_pipe<.., DIST>, k_restrict<DIST>, k_prolong<DIST>): where the records of this rank's send-list nodes
 // go.  The k-th node this rank sends to peer p is p's ghost row  first_ghost_row_p + recv_off_p[this rank] + k  (ghost rows follow
 // the owned tiles, grouped by owner in rank order: partition.h).  Pure host arithmetic, shared by mgcfd_dist_p2p_attach and the
 // host regression harness.

@@ -47,7 +47,7 @@ int main() {
                     mixv(T.child_off); mixv(T.child_ids); mixv(T.parent); mixv(T.idist_own); mixv(T.ent_off); mixv(T.ent_src); mixv(T.ent_w);
                 }
             }
-            // in-kernel halo exchange (MGCFD_P2P_FUSED): every rank "stores" the global id of its send-list nodes through
+            // in-kernel halo exchange: every rank "stores" the global id of its send-list nodes through
             // build_send_targets into the peers' row space; every ghost row must receive exactly its own node, exactly once
             for (size_t l = 0; l < full.levels.size(); l++) {
                 std::vector<std::vector<long>> rows(nr), writes(nr);

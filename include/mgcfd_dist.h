@@ -3,8 +3,10 @@
  * prolongation, the coarse residuals of ghost nodes before a prolongation, and two scalar all-reduces (min dt per smoothing
  * visit: src/Kernels/cfd_loops.cpp:138-150; RMS sums per cycle: validation.cpp:91-105).  Two data planes, same results:
  *   - peer-to-peer (mgcfd_dist_p2p_prepare / _attach, the default of bench.py and the driver): every kernel that PRODUCES a row
- *     stores it straight into the other ranks' copies over NVLink (one CUDA IPC slab per rank); the persistent visit kernel's
- *     grid barriers double as the halo exchange; the whole distributed V-cycle is one replayed CUDA graph;
+ *     stores it straight into the other ranks' copies over NVLink (one CUDA IPC slab per rank) and every kernel that READS ghost
+ *     rows waits for its neighbours' epoch flags as late as it can -- no exchange kernel is left in a V-cycle; with
+ *     the optional persistent visit kernel the grid barriers double as the halo exchange; the whole distributed V-cycle is one
+ *     replayed CUDA graph;
  *   - NCCL (no attach): packing kernels + grouped ncclSend/ncclRecv + ncclAllReduce between the stage kernels, launched eagerly
  *     (MGCFD_DIST_GRAPH=1 captures them too).
  * The reference has no distributed path at all (single process): nothing here replaces a reference
@@ -48,8 +50,8 @@ int mgcfd_generate_partition_plan(int kind, int levels, const long* dims, const 
 /* Direct peer-to-peer data path (after the upload): prepare returns the 64-byte cudaIpcMemHandle of this rank's slab (window of
  * flags / reduction slots / staging + the record buffers and residual planes of every level) and a table of offsets
  * (mgcfd_dist_p2p_table_len longs); the launcher all-gathers handles and tables in rank order; attach maps the peers' slabs, builds
- * the row -> (peer, remote row) tables and switches the data plane.  From then on restrict, prolong and the visit kernel deliver the
- * rows they produce themselves and synchronise through epoch numbers in system-scope flags (every rank runs the same kernel
+ * the row -> (peer, remote row) tables and switches the data plane.  From then on the stage kernels, restrict, prolong (and the visit
+ * kernel) deliver the rows they produce themselves and synchronise through epoch numbers in system-scope flags (every rank runs the same kernel
  * sequence, so the epochs advance alike on all ranks -- also on a rank that has no halo at some level).  One process per GPU, all
  * GPUs peer-accessible (NVLink / NVSwitch).  MGCFD_NO_P2P=1 in the launchers keeps the NCCL plane. */
 long mgcfd_dist_p2p_table_len(mgcfd_ctx* ctx);

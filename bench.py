@@ -13,11 +13,12 @@ a cycle performs  sum_l E_I(l) * RK(3) * visits(l)  of them (BASELINE.json metri
            state resident in HBM, L2 flushed before every timed cycle, max over ranks)
   e2e    = the same metric through the public API with HOST buffers: every step copies level-0 `variables` from pinned
            host memory (set_field), runs one cycle (run_cycles -> RMS back), and reads `variables` back (get_field)
-  roofline = the dominant kernel, the persistent visit kernel on level 0 (k_visit: minimum dt + the three RK stages
-           compute_flux_edge + boundary + wall flux + time_step + residual in ONE launch): algorithmic bytes per launch
-           3 * (32*E_I + 28*(E_B+E_W) + 128*N) / its mean launch duration, measured with CUDA events in a second pass over
-           the same K cycles (every kernel bracketed by its own event pair); peak = MEASURED_PEAKS.json hbm_gbs.  When the level
-           is too large for the visit kernel the stage kernel (one launch per RK stage) is reported the same way.
+  roofline = the dominant kernel, the fused stage kernel on level 0 (k_stage_pipe: compute_flux_edge + boundary + wall flux +
+           time_step in one launch per Runge-Kutta stage): algorithmic bytes per launch 32*E_I + 28*(E_B+E_W) + 128*N
+           / its mean launch duration, measured with CUDA events in a second pass over the same K cycles (the three stage
+           launches of a smoothing visit share one event pair, so that they overlap as in the replayed graph); peak =
+           MEASURED_PEAKS.json hbm_gbs; traffic = DRAM bytes per launch from the ncu capture (profiles/traffic.json).  With the
+           optional visit kernel (mgcfd_options.visit) one launch covers the three stages and is reported the same way.
   roofline_other = the same for the multigrid transfers on level 0/1 (prolong: 8*E_I + 148*N_f + 64*N_c; restrict: 44*N_f + 40*N_c)
   sustained = ms per step and SM clock over a >= 2 s back-to-back replay of the same cycle (the headline region is short enough to
            run at burst clocks)

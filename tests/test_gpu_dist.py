@@ -24,6 +24,8 @@ def test_distributed_matches_single_gpu(nranks, plane):
         env["MGCFD_VISIT"] = "1"
     if plane == "nccl":
         env["MGCFD_NO_P2P"] = "1"
+    if plane == "p2p-stage":
+        env["MGCFD_GUARD"] = "1"          # the default plane also with guard zones around every device array of every rank
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nranks}", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "dist_check PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

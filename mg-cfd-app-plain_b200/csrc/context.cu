@@ -813,9 +813,10 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     // the visit's minimum dt: already all-reduced by the transfer kernel that produced this state (multi-GPU), or reduced by every
     // CTA of the first stage from the per-block minima that kernel left behind (one GPU), or -- the state came from elsewhere --
     // by k_min_dt (+ all-reduce)
-    bool use_premin = false, recv_min = false;
+    bool use_premin = false, recv_min = false, use_word = false;
     if (!legacy) {
         if (c->dist.active) { if (deliver && v.minword_state == 1) recv_min = true; else CKRC(min_dt_fused(c, l)); }
+        else if (v.minword_state == 1 && v.pipe) use_word = true;  // one GPU, MGCFD_MINWORD=1: the transfer kernel folded the minimum into one word
         else if (v.premin_valid && v.pipe) use_premin = true;      // (the simple one-CTA-per-tile kernel reads *min_bits only)
         else CKRC(min_dt_fused(c, l));
     } else if (!deliver) CKRC(min_dt_fused(c, l));
@@ -841,6 +842,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
             a.rms_partial = (l == 0) ? v.rms_partial : nullptr;
         }
         if (j == 0 && use_premin) { a.premin = v.blockmins; a.npremin = (int)blocks_for(v.ncomp, 128); }
+        if (use_word) { a.minword = v.d_minword; a.min_from_word = (j == 0); a.reset_word = (j == 1); }
         if (deliver) {
             const int ib = (a.vout == v.buf[0]) ? 0 : (a.vout == v.buf[1] ? 1 : 2);
             a.d = dist_tail(c, v, ib, v.d_peers, v.npeers);
@@ -858,7 +860,7 @@ int smooth_fused(mgcfd_ctx* c, int l) {
     visit_tm.reset();
     v.i_old = X; v.i_var = A; v.i_tmp = B;
     v.premin_valid = false;
-    if (recv_min) v.minword_state = 0; else if (v.minword_state == 1) v.minword_state = 2;
+    if (recv_min || use_word) v.minword_state = 0; else if (v.minword_state == 1) v.minword_state = 2;
     if (l == 0) { v.rms_parts = v.ntiles; CKRC(rms_final(c, v, true)); }
     return MGCFD_OK;
 }
@@ -878,6 +880,12 @@ inline int release_early(mgcfd_ctx* c, unsigned nb) {
     static const int on = env_int("MGCFD_EARLY_RELEASE", 1), per_sm = env_int("MGCFD_EARLY_RELEASE_BLOCKS", 12);
     return (on && !c->opt.no_pdl && nb <= (unsigned)per_sm * (unsigned)c->num_sms) ? 1 : 0;
 }
+
+// one GPU: the minimum dt the transfer kernels leave behind as ONE word per level (what the multi-GPU path does) instead of one
+// value per block that every CTA of the first stage kernel reduces again (2350 loads per CTA on C2's fine level: 8 % of the stage
+// kernels' stall samples, profiles/r02I_final_c2_stage_tn256_level0_stalls.txt).  Measured 0.3187 vs 0.3265 ms per C2 cycle
+// (profiles/r02U_minword_one_gpu.txt), bit-identical results; MGCFD_MINWORD=0 brings the per-block minima back.
+inline bool minword_one_gpu() { static const int on = env_int("MGCFD_MINWORD", 1); return on != 0; }
 
 int do_restrict(mgcfd_ctx* c, int lc) {
     Level& vc = c->L[lc]; Level& vf = c->L[lc - 1];
@@ -900,6 +908,8 @@ int do_restrict(mgcfd_ctx* c, int lc) {
     DistTail none;
     memset(&none, 0, sizeof(none));
     none.release_early = release_early(c, nb);
+    if (bm && vc.pipe && !vc.visit && minword_one_gpu()) { CKRC(minword_arm(c, vc, none)); bm = nullptr; }
+    else if (vc.minword_state == 1) vc.minword_state = 2;
     CKRC(launch_dependent(c, k_restrict<false>, nb, 128u, vf.V(vf.i_var), vc.V(vc.i_var), vc.ncomp, vc.child_off, vc.child_ids, vc.vol_root, bm, none));
     CKRC(post_launch(c));
     vc.premin_valid = (bm != nullptr);
@@ -929,6 +939,8 @@ int do_prolong(mgcfd_ctx* c, int lf) {
     DistTail none;
     memset(&none, 0, sizeof(none));
     none.release_early = release_early(c, nb);
+    if (bm && vf.pipe && !vf.visit && minword_one_gpu()) { CKRC(minword_arm(c, vf, none)); bm = nullptr; }
+    else if (vf.minword_state == 1) vf.minword_state = 2;
     CKRC(launch_dependent(c, k_prolong<false>, nb, 128u, vf.ncomp, vf.npad, vc.npad, vf.parent, vf.idist_own, vf.ent_off, vf.ent_src, vf.ent_w,
                           vc.res, vf.res, vf.V(vf.i_var), vf.vol_root, bm, none));
     CKRC(post_launch(c));

@@ -389,6 +389,8 @@ struct StageArgs {
     unsigned long long stage_seq;
     int mask;              // bit0 internal, bit1 boundary, bit2 wall
     const double* premin; int npremin;     // first stage: per-block minima of dt left by the transfer kernel that produced vin (or nullptr: *min_bits holds the minimum)
+    unsigned long long* minword;           // one GPU, MGCFD_MINWORD=1: the level's minimum dt as ONE word (atomicMin of the transfer kernel's block minima)
+    int min_from_word, reset_word;         //   first stage: the minimum is *minword; second stage: block 0 puts the word back to +inf
     DistTail d;            // DIST instantiation of k_stage_pipe: rows are delivered by the kernel itself
 };
 
@@ -734,8 +736,10 @@ k_stage_pipe(const StageArgs a) {
     // produced this state), or the per-block minima that transfer kernel left behind, reduced here by every CTA for itself
     double min_dt = 0.0;
     const bool recv_min_late = DIST && first_stage && !a.legacy && a.d.recv_min;      // picked up before the first update, behind the first edge rounds
+    if (!DIST && a.reset_word && blockIdx.x == 0 && t == 0) *a.minword = 0x7F7F7F7F7F7F7F7FULL;      // consumed by the first stage (complete: we are past griddepcontrol.wait)
     if (first_stage && !a.legacy && !recv_min_late) {
-        if (a.premin) {
+        if (!DIST && a.min_from_word) min_dt = __longlong_as_double((long long)*(volatile const unsigned long long*)a.minword);
+        else if (a.premin) {
             double v = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);
             for (int b = t; b < a.npremin; b += TN) v = fmin(v, __ldcg(a.premin + b));
 #pragma unroll
@@ -1018,7 +1022,7 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
     if (DIST) dist_kernel_begin(d, !d.blk_wait || d.blk_wait[blockIdx.x] != 0);      // only blocks with ghost children wait for the fine level's owners
     const long c = blockIdx.x * (long)blockDim.x + threadIdx.x;
     double s_new = 0.0;          // |v| + c of the node's state after this kernel
-    const bool want_min = blockmins || (DIST && d.minword);
+    const bool want_min = blockmins || d.minword;
     const double vroot = (want_min && c < ncoarse) ? vol_root[c] : 0.0;      // requested first: in flight behind the gather chain
     if (c < ncoarse) {
         const long k0 = child_off[c], k1 = child_off[c + 1];
@@ -1043,7 +1047,7 @@ __global__ void k_restrict(const double* __restrict__ vf, double* __restrict__ v
         }
     }
     if (blockmins) block_min_store(c < ncoarse ? 0.5 * (vroot / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), blockmins);
-    if (DIST && d.minword) block_min_atomic(c < ncoarse ? 0.5 * (vroot / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), d.minword);
+    if (d.minword) block_min_atomic(c < ncoarse ? 0.5 * (vroot / s_new) : __longlong_as_double(0x7F7F7F7F7F7F7F7FLL), d.minword);
 }
 // prolong_residuals_interpolate_proper (mg_loops.cpp:678-864) as a gather over each fine node's incident internal
 // edges in original edge order: per edge the own-parent term then the neighbour-parent term (whose source is the own
@@ -1060,7 +1064,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
     const int p = (i < nfine) ? parent[i] : -1;
     double dt_new = __longlong_as_double(0x7F7F7F7F7F7F7F7FLL);      // padding rows (no parent) never win the minimum
     if (p >= 0) {
-        const bool want_min = blockmins || (DIST && d.minword);
+        const bool want_min = blockmins || d.minword;
         double rp[5];
 #pragma unroll
         for (int j = 0; j < 5; j++) rp[j] = res_c[j * scoarse + p];
@@ -1112,7 +1116,7 @@ __global__ void k_prolong(long nfine, long sfine, long scoarse, const int* __res
         if (DIST) dist_push_rec(d, i, n);
     }
     if (blockmins) block_min_store(dt_new, blockmins);
-    if (DIST && d.minword) block_min_atomic(dt_new, d.minword);
+    if (d.minword) block_min_atomic(dt_new, d.minword);
 }
 
 // ------------------------------------------------------------------------------------------------------
